@@ -1,0 +1,205 @@
+/*
+ * marlgrid_b200.h -- C ABI of the B200-native batched MarlGrid hot path.
+ *
+ * The reference (kandouss/marlgrid, pure Python) has NO FFI; its boundary for this path is the
+ * gym surface of MultiGridEnv (marlgrid/base.py:334-653).  This header is the boundary a
+ * maintainer would bind instead (ctypes stub: INTEGRATION.md).  Every entry point names the
+ * reference code it replaces.  All functions are `extern "C"`, take plain pointers and sizes,
+ * never throw, never allocate behind the caller's back (except the mg_engine_* family, which
+ * owns its device buffers by design), and return 0 on success or a CUDA error code (>0) /
+ * MG_E_* (<0).
+ *
+ * World state for B independent env instances is structure-of-arrays in device memory:
+ *
+ *   grid    uint8 [B][3][S]     three planes per env: object TYPE index, COLOUR index, STATE
+ *                               (marlgrid/objects.py:31-43 OBJECT_TYPES order, :11-29 COLORS order,
+ *                               WorldObj.encode objects.py:90-99).  Cell (x, y) of a plane lives at
+ *                               x*H + y, i.e. the reference's `MultiGrid.grid[i, j]` (base.py:91).
+ *                               S = plane_stride >= W*H, a multiple of 16 B (bulk-copy granularity).
+ *                               Agents are NOT stored in the planes; they are an overlay:
+ *   agents  uint8 [B][A][16]    per-agent record (GridAgentInterface state, marlgrid/agents.py:155-170):
+ *                                 +0 x  +1 y  +2 dir  +3 flags(MG_AF_*)  +4 carry_type  +5 carry_colour
+ *                                 +6 carry_state  +7 bonus_state (0xFF = None)  +8 int32 stamp (arrival
+ *                                 order inside the episode: queue position of stacked agents,
+ *                                 base.py:547-572)  +12 reserved
+ *   envrec  int32 [B][4]        +0 step_count (base.py:414,512)  +1 episode (resets so far)
+ *                               +2 lifetime step() calls  +3 lo16 = next stamp, hi16 = MG_ERR_* bits
+ *
+ * Randomness is a counter-based Philox4x32-10 stream keyed by (seed, global env index); the exact
+ * draw schedule is stated in oracle/philox.py and DESIGN.md.  It replaces `self.np_random`
+ * (base.py:373) at its two call sites, base.py:516 (per-step agent order) and :699 (placement).
+ */
+#ifndef MARLGRID_B200_H
+#define MARLGRID_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MG_MAX_AGENTS 8
+#define MG_MAX_VIEW 8
+#define MG_AGENT_REC 16
+#define MG_ENV_REC 16
+
+/* object type indices: position in OBJECT_TYPES (marlgrid/objects.py:31-43; agents.py:9) */
+enum {
+  MG_T_EMPTY = 0, MG_T_GRIDAGENT = 1, MG_T_BULK = 2, MG_T_BONUS = 3, MG_T_GOAL = 4, MG_T_FLOOR = 5,
+  MG_T_EMPTYSPACE = 6, MG_T_LAVA = 7, MG_T_WALL = 8, MG_T_KEY = 9, MG_T_BALL = 10, MG_T_DOOR = 11,
+  MG_T_BOX = 12, MG_T_AGENT = 13, MG_N_TYPES = 14
+};
+/* colour indices: key order of COLORS (marlgrid/objects.py:11-29) */
+enum {
+  MG_C_RED = 0, MG_C_ORANGE = 1, MG_C_GREEN = 2, MG_C_BLUE = 3, MG_C_CYAN = 4, MG_C_PURPLE = 5,
+  MG_C_YELLOW = 6, MG_C_OLIVE = 7, MG_C_GREY = 8, MG_C_WORST = 9, MG_C_PINK = 10, MG_C_WHITE = 11,
+  MG_C_PRESTIGE = 12, MG_C_SHADOW = 13
+};
+/* Door.states (marlgrid/objects.py:325) */
+enum { MG_DOOR_OPEN = 1, MG_DOOR_CLOSED = 2, MG_DOOR_LOCKED = 3 };
+/* GridAgentInterface.actions (marlgrid/agents.py:10-17) */
+enum { MG_A_LEFT = 0, MG_A_RIGHT = 1, MG_A_FORWARD = 2, MG_A_PICKUP = 3, MG_A_DROP = 4, MG_A_TOGGLE = 5, MG_A_DONE = 6 };
+
+/* agent flags (record byte +3) */
+#define MG_AF_PLACED 1u  /* pos is not None: the agent is somewhere in the grid */
+#define MG_AF_ACTIVE 2u  /* GridAgentInterface.active (agents.py:155-159) */
+#define MG_AF_DONE 4u    /* GridAgentInterface.done (base.py:584-585) */
+
+/* MgConfig.flags */
+#define MG_F_GHOST 1u           /* ghost_mode (base.py:345,541-542,683-684) */
+#define MG_F_RESPAWN 2u         /* respawn (base.py:344,629-644) */
+#define MG_F_REWARD_DECAY 4u    /* reward_decay (base.py:342,578-579) */
+#define MG_F_SEE_THROUGH 8u     /* see_through_walls (agents.py:292-295) */
+#define MG_F_BONUS_INITIAL 16u  /* BonusTile.initial_reward (objects.py:203) */
+#define MG_F_BONUS_RESET 32u    /* BonusTile.reset_on_mistake (objects.py:200) */
+
+/* goal_mode */
+enum { MG_GOAL_NONE = 0, MG_GOAL_FIXED = 1, MG_GOAL_RANDOM = 2 };
+
+/* error bits accumulated in envrec word 3 (hi16): what the reference would have raised */
+#define MG_ERR_BAD_ACTION 1u  /* ValueError("Environment can't handle action") base.py:619-620 */
+#define MG_ERR_PLACEMENT 2u   /* RecursionError("Rejection sampling failed") base.py:706 */
+#define MG_ERR_STACK 4u       /* AssertionError / ValueError("?!?!?!") base.py:558,568-569 */
+#define MG_ERR_TOGGLE 8u      /* TypeError from Box.toggle(self) objects.py:381 */
+#define MG_ERR_RENDER 16u     /* object whose render() raises in the reference (objects.py:274-277,309-321,370) */
+
+/* negative return codes */
+#define MG_E_CONFIG (-1)
+#define MG_E_ARG (-2)
+
+/* Static description of one env family: MultiGridEnv ctor kwargs (base.py:335-347), the scenario
+ * generator (envs/empty.py:9-16, envs/cluttered.py:9-36, envs/goalcycle.py:9-51) and the agent
+ * interface geometry (agents.py:19-35).  POD, passed by pointer, copied by the callee. */
+typedef struct MgConfig {
+  int32_t width, height;     /* grid_size | width/height (base.py:349-358) */
+  int32_t n_agents;          /* len(agents) <= MG_MAX_AGENTS */
+  int32_t view_size;         /* GridAgentInterface.view_size (agents.py:21), 3..MG_MAX_VIEW */
+  int32_t view_offset;       /* agents.py:23 */
+  int32_t view_tile_size;    /* agents.py:22; RGB path only */
+  int32_t max_steps;         /* base.py:341 */
+  int32_t n_clutter;         /* cluttered.py:15-18 (already resolved from clutter_density) */
+  int32_t n_bonus_tiles;     /* goalcycle.py:9 */
+  int32_t goal_mode;         /* MG_GOAL_* : empty.py:12 / cluttered.py:28-31 */
+  uint32_t flags;            /* MG_F_* */
+  int32_t plane_stride;      /* S, bytes per plane per env, multiple of 16, >= width*height */
+  double goal_reward;        /* Goal(reward=1) empty.py:12, cluttered.py:29,31 */
+  double bonus_reward;       /* goalcycle.py:9 reward */
+  double bonus_penalty;      /* goalcycle.py:9 penalty */
+  uint8_t agent_color[MG_MAX_AGENTS];  /* colour index per agent (envs/__init__.py:31) */
+  int32_t spawn_delay[MG_MAX_AGENTS];  /* agents.py:34 */
+  uint8_t n_static_kinds;    /* RGB: number of distinct static tile kinds in the atlas (excl. empty) */
+  uint8_t kind_of_type[15];  /* RGB: type index -> atlas kind (0 = none/empty, 0xFF = undefined render) */
+} MgConfig;
+
+/* Device pointers of the SoA world state (caller-owned, e.g. torch tensors). */
+typedef struct MgState {
+  uint8_t* grid;    /* [B][3][S] */
+  uint8_t* agents;  /* [B][A][16] */
+  int32_t* envrec;  /* [B][4] */
+  int64_t n_envs;   /* B (envs on THIS device) */
+  int64_t env_offset; /* global index of local env 0 (RNG is keyed by the global index) */
+  uint64_t seed;
+} MgState;
+
+typedef void* mg_stream_t; /* cudaStream_t */
+
+/* ---- library / build info ------------------------------------------------------------------ */
+int mg_version(void);                 /* ABI version */
+const char* mg_build_info(void);      /* "sm_100a ..." */
+int mg_config_validate(const MgConfig* cfg);
+int64_t mg_obs_bytes_per_env(const MgConfig* cfg, int rgb);
+
+/* ---- device-pointer API (all pointers are DEVICE pointers; async on `stream`) -------------- */
+
+/* Zero-initialise state as a freshly constructed env family (all agents unplaced, dir 0,
+ * episode 0).  Replaces MultiGridEnv.__init__ state setup (base.py:353-367, agents.py:90). */
+int mg_init(const MgConfig* cfg, const MgState* st, mg_stream_t stream);
+
+/* Start a new episode in every env (reset_mask == NULL) or in envs whose mask byte != 0.
+ * Replaces MultiGridEnv.reset (base.py:402-416) + _gen_grid (empty.py:9-16, cluttered.py:25-36,
+ * goalcycle.py:30-51) + place_obj/try_place_obj (base.py:664-708). */
+int mg_reset(const MgConfig* cfg, const MgState* st, const uint8_t* reset_mask, mg_stream_t stream);
+
+/* One env.step() for every env: MultiGridEnv.step (base.py:501-649) without the obs
+ * (actions int32 [B][A]; rewards float64 [B][A]; done uint8 [B]).  autoreset != 0 starts a new
+ * episode inside the kernel for envs that finished (the reference has no such mode; it is
+ * `obs,r,d,_ = env.step(a); if d: obs = env.reset()` of the caller loop). */
+int mg_step(const MgConfig* cfg, const MgState* st, const int32_t* actions, double* rewards,
+            uint8_t* done, int autoreset, mg_stream_t stream);
+
+/* Encoded egocentric observation uint8 [B][A][V][V][3]:
+ * gen_obs_grid (base.py:418-451) + occlude_mask (agents.py:298-343) + MultiGrid.encode (base.py:196-214). */
+int mg_obs_encode(const MgConfig* cfg, const MgState* st, uint8_t* obs, mg_stream_t stream);
+
+/* RGB egocentric observation uint8 [B][A][V*ts][V*ts][3]:
+ * gen_agent_obs (base.py:453-460) + MultiGrid.render/render_tile (base.py:275-331).
+ * atlas: uint8 [n_tiles][4][ts][ts][3], n_tiles = (n_static_kinds+1)*(1+4A). */
+int mg_obs_rgb(const MgConfig* cfg, const MgState* st, const uint8_t* atlas, uint8_t* obs, mg_stream_t stream);
+
+/* step + autoreset + encoded obs in ONE launch (the benchmarked hot path). */
+int mg_step_fused(const MgConfig* cfg, const MgState* st, const int32_t* actions, double* rewards,
+                  uint8_t* done, uint8_t* obs, int autoreset, mg_stream_t stream);
+
+/* step + autoreset + RGB obs in one launch. */
+int mg_step_fused_rgb(const MgConfig* cfg, const MgState* st, const int32_t* actions, double* rewards,
+                      uint8_t* done, const uint8_t* atlas, uint8_t* obs, int autoreset, mg_stream_t stream);
+
+/* n_steps fused steps back to back; actions int32 [n_steps][B][A]; rewards/done/obs hold the LAST
+ * step's outputs.  Rollout driver for benchmarking (launch overhead amortised by the C loop). */
+int mg_rollout_fused(const MgConfig* cfg, const MgState* st, const int32_t* actions, int64_t n_steps,
+                     double* rewards, uint8_t* done, uint8_t* obs, int autoreset, mg_stream_t stream);
+
+/* Uniform random actions in {0..n_actions-1}, Philox stream keyed (seed, call counter):
+ * the synthetic policy of the benchmark. */
+int mg_random_actions(int32_t* actions, int64_t n, int n_actions, uint64_t seed, uint64_t counter,
+                      mg_stream_t stream);
+
+/* Line-of-sight known-answer entry: n independent VxV transparency grids (uint8, [n][V][V],
+ * index [i][j] like the reference) -> visibility masks (same layout).  Replaces occlude_mask
+ * (agents.py:298-343) for one agent position (ax, ay). */
+int mg_los_batch(const uint8_t* transparent, uint8_t* mask, int64_t n, int view_size, int ax, int ay,
+                 mg_stream_t stream);
+
+/* ---- host-buffer engine API (owns device memory; HOST pointers; synchronous) ---------------- */
+typedef struct MgEngine MgEngine;
+
+/* Allocates device state for n_envs on CUDA device `device`.  rgb != 0 selects the RGB path
+ * (atlas_host: host pointer to the atlas, copied once). */
+int mg_engine_create(MgEngine** out, const MgConfig* cfg, int64_t n_envs, int64_t env_offset, uint64_t seed,
+                     int device, int rgb, const uint8_t* atlas_host, int64_t atlas_bytes);
+void mg_engine_destroy(MgEngine* e);
+/* env.reset(): obs_host (pageable or pinned) receives the first observations. */
+int mg_engine_reset(MgEngine* e, uint8_t* obs_host);
+/* env.step(actions): H2D actions, fused step kernel, D2H obs/rewards/done; returns after the copies. */
+int mg_engine_step(MgEngine* e, const int32_t* actions_host, uint8_t* obs_host, double* rewards_host,
+                   uint8_t* done_host, int autoreset);
+/* Pinned host allocation helpers so callers without a CUDA runtime can get page-locked buffers. */
+void* mg_host_alloc(int64_t bytes);
+void mg_host_free(void* p);
+/* Counters: kernels launched by this library since load (bench.py's gpu_launches). */
+int64_t mg_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MARLGRID_B200_H */
