@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/s of the batched MarlGrid hot path (BASELINE.json metric).
+
+  python bench.py --gpus 1 --steps K --warmup W                 # this repo's CUDA path
+  torchrun --nproc-per-node N ... bench.py --gpus N ...         # N ranks, one per GPU, env-index sharded
+  python bench.py --impl reference ...                          # CPU arm: the oracle port on the host cores
+
+A "step" is one env.step() of the whole batch: MarlGrid-3AgentCluttered15x15-v0, 65 536 envs per GPU,
+encoded observations, uniform random actions, auto-reset (BASELINE.json configs[2]; 8 GPUs = the
+sharded family of configs[4]).  One JSON line is printed by rank 0.
+
+Timing: W warm-up steps, then K steps each bracketed by CUDA events on the launching stream; a
+256 MiB write flushes L2 before every timed step (the 52 MB world state would otherwise stay
+L2-resident), so `value` = B*K / sum of cold per-step device times, max over ranks.  `warm` repeats
+the K steps back to back without flushing (what a rollout loop sees).  `e2e` drives the C-ABI host
+buffer engine (mg_engine_step): pinned host actions in, obs/rewards/done out, copies inside the timer.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+ENV_ID = "MarlGrid-3AgentCluttered15x15-v0"
+ALGO_BYTES_PER_ENV_STEP = 1272  # 743 read + 522 write + 7 amortised reset
+FALLBACK_HBM_GBS = 6650.0       # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:  # noqa: BLE001
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_port_throughput(n_envs, n_steps, threads, seed=1337):
+    """The oracle (CPU port of the reference algorithm) on a bounded sample of the same workload."""
+    import numpy as np
+
+    from marlgrid_b200 import envs  # config only; constructing an env would need the GPU
+    from marlgrid_b200.config import GOAL_FIXED, make_config
+    from oracle import mg_oracle
+
+    del envs
+    cfg = make_config(15, 15, ["red", "blue", "purple"], view_size=7, view_tile_size=8, n_clutter=int(0.15 * 13 * 13), goal_mode=GOAL_FIXED)
+    ob = mg_oracle.OracleBatch(cfg, n_envs, seed=seed, threads=threads)
+    ob.reset()
+    rng = np.random.RandomState(0)
+    act = rng.randint(0, 7, size=(n_steps, n_envs, 3)).astype(np.int32)
+    ob.rollout(act[:2])  # warm-up
+    t0 = time.perf_counter()
+    ob.rollout(act)
+    dt = time.perf_counter() - t0
+    return n_envs * n_steps / dt, dt
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:  # noqa: BLE001
+        return os.cpu_count() or 1
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference algorithm's CPU implementation (oracle port), all host threads."""
+    if rank != 0:
+        return
+    threads = host_threads()
+    n_envs = 8192
+    n_steps_per = 100  # one bench "step" of this arm = one env.step over the 8 192-env sample
+    vals = []
+    for _ in range(max(1, args.warmup // 100)):
+        cpu_port_throughput(n_envs, 10, threads)
+    reps = max(1, min(5, args.steps // 100))
+    for _ in range(reps):
+        v, dt = cpu_port_throughput(n_envs, n_steps_per, threads)
+        vals.append(v)
+    vals.sort()
+    v = vals[len(vals) // 2]
+    sample = f"{n_envs} envs x {n_steps_per} steps x {reps} reps (median), C port of the reference step+reset+encode, {threads} threads"
+    line = {
+        "impl": "reference", "metric": "env-steps/s", "value": v, "unit": "env-steps/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * n_envs / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8", "data": "synthetic", "config": workload_config(args, world),
+        "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "agent_steps_per_s": 3 * v,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return {
+        "workload": f"{ENV_ID} batch={args.batch_per_gpu}/GPU x {world} GPU(s), encoded obs [B,3,7,7,3] u8, uniform random actions, auto-reset "
+                    f"(BASELINE.json configs[2]{'; sharded family of configs[4]' if world > 1 else ''})",
+        "env_id": ENV_ID, "batch_per_gpu": args.batch_per_gpu, "global_batch": args.batch_per_gpu * world, "n_agents": 3,
+        "parallelism": f"env-index sharding x{world}, no collective on the data path",
+        "l2": "flushed before every timed step (256 MiB write); per-step CUDA events summed",
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=200)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch-per-gpu", type=int, default=65536)
+    ap.add_argument("--e2e-steps", type=int, default=100)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+
+    from marlgrid_b200 import _lib, envs
+
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist = dist_mod
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    B, K, W = args.batch_per_gpu, args.steps, args.warmup
+    L = _lib.load()
+
+    env = envs.make(ENV_ID, num_envs=B, obs_mode="encoded", seed=1337, env_offset=rank * B, device=dev)
+    A = env.num_agents
+    env.reset()
+    POOL = 128
+    actions = torch.empty((POOL, B, A), dtype=torch.int32, device=dev)
+    for t in range(POOL):
+        env.random_actions(t, seed=rank, out=actions[t])
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up -------------------------------------------------------------------------------
+    for t in range(W):
+        env.step(actions[t % POOL])
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    # ---- timed: K cold steps (L2 flushed before each), per-step events ---------------------------
+    launches0 = L.mg_launch_count()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    barrier()
+    wall0 = time.perf_counter()
+    for t in range(K):
+        flush.fill_(t & 0xFF)
+        starts[t].record()
+        env.step(actions[(W + t) % POOL])
+        stops[t].record()
+    barrier()
+    wall_cold = time.perf_counter() - wall0
+    launches = L.mg_launch_count() - launches0
+    cold_ms = [s.elapsed_time(e) for s, e in zip(starts, stops)]
+    cold_total_ms = float(sum(cold_ms))
+
+    # ---- timed: K warm steps back to back (one event pair), launched from the C rollout loop ----
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    done_steps = 0
+    while done_steps < K:
+        n = min(POOL, K - done_steps)
+        env.rollout(actions[:n])
+        done_steps += n
+    e1.record()
+    barrier()
+    warm_total_ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- e2e: host buffers through the C ABI engine ----------------------------------------------
+    import ctypes
+
+    h = ctypes.c_void_p()
+    _lib.check(L.mg_engine_create(ctypes.byref(h), ctypes.byref(env.cfg), B, rank * B, 1337, local_rank, 0, None, 0), "mg_engine_create")
+    obs_bytes, rew_bytes, act_bytes = B * A * 147, B * A * 8, B * A * 4
+    p_obs, p_rew, p_done, p_act = L.mg_host_alloc(obs_bytes), L.mg_host_alloc(rew_bytes), L.mg_host_alloc(B), L.mg_host_alloc(act_bytes)
+    act_np = np.ctypeslib.as_array(ctypes.cast(p_act, ctypes.POINTER(ctypes.c_int32)), shape=(B * A,))
+    host_actions = np.random.RandomState(rank).randint(0, 7, size=(8, B * A)).astype(np.int32)
+    _lib.check(L.mg_engine_reset(h, p_obs), "mg_engine_reset")
+    for t in range(5):
+        act_np[:] = host_actions[t % 8]
+        _lib.check(L.mg_engine_step(h, p_act, p_obs, p_rew, p_done, 1), "mg_engine_step")
+    barrier()
+    t0 = time.perf_counter()
+    KE = args.e2e_steps
+    for t in range(KE):
+        act_np[:] = host_actions[t % 8]  # a fresh action batch lands in the pinned buffer every step
+        _lib.check(L.mg_engine_step(h, p_act, p_obs, p_rew, p_done, 1), "mg_engine_step")
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    obs_last = np.ctypeslib.as_array(ctypes.cast(p_obs, ctypes.POINTER(ctypes.c_uint8)), shape=(obs_bytes,))
+    e2e_checksum = int(obs_last[:: 4099].astype(np.int64).sum())
+    L.mg_engine_destroy(h)
+
+    # ---- max over ranks --------------------------------------------------------------------------
+    times = torch.tensor([cold_total_ms, warm_total_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    cold_total_ms, warm_total_ms, e2e_ms = (float(x) for x in times.tolist())
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        value = world * B * K / (cold_total_ms * 1e-3)
+        warm_value = world * B * K / (warm_total_ms * 1e-3)
+        e2e_value = world * B * KE / (e2e_ms * 1e-3)
+        srt = sorted(cold_ms)
+        avg_launch_s = (sum(cold_ms) / K) * 1e-3
+        achieved = ALGO_BYTES_PER_ENV_STEP * B / avg_launch_s / 1e9
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                traffic = json.load(f).get("mg_step_fused_dram_bytes_per_launch")
+        except Exception:  # noqa: BLE001
+            pass
+        cpu = None
+        if not args.no_cpu_baseline and world >= 1:
+            thr = host_threads()
+            v, dt = cpu_port_throughput(8192, 200, thr)
+            cpu = {"value": v, "unit": "env-steps/s", "cores": thr, "kind": "port",
+                   "sample": f"8192 envs x 200 steps of the same workload ({dt:.1f} s), C port of the reference step+reset+encode (oracle/mg_oracle.c)"}
+        line = {
+            "metric": "env-steps/s", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": cold_total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+            "data": "synthetic", "config": workload_config(args, world),
+            "agent_steps_per_s": value * A,
+            "step_ms": {"min": srt[0], "median": srt[len(srt) // 2], "p99": srt[min(len(srt) - 1, int(0.99 * len(srt)))], "max": srt[-1]},
+            "warm": {"value": warm_value, "ms_per_step": warm_total_ms / K, "note": "K steps back to back, state L2-resident, launched from mg_rollout_fused"},
+            "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": act_bytes, "d2h_bytes_per_step": obs_bytes + rew_bytes + B,
+                    "steps": KE, "api": "mg_engine_step (C ABI, pinned host buffers, synchronous)", "checksum": e2e_checksum},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "kernel": "mg_kernel<1,1,7> (fused step+autoreset+encode)", "algorithmic_bytes_per_launch": ALGO_BYTES_PER_ENV_STEP * B,
+                         "peak_source": peak_src},
+            "cpu_baseline": cpu,
+            "clocks": clocks,
+            "wall_s": {"cold_loop": wall_cold},
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

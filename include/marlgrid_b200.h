@@ -126,6 +126,7 @@ typedef void* mg_stream_t; /* cudaStream_t */
 /* ---- library / build info ------------------------------------------------------------------ */
 int mg_version(void);                 /* ABI version */
 const char* mg_build_info(void);      /* "sm_100a ..." */
+int mg_sizeof_config(void);           /* sizeof(MgConfig) as compiled: binding self-check */
 int mg_config_validate(const MgConfig* cfg);
 int64_t mg_obs_bytes_per_env(const MgConfig* cfg, int rgb);
 

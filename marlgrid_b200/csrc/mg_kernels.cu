@@ -1,0 +1,984 @@
+// mg_kernels.cu -- batched MarlGrid hot path for B200 (sm_100a): step / reset / egocentric obs kernels.
+//
+// One CTA owns ENVS_PER_CTA = 32 consecutive env instances:
+//   * the envs' three grid planes (one contiguous 32*3*S byte chunk of HBM) are staged into shared
+//     memory by ONE bulk-async copy (cp.async.bulk + mbarrier: the TMA engine, SASS UBLKCP);
+//   * warp 0 runs the sequential part of MultiGridEnv.step (base.py:501-649) with lane == env:
+//     Philox agent order, per-agent action application, stacking stamps, float64 reward, done,
+//     in-kernel auto-reset (Philox rejection sampling, base.py:402-416,690-708);
+//   * then every thread is one agent-view (warp == agent index, lane == env): VxV rotated crop out
+//     of the staged planes, line-of-sight as carry-propagating row masks, sparse encode into a shared
+//     staging tile; the CTA finally streams the staging tile to HBM as 16-byte coalesced stores.
+//   * modified planes (reset / pickup / drop / toggle) go back with a shared->global bulk copy.
+// See DESIGN.md for the layout, the RNG contract and the roofline accounting.
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+
+#include "mg_device.cuh"
+
+namespace mg {
+
+constexpr int ENVS_PER_CTA = 32;
+constexpr uint32_t AF_HEAD = 0x80u;  // transient flag bit: agent is the head of its cell's queue
+
+struct KP {
+  int W, H, A, V, vo, ts, max_steps, n_clutter, n_bonus, goal_mode;
+  uint32_t flags;
+  int S;
+  double goal_reward, bonus_reward, bonus_penalty;
+  uint8_t agent_color[MG_MAX_AGENTS];
+  int spawn_delay[MG_MAX_AGENTS];
+  uint8_t kind_of_type[16];
+  uint8_t* grid;
+  uint8_t* agents;
+  int32_t* envrec;
+  long long B, env_offset;
+  unsigned long long seed;
+  const int32_t* actions;
+  double* rewards;
+  uint8_t* done;
+  uint8_t* obs;
+  const uint8_t* atlas;
+  const uint8_t* reset_mask;
+  int autoreset;
+  int n_tiles;       // atlas tiles (without the appended shadow tile)
+  int orient_slots;  // 1: atlas is rotation-equivariant (dir remap), 4: one slot per view orientation
+};
+
+// ---------------------------------------------------------------------------------------------
+// warp-0 (lane == env) state: agent records live transposed in shared memory, word w of agent a of
+// env `lane` at s_rec[(a*4+w)*32 + lane]  -> bank == lane, conflict-free under any per-lane a.
+//   w0 = x | y<<8 | dir<<16 | flags<<24     w1 = carry_type | carry_colour<<8 | carry_state<<16 | bonus<<24
+//   w2 = stamp                               w3 = reserved
+// ---------------------------------------------------------------------------------------------
+struct EnvCtx {
+  const KP& p;
+  uint32_t* rec;   // s_rec + lane
+  uint8_t* tp;     // this env's type plane in shared memory (colour at +S, state at +2S)
+  int sc, ep, tl;  // step_count, episode, lifetime steps
+  uint32_t w3;     // lo16 next stamp, hi16 error bits
+  bool dirty;      // planes modified -> write back
+  __device__ __forceinline__ uint32_t& R(int a, int w) { return rec[(a * 4 + w) * 32]; }
+  __device__ __forceinline__ void add_err(uint32_t bits) { w3 |= bits << 16; }
+  __device__ __forceinline__ uint32_t next_stamp() {
+    const uint32_t s = w3 & 0xFFFFu;
+    w3 = (w3 & 0xFFFF0000u) | ((s + 1u) & 0xFFFFu);
+    return s;
+  }
+};
+
+// placed agent with the smallest stamp on (x, y), -1 if none: the reference's cell object when it is
+// an agent, else `static_obj.agents[0]` (base.py:547-572)
+__device__ __forceinline__ int queue_head(EnvCtx& c, int x, int y) {
+  int best = -1;
+  uint32_t bs = 0;
+  const uint32_t key = (uint32_t)x | ((uint32_t)y << 8);
+  for (int a = 0; a < c.p.A; ++a) {
+    const uint32_t w0 = c.R(a, 0);
+    if (((w0 >> 24) & MG_AF_PLACED) && (w0 & 0xFFFFu) == key) {
+      const uint32_t s = c.R(a, 2);
+      if (best < 0 || s < bs) { best = a; bs = s; }
+    }
+  }
+  return best;
+}
+
+// base.py:664-688 try_place_obj (agent >= 0: that agent; else the static triple)
+__device__ __forceinline__ bool try_place(EnvCtx& c, int x, int y, int agent, int type, int colour, int state) {
+  const int idx = x * c.p.H + y;
+  const int st = c.tp[idx];
+  const bool occupied = queue_head(c, x, y) >= 0;
+  bool ok;
+  if (st == MG_T_EMPTY && !occupied) ok = true;                                          // grid_obj is None
+  else if (agent < 0) ok = false;                                                        // base.py:678-679
+  else if (st != MG_T_EMPTY && !can_overlap_static(st, c.tp[2 * c.p.S + idx])) ok = false;
+  else ok = (c.p.flags & MG_F_GHOST) || !occupied;                                       // base.py:683-684
+  if (!ok) return false;
+  if (agent >= 0) {
+    const uint32_t w0 = c.R(agent, 0);
+    c.R(agent, 0) = (w0 & 0xFFFF0000u) | (uint32_t)x | ((uint32_t)y << 8) | ((uint32_t)MG_AF_PLACED << 24);
+    c.R(agent, 2) = c.next_stamp();
+  } else {
+    c.tp[idx] = (uint8_t)type; c.tp[c.p.S + idx] = (uint8_t)colour; c.tp[2 * c.p.S + idx] = (uint8_t)state;
+    c.dirty = true;
+  }
+  return true;
+}
+
+// base.py:690-708 place_obj(top=(0,0), size=None)
+__device__ __forceinline__ void place_obj(EnvCtx& c, Draws& d, int agent, int type, int colour, int state, int max_tries) {
+  for (int t = 0; t < max_tries; ++t) {
+    int x, y;
+    d.next(c.p.W, c.p.H, x, y);
+    if (try_place(c, x, y, agent, type, colour, state)) return;
+  }
+  c.add_err(MG_ERR_PLACEMENT);  // RecursionError base.py:706
+}
+
+__device__ __forceinline__ Draws make_draws(const KP& p, unsigned long long g, uint32_t c2, uint32_t tag) {
+  Draws d;
+  d.g_lo = (uint32_t)g; d.g_hi = (uint32_t)(g >> 32); d.c2 = c2; d.tag = tag;
+  d.k0 = (uint32_t)p.seed; d.k1 = (uint32_t)(p.seed >> 32); d.k = 0;
+  d.r = U4{0, 0, 0, 0};
+  return d;
+}
+
+// base.py:402-416 reset + _gen_grid (empty.py:9-16, cluttered.py:25-36, goalcycle.py:30-51)
+__device__ void env_reset(EnvCtx& c, unsigned long long g) {
+  const KP& p = c.p;
+  const int W = p.W, H = p.H;
+  for (int a = 0; a < p.A; ++a) {  // agents.py:161-170 (dir survives)
+    c.R(a, 0) = c.R(a, 0) & 0x00FF0000u;
+    c.R(a, 1) = 0xFF000000u;
+    c.R(a, 2) = 0;
+  }
+  uint32_t* w = reinterpret_cast<uint32_t*>(c.tp);
+  for (int i = 0; i < 3 * p.S / 4; ++i) w[i] = 0u;
+  c.w3 &= 0xFFFF0000u;
+  for (int i = 0; i < W; ++i) {  // wall_rect base.py:172-176
+    c.tp[i * H] = MG_T_WALL; c.tp[p.S + i * H] = MG_C_WORST;
+    c.tp[i * H + H - 1] = MG_T_WALL; c.tp[p.S + i * H + H - 1] = MG_C_WORST;
+  }
+  for (int j = 0; j < H; ++j) {
+    c.tp[j] = MG_T_WALL; c.tp[p.S + j] = MG_C_WORST;
+    c.tp[(W - 1) * H + j] = MG_T_WALL; c.tp[p.S + (W - 1) * H + j] = MG_C_WORST;
+  }
+  c.dirty = true;
+  Draws d = make_draws(p, g, (uint32_t)c.ep, TAG_RESET);
+  if (p.goal_mode == MG_GOAL_FIXED) {  // put_obj base.py:655-662
+    const int idx = (W - 2) * H + (H - 2);
+    c.tp[idx] = MG_T_GOAL; c.tp[p.S + idx] = MG_C_GREEN; c.tp[2 * p.S + idx] = 0;
+  } else if (p.goal_mode == MG_GOAL_RANDOM) {
+    place_obj(c, d, -1, MG_T_GOAL, MG_C_GREEN, 0, 100);  // cluttered.py:28-29
+  }
+  for (int b = 0; b < p.n_bonus; ++b) place_obj(c, d, -1, MG_T_BONUS, MG_C_YELLOW, b, 100);  // goalcycle.py:34-46
+  for (int k = 0; k < p.n_clutter; ++k) place_obj(c, d, -1, MG_T_WALL, MG_C_WORST, 0, 100);  // cluttered.py:32-33
+  for (int a = 0; a < p.A; ++a)                                                                // base.py:409-412
+    if (p.spawn_delay[a] == 0) {
+      place_obj(c, d, a, 0, 0, 0, 100000);
+      c.R(a, 0) |= (uint32_t)MG_AF_ACTIVE << 24;
+    }
+  c.sc = 0;
+  c.ep += 1;
+}
+
+// BonusTile.get_reward objects.py:180-206
+__device__ __forceinline__ double bonus_get_reward(EnvCtx& c, int a, int bonus_id) {
+  const KP& p = c.p;
+  const int n = p.n_bonus;
+  uint32_t w1 = c.R(a, 1);
+  int bs = (int)(w1 >> 24);
+  bool first = false;
+  const double pen = p.bonus_penalty < 0 ? p.bonus_penalty : -p.bonus_penalty;
+  double rew;
+  if (bs == 0xFF) { bs = ((bonus_id - 1) % n + n) % n; first = true; }
+  if (bs == bonus_id) rew = pen;
+  else if ((bs + 1) % n == bonus_id) { bs = bonus_id; rew = p.bonus_reward; }
+  else rew = pen;
+  if (p.flags & MG_F_BONUS_RESET) bs = bonus_id;
+  c.R(a, 1) = (w1 & 0x00FFFFFFu) | ((uint32_t)bs << 24);
+  if (first && !(p.flags & MG_F_BONUS_INITIAL)) return 0.0;
+  return rew;
+}
+
+// base.py:501-649 step without the obs; returns done
+__device__ bool env_step(EnvCtx& c, unsigned long long g, const int32_t* __restrict__ act, double* __restrict__ rew) {
+  const KP& p = c.p;
+  const int W = p.W, H = p.H, A = p.A, S = p.S;
+  const uint32_t t_life = (uint32_t)c.tl;
+  Draws d = make_draws(p, g, t_life, TAG_INSTEP);
+  for (int a = 0; a < A; ++a) {  // base.py:503-506
+    const uint32_t fl = c.R(a, 0) >> 24;
+    if (!(fl & MG_AF_ACTIVE) && !(fl & MG_AF_DONE) && c.sc >= p.spawn_delay[a]) {
+      place_obj(c, d, a, 0, 0, 0, 100000);
+      c.R(a, 0) |= (uint32_t)MG_AF_ACTIVE << 24;
+    }
+  }
+  c.sc += 1;  // base.py:512
+  // base.py:514-516: one Philox word -> index of the permutation (Lehmer / Fisher-Yates decode)
+  uint32_t fact = 1;
+  for (int i = 2; i <= A; ++i) fact *= (uint32_t)i;
+  const U4 r = philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), t_life, 0u, (uint32_t)p.seed, (uint32_t)(p.seed >> 32));
+  uint32_t pidx = __umulhi(r.x, fact);
+  uint32_t order = 0x76543210u;  // nibble i = order[i]
+  for (int i = A - 1; i >= 1; --i) {
+    const uint32_t j = pidx % (uint32_t)(i + 1);
+    pidx /= (uint32_t)(i + 1);
+    const uint32_t ni = (order >> (4 * i)) & 0xFu, nj = (order >> (4 * j)) & 0xFu;
+    order = (order & ~(0xFu << (4 * i)) & ~(0xFu << (4 * j))) | (nj << (4 * i)) | (ni << (4 * j));
+  }
+  c.tl += 1;
+  for (int q = 0; q < A; ++q) {
+    const int a = (int)((order >> (4 * q)) & 0xFu);
+    const int action = act[a];
+    double reward = 0.0;
+    uint32_t w0 = c.R(a, 0);
+    if ((w0 >> 24) & MG_AF_ACTIVE) {  // base.py:521
+      const int cx = (int)(w0 & 0xFFu), cy = (int)((w0 >> 8) & 0xFFu), dir = (int)((w0 >> 16) & 3u);
+      const int fx = cx + ((dir == 0) ? 1 : (dir == 2) ? -1 : 0);  // agents.py:183
+      const int fy = cy + ((dir == 1) ? 1 : (dir == 3) ? -1 : 0);
+      const bool inb = (unsigned)fx < (unsigned)W && (unsigned)fy < (unsigned)H;
+      const int fidx = inb ? fx * H + fy : 0;
+      const int ftype = inb ? (int)c.tp[fidx] : (int)MG_T_WALL;
+      const int fstate = inb ? (int)c.tp[2 * S + fidx] : 0;
+      if (!inb) c.add_err(MG_ERR_STACK);
+      if (action == MG_A_LEFT) {  // base.py:530-531
+        c.R(a, 0) = (w0 & 0xFF00FFFFu) | ((uint32_t)((dir + 3) & 3) << 16);
+      } else if (action == MG_A_RIGHT) {  // base.py:534-535
+        c.R(a, 0) = (w0 & 0xFF00FFFFu) | ((uint32_t)((dir + 1) & 3) << 16);
+      } else if (action == MG_A_FORWARD) {  // base.py:538-585
+        const bool f_is_agent = (ftype == MG_T_EMPTY) && (queue_head(c, fx, fy) >= 0);
+        bool can_move = (ftype == MG_T_EMPTY) || can_overlap_static(ftype, fstate);
+        if (!(p.flags & MG_F_GHOST) && f_is_agent) can_move = false;
+        if (can_move) {
+          const int cidx = cx * H + cy;
+          const int ctype = c.tp[cidx];
+          if (ctype != MG_T_EMPTY && !can_overlap_static(ctype, c.tp[2 * S + cidx])) c.add_err(MG_ERR_STACK);  // base.py:558
+          w0 = (w0 & 0xFFFF0000u) | (uint32_t)fx | ((uint32_t)fy << 8);
+          c.R(a, 2) = c.next_stamp();  // appended last to the target cell's queue (base.py:547-552)
+          if (ftype == MG_T_GOAL || ftype == MG_T_BONUS) {  // hasattr(fwd_cell, 'get_reward') base.py:576
+            double rwd = (ftype == MG_T_GOAL) ? p.goal_reward : bonus_get_reward(c, a, fstate);
+            if (p.flags & MG_F_REWARD_DECAY) {  // base.py:579, every operation rounded on its own
+              const double qd = __ddiv_rn((double)c.sc, (double)p.max_steps);
+              const double u = __dmul_rn(0.9, qd);
+              const double f = __dsub_rn(1.0, u);
+              rwd = __dmul_rn(rwd, f);
+            }
+            reward = rwd;
+          }
+          if (ftype == MG_T_LAVA || ftype == MG_T_GOAL) w0 |= (uint32_t)MG_AF_DONE << 24;  // base.py:584-585
+          c.R(a, 0) = w0;
+        }
+      } else if (action == MG_A_PICKUP) {  // base.py:590-597
+        const uint32_t w1 = c.R(a, 1);
+        if (ftype != MG_T_EMPTY && ((PICKUP_MASK >> ftype) & 1u) && (w1 & 0xFFu) == 0u) {
+          c.R(a, 1) = (w1 & 0xFF000000u) | (uint32_t)ftype | ((uint32_t)c.tp[S + fidx] << 8) | ((uint32_t)fstate << 16);
+          c.tp[fidx] = 0; c.tp[S + fidx] = 0; c.tp[2 * S + fidx] = 0;
+          c.dirty = true;
+        }
+      } else if (action == MG_A_DROP) {  // base.py:600-606
+        const uint32_t w1 = c.R(a, 1);
+        if (inb && ftype == MG_T_EMPTY && (w1 & 0xFFu) != 0u && queue_head(c, fx, fy) < 0) {
+          c.tp[fidx] = (uint8_t)(w1 & 0xFFu); c.tp[S + fidx] = (uint8_t)((w1 >> 8) & 0xFFu); c.tp[2 * S + fidx] = (uint8_t)((w1 >> 16) & 0xFFu);
+          c.R(a, 1) = w1 & 0xFF000000u;
+          c.dirty = true;
+        }
+      } else if (action == MG_A_TOGGLE) {  // base.py:609-613, Door.toggle objects.py:333-346
+        if (ftype == MG_T_DOOR) {
+          const uint32_t w1 = c.R(a, 1);
+          int ns = fstate;
+          if (fstate == MG_DOOR_LOCKED) {
+            if ((w1 & 0xFFu) == MG_T_KEY && ((w1 >> 8) & 0xFFu) == c.tp[S + fidx]) ns = MG_DOOR_CLOSED;
+          } else if (fstate == MG_DOOR_CLOSED) ns = MG_DOOR_OPEN;
+          else if (fstate == MG_DOOR_OPEN) ns = MG_DOOR_CLOSED;
+          if (ns != fstate) { c.tp[2 * S + fidx] = (uint8_t)ns; c.dirty = true; }
+        } else if (ftype == MG_T_BOX) c.add_err(MG_ERR_TOGGLE);  // Box.toggle(self) objects.py:381
+      } else if (action != MG_A_DONE) {
+        c.add_err(MG_ERR_BAD_ACTION);  // base.py:619-620
+      }
+    }
+    rew[a] = reward;
+  }
+  bool all_done = true;
+  for (int a = 0; a < A; ++a) {  // base.py:627-646
+    uint32_t w0 = c.R(a, 0);
+    if ((w0 >> 24) & MG_AF_DONE) {
+      if (p.flags & MG_F_RESPAWN) {
+        c.R(a, 0) = w0 & 0x00FF0000u;  // agent.reset(new_episode=False) agents.py:161-166
+        c.R(a, 1) = c.R(a, 1) & 0xFF000000u;
+        place_obj(c, d, a, 0, 0, 0, 100000);
+        c.R(a, 0) |= (uint32_t)MG_AF_ACTIVE << 24;
+        all_done = false;
+      } else {
+        c.R(a, 0) = w0 & ~((uint32_t)MG_AF_ACTIVE << 24);
+      }
+    } else all_done = false;
+  }
+  return (c.sc >= p.max_steps) || all_done;  // base.py:649
+}
+
+// mark queue heads (transient bit) for the obs phase
+__device__ __forceinline__ void mark_heads(EnvCtx& c) {
+  for (int a = 0; a < c.p.A; ++a) {
+    const uint32_t w0 = c.R(a, 0);
+    bool head = ((w0 >> 24) & MG_AF_PLACED) != 0;
+    if (head) {
+      const uint32_t s = c.R(a, 2);
+      for (int q = 0; q < c.p.A; ++q) {
+        const uint32_t v0 = c.R(q, 0);
+        if (q != a && ((v0 >> 24) & MG_AF_PLACED) && (v0 & 0xFFFFu) == (w0 & 0xFFFFu) && c.R(q, 2) < s) head = false;
+      }
+    }
+    c.R(a, 0) = head ? (w0 | (AF_HEAD << 24)) : (w0 & ~(AF_HEAD << 24));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// egocentric view of one agent (thread == view): gen_obs_grid (base.py:418-451)
+// ---------------------------------------------------------------------------------------------
+struct ViewGeom {
+  int ox, oy, sax, say, sbx, sby;  // world = (ox,oy) + a*(sax,say) + b*(sbx,sby)
+};
+
+// agents.py:237-266 get_view_exts + base.py:67-80 rotate_grid with rot_k = dir+1 (base.py:429-431)
+__device__ __forceinline__ ViewGeom view_geom(int px, int py, int dir, int V, int vo) {
+  const int h = V / 2;
+  ViewGeom g;
+  if (dir == 0) {        // topX = px - vo, topY = py - h;   view[a][b] = sub[V-1-b][a]
+    g.ox = px - vo + V - 1; g.oy = py - h; g.sax = 0; g.say = 1; g.sbx = -1; g.sby = 0;
+  } else if (dir == 1) { // topX = px - h, topY = py - vo;   view[a][b] = sub[V-1-a][V-1-b]
+    g.ox = px - h + V - 1; g.oy = py - vo + V - 1; g.sax = -1; g.say = 0; g.sbx = 0; g.sby = -1;
+  } else if (dir == 2) { // topX = px-V+1+vo, topY = py - h; view[a][b] = sub[b][V-1-a]
+    g.ox = px - V + 1 + vo; g.oy = py - h + V - 1; g.sax = 0; g.say = -1; g.sbx = 1; g.sby = 0;
+  } else {               // topX = px - h, topY = py-V+1+vo; view[a][b] = sub[a][b]
+    g.ox = px - h; g.oy = py - V + 1 + vo; g.sax = 1; g.say = 0; g.sbx = 0; g.sby = 1;
+  }
+  return g;
+}
+
+// Gathers the VxV crop of the type plane and returns the visibility / non-empty masks as V-bit rows
+// packed into 64 bits (bit b*V + a).  transparent: base.py:103-106 opacity; vis: agents.py:290-343.
+template <int V>
+__device__ __forceinline__ void view_masks(const KP& p, const uint8_t* __restrict__ tp, const ViewGeom& g, int vo,
+                                           unsigned long long& vis, unsigned long long& nonempty) {
+  const int W = p.W, H = p.H, S = p.S;
+  uint32_t T[V], NE[V];
+  // the coordinate driven by a (resp. b) is in range: one compare per row / column instead of per cell
+  uint32_t va = 0, vb = 0;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int ax = g.ox + i * g.sax, ay = g.oy + i * g.say;  // varies along a (other axis fixed)
+    const bool oka = g.sax != 0 ? ((unsigned)ax < (unsigned)W) : ((unsigned)ay < (unsigned)H);
+    const int bx = g.ox + i * g.sbx, by = g.oy + i * g.sby;
+    const bool okb = g.sbx != 0 ? ((unsigned)bx < (unsigned)W) : ((unsigned)by < (unsigned)H);
+    va |= (oka ? 1u : 0u) << i;
+    vb |= (okb ? 1u : 0u) << i;
+  }
+  const int da = g.sax * H + g.say, db = g.sbx * H + g.sby;
+  const int base = g.ox * H + g.oy;
+#pragma unroll
+  for (int b = 0; b < V; ++b) {
+    uint32_t t_row = (1u << V) - 1u, ne_row = 0;
+    if ((vb >> b) & 1u) {
+#pragma unroll
+      for (int a = 0; a < V; ++a) {
+        if ((va >> a) & 1u) {
+          const int idx = base + b * db + a * da;
+          const int t = tp[idx];
+          bool opaque = (t == MG_T_WALL);
+          if (t == MG_T_DOOR) opaque = tp[2 * S + idx] != MG_DOOR_OPEN;  // objects.py:330-331
+          if (opaque) t_row &= ~(1u << a);
+          if (t != MG_T_EMPTY) ne_row |= 1u << a;
+        }
+      }
+    }
+    T[b] = t_row; NE[b] = ne_row;
+  }
+  uint32_t M[V];
+  if (p.flags & MG_F_SEE_THROUGH) {  // agents.py:294-295
+#pragma unroll
+    for (int b = 0; b < V; ++b) M[b] = (1u << V) - 1u;
+  } else {
+    occlude_rows<V>(T, V / 2, V - 1 - vo, M);  // agents.py:233-234,293
+  }
+  vis = 0ull; nonempty = 0ull;
+#pragma unroll
+  for (int b = 0; b < V; ++b) {
+    vis |= (unsigned long long)M[b] << (b * V);
+    nonempty |= (unsigned long long)NE[b] << (b * V);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// the kernel
+//   STEP: 0 = observe only, 1 = env.step (+ auto-reset), 2 = env.reset (optionally masked)
+//   OBS : 0 = none, 1 = encoded (MultiGrid.encode base.py:196-214), 2 = RGB tiles (base.py:301-331)
+//   TS4 : RGB only: tile rows are whole 32-bit words (ts % 4 == 0) -> 16-byte store path
+// ---------------------------------------------------------------------------------------------
+template <int STEP, int OBS, int V, bool TS4>
+__global__ void __launch_bounds__(32 * MG_MAX_AGENTS) mg_kernel(const KP p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x;
+  const long long env0 = (long long)blockIdx.x * ENVS_PER_CTA;
+  const int n_valid = (int)min((long long)ENVS_PER_CTA, p.B - env0);
+  const int A = p.A, S = p.S;
+  constexpr int VV = V * V;
+
+  uint8_t* s_grid = smem;
+  uint32_t* s_rec = reinterpret_cast<uint32_t*>(s_grid + ENVS_PER_CTA * 3 * S);
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_rec + A * 4 * 32);
+  uint8_t* s_out = reinterpret_cast<uint8_t*>(s_bar + 2);  // 16-byte aligned: 32*3*S, 512*A and 16 are multiples of 16
+
+  if (tid == 0) mbar_init(s_bar, 1);
+  __syncthreads();
+  if (tid == 0) {
+    const uint32_t bytes = (uint32_t)n_valid * 3u * (uint32_t)S;
+    mbar_expect_tx(s_bar, bytes);
+    bulk_g2s(s_grid, p.grid + env0 * 3 * S, bytes, s_bar);
+  }
+
+  // ---- shared-memory output areas, prepared while the planes are in flight ----
+  // OBS 1: staging tile [32*A][V*V*3], zero filled (invisible / empty cells encode as 0)
+  // OBS 2: tile-id map [32*A][VV] + orientation [32*A] + atlas copy (+ one shadow tile)
+  const int tile_bytes = p.ts * p.ts * 3;
+  uint8_t* s_tile = s_out;
+  uint8_t* s_orient = s_tile + ENVS_PER_CTA * A * VV;
+  uint8_t* s_atlas = s_orient + ((ENVS_PER_CTA * A + 15) / 16) * 16;
+  if (OBS == 1) {
+    int4* z = reinterpret_cast<int4*>(s_out);
+    const int n16 = ENVS_PER_CTA * A * VV * 3 / 16;
+    for (int i = tid; i < n16; i += nthreads) z[i] = make_int4(0, 0, 0, 0);
+  } else if (OBS == 2) {
+    const int slots = p.n_tiles * p.orient_slots;
+    for (int i = tid; i < slots * tile_bytes; i += nthreads) {
+      const int slot = i / tile_bytes, off = i - slot * tile_bytes;
+      const int tile = slot / p.orient_slots, orient = slot - tile * p.orient_slots;
+      s_atlas[i] = p.atlas[(size_t)(tile * 4 + orient) * tile_bytes + off];
+    }
+    for (int i = tid; i < tile_bytes; i += nthreads) {  // COLORS['shadow'] objects.py:25, base.py:305
+      const int c = i % 3;
+      s_atlas[slots * tile_bytes + i] = (c == 0) ? 35 : (c == 1) ? 25 : 30;
+    }
+  }
+
+  // ---- warp 0: lane == env.  sequential game logic ----
+  if (warp == 0) {
+    const bool valid = lane < n_valid;
+    const long long env = env0 + lane;
+    EnvCtx c{p, s_rec + lane, s_grid + lane * 3 * S, 0, 0, 0, 0u, false};
+    if (valid) {
+      const int4* arec = reinterpret_cast<const int4*>(p.agents) + env * A;
+      for (int a = 0; a < A; ++a) {
+        const int4 r = arec[a];
+        c.R(a, 0) = (uint32_t)r.x; c.R(a, 1) = (uint32_t)r.y; c.R(a, 2) = (uint32_t)r.z; c.R(a, 3) = (uint32_t)r.w;
+      }
+      const int4 er = reinterpret_cast<const int4*>(p.envrec)[env];
+      c.sc = er.x; c.ep = er.y; c.tl = er.z; c.w3 = (uint32_t)er.w;
+    }
+    mbar_wait(s_bar, 0);
+    if (valid) {
+      const unsigned long long g = (unsigned long long)(p.env_offset + env);
+      if (STEP == 1) {
+        const bool dn = env_step(c, g, p.actions + env * A, p.rewards + env * A);
+        p.done[env] = dn ? 1 : 0;
+        if (dn && p.autoreset) env_reset(c, g);
+      } else if (STEP == 2) {
+        if (p.reset_mask == nullptr || p.reset_mask[env]) env_reset(c, g);
+      }
+      if (STEP != 0) {
+        int4* arec = reinterpret_cast<int4*>(p.agents) + env * A;
+        for (int a = 0; a < A; ++a)
+          arec[a] = make_int4((int)(c.R(a, 0) & ~(AF_HEAD << 24)), (int)c.R(a, 1), (int)c.R(a, 2), (int)c.R(a, 3));
+        reinterpret_cast<int4*>(p.envrec)[env] = make_int4(c.sc, c.ep, c.tl, (int)c.w3);
+        if (c.dirty) {  // planes changed (reset / pickup / drop / toggle): shared -> global bulk copy
+          fence_proxy_async_smem();
+          bulk_s2g(p.grid + env * 3 * S, c.tp, 3u * (uint32_t)S);
+          bulk_commit();
+        }
+      }
+      if (OBS != 0) mark_heads(c);
+    }
+  } else {
+    mbar_wait(s_bar, 0);
+  }
+  __syncthreads();
+
+  // ---- every thread: one agent view (warp == agent, lane == env) ----
+  if (OBS != 0 && warp < A && lane < n_valid) {
+    const int a = warp;
+    const uint32_t* rec = s_rec + lane;
+    const uint8_t* tp = s_grid + lane * 3 * S;
+    const uint32_t w0 = rec[(a * 4) * 32];
+    const int view = lane * A + a;
+    const bool active = ((w0 >> 24) & MG_AF_ACTIVE) != 0;  // base.py:420-425
+    const int px = (int)(w0 & 0xFFu), py = (int)((w0 >> 8) & 0xFFu), dir = (int)((w0 >> 16) & 3u);
+    const int orient = (3 - dir) & 3;  // view orientation (0 - rot_k) % 4, base.py:130
+    if (OBS == 2) {
+      s_orient[view] = (uint8_t)((p.orient_slots == 4) ? orient : 0);
+      if (!active) {
+        const uint8_t shadow = (uint8_t)(p.n_tiles);  // one past the last tile: resolved to the shadow slot below
+        for (int i = 0; i < VV; ++i) s_tile[view * VV + i] = shadow;
+      }
+    }
+    if (active) {
+      const ViewGeom g = view_geom(px, py, dir, V, p.vo);
+      unsigned long long vis, ne;
+      view_masks<V>(p, tp, g, p.vo, vis, ne);
+      const int H = p.H, W = p.W;
+      const int da = g.sax * H + g.say, db = g.sbx * H + g.sby, base = g.ox * H + g.oy;
+      if (OBS == 1) {
+        uint8_t* out = s_out + view * (VV * 3);
+        unsigned long long m = vis & ne;
+        while (m) {  // visible non-empty cells: WorldObj.encode objects.py:90-99
+          const int bit = __ffsll((long long)m) - 1;
+          m &= m - 1;
+          const int vb = bit / V, va = bit - vb * V;
+          const int idx = base + vb * db + va * da;
+          uint8_t* o = out + (va * V + vb) * 3;
+          o[0] = tp[idx]; o[1] = tp[S + idx]; o[2] = tp[2 * S + idx];
+        }
+        for (int q = 0; q < A; ++q) {  // agents that are their cell's object: (13, colour, dir)
+          const uint32_t v0 = rec[(q * 4) * 32];
+          if (!((v0 >> 24) & AF_HEAD)) continue;
+          const int qx = (int)(v0 & 0xFFu) - g.ox, qy = (int)((v0 >> 8) & 0xFFu) - g.oy;
+          const int va = qx * g.sax + qy * g.say, vb = qx * g.sbx + qy * g.sby;
+          if ((unsigned)va >= (unsigned)V || (unsigned)vb >= (unsigned)V) continue;
+          const int bit = vb * V + va;
+          if (!((vis >> bit) & 1ull) || ((ne >> bit) & 1ull)) continue;
+          uint8_t* o = out + (va * V + vb) * 3;
+          o[0] = MG_T_AGENT; o[1] = p.agent_color[q]; o[2] = (uint8_t)((v0 >> 16) & 3u);
+        }
+      } else {  // OBS == 2: tile ids, render_tile base.py:275-299
+        const int per_kind = 1 + 4 * A;
+        uint8_t* tl = s_tile + view * VV;
+        uint32_t bad = 0;
+        for (int bit = 0; bit < VV; ++bit) {
+          const int vb = bit / V, va = bit - vb * V;
+          uint8_t t = (uint8_t)p.n_tiles;  // shadow
+          if ((vis >> bit) & 1ull) {
+            t = 0;
+            if ((ne >> bit) & 1ull) {
+              const int kind = p.kind_of_type[tp[base + vb * db + va * da]];
+              if (kind == 0xFF) bad = 1; else t = (uint8_t)(kind * per_kind);
+            }
+          }
+          tl[vb * V + va] = t;
+        }
+        for (int q = 0; q < A; ++q) {
+          const uint32_t v0 = rec[(q * 4) * 32];
+          if (!((v0 >> 24) & AF_HEAD)) continue;
+          const int qx = (int)(v0 & 0xFFu) - g.ox, qy = (int)((v0 >> 8) & 0xFFu) - g.oy;
+          const int va = qx * g.sax + qy * g.say, vb = qx * g.sbx + qy * g.sby;
+          if ((unsigned)va >= (unsigned)V || (unsigned)vb >= (unsigned)V) continue;
+          if (!((vis >> (vb * V + va)) & 1ull)) continue;
+          // top_agent if it stands on this cell, else the queue head (base.py:282-293)
+          const bool mine = ((v0 ^ w0) & 0xFFFFu) == 0u;
+          const int qq = mine ? a : q;
+          const int qd = (int)(((mine ? w0 : v0) >> 16) & 3u);
+          const int slot_dir = (p.orient_slots == 4) ? qd : ((qd + orient) & 3);
+          tl[vb * V + va] = (uint8_t)(tl[vb * V + va] + 1 + 4 * qq + slot_dir);
+        }
+        if (bad) atomicOr(reinterpret_cast<unsigned int*>(p.envrec) + (env0 + lane) * 4 + 3, (unsigned int)MG_ERR_RENDER << 16);
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- stream the observation out ----
+  if (OBS == 1) {
+    const long long total = (long long)n_valid * A * VV * 3;
+    uint8_t* dst = p.obs + env0 * A * VV * 3;
+    const int n16 = (int)(total / 16);
+    const int4* src = reinterpret_cast<const int4*>(s_out);
+    for (int i = tid; i < n16; i += nthreads) st_stream_v4(reinterpret_cast<int4*>(dst) + i, src[i]);
+    for (int i = n16 * 16 + tid; i < total; i += nthreads) dst[i] = s_out[i];
+  } else if (OBS == 2) {
+    const int ts = p.ts, n_views = n_valid * A;
+    const int row_bytes = V * ts * 3;
+    const long long view_bytes = (long long)row_bytes * V * ts;
+    uint8_t* dst = p.obs + env0 * A * view_bytes;
+    if (TS4) {
+      const int wpt = ts * 3 / 4;         // words per tile row
+      const int wpr = V * wpt;            // words per image row
+      const int v16 = (int)(view_bytes / 16);
+      const uint32_t* atlas_w = reinterpret_cast<const uint32_t*>(s_atlas);
+      const int total16 = n_views * v16;
+      for (int i = tid; i < total16; i += nthreads) {
+        const int view = i / v16, k = i - view * v16;
+        const int os = s_orient[view];
+        const uint8_t* tl = s_tile + view * VV;
+        uint32_t wv[4];
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          const int gw = 4 * k + w;
+          const int y = gw / wpr, xw = gw - y * wpr;
+          const int va = xw / wpt, r = xw - va * wpt;
+          const int vb = y / ts, pyy = y - vb * ts;
+          const int t = tl[vb * V + va];
+          const int slot = (t >= p.n_tiles) ? p.n_tiles * p.orient_slots : t * p.orient_slots + os;
+          wv[w] = atlas_w[(slot * ts + pyy) * wpt + r];
+        }
+        st_stream_v4(reinterpret_cast<int4*>(dst) + i, make_int4((int)wv[0], (int)wv[1], (int)wv[2], (int)wv[3]));
+      }
+    } else {
+      const long long total = (long long)n_views * view_bytes;
+      for (long long i = tid; i < total; i += nthreads) {
+        const int view = (int)(i / view_bytes);
+        const int k = (int)(i - view * view_bytes);
+        const int y = k / row_bytes, xb = k - y * row_bytes;
+        const int va = xb / (ts * 3), r = xb - va * ts * 3;
+        const int vb = y / ts, pyy = y - vb * ts;
+        const int t = s_tile[view * VV + vb * V + va];
+        const int slot = (t >= p.n_tiles) ? p.n_tiles * p.orient_slots : t * p.orient_slots + s_orient[view];
+        dst[i] = s_atlas[(slot * ts + pyy) * ts * 3 + r];
+      }
+    }
+  }
+  if (STEP != 0 && warp == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// zero-initialised family of freshly constructed envs (bonus_state = None)
+__global__ void init_kernel(uint8_t* grid, uint8_t* agents, int32_t* envrec, long long B, int A, int S) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long n_grid = B * 3 * S / 16, n_ag = B * A, n_er = B;
+  if (i < n_grid) reinterpret_cast<int4*>(grid)[i] = make_int4(0, 0, 0, 0);
+  if (i < n_ag) reinterpret_cast<int4*>(agents)[i] = make_int4(0, (int)0xFF000000u, 0, 0);
+  if (i < n_er) reinterpret_cast<int4*>(envrec)[i] = make_int4(0, 0, 0, 0);
+}
+
+// synthetic uniform policy: 4 actions per Philox call
+__global__ void random_actions_kernel(int32_t* actions, long long n, int n_actions, unsigned long long seed, unsigned long long counter) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i * 4 >= n) return;
+  const U4 r = philox4x32_10((uint32_t)i, (uint32_t)(i >> 32), (uint32_t)counter, (uint32_t)(counter >> 32) ^ 0xAC710000u, (uint32_t)seed,
+                             (uint32_t)(seed >> 32));
+  const uint32_t v[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (i * 4 + k < n) actions[i * 4 + k] = (int32_t)__umulhi(v[k], (uint32_t)n_actions);
+}
+
+// occlude_mask (agents.py:298-343) known-answer kernel: one thread per VxV grid, layout [i][j]
+template <int V>
+__global__ void los_kernel(const uint8_t* __restrict__ transparent, uint8_t* __restrict__ mask, long long n, int ax, int ay) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint8_t* t = transparent + i * V * V;
+  uint32_t T[V], M[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    uint32_t row = 0;
+#pragma unroll
+    for (int x = 0; x < V; ++x) row |= (t[x * V + j] ? 1u : 0u) << x;
+    T[j] = row;
+  }
+  // generic agent position: the row-mask routine is specialised on (ax, ay) being runtime values
+  occlude_rows<V>(T, ax, ay, M);
+  uint8_t* m = mask + i * V * V;
+#pragma unroll
+  for (int j = 0; j < V; ++j)
+#pragma unroll
+    for (int x = 0; x < V; ++x) m[x * V + j] = (uint8_t)((M[j] >> x) & 1u);
+}
+
+}  // namespace mg
+
+// =============================================================================================
+// host side: C ABI (include/marlgrid_b200.h)
+// =============================================================================================
+using namespace mg;
+
+static std::atomic<long long> g_launches{0};
+
+static int check_cfg(const MgConfig* c) {
+  if (!c) return MG_E_CONFIG;
+  if (c->n_agents < 1 || c->n_agents > MG_MAX_AGENTS) return MG_E_CONFIG;
+  if (c->view_size < 3 || c->view_size > MG_MAX_VIEW) return MG_E_CONFIG;
+  if (c->width < 3 || c->height < 3 || c->width > 255 || c->height > 255) return MG_E_CONFIG;
+  if (c->plane_stride % 16 != 0 || c->plane_stride < c->width * c->height) return MG_E_CONFIG;
+  if (c->view_offset < 0 || c->view_offset >= c->view_size) return MG_E_CONFIG;
+  if (c->max_steps < 1 || c->n_clutter < 0 || c->n_bonus_tiles < 0 || c->n_bonus_tiles > 250) return MG_E_CONFIG;
+  return 0;
+}
+
+static KP make_kp(const MgConfig* c, const MgState* st) {
+  KP p;
+  memset(&p, 0, sizeof p);
+  p.W = c->width; p.H = c->height; p.A = c->n_agents; p.V = c->view_size; p.vo = c->view_offset; p.ts = c->view_tile_size;
+  p.max_steps = c->max_steps; p.n_clutter = c->n_clutter; p.n_bonus = c->n_bonus_tiles; p.goal_mode = c->goal_mode;
+  p.flags = c->flags; p.S = c->plane_stride;
+  p.goal_reward = c->goal_reward; p.bonus_reward = c->bonus_reward; p.bonus_penalty = c->bonus_penalty;
+  for (int i = 0; i < MG_MAX_AGENTS; ++i) { p.agent_color[i] = c->agent_color[i]; p.spawn_delay[i] = c->spawn_delay[i]; }
+  for (int i = 0; i < 15; ++i) p.kind_of_type[i] = c->kind_of_type[i];
+  p.kind_of_type[15] = 0xFF;
+  p.grid = st->grid; p.agents = st->agents; p.envrec = st->envrec; p.B = st->n_envs; p.env_offset = st->env_offset; p.seed = st->seed;
+  p.n_tiles = (c->n_static_kinds + 1) * (1 + 4 * c->n_agents);
+  p.orient_slots = 4;
+  return p;
+}
+
+static size_t smem_bytes(const KP& p, int obs) {
+  size_t b = (size_t)ENVS_PER_CTA * 3 * p.S + (size_t)p.A * 4 * 32 * 4 + 16;
+  if (obs == 1) b += (size_t)ENVS_PER_CTA * p.A * p.V * p.V * 3;
+  if (obs == 2) {
+    b += (size_t)ENVS_PER_CTA * p.A * p.V * p.V + (size_t)((ENVS_PER_CTA * p.A + 15) / 16) * 16;
+    b += (size_t)(p.n_tiles * p.orient_slots + 1) * p.ts * p.ts * 3;
+  }
+  return (b + 15) / 16 * 16;
+}
+
+template <int STEP, int OBS, int V, bool TS4>
+static int launch_one(const KP& p, cudaStream_t s) {
+  const size_t sm = smem_bytes(p, OBS);
+  auto k = mg_kernel<STEP, OBS, V, TS4>;
+  static size_t configured[64] = {0};  // per instantiation and device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (sm > 48 * 1024 && sm > configured[dev & 63]) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    if (e != cudaSuccess) return (int)e;
+    configured[dev & 63] = sm;
+  }
+  const int threads = (OBS == 0) ? 32 : 32 * p.A;
+  const long long blocks = (p.B + ENVS_PER_CTA - 1) / ENVS_PER_CTA;
+  if (blocks <= 0) return 0;
+  k<<<(unsigned)blocks, threads, sm, s>>>(p);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return (int)cudaGetLastError();
+}
+
+template <int STEP, int OBS, bool TS4>
+static int launch_v(const KP& p, cudaStream_t s) {
+  switch (p.V) {
+    case 3: return launch_one<STEP, OBS, 3, TS4>(p, s);
+    case 4: return launch_one<STEP, OBS, 4, TS4>(p, s);
+    case 5: return launch_one<STEP, OBS, 5, TS4>(p, s);
+    case 6: return launch_one<STEP, OBS, 6, TS4>(p, s);
+    case 7: return launch_one<STEP, OBS, 7, TS4>(p, s);
+    case 8: return launch_one<STEP, OBS, 8, TS4>(p, s);
+  }
+  return MG_E_CONFIG;
+}
+
+template <int STEP>
+static int launch(const KP& p, int obs, cudaStream_t s) {
+  if (obs == 0) return launch_one<STEP, 0, 7, false>(p, s);
+  if (obs == 1) return launch_v<STEP, 1, false>(p, s);
+  if (p.ts % 4 == 0) return launch_v<STEP, 2, true>(p, s);
+  return launch_v<STEP, 2, false>(p, s);
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+static int check_state(const MgConfig* c, const MgState* st) {
+  int e = check_cfg(c);
+  if (e) return e;
+  if (!st || !st->grid || !st->agents || !st->envrec || st->n_envs < 0) return MG_E_ARG;
+  if (!aligned16(st->grid) || !aligned16(st->agents) || !aligned16(st->envrec)) return MG_E_ARG;
+  return 0;
+}
+
+extern "C" {
+
+int mg_version(void) { return 1; }
+const char* mg_build_info(void) { return "marlgrid_b200 sm_100a cp.async.bulk+mbarrier staging, 32 envs/CTA"; }
+int mg_sizeof_config(void) { return (int)sizeof(MgConfig); }
+int mg_config_validate(const MgConfig* cfg) { return check_cfg(cfg); }
+int64_t mg_obs_bytes_per_env(const MgConfig* c, int rgb) {
+  if (check_cfg(c)) return MG_E_CONFIG;
+  const int64_t v = c->view_size;
+  return rgb ? (int64_t)c->n_agents * v * c->view_tile_size * v * c->view_tile_size * 3 : (int64_t)c->n_agents * v * v * 3;
+}
+int64_t mg_launch_count(void) { return g_launches.load(); }
+
+int mg_init(const MgConfig* cfg, const MgState* st, mg_stream_t stream) {
+  int e = check_state(cfg, st);
+  if (e) return e;
+  if (st->n_envs == 0) return 0;
+  const long long n = std::max<long long>(st->n_envs * 3 * cfg->plane_stride / 16, st->n_envs * cfg->n_agents);
+  init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(st->grid, st->agents, st->envrec, st->n_envs, cfg->n_agents, cfg->plane_stride);
+  g_launches.fetch_add(1);
+  return (int)cudaGetLastError();
+}
+
+int mg_reset(const MgConfig* cfg, const MgState* st, const uint8_t* reset_mask, mg_stream_t stream) {
+  int e = check_state(cfg, st);
+  if (e) return e;
+  KP p = make_kp(cfg, st);
+  p.reset_mask = reset_mask;
+  return launch<2>(p, 0, (cudaStream_t)stream);
+}
+
+int mg_step(const MgConfig* cfg, const MgState* st, const int32_t* actions, double* rewards, uint8_t* done, int autoreset,
+            mg_stream_t stream) {
+  int e = check_state(cfg, st);
+  if (e) return e;
+  if (!actions || !rewards || !done) return MG_E_ARG;
+  KP p = make_kp(cfg, st);
+  p.actions = actions; p.rewards = rewards; p.done = done; p.autoreset = autoreset;
+  return launch<1>(p, 0, (cudaStream_t)stream);
+}
+
+int mg_obs_encode(const MgConfig* cfg, const MgState* st, uint8_t* obs, mg_stream_t stream) {
+  int e = check_state(cfg, st);
+  if (e) return e;
+  if (!obs || !aligned16(obs)) return MG_E_ARG;
+  KP p = make_kp(cfg, st);
+  p.obs = obs;
+  return launch<0>(p, 1, (cudaStream_t)stream);
+}
+
+static int atlas_mode(const MgConfig* cfg) { return (cfg->view_tile_size <= 10) ? 1 : 4; }  // empty_tile alpha == 0 (base.py:247): rotation-equivariant
+
+int mg_obs_rgb(const MgConfig* cfg, const MgState* st, const uint8_t* atlas, uint8_t* obs, mg_stream_t stream) {
+  int e = check_state(cfg, st);
+  if (e) return e;
+  if (!obs || !atlas || !aligned16(obs) || cfg->view_tile_size < 1) return MG_E_ARG;
+  KP p = make_kp(cfg, st);
+  p.obs = obs; p.atlas = atlas; p.orient_slots = atlas_mode(cfg);
+  return launch<0>(p, 2, (cudaStream_t)stream);
+}
+
+int mg_step_fused(const MgConfig* cfg, const MgState* st, const int32_t* actions, double* rewards, uint8_t* done, uint8_t* obs,
+                  int autoreset, mg_stream_t stream) {
+  int e = check_state(cfg, st);
+  if (e) return e;
+  if (!actions || !rewards || !done || !obs || !aligned16(obs)) return MG_E_ARG;
+  KP p = make_kp(cfg, st);
+  p.actions = actions; p.rewards = rewards; p.done = done; p.obs = obs; p.autoreset = autoreset;
+  return launch<1>(p, 1, (cudaStream_t)stream);
+}
+
+int mg_step_fused_rgb(const MgConfig* cfg, const MgState* st, const int32_t* actions, double* rewards, uint8_t* done,
+                      const uint8_t* atlas, uint8_t* obs, int autoreset, mg_stream_t stream) {
+  int e = check_state(cfg, st);
+  if (e) return e;
+  if (!actions || !rewards || !done || !obs || !atlas || !aligned16(obs) || cfg->view_tile_size < 1) return MG_E_ARG;
+  KP p = make_kp(cfg, st);
+  p.actions = actions; p.rewards = rewards; p.done = done; p.obs = obs; p.atlas = atlas; p.autoreset = autoreset;
+  p.orient_slots = atlas_mode(cfg);
+  return launch<1>(p, 2, (cudaStream_t)stream);
+}
+
+int mg_rollout_fused(const MgConfig* cfg, const MgState* st, const int32_t* actions, int64_t n_steps, double* rewards, uint8_t* done,
+                     uint8_t* obs, int autoreset, mg_stream_t stream) {
+  int e = check_state(cfg, st);
+  if (e) return e;
+  if (!actions || !rewards || !done || !obs || !aligned16(obs)) return MG_E_ARG;
+  KP p = make_kp(cfg, st);
+  p.rewards = rewards; p.done = done; p.obs = obs; p.autoreset = autoreset;
+  for (int64_t t = 0; t < n_steps; ++t) {
+    p.actions = actions + t * st->n_envs * cfg->n_agents;
+    e = launch<1>(p, 1, (cudaStream_t)stream);
+    if (e) return e;
+  }
+  return 0;
+}
+
+int mg_random_actions(int32_t* actions, int64_t n, int n_actions, uint64_t seed, uint64_t counter, mg_stream_t stream) {
+  if (!actions || n < 0 || n_actions < 1) return MG_E_ARG;
+  if (n == 0) return 0;
+  const long long threads = (n + 3) / 4;
+  random_actions_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(actions, n, n_actions, seed, counter);
+  g_launches.fetch_add(1);
+  return (int)cudaGetLastError();
+}
+
+int mg_los_batch(const uint8_t* transparent, uint8_t* mask, int64_t n, int view_size, int ax, int ay, mg_stream_t stream) {
+  if (!transparent || !mask || n < 0 || ax < 0 || ay < 0 || ax >= view_size || ay >= view_size) return MG_E_ARG;
+  if (n == 0) return 0;
+  const unsigned blocks = (unsigned)((n + 127) / 128);
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (view_size) {
+    case 3: los_kernel<3><<<blocks, 128, 0, s>>>(transparent, mask, n, ax, ay); break;
+    case 4: los_kernel<4><<<blocks, 128, 0, s>>>(transparent, mask, n, ax, ay); break;
+    case 5: los_kernel<5><<<blocks, 128, 0, s>>>(transparent, mask, n, ax, ay); break;
+    case 6: los_kernel<6><<<blocks, 128, 0, s>>>(transparent, mask, n, ax, ay); break;
+    case 7: los_kernel<7><<<blocks, 128, 0, s>>>(transparent, mask, n, ax, ay); break;
+    case 8: los_kernel<8><<<blocks, 128, 0, s>>>(transparent, mask, n, ax, ay); break;
+    default: return MG_E_CONFIG;
+  }
+  g_launches.fetch_add(1);
+  return (int)cudaGetLastError();
+}
+
+// ---- host-buffer engine -----------------------------------------------------------------------
+struct MgEngine {
+  MgConfig cfg;
+  MgState st;
+  int device, rgb;
+  cudaStream_t stream;
+  int32_t* d_actions;
+  double* d_rewards;
+  uint8_t* d_done;
+  uint8_t* d_obs;
+  uint8_t* d_atlas;
+  int64_t obs_bytes;
+};
+
+#define MG_CUDA(x)                                \
+  do {                                            \
+    cudaError_t _e = (x);                         \
+    if (_e != cudaSuccess) return (int)_e;        \
+  } while (0)
+
+int mg_engine_create(MgEngine** out, const MgConfig* cfg, int64_t n_envs, int64_t env_offset, uint64_t seed, int device, int rgb,
+                     const uint8_t* atlas_host, int64_t atlas_bytes) {
+  if (!out || n_envs < 1) return MG_E_ARG;
+  int e = check_cfg(cfg);
+  if (e) return e;
+  if (rgb && (!atlas_host || atlas_bytes <= 0)) return MG_E_ARG;
+  MG_CUDA(cudaSetDevice(device));
+  MgEngine* en = new MgEngine();
+  memset(en, 0, sizeof *en);
+  en->cfg = *cfg; en->device = device; en->rgb = rgb;
+  en->st.n_envs = n_envs; en->st.env_offset = env_offset; en->st.seed = seed;
+  en->obs_bytes = n_envs * mg_obs_bytes_per_env(cfg, rgb);
+  MG_CUDA(cudaStreamCreateWithFlags(&en->stream, cudaStreamNonBlocking));
+  MG_CUDA(cudaMalloc(&en->st.grid, (size_t)n_envs * 3 * cfg->plane_stride));
+  MG_CUDA(cudaMalloc(&en->st.agents, (size_t)n_envs * cfg->n_agents * MG_AGENT_REC));
+  MG_CUDA(cudaMalloc(&en->st.envrec, (size_t)n_envs * MG_ENV_REC));
+  MG_CUDA(cudaMalloc(&en->d_actions, (size_t)n_envs * cfg->n_agents * sizeof(int32_t)));
+  MG_CUDA(cudaMalloc(&en->d_rewards, (size_t)n_envs * cfg->n_agents * sizeof(double)));
+  MG_CUDA(cudaMalloc(&en->d_done, (size_t)n_envs));
+  MG_CUDA(cudaMalloc(&en->d_obs, (size_t)en->obs_bytes));
+  if (rgb) {
+    MG_CUDA(cudaMalloc(&en->d_atlas, (size_t)atlas_bytes));
+    MG_CUDA(cudaMemcpy(en->d_atlas, atlas_host, (size_t)atlas_bytes, cudaMemcpyHostToDevice));
+  }
+  e = mg_init(&en->cfg, &en->st, en->stream);
+  if (e) return e;
+  MG_CUDA(cudaStreamSynchronize(en->stream));
+  *out = en;
+  return 0;
+}
+
+void mg_engine_destroy(MgEngine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  cudaStreamSynchronize(e->stream);
+  cudaFree(e->st.grid); cudaFree(e->st.agents); cudaFree(e->st.envrec);
+  cudaFree(e->d_actions); cudaFree(e->d_rewards); cudaFree(e->d_done); cudaFree(e->d_obs); cudaFree(e->d_atlas);
+  cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+int mg_engine_reset(MgEngine* e, uint8_t* obs_host) {
+  if (!e) return MG_E_ARG;
+  MG_CUDA(cudaSetDevice(e->device));
+  int r = mg_reset(&e->cfg, &e->st, nullptr, e->stream);
+  if (r) return r;
+  r = e->rgb ? mg_obs_rgb(&e->cfg, &e->st, e->d_atlas, e->d_obs, e->stream) : mg_obs_encode(&e->cfg, &e->st, e->d_obs, e->stream);
+  if (r) return r;
+  if (obs_host) MG_CUDA(cudaMemcpyAsync(obs_host, e->d_obs, (size_t)e->obs_bytes, cudaMemcpyDeviceToHost, e->stream));
+  MG_CUDA(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+int mg_engine_step(MgEngine* e, const int32_t* actions_host, uint8_t* obs_host, double* rewards_host, uint8_t* done_host, int autoreset) {
+  if (!e || !actions_host) return MG_E_ARG;
+  MG_CUDA(cudaSetDevice(e->device));
+  const size_t na = (size_t)e->st.n_envs * e->cfg.n_agents;
+  MG_CUDA(cudaMemcpyAsync(e->d_actions, actions_host, na * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+  int r = e->rgb ? mg_step_fused_rgb(&e->cfg, &e->st, e->d_actions, e->d_rewards, e->d_done, e->d_atlas, e->d_obs, autoreset, e->stream)
+                 : mg_step_fused(&e->cfg, &e->st, e->d_actions, e->d_rewards, e->d_done, e->d_obs, autoreset, e->stream);
+  if (r) return r;
+  if (obs_host) MG_CUDA(cudaMemcpyAsync(obs_host, e->d_obs, (size_t)e->obs_bytes, cudaMemcpyDeviceToHost, e->stream));
+  if (rewards_host) MG_CUDA(cudaMemcpyAsync(rewards_host, e->d_rewards, na * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+  if (done_host) MG_CUDA(cudaMemcpyAsync(done_host, e->d_done, (size_t)e->st.n_envs, cudaMemcpyDeviceToHost, e->stream));
+  MG_CUDA(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+void* mg_host_alloc(int64_t bytes) {
+  void* p = nullptr;
+  if (cudaMallocHost(&p, (size_t)bytes) != cudaSuccess) return nullptr;
+  return p;
+}
+void mg_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+}  // extern "C"

@@ -1,0 +1,309 @@
+"""BatchedMultiGridEnv: N independent MarlGrid envs stepped on one B200 by hand-written CUDA kernels.
+
+Host-side mirror of the reference's env runtime, MultiGridEnv (marlgrid/base.py:334-653): same
+constructor kwargs, `seed`, `reset`, `step`, `action_space`, `observation_space`, `num_agents`; the
+per-cell Python loops are replaced by calls through the C ABI (include/marlgrid_b200.h) on
+structure-of-arrays torch tensors that never leave the device.
+
+    env.reset()            -> obs  uint8 [B, A, V, V, 3]            (obs_mode='encoded', MultiGrid.encode base.py:196-214)
+                                   uint8 [B, A, V*ts, V*ts, 3]      (obs_mode='rgb',     MultiGrid.render base.py:301-331)
+    env.step(actions[B,A]) -> (obs, rewards float64 [B, A], done bool [B], {})
+
+With `autoreset=True` (default) envs whose episode ended are reset inside the same kernel launch and
+the returned obs are the first obs of the new episode, which is what a caller loop
+`obs, r, d, _ = env.step(a); if d: obs = env.reset()` produces with the reference.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import atlas as _atlas
+from .config import (AF_ACTIVE, AF_DONE, AF_PLACED, ERR_BAD_ACTION, ERR_PLACEMENT, ERR_RENDER, ERR_STACK, ERR_TOGGLE,
+                     MgConfig, MgState, n_tiles)
+from .spaces import Box, Discrete, Tuple
+
+
+class BatchedMultiGridEnv:
+    metadata = {}
+
+    def __init__(self, cfg, num_envs=1, device="cuda", seed=1337, env_offset=0, obs_mode="encoded", autoreset=True,
+                 check_errors=False):
+        if not isinstance(cfg, MgConfig):
+            raise TypeError("cfg must be a marlgrid_b200.config.MgConfig")
+        if obs_mode not in ("encoded", "rgb"):
+            raise ValueError("obs_mode must be 'encoded' or 'rgb'")
+        self._lib = _lib.load()  # raises if the CUDA extension is not built: there is no CPU path
+        self.cfg = cfg
+        self.num_envs = int(num_envs)
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise ValueError("marlgrid_b200 runs on CUDA devices only (no CPU fallback)")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.obs_mode = obs_mode
+        self.autoreset = bool(autoreset)
+        self.check_errors_each_step = bool(check_errors)
+        self.env_offset = int(env_offset)
+        _lib.check(self._lib.mg_config_validate(ctypes.byref(cfg)), "mg_config_validate")
+
+        B, A, V, ts, S = self.num_envs, cfg.n_agents, cfg.view_size, cfg.view_tile_size, cfg.plane_stride
+        dev = self.device
+        self.grid = torch.empty((B, 3, S), dtype=torch.uint8, device=dev)
+        self.agents = torch.empty((B, A, 16), dtype=torch.uint8, device=dev)
+        self.envrec = torch.empty((B, 4), dtype=torch.int32, device=dev)
+        self.rewards = torch.zeros((B, A), dtype=torch.float64, device=dev)
+        self.done = torch.zeros((B,), dtype=torch.uint8, device=dev)
+        if obs_mode == "encoded":
+            self.obs = torch.zeros((B, A, V, V, 3), dtype=torch.uint8, device=dev)
+            self.atlas = None
+        else:
+            self.obs = torch.zeros((B, A, V * ts, V * ts, 3), dtype=torch.uint8, device=dev)
+            at = _atlas.build_atlas([int(c) for c in cfg.agent_color[:A]], ts, cfg.n_static_kinds)
+            assert at.shape[0] == n_tiles(cfg)
+            self.atlas = torch.from_numpy(at).to(dev)
+        self._state = MgState()
+        self.seed(seed)
+        self._sync_state_struct()
+        with torch.cuda.device(dev):
+            _lib.check(self._lib.mg_init(ctypes.byref(cfg), ctypes.byref(self._state), self._stream()), "mg_init")
+
+    # ---- plumbing ------------------------------------------------------------------------------
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _sync_state_struct(self):
+        st = self._state
+        st.grid, st.agents, st.envrec = self.grid.data_ptr(), self.agents.data_ptr(), self.envrec.data_ptr()
+        st.n_envs, st.env_offset, st.seed = self.num_envs, self.env_offset, self._seed
+
+    def seed(self, seed=1337):
+        """marlgrid/base.py:371-374.  The Philox key; the global env index is the counter."""
+        self._seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        self._state.seed = self._seed
+        return [seed]
+
+    # ---- gym surface ---------------------------------------------------------------------------
+    @property
+    def num_agents(self):
+        return self.cfg.n_agents
+
+    @property
+    def action_space(self):
+        return Tuple([Discrete(7) for _ in range(self.cfg.n_agents)])
+
+    @property
+    def observation_space(self):
+        shape = tuple(self.obs.shape[2:])
+        return Tuple([Box(0, 255, shape, np.uint8) for _ in range(self.cfg.n_agents)])
+
+    def _observe(self):
+        cfg, st = ctypes.byref(self.cfg), ctypes.byref(self._state)
+        if self.obs_mode == "encoded":
+            _lib.check(self._lib.mg_obs_encode(cfg, st, self.obs.data_ptr(), self._stream()), "mg_obs_encode")
+        else:
+            _lib.check(self._lib.mg_obs_rgb(cfg, st, self.atlas.data_ptr(), self.obs.data_ptr(), self._stream()), "mg_obs_rgb")
+        return self.obs
+
+    def reset(self, mask=None, **kwargs):
+        """Start a new episode in every env (or where mask[b] != 0); returns the observations."""
+        with torch.cuda.device(self.device):
+            m = None
+            if mask is not None:
+                m = torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
+            _lib.check(self._lib.mg_reset(ctypes.byref(self.cfg), ctypes.byref(self._state), m.data_ptr() if m is not None else None,
+                                          self._stream()), "mg_reset")
+            return self._observe()
+
+    def _actions(self, actions):
+        a = torch.as_tensor(actions, device=self.device)
+        if a.dtype != torch.int32:
+            a = a.to(torch.int32)
+        a = a.reshape(self.num_envs, self.cfg.n_agents).contiguous()
+        return a
+
+    def step(self, actions):
+        """One env.step for the whole batch (marlgrid/base.py:501-653) in a single kernel launch."""
+        with torch.cuda.device(self.device):
+            a = self._actions(actions)
+            cfg, st = ctypes.byref(self.cfg), ctypes.byref(self._state)
+            if self.obs_mode == "encoded":
+                rc = self._lib.mg_step_fused(cfg, st, a.data_ptr(), self.rewards.data_ptr(), self.done.data_ptr(), self.obs.data_ptr(),
+                                             int(self.autoreset), self._stream())
+            else:
+                rc = self._lib.mg_step_fused_rgb(cfg, st, a.data_ptr(), self.rewards.data_ptr(), self.done.data_ptr(),
+                                                 self.atlas.data_ptr(), self.obs.data_ptr(), int(self.autoreset), self._stream())
+            _lib.check(rc, "mg_step_fused")
+            if self.check_errors_each_step:
+                self.check_errors()
+            return self.obs, self.rewards, self.done.bool(), {}
+
+    def step_only(self, actions):
+        """step without producing observations (mg_step); returns (rewards, done)."""
+        with torch.cuda.device(self.device):
+            a = self._actions(actions)
+            _lib.check(self._lib.mg_step(ctypes.byref(self.cfg), ctypes.byref(self._state), a.data_ptr(), self.rewards.data_ptr(),
+                                         self.done.data_ptr(), int(self.autoreset), self._stream()), "mg_step")
+            return self.rewards, self.done.bool()
+
+    def observe(self):
+        with torch.cuda.device(self.device):
+            return self._observe()
+
+    def rollout(self, actions):
+        """actions int32 [T, B, A]: T fused steps enqueued from C; returns the last (obs, rewards, done)."""
+        with torch.cuda.device(self.device):
+            if self.obs_mode != "encoded":
+                raise NotImplementedError("rollout() drives the encoded-obs path")
+            a = torch.as_tensor(actions, device=self.device).to(torch.int32).contiguous()
+            T = a.shape[0]
+            assert a.shape[1:] == (self.num_envs, self.cfg.n_agents)
+            _lib.check(self._lib.mg_rollout_fused(ctypes.byref(self.cfg), ctypes.byref(self._state), a.data_ptr(), T, self.rewards.data_ptr(),
+                                                  self.done.data_ptr(), self.obs.data_ptr(), int(self.autoreset), self._stream()), "mg_rollout_fused")
+            return self.obs, self.rewards, self.done.bool()
+
+    def random_actions(self, counter, n_actions=7, seed=0, out=None):
+        """Uniform synthetic policy on the device; `counter` selects the draw."""
+        with torch.cuda.device(self.device):
+            if out is None:
+                out = torch.empty((self.num_envs, self.cfg.n_agents), dtype=torch.int32, device=self.device)
+            _lib.check(self._lib.mg_random_actions(out.data_ptr(), out.numel(), n_actions, seed, counter, self._stream()), "mg_random_actions")
+            return out
+
+    # ---- errors the reference would have raised --------------------------------------------------
+    @property
+    def err(self):
+        return (self.envrec[:, 3] >> 16) & 0xFFFF
+
+    def check_errors(self, clear=True):
+        """Device code cannot raise; it accumulates MG_ERR_* bits per env.  Raise like the reference."""
+        bits = int(np.bitwise_or.reduce(self.err.cpu().numpy())) if self.num_envs else 0
+        if bits and clear:
+            self.envrec[:, 3] &= 0xFFFF
+        if bits & ERR_BAD_ACTION:
+            raise ValueError("Environment can't handle action (marlgrid/base.py:619-620)")
+        if bits & ERR_PLACEMENT:
+            raise RecursionError("Rejection sampling failed in place_obj. (marlgrid/base.py:706)")
+        if bits & ERR_STACK:
+            raise AssertionError("agent left a cell that cannot be overlapped (marlgrid/base.py:558)")
+        if bits & ERR_TOGGLE:
+            raise TypeError("Box.toggle() takes 1 positional argument but 3 were given (marlgrid/objects.py:381)")
+        if bits & ERR_RENDER:
+            raise NameError("object has no working render() in the reference (marlgrid/objects.py:274-277,309-321,370)")
+
+    # ---- SoA views (decoded) -------------------------------------------------------------------
+    @property
+    def planes(self):
+        """uint8 [B, 3, W, H] view: type / colour / state planes, index [x][y] like MultiGrid.grid (base.py:91)."""
+        W, H = self.cfg.width, self.cfg.height
+        return self.grid[:, :, : W * H].unflatten(2, (W, H))
+
+    @property
+    def grid_type(self):
+        return self.planes[:, 0]
+
+    @property
+    def grid_color(self):
+        return self.planes[:, 1]
+
+    @property
+    def grid_state(self):
+        return self.planes[:, 2]
+
+    @property
+    def agent_pos(self):
+        return self.agents[:, :, 0:2]
+
+    @property
+    def agent_dir(self):
+        return self.agents[:, :, 2]
+
+    @property
+    def agent_flags(self):
+        return self.agents[:, :, 3]
+
+    @property
+    def agent_placed(self):
+        return (self.agents[:, :, 3] & AF_PLACED) != 0
+
+    @property
+    def agent_active(self):
+        return (self.agents[:, :, 3] & AF_ACTIVE) != 0
+
+    @property
+    def agent_done(self):
+        return (self.agents[:, :, 3] & AF_DONE) != 0
+
+    @property
+    def agent_carrying(self):
+        return self.agents[:, :, 4:7]
+
+    @property
+    def agent_stamp(self):
+        return self.agents[:, :, 8:12].contiguous().view(torch.int32)[..., 0]
+
+    @property
+    def step_count(self):
+        return self.envrec[:, 0]
+
+    @property
+    def episode(self):
+        return self.envrec[:, 1]
+
+    # ---- checkpoint / resume (the RNG is counter-based: resume is exact) -----------------------
+    def state_dict(self):
+        return {"grid": self.grid.clone(), "agents": self.agents.clone(), "envrec": self.envrec.clone(), "seed": self._seed,
+                "env_offset": self.env_offset}
+
+    def load_state_dict(self, sd):
+        self.grid.copy_(sd["grid"])
+        self.agents.copy_(sd["agents"])
+        self.envrec.copy_(sd["envrec"])
+        self._seed = int(sd["seed"])
+        self.env_offset = int(sd["env_offset"])
+        self._sync_state_struct()
+
+    def unbatched(self, index=0):
+        """gym-style view of env `index`: lists of per-agent obs, like the reference's return values."""
+        return UnbatchedView(self, index)
+
+    def __repr__(self):
+        c = self.cfg
+        return f"<{type(self).__name__} {c.width}x{c.height} agents={c.n_agents} num_envs={self.num_envs} obs={self.obs_mode} on {self.device}>"
+
+
+class UnbatchedView:
+    """The reference's single-env surface on top of a batched env (requires num_envs == 1 to step)."""
+
+    def __init__(self, env, index=0):
+        self.env = env
+        self.index = index
+
+    @property
+    def num_agents(self):
+        return self.env.num_agents
+
+    @property
+    def action_space(self):
+        return self.env.action_space
+
+    @property
+    def observation_space(self):
+        return self.env.observation_space
+
+    def seed(self, seed=1337):
+        return self.env.seed(seed)
+
+    def reset(self, **kw):
+        obs = self.env.reset()
+        return [obs[self.index, a] for a in range(self.env.num_agents)]
+
+    def step(self, actions):
+        if self.env.num_envs != 1:
+            raise ValueError("UnbatchedView.step needs num_envs == 1")
+        if len(actions) != self.env.num_agents:
+            raise AssertionError("len(actions) == len(self.agents)")  # base.py:508
+        obs, rew, done, info = self.env.step(torch.as_tensor(list(int(a) for a in actions), dtype=torch.int32).view(1, -1))
+        self.env.check_errors()
+        return [obs[0, a] for a in range(self.env.num_agents)], rew[0], bool(done[0].item()), info

@@ -1,0 +1,166 @@
+"""Freeze outputs of the UNMODIFIED reference as golden fixtures under tests/golden/.
+
+Run in the dev container (needs /root/reference):   python -m oracle.gen_golden
+TEST INFRASTRUCTURE ONLY.  The reference cannot travel to the GPU box, so its behaviour on seeded
+trajectories is committed as small .npz files together with this generating script:
+
+  traj_<scenario>.npz   event stream (0 = reset, 1 = step(actions), 2 = overwrite planes, 3 = step on which
+                        the reference raises: expect the MG_ERR_* bit, then take `dir` from the fixture) and, after
+                        every event, what the reference shows: encoded obs, RGB obs (first episodes),
+                        rewards (float64), done, grid planes, agent pos/dir/flags/queue-rank/carrying
+  los.npz               transparency grids + occlude_mask results (numba, zero-padded input)
+  atlas_ts<k>.npz       tiles rendered by the reference's MultiGrid.render_tile, all orientations
+Every trajectory is produced by oracle.validate_against_reference.LockStep, i.e. the C oracle is
+checked against the reference on exactly these trajectories while they are recorded.
+"""
+import json
+import os
+
+import numpy as np
+
+from . import reference_harness as rh
+from . import validate_against_reference as val
+
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
+
+
+class Recorder(val.LockStep):
+    def __init__(self, *a, rgb_events=40, **kw):
+        super().__init__(*a, **kw)
+        self.ev = []
+        self.rgb_events = rgb_events
+
+    def _snap(self, kind, actions, rew, done):
+        st = rh.extract_state(self.env)
+        A = len(self.env.agents)
+        rec = dict(
+            kind=kind,
+            actions=np.zeros(A, np.int32) if actions is None else np.asarray(actions, np.int32),
+            rew=np.zeros(A, np.float64) if rew is None else np.asarray(rew, np.float64),
+            done=bool(done),
+            enc=rh.encoded_obs(self.env),
+            grid=st["grid"], x=st["agent_x"], y=st["agent_y"], dir=st["agent_dir"],
+            flags=((st["agent_x"] >= 0) * 1 + st["agent_active"] * 2 + st["agent_done"] * 4).astype(np.uint8),
+            rank=st["agent_rank"], carry=st["agent_carry"], step_count=int(st["step_count"]),
+        )
+        if self.rgb and len(self.ev) < self.rgb_events:
+            rec["rgb"] = rh.rgb_obs(self.env)
+        self.ev.append(rec)
+
+    def reset(self):
+        rh.ref_reset(self.env)
+        self.ob.reset()
+        self._snap(0, None, None, False)
+        if self.inject is not None:
+            self.inject(self)
+            self._snap(2, None, None, False)
+        self.compare("reset")
+
+    def step(self, actions, t):
+        d = super().step(actions, t)
+        if d != "raised":
+            self._snap(1, actions, self.trace["rew"][-1], d)
+        else:  # kind 3: a step on which the reference raises; only actions, err and the post-raise dirs are meaningful
+            rec = dict(self.ev[-1])  # the reference's object graph may be inconsistent after the raise
+            rec.pop("rgb", None)
+            rec.update(kind=3, actions=np.asarray(actions, np.int32), err=self.last_raise[1],
+                       dir=np.array([a.dir for a in self.env.agents], np.int32))
+            self.ev.append(rec)
+        return d
+
+    def save(self, fname, make_kwargs):
+        ev = self.ev
+        n_rgb = sum(1 for e in ev if "rgb" in e)
+        out = dict(
+            meta=np.frombuffer(json.dumps(make_kwargs).encode(), dtype=np.uint8),
+            kind=np.array([e["kind"] for e in ev], np.uint8),
+            actions=np.stack([e["actions"] for e in ev]),
+            rew=np.stack([e["rew"] for e in ev]),
+            done=np.array([e["done"] for e in ev], np.uint8),
+            enc=np.stack([e["enc"] for e in ev]),
+            grid=np.stack([e["grid"] for e in ev]),
+            x=np.stack([e["x"] for e in ev]), y=np.stack([e["y"] for e in ev]), dir=np.stack([e["dir"] for e in ev]),
+            flags=np.stack([e["flags"] for e in ev]), rank=np.stack([e["rank"] for e in ev]), carry=np.stack([e["carry"] for e in ev]),
+            step_count=np.array([e["step_count"] for e in ev], np.int32),
+            err=np.array([e.get("err", 0) for e in ev], np.int32),
+        )
+        if n_rgb:
+            out["rgb"] = np.stack([e["rgb"] for e in ev[:n_rgb]])
+        np.savez_compressed(os.path.join(OUT, fname), **out)
+        return len(ev)
+
+
+def cfg_kwargs(cfg, seed, env_index):
+    """make_config kwargs that rebuild `cfg` (JSON-able), plus the RNG identity of the run."""
+    from marlgrid_b200.config import F_BONUS_INITIAL, F_BONUS_RESET, F_GHOST, F_RESPAWN, F_REWARD_DECAY, F_SEE_THROUGH
+
+    return dict(
+        seed=seed, env_index=env_index,
+        config=dict(
+            width=cfg.width, height=cfg.height, agent_colors=[int(c) for c in cfg.agent_color[: cfg.n_agents]],
+            view_size=cfg.view_size, view_offset=cfg.view_offset, view_tile_size=cfg.view_tile_size,
+            max_steps=cfg.max_steps, n_clutter=cfg.n_clutter, n_bonus_tiles=cfg.n_bonus_tiles, goal_mode=cfg.goal_mode,
+            ghost_mode=bool(cfg.flags & F_GHOST), respawn=bool(cfg.flags & F_RESPAWN), reward_decay=bool(cfg.flags & F_REWARD_DECAY),
+            see_through_walls=bool(cfg.flags & F_SEE_THROUGH), goal_reward=cfg.goal_reward, bonus_reward=cfg.bonus_reward,
+            bonus_penalty=cfg.bonus_penalty, bonus_initial_reward=bool(cfg.flags & F_BONUS_INITIAL),
+            bonus_reset_on_mistake=bool(cfg.flags & F_BONUS_RESET), spawn_delay=[int(s) for s in cfg.spawn_delay[: cfg.n_agents]],
+        ),
+    )
+
+
+def gen_trajectories():
+    rng = np.random.RandomState(2024)
+    k = 0
+    for sc in val.SCENARIOS + val.INTERACTIVE[:3]:
+        sc = dict(sc)
+        name = sc.pop("name")
+        interactive = sc.pop("interactive", False)
+        with_box = sc.pop("with_box", False)
+        sc.pop("n_actions", None)
+        seed, env_index = 1337 + 17 * k, 1000 * k + 3
+        k += 1
+        rec = Recorder(name, seed=seed, env_index=env_index, rgb=not interactive, **sc)
+        if interactive:
+            rec.inject = val.inject_interactive
+            rec.with_box = with_box
+        rec.run(episodes=3, steps=rec.cfg.max_steps + 3, rng=rng, p_forward=0.35 if interactive else 0.5)
+        fname = "traj_" + "".join(ch if ch.isalnum() else "_" for ch in name).strip("_") + ".npz"
+        n = rec.save(fname, cfg_kwargs(rec.cfg, seed, env_index))
+        print(f"  {fname:48s} {n} events; {rec.events}")
+
+
+def gen_los():
+    ref = rh.load_reference()
+    rng = np.random.RandomState(5)
+    out = {}
+    for V, positions in ((7, [(3, 6), (3, 5)]), (5, [(2, 4), (2, 3)])):
+        for (ax, ay) in positions:
+            n = 1500
+            dens = rng.rand(n, 1, 1)
+            t = rng.rand(n, V, V) > dens * 0.6
+            # hand cases of SURVEY.md A.4: column-1 wall vs column-5 wall asymmetry, all transparent, all opaque
+            t[0] = True
+            t[1] = False
+            t[2] = True; t[2][1, : V - 1] = False
+            t[3] = True; t[3][V - 2, : V - 1] = False
+            m = np.stack([ref.agents.occlude_mask(np.ascontiguousarray(t[i]), (ax, ay)) for i in range(n)])
+            out[f"t_V{V}_{ax}_{ay}"] = np.packbits(t, axis=None)
+            out[f"m_V{V}_{ax}_{ay}"] = np.packbits(m, axis=None)
+            out[f"n_V{V}_{ax}_{ay}"] = np.array([n])
+    np.savez_compressed(os.path.join(OUT, "los.npz"), **out)
+    print("  los.npz")
+
+
+def gen_atlas():
+    colors = ["red", "blue", "purple", "orange", "olive", "pink"]
+    for ts in (8, 5, 11):
+        np.savez_compressed(os.path.join(OUT, f"atlas_ts{ts}.npz"), atlas=val.reference_atlas(colors, ts),
+                            colors=np.array([val.COLOR_TO_IDX[c] for c in colors], np.uint8))
+        print(f"  atlas_ts{ts}.npz")
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    gen_los()
+    gen_atlas()
+    gen_trajectories()

@@ -155,6 +155,10 @@ class LockStep:
             got = int(self.ob.err[0])
             assert got & want, f"{self.name} step {t}: reference raised {type(exc).__name__} but oracle err={got}"
             self.events["raised"] += 1
+            # the reference aborted mid-step, the oracle completed it: agent dirs (which survive the
+            # reset that follows, agents.py:161-170) are re-synchronised from the reference
+            self.ob.agents[0, :, 2] = [a.dir for a in self.env.agents]
+            self.last_raise = (np.asarray(actions, np.int32), want)
             return "raised"
         rew, done = self.ob.step(np.asarray(actions, np.int32)[None], autoreset=False)
         assert int(self.ob.err[0]) == err_before, f"{self.name} step {t}: oracle flagged err {int(self.ob.err[0])} but the reference did not raise"

@@ -1,0 +1,27 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box: pytest -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    from oracle import mg_oracle
+
+    mg_oracle.build()
+    return mg_oracle
+
+
+@pytest.fixture(scope="session")
+def cuda_lib():
+    from marlgrid_b200 import _lib
+
+    return _lib.load()

@@ -1,0 +1,310 @@
+"""GPU suite: the CUDA path (through the C ABI) against the oracle and the reference's golden vectors.
+
+Bit-exact bar: observations, float64 rewards (bit pattern), done and the full SoA state.
+"""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+from golden_util import load_los, load_traj, rank_from, trajectory_files
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+def _env(cfg, B, **kw):
+    from marlgrid_b200.env import BatchedMultiGridEnv
+
+    return BatchedMultiGridEnv(cfg, num_envs=B, device="cuda:0", **kw)
+
+
+def _state_equal(env, ob, what=""):
+    assert np.array_equal(env.grid.cpu().numpy(), ob.grid), f"{what}: grid planes"
+    ag = env.agents.cpu().numpy()
+    assert np.array_equal(ag[:, :, :12], ob.agents[:, :, :12]), f"{what}: agent records differ at {np.argwhere(ag[:, :, :12] != ob.agents[:, :, :12])[:4]}"
+    assert np.array_equal(env.envrec.cpu().numpy(), ob.envrec), f"{what}: env records"
+
+
+def test_library_is_cuda_native(cuda_lib):
+    assert cuda_lib.mg_version() == 1
+    assert b"sm_100a" in cuda_lib.mg_build_info()
+    assert torch.cuda.is_available()
+
+
+def test_los_kernel_matches_golden_and_oracle(cuda_lib, oracle):
+    from marlgrid_b200 import _lib
+
+    rng = np.random.RandomState(3)
+    cases = load_los()
+    for V in (3, 4, 5, 6, 7, 8):
+        for ay in (V - 1, V - 2):
+            t = (rng.rand(4000, V, V) > rng.rand(4000, 1, 1) * 0.6).astype(np.uint8)
+            cases.append((V, V // 2, ay, t, oracle.los_batch(t, V // 2, ay)))
+    for V, ax, ay, t, want in cases:
+        dt = torch.from_numpy(np.ascontiguousarray(t)).cuda()
+        dm = torch.zeros_like(dt)
+        _lib.check(cuda_lib.mg_los_batch(dt.data_ptr(), dm.data_ptr(), len(t), V, ax, ay, None), "mg_los_batch")
+        torch.cuda.synchronize()
+        assert np.array_equal(dm.cpu().numpy(), want), f"V={V} pos=({ax},{ay})"
+
+
+@pytest.mark.parametrize("path", trajectory_files(), ids=lambda p: os.path.basename(p)[5:-4])
+def test_cuda_replays_reference_trajectory(path):
+    """The event streams recorded from the unmodified reference, replayed through the kernels."""
+    cfg, meta, z = load_traj(path)
+    has_rgb = "rgb" in z.files
+    env = _env(cfg, 1, seed=meta["seed"], env_offset=meta["env_index"], obs_mode="encoded", autoreset=False)
+    env_rgb = _env(cfg, 1, seed=meta["seed"], env_offset=meta["env_index"], obs_mode="rgb", autoreset=False) if has_rgb else None
+    n_rgb = len(z["rgb"]) if has_rgb else 0
+    W, H = cfg.width, cfg.height
+    for i, kind in enumerate(z["kind"]):
+        act = torch.from_numpy(z["actions"][i][None].astype(np.int32)).cuda()
+        if kind == 0:
+            obs = env.reset()
+            if i < n_rgb:
+                rgb = env_rgb.reset()
+        elif kind == 2:
+            env.planes[0].copy_(torch.from_numpy(z["grid"][i]).cuda())
+            obs = env.observe()
+        elif kind == 3:
+            env.step(act)
+            assert int(env.err[0].item()) & int(z["err"][i])
+            env.envrec[:, 3] &= 0xFFFF
+            env.agents[0, :, 2] = torch.from_numpy(z["dir"][i].astype(np.uint8)).cuda()
+            continue
+        else:
+            obs, rew, done, _ = env.step(act)
+            assert np.array_equal(rew[0].cpu().numpy().view(np.uint64), z["rew"][i].view(np.uint64)), f"event {i}: reward bits"
+            assert bool(done[0].item()) == bool(z["done"][i]), f"event {i}: done"
+            if i < n_rgb:
+                rgb, rew2, done2, _ = env_rgb.step(act)
+                assert torch.equal(rew2, rew) and torch.equal(done2, done)
+        assert np.array_equal(obs[0].cpu().numpy(), z["enc"][i]), f"event {i}: encoded obs"
+        if i < n_rgb:
+            assert np.array_equal(rgb[0].cpu().numpy(), z["rgb"][i]), f"event {i}: rgb obs"
+        assert np.array_equal(env.planes[0].cpu().numpy(), z["grid"][i]), f"event {i}: planes"
+        ag = env.agents[0].cpu().numpy()
+        fl = z["flags"][i]
+        placed = (fl & 1).astype(bool)
+        assert np.array_equal(ag[:, 3] & 7, fl), f"event {i}: flags"
+        assert np.array_equal(ag[placed, 0], z["x"][i][placed]) and np.array_equal(ag[placed, 1], z["y"][i][placed]), f"event {i}: pos"
+        assert np.array_equal(ag[:, 2], z["dir"][i]) and np.array_equal(ag[:, 4:7], z["carry"][i])
+        stamp = ag[:, 8:12].copy().view(np.int32)[:, 0]
+        assert np.array_equal(rank_from(ag[:, 0], ag[:, 1], placed, stamp), z["rank"][i]), f"event {i}: queue order"
+        assert int(env.step_count[0].item()) == int(z["step_count"][i])
+    assert int(env.err[0].item()) == 0
+
+
+CONFIGS = {
+    "cfg2_3AgentCluttered11x11": ("MarlGrid-3AgentCluttered11x11-v0", 4096, 230),
+    "3AgentCluttered15x15_small": ("MarlGrid-3AgentCluttered15x15-v0", 1000, 230),
+    "4AgentEmpty9x9": ("MarlGrid-4AgentEmpty9x9-v0", 777, 230),
+    "2AgentEmpty9x9_b1": ("MarlGrid-2AgentEmpty9x9-v0", 1, 330),
+    "1AgentCluttered_V5": ("MarlGrid-1AgentCluttered15x15-v0", 333, 230),
+    "Goalcycle": ("Goalcycle-demo-solo-v0", 300, 230),
+}
+
+
+@pytest.mark.parametrize("name", list(CONFIGS))
+def test_batched_lockstep_vs_oracle(oracle, name):
+    """Seeded random rollouts with auto-reset: every output and the whole state, every step."""
+    from marlgrid_b200 import envs
+
+    env_id, B, T = CONFIGS[name]
+    env = envs.make(env_id, num_envs=B, obs_mode="encoded", seed=4242, env_offset=10_000_000_000)
+    ob = oracle.OracleBatch(env.cfg, B, seed=4242, env_offset=10_000_000_000, threads=8)
+    obs = env.reset()
+    ob.reset()
+    assert np.array_equal(obs.cpu().numpy(), ob.obs_encode())
+    _state_equal(env, ob, "reset")
+    rng = np.random.RandomState(1)
+    for t in range(T):
+        act = rng.randint(0, 7, size=(B, env.num_agents)).astype(np.int32)
+        act[rng.rand(B, env.num_agents) < 0.4] = 2
+        obs, rew, done, _ = env.step(torch.from_numpy(act).cuda())
+        o2, r2, d2 = ob.step(act, autoreset=True, with_obs=True)
+        assert np.array_equal(obs.cpu().numpy(), o2), f"step {t}: obs"
+        assert np.array_equal(rew.cpu().numpy().view(np.uint64), r2.view(np.uint64)), f"step {t}: reward bits"
+        assert np.array_equal(done.cpu().numpy(), d2.astype(bool)), f"step {t}: done"
+        if t % 16 == 0 or t == T - 1:
+            _state_equal(env, ob, f"step {t}")
+    assert int(env.episode.min().item()) >= 3
+    assert int(env.err.max().item()) == 0
+
+
+def test_rgb_batched_vs_oracle(oracle):
+    """RGB tile path (config 4 family) against the oracle fed the same atlas."""
+    from marlgrid_b200 import envs
+    from marlgrid_b200.atlas import build_atlas
+
+    B = 257
+    env = envs.make("MarlGrid-4AgentEmpty9x9-v0", num_envs=B, obs_mode="rgb", seed=7)
+    ob = oracle.OracleBatch(env.cfg, B, seed=7, threads=8)
+    atlas = build_atlas([int(c) for c in env.cfg.agent_color[:4]], 8)
+    obs = env.reset()
+    ob.reset()
+    assert np.array_equal(obs.cpu().numpy(), ob.obs_rgb(atlas))
+    rng = np.random.RandomState(2)
+    for t in range(120):
+        act = rng.randint(0, 7, size=(B, 4)).astype(np.int32)
+        act[rng.rand(B, 4) < 0.5] = 2
+        obs, rew, done, _ = env.step(torch.from_numpy(act).cuda())
+        r2, d2 = ob.step(act, autoreset=True)
+        assert np.array_equal(rew.cpu().numpy().view(np.uint64), r2.view(np.uint64))
+        assert np.array_equal(done.cpu().numpy(), d2.astype(bool))
+        if t % 5 == 0:
+            assert np.array_equal(obs.cpu().numpy(), ob.obs_rgb(atlas)), f"step {t}: rgb obs"
+
+
+@pytest.mark.parametrize("ts,V,off", [(5, 7, 1), (11, 5, 0), (8, 3, 0), (4, 8, 1)])
+def test_rgb_generic_tile_sizes(oracle, ts, V, off):
+    """Tile sizes with grid lines (ts >= 11: orientation-indexed atlas) and the byte-wise store path."""
+    from marlgrid_b200.agents import GridAgentInterface
+    from marlgrid_b200.atlas import build_atlas
+    from marlgrid_b200.envs import ClutteredMultiGrid
+
+    B = 65
+    ags = [GridAgentInterface(color=c, view_size=V, view_tile_size=ts, view_offset=off) for c in ("red", "blue", "pink")]
+    env = ClutteredMultiGrid(agents=ags, grid_size=9, n_clutter=6, num_envs=B, obs_mode="rgb", seed=3)
+    ob = oracle.OracleBatch(env.cfg, B, seed=3, threads=4)
+    atlas = build_atlas([int(c) for c in env.cfg.agent_color[:3]], ts)
+    obs = env.reset()
+    ob.reset()
+    assert np.array_equal(obs.cpu().numpy(), ob.obs_rgb(atlas))
+    rng = np.random.RandomState(5)
+    for t in range(40):
+        act = rng.randint(0, 3, size=(B, 3)).astype(np.int32) + (rng.rand(B, 3) < 0.5)
+        act = np.minimum(act, 2).astype(np.int32)
+        obs, _, _, _ = env.step(torch.from_numpy(act).cuda())
+        ob.step(act, autoreset=True)
+        assert np.array_equal(obs.cpu().numpy(), ob.obs_rgb(atlas)), f"step {t}"
+
+
+def test_split_kernels_equal_fused(oracle):
+    """mg_step + mg_obs_encode == mg_step_fused; mg_reset(mask) resets only the masked envs."""
+    from marlgrid_b200 import envs
+
+    B = 500
+    a = envs.make("MarlGrid-3AgentCluttered11x11-v0", num_envs=B, obs_mode="encoded", seed=11)
+    b = envs.make("MarlGrid-3AgentCluttered11x11-v0", num_envs=B, obs_mode="encoded", seed=11)
+    a.reset()
+    b.reset()
+    g = torch.Generator(device="cpu").manual_seed(0)
+    for t in range(130):
+        act = torch.randint(0, 7, (B, 3), generator=g, dtype=torch.int32).cuda()
+        o1, r1, d1, _ = a.step(act)
+        r2, d2 = b.step_only(act)
+        o2 = b.observe()
+        assert torch.equal(o1, o2) and torch.equal(r1, r2) and torch.equal(d1, d2)
+    mask = (torch.arange(B) % 3 == 0).to(torch.uint8).cuda()
+    ep = a.episode.clone()
+    grid = a.grid.clone()
+    a.reset(mask=mask)
+    assert torch.equal(a.episode, ep + mask.int())
+    assert torch.equal(a.grid[mask == 0], grid[mask == 0])
+    assert bool((a.step_count[mask == 1] == 0).all())
+
+
+def test_full_size_properties():
+    """BASELINE config 3 at its full batch (65 536 envs): size-independent properties."""
+    from marlgrid_b200 import envs
+
+    B = 65536
+    env = envs.make("MarlGrid-3AgentCluttered15x15-v0", num_envs=B, obs_mode="encoded", seed=1337)
+    half = envs.make("MarlGrid-3AgentCluttered15x15-v0", num_envs=B // 2, obs_mode="encoded", seed=1337, env_offset=B // 2)
+    obs = env.reset()
+    obs_h = half.reset()
+    assert torch.equal(obs[B // 2:], obs_h)  # sharding invariance: RNG keyed by the global env index
+    t = env.grid_type
+    assert bool((t[:, 0, :] == 8).all() and (t[:, -1, :] == 8).all() and (t[:, :, 0] == 8).all() and (t[:, :, -1] == 8).all())
+    assert bool((t[:, 13, 13] == 4).all())
+    assert bool(((t == 8).sum(dim=(1, 2)) == 56 + 25).all())  # border + n_clutter = int(.15*13*13)
+    assert bool(env.agent_active.all() and env.agent_placed.all())
+    assert bool((obs[:, :, 3, 6, 0] == 13).all())  # every agent sees an agent (itself or the one below it) at its own cell
+    for step in range(105):
+        act = env.random_actions(step)
+        obs, rew, done, _ = env.step(act)
+        obs_h, rew_h, done_h, _ = half.step(act[B // 2:])
+        if step in (0, 50, 99, 100, 104):
+            assert torch.equal(obs[B // 2:], obs_h) and torch.equal(rew[B // 2:], rew_h) and torch.equal(done[B // 2:], done_h)
+            assert bool(((rew == 0) | ((rew > 0.09) & (rew <= 0.991))).all())
+            inactive = ~env.agent_active
+            assert bool((obs[inactive] == 0).all())  # inactive agents observe nothing (base.py:420-425)
+        if step == 99:
+            assert bool(done.all())  # max_steps = 100: every episode ends here at the latest
+    assert int(env.episode.min().item()) == 2 and int(env.err.max().item()) == 0
+    assert bool((env.step_count <= 5).all())
+
+
+def test_error_bits_mirror_reference_exceptions():
+    from marlgrid_b200 import envs
+
+    env = envs.make("MarlGrid-2AgentEmpty9x9-v0", num_envs=40, obs_mode="encoded")
+    env.reset()
+    act = torch.zeros((40, 2), dtype=torch.int32, device="cuda")
+    act[7, 1] = 9
+    env.step(act)
+    assert int(env.err[7].item()) == 1 and int(env.err.sum().item()) == 1
+    with pytest.raises(ValueError):
+        env.check_errors()
+    assert int(env.err.sum().item()) == 0
+
+
+def test_engine_host_buffer_api(cuda_lib, oracle):
+    """mg_engine_*: host buffers in, host buffers out (the e2e path of bench.py)."""
+    from marlgrid_b200 import _lib
+    from marlgrid_b200.config import make_config
+
+    cfg = make_config(15, 15, ["red", "blue", "purple"], n_clutter=25)
+    B = 3000
+    h = ctypes.c_void_p()
+    _lib.check(cuda_lib.mg_engine_create(ctypes.byref(h), ctypes.byref(cfg), B, 0, 1337, 0, 0, None, 0), "mg_engine_create")
+    ob = oracle.OracleBatch(cfg, B, seed=1337, threads=8)
+    obs = np.zeros((B, 3, 7, 7, 3), np.uint8)
+    rew = np.zeros((B, 3), np.float64)
+    done = np.zeros((B,), np.uint8)
+    _lib.check(cuda_lib.mg_engine_reset(h, obs.ctypes.data), "mg_engine_reset")
+    ob.reset()
+    assert np.array_equal(obs, ob.obs_encode())
+    rng = np.random.RandomState(0)
+    for t in range(110):
+        act = rng.randint(0, 7, size=(B, 3)).astype(np.int32)
+        _lib.check(cuda_lib.mg_engine_step(h, act.ctypes.data, obs.ctypes.data, rew.ctypes.data, done.ctypes.data, 1), "mg_engine_step")
+        o2, r2, d2 = ob.step(act, autoreset=True, with_obs=True)
+        assert np.array_equal(obs, o2) and np.array_equal(rew.view(np.uint64), r2.view(np.uint64)) and np.array_equal(done, d2)
+    cuda_lib.mg_engine_destroy(h)
+
+
+def test_checkpoint_resume_is_exact():
+    from marlgrid_b200 import envs
+
+    a = envs.make("MarlGrid-3AgentCluttered11x11-v0", num_envs=300, obs_mode="encoded", seed=5)
+    a.reset()
+    for t in range(37):
+        a.step(a.random_actions(t))
+    sd = a.state_dict()
+    b = envs.make("MarlGrid-3AgentCluttered11x11-v0", num_envs=300, obs_mode="encoded", seed=999)
+    b.load_state_dict(sd)
+    for t in range(37, 160):
+        act = a.random_actions(t)
+        o1, r1, d1, _ = a.step(act)
+        o2, r2, d2, _ = b.step(act)
+        assert torch.equal(o1, o2) and torch.equal(r1, r2) and torch.equal(d1, d2)
+
+
+def test_unbatched_gym_surface():
+    """The reference's single-env surface: lists of per-agent obs, float64 reward array, python bool done."""
+    from marlgrid_b200 import envs
+
+    env = envs.make("MarlGrid-2AgentEmpty9x9-v0").unbatched()
+    obs_list = env.reset()
+    assert len(obs_list) == 2 and tuple(obs_list[0].shape) == (56, 56, 3) and obs_list[0].dtype == torch.uint8
+    obs_list, rew, done, info = env.step([2, 0])
+    assert tuple(rew.shape) == (2,) and rew.dtype == torch.float64 and isinstance(done, bool) and info == {}
+    with pytest.raises(ValueError):
+        env.step([2, 17])
+    with pytest.raises(AssertionError):
+        env.step([2])
