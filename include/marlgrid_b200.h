@@ -64,6 +64,9 @@ enum { MG_A_LEFT = 0, MG_A_RIGHT = 1, MG_A_FORWARD = 2, MG_A_PICKUP = 3, MG_A_DR
 #define MG_AF_PLACED 1u  /* pos is not None: the agent is somewhere in the grid */
 #define MG_AF_ACTIVE 2u  /* GridAgentInterface.active (agents.py:155-159) */
 #define MG_AF_DONE 4u    /* GridAgentInterface.done (base.py:584-585) */
+#define MG_AF_HEAD 128u  /* DERIVED (maintained by the kernels): the agent is the head of its cell's queue, i.e. the
+                            cell object or `static_obj.agents[0]` of the reference (base.py:547-572).  Callers that edit
+                            agent records by hand must keep it consistent (or call mg_reset). */
 
 /* MgConfig.flags */
 #define MG_F_GHOST 1u           /* ghost_mode (base.py:345,541-542,683-684) */

@@ -1,15 +1,19 @@
 // mg_kernels.cu -- batched MarlGrid hot path for B200 (sm_100a): step / reset / egocentric obs kernels.
 //
-// One CTA owns ENVS_PER_CTA = 32 consecutive env instances:
-//   * the envs' three grid planes (one contiguous 32*3*S byte chunk of HBM) are staged into shared
-//     memory by ONE bulk-async copy (cp.async.bulk + mbarrier: the TMA engine, SASS UBLKCP);
-//   * warp 0 runs the sequential part of MultiGridEnv.step (base.py:501-649) with lane == env:
-//     Philox agent order, per-agent action application, stacking stamps, float64 reward, done,
-//     in-kernel auto-reset (Philox rejection sampling, base.py:402-416,690-708);
-//   * then every thread is one agent-view (warp == agent index, lane == env): VxV rotated crop out
-//     of the staged planes, line-of-sight as carry-propagating row masks, sparse encode into a shared
-//     staging tile; the CTA finally streams the staging tile to HBM as 16-byte coalesced stores.
-//   * modified planes (reset / pickup / drop / toggle) go back with a shared->global bulk copy.
+// env.step is two launches on one stream:
+//   1. step_kernel -- one THREAD per env: the sequential part of MultiGridEnv.step (base.py:501-649):
+//      Philox agent order, per-agent action application, stacking stamps, float64 reward, done.  It
+//      touches two cells per agent, so it works in place on global memory at full occupancy.
+//   2. mg_kernel<RESET, OBS> -- one CTA per 32 consecutive envs:
+//      * the envs' three grid planes (one contiguous 32*3*S byte chunk of HBM) are staged into shared
+//        memory by ONE bulk-async copy (cp.async.bulk + mbarrier: the TMA engine, SASS UBLKCP);
+//      * warp 0 (lane == env) regenerates the world of envs whose episode ended (Philox rejection
+//        sampling, base.py:402-416,690-708) directly in shared memory and sends the new planes back
+//        with a shared->global bulk copy;
+//      * every thread is one agent-view: VxV crop gathered along per-thread strides, the reference's
+//        rotation reduced to row-order / bit reversals, line-of-sight as carry-propagating row masks,
+//        sparse encode into a shared staging tile; the CTA finally streams the staging tile to HBM as
+//        16-byte coalesced stores.
 // See DESIGN.md for the layout, the RNG contract and the roofline accounting.
 #include <algorithm>
 #include <atomic>
@@ -48,19 +52,25 @@ struct KP {
 };
 
 // ---------------------------------------------------------------------------------------------
-// warp-0 (lane == env) state: agent records live transposed in shared memory, word w of agent a of
-// env `lane` at s_rec[(a*4+w)*32 + lane]  -> bank == lane, conflict-free under any per-lane a.
+// per-env game state while a thread runs the sequential part of step()/reset():
+// agent records live transposed in shared memory, word w of agent a of the thread's env at
+// rec[(a*4+w)*RS]  (RS = threads sharing the array) -> bank == thread, conflict-free for any per-thread a.
 //   w0 = x | y<<8 | dir<<16 | flags<<24     w1 = carry_type | carry_colour<<8 | carry_state<<16 | bonus<<24
 //   w2 = stamp                               w3 = reserved
+// `tp` is the env's type plane (colour at +S, state at +2S): global memory in the step kernel,
+// shared memory in the reset/observe kernel.
 // ---------------------------------------------------------------------------------------------
+constexpr uint32_t ERR_RESET_PENDING = 0x8000u;  // internal: episode ended, auto-reset owed by the next kernel
+
+template <int RS>
 struct EnvCtx {
   const KP& p;
-  uint32_t* rec;   // s_rec + lane
-  uint8_t* tp;     // this env's type plane in shared memory (colour at +S, state at +2S)
+  uint32_t* rec;
+  uint8_t* tp;
   int sc, ep, tl;  // step_count, episode, lifetime steps
   uint32_t w3;     // lo16 next stamp, hi16 error bits
-  bool dirty;      // planes modified -> write back
-  __device__ __forceinline__ uint32_t& R(int a, int w) { return rec[(a * 4 + w) * 32]; }
+  bool dirty;      // planes modified
+  __device__ __forceinline__ uint32_t& R(int a, int w) { return rec[(a * 4 + w) * RS]; }
   __device__ __forceinline__ void add_err(uint32_t bits) { w3 |= bits << 16; }
   __device__ __forceinline__ uint32_t next_stamp() {
     const uint32_t s = w3 & 0xFFFFu;
@@ -71,7 +81,8 @@ struct EnvCtx {
 
 // placed agent with the smallest stamp on (x, y), -1 if none: the reference's cell object when it is
 // an agent, else `static_obj.agents[0]` (base.py:547-572)
-__device__ __forceinline__ int queue_head(EnvCtx& c, int x, int y) {
+template <int RS>
+__device__ __forceinline__ int queue_head(EnvCtx<RS>& c, int x, int y) {
   int best = -1;
   uint32_t bs = 0;
   const uint32_t key = (uint32_t)x | ((uint32_t)y << 8);
@@ -86,7 +97,8 @@ __device__ __forceinline__ int queue_head(EnvCtx& c, int x, int y) {
 }
 
 // base.py:664-688 try_place_obj (agent >= 0: that agent; else the static triple)
-__device__ __forceinline__ bool try_place(EnvCtx& c, int x, int y, int agent, int type, int colour, int state) {
+template <int RS>
+__device__ __forceinline__ bool try_place(EnvCtx<RS>& c, int x, int y, int agent, int type, int colour, int state) {
   const int idx = x * c.p.H + y;
   const int st = c.tp[idx];
   const bool occupied = queue_head(c, x, y) >= 0;
@@ -108,7 +120,8 @@ __device__ __forceinline__ bool try_place(EnvCtx& c, int x, int y, int agent, in
 }
 
 // base.py:690-708 place_obj(top=(0,0), size=None)
-__device__ __forceinline__ void place_obj(EnvCtx& c, Draws& d, int agent, int type, int colour, int state, int max_tries) {
+template <int RS>
+__device__ __forceinline__ void place_obj(EnvCtx<RS>& c, Draws& d, int agent, int type, int colour, int state, int max_tries) {
   for (int t = 0; t < max_tries; ++t) {
     int x, y;
     d.next(c.p.W, c.p.H, x, y);
@@ -125,8 +138,9 @@ __device__ __forceinline__ Draws make_draws(const KP& p, unsigned long long g, u
   return d;
 }
 
-// base.py:402-416 reset + _gen_grid (empty.py:9-16, cluttered.py:25-36, goalcycle.py:30-51)
-__device__ void env_reset(EnvCtx& c, unsigned long long g) {
+// base.py:402-416 reset + _gen_grid (empty.py:9-16, cluttered.py:25-36, goalcycle.py:30-51); planes in shared memory
+template <int RS>
+__device__ void env_reset(EnvCtx<RS>& c, unsigned long long g) {
   const KP& p = c.p;
   const int W = p.W, H = p.H;
   for (int a = 0; a < p.A; ++a) {  // agents.py:161-170 (dir survives)
@@ -136,7 +150,7 @@ __device__ void env_reset(EnvCtx& c, unsigned long long g) {
   }
   uint32_t* w = reinterpret_cast<uint32_t*>(c.tp);
   for (int i = 0; i < 3 * p.S / 4; ++i) w[i] = 0u;
-  c.w3 &= 0xFFFF0000u;
+  c.w3 &= 0xFFFF0000u & ~(ERR_RESET_PENDING << 16);
   for (int i = 0; i < W; ++i) {  // wall_rect base.py:172-176
     c.tp[i * H] = MG_T_WALL; c.tp[p.S + i * H] = MG_C_WORST;
     c.tp[i * H + H - 1] = MG_T_WALL; c.tp[p.S + i * H + H - 1] = MG_C_WORST;
@@ -165,7 +179,8 @@ __device__ void env_reset(EnvCtx& c, unsigned long long g) {
 }
 
 // BonusTile.get_reward objects.py:180-206
-__device__ __forceinline__ double bonus_get_reward(EnvCtx& c, int a, int bonus_id) {
+template <int RS>
+__device__ __forceinline__ double bonus_get_reward(EnvCtx<RS>& c, int a, int bonus_id) {
   const KP& p = c.p;
   const int n = p.n_bonus;
   uint32_t w1 = c.R(a, 1);
@@ -183,8 +198,22 @@ __device__ __forceinline__ double bonus_get_reward(EnvCtx& c, int a, int bonus_i
   return rew;
 }
 
+// permutation number idx in [0, A!) -> processing order, nibble q of the result = order[q]
+// (Fisher-Yates / Lehmer decode of the contract, oracle/philox.py shuffle_perm)
+__device__ __forceinline__ uint32_t decode_order(uint32_t pidx, int A) {
+  uint32_t order = 0x76543210u;
+  for (int i = A - 1; i >= 1; --i) {
+    const uint32_t j = pidx % (uint32_t)(i + 1);
+    pidx /= (uint32_t)(i + 1);
+    const uint32_t ni = (order >> (4 * i)) & 0xFu, nj = (order >> (4 * j)) & 0xFu;
+    order = (order & ~(0xFu << (4 * i)) & ~(0xFu << (4 * j))) | (nj << (4 * i)) | (ni << (4 * j));
+  }
+  return order;
+}
+
 // base.py:501-649 step without the obs; returns done
-__device__ bool env_step(EnvCtx& c, unsigned long long g, const int32_t* __restrict__ act, double* __restrict__ rew) {
+template <int RS>
+__device__ bool env_step(EnvCtx<RS>& c, unsigned long long g, const int32_t* __restrict__ act, double* __restrict__ rew) {
   const KP& p = c.p;
   const int W = p.W, H = p.H, A = p.A, S = p.S;
   const uint32_t t_life = (uint32_t)c.tl;
@@ -197,18 +226,11 @@ __device__ bool env_step(EnvCtx& c, unsigned long long g, const int32_t* __restr
     }
   }
   c.sc += 1;  // base.py:512
-  // base.py:514-516: one Philox word -> index of the permutation (Lehmer / Fisher-Yates decode)
+  // base.py:514-516: one Philox word -> index of the permutation
   uint32_t fact = 1;
   for (int i = 2; i <= A; ++i) fact *= (uint32_t)i;
   const U4 r = philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), t_life, 0u, (uint32_t)p.seed, (uint32_t)(p.seed >> 32));
-  uint32_t pidx = __umulhi(r.x, fact);
-  uint32_t order = 0x76543210u;  // nibble i = order[i]
-  for (int i = A - 1; i >= 1; --i) {
-    const uint32_t j = pidx % (uint32_t)(i + 1);
-    pidx /= (uint32_t)(i + 1);
-    const uint32_t ni = (order >> (4 * i)) & 0xFu, nj = (order >> (4 * j)) & 0xFu;
-    order = (order & ~(0xFu << (4 * i)) & ~(0xFu << (4 * j))) | (nj << (4 * i)) | (ni << (4 * j));
-  }
+  const uint32_t order = decode_order(__umulhi(r.x, fact), A);
   c.tl += 1;
   for (int q = 0; q < A; ++q) {
     const int a = (int)((order >> (4 * q)) & 0xFu);
@@ -217,64 +239,66 @@ __device__ bool env_step(EnvCtx& c, unsigned long long g, const int32_t* __restr
     uint32_t w0 = c.R(a, 0);
     if ((w0 >> 24) & MG_AF_ACTIVE) {  // base.py:521
       const int cx = (int)(w0 & 0xFFu), cy = (int)((w0 >> 8) & 0xFFu), dir = (int)((w0 >> 16) & 3u);
-      const int fx = cx + ((dir == 0) ? 1 : (dir == 2) ? -1 : 0);  // agents.py:183
-      const int fy = cy + ((dir == 1) ? 1 : (dir == 3) ? -1 : 0);
-      const bool inb = (unsigned)fx < (unsigned)W && (unsigned)fy < (unsigned)H;
-      const int fidx = inb ? fx * H + fy : 0;
-      const int ftype = inb ? (int)c.tp[fidx] : (int)MG_T_WALL;
-      const int fstate = inb ? (int)c.tp[2 * S + fidx] : 0;
-      if (!inb) c.add_err(MG_ERR_STACK);
       if (action == MG_A_LEFT) {  // base.py:530-531
         c.R(a, 0) = (w0 & 0xFF00FFFFu) | ((uint32_t)((dir + 3) & 3) << 16);
       } else if (action == MG_A_RIGHT) {  // base.py:534-535
         c.R(a, 0) = (w0 & 0xFF00FFFFu) | ((uint32_t)((dir + 1) & 3) << 16);
-      } else if (action == MG_A_FORWARD) {  // base.py:538-585
-        const bool f_is_agent = (ftype == MG_T_EMPTY) && (queue_head(c, fx, fy) >= 0);
-        bool can_move = (ftype == MG_T_EMPTY) || can_overlap_static(ftype, fstate);
-        if (!(p.flags & MG_F_GHOST) && f_is_agent) can_move = false;
-        if (can_move) {
-          const int cidx = cx * H + cy;
-          const int ctype = c.tp[cidx];
-          if (ctype != MG_T_EMPTY && !can_overlap_static(ctype, c.tp[2 * S + cidx])) c.add_err(MG_ERR_STACK);  // base.py:558
-          w0 = (w0 & 0xFFFF0000u) | (uint32_t)fx | ((uint32_t)fy << 8);
-          c.R(a, 2) = c.next_stamp();  // appended last to the target cell's queue (base.py:547-552)
-          if (ftype == MG_T_GOAL || ftype == MG_T_BONUS) {  // hasattr(fwd_cell, 'get_reward') base.py:576
-            double rwd = (ftype == MG_T_GOAL) ? p.goal_reward : bonus_get_reward(c, a, fstate);
-            if (p.flags & MG_F_REWARD_DECAY) {  // base.py:579, every operation rounded on its own
-              const double qd = __ddiv_rn((double)c.sc, (double)p.max_steps);
-              const double u = __dmul_rn(0.9, qd);
-              const double f = __dsub_rn(1.0, u);
-              rwd = __dmul_rn(rwd, f);
+      } else if (action >= MG_A_FORWARD && action <= MG_A_TOGGLE) {
+        const int fx = cx + ((dir == 0) ? 1 : (dir == 2) ? -1 : 0);  // agents.py:183
+        const int fy = cy + ((dir == 1) ? 1 : (dir == 3) ? -1 : 0);
+        const bool inb = (unsigned)fx < (unsigned)W && (unsigned)fy < (unsigned)H;
+        const int fidx = inb ? fx * H + fy : 0;
+        const int ftype = inb ? (int)c.tp[fidx] : (int)MG_T_WALL;
+        if (!inb) c.add_err(MG_ERR_STACK);  // grid.get asserts in-bounds (base.py:154-156); never hit with wall_rect
+        if (action == MG_A_FORWARD) {  // base.py:538-585
+          const int fstate = (ftype == MG_T_DOOR || ftype == MG_T_BONUS) ? (int)c.tp[2 * S + fidx] : 0;
+          bool can_move = (ftype == MG_T_EMPTY) || can_overlap_static(ftype, fstate);
+          if (!(p.flags & MG_F_GHOST) && ftype == MG_T_EMPTY && queue_head(c, fx, fy) >= 0) can_move = false;  // fwd_cell is a GridAgent
+          if (can_move) {
+            const int cidx = cx * H + cy;
+            const int ctype = c.tp[cidx];
+            if (ctype != MG_T_EMPTY && !can_overlap_static(ctype, c.tp[2 * S + cidx])) c.add_err(MG_ERR_STACK);  // base.py:558
+            w0 = (w0 & 0xFFFF0000u) | (uint32_t)fx | ((uint32_t)fy << 8);
+            c.R(a, 2) = c.next_stamp();  // appended last to the target cell's queue (base.py:547-552)
+            if (ftype == MG_T_GOAL || ftype == MG_T_BONUS) {  // hasattr(fwd_cell, 'get_reward') base.py:576
+              double rwd = (ftype == MG_T_GOAL) ? p.goal_reward : bonus_get_reward(c, a, fstate);
+              if (p.flags & MG_F_REWARD_DECAY) {  // base.py:579, every operation rounded on its own
+                const double qd = __ddiv_rn((double)c.sc, (double)p.max_steps);
+                const double u = __dmul_rn(0.9, qd);
+                const double f = __dsub_rn(1.0, u);
+                rwd = __dmul_rn(rwd, f);
+              }
+              reward = __dadd_rn(0.0, rwd);  // step_rewards[agent_no] += rwd (base.py:580): 0.0 + (-0.0) is +0.0
             }
-            reward = rwd;
+            if (ftype == MG_T_LAVA || ftype == MG_T_GOAL) w0 |= (uint32_t)MG_AF_DONE << 24;  // base.py:584-585
+            c.R(a, 0) = w0;
           }
-          if (ftype == MG_T_LAVA || ftype == MG_T_GOAL) w0 |= (uint32_t)MG_AF_DONE << 24;  // base.py:584-585
-          c.R(a, 0) = w0;
-        }
-      } else if (action == MG_A_PICKUP) {  // base.py:590-597
-        const uint32_t w1 = c.R(a, 1);
-        if (ftype != MG_T_EMPTY && ((PICKUP_MASK >> ftype) & 1u) && (w1 & 0xFFu) == 0u) {
-          c.R(a, 1) = (w1 & 0xFF000000u) | (uint32_t)ftype | ((uint32_t)c.tp[S + fidx] << 8) | ((uint32_t)fstate << 16);
-          c.tp[fidx] = 0; c.tp[S + fidx] = 0; c.tp[2 * S + fidx] = 0;
-          c.dirty = true;
-        }
-      } else if (action == MG_A_DROP) {  // base.py:600-606
-        const uint32_t w1 = c.R(a, 1);
-        if (inb && ftype == MG_T_EMPTY && (w1 & 0xFFu) != 0u && queue_head(c, fx, fy) < 0) {
-          c.tp[fidx] = (uint8_t)(w1 & 0xFFu); c.tp[S + fidx] = (uint8_t)((w1 >> 8) & 0xFFu); c.tp[2 * S + fidx] = (uint8_t)((w1 >> 16) & 0xFFu);
-          c.R(a, 1) = w1 & 0xFF000000u;
-          c.dirty = true;
-        }
-      } else if (action == MG_A_TOGGLE) {  // base.py:609-613, Door.toggle objects.py:333-346
-        if (ftype == MG_T_DOOR) {
+        } else if (action == MG_A_PICKUP) {  // base.py:590-597
           const uint32_t w1 = c.R(a, 1);
-          int ns = fstate;
-          if (fstate == MG_DOOR_LOCKED) {
-            if ((w1 & 0xFFu) == MG_T_KEY && ((w1 >> 8) & 0xFFu) == c.tp[S + fidx]) ns = MG_DOOR_CLOSED;
-          } else if (fstate == MG_DOOR_CLOSED) ns = MG_DOOR_OPEN;
-          else if (fstate == MG_DOOR_OPEN) ns = MG_DOOR_CLOSED;
-          if (ns != fstate) { c.tp[2 * S + fidx] = (uint8_t)ns; c.dirty = true; }
-        } else if (ftype == MG_T_BOX) c.add_err(MG_ERR_TOGGLE);  // Box.toggle(self) objects.py:381
+          if (ftype != MG_T_EMPTY && ((PICKUP_MASK >> ftype) & 1u) && (w1 & 0xFFu) == 0u) {
+            c.R(a, 1) = (w1 & 0xFF000000u) | (uint32_t)ftype | ((uint32_t)c.tp[S + fidx] << 8) | ((uint32_t)c.tp[2 * S + fidx] << 16);
+            c.tp[fidx] = 0; c.tp[S + fidx] = 0; c.tp[2 * S + fidx] = 0;
+            c.dirty = true;
+          }
+        } else if (action == MG_A_DROP) {  // base.py:600-606
+          const uint32_t w1 = c.R(a, 1);
+          if (inb && ftype == MG_T_EMPTY && (w1 & 0xFFu) != 0u && queue_head(c, fx, fy) < 0) {
+            c.tp[fidx] = (uint8_t)(w1 & 0xFFu); c.tp[S + fidx] = (uint8_t)((w1 >> 8) & 0xFFu); c.tp[2 * S + fidx] = (uint8_t)((w1 >> 16) & 0xFFu);
+            c.R(a, 1) = w1 & 0xFF000000u;
+            c.dirty = true;
+          }
+        } else {  // MG_A_TOGGLE base.py:609-613, Door.toggle objects.py:333-346
+          if (ftype == MG_T_DOOR) {
+            const uint32_t w1 = c.R(a, 1);
+            const int fstate = c.tp[2 * S + fidx];
+            int ns = fstate;
+            if (fstate == MG_DOOR_LOCKED) {
+              if ((w1 & 0xFFu) == MG_T_KEY && ((w1 >> 8) & 0xFFu) == c.tp[S + fidx]) ns = MG_DOOR_CLOSED;
+            } else if (fstate == MG_DOOR_CLOSED) ns = MG_DOOR_OPEN;
+            else if (fstate == MG_DOOR_OPEN) ns = MG_DOOR_CLOSED;
+            if (ns != fstate) { c.tp[2 * S + fidx] = (uint8_t)ns; c.dirty = true; }
+          } else if (ftype == MG_T_BOX) c.add_err(MG_ERR_TOGGLE);  // Box.toggle(self) objects.py:381
+        }
       } else if (action != MG_A_DONE) {
         c.add_err(MG_ERR_BAD_ACTION);  // base.py:619-620
       }
@@ -299,8 +323,10 @@ __device__ bool env_step(EnvCtx& c, unsigned long long g, const int32_t* __restr
   return (c.sc >= p.max_steps) || all_done;  // base.py:649
 }
 
-// mark queue heads (transient bit) for the obs phase
-__device__ __forceinline__ void mark_heads(EnvCtx& c) {
+// queue heads: the flag bit AF_HEAD (record byte +3, bit 7) is DERIVED state kept in the record so the
+// observe kernel needs no per-view O(A^2) search; it is recomputed by whoever moves agents.
+template <int RS>
+__device__ __forceinline__ void mark_heads(EnvCtx<RS>& c) {
   for (int a = 0; a < c.p.A; ++a) {
     const uint32_t w0 = c.R(a, 0);
     bool head = ((w0 >> 24) & MG_AF_PLACED) != 0;
@@ -316,88 +342,152 @@ __device__ __forceinline__ void mark_heads(EnvCtx& c) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// step kernel: one THREAD per env, world state read/written in place in global memory (a step
+// touches two cells per agent; staging the planes would move 100x more bytes).  No grid-wide or
+// block-wide dependency: 64 resident warps per SM hide the latency of the scattered cell reads.
+// ---------------------------------------------------------------------------------------------
+constexpr int STEP_THREADS = 128;
+
+__global__ void __launch_bounds__(STEP_THREADS) step_kernel(const KP p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint32_t* s_rec = reinterpret_cast<uint32_t*>(smem);
+  const long long env = (long long)blockIdx.x * STEP_THREADS + threadIdx.x;
+  if (env >= p.B) return;
+  const int A = p.A;
+  EnvCtx<STEP_THREADS> c{p, s_rec + threadIdx.x, p.grid + env * 3 * p.S, 0, 0, 0, 0u, false};
+  int4* arec = reinterpret_cast<int4*>(p.agents) + env * A;
+  for (int a = 0; a < A; ++a) {
+    const int4 r = arec[a];
+    c.R(a, 0) = (uint32_t)r.x; c.R(a, 1) = (uint32_t)r.y; c.R(a, 2) = (uint32_t)r.z; c.R(a, 3) = (uint32_t)r.w;
+  }
+  const int4 er = reinterpret_cast<const int4*>(p.envrec)[env];
+  c.sc = er.x; c.ep = er.y; c.tl = er.z; c.w3 = (uint32_t)er.w;
+  const unsigned long long g = (unsigned long long)(p.env_offset + env);
+  const bool dn = env_step(c, g, p.actions + env * A, p.rewards + env * A);
+  p.done[env] = dn ? 1 : 0;
+  if (dn && p.autoreset) c.w3 |= ERR_RESET_PENDING << 16;  // the reset+observe kernel regenerates the planes in shared memory
+  mark_heads(c);
+  for (int a = 0; a < A; ++a) arec[a] = make_int4((int)c.R(a, 0), (int)c.R(a, 1), (int)c.R(a, 2), (int)c.R(a, 3));
+  reinterpret_cast<int4*>(p.envrec)[env] = make_int4(c.sc, c.ep, c.tl, (int)c.w3);
+}
+
+// ---------------------------------------------------------------------------------------------
 // egocentric view of one agent (thread == view): gen_obs_grid (base.py:418-451)
+//
+// The VxV crop is gathered in WORLD orientation along per-thread strides: u walks the axis the agent
+// faces along, v the axis across (so that a view row of the reference's rotated grid is a run of v at
+// fixed u).  The reference's rotation (rotate_grid, base.py:67-80, rot_k = dir+1) then reduces to an
+// optional reversal of the row order (dir 0,1) and an optional bit reversal inside rows (dir 1,2):
+//   dir 0: view[a][b] = sub[V-1-b][a]      rows flipped
+//   dir 1: view[a][b] = sub[V-1-a][V-1-b]  rows flipped, bits reversed (u <-> y, v <-> x)
+//   dir 2: view[a][b] = sub[b][V-1-a]      bits reversed
+//   dir 3: view[a][b] = sub[a][b]          (u <-> y, v <-> x)
 // ---------------------------------------------------------------------------------------------
 struct ViewGeom {
-  int ox, oy, sax, say, sbx, sby;  // world = (ox,oy) + a*(sax,say) + b*(sbx,sby)
+  int topX, topY;  // agents.py:237-266 get_view_exts
+  int su, sv;      // byte strides of u and v inside a plane
+  int u0, v0;      // world coordinate of u = 0 / v = 0 along their axes
+  int Lu, Lv;      // axis lengths
+  bool vertical, flip, rev;
 };
 
-// agents.py:237-266 get_view_exts + base.py:67-80 rotate_grid with rot_k = dir+1 (base.py:429-431)
-__device__ __forceinline__ ViewGeom view_geom(int px, int py, int dir, int V, int vo) {
+__device__ __forceinline__ ViewGeom view_geom(int px, int py, int dir, int V, int vo, int W, int H) {
   const int h = V / 2;
   ViewGeom g;
-  if (dir == 0) {        // topX = px - vo, topY = py - h;   view[a][b] = sub[V-1-b][a]
-    g.ox = px - vo + V - 1; g.oy = py - h; g.sax = 0; g.say = 1; g.sbx = -1; g.sby = 0;
-  } else if (dir == 1) { // topX = px - h, topY = py - vo;   view[a][b] = sub[V-1-a][V-1-b]
-    g.ox = px - h + V - 1; g.oy = py - vo + V - 1; g.sax = -1; g.say = 0; g.sbx = 0; g.sby = -1;
-  } else if (dir == 2) { // topX = px-V+1+vo, topY = py - h; view[a][b] = sub[b][V-1-a]
-    g.ox = px - V + 1 + vo; g.oy = py - h + V - 1; g.sax = 0; g.say = -1; g.sbx = 1; g.sby = 0;
-  } else {               // topX = px - h, topY = py-V+1+vo; view[a][b] = sub[a][b]
-    g.ox = px - h; g.oy = py - V + 1 + vo; g.sax = 1; g.say = 0; g.sbx = 0; g.sby = 1;
-  }
+  g.topX = (dir == 0) ? px - vo : (dir == 2) ? px - V + 1 + vo : px - h;
+  g.topY = (dir == 1) ? py - vo : (dir == 3) ? py - V + 1 + vo : py - h;
+  g.vertical = (dir & 1) != 0;
+  g.flip = dir < 2;
+  g.rev = (dir == 1) || (dir == 2);
+  g.su = g.vertical ? 1 : H; g.sv = g.vertical ? H : 1;
+  g.u0 = g.vertical ? g.topY : g.topX; g.v0 = g.vertical ? g.topX : g.topY;
+  g.Lu = g.vertical ? H : W; g.Lv = g.vertical ? W : H;
   return g;
 }
 
-// Gathers the VxV crop of the type plane and returns the visibility / non-empty masks as V-bit rows
-// packed into 64 bits (bit b*V + a).  transparent: base.py:103-106 opacity; vis: agents.py:290-343.
+// visibility and non-empty masks of the view, rows b (bit a), plus the plane offset of view cell (a, b):
+// cell_idx = row_base[b] + a * vstep
 template <int V>
-__device__ __forceinline__ void view_masks(const KP& p, const uint8_t* __restrict__ tp, const ViewGeom& g, int vo,
-                                           unsigned long long& vis, unsigned long long& nonempty) {
-  const int W = p.W, H = p.H, S = p.S;
-  uint32_t T[V], NE[V];
-  // the coordinate driven by a (resp. b) is in range: one compare per row / column instead of per cell
-  uint32_t va = 0, vb = 0;
+struct ViewMasks {
+  uint32_t vis[V], ne[V];
+  int row0, ustep, vstep;  // idx(a, b) = row0 + b*ustep + a*vstep
+};
+
+template <int V>
+__device__ __forceinline__ void view_masks(const KP& p, const uint8_t* __restrict__ tp, const ViewGeom& g, ViewMasks<V>& out) {
+  constexpr uint32_t RM = (1u << V) - 1u;
+  const int S = p.S;
+  // clamped per-axis offsets: every load is in range, out-of-world cells are masked afterwards
+  // (MultiGrid.slice zero-pads: empty, transparent; base.py:132-141)
+  uint32_t valid_u = 0, valid_v = 0;
+  int voff[V];
 #pragma unroll
   for (int i = 0; i < V; ++i) {
-    const int ax = g.ox + i * g.sax, ay = g.oy + i * g.say;  // varies along a (other axis fixed)
-    const bool oka = g.sax != 0 ? ((unsigned)ax < (unsigned)W) : ((unsigned)ay < (unsigned)H);
-    const int bx = g.ox + i * g.sbx, by = g.oy + i * g.sby;
-    const bool okb = g.sbx != 0 ? ((unsigned)bx < (unsigned)W) : ((unsigned)by < (unsigned)H);
-    va |= (oka ? 1u : 0u) << i;
-    vb |= (okb ? 1u : 0u) << i;
+    const int vv = g.v0 + i, uu = g.u0 + i;
+    valid_v |= ((unsigned)vv < (unsigned)g.Lv ? 1u : 0u) << i;
+    valid_u |= ((unsigned)uu < (unsigned)g.Lu ? 1u : 0u) << i;
+    voff[i] = min(max(vv, 0), g.Lv - 1) * g.sv;
   }
-  const int da = g.sax * H + g.say, db = g.sbx * H + g.sby;
-  const int base = g.ox * H + g.oy;
+  uint32_t Tu[V], NEu[V];
+#pragma unroll
+  for (int u = 0; u < V; ++u) {
+    const uint8_t* rowp = tp + min(max(g.u0 + u, 0), g.Lu - 1) * g.su;
+    uint32_t opaque = 0, nonempty = 0, doors = 0;
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      const uint32_t t = rowp[voff[v]];
+      opaque |= (t == MG_T_WALL ? 1u : 0u) << v;
+      nonempty |= (t != MG_T_EMPTY ? 1u : 0u) << v;
+      doors |= (t == MG_T_DOOR ? 1u : 0u) << v;
+    }
+    doors &= valid_v;
+    while (doors) {  // objects.py:330-331: a door hides what is behind it unless open (rare)
+      const int v = __ffs(doors) - 1;
+      doors &= doors - 1;
+      if (rowp[2 * S + (g.v0 + v) * g.sv] != MG_DOOR_OPEN) opaque |= 1u << v;  // v is valid: no clamping needed
+    }
+    const bool urow = (valid_u >> u) & 1u;
+    Tu[u] = urow ? (~opaque | ~valid_v) & RM : RM;
+    NEu[u] = urow ? (nonempty & valid_v) : 0u;
+  }
+  // world rows -> view rows (rotate_grid as flip / bit reversal)
+  uint32_t T[V];
 #pragma unroll
   for (int b = 0; b < V; ++b) {
-    uint32_t t_row = (1u << V) - 1u, ne_row = 0;
-    if ((vb >> b) & 1u) {
-#pragma unroll
-      for (int a = 0; a < V; ++a) {
-        if ((va >> a) & 1u) {
-          const int idx = base + b * db + a * da;
-          const int t = tp[idx];
-          bool opaque = (t == MG_T_WALL);
-          if (t == MG_T_DOOR) opaque = tp[2 * S + idx] != MG_DOOR_OPEN;  // objects.py:330-331
-          if (opaque) t_row &= ~(1u << a);
-          if (t != MG_T_EMPTY) ne_row |= 1u << a;
-        }
-      }
-    }
-    T[b] = t_row; NE[b] = ne_row;
+    uint32_t t = g.flip ? Tu[V - 1 - b] : Tu[b];
+    uint32_t n = g.flip ? NEu[V - 1 - b] : NEu[b];
+    if (g.rev) { t = rev_bits<V>(t); n = rev_bits<V>(n); }
+    T[b] = t; out.ne[b] = n;
   }
-  uint32_t M[V];
   if (p.flags & MG_F_SEE_THROUGH) {  // agents.py:294-295
 #pragma unroll
-    for (int b = 0; b < V; ++b) M[b] = (1u << V) - 1u;
+    for (int b = 0; b < V; ++b) out.vis[b] = RM;
   } else {
-    occlude_rows<V>(T, V / 2, V - 1 - vo, M);  // agents.py:233-234,293
+    occlude_rows<V>(T, V / 2, V - 1 - p.vo, out.vis);  // agents.py:233-234,293
   }
-  vis = 0ull; nonempty = 0ull;
-#pragma unroll
-  for (int b = 0; b < V; ++b) {
-    vis |= (unsigned long long)M[b] << (b * V);
-    nonempty |= (unsigned long long)NE[b] << (b * V);
-  }
+  out.ustep = g.flip ? -g.su : g.su;
+  out.vstep = g.rev ? -g.sv : g.sv;
+  out.row0 = g.topX * p.H + g.topY + (g.flip ? (V - 1) * g.su : 0) + (g.rev ? (V - 1) * g.sv : 0);
+}
+
+// world cell (qx, qy) -> view cell (a, b); false if outside the view
+template <int V>
+__device__ __forceinline__ bool world_to_view(const ViewGeom& g, int qx, int qy, int& a, int& b) {
+  const int sx = qx - g.topX, sy = qy - g.topY;
+  const int u = g.vertical ? sy : sx, v = g.vertical ? sx : sy;
+  if ((unsigned)u >= (unsigned)V || (unsigned)v >= (unsigned)V) return false;
+  b = g.flip ? V - 1 - u : u;
+  a = g.rev ? V - 1 - v : v;
+  return true;
 }
 
 // ---------------------------------------------------------------------------------------------
-// the kernel
-//   STEP: 0 = observe only, 1 = env.step (+ auto-reset), 2 = env.reset (optionally masked)
-//   OBS : 0 = none, 1 = encoded (MultiGrid.encode base.py:196-214), 2 = RGB tiles (base.py:301-331)
-//   TS4 : RGB only: tile rows are whole 32-bit words (ts % 4 == 0) -> 16-byte store path
+// reset + observe kernel (32 envs per CTA, planes staged in shared memory by one bulk-async copy)
+//   RESET: 0 = none, 1 = envs whose step ended the episode (ERR_RESET_PENDING), 2 = explicit (mask or all)
+//   OBS  : 0 = none, 1 = encoded (MultiGrid.encode base.py:196-214), 2 = RGB tiles (base.py:301-331)
+//   TS4  : RGB only: tile rows are whole 32-bit words (ts % 4 == 0) -> 16-byte store path
 // ---------------------------------------------------------------------------------------------
-template <int STEP, int OBS, int V, bool TS4>
+template <int RESET, int OBS, int V, bool TS4>
 __global__ void __launch_bounds__(32 * MG_MAX_AGENTS) mg_kernel(const KP p) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x;
@@ -411,12 +501,14 @@ __global__ void __launch_bounds__(32 * MG_MAX_AGENTS) mg_kernel(const KP p) {
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_rec + A * 4 * 32);
   uint8_t* s_out = reinterpret_cast<uint8_t*>(s_bar + 2);  // 16-byte aligned: 32*3*S, 512*A and 16 are multiples of 16
 
-  if (tid == 0) mbar_init(s_bar, 1);
-  __syncthreads();
-  if (tid == 0) {
-    const uint32_t bytes = (uint32_t)n_valid * 3u * (uint32_t)S;
-    mbar_expect_tx(s_bar, bytes);
-    bulk_g2s(s_grid, p.grid + env0 * 3 * S, bytes, s_bar);
+  if (OBS != 0) {  // a reset regenerates the planes from scratch: only observing needs the old ones
+    if (tid == 0) mbar_init(s_bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+      const uint32_t bytes = (uint32_t)n_valid * 3u * (uint32_t)S;
+      mbar_expect_tx(s_bar, bytes);
+      bulk_g2s(s_grid, p.grid + env0 * 3 * S, bytes, s_bar);
+    }
   }
 
   // ---- shared-memory output areas, prepared while the planes are in flight ----
@@ -443,55 +535,51 @@ __global__ void __launch_bounds__(32 * MG_MAX_AGENTS) mg_kernel(const KP p) {
     }
   }
 
-  // ---- warp 0: lane == env.  sequential game logic ----
+  // ---- warp 0: lane == env: records to shared memory, resets that are due ----
   if (warp == 0) {
     const bool valid = lane < n_valid;
     const long long env = env0 + lane;
-    EnvCtx c{p, s_rec + lane, s_grid + lane * 3 * S, 0, 0, 0, 0u, false};
+    EnvCtx<32> c{p, s_rec + lane, s_grid + lane * 3 * S, 0, 0, 0, 0u, false};
+    bool do_reset = false;
     if (valid) {
       const int4* arec = reinterpret_cast<const int4*>(p.agents) + env * A;
       for (int a = 0; a < A; ++a) {
         const int4 r = arec[a];
         c.R(a, 0) = (uint32_t)r.x; c.R(a, 1) = (uint32_t)r.y; c.R(a, 2) = (uint32_t)r.z; c.R(a, 3) = (uint32_t)r.w;
       }
-      const int4 er = reinterpret_cast<const int4*>(p.envrec)[env];
-      c.sc = er.x; c.ep = er.y; c.tl = er.z; c.w3 = (uint32_t)er.w;
-    }
-    mbar_wait(s_bar, 0);
-    if (valid) {
-      const unsigned long long g = (unsigned long long)(p.env_offset + env);
-      if (STEP == 1) {
-        const bool dn = env_step(c, g, p.actions + env * A, p.rewards + env * A);
-        p.done[env] = dn ? 1 : 0;
-        if (dn && p.autoreset) env_reset(c, g);
-      } else if (STEP == 2) {
-        if (p.reset_mask == nullptr || p.reset_mask[env]) env_reset(c, g);
+      if (RESET != 0) {
+        const int4 er = reinterpret_cast<const int4*>(p.envrec)[env];
+        c.sc = er.x; c.ep = er.y; c.tl = er.z; c.w3 = (uint32_t)er.w;
+        do_reset = (RESET == 1) ? (((c.w3 >> 16) & ERR_RESET_PENDING) != 0) : (p.reset_mask == nullptr || p.reset_mask[env] != 0);
       }
-      if (STEP != 0) {
+    }
+    if (RESET != 0 && __any_sync(0xffffffffu, do_reset)) {
+      if (OBS != 0) mbar_wait(s_bar, 0);  // the incoming copy must land before the planes are rewritten
+      if (do_reset) {
+        env_reset(c, (unsigned long long)(p.env_offset + env));
+        mark_heads(c);
         int4* arec = reinterpret_cast<int4*>(p.agents) + env * A;
-        for (int a = 0; a < A; ++a)
-          arec[a] = make_int4((int)(c.R(a, 0) & ~(AF_HEAD << 24)), (int)c.R(a, 1), (int)c.R(a, 2), (int)c.R(a, 3));
+        for (int a = 0; a < A; ++a) arec[a] = make_int4((int)c.R(a, 0), (int)c.R(a, 1), (int)c.R(a, 2), (int)c.R(a, 3));
         reinterpret_cast<int4*>(p.envrec)[env] = make_int4(c.sc, c.ep, c.tl, (int)c.w3);
-        if (c.dirty) {  // planes changed (reset / pickup / drop / toggle): shared -> global bulk copy
-          fence_proxy_async_smem();
-          bulk_s2g(p.grid + env * 3 * S, c.tp, 3u * (uint32_t)S);
-          bulk_commit();
-        }
+        fence_proxy_async_smem();  // regenerated planes: shared -> global bulk copy
+        bulk_s2g(p.grid + env * 3 * S, c.tp, 3u * (uint32_t)S);
+        bulk_commit();
       }
-      if (OBS != 0) mark_heads(c);
     }
-  } else {
-    mbar_wait(s_bar, 0);
   }
+  if (OBS == 0) {
+    if (RESET != 0 && warp == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    return;
+  }
+  mbar_wait(s_bar, 0);
   __syncthreads();
 
-  // ---- every thread: one agent view (warp == agent, lane == env) ----
-  if (OBS != 0 && warp < A && lane < n_valid) {
-    const int a = warp;
-    const uint32_t* rec = s_rec + lane;
-    const uint8_t* tp = s_grid + lane * 3 * S;
+  // ---- every thread: one agent view ----
+  if (tid < n_valid * A) {
+    const int view = tid, le = view / A, a = view - le * A;
+    const uint32_t* rec = s_rec + le;
+    const uint8_t* tp = s_grid + le * 3 * S;
     const uint32_t w0 = rec[(a * 4) * 32];
-    const int view = lane * A + a;
     const bool active = ((w0 >> 24) & MG_AF_ACTIVE) != 0;  // base.py:420-425
     const int px = (int)(w0 & 0xFFu), py = (int)((w0 >> 8) & 0xFFu), dir = (int)((w0 >> 16) & 3u);
     const int orient = (3 - dir) & 3;  // view orientation (0 - rot_k) % 4, base.py:130
@@ -503,56 +591,64 @@ __global__ void __launch_bounds__(32 * MG_MAX_AGENTS) mg_kernel(const KP p) {
       }
     }
     if (active) {
-      const ViewGeom g = view_geom(px, py, dir, V, p.vo);
-      unsigned long long vis, ne;
-      view_masks<V>(p, tp, g, p.vo, vis, ne);
-      const int H = p.H, W = p.W;
-      const int da = g.sax * H + g.say, db = g.sbx * H + g.sby, base = g.ox * H + g.oy;
+      const ViewGeom g = view_geom(px, py, dir, V, p.vo, p.W, p.H);
+      ViewMasks<V> vm;
+      view_masks<V>(p, tp, g, vm);
       if (OBS == 1) {
         uint8_t* out = s_out + view * (VV * 3);
-        unsigned long long m = vis & ne;
-        while (m) {  // visible non-empty cells: WorldObj.encode objects.py:90-99
-          const int bit = __ffsll((long long)m) - 1;
-          m &= m - 1;
-          const int vb = bit / V, va = bit - vb * V;
-          const int idx = base + vb * db + va * da;
-          uint8_t* o = out + (va * V + vb) * 3;
-          o[0] = tp[idx]; o[1] = tp[S + idx]; o[2] = tp[2 * S + idx];
+#pragma unroll
+        for (int b = 0; b < V; ++b) {  // visible non-empty cells: WorldObj.encode objects.py:90-99
+          uint32_t m = vm.vis[b] & vm.ne[b];
+          const uint8_t* rowp = tp + vm.row0 + b * vm.ustep;
+          while (m) {
+            const int va = __ffs(m) - 1;
+            m &= m - 1;
+            const uint8_t* cp = rowp + va * vm.vstep;
+            uint8_t* o = out + va * (V * 3) + b * 3;
+            o[0] = cp[0]; o[1] = cp[S]; o[2] = cp[2 * S];
+          }
         }
         for (int q = 0; q < A; ++q) {  // agents that are their cell's object: (13, colour, dir)
           const uint32_t v0 = rec[(q * 4) * 32];
           if (!((v0 >> 24) & AF_HEAD)) continue;
-          const int qx = (int)(v0 & 0xFFu) - g.ox, qy = (int)((v0 >> 8) & 0xFFu) - g.oy;
-          const int va = qx * g.sax + qy * g.say, vb = qx * g.sbx + qy * g.sby;
-          if ((unsigned)va >= (unsigned)V || (unsigned)vb >= (unsigned)V) continue;
-          const int bit = vb * V + va;
-          if (!((vis >> bit) & 1ull) || ((ne >> bit) & 1ull)) continue;
-          uint8_t* o = out + (va * V + vb) * 3;
+          int va, vb;
+          if (!world_to_view<V>(g, (int)(v0 & 0xFFu), (int)((v0 >> 8) & 0xFFu), va, vb)) continue;
+          uint32_t visb = 0, neb = 0;
+#pragma unroll
+          for (int b = 0; b < V; ++b) { if (b == vb) { visb = vm.vis[b]; neb = vm.ne[b]; } }
+          if (!((visb >> va) & 1u) || ((neb >> va) & 1u)) continue;
+          uint8_t* o = out + va * (V * 3) + vb * 3;
           o[0] = MG_T_AGENT; o[1] = p.agent_color[q]; o[2] = (uint8_t)((v0 >> 16) & 3u);
         }
       } else {  // OBS == 2: tile ids, render_tile base.py:275-299
         const int per_kind = 1 + 4 * A;
         uint8_t* tl = s_tile + view * VV;
         uint32_t bad = 0;
-        for (int bit = 0; bit < VV; ++bit) {
-          const int vb = bit / V, va = bit - vb * V;
-          uint8_t t = (uint8_t)p.n_tiles;  // shadow
-          if ((vis >> bit) & 1ull) {
-            t = 0;
-            if ((ne >> bit) & 1ull) {
-              const int kind = p.kind_of_type[tp[base + vb * db + va * da]];
-              if (kind == 0xFF) bad = 1; else t = (uint8_t)(kind * per_kind);
+#pragma unroll
+        for (int b = 0; b < V; ++b) {
+          const uint8_t* rowp = tp + vm.row0 + b * vm.ustep;
+#pragma unroll
+          for (int va = 0; va < V; ++va) {
+            uint8_t t = (uint8_t)p.n_tiles;  // shadow
+            if ((vm.vis[b] >> va) & 1u) {
+              t = 0;
+              if ((vm.ne[b] >> va) & 1u) {
+                const int kind = p.kind_of_type[rowp[va * vm.vstep]];
+                if (kind == 0xFF) bad = 1; else t = (uint8_t)(kind * per_kind);
+              }
             }
+            tl[b * V + va] = t;
           }
-          tl[vb * V + va] = t;
         }
         for (int q = 0; q < A; ++q) {
           const uint32_t v0 = rec[(q * 4) * 32];
           if (!((v0 >> 24) & AF_HEAD)) continue;
-          const int qx = (int)(v0 & 0xFFu) - g.ox, qy = (int)((v0 >> 8) & 0xFFu) - g.oy;
-          const int va = qx * g.sax + qy * g.say, vb = qx * g.sbx + qy * g.sby;
-          if ((unsigned)va >= (unsigned)V || (unsigned)vb >= (unsigned)V) continue;
-          if (!((vis >> (vb * V + va)) & 1ull)) continue;
+          int va, vb;
+          if (!world_to_view<V>(g, (int)(v0 & 0xFFu), (int)((v0 >> 8) & 0xFFu), va, vb)) continue;
+          uint32_t visb = 0;
+#pragma unroll
+          for (int b = 0; b < V; ++b) { if (b == vb) visb = vm.vis[b]; }
+          if (!((visb >> va) & 1u)) continue;
           // top_agent if it stands on this cell, else the queue head (base.py:282-293)
           const bool mine = ((v0 ^ w0) & 0xFFFFu) == 0u;
           const int qq = mine ? a : q;
@@ -560,7 +656,7 @@ __global__ void __launch_bounds__(32 * MG_MAX_AGENTS) mg_kernel(const KP p) {
           const int slot_dir = (p.orient_slots == 4) ? qd : ((qd + orient) & 3);
           tl[vb * V + va] = (uint8_t)(tl[vb * V + va] + 1 + 4 * qq + slot_dir);
         }
-        if (bad) atomicOr(reinterpret_cast<unsigned int*>(p.envrec) + (env0 + lane) * 4 + 3, (unsigned int)MG_ERR_RENDER << 16);
+        if (bad) atomicOr(reinterpret_cast<unsigned int*>(p.envrec) + (env0 + le) * 4 + 3, (unsigned int)MG_ERR_RENDER << 16);
       }
     }
   }
@@ -616,7 +712,7 @@ __global__ void __launch_bounds__(32 * MG_MAX_AGENTS) mg_kernel(const KP p) {
       }
     }
   }
-  if (STEP != 0 && warp == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  if (RESET != 0 && warp == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 // zero-initialised family of freshly constructed envs (bonus_state = None)
@@ -709,10 +805,10 @@ static size_t smem_bytes(const KP& p, int obs) {
   return (b + 15) / 16 * 16;
 }
 
-template <int STEP, int OBS, int V, bool TS4>
+template <int RESET, int OBS, int V, bool TS4>
 static int launch_one(const KP& p, cudaStream_t s) {
   const size_t sm = smem_bytes(p, OBS);
-  auto k = mg_kernel<STEP, OBS, V, TS4>;
+  auto k = mg_kernel<RESET, OBS, V, TS4>;
   static size_t configured[64] = {0};  // per instantiation and device
   int dev = 0;
   cudaGetDevice(&dev);
@@ -729,25 +825,43 @@ static int launch_one(const KP& p, cudaStream_t s) {
   return (int)cudaGetLastError();
 }
 
-template <int STEP, int OBS, bool TS4>
+template <int RESET, int OBS, bool TS4>
 static int launch_v(const KP& p, cudaStream_t s) {
   switch (p.V) {
-    case 3: return launch_one<STEP, OBS, 3, TS4>(p, s);
-    case 4: return launch_one<STEP, OBS, 4, TS4>(p, s);
-    case 5: return launch_one<STEP, OBS, 5, TS4>(p, s);
-    case 6: return launch_one<STEP, OBS, 6, TS4>(p, s);
-    case 7: return launch_one<STEP, OBS, 7, TS4>(p, s);
-    case 8: return launch_one<STEP, OBS, 8, TS4>(p, s);
+    case 3: return launch_one<RESET, OBS, 3, TS4>(p, s);
+    case 4: return launch_one<RESET, OBS, 4, TS4>(p, s);
+    case 5: return launch_one<RESET, OBS, 5, TS4>(p, s);
+    case 6: return launch_one<RESET, OBS, 6, TS4>(p, s);
+    case 7: return launch_one<RESET, OBS, 7, TS4>(p, s);
+    case 8: return launch_one<RESET, OBS, 8, TS4>(p, s);
   }
   return MG_E_CONFIG;
 }
 
-template <int STEP>
-static int launch(const KP& p, int obs, cudaStream_t s) {
-  if (obs == 0) return launch_one<STEP, 0, 7, false>(p, s);
-  if (obs == 1) return launch_v<STEP, 1, false>(p, s);
-  if (p.ts % 4 == 0) return launch_v<STEP, 2, true>(p, s);
-  return launch_v<STEP, 2, false>(p, s);
+// reset (RESET: 0 none / 1 pending / 2 explicit) and/or observe (obs: 0 none / 1 encoded / 2 rgb)
+template <int RESET>
+static int launch_obs(const KP& p, int obs, cudaStream_t s) {
+  if (obs == 0) return launch_one<RESET, 0, 7, false>(p, s);
+  if (obs == 1) return launch_v<RESET, 1, false>(p, s);
+  if (p.ts % 4 == 0) return launch_v<RESET, 2, true>(p, s);
+  return launch_v<RESET, 2, false>(p, s);
+}
+
+static int launch_step(const KP& p, cudaStream_t s) {
+  const long long blocks = (p.B + STEP_THREADS - 1) / STEP_THREADS;
+  if (blocks <= 0) return 0;
+  step_kernel<<<(unsigned)blocks, STEP_THREADS, (size_t)STEP_THREADS * p.A * 16, s>>>(p);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return (int)cudaGetLastError();
+}
+
+// env.step: the step kernel, then (auto-reset and/or observation) in one more launch
+static int launch_step_obs(const KP& p, int obs, cudaStream_t s) {
+  int e = launch_step(p, s);
+  if (e) return e;
+  if (p.autoreset) return launch_obs<1>(p, obs, s);
+  if (obs != 0) return launch_obs<0>(p, obs, s);
+  return 0;
 }
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
@@ -788,7 +902,7 @@ int mg_reset(const MgConfig* cfg, const MgState* st, const uint8_t* reset_mask, 
   if (e) return e;
   KP p = make_kp(cfg, st);
   p.reset_mask = reset_mask;
-  return launch<2>(p, 0, (cudaStream_t)stream);
+  return launch_obs<2>(p, 0, (cudaStream_t)stream);
 }
 
 int mg_step(const MgConfig* cfg, const MgState* st, const int32_t* actions, double* rewards, uint8_t* done, int autoreset,
@@ -798,7 +912,7 @@ int mg_step(const MgConfig* cfg, const MgState* st, const int32_t* actions, doub
   if (!actions || !rewards || !done) return MG_E_ARG;
   KP p = make_kp(cfg, st);
   p.actions = actions; p.rewards = rewards; p.done = done; p.autoreset = autoreset;
-  return launch<1>(p, 0, (cudaStream_t)stream);
+  return launch_step_obs(p, 0, (cudaStream_t)stream);
 }
 
 int mg_obs_encode(const MgConfig* cfg, const MgState* st, uint8_t* obs, mg_stream_t stream) {
@@ -807,7 +921,7 @@ int mg_obs_encode(const MgConfig* cfg, const MgState* st, uint8_t* obs, mg_strea
   if (!obs || !aligned16(obs)) return MG_E_ARG;
   KP p = make_kp(cfg, st);
   p.obs = obs;
-  return launch<0>(p, 1, (cudaStream_t)stream);
+  return launch_obs<0>(p, 1, (cudaStream_t)stream);
 }
 
 static int atlas_mode(const MgConfig* cfg) { return (cfg->view_tile_size <= 10) ? 1 : 4; }  // empty_tile alpha == 0 (base.py:247): rotation-equivariant
@@ -818,7 +932,7 @@ int mg_obs_rgb(const MgConfig* cfg, const MgState* st, const uint8_t* atlas, uin
   if (!obs || !atlas || !aligned16(obs) || cfg->view_tile_size < 1) return MG_E_ARG;
   KP p = make_kp(cfg, st);
   p.obs = obs; p.atlas = atlas; p.orient_slots = atlas_mode(cfg);
-  return launch<0>(p, 2, (cudaStream_t)stream);
+  return launch_obs<0>(p, 2, (cudaStream_t)stream);
 }
 
 int mg_step_fused(const MgConfig* cfg, const MgState* st, const int32_t* actions, double* rewards, uint8_t* done, uint8_t* obs,
@@ -828,7 +942,7 @@ int mg_step_fused(const MgConfig* cfg, const MgState* st, const int32_t* actions
   if (!actions || !rewards || !done || !obs || !aligned16(obs)) return MG_E_ARG;
   KP p = make_kp(cfg, st);
   p.actions = actions; p.rewards = rewards; p.done = done; p.obs = obs; p.autoreset = autoreset;
-  return launch<1>(p, 1, (cudaStream_t)stream);
+  return launch_step_obs(p, 1, (cudaStream_t)stream);
 }
 
 int mg_step_fused_rgb(const MgConfig* cfg, const MgState* st, const int32_t* actions, double* rewards, uint8_t* done,
@@ -839,7 +953,7 @@ int mg_step_fused_rgb(const MgConfig* cfg, const MgState* st, const int32_t* act
   KP p = make_kp(cfg, st);
   p.actions = actions; p.rewards = rewards; p.done = done; p.obs = obs; p.atlas = atlas; p.autoreset = autoreset;
   p.orient_slots = atlas_mode(cfg);
-  return launch<1>(p, 2, (cudaStream_t)stream);
+  return launch_step_obs(p, 2, (cudaStream_t)stream);
 }
 
 int mg_rollout_fused(const MgConfig* cfg, const MgState* st, const int32_t* actions, int64_t n_steps, double* rewards, uint8_t* done,
@@ -851,7 +965,7 @@ int mg_rollout_fused(const MgConfig* cfg, const MgState* st, const int32_t* acti
   p.rewards = rewards; p.done = done; p.obs = obs; p.autoreset = autoreset;
   for (int64_t t = 0; t < n_steps; ++t) {
     p.actions = actions + t * st->n_envs * cfg->n_agents;
-    e = launch<1>(p, 1, (cudaStream_t)stream);
+    e = launch_step_obs(p, 1, (cudaStream_t)stream);
     if (e) return e;
   }
   return 0;

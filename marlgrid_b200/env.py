@@ -221,7 +221,8 @@ class BatchedMultiGridEnv:
 
     @property
     def agent_flags(self):
-        return self.agents[:, :, 3]
+        """MG_AF_* bits (bit 7 of the stored byte is device-derived queue-head state and is masked off)."""
+        return self.agents[:, :, 3] & 0x7F
 
     @property
     def agent_placed(self):
