@@ -28,7 +28,8 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 ENV_ID = "MarlGrid-3AgentCluttered15x15-v0"
-ALGO_BYTES_PER_ENV_STEP = 1272  # 743 read + 522 write + 7 amortised reset
+ALGO_BYTES_PER_ENV_STEP = 1272  # 743 read + 522 write + 7 amortised reset (whole env.step)
+ALGO_BYTES_OBS_KERNEL = 1164    # SURVEY.md 8(d) obs-kernel-only figure: read 3*W*H + 16*A = 723, write obs 441
 FALLBACK_HBM_GBS = 6650.0       # /opt/skills/guides/B200_PROFILING.md fallback
 
 
@@ -92,25 +93,27 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_port_throughput(n_envs, n_steps, threads, seed=1337):
-    """The oracle (CPU port of the reference algorithm) on a bounded sample of the same workload."""
+def cpu_port_throughput(n_envs, threads, target_s=12.0, seed=1337):
+    """The oracle (CPU port of the reference algorithm, oracle/mg_oracle.c) on a bounded sample of the same
+    workload: n_envs envs, as many steps as fit ~target_s seconds (probed first), all `threads` host threads."""
     import numpy as np
 
-    from marlgrid_b200 import envs  # config only; constructing an env would need the GPU
     from marlgrid_b200.config import GOAL_FIXED, make_config
     from oracle import mg_oracle
 
-    del envs
     cfg = make_config(15, 15, ["red", "blue", "purple"], view_size=7, view_tile_size=8, n_clutter=int(0.15 * 13 * 13), goal_mode=GOAL_FIXED)
     ob = mg_oracle.OracleBatch(cfg, n_envs, seed=seed, threads=threads)
     ob.reset()
     rng = np.random.RandomState(0)
-    act = rng.randint(0, 7, size=(n_steps, n_envs, 3)).astype(np.int32)
-    ob.rollout(act[:2])  # warm-up
+    act = rng.randint(0, 7, size=(16, n_envs, 3)).astype(np.int32)
     t0 = time.perf_counter()
-    ob.rollout(act)
+    ob.rollout(act, n_steps=20)  # warm-up + probe
+    probe = (time.perf_counter() - t0) / 20
+    n_steps = int(min(5000, max(100, target_s / max(probe, 1e-6))))
+    t0 = time.perf_counter()
+    ob.rollout(act, n_steps=n_steps)
     dt = time.perf_counter() - t0
-    return n_envs * n_steps / dt, dt
+    return n_envs * n_steps / dt, dt, n_steps
 
 
 def host_threads():
@@ -125,18 +128,10 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     threads = host_threads()
-    n_envs = 8192
-    n_steps_per = 100  # one bench "step" of this arm = one env.step over the 8 192-env sample
-    vals = []
-    for _ in range(max(1, args.warmup // 100)):
-        cpu_port_throughput(n_envs, 10, threads)
-    reps = max(1, min(5, args.steps // 100))
-    for _ in range(reps):
-        v, dt = cpu_port_throughput(n_envs, n_steps_per, threads)
-        vals.append(v)
-    vals.sort()
-    v = vals[len(vals) // 2]
-    sample = f"{n_envs} envs x {n_steps_per} steps x {reps} reps (median), C port of the reference step+reset+encode, {threads} threads"
+    n_envs = 65536 if threads >= 32 else 8192  # a bench "step" of this arm = one env.step over this sample of the batch
+    v, dt, n_steps = cpu_port_throughput(n_envs, threads, target_s=20.0)
+    sample = (f"{n_envs} envs x {n_steps} steps ({dt:.1f} s) of the same workload, C port of the reference step+reset+encode "
+              f"(oracle/mg_oracle.c), {threads} threads")
     line = {
         "impl": "reference", "metric": "env-steps/s", "value": v, "unit": "env-steps/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * n_envs / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -176,6 +171,8 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
+
+    import ctypes
 
     import numpy as np
     import torch
@@ -220,18 +217,25 @@ def main():
     # ---- timed: K cold steps (L2 flushed before each), per-step events ---------------------------
     launches0 = L.mg_launch_count()
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    mids = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     stops = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    for ev in mids:
+        ev.record()  # materialise the cudaEvent_t handles handed to the library below
     barrier()
     wall0 = time.perf_counter()
     for t in range(K):
         flush.fill_(t & 0xFF)
+        L.mg_debug_set_mid_event(ctypes.c_void_p(mids[t].cuda_event))
         starts[t].record()
         env.step(actions[(W + t) % POOL])
         stops[t].record()
+    L.mg_debug_set_mid_event(None)
     barrier()
     wall_cold = time.perf_counter() - wall0
     launches = L.mg_launch_count() - launches0
     cold_ms = [s.elapsed_time(e) for s, e in zip(starts, stops)]
+    obs_kernel_ms = [m.elapsed_time(e) for m, e in zip(mids, stops)]
+    step_kernel_ms = [s.elapsed_time(m) for s, m in zip(starts, mids)]
     cold_total_ms = float(sum(cold_ms))
 
     # ---- timed: K warm steps back to back (one event pair), launched from the C rollout loop ----
@@ -249,8 +253,6 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- e2e: host buffers through the C ABI engine ----------------------------------------------
-    import ctypes
-
     h = ctypes.c_void_p()
     _lib.check(L.mg_engine_create(ctypes.byref(h), ctypes.byref(env.cfg), B, rank * B, 1337, local_rank, 0, None, 0), "mg_engine_create")
     obs_bytes, rew_bytes, act_bytes = B * A * 147, B * A * 8, B * A * 4
@@ -285,8 +287,10 @@ def main():
         warm_value = world * B * K / (warm_total_ms * 1e-3)
         e2e_value = world * B * KE / (e2e_ms * 1e-3)
         srt = sorted(cold_ms)
-        avg_launch_s = (sum(cold_ms) / K) * 1e-3
-        achieved = ALGO_BYTES_PER_ENV_STEP * B / avg_launch_s / 1e9
+        avg_step_s = (sum(cold_ms) / K) * 1e-3
+        avg_obs_s = (sum(obs_kernel_ms) / K) * 1e-3
+        achieved = ALGO_BYTES_OBS_KERNEL * B / avg_obs_s / 1e9
+        achieved_step = ALGO_BYTES_PER_ENV_STEP * B / avg_step_s / 1e9
         traffic = None
         try:
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
@@ -294,11 +298,12 @@ def main():
         except Exception:  # noqa: BLE001
             pass
         cpu = None
-        if not args.no_cpu_baseline and world >= 1:
+        if not args.no_cpu_baseline and world == 1:
             thr = host_threads()
-            v, dt = cpu_port_throughput(8192, 200, thr)
+            n_envs = 65536 if thr >= 32 else 8192
+            v, dt, n_steps = cpu_port_throughput(n_envs, thr, target_s=12.0)
             cpu = {"value": v, "unit": "env-steps/s", "cores": thr, "kind": "port",
-                   "sample": f"8192 envs x 200 steps of the same workload ({dt:.1f} s), C port of the reference step+reset+encode (oracle/mg_oracle.c)"}
+                   "sample": f"{n_envs} envs x {n_steps} steps of the same workload ({dt:.1f} s), C port of the reference step+reset+encode (oracle/mg_oracle.c)"}
         line = {
             "metric": "env-steps/s", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": cold_total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
@@ -310,8 +315,11 @@ def main():
                     "steps": KE, "api": "mg_engine_step (C ABI, pinned host buffers, synchronous)", "checksum": e2e_checksum},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "kernel": "mg_kernel<1,1,7> (fused step+autoreset+encode)", "algorithmic_bytes_per_launch": ALGO_BYTES_PER_ENV_STEP * B,
-                         "peak_source": peak_src},
+                         "kernel": "mg_kernel<RESET=1,OBS=1,V=7> (auto-reset + egocentric encode; the dominant launch of a step)",
+                         "algorithmic_bytes_per_launch": ALGO_BYTES_OBS_KERNEL * B, "avg_launch_ms": avg_obs_s * 1e3,
+                         "peak_source": peak_src,
+                         "whole_step": {"achieved": achieved_step, "frac": achieved_step / peak, "algorithmic_bytes": ALGO_BYTES_PER_ENV_STEP * B,
+                                        "avg_ms": avg_step_s * 1e3, "step_kernel_avg_ms": sum(step_kernel_ms) / K}},
             "cpu_baseline": cpu,
             "clocks": clocks,
             "wall_s": {"cold_loop": wall_cold},

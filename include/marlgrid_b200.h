@@ -119,6 +119,11 @@ typedef struct MgState {
   uint8_t* grid;    /* [B][3][S] */
   uint8_t* agents;  /* [B][A][16] */
   int32_t* envrec;  /* [B][4] */
+  uint32_t* cellbits; /* [B][32] DERIVED occupancy bitboards, or NULL (then, and for grids wider/taller than 16, the
+                         observe kernel gathers bytes instead).  word x (0..15): row x, bit y = cell (x,y) is opaque
+                         (Wall, or Door not open), bit 16+y = non-empty; word 16+y: column y, bit x / 16+x likewise.
+                         Maintained by mg_reset / mg_step*; after editing planes or agent records by hand call
+                         mg_sync_derived. */
   int64_t n_envs;   /* B (envs on THIS device) */
   int64_t env_offset; /* global index of local env 0 (RNG is keyed by the global index) */
   uint64_t seed;
@@ -138,6 +143,9 @@ int64_t mg_obs_bytes_per_env(const MgConfig* cfg, int rgb);
 /* Zero-initialise state as a freshly constructed env family (all agents unplaced, dir 0,
  * episode 0).  Replaces MultiGridEnv.__init__ state setup (base.py:353-367, agents.py:90). */
 int mg_init(const MgConfig* cfg, const MgState* st, mg_stream_t stream);
+
+/* Recompute the derived state (MgState.cellbits, MG_AF_HEAD flags) from the planes and agent records. */
+int mg_sync_derived(const MgConfig* cfg, const MgState* st, mg_stream_t stream);
 
 /* Start a new episode in every env (reset_mask == NULL) or in envs whose mask byte != 0.
  * Replaces MultiGridEnv.reset (base.py:402-416) + _gen_grid (empty.py:9-16, cluttered.py:25-36,
@@ -160,11 +168,12 @@ int mg_obs_encode(const MgConfig* cfg, const MgState* st, uint8_t* obs, mg_strea
  * atlas: uint8 [n_tiles][4][ts][ts][3], n_tiles = (n_static_kinds+1)*(1+4A). */
 int mg_obs_rgb(const MgConfig* cfg, const MgState* st, const uint8_t* atlas, uint8_t* obs, mg_stream_t stream);
 
-/* step + autoreset + encoded obs in ONE launch (the benchmarked hot path). */
+/* step + autoreset + encoded obs in one call = two launches on `stream`: the step kernel (one thread per env),
+ * then the reset+observe kernel (the benchmarked hot path). */
 int mg_step_fused(const MgConfig* cfg, const MgState* st, const int32_t* actions, double* rewards,
                   uint8_t* done, uint8_t* obs, int autoreset, mg_stream_t stream);
 
-/* step + autoreset + RGB obs in one launch. */
+/* step + autoreset + RGB obs in one call (step kernel, then reset+render kernel). */
 int mg_step_fused_rgb(const MgConfig* cfg, const MgState* st, const int32_t* actions, double* rewards,
                       uint8_t* done, const uint8_t* atlas, uint8_t* obs, int autoreset, mg_stream_t stream);
 
@@ -202,6 +211,9 @@ void* mg_host_alloc(int64_t bytes);
 void mg_host_free(void* p);
 /* Counters: kernels launched by this library since load (bench.py's gpu_launches). */
 int64_t mg_launch_count(void);
+/* Profiling hook (bench.py): a cudaEvent_t recorded between the step kernel and the reset+observe kernel
+ * of every following mg_step* call, so each kernel's duration can be read live; NULL disables it. */
+void mg_debug_set_mid_event(void* cuda_event);
 
 #ifdef __cplusplus
 }

@@ -11,10 +11,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libmarlgrid_b200.so")
 
 EXPORTS = (
-    "mg_version", "mg_build_info", "mg_sizeof_config", "mg_config_validate", "mg_obs_bytes_per_env", "mg_init", "mg_reset", "mg_step",
+    "mg_version", "mg_build_info", "mg_sizeof_config", "mg_config_validate", "mg_obs_bytes_per_env", "mg_init", "mg_sync_derived", "mg_reset", "mg_step",
     "mg_obs_encode", "mg_obs_rgb", "mg_step_fused", "mg_step_fused_rgb", "mg_rollout_fused", "mg_random_actions",
     "mg_los_batch", "mg_engine_create", "mg_engine_destroy", "mg_engine_reset", "mg_engine_step", "mg_host_alloc",
-    "mg_host_free", "mg_launch_count",
+    "mg_host_free", "mg_launch_count", "mg_debug_set_mid_event",
 )
 
 _lib = None
@@ -45,6 +45,7 @@ def load():
     L.mg_obs_bytes_per_env.argtypes = [CFG, I]
     L.mg_obs_bytes_per_env.restype = I64
     L.mg_init.argtypes = [CFG, ST, P]
+    L.mg_sync_derived.argtypes = [CFG, ST, P]
     L.mg_reset.argtypes = [CFG, ST, P, P]
     L.mg_step.argtypes = [CFG, ST, P, P, P, I, P]
     L.mg_obs_encode.argtypes = [CFG, ST, P, P]
@@ -64,6 +65,8 @@ def load():
     L.mg_host_free.argtypes = [P]
     L.mg_host_free.restype = None
     L.mg_launch_count.restype = I64
+    L.mg_debug_set_mid_event.argtypes = [P]
+    L.mg_debug_set_mid_event.restype = None
     for name in EXPORTS:
         fn = getattr(L, name)
         if fn.restype is ctypes.c_int and name not in ("mg_version",):

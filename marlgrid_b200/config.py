@@ -52,6 +52,7 @@ class MgState(ctypes.Structure):
         ("grid", ctypes.c_void_p),
         ("agents", ctypes.c_void_p),
         ("envrec", ctypes.c_void_p),
+        ("cellbits", ctypes.c_void_p),
         ("n_envs", ctypes.c_int64),
         ("env_offset", ctypes.c_int64),
         ("seed", ctypes.c_uint64),

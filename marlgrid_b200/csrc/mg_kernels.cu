@@ -38,6 +38,7 @@ struct KP {
   uint8_t* grid;
   uint8_t* agents;
   int32_t* envrec;
+  uint32_t* cellbits;  // [B][32] occupancy bitboards (derived state), nullptr / W,H > 16: byte-gather path
   long long B, env_offset;
   unsigned long long seed;
   const int32_t* actions;
@@ -67,6 +68,7 @@ struct EnvCtx {
   const KP& p;
   uint32_t* rec;
   uint8_t* tp;
+  uint32_t* bits;  // this env's 32 bitboard words (or nullptr)
   int sc, ep, tl;  // step_count, episode, lifetime steps
   uint32_t w3;     // lo16 next stamp, hi16 error bits
   bool dirty;      // planes modified
@@ -78,6 +80,38 @@ struct EnvCtx {
     return s;
   }
 };
+
+// Occupancy bitboards (DERIVED state, MgState.cellbits): word x = row x of the grid, word 16+y = column y;
+// low half = "opaque" (Wall, or Door that is not open: objects.py:281-282,330-331), high half = "non-empty".
+// They let the observe kernel build a view's transparency rows with one load + two shifts per row instead of
+// V byte loads.  Whoever writes a plane cell keeps them current.
+__device__ __forceinline__ bool cell_opaque(int type, int state) {
+  return type == MG_T_WALL || (type == MG_T_DOOR && state != MG_DOOR_OPEN);
+}
+__device__ __forceinline__ void bits_update_cell(uint32_t* bits, int x, int y, int type, int state) {
+  if (bits == nullptr) return;
+  const uint32_t op = cell_opaque(type, state) ? 1u : 0u, ne = type != MG_T_EMPTY ? 1u : 0u;
+  bits[x] = (bits[x] & ~((1u << y) | (1u << (16 + y)))) | (op << y) | (ne << (16 + y));
+  bits[16 + y] = (bits[16 + y] & ~((1u << x) | (1u << (16 + x)))) | (op << x) | (ne << (16 + x));
+}
+__device__ void bits_rebuild(const uint8_t* tp, uint32_t* bits, int W, int H, int S) {
+  if (bits == nullptr) return;
+  for (int x = 0; x < 16; ++x) {
+    uint32_t w = 0;
+    if (x < W)
+      for (int y = 0; y < H; ++y) {
+        const int t = tp[x * H + y];
+        if (t != MG_T_EMPTY) w |= (1u << (16 + y)) | ((cell_opaque(t, tp[2 * S + x * H + y]) ? 1u : 0u) << y);
+      }
+    bits[x] = w;
+  }
+  for (int y = 0; y < 16; ++y) {
+    uint32_t w = 0;
+    if (y < H)
+      for (int x = 0; x < W; ++x) w |= (((bits[x] >> y) & 1u) << x) | (((bits[x] >> (16 + y)) & 1u) << (16 + x));
+    bits[16 + y] = w;
+  }
+}
 
 // placed agent with the smallest stamp on (x, y), -1 if none: the reference's cell object when it is
 // an agent, else `static_obj.agents[0]` (base.py:547-572)
@@ -176,6 +210,7 @@ __device__ void env_reset(EnvCtx<RS>& c, unsigned long long g) {
     }
   c.sc = 0;
   c.ep += 1;
+  bits_rebuild(c.tp, c.bits, W, H, p.S);
 }
 
 // BonusTile.get_reward objects.py:180-206
@@ -200,11 +235,14 @@ __device__ __forceinline__ double bonus_get_reward(EnvCtx<RS>& c, int a, int bon
 
 // permutation number idx in [0, A!) -> processing order, nibble q of the result = order[q]
 // (Fisher-Yates / Lehmer decode of the contract, oracle/philox.py shuffle_perm)
+__constant__ uint32_t RECIP32[9] = {0u, 0u, 0x80000000u, 0x55555556u, 0x40000000u, 0x33333334u, 0x2AAAAAABu, 0x24924925u, 0x20000000u};  // ceil(2^32/n)
 __device__ __forceinline__ uint32_t decode_order(uint32_t pidx, int A) {
   uint32_t order = 0x76543210u;
   for (int i = A - 1; i >= 1; --i) {
-    const uint32_t j = pidx % (uint32_t)(i + 1);
-    pidx /= (uint32_t)(i + 1);
+    const uint32_t n = (uint32_t)(i + 1);
+    const uint32_t qd = __umulhi(pidx, RECIP32[n]);  // exact quotient: pidx < 8! = 40320, n <= 8
+    const uint32_t j = pidx - qd * n;
+    pidx = qd;
     const uint32_t ni = (order >> (4 * i)) & 0xFu, nj = (order >> (4 * j)) & 0xFu;
     order = (order & ~(0xFu << (4 * i)) & ~(0xFu << (4 * j))) | (nj << (4 * i)) | (ni << (4 * j));
   }
@@ -226,6 +264,25 @@ __device__ bool env_step(EnvCtx<RS>& c, unsigned long long g, const int32_t* __r
     }
   }
   c.sc += 1;  // base.py:512
+  // Prefetch, for every agent at once, the cells its action can touch (the cell in front: type + state, the
+  // cell under it: type): independent loads -> one memory round trip instead of one per agent.  An agent's
+  // own pos/dir only change when it is processed, so the addresses are final; plane bytes are re-read on
+  // the slow path below if an earlier agent of this step edited the planes (pickup / drop / toggle).
+#pragma unroll
+  for (int a = 0; a < MG_MAX_AGENTS; ++a) {
+    if (a < A) {
+      const uint32_t w0 = c.R(a, 0);
+      uint32_t pf = 0;
+      if ((w0 >> 24) & MG_AF_ACTIVE) {
+        const int cx = (int)(w0 & 0xFFu), cy = (int)((w0 >> 8) & 0xFFu), dir = (int)((w0 >> 16) & 3u);
+        const int fx = cx + ((dir == 0) ? 1 : (dir == 2) ? -1 : 0), fy = cy + ((dir == 1) ? 1 : (dir == 3) ? -1 : 0);
+        const bool inb = (unsigned)fx < (unsigned)W && (unsigned)fy < (unsigned)H;
+        const int fidx = inb ? fx * H + fy : 0;
+        pf = (uint32_t)c.tp[fidx] | ((uint32_t)c.tp[2 * S + fidx] << 8) | ((uint32_t)c.tp[cx * H + cy] << 16);
+      }
+      c.R(a, 3) = pf;
+    }
+  }
   // base.py:514-516: one Philox word -> index of the permutation
   uint32_t fact = 1;
   for (int i = 2; i <= A; ++i) fact *= (uint32_t)i;
@@ -248,16 +305,17 @@ __device__ bool env_step(EnvCtx<RS>& c, unsigned long long g, const int32_t* __r
         const int fy = cy + ((dir == 1) ? 1 : (dir == 3) ? -1 : 0);
         const bool inb = (unsigned)fx < (unsigned)W && (unsigned)fy < (unsigned)H;
         const int fidx = inb ? fx * H + fy : 0;
-        const int ftype = inb ? (int)c.tp[fidx] : (int)MG_T_WALL;
+        uint32_t pf = c.R(a, 3);
+        if (c.dirty) pf = (uint32_t)c.tp[fidx] | ((uint32_t)c.tp[2 * S + fidx] << 8) | ((uint32_t)c.tp[cx * H + cy] << 16);
+        const int ftype = inb ? (int)(pf & 0xFFu) : (int)MG_T_WALL;
         if (!inb) c.add_err(MG_ERR_STACK);  // grid.get asserts in-bounds (base.py:154-156); never hit with wall_rect
         if (action == MG_A_FORWARD) {  // base.py:538-585
-          const int fstate = (ftype == MG_T_DOOR || ftype == MG_T_BONUS) ? (int)c.tp[2 * S + fidx] : 0;
+          const int fstate = (int)((pf >> 8) & 0xFFu);
           bool can_move = (ftype == MG_T_EMPTY) || can_overlap_static(ftype, fstate);
           if (!(p.flags & MG_F_GHOST) && ftype == MG_T_EMPTY && queue_head(c, fx, fy) >= 0) can_move = false;  // fwd_cell is a GridAgent
           if (can_move) {
-            const int cidx = cx * H + cy;
-            const int ctype = c.tp[cidx];
-            if (ctype != MG_T_EMPTY && !can_overlap_static(ctype, c.tp[2 * S + cidx])) c.add_err(MG_ERR_STACK);  // base.py:558
+            const int ctype = (int)((pf >> 16) & 0xFFu);
+            if (ctype != MG_T_EMPTY && !can_overlap_static(ctype, c.tp[2 * S + cx * H + cy])) c.add_err(MG_ERR_STACK);  // base.py:558
             w0 = (w0 & 0xFFFF0000u) | (uint32_t)fx | ((uint32_t)fy << 8);
             c.R(a, 2) = c.next_stamp();  // appended last to the target cell's queue (base.py:547-552)
             if (ftype == MG_T_GOAL || ftype == MG_T_BONUS) {  // hasattr(fwd_cell, 'get_reward') base.py:576
@@ -278,6 +336,7 @@ __device__ bool env_step(EnvCtx<RS>& c, unsigned long long g, const int32_t* __r
           if (ftype != MG_T_EMPTY && ((PICKUP_MASK >> ftype) & 1u) && (w1 & 0xFFu) == 0u) {
             c.R(a, 1) = (w1 & 0xFF000000u) | (uint32_t)ftype | ((uint32_t)c.tp[S + fidx] << 8) | ((uint32_t)c.tp[2 * S + fidx] << 16);
             c.tp[fidx] = 0; c.tp[S + fidx] = 0; c.tp[2 * S + fidx] = 0;
+            bits_update_cell(c.bits, fx, fy, 0, 0);
             c.dirty = true;
           }
         } else if (action == MG_A_DROP) {  // base.py:600-606
@@ -285,18 +344,19 @@ __device__ bool env_step(EnvCtx<RS>& c, unsigned long long g, const int32_t* __r
           if (inb && ftype == MG_T_EMPTY && (w1 & 0xFFu) != 0u && queue_head(c, fx, fy) < 0) {
             c.tp[fidx] = (uint8_t)(w1 & 0xFFu); c.tp[S + fidx] = (uint8_t)((w1 >> 8) & 0xFFu); c.tp[2 * S + fidx] = (uint8_t)((w1 >> 16) & 0xFFu);
             c.R(a, 1) = w1 & 0xFF000000u;
+            bits_update_cell(c.bits, fx, fy, (int)(w1 & 0xFFu), (int)((w1 >> 16) & 0xFFu));
             c.dirty = true;
           }
         } else {  // MG_A_TOGGLE base.py:609-613, Door.toggle objects.py:333-346
           if (ftype == MG_T_DOOR) {
             const uint32_t w1 = c.R(a, 1);
-            const int fstate = c.tp[2 * S + fidx];
+            const int fstate = (int)((pf >> 8) & 0xFFu);
             int ns = fstate;
             if (fstate == MG_DOOR_LOCKED) {
               if ((w1 & 0xFFu) == MG_T_KEY && ((w1 >> 8) & 0xFFu) == c.tp[S + fidx]) ns = MG_DOOR_CLOSED;
             } else if (fstate == MG_DOOR_CLOSED) ns = MG_DOOR_OPEN;
             else if (fstate == MG_DOOR_OPEN) ns = MG_DOOR_CLOSED;
-            if (ns != fstate) { c.tp[2 * S + fidx] = (uint8_t)ns; c.dirty = true; }
+            if (ns != fstate) { c.tp[2 * S + fidx] = (uint8_t)ns; bits_update_cell(c.bits, fx, fy, MG_T_DOOR, ns); c.dirty = true; }
           } else if (ftype == MG_T_BOX) c.add_err(MG_ERR_TOGGLE);  // Box.toggle(self) objects.py:381
         }
       } else if (action != MG_A_DONE) {
@@ -354,20 +414,23 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel(const KP p) {
   const long long env = (long long)blockIdx.x * STEP_THREADS + threadIdx.x;
   if (env >= p.B) return;
   const int A = p.A;
-  EnvCtx<STEP_THREADS> c{p, s_rec + threadIdx.x, p.grid + env * 3 * p.S, 0, 0, 0, 0u, false};
+  EnvCtx<STEP_THREADS> c{p, s_rec + threadIdx.x, p.grid + env * 3 * p.S, p.cellbits ? p.cellbits + env * 32 : nullptr, 0, 0, 0, 0u, false};
   int4* arec = reinterpret_cast<int4*>(p.agents) + env * A;
-  for (int a = 0; a < A; ++a) {
-    const int4 r = arec[a];
-    c.R(a, 0) = (uint32_t)r.x; c.R(a, 1) = (uint32_t)r.y; c.R(a, 2) = (uint32_t)r.z; c.R(a, 3) = (uint32_t)r.w;
-  }
   const int4 er = reinterpret_cast<const int4*>(p.envrec)[env];
+#pragma unroll
+  for (int a = 0; a < MG_MAX_AGENTS; ++a) {
+    if (a < A) {
+      const int4 r = arec[a];
+      c.R(a, 0) = (uint32_t)r.x; c.R(a, 1) = (uint32_t)r.y; c.R(a, 2) = (uint32_t)r.z;
+    }
+  }
   c.sc = er.x; c.ep = er.y; c.tl = er.z; c.w3 = (uint32_t)er.w;
   const unsigned long long g = (unsigned long long)(p.env_offset + env);
   const bool dn = env_step(c, g, p.actions + env * A, p.rewards + env * A);
   p.done[env] = dn ? 1 : 0;
   if (dn && p.autoreset) c.w3 |= ERR_RESET_PENDING << 16;  // the reset+observe kernel regenerates the planes in shared memory
   mark_heads(c);
-  for (int a = 0; a < A; ++a) arec[a] = make_int4((int)c.R(a, 0), (int)c.R(a, 1), (int)c.R(a, 2), (int)c.R(a, 3));
+  for (int a = 0; a < A; ++a) arec[a] = make_int4((int)c.R(a, 0), (int)c.R(a, 1), (int)c.R(a, 2), 0);  // word 3 was prefetch scratch
   reinterpret_cast<int4*>(p.envrec)[env] = make_int4(c.sc, c.ep, c.tl, (int)c.w3);
 }
 
@@ -405,16 +468,48 @@ __device__ __forceinline__ ViewGeom view_geom(int px, int py, int dir, int V, in
   return g;
 }
 
-// visibility and non-empty masks of the view, rows b (bit a), plus the plane offset of view cell (a, b):
-// cell_idx = row_base[b] + a * vstep
-template <int V>
-struct ViewMasks {
-  uint32_t vis[V], ne[V];
-  int row0, ustep, vstep;  // idx(a, b) = row0 + b*ustep + a*vstep
+// What the view thread needs after line of sight: visibility and non-empty masks in VIEW orientation,
+// packed with a row stride of 8 bits (bit 8*(b&3) + a of the lo word for rows 0..3, of the hi word for
+// rows 4..7), and the plane offset of view cell (a, b): cell_idx = row0 + b*ustep + a*vstep.
+struct PackedView {
+  uint32_t vis_lo, vis_hi, ne_lo, ne_hi;
+  int row0, ustep, vstep;
+  __device__ __forceinline__ bool visible(int a, int b) const { return (((b < 4 ? vis_lo : vis_hi) >> (8 * (b & 3) + a)) & 1u) != 0; }
+  __device__ __forceinline__ bool nonempty(int a, int b) const { return (((b < 4 ? ne_lo : ne_hi) >> (8 * (b & 3) + a)) & 1u) != 0; }
 };
 
 template <int V>
-__device__ __forceinline__ void view_masks(const KP& p, const uint8_t* __restrict__ tp, const ViewGeom& g, ViewMasks<V>& out) {
+__device__ __forceinline__ void pack_rows(const uint32_t (&r)[V], uint32_t& lo, uint32_t& hi) {
+  lo = 0; hi = 0;
+#pragma unroll
+  for (int b = 0; b < V; ++b) {
+    if (b < 4) lo |= r[b] << (8 * b); else hi |= r[b] << (8 * (b - 4));
+  }
+}
+
+// transparency / non-empty rows from the occupancy bitboards (W, H <= 16): one word per view row
+template <int V>
+__device__ __forceinline__ void rows_from_bits(const uint32_t* __restrict__ bits /* this env's 32 words */, const ViewGeom& g,
+                                               uint32_t (&T)[V], uint32_t (&NE)[V]) {
+  constexpr uint32_t RM = (1u << V) - 1u;
+  const uint32_t* bp = bits + (g.vertical ? 16 : 0);
+  const int sh = g.v0 + 8;  // >= 1: the 16 board bits are parked at bits 8..23 before shifting right
+#pragma unroll
+  for (int b = 0; b < V; ++b) {
+    const int idx = g.u0 + (g.flip ? V - 1 - b : b);
+    const uint32_t w = ((unsigned)idx < (unsigned)g.Lu) ? bp[idx] : 0u;  // rows outside the world: empty, transparent
+    uint32_t opq = (((w & 0xFFFFu) << 8) >> sh) & RM;
+    uint32_t ne = (((w >> 16) << 8) >> sh) & RM;
+    if (g.rev) { opq = rev_bits<V>(opq); ne = rev_bits<V>(ne); }
+    T[b] = ~opq & RM;
+    NE[b] = ne;
+  }
+}
+
+// the same rows gathered byte by byte from the type plane (any grid size)
+template <int V>
+__device__ __forceinline__ void rows_from_planes(const KP& p, const uint8_t* __restrict__ tp, const ViewGeom& g, uint32_t (&T)[V],
+                                                 uint32_t (&NE)[V]) {
   constexpr uint32_t RM = (1u << V) - 1u;
   const int S = p.S;
   // clamped per-axis offsets: every load is in range, out-of-world cells are masked afterwards
@@ -450,24 +545,35 @@ __device__ __forceinline__ void view_masks(const KP& p, const uint8_t* __restric
     Tu[u] = urow ? (~opaque | ~valid_v) & RM : RM;
     NEu[u] = urow ? (nonempty & valid_v) : 0u;
   }
-  // world rows -> view rows (rotate_grid as flip / bit reversal)
-  uint32_t T[V];
 #pragma unroll
-  for (int b = 0; b < V; ++b) {
+  for (int b = 0; b < V; ++b) {  // world rows -> view rows (rotate_grid as flip / bit reversal)
     uint32_t t = g.flip ? Tu[V - 1 - b] : Tu[b];
     uint32_t n = g.flip ? NEu[V - 1 - b] : NEu[b];
     if (g.rev) { t = rev_bits<V>(t); n = rev_bits<V>(n); }
-    T[b] = t; out.ne[b] = n;
+    T[b] = t; NE[b] = n;
   }
+}
+
+template <int V, bool BITS>
+__device__ __forceinline__ PackedView view_masks(const KP& p, const uint8_t* __restrict__ tp, const uint32_t* __restrict__ bits,
+                                                 const ViewGeom& g) {
+  constexpr uint32_t RM = (1u << V) - 1u;
+  uint32_t T[V], NE[V], M[V];
+  if (BITS) rows_from_bits<V>(bits, g, T, NE);
+  else rows_from_planes<V>(p, tp, g, T, NE);
   if (p.flags & MG_F_SEE_THROUGH) {  // agents.py:294-295
 #pragma unroll
-    for (int b = 0; b < V; ++b) out.vis[b] = RM;
+    for (int b = 0; b < V; ++b) M[b] = RM;
   } else {
-    occlude_rows<V>(T, V / 2, V - 1 - p.vo, out.vis);  // agents.py:233-234,293
+    occlude_rows<V>(T, V / 2, V - 1 - p.vo, M);  // agents.py:233-234,293
   }
-  out.ustep = g.flip ? -g.su : g.su;
-  out.vstep = g.rev ? -g.sv : g.sv;
-  out.row0 = g.topX * p.H + g.topY + (g.flip ? (V - 1) * g.su : 0) + (g.rev ? (V - 1) * g.sv : 0);
+  PackedView pv;
+  pack_rows<V>(M, pv.vis_lo, pv.vis_hi);
+  pack_rows<V>(NE, pv.ne_lo, pv.ne_hi);
+  pv.ustep = g.flip ? -g.su : g.su;
+  pv.vstep = g.rev ? -g.sv : g.sv;
+  pv.row0 = g.topX * p.H + g.topY + (g.flip ? (V - 1) * g.su : 0) + (g.rev ? (V - 1) * g.sv : 0);
+  return pv;
 }
 
 // world cell (qx, qy) -> view cell (a, b); false if outside the view
@@ -481,13 +587,27 @@ __device__ __forceinline__ bool world_to_view(const ViewGeom& g, int qx, int qy,
   return true;
 }
 
+// visible non-empty cells of rows [B0, B0+4) of the view: WorldObj.encode (objects.py:90-99) into the staging tile
+template <int V, int B0>
+__device__ __forceinline__ void encode_cells(uint32_t m, const PackedView& pv, const uint8_t* __restrict__ tp, int S, uint8_t* __restrict__ out) {
+  while (m) {
+    const int bit = __ffs(m) - 1;
+    m &= m - 1;
+    const int va = bit & 7, vb = (bit >> 3) + B0;
+    const uint8_t* cp = tp + pv.row0 + vb * pv.ustep + va * pv.vstep;
+    uint8_t* o = out + va * (V * 3) + vb * 3;
+    o[0] = cp[0]; o[1] = cp[S]; o[2] = cp[2 * S];
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // reset + observe kernel (32 envs per CTA, planes staged in shared memory by one bulk-async copy)
 //   RESET: 0 = none, 1 = envs whose step ended the episode (ERR_RESET_PENDING), 2 = explicit (mask or all)
 //   OBS  : 0 = none, 1 = encoded (MultiGrid.encode base.py:196-214), 2 = RGB tiles (base.py:301-331)
 //   TS4  : RGB only: tile rows are whole 32-bit words (ts % 4 == 0) -> 16-byte store path
+//   BITS : transparency rows come from the occupancy bitboards (W, H <= 16) instead of byte gathers
 // ---------------------------------------------------------------------------------------------
-template <int RESET, int OBS, int V, bool TS4>
+template <int RESET, int OBS, int V, bool TS4, bool BITS>
 __global__ void __launch_bounds__(32 * MG_MAX_AGENTS) mg_kernel(const KP p) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x;
@@ -497,17 +617,20 @@ __global__ void __launch_bounds__(32 * MG_MAX_AGENTS) mg_kernel(const KP p) {
   constexpr int VV = V * V;
 
   uint8_t* s_grid = smem;
-  uint32_t* s_rec = reinterpret_cast<uint32_t*>(s_grid + ENVS_PER_CTA * 3 * S);
+  uint32_t* s_bits = reinterpret_cast<uint32_t*>(s_grid + ENVS_PER_CTA * 3 * S);
+  uint32_t* s_rec = s_bits + (BITS ? ENVS_PER_CTA * 32 : 0);
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_rec + A * 4 * 32);
-  uint8_t* s_out = reinterpret_cast<uint8_t*>(s_bar + 2);  // 16-byte aligned: 32*3*S, 512*A and 16 are multiples of 16
+  uint8_t* s_out = reinterpret_cast<uint8_t*>(s_bar + 2);  // 16-byte aligned: every block above is a multiple of 16 bytes
 
   if (OBS != 0) {  // a reset regenerates the planes from scratch: only observing needs the old ones
     if (tid == 0) mbar_init(s_bar, 1);
     __syncthreads();
     if (tid == 0) {
       const uint32_t bytes = (uint32_t)n_valid * 3u * (uint32_t)S;
-      mbar_expect_tx(s_bar, bytes);
+      const uint32_t bbytes = BITS ? (uint32_t)n_valid * 128u : 0u;
+      mbar_expect_tx(s_bar, bytes + bbytes);
       bulk_g2s(s_grid, p.grid + env0 * 3 * S, bytes, s_bar);
+      if (BITS) bulk_g2s(s_bits, p.cellbits + env0 * 32, bbytes, s_bar);
     }
   }
 
@@ -539,7 +662,7 @@ __global__ void __launch_bounds__(32 * MG_MAX_AGENTS) mg_kernel(const KP p) {
   if (warp == 0) {
     const bool valid = lane < n_valid;
     const long long env = env0 + lane;
-    EnvCtx<32> c{p, s_rec + lane, s_grid + lane * 3 * S, 0, 0, 0, 0u, false};
+    EnvCtx<32> c{p, s_rec + lane, s_grid + lane * 3 * S, BITS ? s_bits + lane * 32 : nullptr, 0, 0, 0, 0u, false};
     bool do_reset = false;
     if (valid) {
       const int4* arec = reinterpret_cast<const int4*>(p.agents) + env * A;
@@ -561,8 +684,9 @@ __global__ void __launch_bounds__(32 * MG_MAX_AGENTS) mg_kernel(const KP p) {
         int4* arec = reinterpret_cast<int4*>(p.agents) + env * A;
         for (int a = 0; a < A; ++a) arec[a] = make_int4((int)c.R(a, 0), (int)c.R(a, 1), (int)c.R(a, 2), (int)c.R(a, 3));
         reinterpret_cast<int4*>(p.envrec)[env] = make_int4(c.sc, c.ep, c.tl, (int)c.w3);
-        fence_proxy_async_smem();  // regenerated planes: shared -> global bulk copy
+        fence_proxy_async_smem();  // regenerated planes (+ bitboards): shared -> global bulk copies
         bulk_s2g(p.grid + env * 3 * S, c.tp, 3u * (uint32_t)S);
+        if (BITS) bulk_s2g(p.cellbits + env * 32, c.bits, 128u);
         bulk_commit();
       }
     }
@@ -592,31 +716,17 @@ __global__ void __launch_bounds__(32 * MG_MAX_AGENTS) mg_kernel(const KP p) {
     }
     if (active) {
       const ViewGeom g = view_geom(px, py, dir, V, p.vo, p.W, p.H);
-      ViewMasks<V> vm;
-      view_masks<V>(p, tp, g, vm);
+      const PackedView pv = view_masks<V, BITS>(p, tp, BITS ? s_bits + le * 32 : nullptr, g);
       if (OBS == 1) {
         uint8_t* out = s_out + view * (VV * 3);
-#pragma unroll
-        for (int b = 0; b < V; ++b) {  // visible non-empty cells: WorldObj.encode objects.py:90-99
-          uint32_t m = vm.vis[b] & vm.ne[b];
-          const uint8_t* rowp = tp + vm.row0 + b * vm.ustep;
-          while (m) {
-            const int va = __ffs(m) - 1;
-            m &= m - 1;
-            const uint8_t* cp = rowp + va * vm.vstep;
-            uint8_t* o = out + va * (V * 3) + b * 3;
-            o[0] = cp[0]; o[1] = cp[S]; o[2] = cp[2 * S];
-          }
-        }
+        encode_cells<V, 0>(pv.vis_lo & pv.ne_lo, pv, tp, S, out);
+        if (V > 4) encode_cells<V, 4>(pv.vis_hi & pv.ne_hi, pv, tp, S, out);
         for (int q = 0; q < A; ++q) {  // agents that are their cell's object: (13, colour, dir)
           const uint32_t v0 = rec[(q * 4) * 32];
           if (!((v0 >> 24) & AF_HEAD)) continue;
           int va, vb;
           if (!world_to_view<V>(g, (int)(v0 & 0xFFu), (int)((v0 >> 8) & 0xFFu), va, vb)) continue;
-          uint32_t visb = 0, neb = 0;
-#pragma unroll
-          for (int b = 0; b < V; ++b) { if (b == vb) { visb = vm.vis[b]; neb = vm.ne[b]; } }
-          if (!((visb >> va) & 1u) || ((neb >> va) & 1u)) continue;
+          if (!pv.visible(va, vb) || pv.nonempty(va, vb)) continue;
           uint8_t* o = out + va * (V * 3) + vb * 3;
           o[0] = MG_T_AGENT; o[1] = p.agent_color[q]; o[2] = (uint8_t)((v0 >> 16) & 3u);
         }
@@ -626,14 +736,16 @@ __global__ void __launch_bounds__(32 * MG_MAX_AGENTS) mg_kernel(const KP p) {
         uint32_t bad = 0;
 #pragma unroll
         for (int b = 0; b < V; ++b) {
-          const uint8_t* rowp = tp + vm.row0 + b * vm.ustep;
+          const uint8_t* rowp = tp + pv.row0 + b * pv.ustep;
+          const uint32_t visr = ((b < 4 ? pv.vis_lo : pv.vis_hi) >> (8 * (b & 3))) & 0xFFu;
+          const uint32_t ner = ((b < 4 ? pv.ne_lo : pv.ne_hi) >> (8 * (b & 3))) & 0xFFu;
 #pragma unroll
           for (int va = 0; va < V; ++va) {
             uint8_t t = (uint8_t)p.n_tiles;  // shadow
-            if ((vm.vis[b] >> va) & 1u) {
+            if ((visr >> va) & 1u) {
               t = 0;
-              if ((vm.ne[b] >> va) & 1u) {
-                const int kind = p.kind_of_type[rowp[va * vm.vstep]];
+              if ((ner >> va) & 1u) {
+                const int kind = p.kind_of_type[rowp[va * pv.vstep]];
                 if (kind == 0xFF) bad = 1; else t = (uint8_t)(kind * per_kind);
               }
             }
@@ -645,10 +757,7 @@ __global__ void __launch_bounds__(32 * MG_MAX_AGENTS) mg_kernel(const KP p) {
           if (!((v0 >> 24) & AF_HEAD)) continue;
           int va, vb;
           if (!world_to_view<V>(g, (int)(v0 & 0xFFu), (int)((v0 >> 8) & 0xFFu), va, vb)) continue;
-          uint32_t visb = 0;
-#pragma unroll
-          for (int b = 0; b < V; ++b) { if (b == vb) visb = vm.vis[b]; }
-          if (!((visb >> va) & 1u)) continue;
+          if (!pv.visible(va, vb)) continue;
           // top_agent if it stands on this cell, else the queue head (base.py:282-293)
           const bool mine = ((v0 ^ w0) & 0xFFFFu) == 0u;
           const int qq = mine ? a : q;
@@ -715,11 +824,31 @@ __global__ void __launch_bounds__(32 * MG_MAX_AGENTS) mg_kernel(const KP p) {
   if (RESET != 0 && warp == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
+// recompute the DERIVED state (occupancy bitboards, queue-head flags) from the planes and agent records:
+// for callers that edited them by hand (mg_sync_derived)
+__global__ void sync_derived_kernel(const KP p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint32_t* s_rec = reinterpret_cast<uint32_t*>(smem);
+  const long long env = (long long)blockIdx.x * STEP_THREADS + threadIdx.x;
+  if (env >= p.B) return;
+  const int A = p.A;
+  EnvCtx<STEP_THREADS> c{p, s_rec + threadIdx.x, p.grid + env * 3 * p.S, p.cellbits ? p.cellbits + env * 32 : nullptr, 0, 0, 0, 0u, false};
+  int4* arec = reinterpret_cast<int4*>(p.agents) + env * A;
+  for (int a = 0; a < A; ++a) {
+    const int4 r = arec[a];
+    c.R(a, 0) = (uint32_t)r.x; c.R(a, 1) = (uint32_t)r.y; c.R(a, 2) = (uint32_t)r.z; c.R(a, 3) = (uint32_t)r.w;
+  }
+  mark_heads(c);
+  for (int a = 0; a < A; ++a) arec[a] = make_int4((int)c.R(a, 0), (int)c.R(a, 1), (int)c.R(a, 2), (int)c.R(a, 3));
+  bits_rebuild(c.tp, c.bits, p.W, p.H, p.S);
+}
+
 // zero-initialised family of freshly constructed envs (bonus_state = None)
-__global__ void init_kernel(uint8_t* grid, uint8_t* agents, int32_t* envrec, long long B, int A, int S) {
+__global__ void init_kernel(uint8_t* grid, uint8_t* agents, int32_t* envrec, uint32_t* cellbits, long long B, int A, int S) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long n_grid = B * 3 * S / 16, n_ag = B * A, n_er = B;
   if (i < n_grid) reinterpret_cast<int4*>(grid)[i] = make_int4(0, 0, 0, 0);
+  if (cellbits != nullptr && i < B * 8) reinterpret_cast<int4*>(cellbits)[i] = make_int4(0, 0, 0, 0);
   if (i < n_ag) reinterpret_cast<int4*>(agents)[i] = make_int4(0, (int)0xFF000000u, 0, 0);
   if (i < n_er) reinterpret_cast<int4*>(envrec)[i] = make_int4(0, 0, 0, 0);
 }
@@ -789,14 +918,15 @@ static KP make_kp(const MgConfig* c, const MgState* st) {
   for (int i = 0; i < MG_MAX_AGENTS; ++i) { p.agent_color[i] = c->agent_color[i]; p.spawn_delay[i] = c->spawn_delay[i]; }
   for (int i = 0; i < 15; ++i) p.kind_of_type[i] = c->kind_of_type[i];
   p.kind_of_type[15] = 0xFF;
-  p.grid = st->grid; p.agents = st->agents; p.envrec = st->envrec; p.B = st->n_envs; p.env_offset = st->env_offset; p.seed = st->seed;
+  p.grid = st->grid; p.agents = st->agents; p.envrec = st->envrec; p.B = st->n_envs;
+  p.cellbits = (c->width <= 16 && c->height <= 16) ? st->cellbits : nullptr; p.env_offset = st->env_offset; p.seed = st->seed;
   p.n_tiles = (c->n_static_kinds + 1) * (1 + 4 * c->n_agents);
   p.orient_slots = 4;
   return p;
 }
 
 static size_t smem_bytes(const KP& p, int obs) {
-  size_t b = (size_t)ENVS_PER_CTA * 3 * p.S + (size_t)p.A * 4 * 32 * 4 + 16;
+  size_t b = (size_t)ENVS_PER_CTA * 3 * p.S + (size_t)p.A * 4 * 32 * 4 + 16 + (p.cellbits ? (size_t)ENVS_PER_CTA * 128 : 0);
   if (obs == 1) b += (size_t)ENVS_PER_CTA * p.A * p.V * p.V * 3;
   if (obs == 2) {
     b += (size_t)ENVS_PER_CTA * p.A * p.V * p.V + (size_t)((ENVS_PER_CTA * p.A + 15) / 16) * 16;
@@ -805,10 +935,10 @@ static size_t smem_bytes(const KP& p, int obs) {
   return (b + 15) / 16 * 16;
 }
 
-template <int RESET, int OBS, int V, bool TS4>
+template <int RESET, int OBS, int V, bool TS4, bool BITS>
 static int launch_one(const KP& p, cudaStream_t s) {
   const size_t sm = smem_bytes(p, OBS);
-  auto k = mg_kernel<RESET, OBS, V, TS4>;
+  auto k = mg_kernel<RESET, OBS, V, TS4, BITS>;
   static size_t configured[64] = {0};  // per instantiation and device
   int dev = 0;
   cudaGetDevice(&dev);
@@ -825,15 +955,15 @@ static int launch_one(const KP& p, cudaStream_t s) {
   return (int)cudaGetLastError();
 }
 
-template <int RESET, int OBS, bool TS4>
+template <int RESET, int OBS, bool TS4, bool BITS>
 static int launch_v(const KP& p, cudaStream_t s) {
   switch (p.V) {
-    case 3: return launch_one<RESET, OBS, 3, TS4>(p, s);
-    case 4: return launch_one<RESET, OBS, 4, TS4>(p, s);
-    case 5: return launch_one<RESET, OBS, 5, TS4>(p, s);
-    case 6: return launch_one<RESET, OBS, 6, TS4>(p, s);
-    case 7: return launch_one<RESET, OBS, 7, TS4>(p, s);
-    case 8: return launch_one<RESET, OBS, 8, TS4>(p, s);
+    case 3: return launch_one<RESET, OBS, 3, TS4, BITS>(p, s);
+    case 4: return launch_one<RESET, OBS, 4, TS4, BITS>(p, s);
+    case 5: return launch_one<RESET, OBS, 5, TS4, BITS>(p, s);
+    case 6: return launch_one<RESET, OBS, 6, TS4, BITS>(p, s);
+    case 7: return launch_one<RESET, OBS, 7, TS4, BITS>(p, s);
+    case 8: return launch_one<RESET, OBS, 8, TS4, BITS>(p, s);
   }
   return MG_E_CONFIG;
 }
@@ -841,10 +971,11 @@ static int launch_v(const KP& p, cudaStream_t s) {
 // reset (RESET: 0 none / 1 pending / 2 explicit) and/or observe (obs: 0 none / 1 encoded / 2 rgb)
 template <int RESET>
 static int launch_obs(const KP& p, int obs, cudaStream_t s) {
-  if (obs == 0) return launch_one<RESET, 0, 7, false>(p, s);
-  if (obs == 1) return launch_v<RESET, 1, false>(p, s);
-  if (p.ts % 4 == 0) return launch_v<RESET, 2, true>(p, s);
-  return launch_v<RESET, 2, false>(p, s);
+  const bool bits = p.cellbits != nullptr;
+  if (obs == 0) return bits ? launch_one<RESET, 0, 7, false, true>(p, s) : launch_one<RESET, 0, 7, false, false>(p, s);
+  if (obs == 1) return bits ? launch_v<RESET, 1, false, true>(p, s) : launch_v<RESET, 1, false, false>(p, s);
+  if (p.ts % 4 == 0) return bits ? launch_v<RESET, 2, true, true>(p, s) : launch_v<RESET, 2, true, false>(p, s);
+  return bits ? launch_v<RESET, 2, false, true>(p, s) : launch_v<RESET, 2, false, false>(p, s);
 }
 
 static int launch_step(const KP& p, cudaStream_t s) {
@@ -855,10 +986,13 @@ static int launch_step(const KP& p, cudaStream_t s) {
   return (int)cudaGetLastError();
 }
 
+static cudaEvent_t g_mid_event = nullptr;  // profiling hook: recorded between the two launches of a step
+
 // env.step: the step kernel, then (auto-reset and/or observation) in one more launch
 static int launch_step_obs(const KP& p, int obs, cudaStream_t s) {
   int e = launch_step(p, s);
   if (e) return e;
+  if (g_mid_event) cudaEventRecord(g_mid_event, s);
   if (p.autoreset) return launch_obs<1>(p, obs, s);
   if (obs != 0) return launch_obs<0>(p, obs, s);
   return 0;
@@ -870,7 +1004,7 @@ static int check_state(const MgConfig* c, const MgState* st) {
   int e = check_cfg(c);
   if (e) return e;
   if (!st || !st->grid || !st->agents || !st->envrec || st->n_envs < 0) return MG_E_ARG;
-  if (!aligned16(st->grid) || !aligned16(st->agents) || !aligned16(st->envrec)) return MG_E_ARG;
+  if (!aligned16(st->grid) || !aligned16(st->agents) || !aligned16(st->envrec) || !aligned16(st->cellbits)) return MG_E_ARG;
   return 0;
 }
 
@@ -886,13 +1020,25 @@ int64_t mg_obs_bytes_per_env(const MgConfig* c, int rgb) {
   return rgb ? (int64_t)c->n_agents * v * c->view_tile_size * v * c->view_tile_size * 3 : (int64_t)c->n_agents * v * v * 3;
 }
 int64_t mg_launch_count(void) { return g_launches.load(); }
+void mg_debug_set_mid_event(void* cuda_event) { g_mid_event = (cudaEvent_t)cuda_event; }
 
 int mg_init(const MgConfig* cfg, const MgState* st, mg_stream_t stream) {
   int e = check_state(cfg, st);
   if (e) return e;
   if (st->n_envs == 0) return 0;
-  const long long n = std::max<long long>(st->n_envs * 3 * cfg->plane_stride / 16, st->n_envs * cfg->n_agents);
-  init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(st->grid, st->agents, st->envrec, st->n_envs, cfg->n_agents, cfg->plane_stride);
+  const long long n = std::max<long long>(std::max<long long>(st->n_envs * 3 * cfg->plane_stride / 16, st->n_envs * cfg->n_agents), st->n_envs * 8);
+  init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(st->grid, st->agents, st->envrec, st->cellbits, st->n_envs, cfg->n_agents, cfg->plane_stride);
+  g_launches.fetch_add(1);
+  return (int)cudaGetLastError();
+}
+
+int mg_sync_derived(const MgConfig* cfg, const MgState* st, mg_stream_t stream) {
+  int e = check_state(cfg, st);
+  if (e) return e;
+  if (st->n_envs == 0) return 0;
+  KP p = make_kp(cfg, st);
+  const long long blocks = (p.B + STEP_THREADS - 1) / STEP_THREADS;
+  sync_derived_kernel<<<(unsigned)blocks, STEP_THREADS, (size_t)STEP_THREADS * p.A * 16, (cudaStream_t)stream>>>(p);
   g_launches.fetch_add(1);
   return (int)cudaGetLastError();
 }
@@ -1034,6 +1180,7 @@ int mg_engine_create(MgEngine** out, const MgConfig* cfg, int64_t n_envs, int64_
   MG_CUDA(cudaMalloc(&en->st.grid, (size_t)n_envs * 3 * cfg->plane_stride));
   MG_CUDA(cudaMalloc(&en->st.agents, (size_t)n_envs * cfg->n_agents * MG_AGENT_REC));
   MG_CUDA(cudaMalloc(&en->st.envrec, (size_t)n_envs * MG_ENV_REC));
+  MG_CUDA(cudaMalloc(&en->st.cellbits, (size_t)n_envs * 128));
   MG_CUDA(cudaMalloc(&en->d_actions, (size_t)n_envs * cfg->n_agents * sizeof(int32_t)));
   MG_CUDA(cudaMalloc(&en->d_rewards, (size_t)n_envs * cfg->n_agents * sizeof(double)));
   MG_CUDA(cudaMalloc(&en->d_done, (size_t)n_envs));
@@ -1053,7 +1200,7 @@ void mg_engine_destroy(MgEngine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
-  cudaFree(e->st.grid); cudaFree(e->st.agents); cudaFree(e->st.envrec);
+  cudaFree(e->st.grid); cudaFree(e->st.agents); cudaFree(e->st.envrec); cudaFree(e->st.cellbits);
   cudaFree(e->d_actions); cudaFree(e->d_rewards); cudaFree(e->d_done); cudaFree(e->d_obs); cudaFree(e->d_atlas);
   cudaStreamDestroy(e->stream);
   delete e;

@@ -53,6 +53,7 @@ class BatchedMultiGridEnv:
         self.grid = torch.empty((B, 3, S), dtype=torch.uint8, device=dev)
         self.agents = torch.empty((B, A, 16), dtype=torch.uint8, device=dev)
         self.envrec = torch.empty((B, 4), dtype=torch.int32, device=dev)
+        self.cellbits = torch.empty((B, 32), dtype=torch.int32, device=dev)  # derived occupancy bitboards (include/marlgrid_b200.h)
         self.rewards = torch.zeros((B, A), dtype=torch.float64, device=dev)
         self.done = torch.zeros((B,), dtype=torch.uint8, device=dev)
         if obs_mode == "encoded":
@@ -76,6 +77,7 @@ class BatchedMultiGridEnv:
     def _sync_state_struct(self):
         st = self._state
         st.grid, st.agents, st.envrec = self.grid.data_ptr(), self.agents.data_ptr(), self.envrec.data_ptr()
+        st.cellbits = self.cellbits.data_ptr()
         st.n_envs, st.env_offset, st.seed = self.num_envs, self.env_offset, self._seed
 
     def seed(self, seed=1337):
@@ -151,6 +153,12 @@ class BatchedMultiGridEnv:
         with torch.cuda.device(self.device):
             return self._observe()
 
+    def sync_derived(self):
+        """Recompute the derived device state (occupancy bitboards, queue-head flags) after the planes or
+        the agent records were edited from Python (e.g. `env.planes[...] = ...`)."""
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.mg_sync_derived(ctypes.byref(self.cfg), ctypes.byref(self._state), self._stream()), "mg_sync_derived")
+
     def rollout(self, actions):
         """actions int32 [T, B, A]: T fused steps enqueued from C; returns the last (obs, rewards, done)."""
         with torch.cuda.device(self.device):
@@ -195,7 +203,8 @@ class BatchedMultiGridEnv:
     # ---- SoA views (decoded) -------------------------------------------------------------------
     @property
     def planes(self):
-        """uint8 [B, 3, W, H] view: type / colour / state planes, index [x][y] like MultiGrid.grid (base.py:91)."""
+        """uint8 [B, 3, W, H] view: type / colour / state planes, index [x][y] like MultiGrid.grid (base.py:91).
+        After writing through this view call sync_derived()."""
         W, H = self.cfg.width, self.cfg.height
         return self.grid[:, :, : W * H].unflatten(2, (W, H))
 
@@ -264,6 +273,7 @@ class BatchedMultiGridEnv:
         self._seed = int(sd["seed"])
         self.env_offset = int(sd["env_offset"])
         self._sync_state_struct()
+        self.sync_derived()
 
     def unbatched(self, index=0):
         """gym-style view of env `index`: lists of per-agent obs, like the reference's return values."""

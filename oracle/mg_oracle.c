@@ -456,7 +456,7 @@ int mgo_hw_threads(void) { long n = sysconf(_SC_NPROCESSORS_ONLN); return n > 0 
 
 typedef struct Job {
   int kind; /* 0 reset, 1 step, 2 obs_encode, 3 obs_rgb, 4 rollout (n_steps fused steps per env) */
-  int64_t n_steps, B;
+  int64_t n_steps, B, pool; /* rollout: actions[(t % pool)][B][A] */
   const MgConfig* c; uint8_t* grid; uint8_t* agents; int32_t* envrec;
   uint64_t seed; int64_t env_offset; const uint8_t* mask; const int32_t* actions; double* rewards; uint8_t* done;
   int autoreset; const uint8_t* atlas; uint8_t* obs;
@@ -481,7 +481,7 @@ static void* run_job(void* arg) {
       } break;
       case 4: /* time-major actions [n_steps][B][A]; every env is independent, so each thread runs its envs to the end */
         for (int64_t t = 0; t < j->n_steps; ++t) {
-          int d = env_step(&v, j->actions + ((size_t)t * j->B + e) * c->n_agents, j->rewards + e * c->n_agents, j->seed, g);
+          int d = env_step(&v, j->actions + ((size_t)(t % j->pool) * j->B + e) * c->n_agents, j->rewards + e * c->n_agents, j->seed, g);
           j->done[e] = (uint8_t)d;
           if (d && j->autoreset) env_reset(&v, j->seed, g);
           obs_encode_env(&v, j->obs + (size_t)e * enc_env);
@@ -533,12 +533,13 @@ void mgo_step(const MgConfig* c, uint8_t* grid, uint8_t* agents, int32_t* envrec
   run_parallel(&j, B);
 }
 
-/* n_steps x (step + auto-reset + encoded obs) for every env; outputs hold the last step's values */
+/* n_steps x (step + auto-reset + encoded obs) for every env; outputs hold the last step's values;
+ * actions is a pool of `pool` time-major action batches used cyclically */
 void mgo_rollout(const MgConfig* c, uint8_t* grid, uint8_t* agents, int32_t* envrec, int64_t B, uint64_t seed, int64_t env_offset,
-                 const int32_t* actions, int64_t n_steps, double* rewards, uint8_t* done, int autoreset, uint8_t* obs) {
+                 const int32_t* actions, int64_t n_steps, int64_t pool, double* rewards, uint8_t* done, int autoreset, uint8_t* obs) {
   Job j; memset(&j, 0, sizeof j);
   j.kind = 4; j.c = c; j.grid = grid; j.agents = agents; j.envrec = envrec; j.seed = seed; j.env_offset = env_offset;
-  j.actions = actions; j.rewards = rewards; j.done = done; j.autoreset = autoreset; j.obs = obs; j.n_steps = n_steps; j.B = B;
+  j.actions = actions; j.rewards = rewards; j.done = done; j.autoreset = autoreset; j.obs = obs; j.n_steps = n_steps; j.B = B; j.pool = pool > 0 ? pool : n_steps;
   run_parallel(&j, B);
 }
 

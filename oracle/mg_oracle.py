@@ -85,18 +85,20 @@ class OracleBatch:
             return obs, rew, done
         return rew, done
 
-    def rollout(self, actions, autoreset=True):
-        """actions int32 [T, B, A]; T fused steps per env inside C (threads own env ranges)."""
+    def rollout(self, actions, autoreset=True, n_steps=None):
+        """actions int32 [P, B, A]; n_steps (default P) fused steps per env inside C, cycling through the
+        P action batches (threads own env ranges)."""
         self._thr()
         act = np.ascontiguousarray(actions, np.int32)
-        T = act.shape[0]
+        P = act.shape[0]
+        T = P if n_steps is None else int(n_steps)
         assert act.shape[1:] == (self.B, self.A)
         if not hasattr(self, "_ro"):
             self._ro = (np.zeros((self.B, self.A, self.V, self.V, 3), np.uint8), np.zeros((self.B, self.A), np.float64), np.zeros((self.B,), np.uint8))
         obs, rew, done = self._ro
         lib().mgo_rollout(
             ctypes.byref(self.cfg), _p(self.grid), _p(self.agents), _p(self.envrec), ctypes.c_int64(self.B), ctypes.c_uint64(self.seed),
-            ctypes.c_int64(self.env_offset), _p(act), ctypes.c_int64(T), _p(rew), _p(done), ctypes.c_int(int(autoreset)), _p(obs),
+            ctypes.c_int64(self.env_offset), _p(act), ctypes.c_int64(T), ctypes.c_int64(P), _p(rew), _p(done), ctypes.c_int(int(autoreset)), _p(obs),
         )
         return obs, rew, done
 

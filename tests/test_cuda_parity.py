@@ -69,12 +69,14 @@ def test_cuda_replays_reference_trajectory(path):
                 rgb = env_rgb.reset()
         elif kind == 2:
             env.planes[0].copy_(torch.from_numpy(z["grid"][i]).cuda())
+            env.sync_derived()
             obs = env.observe()
         elif kind == 3:
             env.step(act)
             assert int(env.err[0].item()) & int(z["err"][i])
             env.envrec[:, 3] &= 0xFFFF
             env.agents[0, :, 2] = torch.from_numpy(z["dir"][i].astype(np.uint8)).cuda()
+            env.sync_derived()
             continue
         else:
             obs, rew, done, _ = env.step(act)

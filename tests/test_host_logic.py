@@ -1,0 +1,184 @@
+"""CPU suite: host-side logic, the C-ABI surface and the failure mode without a GPU."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_loads_and_exports_every_declared_symbol(cuda_lib):
+    """Every function declared in include/marlgrid_b200.h is exported by libmarlgrid_b200.so (no compute calls)."""
+    hdr = open(os.path.join(ROOT, "include", "marlgrid_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = set(re.findall(r"\b(mg_[a-z0-9_]+)\s*\(", hdr))
+    names -= {"mg_stream_t"}
+    assert len(names) >= 20
+    raw = ctypes.CDLL(os.path.join(ROOT, "marlgrid_b200", "libmarlgrid_b200.so"))
+    for n in sorted(names):
+        assert hasattr(raw, n), f"{n} declared in the header but not exported"
+    assert cuda_lib.mg_version() == 1
+    assert b"sm_100a" in cuda_lib.mg_build_info()
+
+
+def test_config_struct_matches_c_layout(cuda_lib):
+    from marlgrid_b200.config import MgConfig, make_config
+
+    assert cuda_lib.mg_sizeof_config() == ctypes.sizeof(MgConfig)
+    cfg = make_config(15, 15, ["red", "blue", "purple"], n_clutter=25)
+    assert cuda_lib.mg_config_validate(ctypes.byref(cfg)) == 0
+    assert cuda_lib.mg_obs_bytes_per_env(ctypes.byref(cfg), 0) == 3 * 147
+    assert cuda_lib.mg_obs_bytes_per_env(ctypes.byref(cfg), 1) == 3 * 56 * 56 * 3
+    assert cfg.plane_stride == 240 and cfg.plane_stride % 16 == 0
+    bad = make_config(15, 15, ["red"], n_clutter=1)
+    bad.plane_stride = 100
+    assert cuda_lib.mg_config_validate(ctypes.byref(bad)) == -1
+    with pytest.raises(ValueError):
+        make_config(2, 9, ["red"])  # Grid needs width, height >= 3 (base.py:98-99)
+    with pytest.raises(ValueError):
+        make_config(9, 9, ["red"] * 9)
+
+
+def test_registry_ids_match_reference():
+    """Same ids and resolved scenario parameters as marlgrid/envs/__init__.py:70-121 (incl. its quirks)."""
+    from marlgrid_b200 import envs
+
+    assert envs.registered_envs == [
+        "MarlGrid-1AgentCluttered15x15-v0", "MarlGrid-3AgentCluttered11x11-v0", "MarlGrid-3AgentCluttered15x15-v0",
+        "MarlGrid-2AgentEmpty9x9-v0", "MarlGrid-3AgentEmpty9x9-v0", "MarlGrid-4AgentEmpty9x9-v0", "Goalcycle-demo-solo-v0",
+    ]
+
+
+def test_env_construction_fails_loudly_without_gpu():
+    """No CPU fallback: on a box without CUDA the product refuses to build an env."""
+    import torch
+
+    from marlgrid_b200 import envs
+
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    with pytest.raises(Exception) as ei:
+        envs.make("MarlGrid-2AgentEmpty9x9-v0")
+    assert not isinstance(ei.value, (ImportError, AttributeError)), ei.value
+    with pytest.raises(ValueError):
+        envs.make("MarlGrid-2AgentEmpty9x9-v0", device="cpu")
+
+
+def test_product_never_imports_the_oracle():
+    """The product path must not route through oracle/ (or any CPU fallback)."""
+    pkg = os.path.join(ROOT, "marlgrid_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+                assert "libmg_oracle" not in src, f
+
+
+def test_scenario_kwargs_resolve_like_reference():
+    from marlgrid_b200.agents import GridAgentInterface
+    from marlgrid_b200.config import GOAL_FIXED, GOAL_NONE, GOAL_RANDOM
+    from marlgrid_b200.envs import ClutteredGoalCycleEnv, ClutteredMultiGrid, EmptyMultiGrid
+
+    class Probe(Exception):
+        pass
+
+    def cfg_of(cls, **kw):
+        # intercept before any device work: BatchedMultiGridEnv.__init__ receives the finished MgConfig
+        import marlgrid_b200.envs as E
+
+        orig = E.BatchedMultiGridEnv.__init__
+
+        def grab(self, cfg, **k):
+            raise Probe(cfg, k)
+
+        E.BatchedMultiGridEnv.__init__ = grab
+        try:
+            cls(**kw)
+        except Probe as p:
+            return p.args
+        finally:
+            E.BatchedMultiGridEnv.__init__ = orig
+
+    ag = [GridAgentInterface(color=c, view_size=7, view_tile_size=8) for c in ("red", "blue", "purple")]
+    cfg, k = cfg_of(ClutteredMultiGrid, agents=ag, grid_size=15, clutter_density=0.15, num_envs=5)
+    assert (cfg.width, cfg.height, cfg.n_agents, cfg.n_clutter, cfg.goal_mode) == (15, 15, 3, 25, GOAL_FIXED)  # int(.15*13*13)
+    assert k["num_envs"] == 5 and list(cfg.agent_color[:3]) == [0, 3, 5]
+    cfg, _ = cfg_of(ClutteredMultiGrid, agents=ag, grid_size=11, n_clutter=7, randomize_goal=True)
+    assert (cfg.n_clutter, cfg.goal_mode) == (7, GOAL_RANDOM)
+    cfg, _ = cfg_of(EmptyMultiGrid, agents=ag[:2], width=9, height=7, max_steps=50, ghost_mode=False, respawn=True, reward_decay=False)
+    assert (cfg.width, cfg.height, cfg.max_steps, cfg.flags & 7, cfg.goal_mode) == (9, 7, 50, 2, GOAL_FIXED)
+    cfg, _ = cfg_of(ClutteredGoalCycleEnv, agents=[dict(color="prestige", view_size=7, view_offset=1, view_tile_size=11)], grid_size=13,
+                    clutter_density=0.15, n_bonus_tiles=3, penalty=-1.5, max_steps=250, respawn=True)
+    assert (cfg.goal_mode, cfg.n_bonus_tiles, cfg.bonus_penalty, cfg.view_offset, cfg.view_tile_size) == (GOAL_NONE, 3, -1.5, 1, 11)
+    assert not (cfg.flags & 4)  # goal-cycle envs default reward_decay=False (goalcycle.py:9,14)
+    with pytest.raises(ValueError):
+        ClutteredMultiGrid(agents=ag, grid_size=9)  # n_clutter xor clutter_density (cluttered.py:10-11)
+    with pytest.raises(ValueError):
+        EmptyMultiGrid(agents=[ag[0], GridAgentInterface(view_size=5)], grid_size=9)  # views must be uniform
+    with pytest.raises(ValueError):
+        EmptyMultiGrid(agents=[object()], grid_size=9)
+
+
+def test_agent_interface_spaces():
+    from marlgrid_b200.agents import GridAgentInterface
+
+    a = GridAgentInterface(view_size=7, view_tile_size=8, color="blue")
+    assert a.observation_space.shape == (56, 56, 3) and a.action_space.n == 7
+    assert GridAgentInterface(restrict_actions=True).action_space.n == 3
+    r = GridAgentInterface(observation_style="rich", observe_position=True, observe_orientation=True)
+    assert set(r.observation_space.spaces) == {"pov", "position", "orientation"}
+    with pytest.raises(ValueError):
+        GridAgentInterface(observation_style="nope")
+    c = a.clone()
+    assert (c.view_size, c.view_tile_size, c.color) == (7, 8, "blue")
+
+
+def test_independent_learners_protocol():
+    """README.md:21-64 usage: action_step / save_step / episode() with per-agent slices."""
+    import torch
+
+    from marlgrid_b200 import IndependentLearners, LearningAgent
+
+    log = []
+
+    class L(LearningAgent):
+        def __init__(self, k):
+            super().__init__(color=["red", "blue"][k])
+            self.k = k
+
+        def action_step(self, obs):
+            return torch.full((obs.shape[0],), self.k, dtype=torch.int32) if obs.ndim == 4 else self.k
+
+        def save_step(self, *tr):
+            log.append((self.k, tuple(getattr(t, "shape", None) for t in tr[:4])))
+
+        def start_episode(self):
+            log.append((self.k, "start"))
+
+        def end_episode(self):
+            log.append((self.k, "end"))
+
+    agents = IndependentLearners(L(0), L(1))
+    obs = torch.zeros((5, 2, 7, 7, 3), dtype=torch.uint8)
+    with agents.episode():
+        act = agents.action_step(obs)
+        assert tuple(act.shape) == (5, 2) and act[:, 1].eq(1).all()
+        agents.save_step(obs, act, obs, torch.zeros(5, 2, dtype=torch.float64), torch.zeros(5, dtype=torch.bool))
+    assert log[0] == (0, "start") and log[-1] == (1, "end")
+    assert (0, (torch.Size([5, 7, 7, 3]), torch.Size([5]), torch.Size([5, 7, 7, 3]), torch.Size([5]))) in log
+    single = [np.zeros((56, 56, 3)), np.zeros((56, 56, 3))]
+    assert agents.action_step(single) == [0, 1]
+
+
+def test_shard_ranges_partition_the_batch():
+    from marlgrid_b200.sharding import shard_range
+
+    for total, world in ((1048576, 8), (65536, 1), (10, 3), (7, 8)):
+        spans = [shard_range(total, r, world) for r in range(world)]
+        assert spans[0][0] == 0 and sum(c for _, c in spans) == total
+        for (o1, c1), (o2, _) in zip(spans, spans[1:]):
+            assert o1 + c1 == o2
+    assert shard_range(1048576, 3, 8) == (3 * 131072, 131072)
