@@ -1,19 +1,23 @@
 // mg_kernels.cu -- batched MarlGrid hot path for B200 (sm_100a): step / reset / egocentric obs kernels.
 //
+// World state (include/marlgrid_b200.h): byte planes type/colour/state [B][3][S], agent records, env
+// records -- plus DERIVED bit-planes `cellbits` [B][48] (grids up to 16x16): per cell one bit each for
+// "opaque" (Wall / closed Door), "non-empty" and "canonical wall" (exactly Wall('worst', state 0), the only
+// wall the reference's generators ever create), stored row-major AND column-major.  They are a lossless
+// index of where things are: what is NOT a canonical wall or empty is looked up in the byte planes.
+//
 // env.step is two launches on one stream:
-//   1. step_kernel -- one THREAD per env: the sequential part of MultiGridEnv.step (base.py:501-649):
-//      Philox agent order, per-agent action application, stacking stamps, float64 reward, done.  It
-//      touches two cells per agent, so it works in place on global memory at full occupancy.
-//   2. mg_kernel<RESET, OBS> -- one CTA per 32 consecutive envs:
-//      * the envs' three grid planes (one contiguous 32*3*S byte chunk of HBM) are staged into shared
-//        memory by ONE bulk-async copy (cp.async.bulk + mbarrier: the TMA engine, SASS UBLKCP);
-//      * warp 0 (lane == env) regenerates the world of envs whose episode ended (Philox rejection
-//        sampling, base.py:402-416,690-708) directly in shared memory and sends the new planes back
-//        with a shared->global bulk copy;
-//      * every thread is one agent-view: VxV crop gathered along per-thread strides, the reference's
-//        rotation reduced to row-order / bit reversals, line-of-sight as carry-propagating row masks,
-//        sparse encode into a shared staging tile; the CTA finally streams the staging tile to HBM as
-//        16-byte coalesced stores.
+//   1. step_kernel -- one THREAD per env: MultiGridEnv.step (base.py:501-649): Philox agent order, per-agent
+//      action application, stacking stamps, float64 reward, done, and -- for envs whose episode ended --
+//      MultiGridEnv.reset (base.py:402-416) by Philox rejection sampling.  A step touches two cells per
+//      agent: it works in place on global memory, answering "what is in that cell" from the bit-planes.
+//   2. obs_kernel -- one CTA per 32 consecutive envs, one thread per agent-view: the envs' bit-planes and
+//      agent records (two contiguous chunks) are staged into shared memory by bulk-async copies
+//      (cp.async.bulk + mbarrier: the TMA engine, SASS UBLKCP); a view's transparency rows are one word
+//      load + shifts each, the reference's rotation is a row-order / bit reversal, line of sight is carry
+//      propagation on row masks, visible canonical walls are written as constants, the few other visible
+//      objects are fetched from the byte planes; the CTA streams its staging tile to HBM as 16-byte stores.
+//      Grids larger than 16x16 take the byte path: planes staged by TMA, crop gathered byte by byte.
 // See DESIGN.md for the layout, the RNG contract and the roofline accounting.
 #include <algorithm>
 #include <atomic>
@@ -25,7 +29,8 @@
 namespace mg {
 
 constexpr int ENVS_PER_CTA = 32;
-constexpr uint32_t AF_HEAD = 0x80u;  // transient flag bit: agent is the head of its cell's queue
+constexpr int BITS_WORDS = 48;       // per env: 16 row words, 16 column words, 16 canonical-wall words
+constexpr uint32_t AF_HEAD = 0x80u;  // derived flag bit: agent is the head of its cell's queue
 
 struct KP {
   int W, H, A, V, vo, ts, max_steps, n_clutter, n_bonus, goal_mode;
@@ -38,7 +43,7 @@ struct KP {
   uint8_t* grid;
   uint8_t* agents;
   int32_t* envrec;
-  uint32_t* cellbits;  // [B][32] occupancy bitboards (derived state), nullptr / W,H > 16: byte-gather path
+  uint32_t* cellbits;  // [B][48] or nullptr (grid wider/taller than 16, or caller passed none): byte path
   long long B, env_offset;
   unsigned long long seed;
   const int32_t* actions;
@@ -53,65 +58,75 @@ struct KP {
 };
 
 // ---------------------------------------------------------------------------------------------
-// per-env game state while a thread runs the sequential part of step()/reset():
-// agent records live transposed in shared memory, word w of agent a of the thread's env at
-// rec[(a*4+w)*RS]  (RS = threads sharing the array) -> bank == thread, conflict-free for any per-thread a.
-//   w0 = x | y<<8 | dir<<16 | flags<<24     w1 = carry_type | carry_colour<<8 | carry_state<<16 | bonus<<24
-//   w2 = stamp                               w3 = reserved
-// `tp` is the env's type plane (colour at +S, state at +2S): global memory in the step kernel,
-// shared memory in the reset/observe kernel.
+// bit-planes.  word x (0..15): row x, bit y = opaque(x,y), bit 16+y = non-empty(x,y)
+//              word 16+y     : column y, bit x = opaque, bit 16+x = non-empty
+//              word 32+i     : bit j = canonical wall at (i, j) [row i], bit 16+j = canonical wall at (j, i) [column i]
 // ---------------------------------------------------------------------------------------------
-constexpr uint32_t ERR_RESET_PENDING = 0x8000u;  // internal: episode ended, auto-reset owed by the next kernel
+__device__ __forceinline__ bool cell_opaque(int type, int state) {  // objects.py:281-282,330-331
+  return type == MG_T_WALL || (type == MG_T_DOOR && state != MG_DOOR_OPEN);
+}
+__device__ __forceinline__ bool cell_canon(int type, int colour, int state) {
+  return type == MG_T_WALL && colour == MG_C_WORST && state == 0;
+}
+__device__ __forceinline__ void bits_update_cell(uint32_t* bits, int x, int y, int type, int colour, int state) {
+  if (bits == nullptr) return;
+  const uint32_t op = cell_opaque(type, state) ? 1u : 0u, ne = type != MG_T_EMPTY ? 1u : 0u, cn = cell_canon(type, colour, state) ? 1u : 0u;
+  bits[x] = (bits[x] & ~((1u << y) | (1u << (16 + y)))) | (op << y) | (ne << (16 + y));
+  bits[16 + y] = (bits[16 + y] & ~((1u << x) | (1u << (16 + x)))) | (op << x) | (ne << (16 + x));
+  bits[32 + x] = (bits[32 + x] & ~(1u << y)) | (cn << y);
+  bits[32 + y] = (bits[32 + y] & ~(1u << (16 + x))) | (cn << (16 + x));
+}
+// rebuild all 48 words from the byte planes
+__device__ void bits_rebuild(const uint8_t* tp, uint32_t* bits, int W, int H, int S) {
+  if (bits == nullptr) return;
+  for (int i = 0; i < BITS_WORDS; ++i) bits[i] = 0u;
+  for (int x = 0; x < W; ++x)
+    for (int y = 0; y < H; ++y) {
+      const int idx = x * H + y;
+      const int t = tp[idx];
+      if (t != MG_T_EMPTY) bits_update_cell(bits, x, y, t, tp[S + idx], tp[2 * S + idx]);
+    }
+}
 
+// ---------------------------------------------------------------------------------------------
+// per-env game state while a thread runs step()/reset(): agent records transposed in shared memory, word w
+// of agent a at rec[(a*4+w)*RS] (RS = threads per CTA) -> bank == thread, conflict-free for any per-thread a.
+//   w0 = x | y<<8 | dir<<16 | flags<<24     w1 = carry_type | carry_colour<<8 | carry_state<<16 | bonus<<24
+//   w2 = stamp                               w3 = scratch (front-cell prefetch)
+// `tp` = the env's type plane in global memory (colour at +S, state at +2S); `bits` = its 48 bit-plane words.
+// ---------------------------------------------------------------------------------------------
 template <int RS>
 struct EnvCtx {
   const KP& p;
   uint32_t* rec;
   uint8_t* tp;
-  uint32_t* bits;  // this env's 32 bitboard words (or nullptr)
-  int sc, ep, tl;  // step_count, episode, lifetime steps
-  uint32_t w3;     // lo16 next stamp, hi16 error bits
-  bool dirty;      // planes modified
+  uint32_t* bits;
+  uint32_t* scratch;  // reset only: 32 transposed words (wall rows, other-object rows)
+  int sc, ep, tl;     // step_count, episode, lifetime steps
+  uint32_t w3;        // lo16 next stamp, hi16 error bits
+  bool dirty;         // planes modified during this step
   __device__ __forceinline__ uint32_t& R(int a, int w) { return rec[(a * 4 + w) * RS]; }
-  __device__ __forceinline__ void add_err(uint32_t bits) { w3 |= bits << 16; }
+  __device__ __forceinline__ void add_err(uint32_t bits_) { w3 |= bits_ << 16; }
   __device__ __forceinline__ uint32_t next_stamp() {
     const uint32_t s = w3 & 0xFFFFu;
     w3 = (w3 & 0xFFFF0000u) | ((s + 1u) & 0xFFFFu);
     return s;
   }
+  // static object type at (x, y): bit-planes first, byte plane only for the few "other" objects
+  __device__ __forceinline__ int static_type(int x, int y) {
+    if (bits != nullptr) {
+      if (!((bits[x] >> (16 + y)) & 1u)) return MG_T_EMPTY;
+      if ((bits[32 + x] >> y) & 1u) return MG_T_WALL;
+    }
+    return tp[x * p.H + y];
+  }
+  __device__ __forceinline__ void set_cell(int x, int y, int type, int colour, int state) {
+    const int idx = x * p.H + y;
+    tp[idx] = (uint8_t)type; tp[p.S + idx] = (uint8_t)colour; tp[2 * p.S + idx] = (uint8_t)state;
+    bits_update_cell(bits, x, y, type, colour, state);
+    dirty = true;
+  }
 };
-
-// Occupancy bitboards (DERIVED state, MgState.cellbits): word x = row x of the grid, word 16+y = column y;
-// low half = "opaque" (Wall, or Door that is not open: objects.py:281-282,330-331), high half = "non-empty".
-// They let the observe kernel build a view's transparency rows with one load + two shifts per row instead of
-// V byte loads.  Whoever writes a plane cell keeps them current.
-__device__ __forceinline__ bool cell_opaque(int type, int state) {
-  return type == MG_T_WALL || (type == MG_T_DOOR && state != MG_DOOR_OPEN);
-}
-__device__ __forceinline__ void bits_update_cell(uint32_t* bits, int x, int y, int type, int state) {
-  if (bits == nullptr) return;
-  const uint32_t op = cell_opaque(type, state) ? 1u : 0u, ne = type != MG_T_EMPTY ? 1u : 0u;
-  bits[x] = (bits[x] & ~((1u << y) | (1u << (16 + y)))) | (op << y) | (ne << (16 + y));
-  bits[16 + y] = (bits[16 + y] & ~((1u << x) | (1u << (16 + x)))) | (op << x) | (ne << (16 + x));
-}
-__device__ void bits_rebuild(const uint8_t* tp, uint32_t* bits, int W, int H, int S) {
-  if (bits == nullptr) return;
-  for (int x = 0; x < 16; ++x) {
-    uint32_t w = 0;
-    if (x < W)
-      for (int y = 0; y < H; ++y) {
-        const int t = tp[x * H + y];
-        if (t != MG_T_EMPTY) w |= (1u << (16 + y)) | ((cell_opaque(t, tp[2 * S + x * H + y]) ? 1u : 0u) << y);
-      }
-    bits[x] = w;
-  }
-  for (int y = 0; y < 16; ++y) {
-    uint32_t w = 0;
-    if (y < H)
-      for (int x = 0; x < W; ++x) w |= (((bits[x] >> y) & 1u) << x) | (((bits[x] >> (16 + y)) & 1u) << (16 + x));
-    bits[16 + y] = w;
-  }
-}
 
 // placed agent with the smallest stamp on (x, y), -1 if none: the reference's cell object when it is
 // an agent, else `static_obj.agents[0]` (base.py:547-572)
@@ -130,36 +145,30 @@ __device__ __forceinline__ int queue_head(EnvCtx<RS>& c, int x, int y) {
   return best;
 }
 
-// base.py:664-688 try_place_obj (agent >= 0: that agent; else the static triple)
 template <int RS>
-__device__ __forceinline__ bool try_place(EnvCtx<RS>& c, int x, int y, int agent, int type, int colour, int state) {
-  const int idx = x * c.p.H + y;
-  const int st = c.tp[idx];
-  const bool occupied = queue_head(c, x, y) >= 0;
-  bool ok;
-  if (st == MG_T_EMPTY && !occupied) ok = true;                                          // grid_obj is None
-  else if (agent < 0) ok = false;                                                        // base.py:678-679
-  else if (st != MG_T_EMPTY && !can_overlap_static(st, c.tp[2 * c.p.S + idx])) ok = false;
-  else ok = (c.p.flags & MG_F_GHOST) || !occupied;                                       // base.py:683-684
-  if (!ok) return false;
-  if (agent >= 0) {
-    const uint32_t w0 = c.R(agent, 0);
-    c.R(agent, 0) = (w0 & 0xFFFF0000u) | (uint32_t)x | ((uint32_t)y << 8) | ((uint32_t)MG_AF_PLACED << 24);
-    c.R(agent, 2) = c.next_stamp();
-  } else {
-    c.tp[idx] = (uint8_t)type; c.tp[c.p.S + idx] = (uint8_t)colour; c.tp[2 * c.p.S + idx] = (uint8_t)state;
-    c.dirty = true;
-  }
+__device__ __forceinline__ void put_agent(EnvCtx<RS>& c, int agent, int x, int y) {
+  const uint32_t w0 = c.R(agent, 0);
+  c.R(agent, 0) = (w0 & 0xFFFF0000u) | (uint32_t)x | ((uint32_t)y << 8) | ((uint32_t)MG_AF_PLACED << 24);
+  c.R(agent, 2) = c.next_stamp();
+}
+
+// base.py:664-688 try_place_obj for an AGENT in the live world (spawn delay / respawn inside step)
+template <int RS>
+__device__ __forceinline__ bool try_place_agent(EnvCtx<RS>& c, int x, int y, int agent) {
+  const int st = c.static_type(x, y);
+  if (st != MG_T_EMPTY && !can_overlap_static(st, c.tp[2 * c.p.S + x * c.p.H + y])) return false;  // base.py:678-679
+  if (!(c.p.flags & MG_F_GHOST) && queue_head(c, x, y) >= 0) return false;                          // base.py:683-684
+  put_agent(c, agent, x, y);
   return true;
 }
 
-// base.py:690-708 place_obj(top=(0,0), size=None)
+// base.py:690-708 place_obj(top=(0,0), size=None) for an agent in the live world
 template <int RS>
-__device__ __forceinline__ void place_obj(EnvCtx<RS>& c, Draws& d, int agent, int type, int colour, int state, int max_tries) {
-  for (int t = 0; t < max_tries; ++t) {
+__device__ __forceinline__ void place_agent(EnvCtx<RS>& c, Draws& d, int agent) {
+  for (int t = 0; t < 100000; ++t) {
     int x, y;
     d.next(c.p.W, c.p.H, x, y);
-    if (try_place(c, x, y, agent, type, colour, state)) return;
+    if (try_place_agent(c, x, y, agent)) return;
   }
   c.add_err(MG_ERR_PLACEMENT);  // RecursionError base.py:706
 }
@@ -172,45 +181,95 @@ __device__ __forceinline__ Draws make_draws(const KP& p, unsigned long long g, u
   return d;
 }
 
-// base.py:402-416 reset + _gen_grid (empty.py:9-16, cluttered.py:25-36, goalcycle.py:30-51); planes in shared memory
-template <int RS>
+// base.py:402-416 reset + _gen_grid (empty.py:9-16, cluttered.py:25-36, goalcycle.py:30-51), written straight to
+// the global planes.  A fresh world only ever holds canonical walls, a Goal and BonusTiles, so with BITS the
+// rejection sampling (base.py:690-708) runs on two row-mask sets kept in shared memory (walls / overlappable
+// others) and never reads a plane; the 48 bit-plane words are derived from them at the end.
+template <int RS, bool BITS>
 __device__ void env_reset(EnvCtx<RS>& c, unsigned long long g) {
   const KP& p = c.p;
-  const int W = p.W, H = p.H;
+  const int W = p.W, H = p.H, S = p.S;
   for (int a = 0; a < p.A; ++a) {  // agents.py:161-170 (dir survives)
     c.R(a, 0) = c.R(a, 0) & 0x00FF0000u;
     c.R(a, 1) = 0xFF000000u;
     c.R(a, 2) = 0;
   }
-  uint32_t* w = reinterpret_cast<uint32_t*>(c.tp);
-  for (int i = 0; i < 3 * p.S / 4; ++i) w[i] = 0u;
-  c.w3 &= 0xFFFF0000u & ~(ERR_RESET_PENDING << 16);
+  int4* z = reinterpret_cast<int4*>(c.tp);
+  for (int i = 0; i < 3 * S / 16; ++i) z[i] = make_int4(0, 0, 0, 0);
+  c.w3 &= 0xFFFF0000u;
+  uint32_t* wall = c.scratch;             // wall[x*RS]: bit y = canonical wall at (x, y)
+  uint32_t* other = c.scratch + 16 * RS;  // other[x*RS]: bit y = Goal / BonusTile (both can_overlap)
+  if (BITS) {
+    const uint32_t full = (1u << H) - 1u, ends = 1u | (1u << (H - 1));
+    for (int x = 0; x < 16; ++x) { wall[x * RS] = (x == 0 || x == W - 1) ? full : (x < W ? ends : 0u); other[x * RS] = 0u; }
+  }
   for (int i = 0; i < W; ++i) {  // wall_rect base.py:172-176
-    c.tp[i * H] = MG_T_WALL; c.tp[p.S + i * H] = MG_C_WORST;
-    c.tp[i * H + H - 1] = MG_T_WALL; c.tp[p.S + i * H + H - 1] = MG_C_WORST;
+    c.tp[i * H] = MG_T_WALL; c.tp[S + i * H] = MG_C_WORST;
+    c.tp[i * H + H - 1] = MG_T_WALL; c.tp[S + i * H + H - 1] = MG_C_WORST;
   }
   for (int j = 0; j < H; ++j) {
-    c.tp[j] = MG_T_WALL; c.tp[p.S + j] = MG_C_WORST;
-    c.tp[(W - 1) * H + j] = MG_T_WALL; c.tp[p.S + (W - 1) * H + j] = MG_C_WORST;
+    c.tp[j] = MG_T_WALL; c.tp[S + j] = MG_C_WORST;
+    c.tp[(W - 1) * H + j] = MG_T_WALL; c.tp[S + (W - 1) * H + j] = MG_C_WORST;
   }
-  c.dirty = true;
+  auto put_static = [&](int x, int y, int type, int colour, int state) {
+    const int idx = x * H + y;
+    c.tp[idx] = (uint8_t)type; c.tp[S + idx] = (uint8_t)colour; c.tp[2 * S + idx] = (uint8_t)state;
+    if (BITS) {
+      if (type == MG_T_WALL) { wall[x * RS] |= 1u << y; other[x * RS] &= ~(1u << y); }
+      else { other[x * RS] |= 1u << y; wall[x * RS] &= ~(1u << y); }
+    }
+  };
+  auto cell_type = [&](int x, int y) -> int {  // 0 empty, WALL, or GOAL standing for "overlappable other"
+    if (BITS) return ((wall[x * RS] >> y) & 1u) ? (int)MG_T_WALL : (((other[x * RS] >> y) & 1u) ? (int)MG_T_GOAL : (int)MG_T_EMPTY);
+    return c.tp[x * H + y];
+  };
   Draws d = make_draws(p, g, (uint32_t)c.ep, TAG_RESET);
-  if (p.goal_mode == MG_GOAL_FIXED) {  // put_obj base.py:655-662
-    const int idx = (W - 2) * H + (H - 2);
-    c.tp[idx] = MG_T_GOAL; c.tp[p.S + idx] = MG_C_GREEN; c.tp[2 * p.S + idx] = 0;
-  } else if (p.goal_mode == MG_GOAL_RANDOM) {
-    place_obj(c, d, -1, MG_T_GOAL, MG_C_GREEN, 0, 100);  // cluttered.py:28-29
-  }
-  for (int b = 0; b < p.n_bonus; ++b) place_obj(c, d, -1, MG_T_BONUS, MG_C_YELLOW, b, 100);  // goalcycle.py:34-46
-  for (int k = 0; k < p.n_clutter; ++k) place_obj(c, d, -1, MG_T_WALL, MG_C_WORST, 0, 100);  // cluttered.py:32-33
-  for (int a = 0; a < p.A; ++a)                                                                // base.py:409-412
+  // base.py:690-708 place_obj / :664-688 try_place_obj
+  auto place = [&](int agent, int type, int colour, int state, int max_tries) {
+    for (int t = 0; t < max_tries; ++t) {
+      int x, y;
+      d.next(W, H, x, y);
+      const int st = cell_type(x, y);
+      bool ok;
+      if (agent < 0) ok = (st == MG_T_EMPTY);  // statics are placed before any agent: empty cell <=> grid_obj is None
+      else {
+        const bool overlap = (st == MG_T_EMPTY) || (BITS ? st != MG_T_WALL : can_overlap_static(st, c.tp[2 * S + x * H + y]));
+        ok = overlap && ((p.flags & MG_F_GHOST) || queue_head(c, x, y) < 0);
+      }
+      if (!ok) continue;
+      if (agent >= 0) put_agent(c, agent, x, y); else put_static(x, y, type, colour, state);
+      return;
+    }
+    c.add_err(MG_ERR_PLACEMENT);  // RecursionError base.py:706
+  };
+  if (p.goal_mode == MG_GOAL_FIXED) put_static(W - 2, H - 2, MG_T_GOAL, MG_C_GREEN, 0);  // put_obj base.py:655-662 (replaces)
+  else if (p.goal_mode == MG_GOAL_RANDOM) place(-1, MG_T_GOAL, MG_C_GREEN, 0, 100);      // cluttered.py:28-29
+  for (int b = 0; b < p.n_bonus; ++b) place(-1, MG_T_BONUS, MG_C_YELLOW, b, 100);        // goalcycle.py:34-46
+  for (int k = 0; k < p.n_clutter; ++k) place(-1, MG_T_WALL, MG_C_WORST, 0, 100);        // cluttered.py:32-33
+  for (int a = 0; a < p.A; ++a)                                                          // base.py:409-412
     if (p.spawn_delay[a] == 0) {
-      place_obj(c, d, a, 0, 0, 0, 100000);
+      place(a, 0, 0, 0, 100000);
       c.R(a, 0) |= (uint32_t)MG_AF_ACTIVE << 24;
     }
   c.sc = 0;
   c.ep += 1;
-  bits_rebuild(c.tp, c.bits, W, H, p.S);
+  if (BITS) {  // derive the 48 words: rows, columns (transposes), canonical walls
+    uint32_t* bits = c.bits;
+    for (int x = 0; x < 16; ++x) {
+      const uint32_t wl = wall[x * RS], ot = other[x * RS];
+      bits[x] = wl | ((wl | ot) << 16);
+      bits[32 + x] = wl;
+    }
+    for (int y = 0; y < 16; ++y) {
+      uint32_t opq = 0, ne = 0;
+      for (int x = 0; x < 16; ++x) {
+        const uint32_t wl = (wall[x * RS] >> y) & 1u, ot = (other[x * RS] >> y) & 1u;
+        opq |= wl << x; ne |= (wl | ot) << x;
+      }
+      bits[16 + y] = opq | (ne << 16);
+      bits[32 + y] |= opq << 16;
+    }
+  }
 }
 
 // BonusTile.get_reward objects.py:180-206
@@ -249,8 +308,28 @@ __device__ __forceinline__ uint32_t decode_order(uint32_t pidx, int A) {
   return order;
 }
 
-// base.py:501-649 step without the obs; returns done
+// front-cell word of an agent: type of the cell it faces | its state << 8 | type of the cell it stands on << 16
+// (slow path: used when the planes changed earlier in the same step)
 template <int RS>
+__device__ __forceinline__ uint32_t front_cells(EnvCtx<RS>& c, int cx, int cy, int fx, int fy, bool inb) {
+  const int H = c.p.H, S = c.p.S;
+  uint32_t pf = 0;
+  if (inb) {
+    const int ft = c.static_type(fx, fy);
+    pf = (uint32_t)ft;
+    if (ft == MG_T_DOOR || ft == MG_T_BONUS) pf |= (uint32_t)c.tp[2 * S + fx * H + fy] << 8;
+  }
+  return pf | ((uint32_t)c.static_type(cx, cy) << 16);
+}
+// type of the static object at (x, y) given the row word and the canonical-wall word of row x
+__device__ __forceinline__ int type_from_words(uint32_t roww, uint32_t canw, int y, const uint8_t* tp, int idx) {
+  if (!((roww >> (16 + y)) & 1u)) return MG_T_EMPTY;
+  if ((canw >> y) & 1u) return MG_T_WALL;
+  return tp[idx];  // one of the few other objects: byte plane
+}
+
+// base.py:501-649 step without the obs; returns done
+template <int RS, bool BITS, int AMAX>
 __device__ bool env_step(EnvCtx<RS>& c, unsigned long long g, const int32_t* __restrict__ act, double* __restrict__ rew) {
   const KP& p = c.p;
   const int W = p.W, H = p.H, A = p.A, S = p.S;
@@ -259,28 +338,59 @@ __device__ bool env_step(EnvCtx<RS>& c, unsigned long long g, const int32_t* __r
   for (int a = 0; a < A; ++a) {  // base.py:503-506
     const uint32_t fl = c.R(a, 0) >> 24;
     if (!(fl & MG_AF_ACTIVE) && !(fl & MG_AF_DONE) && c.sc >= p.spawn_delay[a]) {
-      place_obj(c, d, a, 0, 0, 0, 100000);
+      place_agent(c, d, a);
       c.R(a, 0) |= (uint32_t)MG_AF_ACTIVE << 24;
     }
   }
   c.sc += 1;  // base.py:512
-  // Prefetch, for every agent at once, the cells its action can touch (the cell in front: type + state, the
-  // cell under it: type): independent loads -> one memory round trip instead of one per agent.  An agent's
-  // own pos/dir only change when it is processed, so the addresses are final; plane bytes are re-read on
-  // the slow path below if an earlier agent of this step edited the planes (pickup / drop / toggle).
+  // Look up, for every agent at once, the cells its action can touch, together with its action: all loads of
+  // this block are unconditional and independent (the bit-plane words of the row in front of / under each
+  // agent), so they overlap into ONE memory round trip instead of one per agent and cell.  An agent's own
+  // pos/dir only change when it is processed, so the addresses are final; the lookup is redone below if an
+  // earlier agent of this step edited the planes (pickup / drop / toggle).  w3 = front word | action << 24.
+  {
+    uint32_t wf[AMAX], cf[AMAX], wc[AMAX], cc[AMAX];
+    int act_r[AMAX];
 #pragma unroll
-  for (int a = 0; a < MG_MAX_AGENTS; ++a) {
-    if (a < A) {
-      const uint32_t w0 = c.R(a, 0);
-      uint32_t pf = 0;
-      if ((w0 >> 24) & MG_AF_ACTIVE) {
+    for (int a = 0; a < AMAX; ++a) {
+      wf[a] = cf[a] = wc[a] = cc[a] = 0u; act_r[a] = 0;
+      if (a < A) {
+        act_r[a] = act[a];
+        const uint32_t w0 = c.R(a, 0);
         const int cx = (int)(w0 & 0xFFu), cy = (int)((w0 >> 8) & 0xFFu), dir = (int)((w0 >> 16) & 3u);
-        const int fx = cx + ((dir == 0) ? 1 : (dir == 2) ? -1 : 0), fy = cy + ((dir == 1) ? 1 : (dir == 3) ? -1 : 0);
-        const bool inb = (unsigned)fx < (unsigned)W && (unsigned)fy < (unsigned)H;
-        const int fidx = inb ? fx * H + fy : 0;
-        pf = (uint32_t)c.tp[fidx] | ((uint32_t)c.tp[2 * S + fidx] << 8) | ((uint32_t)c.tp[cx * H + cy] << 16);
+        const int fx = cx + ((dir == 0) ? 1 : (dir == 2) ? -1 : 0);
+        const int rx = ((unsigned)fx < (unsigned)W) ? fx : cx;  // row of the front cell (clamped: the value is unused if out of range)
+        if (BITS) {
+          const bool on = ((w0 >> 24) & MG_AF_ACTIVE) != 0 && cx < 16;
+          const uint32_t* bp = c.bits;
+          wf[a] = on ? bp[rx & 15] : 0u; cf[a] = on ? bp[32 + (rx & 15)] : 0u;
+          wc[a] = on ? bp[cx & 15] : 0u; cc[a] = on ? bp[32 + (cx & 15)] : 0u;
+        }
       }
-      c.R(a, 3) = pf;
+    }
+#pragma unroll
+    for (int a = 0; a < AMAX; ++a) {
+      if (a < A) {
+        const uint32_t w0 = c.R(a, 0);
+        const int action = act_r[a];
+        uint32_t pf = 0;
+        if ((w0 >> 24) & MG_AF_ACTIVE) {
+          const int cx = (int)(w0 & 0xFFu), cy = (int)((w0 >> 8) & 0xFFu), dir = (int)((w0 >> 16) & 3u);
+          const int fx = cx + ((dir == 0) ? 1 : (dir == 2) ? -1 : 0), fy = cy + ((dir == 1) ? 1 : (dir == 3) ? -1 : 0);
+          const bool inb = (unsigned)fx < (unsigned)W && (unsigned)fy < (unsigned)H;
+          if (BITS) {
+            if (inb) {
+              const int ft = type_from_words(wf[a], cf[a], fy, c.tp, fx * H + fy);
+              pf = (uint32_t)ft;
+              if (ft == MG_T_DOOR || ft == MG_T_BONUS) pf |= (uint32_t)c.tp[2 * S + fx * H + fy] << 8;
+            }
+            pf |= (uint32_t)type_from_words(wc[a], cc[a], cy, c.tp, cx * H + cy) << 16;
+          } else {
+            pf = front_cells(c, cx, cy, fx, fy, inb);
+          }
+        }
+        c.R(a, 3) = (pf & 0x00FFFFFFu) | ((uint32_t)min(max(action, 0), 255) << 24) | ((action < 0) ? 0xFF000000u : 0u);
+      }
     }
   }
   // base.py:514-516: one Philox word -> index of the permutation
@@ -291,7 +401,8 @@ __device__ bool env_step(EnvCtx<RS>& c, unsigned long long g, const int32_t* __r
   c.tl += 1;
   for (int q = 0; q < A; ++q) {
     const int a = (int)((order >> (4 * q)) & 0xFu);
-    const int action = act[a];
+    uint32_t pf = c.R(a, 3);
+    const int action = (int)(pf >> 24);  // out-of-range actions were clamped to 255: still invalid
     double reward = 0.0;
     uint32_t w0 = c.R(a, 0);
     if ((w0 >> 24) & MG_AF_ACTIVE) {  // base.py:521
@@ -305,8 +416,7 @@ __device__ bool env_step(EnvCtx<RS>& c, unsigned long long g, const int32_t* __r
         const int fy = cy + ((dir == 1) ? 1 : (dir == 3) ? -1 : 0);
         const bool inb = (unsigned)fx < (unsigned)W && (unsigned)fy < (unsigned)H;
         const int fidx = inb ? fx * H + fy : 0;
-        uint32_t pf = c.R(a, 3);
-        if (c.dirty) pf = (uint32_t)c.tp[fidx] | ((uint32_t)c.tp[2 * S + fidx] << 8) | ((uint32_t)c.tp[cx * H + cy] << 16);
+        if (c.dirty) pf = front_cells(c, cx, cy, fx, fy, inb);
         const int ftype = inb ? (int)(pf & 0xFFu) : (int)MG_T_WALL;
         if (!inb) c.add_err(MG_ERR_STACK);  // grid.get asserts in-bounds (base.py:154-156); never hit with wall_rect
         if (action == MG_A_FORWARD) {  // base.py:538-585
@@ -335,28 +445,24 @@ __device__ bool env_step(EnvCtx<RS>& c, unsigned long long g, const int32_t* __r
           const uint32_t w1 = c.R(a, 1);
           if (ftype != MG_T_EMPTY && ((PICKUP_MASK >> ftype) & 1u) && (w1 & 0xFFu) == 0u) {
             c.R(a, 1) = (w1 & 0xFF000000u) | (uint32_t)ftype | ((uint32_t)c.tp[S + fidx] << 8) | ((uint32_t)c.tp[2 * S + fidx] << 16);
-            c.tp[fidx] = 0; c.tp[S + fidx] = 0; c.tp[2 * S + fidx] = 0;
-            bits_update_cell(c.bits, fx, fy, 0, 0);
-            c.dirty = true;
+            c.set_cell(fx, fy, 0, 0, 0);
           }
         } else if (action == MG_A_DROP) {  // base.py:600-606
           const uint32_t w1 = c.R(a, 1);
           if (inb && ftype == MG_T_EMPTY && (w1 & 0xFFu) != 0u && queue_head(c, fx, fy) < 0) {
-            c.tp[fidx] = (uint8_t)(w1 & 0xFFu); c.tp[S + fidx] = (uint8_t)((w1 >> 8) & 0xFFu); c.tp[2 * S + fidx] = (uint8_t)((w1 >> 16) & 0xFFu);
+            c.set_cell(fx, fy, (int)(w1 & 0xFFu), (int)((w1 >> 8) & 0xFFu), (int)((w1 >> 16) & 0xFFu));
             c.R(a, 1) = w1 & 0xFF000000u;
-            bits_update_cell(c.bits, fx, fy, (int)(w1 & 0xFFu), (int)((w1 >> 16) & 0xFFu));
-            c.dirty = true;
           }
         } else {  // MG_A_TOGGLE base.py:609-613, Door.toggle objects.py:333-346
           if (ftype == MG_T_DOOR) {
             const uint32_t w1 = c.R(a, 1);
-            const int fstate = (int)((pf >> 8) & 0xFFu);
+            const int fstate = (int)((pf >> 8) & 0xFFu), fcol = c.tp[S + fidx];
             int ns = fstate;
             if (fstate == MG_DOOR_LOCKED) {
-              if ((w1 & 0xFFu) == MG_T_KEY && ((w1 >> 8) & 0xFFu) == c.tp[S + fidx]) ns = MG_DOOR_CLOSED;
+              if ((w1 & 0xFFu) == MG_T_KEY && (int)((w1 >> 8) & 0xFFu) == fcol) ns = MG_DOOR_CLOSED;
             } else if (fstate == MG_DOOR_CLOSED) ns = MG_DOOR_OPEN;
             else if (fstate == MG_DOOR_OPEN) ns = MG_DOOR_CLOSED;
-            if (ns != fstate) { c.tp[2 * S + fidx] = (uint8_t)ns; bits_update_cell(c.bits, fx, fy, MG_T_DOOR, ns); c.dirty = true; }
+            if (ns != fstate) c.set_cell(fx, fy, MG_T_DOOR, fcol, ns);
           } else if (ftype == MG_T_BOX) c.add_err(MG_ERR_TOGGLE);  // Box.toggle(self) objects.py:381
         }
       } else if (action != MG_A_DONE) {
@@ -372,7 +478,7 @@ __device__ bool env_step(EnvCtx<RS>& c, unsigned long long g, const int32_t* __r
       if (p.flags & MG_F_RESPAWN) {
         c.R(a, 0) = w0 & 0x00FF0000u;  // agent.reset(new_episode=False) agents.py:161-166
         c.R(a, 1) = c.R(a, 1) & 0xFF000000u;
-        place_obj(c, d, a, 0, 0, 0, 100000);
+        place_agent(c, d, a);
         c.R(a, 0) |= (uint32_t)MG_AF_ACTIVE << 24;
         all_done = false;
       } else {
@@ -402,23 +508,26 @@ __device__ __forceinline__ void mark_heads(EnvCtx<RS>& c) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// step kernel: one THREAD per env, world state read/written in place in global memory (a step
-// touches two cells per agent; staging the planes would move 100x more bytes).  No grid-wide or
-// block-wide dependency: 64 resident warps per SM hide the latency of the scattered cell reads.
+// per-env kernels (one THREAD per env, world state in place in global memory)
+//   MODE 0: env.step (+ auto-reset of finished envs)   MODE 1: env.reset (mask or all)   MODE 2: sync derived state
 // ---------------------------------------------------------------------------------------------
-constexpr int STEP_THREADS = 128;
+constexpr int ENV_THREADS = 128;
 
-__global__ void __launch_bounds__(STEP_THREADS) step_kernel(const KP p) {
+template <int MODE, bool BITS, int AMAX>
+__global__ void __launch_bounds__(ENV_THREADS) env_kernel(const KP p) {
   extern __shared__ __align__(128) unsigned char smem[];
   uint32_t* s_rec = reinterpret_cast<uint32_t*>(smem);
-  const long long env = (long long)blockIdx.x * STEP_THREADS + threadIdx.x;
+  uint32_t* s_scr = s_rec + p.A * 4 * ENV_THREADS;
+  const long long env = (long long)blockIdx.x * ENV_THREADS + threadIdx.x;
   if (env >= p.B) return;
+  if (MODE == 1 && p.reset_mask != nullptr && p.reset_mask[env] == 0) return;
   const int A = p.A;
-  EnvCtx<STEP_THREADS> c{p, s_rec + threadIdx.x, p.grid + env * 3 * p.S, p.cellbits ? p.cellbits + env * 32 : nullptr, 0, 0, 0, 0u, false};
+  EnvCtx<ENV_THREADS> c{p, s_rec + threadIdx.x, p.grid + env * 3 * p.S, BITS ? p.cellbits + env * BITS_WORDS : nullptr,
+                        s_scr + threadIdx.x, 0, 0, 0, 0u, false};
   int4* arec = reinterpret_cast<int4*>(p.agents) + env * A;
   const int4 er = reinterpret_cast<const int4*>(p.envrec)[env];
 #pragma unroll
-  for (int a = 0; a < MG_MAX_AGENTS; ++a) {
+  for (int a = 0; a < AMAX; ++a) {
     if (a < A) {
       const int4 r = arec[a];
       c.R(a, 0) = (uint32_t)r.x; c.R(a, 1) = (uint32_t)r.y; c.R(a, 2) = (uint32_t)r.z;
@@ -426,21 +535,27 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel(const KP p) {
   }
   c.sc = er.x; c.ep = er.y; c.tl = er.z; c.w3 = (uint32_t)er.w;
   const unsigned long long g = (unsigned long long)(p.env_offset + env);
-  const bool dn = env_step(c, g, p.actions + env * A, p.rewards + env * A);
-  p.done[env] = dn ? 1 : 0;
-  if (dn && p.autoreset) c.w3 |= ERR_RESET_PENDING << 16;  // the reset+observe kernel regenerates the planes in shared memory
+  if (MODE == 0) {
+    const bool dn = env_step<ENV_THREADS, BITS, AMAX>(c, g, p.actions + env * A, p.rewards + env * A);
+    p.done[env] = dn ? 1 : 0;
+    if (dn && p.autoreset) env_reset<ENV_THREADS, BITS>(c, g);
+  } else if (MODE == 1) {
+    env_reset<ENV_THREADS, BITS>(c, g);
+  } else {
+    bits_rebuild(c.tp, c.bits, p.W, p.H, p.S);
+  }
   mark_heads(c);
-  for (int a = 0; a < A; ++a) arec[a] = make_int4((int)c.R(a, 0), (int)c.R(a, 1), (int)c.R(a, 2), 0);  // word 3 was prefetch scratch
-  reinterpret_cast<int4*>(p.envrec)[env] = make_int4(c.sc, c.ep, c.tl, (int)c.w3);
+  for (int a = 0; a < A; ++a) arec[a] = make_int4((int)c.R(a, 0), (int)c.R(a, 1), (int)c.R(a, 2), 0);
+  if (MODE != 2) reinterpret_cast<int4*>(p.envrec)[env] = make_int4(c.sc, c.ep, c.tl, (int)c.w3);
 }
 
 // ---------------------------------------------------------------------------------------------
 // egocentric view of one agent (thread == view): gen_obs_grid (base.py:418-451)
 //
-// The VxV crop is gathered in WORLD orientation along per-thread strides: u walks the axis the agent
-// faces along, v the axis across (so that a view row of the reference's rotated grid is a run of v at
-// fixed u).  The reference's rotation (rotate_grid, base.py:67-80, rot_k = dir+1) then reduces to an
-// optional reversal of the row order (dir 0,1) and an optional bit reversal inside rows (dir 1,2):
+// The VxV crop is described in WORLD orientation along per-thread axes: u walks the axis the agent faces
+// along, v the axis across (so that a view row of the reference's rotated grid is a run of v at fixed u).
+// The reference's rotation (rotate_grid, base.py:67-80, rot_k = dir+1) then reduces to an optional reversal
+// of the row order (dir 0,1) and an optional bit reversal inside rows (dir 1,2):
 //   dir 0: view[a][b] = sub[V-1-b][a]      rows flipped
 //   dir 1: view[a][b] = sub[V-1-a][V-1-b]  rows flipped, bits reversed (u <-> y, v <-> x)
 //   dir 2: view[a][b] = sub[b][V-1-a]      bits reversed
@@ -468,11 +583,11 @@ __device__ __forceinline__ ViewGeom view_geom(int px, int py, int dir, int V, in
   return g;
 }
 
-// What the view thread needs after line of sight: visibility and non-empty masks in VIEW orientation,
-// packed with a row stride of 8 bits (bit 8*(b&3) + a of the lo word for rows 0..3, of the hi word for
-// rows 4..7), and the plane offset of view cell (a, b): cell_idx = row0 + b*ustep + a*vstep.
+// What the view thread needs after line of sight: visibility / non-empty / canonical-wall masks in VIEW
+// orientation, packed with a row stride of 8 bits (bit 8*(b&3) + a of the lo word for rows 0..3, of the hi
+// word for rows 4..7), and the plane offset of view cell (a, b): cell_idx = row0 + b*ustep + a*vstep.
 struct PackedView {
-  uint32_t vis_lo, vis_hi, ne_lo, ne_hi;
+  uint32_t vis_lo, vis_hi, ne_lo, ne_hi, cw_lo, cw_hi;
   int row0, ustep, vstep;
   __device__ __forceinline__ bool visible(int a, int b) const { return (((b < 4 ? vis_lo : vis_hi) >> (8 * (b & 3) + a)) & 1u) != 0; }
   __device__ __forceinline__ bool nonempty(int a, int b) const { return (((b < 4 ? ne_lo : ne_hi) >> (8 * (b & 3) + a)) & 1u) != 0; }
@@ -487,26 +602,31 @@ __device__ __forceinline__ void pack_rows(const uint32_t (&r)[V], uint32_t& lo, 
   }
 }
 
-// transparency / non-empty rows from the occupancy bitboards (W, H <= 16): one word per view row
+// transparency / non-empty / canonical-wall rows from the bit-planes: two words per view row
 template <int V>
-__device__ __forceinline__ void rows_from_bits(const uint32_t* __restrict__ bits /* this env's 32 words */, const ViewGeom& g,
-                                               uint32_t (&T)[V], uint32_t (&NE)[V]) {
+__device__ __forceinline__ void rows_from_bits(const uint32_t* __restrict__ bits /* this env's 48 words */, const ViewGeom& g,
+                                               uint32_t (&T)[V], uint32_t (&NE)[V], uint32_t (&CW)[V]) {
   constexpr uint32_t RM = (1u << V) - 1u;
   const uint32_t* bp = bits + (g.vertical ? 16 : 0);
-  const int sh = g.v0 + 8;  // >= 1: the 16 board bits are parked at bits 8..23 before shifting right
+  const int sh = g.v0 + 8;                  // >= 1: the 16 board bits are parked at bits 8..23 before shifting right
+  const int csh = g.vertical ? 16 : 0;      // canonical walls: column half / row half of word 32+i
 #pragma unroll
   for (int b = 0; b < V; ++b) {
     const int idx = g.u0 + (g.flip ? V - 1 - b : b);
-    const uint32_t w = ((unsigned)idx < (unsigned)g.Lu) ? bp[idx] : 0u;  // rows outside the world: empty, transparent
+    const bool in = (unsigned)idx < (unsigned)g.Lu;  // rows outside the world: empty, transparent
+    const uint32_t w = in ? bp[idx] : 0u;
+    const uint32_t cwd = in ? bits[32 + idx] : 0u;
     uint32_t opq = (((w & 0xFFFFu) << 8) >> sh) & RM;
     uint32_t ne = (((w >> 16) << 8) >> sh) & RM;
-    if (g.rev) { opq = rev_bits<V>(opq); ne = rev_bits<V>(ne); }
+    uint32_t cw = ((((cwd >> csh) & 0xFFFFu) << 8) >> sh) & RM;
+    if (g.rev) { opq = rev_bits<V>(opq); ne = rev_bits<V>(ne); cw = rev_bits<V>(cw); }
     T[b] = ~opq & RM;
     NE[b] = ne;
+    CW[b] = cw;
   }
 }
 
-// the same rows gathered byte by byte from the type plane (any grid size)
+// the same rows gathered byte by byte from the type plane staged in shared memory (any grid size)
 template <int V>
 __device__ __forceinline__ void rows_from_planes(const KP& p, const uint8_t* __restrict__ tp, const ViewGeom& g, uint32_t (&T)[V],
                                                  uint32_t (&NE)[V]) {
@@ -558,9 +678,13 @@ template <int V, bool BITS>
 __device__ __forceinline__ PackedView view_masks(const KP& p, const uint8_t* __restrict__ tp, const uint32_t* __restrict__ bits,
                                                  const ViewGeom& g) {
   constexpr uint32_t RM = (1u << V) - 1u;
-  uint32_t T[V], NE[V], M[V];
-  if (BITS) rows_from_bits<V>(bits, g, T, NE);
-  else rows_from_planes<V>(p, tp, g, T, NE);
+  uint32_t T[V], NE[V], CW[V], M[V];
+  if (BITS) rows_from_bits<V>(bits, g, T, NE, CW);
+  else {
+    rows_from_planes<V>(p, tp, g, T, NE);
+#pragma unroll
+    for (int b = 0; b < V; ++b) CW[b] = 0u;
+  }
   if (p.flags & MG_F_SEE_THROUGH) {  // agents.py:294-295
 #pragma unroll
     for (int b = 0; b < V; ++b) M[b] = RM;
@@ -570,6 +694,7 @@ __device__ __forceinline__ PackedView view_masks(const KP& p, const uint8_t* __r
   PackedView pv;
   pack_rows<V>(M, pv.vis_lo, pv.vis_hi);
   pack_rows<V>(NE, pv.ne_lo, pv.ne_hi);
+  pack_rows<V>(CW, pv.cw_lo, pv.cw_hi);
   pv.ustep = g.flip ? -g.su : g.su;
   pv.vstep = g.rev ? -g.sv : g.sv;
   pv.row0 = g.topX * p.H + g.topY + (g.flip ? (V - 1) * g.su : 0) + (g.rev ? (V - 1) * g.sv : 0);
@@ -587,7 +712,8 @@ __device__ __forceinline__ bool world_to_view(const ViewGeom& g, int qx, int qy,
   return true;
 }
 
-// visible non-empty cells of rows [B0, B0+4) of the view: WorldObj.encode (objects.py:90-99) into the staging tile
+// cells of rows [B0, B0+4) selected by m: WorldObj.encode (objects.py:90-99) from the byte planes `tp`
+// (shared memory on the byte path, global memory for the rare non-wall objects on the bit-plane path)
 template <int V, int B0>
 __device__ __forceinline__ void encode_cells(uint32_t m, const PackedView& pv, const uint8_t* __restrict__ tp, int S, uint8_t* __restrict__ out) {
   while (m) {
@@ -600,41 +726,57 @@ __device__ __forceinline__ void encode_cells(uint32_t m, const PackedView& pv, c
   }
 }
 
+// visible canonical walls of rows [B0, B0+4): constants (8, 9, 0), no plane access, no loop: every store has a
+// compile-time offset into the staging tile
+template <int V, int B0>
+__device__ __forceinline__ void encode_walls(uint32_t m, uint8_t* __restrict__ out) {
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    if (B0 + r < V) {
+#pragma unroll
+      for (int a = 0; a < V; ++a) {
+        if ((m >> (8 * r + a)) & 1u) {
+          out[a * (V * 3) + (B0 + r) * 3 + 0] = MG_T_WALL;
+          out[a * (V * 3) + (B0 + r) * 3 + 1] = MG_C_WORST;
+        }
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
-// reset + observe kernel (32 envs per CTA, planes staged in shared memory by one bulk-async copy)
-//   RESET: 0 = none, 1 = envs whose step ended the episode (ERR_RESET_PENDING), 2 = explicit (mask or all)
-//   OBS  : 0 = none, 1 = encoded (MultiGrid.encode base.py:196-214), 2 = RGB tiles (base.py:301-331)
-//   TS4  : RGB only: tile rows are whole 32-bit words (ts % 4 == 0) -> 16-byte store path
-//   BITS : transparency rows come from the occupancy bitboards (W, H <= 16) instead of byte gathers
+// observe kernel: 32 envs per CTA, one thread per agent view
+//   OBS : 1 = encoded (MultiGrid.encode base.py:196-214), 2 = RGB tiles (base.py:301-331)
+//   TS4 : RGB only: tile rows are whole 32-bit words (ts % 4 == 0) -> 16-byte store path
+//   BITS: world described by the bit-planes (W, H <= 16) / by the byte planes staged in shared memory
 // ---------------------------------------------------------------------------------------------
-template <int RESET, int OBS, int V, bool TS4, bool BITS>
-__global__ void __launch_bounds__(32 * MG_MAX_AGENTS) mg_kernel(const KP p) {
+template <int OBS, int V, bool TS4, bool BITS>
+__global__ void __launch_bounds__(32 * MG_MAX_AGENTS) obs_kernel(const KP p) {
   extern __shared__ __align__(128) unsigned char smem[];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x;
+  const int tid = threadIdx.x, nthreads = blockDim.x;
   const long long env0 = (long long)blockIdx.x * ENVS_PER_CTA;
   const int n_valid = (int)min((long long)ENVS_PER_CTA, p.B - env0);
   const int A = p.A, S = p.S;
   constexpr int VV = V * V;
 
-  uint8_t* s_grid = smem;
-  uint32_t* s_bits = reinterpret_cast<uint32_t*>(s_grid + ENVS_PER_CTA * 3 * S);
-  uint32_t* s_rec = s_bits + (BITS ? ENVS_PER_CTA * 32 : 0);
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_rec + A * 4 * 32);
+  uint8_t* s_grid = smem;                                                                    // byte path only
+  uint32_t* s_bits = reinterpret_cast<uint32_t*>(s_grid + (BITS ? 0 : ENVS_PER_CTA * 3 * S));  // bit-plane path only
+  uint32_t* s_rec = s_bits + (BITS ? ENVS_PER_CTA * BITS_WORDS : 0);                         // agent records as stored: [env][a][4 words]
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_rec + ENVS_PER_CTA * A * 4);
   uint8_t* s_out = reinterpret_cast<uint8_t*>(s_bar + 2);  // 16-byte aligned: every block above is a multiple of 16 bytes
 
-  if (OBS != 0) {  // a reset regenerates the planes from scratch: only observing needs the old ones
-    if (tid == 0) mbar_init(s_bar, 1);
-    __syncthreads();
-    if (tid == 0) {
-      const uint32_t bytes = (uint32_t)n_valid * 3u * (uint32_t)S;
-      const uint32_t bbytes = BITS ? (uint32_t)n_valid * 128u : 0u;
-      mbar_expect_tx(s_bar, bytes + bbytes);
-      bulk_g2s(s_grid, p.grid + env0 * 3 * S, bytes, s_bar);
-      if (BITS) bulk_g2s(s_bits, p.cellbits + env0 * 32, bbytes, s_bar);
-    }
+  if (tid == 0) mbar_init(s_bar, 1);
+  __syncthreads();
+  if (tid == 0) {
+    const uint32_t wbytes = BITS ? (uint32_t)n_valid * (BITS_WORDS * 4u) : (uint32_t)n_valid * 3u * (uint32_t)S;
+    const uint32_t rbytes = (uint32_t)n_valid * (uint32_t)A * 16u;
+    mbar_expect_tx(s_bar, wbytes + rbytes);
+    if (BITS) bulk_g2s(s_bits, p.cellbits + env0 * BITS_WORDS, wbytes, s_bar);
+    else bulk_g2s(s_grid, p.grid + env0 * 3 * S, wbytes, s_bar);
+    bulk_g2s(s_rec, p.agents + env0 * A * 16, rbytes, s_bar);
   }
 
-  // ---- shared-memory output areas, prepared while the planes are in flight ----
+  // ---- shared-memory output areas, prepared while the copies are in flight ----
   // OBS 1: staging tile [32*A][V*V*3], zero filled (invisible / empty cells encode as 0)
   // OBS 2: tile-id map [32*A][VV] + orientation [32*A] + atlas copy (+ one shadow tile)
   const int tile_bytes = p.ts * p.ts * 3;
@@ -644,8 +786,9 @@ __global__ void __launch_bounds__(32 * MG_MAX_AGENTS) mg_kernel(const KP p) {
   if (OBS == 1) {
     int4* z = reinterpret_cast<int4*>(s_out);
     const int n16 = ENVS_PER_CTA * A * VV * 3 / 16;
+#pragma unroll 4
     for (int i = tid; i < n16; i += nthreads) z[i] = make_int4(0, 0, 0, 0);
-  } else if (OBS == 2) {
+  } else {
     const int slots = p.n_tiles * p.orient_slots;
     for (int i = tid; i < slots * tile_bytes; i += nthreads) {
       const int slot = i / tile_bytes, off = i - slot * tile_bytes;
@@ -657,53 +800,15 @@ __global__ void __launch_bounds__(32 * MG_MAX_AGENTS) mg_kernel(const KP p) {
       s_atlas[slots * tile_bytes + i] = (c == 0) ? 35 : (c == 1) ? 25 : 30;
     }
   }
-
-  // ---- warp 0: lane == env: records to shared memory, resets that are due ----
-  if (warp == 0) {
-    const bool valid = lane < n_valid;
-    const long long env = env0 + lane;
-    EnvCtx<32> c{p, s_rec + lane, s_grid + lane * 3 * S, BITS ? s_bits + lane * 32 : nullptr, 0, 0, 0, 0u, false};
-    bool do_reset = false;
-    if (valid) {
-      const int4* arec = reinterpret_cast<const int4*>(p.agents) + env * A;
-      for (int a = 0; a < A; ++a) {
-        const int4 r = arec[a];
-        c.R(a, 0) = (uint32_t)r.x; c.R(a, 1) = (uint32_t)r.y; c.R(a, 2) = (uint32_t)r.z; c.R(a, 3) = (uint32_t)r.w;
-      }
-      if (RESET != 0) {
-        const int4 er = reinterpret_cast<const int4*>(p.envrec)[env];
-        c.sc = er.x; c.ep = er.y; c.tl = er.z; c.w3 = (uint32_t)er.w;
-        do_reset = (RESET == 1) ? (((c.w3 >> 16) & ERR_RESET_PENDING) != 0) : (p.reset_mask == nullptr || p.reset_mask[env] != 0);
-      }
-    }
-    if (RESET != 0 && __any_sync(0xffffffffu, do_reset)) {
-      if (OBS != 0) mbar_wait(s_bar, 0);  // the incoming copy must land before the planes are rewritten
-      if (do_reset) {
-        env_reset(c, (unsigned long long)(p.env_offset + env));
-        mark_heads(c);
-        int4* arec = reinterpret_cast<int4*>(p.agents) + env * A;
-        for (int a = 0; a < A; ++a) arec[a] = make_int4((int)c.R(a, 0), (int)c.R(a, 1), (int)c.R(a, 2), (int)c.R(a, 3));
-        reinterpret_cast<int4*>(p.envrec)[env] = make_int4(c.sc, c.ep, c.tl, (int)c.w3);
-        fence_proxy_async_smem();  // regenerated planes (+ bitboards): shared -> global bulk copies
-        bulk_s2g(p.grid + env * 3 * S, c.tp, 3u * (uint32_t)S);
-        if (BITS) bulk_s2g(p.cellbits + env * 32, c.bits, 128u);
-        bulk_commit();
-      }
-    }
-  }
-  if (OBS == 0) {
-    if (RESET != 0 && warp == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-    return;
-  }
   mbar_wait(s_bar, 0);
   __syncthreads();
 
   // ---- every thread: one agent view ----
   if (tid < n_valid * A) {
     const int view = tid, le = view / A, a = view - le * A;
-    const uint32_t* rec = s_rec + le;
-    const uint8_t* tp = s_grid + le * 3 * S;
-    const uint32_t w0 = rec[(a * 4) * 32];
+    const uint32_t* rec = s_rec + le * A * 4;  // rec[q*4 + w]
+    const uint8_t* tp = BITS ? p.grid + (env0 + le) * 3 * S : s_grid + le * 3 * S;
+    const uint32_t w0 = rec[a * 4];
     const bool active = ((w0 >> 24) & MG_AF_ACTIVE) != 0;  // base.py:420-425
     const int px = (int)(w0 & 0xFFu), py = (int)((w0 >> 8) & 0xFFu), dir = (int)((w0 >> 16) & 3u);
     const int orient = (3 - dir) & 3;  // view orientation (0 - rot_k) % 4, base.py:130
@@ -716,13 +821,17 @@ __global__ void __launch_bounds__(32 * MG_MAX_AGENTS) mg_kernel(const KP p) {
     }
     if (active) {
       const ViewGeom g = view_geom(px, py, dir, V, p.vo, p.W, p.H);
-      const PackedView pv = view_masks<V, BITS>(p, tp, BITS ? s_bits + le * 32 : nullptr, g);
+      const PackedView pv = view_masks<V, BITS>(p, tp, BITS ? s_bits + le * BITS_WORDS : nullptr, g);
       if (OBS == 1) {
         uint8_t* out = s_out + view * (VV * 3);
-        encode_cells<V, 0>(pv.vis_lo & pv.ne_lo, pv, tp, S, out);
-        if (V > 4) encode_cells<V, 4>(pv.vis_hi & pv.ne_hi, pv, tp, S, out);
+        if (BITS) {
+          encode_walls<V, 0>(pv.vis_lo & pv.cw_lo, out);
+          if (V > 4) encode_walls<V, 4>(pv.vis_hi & pv.cw_hi, out);
+        }
+        encode_cells<V, 0>(pv.vis_lo & pv.ne_lo & ~pv.cw_lo, pv, tp, S, out);
+        if (V > 4) encode_cells<V, 4>(pv.vis_hi & pv.ne_hi & ~pv.cw_hi, pv, tp, S, out);
         for (int q = 0; q < A; ++q) {  // agents that are their cell's object: (13, colour, dir)
-          const uint32_t v0 = rec[(q * 4) * 32];
+          const uint32_t v0 = rec[q * 4];
           if (!((v0 >> 24) & AF_HEAD)) continue;
           int va, vb;
           if (!world_to_view<V>(g, (int)(v0 & 0xFFu), (int)((v0 >> 8) & 0xFFu), va, vb)) continue;
@@ -732,6 +841,7 @@ __global__ void __launch_bounds__(32 * MG_MAX_AGENTS) mg_kernel(const KP p) {
         }
       } else {  // OBS == 2: tile ids, render_tile base.py:275-299
         const int per_kind = 1 + 4 * A;
+        const uint8_t wall_tile = (uint8_t)(p.kind_of_type[MG_T_WALL] * per_kind);
         uint8_t* tl = s_tile + view * VV;
         uint32_t bad = 0;
 #pragma unroll
@@ -739,12 +849,14 @@ __global__ void __launch_bounds__(32 * MG_MAX_AGENTS) mg_kernel(const KP p) {
           const uint8_t* rowp = tp + pv.row0 + b * pv.ustep;
           const uint32_t visr = ((b < 4 ? pv.vis_lo : pv.vis_hi) >> (8 * (b & 3))) & 0xFFu;
           const uint32_t ner = ((b < 4 ? pv.ne_lo : pv.ne_hi) >> (8 * (b & 3))) & 0xFFu;
+          const uint32_t cwr = ((b < 4 ? pv.cw_lo : pv.cw_hi) >> (8 * (b & 3))) & 0xFFu;
 #pragma unroll
           for (int va = 0; va < V; ++va) {
             uint8_t t = (uint8_t)p.n_tiles;  // shadow
             if ((visr >> va) & 1u) {
               t = 0;
-              if ((ner >> va) & 1u) {
+              if ((cwr >> va) & 1u) t = wall_tile;
+              else if ((ner >> va) & 1u) {
                 const int kind = p.kind_of_type[rowp[va * pv.vstep]];
                 if (kind == 0xFF) bad = 1; else t = (uint8_t)(kind * per_kind);
               }
@@ -753,7 +865,7 @@ __global__ void __launch_bounds__(32 * MG_MAX_AGENTS) mg_kernel(const KP p) {
           }
         }
         for (int q = 0; q < A; ++q) {
-          const uint32_t v0 = rec[(q * 4) * 32];
+          const uint32_t v0 = rec[q * 4];
           if (!((v0 >> 24) & AF_HEAD)) continue;
           int va, vb;
           if (!world_to_view<V>(g, (int)(v0 & 0xFFu), (int)((v0 >> 8) & 0xFFu), va, vb)) continue;
@@ -775,11 +887,22 @@ __global__ void __launch_bounds__(32 * MG_MAX_AGENTS) mg_kernel(const KP p) {
   if (OBS == 1) {
     const long long total = (long long)n_valid * A * VV * 3;
     uint8_t* dst = p.obs + env0 * A * VV * 3;
-    const int n16 = (int)(total / 16);
-    const int4* src = reinterpret_cast<const int4*>(s_out);
-    for (int i = tid; i < n16; i += nthreads) st_stream_v4(reinterpret_cast<int4*>(dst) + i, src[i]);
-    for (int i = n16 * 16 + tid; i < total; i += nthreads) dst[i] = s_out[i];
-  } else if (OBS == 2) {
+    if ((total & 15) == 0) {
+      // the whole staging tile is one contiguous, 16-byte aligned run of the output tensor: a single
+      // shared->global bulk copy (TMA) moves it; nobody spends an instruction on the 14 KB
+      if (tid == 0) {
+        fence_proxy_async_smem();
+        bulk_s2g(dst, s_out, (uint32_t)total);
+        bulk_commit();
+        bulk_wait_read0();  // the CTA (and its shared memory) must outlive the read
+      }
+    } else {  // ragged last CTA
+      const int n16 = (int)(total / 16);
+      const int4* src = reinterpret_cast<const int4*>(s_out);
+      for (int i = tid; i < n16; i += nthreads) st_stream_v4(reinterpret_cast<int4*>(dst) + i, src[i]);
+      for (int i = n16 * 16 + tid; i < total; i += nthreads) dst[i] = s_out[i];
+    }
+  } else {
     const int ts = p.ts, n_views = n_valid * A;
     const int row_bytes = V * ts * 3;
     const long long view_bytes = (long long)row_bytes * V * ts;
@@ -821,26 +944,6 @@ __global__ void __launch_bounds__(32 * MG_MAX_AGENTS) mg_kernel(const KP p) {
       }
     }
   }
-  if (RESET != 0 && warp == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-}
-
-// recompute the DERIVED state (occupancy bitboards, queue-head flags) from the planes and agent records:
-// for callers that edited them by hand (mg_sync_derived)
-__global__ void sync_derived_kernel(const KP p) {
-  extern __shared__ __align__(128) unsigned char smem[];
-  uint32_t* s_rec = reinterpret_cast<uint32_t*>(smem);
-  const long long env = (long long)blockIdx.x * STEP_THREADS + threadIdx.x;
-  if (env >= p.B) return;
-  const int A = p.A;
-  EnvCtx<STEP_THREADS> c{p, s_rec + threadIdx.x, p.grid + env * 3 * p.S, p.cellbits ? p.cellbits + env * 32 : nullptr, 0, 0, 0, 0u, false};
-  int4* arec = reinterpret_cast<int4*>(p.agents) + env * A;
-  for (int a = 0; a < A; ++a) {
-    const int4 r = arec[a];
-    c.R(a, 0) = (uint32_t)r.x; c.R(a, 1) = (uint32_t)r.y; c.R(a, 2) = (uint32_t)r.z; c.R(a, 3) = (uint32_t)r.w;
-  }
-  mark_heads(c);
-  for (int a = 0; a < A; ++a) arec[a] = make_int4((int)c.R(a, 0), (int)c.R(a, 1), (int)c.R(a, 2), (int)c.R(a, 3));
-  bits_rebuild(c.tp, c.bits, p.W, p.H, p.S);
 }
 
 // zero-initialised family of freshly constructed envs (bonus_state = None)
@@ -848,7 +951,7 @@ __global__ void init_kernel(uint8_t* grid, uint8_t* agents, int32_t* envrec, uin
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long n_grid = B * 3 * S / 16, n_ag = B * A, n_er = B;
   if (i < n_grid) reinterpret_cast<int4*>(grid)[i] = make_int4(0, 0, 0, 0);
-  if (cellbits != nullptr && i < B * 8) reinterpret_cast<int4*>(cellbits)[i] = make_int4(0, 0, 0, 0);
+  if (cellbits != nullptr && i < B * (BITS_WORDS / 4)) reinterpret_cast<int4*>(cellbits)[i] = make_int4(0, 0, 0, 0);
   if (i < n_ag) reinterpret_cast<int4*>(agents)[i] = make_int4(0, (int)0xFF000000u, 0, 0);
   if (i < n_er) reinterpret_cast<int4*>(envrec)[i] = make_int4(0, 0, 0, 0);
 }
@@ -925,8 +1028,8 @@ static KP make_kp(const MgConfig* c, const MgState* st) {
   return p;
 }
 
-static size_t smem_bytes(const KP& p, int obs) {
-  size_t b = (size_t)ENVS_PER_CTA * 3 * p.S + (size_t)p.A * 4 * 32 * 4 + 16 + (p.cellbits ? (size_t)ENVS_PER_CTA * 128 : 0);
+static size_t obs_smem_bytes(const KP& p, int obs) {
+  size_t b = (p.cellbits ? (size_t)ENVS_PER_CTA * BITS_WORDS * 4 : (size_t)ENVS_PER_CTA * 3 * p.S) + (size_t)ENVS_PER_CTA * p.A * 16 + 16;
   if (obs == 1) b += (size_t)ENVS_PER_CTA * p.A * p.V * p.V * 3;
   if (obs == 2) {
     b += (size_t)ENVS_PER_CTA * p.A * p.V * p.V + (size_t)((ENVS_PER_CTA * p.A + 15) / 16) * 16;
@@ -935,10 +1038,10 @@ static size_t smem_bytes(const KP& p, int obs) {
   return (b + 15) / 16 * 16;
 }
 
-template <int RESET, int OBS, int V, bool TS4, bool BITS>
-static int launch_one(const KP& p, cudaStream_t s) {
-  const size_t sm = smem_bytes(p, OBS);
-  auto k = mg_kernel<RESET, OBS, V, TS4, BITS>;
+template <int OBS, int V, bool TS4, bool BITS>
+static int launch_obs_one(const KP& p, cudaStream_t s) {
+  const size_t sm = obs_smem_bytes(p, OBS);
+  auto k = obs_kernel<OBS, V, TS4, BITS>;
   static size_t configured[64] = {0};  // per instantiation and device
   int dev = 0;
   cudaGetDevice(&dev);
@@ -947,54 +1050,59 @@ static int launch_one(const KP& p, cudaStream_t s) {
     if (e != cudaSuccess) return (int)e;
     configured[dev & 63] = sm;
   }
-  const int threads = (OBS == 0) ? 32 : 32 * p.A;
   const long long blocks = (p.B + ENVS_PER_CTA - 1) / ENVS_PER_CTA;
   if (blocks <= 0) return 0;
-  k<<<(unsigned)blocks, threads, sm, s>>>(p);
+  k<<<(unsigned)blocks, 32 * p.A, sm, s>>>(p);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return (int)cudaGetLastError();
 }
 
-template <int RESET, int OBS, bool TS4, bool BITS>
-static int launch_v(const KP& p, cudaStream_t s) {
+template <int OBS, bool TS4, bool BITS>
+static int launch_obs_v(const KP& p, cudaStream_t s) {
   switch (p.V) {
-    case 3: return launch_one<RESET, OBS, 3, TS4, BITS>(p, s);
-    case 4: return launch_one<RESET, OBS, 4, TS4, BITS>(p, s);
-    case 5: return launch_one<RESET, OBS, 5, TS4, BITS>(p, s);
-    case 6: return launch_one<RESET, OBS, 6, TS4, BITS>(p, s);
-    case 7: return launch_one<RESET, OBS, 7, TS4, BITS>(p, s);
-    case 8: return launch_one<RESET, OBS, 8, TS4, BITS>(p, s);
+    case 3: return launch_obs_one<OBS, 3, TS4, BITS>(p, s);
+    case 4: return launch_obs_one<OBS, 4, TS4, BITS>(p, s);
+    case 5: return launch_obs_one<OBS, 5, TS4, BITS>(p, s);
+    case 6: return launch_obs_one<OBS, 6, TS4, BITS>(p, s);
+    case 7: return launch_obs_one<OBS, 7, TS4, BITS>(p, s);
+    case 8: return launch_obs_one<OBS, 8, TS4, BITS>(p, s);
   }
   return MG_E_CONFIG;
 }
 
-// reset (RESET: 0 none / 1 pending / 2 explicit) and/or observe (obs: 0 none / 1 encoded / 2 rgb)
-template <int RESET>
+// obs: 1 encoded / 2 rgb
 static int launch_obs(const KP& p, int obs, cudaStream_t s) {
   const bool bits = p.cellbits != nullptr;
-  if (obs == 0) return bits ? launch_one<RESET, 0, 7, false, true>(p, s) : launch_one<RESET, 0, 7, false, false>(p, s);
-  if (obs == 1) return bits ? launch_v<RESET, 1, false, true>(p, s) : launch_v<RESET, 1, false, false>(p, s);
-  if (p.ts % 4 == 0) return bits ? launch_v<RESET, 2, true, true>(p, s) : launch_v<RESET, 2, true, false>(p, s);
-  return bits ? launch_v<RESET, 2, false, true>(p, s) : launch_v<RESET, 2, false, false>(p, s);
+  if (obs == 1) return bits ? launch_obs_v<1, false, true>(p, s) : launch_obs_v<1, false, false>(p, s);
+  if (p.ts % 4 == 0) return bits ? launch_obs_v<2, true, true>(p, s) : launch_obs_v<2, true, false>(p, s);
+  return bits ? launch_obs_v<2, false, true>(p, s) : launch_obs_v<2, false, false>(p, s);
 }
 
-static int launch_step(const KP& p, cudaStream_t s) {
-  const long long blocks = (p.B + STEP_THREADS - 1) / STEP_THREADS;
+// per-env kernels: MODE 0 step (+auto-reset), 1 reset, 2 sync derived state
+template <int MODE>
+static int launch_env(const KP& p, cudaStream_t s) {
+  const long long blocks = (p.B + ENV_THREADS - 1) / ENV_THREADS;
   if (blocks <= 0) return 0;
-  step_kernel<<<(unsigned)blocks, STEP_THREADS, (size_t)STEP_THREADS * p.A * 16, s>>>(p);
+  const size_t sm = (size_t)ENV_THREADS * p.A * 16 + (size_t)ENV_THREADS * 32 * 4;
+  if (p.A <= 4) {
+    if (p.cellbits) env_kernel<MODE, true, 4><<<(unsigned)blocks, ENV_THREADS, sm, s>>>(p);
+    else env_kernel<MODE, false, 4><<<(unsigned)blocks, ENV_THREADS, sm, s>>>(p);
+  } else {
+    if (p.cellbits) env_kernel<MODE, true, MG_MAX_AGENTS><<<(unsigned)blocks, ENV_THREADS, sm, s>>>(p);
+    else env_kernel<MODE, false, MG_MAX_AGENTS><<<(unsigned)blocks, ENV_THREADS, sm, s>>>(p);
+  }
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return (int)cudaGetLastError();
 }
 
 static cudaEvent_t g_mid_event = nullptr;  // profiling hook: recorded between the two launches of a step
 
-// env.step: the step kernel, then (auto-reset and/or observation) in one more launch
+// env.step: the step kernel (incl. auto-reset), then the observation in one more launch
 static int launch_step_obs(const KP& p, int obs, cudaStream_t s) {
-  int e = launch_step(p, s);
+  int e = launch_env<0>(p, s);
   if (e) return e;
   if (g_mid_event) cudaEventRecord(g_mid_event, s);
-  if (p.autoreset) return launch_obs<1>(p, obs, s);
-  if (obs != 0) return launch_obs<0>(p, obs, s);
+  if (obs != 0) return launch_obs(p, obs, s);
   return 0;
 }
 
@@ -1011,7 +1119,7 @@ static int check_state(const MgConfig* c, const MgState* st) {
 extern "C" {
 
 int mg_version(void) { return 1; }
-const char* mg_build_info(void) { return "marlgrid_b200 sm_100a cp.async.bulk+mbarrier staging, 32 envs/CTA"; }
+const char* mg_build_info(void) { return "marlgrid_b200 sm_100a: per-env step kernel + bit-plane observe kernel (cp.async.bulk + mbarrier staging, 32 envs/CTA)"; }
 int mg_sizeof_config(void) { return (int)sizeof(MgConfig); }
 int mg_config_validate(const MgConfig* cfg) { return check_cfg(cfg); }
 int64_t mg_obs_bytes_per_env(const MgConfig* c, int rgb) {
@@ -1026,7 +1134,7 @@ int mg_init(const MgConfig* cfg, const MgState* st, mg_stream_t stream) {
   int e = check_state(cfg, st);
   if (e) return e;
   if (st->n_envs == 0) return 0;
-  const long long n = std::max<long long>(std::max<long long>(st->n_envs * 3 * cfg->plane_stride / 16, st->n_envs * cfg->n_agents), st->n_envs * 8);
+  const long long n = std::max<long long>(std::max<long long>(st->n_envs * 3 * cfg->plane_stride / 16, st->n_envs * cfg->n_agents), st->n_envs * (BITS_WORDS / 4));
   init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(st->grid, st->agents, st->envrec, st->cellbits, st->n_envs, cfg->n_agents, cfg->plane_stride);
   g_launches.fetch_add(1);
   return (int)cudaGetLastError();
@@ -1037,10 +1145,7 @@ int mg_sync_derived(const MgConfig* cfg, const MgState* st, mg_stream_t stream) 
   if (e) return e;
   if (st->n_envs == 0) return 0;
   KP p = make_kp(cfg, st);
-  const long long blocks = (p.B + STEP_THREADS - 1) / STEP_THREADS;
-  sync_derived_kernel<<<(unsigned)blocks, STEP_THREADS, (size_t)STEP_THREADS * p.A * 16, (cudaStream_t)stream>>>(p);
-  g_launches.fetch_add(1);
-  return (int)cudaGetLastError();
+  return launch_env<2>(p, (cudaStream_t)stream);
 }
 
 int mg_reset(const MgConfig* cfg, const MgState* st, const uint8_t* reset_mask, mg_stream_t stream) {
@@ -1048,7 +1153,7 @@ int mg_reset(const MgConfig* cfg, const MgState* st, const uint8_t* reset_mask, 
   if (e) return e;
   KP p = make_kp(cfg, st);
   p.reset_mask = reset_mask;
-  return launch_obs<2>(p, 0, (cudaStream_t)stream);
+  return launch_env<1>(p, (cudaStream_t)stream);
 }
 
 int mg_step(const MgConfig* cfg, const MgState* st, const int32_t* actions, double* rewards, uint8_t* done, int autoreset,
@@ -1067,7 +1172,7 @@ int mg_obs_encode(const MgConfig* cfg, const MgState* st, uint8_t* obs, mg_strea
   if (!obs || !aligned16(obs)) return MG_E_ARG;
   KP p = make_kp(cfg, st);
   p.obs = obs;
-  return launch_obs<0>(p, 1, (cudaStream_t)stream);
+  return launch_obs(p, 1, (cudaStream_t)stream);
 }
 
 static int atlas_mode(const MgConfig* cfg) { return (cfg->view_tile_size <= 10) ? 1 : 4; }  // empty_tile alpha == 0 (base.py:247): rotation-equivariant
@@ -1078,7 +1183,7 @@ int mg_obs_rgb(const MgConfig* cfg, const MgState* st, const uint8_t* atlas, uin
   if (!obs || !atlas || !aligned16(obs) || cfg->view_tile_size < 1) return MG_E_ARG;
   KP p = make_kp(cfg, st);
   p.obs = obs; p.atlas = atlas; p.orient_slots = atlas_mode(cfg);
-  return launch_obs<0>(p, 2, (cudaStream_t)stream);
+  return launch_obs(p, 2, (cudaStream_t)stream);
 }
 
 int mg_step_fused(const MgConfig* cfg, const MgState* st, const int32_t* actions, double* rewards, uint8_t* done, uint8_t* obs,
@@ -1180,7 +1285,7 @@ int mg_engine_create(MgEngine** out, const MgConfig* cfg, int64_t n_envs, int64_
   MG_CUDA(cudaMalloc(&en->st.grid, (size_t)n_envs * 3 * cfg->plane_stride));
   MG_CUDA(cudaMalloc(&en->st.agents, (size_t)n_envs * cfg->n_agents * MG_AGENT_REC));
   MG_CUDA(cudaMalloc(&en->st.envrec, (size_t)n_envs * MG_ENV_REC));
-  MG_CUDA(cudaMalloc(&en->st.cellbits, (size_t)n_envs * 128));
+  MG_CUDA(cudaMalloc(&en->st.cellbits, (size_t)n_envs * BITS_WORDS * 4));
   MG_CUDA(cudaMalloc(&en->d_actions, (size_t)n_envs * cfg->n_agents * sizeof(int32_t)));
   MG_CUDA(cudaMalloc(&en->d_rewards, (size_t)n_envs * cfg->n_agents * sizeof(double)));
   MG_CUDA(cudaMalloc(&en->d_done, (size_t)n_envs));
