@@ -170,8 +170,9 @@ int mg_obs_encode(const MgConfig* cfg, const MgState* st, uint8_t* obs, mg_strea
  * atlas: uint8 [n_tiles][4][ts][ts][3], n_tiles = (n_static_kinds+1)*(1+4A). */
 int mg_obs_rgb(const MgConfig* cfg, const MgState* st, const uint8_t* atlas, uint8_t* obs, mg_stream_t stream);
 
-/* step + autoreset + encoded obs in one call = two launches on `stream`: the step kernel (one thread per env),
- * then the reset+observe kernel (the benchmarked hot path). */
+/* step + autoreset + encoded obs in one call (the benchmarked hot path).  ONE launch (fused step+observe kernel)
+ * for bit-plane worlds in ghost mode without respawn / spawn delay; otherwise two launches on `stream`: the
+ * per-env step kernel, then the observe kernel. */
 int mg_step_fused(const MgConfig* cfg, const MgState* st, const int32_t* actions, double* rewards,
                   uint8_t* done, uint8_t* obs, int autoreset, mg_stream_t stream);
 
@@ -216,6 +217,9 @@ int64_t mg_launch_count(void);
 /* Profiling hook (bench.py): a cudaEvent_t recorded between the step kernel and the reset+observe kernel
  * of every following mg_step* call, so each kernel's duration can be read live; NULL disables it. */
 void mg_debug_set_mid_event(void* cuda_event);
+/* Test hook: != 0 makes mg_step_fused* use the two-launch path (per-env step kernel, then observe kernel) even
+ * where the single fused kernel applies, so both implementations stay covered. */
+void mg_debug_force_two_kernels(int on);
 
 #ifdef __cplusplus
 }

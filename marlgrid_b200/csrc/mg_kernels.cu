@@ -357,7 +357,7 @@ __device__ bool env_step(EnvCtx<RS>& c, unsigned long long g, const int32_t* __r
       if (a < A) {
         act_r[a] = act[a];
         const uint32_t w0 = c.R(a, 0);
-        const int cx = (int)(w0 & 0xFFu), cy = (int)((w0 >> 8) & 0xFFu), dir = (int)((w0 >> 16) & 3u);
+        const int cx = (int)(w0 & 0xFFu), dir = (int)((w0 >> 16) & 3u);
         const int fx = cx + ((dir == 0) ? 1 : (dir == 2) ? -1 : 0);
         const int rx = ((unsigned)fx < (unsigned)W) ? fx : cx;  // row of the front cell (clamped: the value is unused if out of range)
         if (BITS) {
@@ -514,7 +514,7 @@ __device__ __forceinline__ void mark_heads(EnvCtx<RS>& c) {
 constexpr int ENV_THREADS = 128;
 
 template <int MODE, bool BITS, int AMAX>
-__global__ void __launch_bounds__(ENV_THREADS) env_kernel(const KP p) {
+__global__ void __launch_bounds__(ENV_THREADS) env_kernel(const __grid_constant__ KP p) {
   extern __shared__ __align__(128) unsigned char smem[];
   uint32_t* s_rec = reinterpret_cast<uint32_t*>(smem);
   uint32_t* s_scr = s_rec + p.A * 4 * ENV_THREADS;
@@ -745,145 +745,138 @@ __device__ __forceinline__ void encode_walls(uint32_t m, uint8_t* __restrict__ o
 }
 
 // ---------------------------------------------------------------------------------------------
-// observe kernel: 32 envs per CTA, one thread per agent view
+// building blocks shared by the observe kernel and the fused step+observe kernel (32 envs per CTA, one thread
+// per agent view)
 //   OBS : 1 = encoded (MultiGrid.encode base.py:196-214), 2 = RGB tiles (base.py:301-331)
 //   TS4 : RGB only: tile rows are whole 32-bit words (ts % 4 == 0) -> 16-byte store path
 //   BITS: world described by the bit-planes (W, H <= 16) / by the byte planes staged in shared memory
 // ---------------------------------------------------------------------------------------------
-template <int OBS, int V, bool TS4, bool BITS>
-__global__ void __launch_bounds__(32 * MG_MAX_AGENTS) obs_kernel(const KP p) {
-  extern __shared__ __align__(128) unsigned char smem[];
-  const int tid = threadIdx.x, nthreads = blockDim.x;
-  const long long env0 = (long long)blockIdx.x * ENVS_PER_CTA;
-  const int n_valid = (int)min((long long)ENVS_PER_CTA, p.B - env0);
-  const int A = p.A, S = p.S;
-  constexpr int VV = V * V;
+template <int V>
+struct ObsSmem {
+  uint8_t* out;     // OBS 1: staging tile [32*A][V*V*3]
+  uint8_t* tile;    // OBS 2: tile-id map [32*A][V*V]
+  uint8_t* orient;  // OBS 2: view orientation [32*A]
+  uint8_t* atlas;   // OBS 2: atlas copy + one shadow tile
+};
 
-  uint8_t* s_grid = smem;                                                                    // byte path only
-  uint32_t* s_bits = reinterpret_cast<uint32_t*>(s_grid + (BITS ? 0 : ENVS_PER_CTA * 3 * S));  // bit-plane path only
-  uint32_t* s_rec = s_bits + (BITS ? ENVS_PER_CTA * BITS_WORDS : 0);                         // agent records as stored: [env][a][4 words]
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_rec + ENVS_PER_CTA * A * 4);
-  uint8_t* s_out = reinterpret_cast<uint8_t*>(s_bar + 2);  // 16-byte aligned: every block above is a multiple of 16 bytes
+template <int V>
+__device__ __forceinline__ ObsSmem<V> obs_smem(uint8_t* s_out, int A) {
+  ObsSmem<V> o;
+  o.out = s_out; o.tile = s_out;
+  o.orient = o.tile + ENVS_PER_CTA * A * V * V;
+  o.atlas = o.orient + ((ENVS_PER_CTA * A + 15) / 16) * 16;
+  return o;
+}
 
-  if (tid == 0) mbar_init(s_bar, 1);
-  __syncthreads();
-  if (tid == 0) {
-    const uint32_t wbytes = BITS ? (uint32_t)n_valid * (BITS_WORDS * 4u) : (uint32_t)n_valid * 3u * (uint32_t)S;
-    const uint32_t rbytes = (uint32_t)n_valid * (uint32_t)A * 16u;
-    mbar_expect_tx(s_bar, wbytes + rbytes);
-    if (BITS) bulk_g2s(s_bits, p.cellbits + env0 * BITS_WORDS, wbytes, s_bar);
-    else bulk_g2s(s_grid, p.grid + env0 * 3 * S, wbytes, s_bar);
-    bulk_g2s(s_rec, p.agents + env0 * A * 16, rbytes, s_bar);
-  }
-
-  // ---- shared-memory output areas, prepared while the copies are in flight ----
-  // OBS 1: staging tile [32*A][V*V*3], zero filled (invisible / empty cells encode as 0)
-  // OBS 2: tile-id map [32*A][VV] + orientation [32*A] + atlas copy (+ one shadow tile)
-  const int tile_bytes = p.ts * p.ts * 3;
-  uint8_t* s_tile = s_out;
-  uint8_t* s_orient = s_tile + ENVS_PER_CTA * A * VV;
-  uint8_t* s_atlas = s_orient + ((ENVS_PER_CTA * A + 15) / 16) * 16;
+// zero the staging tile (invisible / empty cells encode as 0) or copy the tile atlas (+ shadow tile)
+template <int OBS, int V>
+__device__ __forceinline__ void obs_prepare(const KP& p, const ObsSmem<V>& o, int tid, int nthreads) {
+  const int A = p.A;
   if (OBS == 1) {
-    int4* z = reinterpret_cast<int4*>(s_out);
-    const int n16 = ENVS_PER_CTA * A * VV * 3 / 16;
+    int4* z = reinterpret_cast<int4*>(o.out);
+    const int n16 = ENVS_PER_CTA * A * V * V * 3 / 16;
 #pragma unroll 4
     for (int i = tid; i < n16; i += nthreads) z[i] = make_int4(0, 0, 0, 0);
   } else {
+    const int tile_bytes = p.ts * p.ts * 3;
     const int slots = p.n_tiles * p.orient_slots;
     for (int i = tid; i < slots * tile_bytes; i += nthreads) {
       const int slot = i / tile_bytes, off = i - slot * tile_bytes;
       const int tile = slot / p.orient_slots, orient = slot - tile * p.orient_slots;
-      s_atlas[i] = p.atlas[(size_t)(tile * 4 + orient) * tile_bytes + off];
+      o.atlas[i] = p.atlas[(size_t)(tile * 4 + orient) * tile_bytes + off];
     }
     for (int i = tid; i < tile_bytes; i += nthreads) {  // COLORS['shadow'] objects.py:25, base.py:305
       const int c = i % 3;
-      s_atlas[slots * tile_bytes + i] = (c == 0) ? 35 : (c == 1) ? 25 : 30;
+      o.atlas[slots * tile_bytes + i] = (c == 0) ? 35 : (c == 1) ? 25 : 30;
     }
   }
-  mbar_wait(s_bar, 0);
-  __syncthreads();
+}
 
-  // ---- every thread: one agent view ----
-  if (tid < n_valid * A) {
-    const int view = tid, le = view / A, a = view - le * A;
-    const uint32_t* rec = s_rec + le * A * 4;  // rec[q*4 + w]
-    const uint8_t* tp = BITS ? p.grid + (env0 + le) * 3 * S : s_grid + le * 3 * S;
-    const uint32_t w0 = rec[a * 4];
-    const bool active = ((w0 >> 24) & MG_AF_ACTIVE) != 0;  // base.py:420-425
-    const int px = (int)(w0 & 0xFFu), py = (int)((w0 >> 8) & 0xFFu), dir = (int)((w0 >> 16) & 3u);
-    const int orient = (3 - dir) & 3;  // view orientation (0 - rot_k) % 4, base.py:130
-    if (OBS == 2) {
-      s_orient[view] = (uint8_t)((p.orient_slots == 4) ? orient : 0);
-      if (!active) {
-        const uint8_t shadow = (uint8_t)(p.n_tiles);  // one past the last tile: resolved to the shadow slot below
-        for (int i = 0; i < VV; ++i) s_tile[view * VV + i] = shadow;
-      }
+// one agent view: gen_obs_grid + encode / tile ids.  rec = the env's agent records [q*4 + w] in shared memory,
+// tp = the env's byte planes (global memory on the bit-plane path, shared memory on the byte path)
+template <int OBS, int V, bool BITS>
+__device__ __forceinline__ void obs_view(const KP& p, const ObsSmem<V>& o, int view, int a, long long env, const uint32_t* __restrict__ rec,
+                                         const uint8_t* __restrict__ tp, const uint32_t* __restrict__ bits) {
+  constexpr int VV = V * V;
+  const int A = p.A, S = p.S;
+  const uint32_t w0 = rec[a * 4];
+  const bool active = ((w0 >> 24) & MG_AF_ACTIVE) != 0;  // base.py:420-425
+  const int px = (int)(w0 & 0xFFu), py = (int)((w0 >> 8) & 0xFFu), dir = (int)((w0 >> 16) & 3u);
+  const int orient = (3 - dir) & 3;  // view orientation (0 - rot_k) % 4, base.py:130
+  if (OBS == 2) {
+    o.orient[view] = (uint8_t)((p.orient_slots == 4) ? orient : 0);
+    if (!active) {
+      const uint8_t shadow = (uint8_t)(p.n_tiles);  // one past the last tile: resolved to the shadow slot when expanding
+      for (int i = 0; i < VV; ++i) o.tile[view * VV + i] = shadow;
     }
-    if (active) {
-      const ViewGeom g = view_geom(px, py, dir, V, p.vo, p.W, p.H);
-      const PackedView pv = view_masks<V, BITS>(p, tp, BITS ? s_bits + le * BITS_WORDS : nullptr, g);
-      if (OBS == 1) {
-        uint8_t* out = s_out + view * (VV * 3);
-        if (BITS) {
-          encode_walls<V, 0>(pv.vis_lo & pv.cw_lo, out);
-          if (V > 4) encode_walls<V, 4>(pv.vis_hi & pv.cw_hi, out);
-        }
-        encode_cells<V, 0>(pv.vis_lo & pv.ne_lo & ~pv.cw_lo, pv, tp, S, out);
-        if (V > 4) encode_cells<V, 4>(pv.vis_hi & pv.ne_hi & ~pv.cw_hi, pv, tp, S, out);
-        for (int q = 0; q < A; ++q) {  // agents that are their cell's object: (13, colour, dir)
-          const uint32_t v0 = rec[q * 4];
-          if (!((v0 >> 24) & AF_HEAD)) continue;
-          int va, vb;
-          if (!world_to_view<V>(g, (int)(v0 & 0xFFu), (int)((v0 >> 8) & 0xFFu), va, vb)) continue;
-          if (!pv.visible(va, vb) || pv.nonempty(va, vb)) continue;
-          uint8_t* o = out + va * (V * 3) + vb * 3;
-          o[0] = MG_T_AGENT; o[1] = p.agent_color[q]; o[2] = (uint8_t)((v0 >> 16) & 3u);
-        }
-      } else {  // OBS == 2: tile ids, render_tile base.py:275-299
-        const int per_kind = 1 + 4 * A;
-        const uint8_t wall_tile = (uint8_t)(p.kind_of_type[MG_T_WALL] * per_kind);
-        uint8_t* tl = s_tile + view * VV;
-        uint32_t bad = 0;
+  }
+  if (!active) return;
+  const ViewGeom g = view_geom(px, py, dir, V, p.vo, p.W, p.H);
+  const PackedView pv = view_masks<V, BITS>(p, tp, bits, g);
+  if (OBS == 1) {
+    uint8_t* out = o.out + view * (VV * 3);
+    if (BITS) {
+      encode_walls<V, 0>(pv.vis_lo & pv.cw_lo, out);
+      if (V > 4) encode_walls<V, 4>(pv.vis_hi & pv.cw_hi, out);
+    }
+    encode_cells<V, 0>(pv.vis_lo & pv.ne_lo & ~pv.cw_lo, pv, tp, S, out);
+    if (V > 4) encode_cells<V, 4>(pv.vis_hi & pv.ne_hi & ~pv.cw_hi, pv, tp, S, out);
+    for (int q = 0; q < A; ++q) {  // agents that are their cell's object: (13, colour, dir)
+      const uint32_t v0 = rec[q * 4];
+      if (!((v0 >> 24) & AF_HEAD)) continue;
+      int va, vb;
+      if (!world_to_view<V>(g, (int)(v0 & 0xFFu), (int)((v0 >> 8) & 0xFFu), va, vb)) continue;
+      if (!pv.visible(va, vb) || pv.nonempty(va, vb)) continue;
+      uint8_t* oo = out + va * (V * 3) + vb * 3;
+      oo[0] = MG_T_AGENT; oo[1] = p.agent_color[q]; oo[2] = (uint8_t)((v0 >> 16) & 3u);
+    }
+  } else {  // OBS == 2: tile ids, render_tile base.py:275-299
+    const int per_kind = 1 + 4 * A;
+    const uint8_t wall_tile = (uint8_t)(p.kind_of_type[MG_T_WALL] * per_kind);
+    uint8_t* tl = o.tile + view * VV;
+    uint32_t bad = 0;
 #pragma unroll
-        for (int b = 0; b < V; ++b) {
-          const uint8_t* rowp = tp + pv.row0 + b * pv.ustep;
-          const uint32_t visr = ((b < 4 ? pv.vis_lo : pv.vis_hi) >> (8 * (b & 3))) & 0xFFu;
-          const uint32_t ner = ((b < 4 ? pv.ne_lo : pv.ne_hi) >> (8 * (b & 3))) & 0xFFu;
-          const uint32_t cwr = ((b < 4 ? pv.cw_lo : pv.cw_hi) >> (8 * (b & 3))) & 0xFFu;
+    for (int b = 0; b < V; ++b) {
+      const uint8_t* rowp = tp + pv.row0 + b * pv.ustep;
+      const uint32_t visr = ((b < 4 ? pv.vis_lo : pv.vis_hi) >> (8 * (b & 3))) & 0xFFu;
+      const uint32_t ner = ((b < 4 ? pv.ne_lo : pv.ne_hi) >> (8 * (b & 3))) & 0xFFu;
+      const uint32_t cwr = ((b < 4 ? pv.cw_lo : pv.cw_hi) >> (8 * (b & 3))) & 0xFFu;
 #pragma unroll
-          for (int va = 0; va < V; ++va) {
-            uint8_t t = (uint8_t)p.n_tiles;  // shadow
-            if ((visr >> va) & 1u) {
-              t = 0;
-              if ((cwr >> va) & 1u) t = wall_tile;
-              else if ((ner >> va) & 1u) {
-                const int kind = p.kind_of_type[rowp[va * pv.vstep]];
-                if (kind == 0xFF) bad = 1; else t = (uint8_t)(kind * per_kind);
-              }
-            }
-            tl[b * V + va] = t;
+      for (int va = 0; va < V; ++va) {
+        uint8_t t = (uint8_t)p.n_tiles;  // shadow
+        if ((visr >> va) & 1u) {
+          t = 0;
+          if ((cwr >> va) & 1u) t = wall_tile;
+          else if ((ner >> va) & 1u) {
+            const int kind = p.kind_of_type[rowp[va * pv.vstep]];
+            if (kind == 0xFF) bad = 1; else t = (uint8_t)(kind * per_kind);
           }
         }
-        for (int q = 0; q < A; ++q) {
-          const uint32_t v0 = rec[q * 4];
-          if (!((v0 >> 24) & AF_HEAD)) continue;
-          int va, vb;
-          if (!world_to_view<V>(g, (int)(v0 & 0xFFu), (int)((v0 >> 8) & 0xFFu), va, vb)) continue;
-          if (!pv.visible(va, vb)) continue;
-          // top_agent if it stands on this cell, else the queue head (base.py:282-293)
-          const bool mine = ((v0 ^ w0) & 0xFFFFu) == 0u;
-          const int qq = mine ? a : q;
-          const int qd = (int)(((mine ? w0 : v0) >> 16) & 3u);
-          const int slot_dir = (p.orient_slots == 4) ? qd : ((qd + orient) & 3);
-          tl[vb * V + va] = (uint8_t)(tl[vb * V + va] + 1 + 4 * qq + slot_dir);
-        }
-        if (bad) atomicOr(reinterpret_cast<unsigned int*>(p.envrec) + (env0 + le) * 4 + 3, (unsigned int)MG_ERR_RENDER << 16);
+        tl[b * V + va] = t;
       }
     }
+    for (int q = 0; q < A; ++q) {
+      const uint32_t v0 = rec[q * 4];
+      if (!((v0 >> 24) & AF_HEAD)) continue;
+      int va, vb;
+      if (!world_to_view<V>(g, (int)(v0 & 0xFFu), (int)((v0 >> 8) & 0xFFu), va, vb)) continue;
+      if (!pv.visible(va, vb)) continue;
+      // top_agent if it stands on this cell, else the queue head (base.py:282-293)
+      const bool mine = ((v0 ^ w0) & 0xFFFFu) == 0u;
+      const int qq = mine ? a : q;
+      const int qd = (int)(((mine ? w0 : v0) >> 16) & 3u);
+      const int slot_dir = (p.orient_slots == 4) ? qd : ((qd + orient) & 3);
+      tl[vb * V + va] = (uint8_t)(tl[vb * V + va] + 1 + 4 * qq + slot_dir);
+    }
+    if (bad) atomicOr(reinterpret_cast<unsigned int*>(p.envrec) + env * 4 + 3, (unsigned int)MG_ERR_RENDER << 16);
   }
-  __syncthreads();
+}
 
-  // ---- stream the observation out ----
+// stream the CTA's observations to HBM.  Must be called by all threads after a __syncthreads().
+template <int OBS, int V, bool TS4>
+__device__ __forceinline__ void obs_emit(const KP& p, const ObsSmem<V>& o, long long env0, int n_valid, int tid, int nthreads) {
+  constexpr int VV = V * V;
+  const int A = p.A;
   if (OBS == 1) {
     const long long total = (long long)n_valid * A * VV * 3;
     uint8_t* dst = p.obs + env0 * A * VV * 3;
@@ -892,15 +885,14 @@ __global__ void __launch_bounds__(32 * MG_MAX_AGENTS) obs_kernel(const KP p) {
       // shared->global bulk copy (TMA) moves it; nobody spends an instruction on the 14 KB
       if (tid == 0) {
         fence_proxy_async_smem();
-        bulk_s2g(dst, s_out, (uint32_t)total);
+        bulk_s2g(dst, o.out, (uint32_t)total);
         bulk_commit();
-        bulk_wait_read0();  // the CTA (and its shared memory) must outlive the read
       }
     } else {  // ragged last CTA
       const int n16 = (int)(total / 16);
-      const int4* src = reinterpret_cast<const int4*>(s_out);
+      const int4* src = reinterpret_cast<const int4*>(o.out);
       for (int i = tid; i < n16; i += nthreads) st_stream_v4(reinterpret_cast<int4*>(dst) + i, src[i]);
-      for (int i = n16 * 16 + tid; i < total; i += nthreads) dst[i] = s_out[i];
+      for (int i = n16 * 16 + tid; i < total; i += nthreads) dst[i] = o.out[i];
     }
   } else {
     const int ts = p.ts, n_views = n_valid * A;
@@ -911,12 +903,12 @@ __global__ void __launch_bounds__(32 * MG_MAX_AGENTS) obs_kernel(const KP p) {
       const int wpt = ts * 3 / 4;         // words per tile row
       const int wpr = V * wpt;            // words per image row
       const int v16 = (int)(view_bytes / 16);
-      const uint32_t* atlas_w = reinterpret_cast<const uint32_t*>(s_atlas);
+      const uint32_t* atlas_w = reinterpret_cast<const uint32_t*>(o.atlas);
       const int total16 = n_views * v16;
       for (int i = tid; i < total16; i += nthreads) {
         const int view = i / v16, k = i - view * v16;
-        const int os = s_orient[view];
-        const uint8_t* tl = s_tile + view * VV;
+        const int os = o.orient[view];
+        const uint8_t* tl = o.tile + view * VV;
         uint32_t wv[4];
 #pragma unroll
         for (int w = 0; w < 4; ++w) {
@@ -938,12 +930,271 @@ __global__ void __launch_bounds__(32 * MG_MAX_AGENTS) obs_kernel(const KP p) {
         const int y = k / row_bytes, xb = k - y * row_bytes;
         const int va = xb / (ts * 3), r = xb - va * ts * 3;
         const int vb = y / ts, pyy = y - vb * ts;
-        const int t = s_tile[view * VV + vb * V + va];
-        const int slot = (t >= p.n_tiles) ? p.n_tiles * p.orient_slots : t * p.orient_slots + s_orient[view];
-        dst[i] = s_atlas[(slot * ts + pyy) * ts * 3 + r];
+        const int t = o.tile[view * VV + vb * V + va];
+        const int slot = (t >= p.n_tiles) ? p.n_tiles * p.orient_slots : t * p.orient_slots + o.orient[view];
+        dst[i] = o.atlas[(slot * ts + pyy) * ts * 3 + r];
       }
     }
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// observe kernel
+// ---------------------------------------------------------------------------------------------
+template <int OBS, int V, bool TS4, bool BITS>
+__global__ void __launch_bounds__(32 * MG_MAX_AGENTS) obs_kernel(const __grid_constant__ KP p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x, nthreads = blockDim.x;
+  const long long env0 = (long long)blockIdx.x * ENVS_PER_CTA;
+  const int n_valid = (int)min((long long)ENVS_PER_CTA, p.B - env0);
+  const int A = p.A, S = p.S;
+
+  uint8_t* s_grid = smem;                                                                    // byte path only
+  uint32_t* s_bits = reinterpret_cast<uint32_t*>(s_grid + (BITS ? 0 : ENVS_PER_CTA * 3 * S));  // bit-plane path only
+  uint32_t* s_rec = s_bits + (BITS ? ENVS_PER_CTA * BITS_WORDS : 0);                         // agent records as stored: [env][a][4 words]
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_rec + ENVS_PER_CTA * A * 4);
+  const ObsSmem<V> o = obs_smem<V>(reinterpret_cast<uint8_t*>(s_bar + 2), A);  // 16-byte aligned: every block above is a multiple of 16 bytes
+
+  if (tid == 0) mbar_init(s_bar, 1);
+  __syncthreads();
+  if (tid == 0) {
+    const uint32_t wbytes = BITS ? (uint32_t)n_valid * (BITS_WORDS * 4u) : (uint32_t)n_valid * 3u * (uint32_t)S;
+    const uint32_t rbytes = (uint32_t)n_valid * (uint32_t)A * 16u;
+    mbar_expect_tx(s_bar, wbytes + rbytes);
+    if (BITS) bulk_g2s(s_bits, p.cellbits + env0 * BITS_WORDS, wbytes, s_bar);
+    else bulk_g2s(s_grid, p.grid + env0 * 3 * S, wbytes, s_bar);
+    bulk_g2s(s_rec, p.agents + env0 * A * 16, rbytes, s_bar);
+  }
+  obs_prepare<OBS, V>(p, o, tid, nthreads);  // while the copies are in flight
+  mbar_wait(s_bar, 0);
+  __syncthreads();
+  if (tid < n_valid * A) {
+    const int le = tid / A, a = tid - le * A;
+    obs_view<OBS, V, BITS>(p, o, tid, a, env0 + le, s_rec + le * A * 4, BITS ? p.grid + (env0 + le) * 3 * S : s_grid + le * 3 * S,
+                           BITS ? s_bits + le * BITS_WORDS : nullptr);
+  }
+  __syncthreads();
+  obs_emit<OBS, V, TS4>(p, o, env0, n_valid, tid, nthreads);
+  if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the CTA (and its shared memory) must outlive the read
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused env.step + observe kernel (bit-plane worlds, ghost mode, no respawn, no spawn delay): ONE launch per step.
+//
+// Thread (env, agent) first plays its own agent's action (MultiGridEnv.step, base.py:517-622): in ghost mode an
+// action that does not edit the planes depends on nothing another agent does in the same step, so the A agents
+// of an env act in parallel and the reference's random processing order (base.py:514-516) only decides the
+// arrival stamps of the agents that moved.  Envs where some action WOULD edit the planes (a pickup / drop /
+// toggle that takes effect) and envs whose episode just ended are handed to one lane that runs the general
+// sequential code (env_step / env_reset above) -- rare, and exact.  Then the same threads observe.
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t FL_SLOW = 1u, FL_RESET = 2u, FL_BITS_DIRTY = 4u;  // s_flag bits; bits 8..15 movers, 16..31 error bits
+
+// the general sequential code, kept out of line so the common path keeps its registers
+__device__ __noinline__ void seq_step(EnvCtx<32>& c, unsigned long long g, const int32_t* act, double* rew) {
+  env_step<32, true, MG_MAX_AGENTS>(c, g, act, rew);
+}
+__device__ __noinline__ void seq_reset(EnvCtx<32>& c, unsigned long long g) { env_reset<32, true>(c, g); }
+
+template <int OBS, int V, bool TS4>
+__global__ void __launch_bounds__(32 * MG_MAX_AGENTS, 4) fused_kernel(const __grid_constant__ KP p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x, nthreads = blockDim.x;
+  const long long env0 = (long long)blockIdx.x * ENVS_PER_CTA;
+  const int n_valid = (int)min((long long)ENVS_PER_CTA, p.B - env0);
+  const int A = p.A, S = p.S, W = p.W, H = p.H;
+
+  uint32_t* s_bits = reinterpret_cast<uint32_t*>(smem);
+  uint32_t* s_rec = s_bits + ENVS_PER_CTA * BITS_WORDS;       // [env][a][4]
+  int32_t* s_env = reinterpret_cast<int32_t*>(s_rec + ENVS_PER_CTA * A * 4);  // [env][4]
+  uint32_t* s_flag = reinterpret_cast<uint32_t*>(s_env + ENVS_PER_CTA * 4);   // [env]
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_flag + ENVS_PER_CTA);
+  uint8_t* s_out = reinterpret_cast<uint8_t*>(s_bar + 2);
+  const ObsSmem<V> o = obs_smem<V>(s_out, A);
+  // scratch of the sequential path, aliased with the (not yet used) output area
+  uint32_t* s_trec = reinterpret_cast<uint32_t*>(s_out);  // [A*4][32] transposed records
+  uint32_t* s_scr = s_trec + A * 4 * 32;                  // [32][32] reset row masks
+
+  if (tid == 0) mbar_init(s_bar, 1);
+  if (tid < ENVS_PER_CTA) s_flag[tid] = 0u;
+  __syncthreads();
+  if (tid == 0) {
+    const uint32_t wbytes = (uint32_t)n_valid * (BITS_WORDS * 4u), rbytes = (uint32_t)n_valid * (uint32_t)A * 16u, ebytes = (uint32_t)n_valid * 16u;
+    mbar_expect_tx(s_bar, wbytes + rbytes + ebytes);
+    bulk_g2s(s_bits, p.cellbits + env0 * BITS_WORDS, wbytes, s_bar);
+    bulk_g2s(s_rec, p.agents + env0 * A * 16, rbytes, s_bar);
+    bulk_g2s(s_env, p.envrec + env0 * 4, ebytes, s_bar);
+  }
+  const bool mine = tid < n_valid * A;
+  const int le = mine ? tid / A : 0, a = mine ? tid - le * A : 0;
+  const long long env = env0 + le;
+  const int action = mine ? p.actions[env * A + a] : (int)MG_A_DONE;
+  mbar_wait(s_bar, 0);
+
+  // ---- phase 1: every agent plays its action on a private copy of its record ----
+  uint32_t* rec = s_rec + le * A * 4;
+  const uint32_t* bits = s_bits + le * BITS_WORDS;
+  uint8_t* tp = p.grid + env * 3 * S;
+  uint32_t w0 = 0, w1 = 0, errb = 0, order = 0;
+  bool moved = false;
+  double reward = 0.0;
+  int sc = 0;
+  if (mine) {
+    w0 = rec[a * 4]; w1 = rec[a * 4 + 1];
+    sc = s_env[le * 4] + 1;  // base.py:512
+    const uint32_t t_life = (uint32_t)s_env[le * 4 + 2];
+    const unsigned long long g = (unsigned long long)(p.env_offset + env);
+    uint32_t fact = 1;
+    for (int i = 2; i <= A; ++i) fact *= (uint32_t)i;
+    const U4 r = philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), t_life, 0u, (uint32_t)p.seed, (uint32_t)(p.seed >> 32));
+    order = decode_order(__umulhi(r.x, fact), A);  // base.py:514-516
+    bool slow = false;
+    if ((w0 >> 24) & MG_AF_ACTIVE) {  // base.py:521
+      const int cx = (int)(w0 & 0xFFu), cy = (int)((w0 >> 8) & 0xFFu), dir = (int)((w0 >> 16) & 3u);
+      if (action == MG_A_LEFT) w0 = (w0 & 0xFF00FFFFu) | ((uint32_t)((dir + 3) & 3) << 16);        // base.py:530-531
+      else if (action == MG_A_RIGHT) w0 = (w0 & 0xFF00FFFFu) | ((uint32_t)((dir + 1) & 3) << 16);  // base.py:534-535
+      else if (action >= MG_A_FORWARD && action <= MG_A_TOGGLE) {
+        const int fx = cx + ((dir == 0) ? 1 : (dir == 2) ? -1 : 0), fy = cy + ((dir == 1) ? 1 : (dir == 3) ? -1 : 0);  // agents.py:183
+        const bool inb = (unsigned)fx < (unsigned)W && (unsigned)fy < (unsigned)H;
+        const int fidx = inb ? fx * H + fy : 0;
+        const int ftype = inb ? type_from_words(bits[fx & 15], bits[32 + (fx & 15)], fy, tp, fidx) : (int)MG_T_WALL;
+        if (!inb) errb |= MG_ERR_STACK;
+        if (action == MG_A_FORWARD) {  // base.py:538-585 (ghost mode: other agents never block)
+          const int fstate = (ftype == MG_T_DOOR || ftype == MG_T_BONUS) ? (int)tp[2 * S + fidx] : 0;
+          if (ftype == MG_T_EMPTY || can_overlap_static(ftype, fstate)) {
+            const int ctype = type_from_words(bits[cx & 15], bits[32 + (cx & 15)], cy, tp, cx * H + cy);
+            if (ctype != MG_T_EMPTY && !can_overlap_static(ctype, tp[2 * S + cx * H + cy])) errb |= MG_ERR_STACK;  // base.py:558
+            w0 = (w0 & 0xFFFF0000u) | (uint32_t)fx | ((uint32_t)fy << 8);
+            moved = true;
+            if (ftype == MG_T_GOAL || ftype == MG_T_BONUS) {  // base.py:576-581
+              double rwd;
+              if (ftype == MG_T_GOAL) rwd = p.goal_reward;
+              else {  // BonusTile.get_reward objects.py:180-206 on the private copy of w1
+                const int n = p.n_bonus, bonus_id = fstate;
+                int bs = (int)(w1 >> 24);
+                bool first = false;
+                const double pen = p.bonus_penalty < 0 ? p.bonus_penalty : -p.bonus_penalty;
+                if (bs == 0xFF) { bs = ((bonus_id - 1) % n + n) % n; first = true; }
+                if (bs == bonus_id) rwd = pen;
+                else if ((bs + 1) % n == bonus_id) { bs = bonus_id; rwd = p.bonus_reward; }
+                else rwd = pen;
+                if (p.flags & MG_F_BONUS_RESET) bs = bonus_id;
+                w1 = (w1 & 0x00FFFFFFu) | ((uint32_t)bs << 24);
+                if (first && !(p.flags & MG_F_BONUS_INITIAL)) rwd = 0.0;
+              }
+              if (p.flags & MG_F_REWARD_DECAY) {  // base.py:579, every operation rounded on its own
+                const double qd = __ddiv_rn((double)sc, (double)p.max_steps);
+                const double u = __dmul_rn(0.9, qd);
+                const double f = __dsub_rn(1.0, u);
+                rwd = __dmul_rn(rwd, f);
+              }
+              reward = __dadd_rn(0.0, rwd);
+            }
+            if (ftype == MG_T_LAVA || ftype == MG_T_GOAL) w0 = (w0 | ((uint32_t)MG_AF_DONE << 24)) & ~((uint32_t)MG_AF_ACTIVE << 24);  // base.py:584-585,646
+          }
+        } else if (action == MG_A_PICKUP) {  // takes effect only on a pickable object with empty hands (base.py:590-597)
+          slow = ftype != MG_T_EMPTY && ((PICKUP_MASK >> ftype) & 1u) && (w1 & 0xFFu) == 0u;
+        } else if (action == MG_A_DROP) {    // takes effect only when carrying and facing an empty cell (base.py:600-606)
+          slow = inb && ftype == MG_T_EMPTY && (w1 & 0xFFu) != 0u;
+        } else {                             // toggle: only Door / Box react (base.py:609-613)
+          slow = ftype == MG_T_DOOR || ftype == MG_T_BOX;
+        }
+      } else if (action != MG_A_DONE) errb |= MG_ERR_BAD_ACTION;  // base.py:619-620
+    }
+    if (slow) atomicOr(&s_flag[le], FL_SLOW);
+  }
+  __syncthreads();
+
+  // ---- phase 2: commit (parallel envs) or replay sequentially (envs whose planes change) ----
+  const bool slow_env = mine && (s_flag[le] & FL_SLOW);
+  if (mine && !slow_env) {
+    rec[a * 4] = w0; rec[a * 4 + 1] = w1;
+    p.rewards[env * A + a] = reward;
+    const uint32_t add = (moved ? (0x100u << a) : 0u) | (errb << 16);
+    if (add) atomicOr(&s_flag[le], add);
+  } else if (slow_env && a == 0) {
+    EnvCtx<32> c{p, s_trec + le, tp, s_bits + le * BITS_WORDS, s_scr + le, 0, 0, 0, 0u, false};
+    for (int q = 0; q < A; ++q) { c.R(q, 0) = rec[q * 4]; c.R(q, 1) = rec[q * 4 + 1]; c.R(q, 2) = rec[q * 4 + 2]; }
+    c.sc = s_env[le * 4]; c.ep = s_env[le * 4 + 1]; c.tl = s_env[le * 4 + 2]; c.w3 = (uint32_t)s_env[le * 4 + 3];
+    seq_step(c, (unsigned long long)(p.env_offset + env), p.actions + env * A, p.rewards + env * A);
+    for (int q = 0; q < A; ++q) { rec[q * 4] = c.R(q, 0); rec[q * 4 + 1] = c.R(q, 1); rec[q * 4 + 2] = c.R(q, 2); rec[q * 4 + 3] = 0u; }
+    s_env[le * 4] = c.sc; s_env[le * 4 + 2] = c.tl; s_env[le * 4 + 3] = (int)c.w3;
+    if (c.dirty) atomicOr(&s_flag[le], FL_BITS_DIRTY);
+  }
+  __syncthreads();
+
+  // ---- phase 3: arrival stamps of the movers, in the reference's processing order (base.py:547-552) ----
+  if (mine && !slow_env && moved) {
+    const uint32_t movers = (s_flag[le] >> 8) & 0xFFu;
+    int rank = 0;
+    for (int q = 0; q < A; ++q) {
+      const int b = (int)((order >> (4 * q)) & 0xFu);
+      if (b == a) break;
+      rank += (int)((movers >> b) & 1u);
+    }
+    rec[a * 4 + 2] = (((uint32_t)s_env[le * 4 + 3] & 0xFFFFu) + (uint32_t)rank) & 0xFFFFu;
+  }
+  __syncthreads();
+
+  // ---- phase 4: env bookkeeping, done (base.py:649), reset of finished envs (base.py:402-416) ----
+  if (mine && a == 0) {
+    const uint32_t fl = s_flag[le];
+    if (!(fl & FL_SLOW)) {
+      const uint32_t w3 = (uint32_t)s_env[le * 4 + 3];
+      s_env[le * 4] = sc;
+      s_env[le * 4 + 2] += 1;
+      s_env[le * 4 + 3] = (int)((w3 & 0xFFFF0000u) | (((w3 & 0xFFFFu) + (uint32_t)__popc((fl >> 8) & 0xFFu)) & 0xFFFFu) | (fl & 0xFFFF0000u));
+    }
+    bool all_done = true;
+    for (int q = 0; q < A; ++q) all_done = all_done && ((rec[q * 4] >> 24) & MG_AF_DONE);
+    const bool dn = (s_env[le * 4] >= p.max_steps) || all_done;
+    p.done[env] = dn ? 1 : 0;
+    if (dn && p.autoreset) {
+      EnvCtx<32> c{p, s_trec + le, tp, s_bits + le * BITS_WORDS, s_scr + le, 0, 0, 0, 0u, false};
+      for (int q = 0; q < A; ++q) { c.R(q, 0) = rec[q * 4]; c.R(q, 1) = rec[q * 4 + 1]; c.R(q, 2) = rec[q * 4 + 2]; }
+      c.sc = s_env[le * 4]; c.ep = s_env[le * 4 + 1]; c.tl = s_env[le * 4 + 2]; c.w3 = (uint32_t)s_env[le * 4 + 3];
+      seq_reset(c, (unsigned long long)(p.env_offset + env));
+      for (int q = 0; q < A; ++q) { rec[q * 4] = c.R(q, 0); rec[q * 4 + 1] = c.R(q, 1); rec[q * 4 + 2] = c.R(q, 2); rec[q * 4 + 3] = 0u; }
+      s_env[le * 4] = c.sc; s_env[le * 4 + 1] = c.ep; s_env[le * 4 + 3] = (int)c.w3;
+      atomicOr(&s_flag[le], FL_BITS_DIRTY | FL_RESET);
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 5: queue heads (derived flag) from the final positions and stamps ----
+  bool head = false;
+  if (mine) {
+    const uint32_t v0 = rec[a * 4];
+    head = ((v0 >> 24) & MG_AF_PLACED) != 0;
+    if (head) {
+      const uint32_t st = rec[a * 4 + 2];
+      for (int q = 0; q < A; ++q) {
+        const uint32_t u0 = rec[q * 4];
+        if (q != a && ((u0 >> 24) & MG_AF_PLACED) && ((u0 ^ v0) & 0xFFFFu) == 0u && rec[q * 4 + 2] < st) head = false;
+      }
+    }
+  }
+  obs_prepare<OBS, V>(p, o, tid, nthreads);  // the scratch area is free again: it becomes the output area
+  __syncthreads();
+  if (mine) rec[a * 4] = head ? (rec[a * 4] | (AF_HEAD << 24)) : (rec[a * 4] & ~(AF_HEAD << 24));
+  __syncthreads();
+
+  // ---- phase 6: observe the post-step world ----
+  if (mine) obs_view<OBS, V, true>(p, o, tid, a, env, rec, tp, bits);
+  __syncthreads();
+  obs_emit<OBS, V, TS4>(p, o, env0, n_valid, tid, nthreads);
+  if (tid == 0) {  // state goes back as it came: contiguous chunks, bulk copies
+    fence_proxy_async_smem();
+    bulk_s2g(p.agents + env0 * A * 16, s_rec, (uint32_t)n_valid * (uint32_t)A * 16u);
+    bulk_s2g(p.envrec + env0 * 4, s_env, (uint32_t)n_valid * 16u);
+    bulk_commit();
+  }
+  if (mine && a == 0 && (s_flag[le] & FL_BITS_DIRTY)) {
+    fence_proxy_async_smem();
+    bulk_s2g(p.cellbits + env * BITS_WORDS, s_bits + le * BITS_WORDS, BITS_WORDS * 4u);
+    bulk_commit();
+  }
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 // zero-initialised family of freshly constructed envs (bonus_state = None)
@@ -1078,6 +1329,58 @@ static int launch_obs(const KP& p, int obs, cudaStream_t s) {
   return bits ? launch_obs_v<2, false, true>(p, s) : launch_obs_v<2, false, false>(p, s);
 }
 
+static size_t fused_smem_bytes(const KP& p, int obs) {
+  size_t out = 0;
+  if (obs == 1) out = (size_t)ENVS_PER_CTA * p.A * p.V * p.V * 3;
+  else out = (size_t)ENVS_PER_CTA * p.A * p.V * p.V + (size_t)((ENVS_PER_CTA * p.A + 15) / 16) * 16 + (size_t)(p.n_tiles * p.orient_slots + 1) * p.ts * p.ts * 3;
+  const size_t scratch = (size_t)(p.A * 4 * 32 + 32 * 32) * 4;
+  const size_t b = (size_t)ENVS_PER_CTA * BITS_WORDS * 4 + (size_t)ENVS_PER_CTA * p.A * 16 + (size_t)ENVS_PER_CTA * 16 + (size_t)ENVS_PER_CTA * 4 + 16 +
+                   std::max(out, scratch);
+  return (b + 15) / 16 * 16;
+}
+
+template <int OBS, int V, bool TS4>
+static int launch_fused_one(const KP& p, cudaStream_t s) {
+  const size_t sm = fused_smem_bytes(p, OBS);
+  auto k = fused_kernel<OBS, V, TS4>;
+  static size_t configured[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (sm > 48 * 1024 && sm > configured[dev & 63]) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    if (e != cudaSuccess) return (int)e;
+    configured[dev & 63] = sm;
+  }
+  const long long blocks = (p.B + ENVS_PER_CTA - 1) / ENVS_PER_CTA;
+  if (blocks <= 0) return 0;
+  k<<<(unsigned)blocks, 32 * p.A, sm, s>>>(p);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return (int)cudaGetLastError();
+}
+
+template <int OBS, bool TS4>
+static int launch_fused_v(const KP& p, cudaStream_t s) {
+  switch (p.V) {
+    case 3: return launch_fused_one<OBS, 3, TS4>(p, s);
+    case 4: return launch_fused_one<OBS, 4, TS4>(p, s);
+    case 5: return launch_fused_one<OBS, 5, TS4>(p, s);
+    case 6: return launch_fused_one<OBS, 6, TS4>(p, s);
+    case 7: return launch_fused_one<OBS, 7, TS4>(p, s);
+    case 8: return launch_fused_one<OBS, 8, TS4>(p, s);
+  }
+  return MG_E_CONFIG;
+}
+
+// the one-launch path exists for bit-plane worlds in ghost mode without respawn / spawn delay (every registered env)
+static bool fused_eligible(const KP& p) {
+  if (p.cellbits == nullptr || !(p.flags & MG_F_GHOST) || (p.flags & MG_F_RESPAWN)) return false;
+  for (int a = 0; a < p.A; ++a)
+    if (p.spawn_delay[a] != 0) return false;
+  return true;
+}
+
+static int g_force_two_kernels = 0;  // test hook: exercise the per-env step kernel + observe kernel pair
+
 // per-env kernels: MODE 0 step (+auto-reset), 1 reset, 2 sync derived state
 template <int MODE>
 static int launch_env(const KP& p, cudaStream_t s) {
@@ -1097,8 +1400,12 @@ static int launch_env(const KP& p, cudaStream_t s) {
 
 static cudaEvent_t g_mid_event = nullptr;  // profiling hook: recorded between the two launches of a step
 
-// env.step: the step kernel (incl. auto-reset), then the observation in one more launch
+// env.step: one fused launch when eligible; else the step kernel (incl. auto-reset), then the observation
 static int launch_step_obs(const KP& p, int obs, cudaStream_t s) {
+  if (obs != 0 && !g_force_two_kernels && fused_eligible(p)) {
+    if (obs == 1) return launch_fused_v<1, false>(p, s);
+    return (p.ts % 4 == 0) ? launch_fused_v<2, true>(p, s) : launch_fused_v<2, false>(p, s);
+  }
   int e = launch_env<0>(p, s);
   if (e) return e;
   if (g_mid_event) cudaEventRecord(g_mid_event, s);
@@ -1129,6 +1436,7 @@ int64_t mg_obs_bytes_per_env(const MgConfig* c, int rgb) {
 }
 int64_t mg_launch_count(void) { return g_launches.load(); }
 void mg_debug_set_mid_event(void* cuda_event) { g_mid_event = (cudaEvent_t)cuda_event; }
+void mg_debug_force_two_kernels(int on) { g_force_two_kernels = on; }
 
 int mg_init(const MgConfig* cfg, const MgState* st, mg_stream_t stream) {
   int e = check_state(cfg, st);

@@ -52,8 +52,16 @@ def test_los_kernel_matches_golden_and_oracle(cuda_lib, oracle):
         assert np.array_equal(dm.cpu().numpy(), want), f"V={V} pos=({ax},{ay})"
 
 
+@pytest.fixture(params=["fused", "two_kernels"])
+def step_impl(request, cuda_lib):
+    """env.step has two implementations (one fused launch / per-env step kernel + observe kernel): test both."""
+    cuda_lib.mg_debug_force_two_kernels(1 if request.param == "two_kernels" else 0)
+    yield request.param
+    cuda_lib.mg_debug_force_two_kernels(0)
+
+
 @pytest.mark.parametrize("path", trajectory_files(), ids=lambda p: os.path.basename(p)[5:-4])
-def test_cuda_replays_reference_trajectory(path):
+def test_cuda_replays_reference_trajectory(path, step_impl):
     """The event streams recorded from the unmodified reference, replayed through the kernels."""
     cfg, meta, z = load_traj(path)
     has_rgb = "rgb" in z.files
@@ -112,7 +120,7 @@ CONFIGS = {
 
 
 @pytest.mark.parametrize("name", list(CONFIGS))
-def test_batched_lockstep_vs_oracle(oracle, name):
+def test_batched_lockstep_vs_oracle(oracle, name, step_impl):
     """Seeded random rollouts with auto-reset: every output and the whole state, every step."""
     from marlgrid_b200 import envs
 
@@ -138,7 +146,7 @@ def test_batched_lockstep_vs_oracle(oracle, name):
     assert int(env.err.max().item()) == 0
 
 
-def test_rgb_batched_vs_oracle(oracle):
+def test_rgb_batched_vs_oracle(oracle, step_impl):
     """RGB tile path (config 4 family) against the oracle fed the same atlas."""
     from marlgrid_b200 import envs
     from marlgrid_b200.atlas import build_atlas
