@@ -29,7 +29,8 @@
 namespace mg {
 
 constexpr int ENVS_PER_CTA = 32;
-constexpr int BITS_WORDS = 48;       // per env: 16 row words, 16 column words, 16 canonical-wall words
+constexpr int BITS_WORDS = 52;       // per env: 16 row words, 16 column words, 16 canonical-wall words, 4 object-list words
+constexpr int OBJ_SLOTS = 4;
 constexpr uint32_t AF_HEAD = 0x80u;  // derived flag bit: agent is the head of its cell's queue
 
 struct KP {
@@ -68,6 +69,33 @@ __device__ __forceinline__ bool cell_opaque(int type, int state) {  // objects.p
 __device__ __forceinline__ bool cell_canon(int type, int colour, int state) {
   return type == MG_T_WALL && colour == MG_C_WORST && state == 0;
 }
+//              word 48+k     : object list: up to 4 of the non-wall objects, x | y<<4 | type<<8 | colour<<12 | state<<16 | 1<<31.
+//                              A non-empty, non-canonical cell that is NOT listed is looked up in the byte planes, so the
+//                              list may be incomplete (more than 4 objects) but never wrong.
+__device__ __forceinline__ uint32_t obj_entry(int x, int y, int type, int colour, int state) {
+  return (uint32_t)x | ((uint32_t)y << 4) | ((uint32_t)type << 8) | ((uint32_t)(colour & 15) << 12) | ((uint32_t)(state & 255) << 16) | 0x80000000u;
+}
+__device__ __forceinline__ uint32_t obj_lookup(const uint32_t* bits, int x, int y) {
+  const uint32_t key = 0x80000000u | (uint32_t)x | ((uint32_t)y << 4);
+  uint32_t e = 0;
+#pragma unroll
+  for (int k = 0; k < OBJ_SLOTS; ++k) {
+    const uint32_t w = bits[48 + k];
+    if ((w & 0x800000FFu) == key) e = w;
+  }
+  return e;
+}
+__device__ __forceinline__ void obj_update(uint32_t* bits, int x, int y, int type, int colour, int state) {
+  const uint32_t key = 0x80000000u | (uint32_t)x | ((uint32_t)y << 4);
+  const bool listable = type != MG_T_EMPTY && !(type == MG_T_WALL && colour == MG_C_WORST && state == 0) && colour < 16;
+  int slot = -1;
+  for (int k = 0; k < OBJ_SLOTS; ++k) {
+    const uint32_t w = bits[48 + k];
+    if ((w & 0x800000FFu) == key) { bits[48 + k] = 0u; if (slot < 0) slot = k; }
+    else if (!(w >> 31) && slot < 0) slot = k;
+  }
+  if (listable && slot >= 0) bits[48 + slot] = obj_entry(x, y, type, colour, state);
+}
 __device__ __forceinline__ void bits_update_cell(uint32_t* bits, int x, int y, int type, int colour, int state) {
   if (bits == nullptr) return;
   const uint32_t op = cell_opaque(type, state) ? 1u : 0u, ne = type != MG_T_EMPTY ? 1u : 0u, cn = cell_canon(type, colour, state) ? 1u : 0u;
@@ -75,8 +103,9 @@ __device__ __forceinline__ void bits_update_cell(uint32_t* bits, int x, int y, i
   bits[16 + y] = (bits[16 + y] & ~((1u << x) | (1u << (16 + x)))) | (op << x) | (ne << (16 + x));
   bits[32 + x] = (bits[32 + x] & ~(1u << y)) | (cn << y);
   bits[32 + y] = (bits[32 + y] & ~(1u << (16 + x))) | (cn << (16 + x));
+  obj_update(bits, x, y, type, colour, state);
 }
-// rebuild all 48 words from the byte planes
+// rebuild all words from the byte planes
 __device__ void bits_rebuild(const uint8_t* tp, uint32_t* bits, int W, int H, int S) {
   if (bits == nullptr) return;
   for (int i = 0; i < BITS_WORDS; ++i) bits[i] = 0u;
@@ -86,6 +115,17 @@ __device__ void bits_rebuild(const uint8_t* tp, uint32_t* bits, int W, int H, in
       const int t = tp[idx];
       if (t != MG_T_EMPTY) bits_update_cell(bits, x, y, t, tp[S + idx], tp[2 * S + idx]);
     }
+}
+
+// (type | colour<<8 | state<<16) of the static object at (x, y): bit-planes, then the object list, then -- for
+// objects that did not fit the list -- the byte planes
+__device__ __forceinline__ uint32_t cell_triple(const uint32_t* bits, int x, int y, const uint8_t* tp, int H, int S) {
+  if (!((bits[x] >> (16 + y)) & 1u)) return 0u;
+  if ((bits[32 + x] >> y) & 1u) return (uint32_t)MG_T_WALL | ((uint32_t)MG_C_WORST << 8);
+  const uint32_t e = obj_lookup(bits, x, y);
+  if (e) return ((e >> 8) & 0xFu) | (((e >> 12) & 0xFu) << 8) | (((e >> 16) & 0xFFu) << 16);
+  const int idx = x * H + y;
+  return (uint32_t)tp[idx] | ((uint32_t)tp[S + idx] << 8) | ((uint32_t)tp[2 * S + idx] << 16);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -112,14 +152,14 @@ struct EnvCtx {
     w3 = (w3 & 0xFFFF0000u) | ((s + 1u) & 0xFFFFu);
     return s;
   }
-  // static object type at (x, y): bit-planes first, byte plane only for the few "other" objects
-  __device__ __forceinline__ int static_type(int x, int y) {
-    if (bits != nullptr) {
-      if (!((bits[x] >> (16 + y)) & 1u)) return MG_T_EMPTY;
-      if ((bits[32 + x] >> y) & 1u) return MG_T_WALL;
-    }
-    return tp[x * p.H + y];
+  // static object at (x, y) as type | colour<<8 | state<<16
+  __device__ __forceinline__ uint32_t static_cell(int x, int y) {
+    if (bits != nullptr) return cell_triple(bits, x, y, tp, p.H, p.S);
+    const int idx = x * p.H + y;
+    const uint32_t t = tp[idx];
+    return t == 0u ? 0u : (t | ((uint32_t)tp[p.S + idx] << 8) | ((uint32_t)tp[2 * p.S + idx] << 16));
   }
+  __device__ __forceinline__ int static_type(int x, int y) { return (int)(static_cell(x, y) & 0xFFu); }
   __device__ __forceinline__ void set_cell(int x, int y, int type, int colour, int state) {
     const int idx = x * p.H + y;
     tp[idx] = (uint8_t)type; tp[p.S + idx] = (uint8_t)colour; tp[2 * p.S + idx] = (uint8_t)state;
@@ -155,8 +195,9 @@ __device__ __forceinline__ void put_agent(EnvCtx<RS>& c, int agent, int x, int y
 // base.py:664-688 try_place_obj for an AGENT in the live world (spawn delay / respawn inside step)
 template <int RS>
 __device__ __forceinline__ bool try_place_agent(EnvCtx<RS>& c, int x, int y, int agent) {
-  const int st = c.static_type(x, y);
-  if (st != MG_T_EMPTY && !can_overlap_static(st, c.tp[2 * c.p.S + x * c.p.H + y])) return false;  // base.py:678-679
+  const uint32_t cell = c.static_cell(x, y);
+  const int st = (int)(cell & 0xFFu);
+  if (st != MG_T_EMPTY && !can_overlap_static(st, (int)(cell >> 16))) return false;  // base.py:678-679
   if (!(c.p.flags & MG_F_GHOST) && queue_head(c, x, y) >= 0) return false;                          // base.py:683-684
   put_agent(c, agent, x, y);
   return true;
@@ -211,12 +252,18 @@ __device__ void env_reset(EnvCtx<RS>& c, unsigned long long g) {
     c.tp[j] = MG_T_WALL; c.tp[S + j] = MG_C_WORST;
     c.tp[(W - 1) * H + j] = MG_T_WALL; c.tp[S + (W - 1) * H + j] = MG_C_WORST;
   }
+  int n_listed = 0;
+  if (BITS)
+    for (int k = 0; k < OBJ_SLOTS; ++k) c.bits[48 + k] = 0u;
   auto put_static = [&](int x, int y, int type, int colour, int state) {
     const int idx = x * H + y;
     c.tp[idx] = (uint8_t)type; c.tp[S + idx] = (uint8_t)colour; c.tp[2 * S + idx] = (uint8_t)state;
     if (BITS) {
       if (type == MG_T_WALL) { wall[x * RS] |= 1u << y; other[x * RS] &= ~(1u << y); }
-      else { other[x * RS] |= 1u << y; wall[x * RS] &= ~(1u << y); }
+      else {
+        other[x * RS] |= 1u << y; wall[x * RS] &= ~(1u << y);
+        if (n_listed < OBJ_SLOTS) c.bits[48 + n_listed++] = obj_entry(x, y, type, colour, state);  // Goal / BonusTiles
+      }
     }
   };
   auto cell_type = [&](int x, int y) -> int {  // 0 empty, WALL, or GOAL standing for "overlappable other"
@@ -309,23 +356,16 @@ __device__ __forceinline__ uint32_t decode_order(uint32_t pidx, int A) {
 }
 
 // front-cell word of an agent: type of the cell it faces | its state << 8 | type of the cell it stands on << 16
-// (slow path: used when the planes changed earlier in the same step)
+// | state of that cell << 24 (only the low 7 bits matter: Door states)
 template <int RS>
 __device__ __forceinline__ uint32_t front_cells(EnvCtx<RS>& c, int cx, int cy, int fx, int fy, bool inb) {
-  const int H = c.p.H, S = c.p.S;
   uint32_t pf = 0;
   if (inb) {
-    const int ft = c.static_type(fx, fy);
-    pf = (uint32_t)ft;
-    if (ft == MG_T_DOOR || ft == MG_T_BONUS) pf |= (uint32_t)c.tp[2 * S + fx * H + fy] << 8;
+    const uint32_t f = c.static_cell(fx, fy);
+    pf = (f & 0xFFu) | (((f >> 16) & 0xFFu) << 8);
   }
-  return pf | ((uint32_t)c.static_type(cx, cy) << 16);
-}
-// type of the static object at (x, y) given the row word and the canonical-wall word of row x
-__device__ __forceinline__ int type_from_words(uint32_t roww, uint32_t canw, int y, const uint8_t* tp, int idx) {
-  if (!((roww >> (16 + y)) & 1u)) return MG_T_EMPTY;
-  if ((canw >> y) & 1u) return MG_T_WALL;
-  return tp[idx];  // one of the few other objects: byte plane
+  const uint32_t u = c.static_cell(cx, cy);
+  return pf | ((u & 0xFFu) << 16);
 }
 
 // base.py:501-649 step without the obs; returns done
@@ -349,25 +389,9 @@ __device__ bool env_step(EnvCtx<RS>& c, unsigned long long g, const int32_t* __r
   // pos/dir only change when it is processed, so the addresses are final; the lookup is redone below if an
   // earlier agent of this step edited the planes (pickup / drop / toggle).  w3 = front word | action << 24.
   {
-    uint32_t wf[AMAX], cf[AMAX], wc[AMAX], cc[AMAX];
     int act_r[AMAX];
 #pragma unroll
-    for (int a = 0; a < AMAX; ++a) {
-      wf[a] = cf[a] = wc[a] = cc[a] = 0u; act_r[a] = 0;
-      if (a < A) {
-        act_r[a] = act[a];
-        const uint32_t w0 = c.R(a, 0);
-        const int cx = (int)(w0 & 0xFFu), dir = (int)((w0 >> 16) & 3u);
-        const int fx = cx + ((dir == 0) ? 1 : (dir == 2) ? -1 : 0);
-        const int rx = ((unsigned)fx < (unsigned)W) ? fx : cx;  // row of the front cell (clamped: the value is unused if out of range)
-        if (BITS) {
-          const bool on = ((w0 >> 24) & MG_AF_ACTIVE) != 0 && cx < 16;
-          const uint32_t* bp = c.bits;
-          wf[a] = on ? bp[rx & 15] : 0u; cf[a] = on ? bp[32 + (rx & 15)] : 0u;
-          wc[a] = on ? bp[cx & 15] : 0u; cc[a] = on ? bp[32 + (cx & 15)] : 0u;
-        }
-      }
-    }
+    for (int a = 0; a < AMAX; ++a) act_r[a] = (a < A) ? act[a] : 0;
 #pragma unroll
     for (int a = 0; a < AMAX; ++a) {
       if (a < A) {
@@ -377,17 +401,7 @@ __device__ bool env_step(EnvCtx<RS>& c, unsigned long long g, const int32_t* __r
         if ((w0 >> 24) & MG_AF_ACTIVE) {
           const int cx = (int)(w0 & 0xFFu), cy = (int)((w0 >> 8) & 0xFFu), dir = (int)((w0 >> 16) & 3u);
           const int fx = cx + ((dir == 0) ? 1 : (dir == 2) ? -1 : 0), fy = cy + ((dir == 1) ? 1 : (dir == 3) ? -1 : 0);
-          const bool inb = (unsigned)fx < (unsigned)W && (unsigned)fy < (unsigned)H;
-          if (BITS) {
-            if (inb) {
-              const int ft = type_from_words(wf[a], cf[a], fy, c.tp, fx * H + fy);
-              pf = (uint32_t)ft;
-              if (ft == MG_T_DOOR || ft == MG_T_BONUS) pf |= (uint32_t)c.tp[2 * S + fx * H + fy] << 8;
-            }
-            pf |= (uint32_t)type_from_words(wc[a], cc[a], cy, c.tp, cx * H + cy) << 16;
-          } else {
-            pf = front_cells(c, cx, cy, fx, fy, inb);
-          }
+          pf = front_cells(c, cx, cy, fx, fy, (unsigned)fx < (unsigned)W && (unsigned)fy < (unsigned)H);
         }
         c.R(a, 3) = (pf & 0x00FFFFFFu) | ((uint32_t)min(max(action, 0), 255) << 24) | ((action < 0) ? 0xFF000000u : 0u);
       }
@@ -415,7 +429,6 @@ __device__ bool env_step(EnvCtx<RS>& c, unsigned long long g, const int32_t* __r
         const int fx = cx + ((dir == 0) ? 1 : (dir == 2) ? -1 : 0);  // agents.py:183
         const int fy = cy + ((dir == 1) ? 1 : (dir == 3) ? -1 : 0);
         const bool inb = (unsigned)fx < (unsigned)W && (unsigned)fy < (unsigned)H;
-        const int fidx = inb ? fx * H + fy : 0;
         if (c.dirty) pf = front_cells(c, cx, cy, fx, fy, inb);
         const int ftype = inb ? (int)(pf & 0xFFu) : (int)MG_T_WALL;
         if (!inb) c.add_err(MG_ERR_STACK);  // grid.get asserts in-bounds (base.py:154-156); never hit with wall_rect
@@ -425,7 +438,7 @@ __device__ bool env_step(EnvCtx<RS>& c, unsigned long long g, const int32_t* __r
           if (!(p.flags & MG_F_GHOST) && ftype == MG_T_EMPTY && queue_head(c, fx, fy) >= 0) can_move = false;  // fwd_cell is a GridAgent
           if (can_move) {
             const int ctype = (int)((pf >> 16) & 0xFFu);
-            if (ctype != MG_T_EMPTY && !can_overlap_static(ctype, c.tp[2 * S + cx * H + cy])) c.add_err(MG_ERR_STACK);  // base.py:558
+            if (ctype != MG_T_EMPTY && !can_overlap_static(ctype, (int)(c.static_cell(cx, cy) >> 16))) c.add_err(MG_ERR_STACK);  // base.py:558
             w0 = (w0 & 0xFFFF0000u) | (uint32_t)fx | ((uint32_t)fy << 8);
             c.R(a, 2) = c.next_stamp();  // appended last to the target cell's queue (base.py:547-552)
             if (ftype == MG_T_GOAL || ftype == MG_T_BONUS) {  // hasattr(fwd_cell, 'get_reward') base.py:576
@@ -444,7 +457,8 @@ __device__ bool env_step(EnvCtx<RS>& c, unsigned long long g, const int32_t* __r
         } else if (action == MG_A_PICKUP) {  // base.py:590-597
           const uint32_t w1 = c.R(a, 1);
           if (ftype != MG_T_EMPTY && ((PICKUP_MASK >> ftype) & 1u) && (w1 & 0xFFu) == 0u) {
-            c.R(a, 1) = (w1 & 0xFF000000u) | (uint32_t)ftype | ((uint32_t)c.tp[S + fidx] << 8) | ((uint32_t)c.tp[2 * S + fidx] << 16);
+            const uint32_t cell = c.static_cell(fx, fy);
+            c.R(a, 1) = (w1 & 0xFF000000u) | (cell & 0x00FFFFFFu);
             c.set_cell(fx, fy, 0, 0, 0);
           }
         } else if (action == MG_A_DROP) {  // base.py:600-606
@@ -456,7 +470,7 @@ __device__ bool env_step(EnvCtx<RS>& c, unsigned long long g, const int32_t* __r
         } else {  // MG_A_TOGGLE base.py:609-613, Door.toggle objects.py:333-346
           if (ftype == MG_T_DOOR) {
             const uint32_t w1 = c.R(a, 1);
-            const int fstate = (int)((pf >> 8) & 0xFFu), fcol = c.tp[S + fidx];
+            const int fstate = (int)((pf >> 8) & 0xFFu), fcol = (int)((c.static_cell(fx, fy) >> 8) & 0xFFu);
             int ns = fstate;
             if (fstate == MG_DOOR_LOCKED) {
               if ((w1 & 0xFFu) == MG_T_KEY && (int)((w1 >> 8) & 0xFFu) == fcol) ns = MG_DOOR_CLOSED;
@@ -775,8 +789,12 @@ __device__ __forceinline__ void obs_prepare(const KP& p, const ObsSmem<V>& o, in
   if (OBS == 1) {
     int4* z = reinterpret_cast<int4*>(o.out);
     const int n16 = ENVS_PER_CTA * A * V * V * 3 / 16;
-#pragma unroll 4
-    for (int i = tid; i < n16; i += nthreads) z[i] = make_int4(0, 0, 0, 0);
+    constexpr int ITERS = (V * V * 3 + 15) / 16;  // n16 / (32*A) rounded up: the block has 32*A threads
+#pragma unroll
+    for (int k = 0; k < ITERS; ++k) {
+      const int i = tid + k * nthreads;
+      if (i < n16) z[i] = make_int4(0, 0, 0, 0);
+    }
   } else {
     const int tile_bytes = p.ts * p.ts * 3;
     const int slots = p.n_tiles * p.orient_slots;
@@ -794,9 +812,9 @@ __device__ __forceinline__ void obs_prepare(const KP& p, const ObsSmem<V>& o, in
 
 // one agent view: gen_obs_grid + encode / tile ids.  rec = the env's agent records [q*4 + w] in shared memory,
 // tp = the env's byte planes (global memory on the bit-plane path, shared memory on the byte path)
-template <int OBS, int V, bool BITS>
+template <int OBS, int V, bool BITS, bool HEADS = false>
 __device__ __forceinline__ void obs_view(const KP& p, const ObsSmem<V>& o, int view, int a, long long env, const uint32_t* __restrict__ rec,
-                                         const uint8_t* __restrict__ tp, const uint32_t* __restrict__ bits) {
+                                         const uint8_t* __restrict__ tp, const uint32_t* __restrict__ bits, const uint8_t* __restrict__ heads = nullptr) {
   constexpr int VV = V * V;
   const int A = p.A, S = p.S;
   const uint32_t w0 = rec[a * 4];
@@ -819,11 +837,24 @@ __device__ __forceinline__ void obs_view(const KP& p, const ObsSmem<V>& o, int v
       encode_walls<V, 0>(pv.vis_lo & pv.cw_lo, out);
       if (V > 4) encode_walls<V, 4>(pv.vis_hi & pv.cw_hi, out);
     }
-    encode_cells<V, 0>(pv.vis_lo & pv.ne_lo & ~pv.cw_lo, pv, tp, S, out);
-    if (V > 4) encode_cells<V, 4>(pv.vis_hi & pv.ne_hi & ~pv.cw_hi, pv, tp, S, out);
+    uint32_t g_lo = pv.vis_lo & pv.ne_lo & ~pv.cw_lo, g_hi = pv.vis_hi & pv.ne_hi & ~pv.cw_hi;  // visible objects that are not canonical walls
+    if (BITS) {
+#pragma unroll
+      for (int k = 0; k < OBJ_SLOTS; ++k) {  // the object list answers for (almost) all of them without touching the planes
+        const uint32_t e = bits[48 + k];
+        int va, vb;
+        if (!(e >> 31) || !world_to_view<V>(g, (int)(e & 15u), (int)((e >> 4) & 15u), va, vb)) continue;
+        const uint32_t bit = 1u << (8 * (vb & 3) + va);
+        if (vb < 4) { if (!(g_lo & bit)) continue; g_lo &= ~bit; } else { if (!(g_hi & bit)) continue; g_hi &= ~bit; }
+        uint8_t* oo = out + va * (V * 3) + vb * 3;
+        oo[0] = (uint8_t)((e >> 8) & 15u); oo[1] = (uint8_t)((e >> 12) & 15u); oo[2] = (uint8_t)((e >> 16) & 255u);
+      }
+    }
+    encode_cells<V, 0>(g_lo, pv, tp, S, out);  // whatever is left (byte path: everything) comes from the planes
+    if (V > 4) encode_cells<V, 4>(g_hi, pv, tp, S, out);
     for (int q = 0; q < A; ++q) {  // agents that are their cell's object: (13, colour, dir)
       const uint32_t v0 = rec[q * 4];
-      if (!((v0 >> 24) & AF_HEAD)) continue;
+      if (HEADS ? !heads[q] : !((v0 >> 24) & AF_HEAD)) continue;
       int va, vb;
       if (!world_to_view<V>(g, (int)(v0 & 0xFFu), (int)((v0 >> 8) & 0xFFu), va, vb)) continue;
       if (!pv.visible(va, vb) || pv.nonempty(va, vb)) continue;
@@ -848,7 +879,13 @@ __device__ __forceinline__ void obs_view(const KP& p, const ObsSmem<V>& o, int v
           t = 0;
           if ((cwr >> va) & 1u) t = wall_tile;
           else if ((ner >> va) & 1u) {
-            const int kind = p.kind_of_type[rowp[va * pv.vstep]];
+            int type;
+            if (BITS) {  // object list first, byte plane for objects that did not fit
+              const int cidx = pv.row0 + b * pv.ustep + va * pv.vstep;
+              const uint32_t e = obj_lookup(bits, cidx / p.H, cidx % p.H);
+              type = e ? (int)((e >> 8) & 15u) : (int)rowp[va * pv.vstep];
+            } else type = rowp[va * pv.vstep];
+            const int kind = p.kind_of_type[type];
             if (kind == 0xFF) bad = 1; else t = (uint8_t)(kind * per_kind);
           }
         }
@@ -857,7 +894,7 @@ __device__ __forceinline__ void obs_view(const KP& p, const ObsSmem<V>& o, int v
     }
     for (int q = 0; q < A; ++q) {
       const uint32_t v0 = rec[q * 4];
-      if (!((v0 >> 24) & AF_HEAD)) continue;
+      if (HEADS ? !heads[q] : !((v0 >> 24) & AF_HEAD)) continue;
       int va, vb;
       if (!world_to_view<V>(g, (int)(v0 & 0xFFu), (int)((v0 >> 8) & 0xFFu), va, vb)) continue;
       if (!pv.visible(va, vb)) continue;
@@ -988,7 +1025,7 @@ __global__ void __launch_bounds__(32 * MG_MAX_AGENTS) obs_kernel(const __grid_co
 // toggle that takes effect) and envs whose episode just ended are handed to one lane that runs the general
 // sequential code (env_step / env_reset above) -- rare, and exact.  Then the same threads observe.
 // ---------------------------------------------------------------------------------------------
-constexpr uint32_t FL_SLOW = 1u, FL_RESET = 2u, FL_BITS_DIRTY = 4u;  // s_flag bits; bits 8..15 movers, 16..31 error bits
+constexpr uint32_t FL_SLOW = 1u, FL_RESET = 2u, FL_BITS_DIRTY = 4u, FL_NOTDONE = 8u;  // s_flag bits; bits 8..15 movers, 16..31 error bits
 
 // the general sequential code, kept out of line so the common path keeps its registers
 __device__ __noinline__ void seq_step(EnvCtx<32>& c, unsigned long long g, const int32_t* act, double* rew) {
@@ -999,19 +1036,21 @@ __device__ __noinline__ void seq_reset(EnvCtx<32>& c, unsigned long long g) { en
 template <int OBS, int V, bool TS4>
 __global__ void __launch_bounds__(32 * MG_MAX_AGENTS, 4) fused_kernel(const __grid_constant__ KP p) {
   extern __shared__ __align__(128) unsigned char smem[];
-  const int tid = threadIdx.x, nthreads = blockDim.x;
+  const int tid = threadIdx.x, nthreads = blockDim.x, lane = tid & 31, warp = tid >> 5;
   const long long env0 = (long long)blockIdx.x * ENVS_PER_CTA;
   const int n_valid = (int)min((long long)ENVS_PER_CTA, p.B - env0);
   const int A = p.A, S = p.S, W = p.W, H = p.H;
 
   uint32_t* s_bits = reinterpret_cast<uint32_t*>(smem);
-  uint32_t* s_rec = s_bits + ENVS_PER_CTA * BITS_WORDS;       // [env][a][4]
+  uint32_t* s_rec = s_bits + ENVS_PER_CTA * BITS_WORDS;                       // [env][a][4]
   int32_t* s_env = reinterpret_cast<int32_t*>(s_rec + ENVS_PER_CTA * A * 4);  // [env][4]
   uint32_t* s_flag = reinterpret_cast<uint32_t*>(s_env + ENVS_PER_CTA * 4);   // [env]
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_flag + ENVS_PER_CTA);
+  uint32_t* s_order = s_flag + ENVS_PER_CTA;                                  // [env] processing order, nibble q = agent
+  uint8_t* s_head = reinterpret_cast<uint8_t*>(s_order + ENVS_PER_CTA);       // [32*A] queue-head flag per agent (padded to 256)
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_head + 32 * MG_MAX_AGENTS);
   uint8_t* s_out = reinterpret_cast<uint8_t*>(s_bar + 2);
   const ObsSmem<V> o = obs_smem<V>(s_out, A);
-  // scratch of the sequential path, aliased with the (not yet used) output area
+  // scratch of the sequential path, aliased with the output area (which is re-zeroed if it was used)
   uint32_t* s_trec = reinterpret_cast<uint32_t*>(s_out);  // [A*4][32] transposed records
   uint32_t* s_scr = s_trec + A * 4 * 32;                  // [32][32] reset row masks
 
@@ -1029,26 +1068,30 @@ __global__ void __launch_bounds__(32 * MG_MAX_AGENTS, 4) fused_kernel(const __gr
   const int le = mine ? tid / A : 0, a = mine ? tid - le * A : 0;
   const long long env = env0 + le;
   const int action = mine ? p.actions[env * A + a] : (int)MG_A_DONE;
+  obs_prepare<OBS, V>(p, o, tid, nthreads);  // while the copies are in flight
   mbar_wait(s_bar, 0);
+
+  // ---- phase 0 (warp 0, lane == env): the step's agent order, base.py:514-516 -- one Philox block per env ----
+  if (warp == 0 && lane < n_valid) {
+    const unsigned long long g = (unsigned long long)(p.env_offset + env0 + lane);
+    uint32_t fact = 1;
+    for (int i = 2; i <= A; ++i) fact *= (uint32_t)i;
+    const U4 r = philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)s_env[lane * 4 + 2], 0u, (uint32_t)p.seed, (uint32_t)(p.seed >> 32));
+    s_order[lane] = decode_order(__umulhi(r.x, fact), A);
+  }
 
   // ---- phase 1: every agent plays its action on a private copy of its record ----
   uint32_t* rec = s_rec + le * A * 4;
   const uint32_t* bits = s_bits + le * BITS_WORDS;
   uint8_t* tp = p.grid + env * 3 * S;
-  uint32_t w0 = 0, w1 = 0, errb = 0, order = 0;
-  bool moved = false;
+  uint32_t w0 = 0, w1 = 0, errb = 0, base_stamp = 0;
+  bool moved = false, slow = false;
   double reward = 0.0;
   int sc = 0;
   if (mine) {
     w0 = rec[a * 4]; w1 = rec[a * 4 + 1];
     sc = s_env[le * 4] + 1;  // base.py:512
-    const uint32_t t_life = (uint32_t)s_env[le * 4 + 2];
-    const unsigned long long g = (unsigned long long)(p.env_offset + env);
-    uint32_t fact = 1;
-    for (int i = 2; i <= A; ++i) fact *= (uint32_t)i;
-    const U4 r = philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), t_life, 0u, (uint32_t)p.seed, (uint32_t)(p.seed >> 32));
-    order = decode_order(__umulhi(r.x, fact), A);  // base.py:514-516
-    bool slow = false;
+    base_stamp = (uint32_t)s_env[le * 4 + 3] & 0xFFFFu;
     if ((w0 >> 24) & MG_AF_ACTIVE) {  // base.py:521
       const int cx = (int)(w0 & 0xFFu), cy = (int)((w0 >> 8) & 0xFFu), dir = (int)((w0 >> 16) & 3u);
       if (action == MG_A_LEFT) w0 = (w0 & 0xFF00FFFFu) | ((uint32_t)((dir + 3) & 3) << 16);        // base.py:530-531
@@ -1056,14 +1099,14 @@ __global__ void __launch_bounds__(32 * MG_MAX_AGENTS, 4) fused_kernel(const __gr
       else if (action >= MG_A_FORWARD && action <= MG_A_TOGGLE) {
         const int fx = cx + ((dir == 0) ? 1 : (dir == 2) ? -1 : 0), fy = cy + ((dir == 1) ? 1 : (dir == 3) ? -1 : 0);  // agents.py:183
         const bool inb = (unsigned)fx < (unsigned)W && (unsigned)fy < (unsigned)H;
-        const int fidx = inb ? fx * H + fy : 0;
-        const int ftype = inb ? type_from_words(bits[fx & 15], bits[32 + (fx & 15)], fy, tp, fidx) : (int)MG_T_WALL;
+        const uint32_t fcell = inb ? cell_triple(bits, fx & 15, fy & 15, tp, H, S) : (uint32_t)MG_T_WALL;
+        const int ftype = (int)(fcell & 0xFFu);
         if (!inb) errb |= MG_ERR_STACK;
         if (action == MG_A_FORWARD) {  // base.py:538-585 (ghost mode: other agents never block)
-          const int fstate = (ftype == MG_T_DOOR || ftype == MG_T_BONUS) ? (int)tp[2 * S + fidx] : 0;
+          const int fstate = (int)(fcell >> 16);
           if (ftype == MG_T_EMPTY || can_overlap_static(ftype, fstate)) {
-            const int ctype = type_from_words(bits[cx & 15], bits[32 + (cx & 15)], cy, tp, cx * H + cy);
-            if (ctype != MG_T_EMPTY && !can_overlap_static(ctype, tp[2 * S + cx * H + cy])) errb |= MG_ERR_STACK;  // base.py:558
+            const uint32_t ccell = cell_triple(bits, cx & 15, cy & 15, tp, H, S);
+            if ((ccell & 0xFFu) != MG_T_EMPTY && !can_overlap_static((int)(ccell & 0xFFu), (int)(ccell >> 16))) errb |= MG_ERR_STACK;  // base.py:558
             w0 = (w0 & 0xFFFF0000u) | (uint32_t)fx | ((uint32_t)fy << 8);
             moved = true;
             if (ftype == MG_T_GOAL || ftype == MG_T_BONUS) {  // base.py:576-581
@@ -1101,71 +1144,79 @@ __global__ void __launch_bounds__(32 * MG_MAX_AGENTS, 4) fused_kernel(const __gr
         }
       } else if (action != MG_A_DONE) errb |= MG_ERR_BAD_ACTION;  // base.py:619-620
     }
-    if (slow) atomicOr(&s_flag[le], FL_SLOW);
+    // one smem atomic per agent: slow request / mover bit / "not done yet" bit / error bits
+    const uint32_t add = (slow ? FL_SLOW : 0u) | (moved ? (0x100u << a) : 0u) | (((w0 >> 24) & MG_AF_DONE) ? 0u : FL_NOTDONE) | (errb << 16);
+    if (add) atomicOr(&s_flag[le], add);
   }
   __syncthreads();
 
   // ---- phase 2: commit (parallel envs) or replay sequentially (envs whose planes change) ----
-  const bool slow_env = mine && (s_flag[le] & FL_SLOW);
+  const uint32_t fl1 = mine ? s_flag[le] : 0u;
+  const bool slow_env = (fl1 & FL_SLOW) != 0;
+  bool used_scratch = false;
   if (mine && !slow_env) {
     rec[a * 4] = w0; rec[a * 4 + 1] = w1;
     p.rewards[env * A + a] = reward;
-    const uint32_t add = (moved ? (0x100u << a) : 0u) | (errb << 16);
-    if (add) atomicOr(&s_flag[le], add);
+    if (moved) {  // arrival stamp: movers are numbered in the reference's processing order (base.py:547-552)
+      const uint32_t order = s_order[le], movers = (fl1 >> 8) & 0xFFu;
+      int rank = 0;
+      for (int q = 0; q < A; ++q) {
+        const int b = (int)((order >> (4 * q)) & 0xFu);
+        if (b == a) break;
+        rank += (int)((movers >> b) & 1u);
+      }
+      rec[a * 4 + 2] = (base_stamp + (uint32_t)rank) & 0xFFFFu;
+    }
   } else if (slow_env && a == 0) {
+    used_scratch = true;
     EnvCtx<32> c{p, s_trec + le, tp, s_bits + le * BITS_WORDS, s_scr + le, 0, 0, 0, 0u, false};
     for (int q = 0; q < A; ++q) { c.R(q, 0) = rec[q * 4]; c.R(q, 1) = rec[q * 4 + 1]; c.R(q, 2) = rec[q * 4 + 2]; }
     c.sc = s_env[le * 4]; c.ep = s_env[le * 4 + 1]; c.tl = s_env[le * 4 + 2]; c.w3 = (uint32_t)s_env[le * 4 + 3];
     seq_step(c, (unsigned long long)(p.env_offset + env), p.actions + env * A, p.rewards + env * A);
-    for (int q = 0; q < A; ++q) { rec[q * 4] = c.R(q, 0); rec[q * 4 + 1] = c.R(q, 1); rec[q * 4 + 2] = c.R(q, 2); rec[q * 4 + 3] = 0u; }
-    s_env[le * 4] = c.sc; s_env[le * 4 + 2] = c.tl; s_env[le * 4 + 3] = (int)c.w3;
-    if (c.dirty) atomicOr(&s_flag[le], FL_BITS_DIRTY);
-  }
-  __syncthreads();
-
-  // ---- phase 3: arrival stamps of the movers, in the reference's processing order (base.py:547-552) ----
-  if (mine && !slow_env && moved) {
-    const uint32_t movers = (s_flag[le] >> 8) & 0xFFu;
-    int rank = 0;
+    bool nd = false;
     for (int q = 0; q < A; ++q) {
-      const int b = (int)((order >> (4 * q)) & 0xFu);
-      if (b == a) break;
-      rank += (int)((movers >> b) & 1u);
+      rec[q * 4] = c.R(q, 0); rec[q * 4 + 1] = c.R(q, 1); rec[q * 4 + 2] = c.R(q, 2); rec[q * 4 + 3] = 0u;
+      nd = nd || !((c.R(q, 0) >> 24) & MG_AF_DONE);
     }
-    rec[a * 4 + 2] = (((uint32_t)s_env[le * 4 + 3] & 0xFFFFu) + (uint32_t)rank) & 0xFFFFu;
+    s_env[le * 4] = c.sc; s_env[le * 4 + 2] = c.tl; s_env[le * 4 + 3] = (int)c.w3;
+    // the parallel pass left its own mover / not-done / error bits in the flag word: replace them by the replay's
+    s_flag[le] = FL_SLOW | (c.dirty ? FL_BITS_DIRTY : 0u) | (nd ? FL_NOTDONE : 0u);
   }
   __syncthreads();
 
-  // ---- phase 4: env bookkeeping, done (base.py:649), reset of finished envs (base.py:402-416) ----
-  if (mine && a == 0) {
-    const uint32_t fl = s_flag[le];
+  // ---- phase 3 (warp 0, lane == env): env bookkeeping, done (base.py:649), reset of finished envs (base.py:402-416) ----
+  if (warp == 0 && lane < n_valid) {
+    const int e = lane;
+    const uint32_t fl = s_flag[e];
     if (!(fl & FL_SLOW)) {
-      const uint32_t w3 = (uint32_t)s_env[le * 4 + 3];
-      s_env[le * 4] = sc;
-      s_env[le * 4 + 2] += 1;
-      s_env[le * 4 + 3] = (int)((w3 & 0xFFFF0000u) | (((w3 & 0xFFFFu) + (uint32_t)__popc((fl >> 8) & 0xFFu)) & 0xFFFFu) | (fl & 0xFFFF0000u));
+      const uint32_t w3 = (uint32_t)s_env[e * 4 + 3];
+      s_env[e * 4] += 1;      // step_count, base.py:512
+      s_env[e * 4 + 2] += 1;  // lifetime steps
+      s_env[e * 4 + 3] = (int)((w3 & 0xFFFF0000u) | (((w3 & 0xFFFFu) + (uint32_t)__popc((fl >> 8) & 0xFFu)) & 0xFFFFu) | (fl & 0xFFFF0000u));
     }
-    bool all_done = true;
-    for (int q = 0; q < A; ++q) all_done = all_done && ((rec[q * 4] >> 24) & MG_AF_DONE);
-    const bool dn = (s_env[le * 4] >= p.max_steps) || all_done;
-    p.done[env] = dn ? 1 : 0;
+    const bool dn = (s_env[e * 4] >= p.max_steps) || !(fl & FL_NOTDONE);
+    p.done[env0 + e] = dn ? 1 : 0;
     if (dn && p.autoreset) {
-      EnvCtx<32> c{p, s_trec + le, tp, s_bits + le * BITS_WORDS, s_scr + le, 0, 0, 0, 0u, false};
-      for (int q = 0; q < A; ++q) { c.R(q, 0) = rec[q * 4]; c.R(q, 1) = rec[q * 4 + 1]; c.R(q, 2) = rec[q * 4 + 2]; }
-      c.sc = s_env[le * 4]; c.ep = s_env[le * 4 + 1]; c.tl = s_env[le * 4 + 2]; c.w3 = (uint32_t)s_env[le * 4 + 3];
-      seq_reset(c, (unsigned long long)(p.env_offset + env));
-      for (int q = 0; q < A; ++q) { rec[q * 4] = c.R(q, 0); rec[q * 4 + 1] = c.R(q, 1); rec[q * 4 + 2] = c.R(q, 2); rec[q * 4 + 3] = 0u; }
-      s_env[le * 4] = c.sc; s_env[le * 4 + 1] = c.ep; s_env[le * 4 + 3] = (int)c.w3;
-      atomicOr(&s_flag[le], FL_BITS_DIRTY | FL_RESET);
+      used_scratch = true;
+      uint32_t* r = s_rec + e * A * 4;
+      EnvCtx<32> c{p, s_trec + e, p.grid + (env0 + e) * 3 * S, s_bits + e * BITS_WORDS, s_scr + e, 0, 0, 0, 0u, false};
+      for (int q = 0; q < A; ++q) { c.R(q, 0) = r[q * 4]; c.R(q, 1) = r[q * 4 + 1]; c.R(q, 2) = r[q * 4 + 2]; }
+      c.sc = s_env[e * 4]; c.ep = s_env[e * 4 + 1]; c.tl = s_env[e * 4 + 2]; c.w3 = (uint32_t)s_env[e * 4 + 3];
+      seq_reset(c, (unsigned long long)(p.env_offset + env0 + e));
+      for (int q = 0; q < A; ++q) { r[q * 4] = c.R(q, 0); r[q * 4 + 1] = c.R(q, 1); r[q * 4 + 2] = c.R(q, 2); r[q * 4 + 3] = 0u; }
+      s_env[e * 4] = c.sc; s_env[e * 4 + 1] = c.ep; s_env[e * 4 + 3] = (int)c.w3;
+      s_flag[e] = fl | FL_BITS_DIRTY | FL_RESET;
     }
   }
-  __syncthreads();
+  if (__syncthreads_or(used_scratch ? 1 : 0)) {  // the sequential path borrowed the output area: clean it again
+    obs_prepare<OBS, V>(p, o, tid, nthreads);
+    __syncthreads();
+  }
 
-  // ---- phase 5: queue heads (derived flag) from the final positions and stamps ----
-  bool head = false;
+  // ---- phase 4: queue heads (derived flag) from the final positions and stamps ----
   if (mine) {
     const uint32_t v0 = rec[a * 4];
-    head = ((v0 >> 24) & MG_AF_PLACED) != 0;
+    bool head = ((v0 >> 24) & MG_AF_PLACED) != 0;
     if (head) {
       const uint32_t st = rec[a * 4 + 2];
       for (int q = 0; q < A; ++q) {
@@ -1173,14 +1224,16 @@ __global__ void __launch_bounds__(32 * MG_MAX_AGENTS, 4) fused_kernel(const __gr
         if (q != a && ((u0 >> 24) & MG_AF_PLACED) && ((u0 ^ v0) & 0xFFFFu) == 0u && rec[q * 4 + 2] < st) head = false;
       }
     }
+    s_head[tid] = head ? 1 : 0;
   }
-  obs_prepare<OBS, V>(p, o, tid, nthreads);  // the scratch area is free again: it becomes the output area
-  __syncthreads();
-  if (mine) rec[a * 4] = head ? (rec[a * 4] | (AF_HEAD << 24)) : (rec[a * 4] & ~(AF_HEAD << 24));
   __syncthreads();
 
-  // ---- phase 6: observe the post-step world ----
-  if (mine) obs_view<OBS, V, true>(p, o, tid, a, env, rec, tp, bits);
+  // ---- phase 5: observe the post-step world ----
+  if (mine) {
+    // own record: publish the head flag (other threads take head flags from s_head and ignore this bit)
+    rec[a * 4] = s_head[tid] ? (rec[a * 4] | (AF_HEAD << 24)) : (rec[a * 4] & ~(AF_HEAD << 24));
+    obs_view<OBS, V, true, true>(p, o, tid, a, env, rec, tp, bits, s_head + le * A);
+  }
   __syncthreads();
   obs_emit<OBS, V, TS4>(p, o, env0, n_valid, tid, nthreads);
   if (tid == 0) {  // state goes back as it came: contiguous chunks, bulk copies
@@ -1189,9 +1242,9 @@ __global__ void __launch_bounds__(32 * MG_MAX_AGENTS, 4) fused_kernel(const __gr
     bulk_s2g(p.envrec + env0 * 4, s_env, (uint32_t)n_valid * 16u);
     bulk_commit();
   }
-  if (mine && a == 0 && (s_flag[le] & FL_BITS_DIRTY)) {
+  if (warp == 0 && lane < n_valid && (s_flag[lane] & FL_BITS_DIRTY)) {
     fence_proxy_async_smem();
-    bulk_s2g(p.cellbits + env * BITS_WORDS, s_bits + le * BITS_WORDS, BITS_WORDS * 4u);
+    bulk_s2g(p.cellbits + (env0 + lane) * BITS_WORDS, s_bits + lane * BITS_WORDS, BITS_WORDS * 4u);
     bulk_commit();
   }
   asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -1334,8 +1387,8 @@ static size_t fused_smem_bytes(const KP& p, int obs) {
   if (obs == 1) out = (size_t)ENVS_PER_CTA * p.A * p.V * p.V * 3;
   else out = (size_t)ENVS_PER_CTA * p.A * p.V * p.V + (size_t)((ENVS_PER_CTA * p.A + 15) / 16) * 16 + (size_t)(p.n_tiles * p.orient_slots + 1) * p.ts * p.ts * 3;
   const size_t scratch = (size_t)(p.A * 4 * 32 + 32 * 32) * 4;
-  const size_t b = (size_t)ENVS_PER_CTA * BITS_WORDS * 4 + (size_t)ENVS_PER_CTA * p.A * 16 + (size_t)ENVS_PER_CTA * 16 + (size_t)ENVS_PER_CTA * 4 + 16 +
-                   std::max(out, scratch);
+  const size_t b = (size_t)ENVS_PER_CTA * BITS_WORDS * 4 + (size_t)ENVS_PER_CTA * p.A * 16 + (size_t)ENVS_PER_CTA * 16 + (size_t)ENVS_PER_CTA * 8 +
+                   32 * MG_MAX_AGENTS + 16 + std::max(out, scratch);
   return (b + 15) / 16 * 16;
 }
 
