@@ -217,25 +217,18 @@ def main():
     # ---- timed: K cold steps (L2 flushed before each), per-step events ---------------------------
     launches0 = L.mg_launch_count()
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
-    mids = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     stops = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
-    for ev in mids:
-        ev.record()  # materialise the cudaEvent_t handles handed to the library below
     barrier()
     wall0 = time.perf_counter()
     for t in range(K):
         flush.fill_(t & 0xFF)
-        L.mg_debug_set_mid_event(ctypes.c_void_p(mids[t].cuda_event))
         starts[t].record()
-        env.step(actions[(W + t) % POOL])
+        env.step(actions[(W + t) % POOL])  # ONE launch: fused step + auto-reset + observe kernel
         stops[t].record()
-    L.mg_debug_set_mid_event(None)
     barrier()
     wall_cold = time.perf_counter() - wall0
     launches = L.mg_launch_count() - launches0
     cold_ms = [s.elapsed_time(e) for s, e in zip(starts, stops)]
-    obs_kernel_ms = [m.elapsed_time(e) for m, e in zip(mids, stops)]
-    step_kernel_ms = [s.elapsed_time(m) for s, m in zip(starts, mids)]
     cold_total_ms = float(sum(cold_ms))
 
     # ---- timed: K warm steps back to back (one event pair), launched from the C rollout loop ----
@@ -287,14 +280,13 @@ def main():
         warm_value = world * B * K / (warm_total_ms * 1e-3)
         e2e_value = world * B * KE / (e2e_ms * 1e-3)
         srt = sorted(cold_ms)
-        avg_step_s = (sum(cold_ms) / K) * 1e-3
-        avg_obs_s = (sum(obs_kernel_ms) / K) * 1e-3
-        achieved = ALGO_BYTES_OBS_KERNEL * B / avg_obs_s / 1e9
-        achieved_step = ALGO_BYTES_PER_ENV_STEP * B / avg_step_s / 1e9
+        avg_step_s = (sum(cold_ms) / K) * 1e-3            # one launch per step: this IS the kernel's average launch duration
+        med_step_s = srt[len(srt) // 2] * 1e-3            # a step on which no episode ends (99 of 100)
+        achieved = ALGO_BYTES_PER_ENV_STEP * B / avg_step_s / 1e9
         traffic = None
         try:
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-                traffic = json.load(f).get("mg_step_fused_dram_bytes_per_launch")
+                traffic = json.load(f).get("fused_kernel_dram_bytes_per_launch")
         except Exception:  # noqa: BLE001
             pass
         cpu = None
@@ -315,11 +307,11 @@ def main():
                     "steps": KE, "api": "mg_engine_step (C ABI, pinned host buffers, synchronous)", "checksum": e2e_checksum},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "kernel": "mg_kernel<RESET=1,OBS=1,V=7> (auto-reset + egocentric encode; the dominant launch of a step)",
-                         "algorithmic_bytes_per_launch": ALGO_BYTES_OBS_KERNEL * B, "avg_launch_ms": avg_obs_s * 1e3,
+                         "kernel": "fused_kernel<OBS=1,V=7> (env.step + auto-reset + egocentric encode: the only launch of a step)",
+                         "algorithmic_bytes_per_launch": ALGO_BYTES_PER_ENV_STEP * B, "avg_launch_ms": avg_step_s * 1e3,
                          "peak_source": peak_src,
-                         "whole_step": {"achieved": achieved_step, "frac": achieved_step / peak, "algorithmic_bytes": ALGO_BYTES_PER_ENV_STEP * B,
-                                        "avg_ms": avg_step_s * 1e3, "step_kernel_avg_ms": sum(step_kernel_ms) / K}},
+                         "note": "algorithmic bytes = SURVEY.md 8(d) 1272 B/env-step x 65536; launches timed cold (L2 flushed before each)",
+                         "median_launch": {"ms": med_step_s * 1e3, "frac": ALGO_BYTES_PER_ENV_STEP * B / med_step_s / 1e9 / peak}},
             "cpu_baseline": cpu,
             "clocks": clocks,
             "wall_s": {"cold_loop": wall_cold},

@@ -141,7 +141,7 @@ struct EnvCtx {
   uint32_t* rec;
   uint8_t* tp;
   uint32_t* bits;
-  uint32_t* scratch;  // reset only: 32 transposed words (wall rows, other-object rows)
+  uint32_t* scratch;  // reset only: 64 transposed words (wall / other-object masks, by row and by column)
   int sc, ep, tl;     // step_count, episode, lifetime steps
   uint32_t w3;        // lo16 next stamp, hi16 error bits
   bool dirty;         // planes modified during this step
@@ -224,13 +224,15 @@ __device__ __forceinline__ Draws make_draws(const KP& p, unsigned long long g, u
 
 // base.py:402-416 reset + _gen_grid (empty.py:9-16, cluttered.py:25-36, goalcycle.py:30-51), written straight to
 // the global planes.  A fresh world only ever holds canonical walls, a Goal and BonusTiles, so with BITS the
-// rejection sampling (base.py:690-708) runs on two row-mask sets kept in shared memory (walls / overlappable
-// others) and never reads a plane; the 48 bit-plane words are derived from them at the end.
+// rejection sampling (base.py:690-708) runs on row/column mask sets kept in shared memory (walls / overlappable
+// others) and never reads a plane; the bit-plane words are those masks.
+// The placement list (goal?, bonus tiles, clutter walls, agents) is walked by ONE loop over the try index k, so
+// that all lanes of a warp draw their Philox block on the same iteration (two tries per block).
 template <int RS, bool BITS>
 __device__ void env_reset(EnvCtx<RS>& c, unsigned long long g) {
   const KP& p = c.p;
-  const int W = p.W, H = p.H, S = p.S;
-  for (int a = 0; a < p.A; ++a) {  // agents.py:161-170 (dir survives)
+  const int W = p.W, H = p.H, S = p.S, A = p.A;
+  for (int a = 0; a < A; ++a) {  // agents.py:161-170 (dir survives)
     c.R(a, 0) = c.R(a, 0) & 0x00FF0000u;
     c.R(a, 1) = 0xFF000000u;
     c.R(a, 2) = 0;
@@ -238,11 +240,18 @@ __device__ void env_reset(EnvCtx<RS>& c, unsigned long long g) {
   int4* z = reinterpret_cast<int4*>(c.tp);
   for (int i = 0; i < 3 * S / 16; ++i) z[i] = make_int4(0, 0, 0, 0);
   c.w3 &= 0xFFFF0000u;
-  uint32_t* wall = c.scratch;             // wall[x*RS]: bit y = canonical wall at (x, y)
-  uint32_t* other = c.scratch + 16 * RS;  // other[x*RS]: bit y = Goal / BonusTile (both can_overlap)
+  uint32_t* wall = c.scratch;                // wall[x*RS]: bit y = canonical wall at (x, y)
+  uint32_t* other = c.scratch + 16 * RS;     // other[x*RS]: bit y = Goal / BonusTile (both can_overlap)
+  uint32_t* wallc = c.scratch + 32 * RS;     // the same two, column-major: wallc[y*RS] bit x
+  uint32_t* otherc = c.scratch + 48 * RS;
   if (BITS) {
-    const uint32_t full = (1u << H) - 1u, ends = 1u | (1u << (H - 1));
-    for (int x = 0; x < 16; ++x) { wall[x * RS] = (x == 0 || x == W - 1) ? full : (x < W ? ends : 0u); other[x * RS] = 0u; }
+    const uint32_t fullr = (1u << H) - 1u, endsr = 1u | (1u << (H - 1)), fullc = (1u << W) - 1u, endsc = 1u | (1u << (W - 1));
+    for (int i = 0; i < 16; ++i) {
+      wall[i * RS] = (i == 0 || i == W - 1) ? fullr : (i < W ? endsr : 0u);
+      wallc[i * RS] = (i == 0 || i == H - 1) ? fullc : (i < H ? endsc : 0u);
+      other[i * RS] = 0u; otherc[i * RS] = 0u;
+    }
+    for (int k = 0; k < OBJ_SLOTS; ++k) c.bits[48 + k] = 0u;
   }
   for (int i = 0; i < W; ++i) {  // wall_rect base.py:172-176
     c.tp[i * H] = MG_T_WALL; c.tp[S + i * H] = MG_C_WORST;
@@ -253,68 +262,63 @@ __device__ void env_reset(EnvCtx<RS>& c, unsigned long long g) {
     c.tp[(W - 1) * H + j] = MG_T_WALL; c.tp[S + (W - 1) * H + j] = MG_C_WORST;
   }
   int n_listed = 0;
-  if (BITS)
-    for (int k = 0; k < OBJ_SLOTS; ++k) c.bits[48 + k] = 0u;
   auto put_static = [&](int x, int y, int type, int colour, int state) {
     const int idx = x * H + y;
     c.tp[idx] = (uint8_t)type; c.tp[S + idx] = (uint8_t)colour; c.tp[2 * S + idx] = (uint8_t)state;
     if (BITS) {
-      if (type == MG_T_WALL) { wall[x * RS] |= 1u << y; other[x * RS] &= ~(1u << y); }
+      if (type == MG_T_WALL) { wall[x * RS] |= 1u << y; wallc[y * RS] |= 1u << x; }
       else {
-        other[x * RS] |= 1u << y; wall[x * RS] &= ~(1u << y);
+        other[x * RS] |= 1u << y; otherc[y * RS] |= 1u << x;
         if (n_listed < OBJ_SLOTS) c.bits[48 + n_listed++] = obj_entry(x, y, type, colour, state);  // Goal / BonusTiles
       }
     }
   };
-  auto cell_type = [&](int x, int y) -> int {  // 0 empty, WALL, or GOAL standing for "overlappable other"
-    if (BITS) return ((wall[x * RS] >> y) & 1u) ? (int)MG_T_WALL : (((other[x * RS] >> y) & 1u) ? (int)MG_T_GOAL : (int)MG_T_EMPTY);
-    return c.tp[x * H + y];
-  };
+  if (p.goal_mode == MG_GOAL_FIXED) put_static(W - 2, H - 2, MG_T_GOAL, MG_C_GREEN, 0);  // put_obj base.py:655-662
+  // placement list: [random goal] (cluttered.py:28-29), bonus tiles (goalcycle.py:34-46), clutter walls (cluttered.py:32-33), max_tries 100 each;
+  // then the agents with spawn_delay 0 (base.py:409-412), max_tries 1e5
+  const int n_goal = (p.goal_mode == MG_GOAL_RANDOM) ? 1 : 0;
+  const int n_bonus = p.n_bonus;
+  const int first_agent = n_goal + n_bonus + p.n_clutter, n_obj = first_agent + A;
+  const bool ghost = (p.flags & MG_F_GHOST) != 0;
+  uint32_t delayed = 0;  // agents that spawn later (agents.py:34): everything the loop needs lives in registers
+  for (int a = 0; a < A; ++a) delayed |= (p.spawn_delay[a] != 0 ? 1u : 0u) << a;
+  int obj = 0, tries = 0;
   Draws d = make_draws(p, g, (uint32_t)c.ep, TAG_RESET);
-  // base.py:690-708 place_obj / :664-688 try_place_obj
-  auto place = [&](int agent, int type, int colour, int state, int max_tries) {
-    for (int t = 0; t < max_tries; ++t) {
-      int x, y;
-      d.next(W, H, x, y);
-      const int st = cell_type(x, y);
-      bool ok;
-      if (agent < 0) ok = (st == MG_T_EMPTY);  // statics are placed before any agent: empty cell <=> grid_obj is None
-      else {
-        const bool overlap = (st == MG_T_EMPTY) || (BITS ? st != MG_T_WALL : can_overlap_static(st, c.tp[2 * S + x * H + y]));
-        ok = overlap && ((p.flags & MG_F_GHOST) || queue_head(c, x, y) < 0);
-      }
-      if (!ok) continue;
-      if (agent >= 0) put_agent(c, agent, x, y); else put_static(x, y, type, colour, state);
-      return;
+  while (obj < n_obj) {  // base.py:690-708 place_obj / :664-688 try_place_obj, one try per iteration
+    const int agent = obj - first_agent;
+    if (agent >= 0 && ((delayed >> agent) & 1u)) { ++obj; continue; }
+    int x, y;
+    d.next(W, H, x, y);
+    int st;  // 0 empty, WALL, or GOAL standing for "overlappable other"
+    if (BITS) st = ((wall[x * RS] >> y) & 1u) ? (int)MG_T_WALL : (((other[x * RS] >> y) & 1u) ? (int)MG_T_GOAL : (int)MG_T_EMPTY);
+    else st = c.tp[x * H + y];
+    bool ok;
+    if (agent < 0) ok = (st == MG_T_EMPTY);  // statics are placed before any agent: empty cell <=> grid_obj is None
+    else {
+      const bool overlap = (st == MG_T_EMPTY) || (BITS ? st != MG_T_WALL : can_overlap_static(st, c.tp[2 * S + x * H + y]));
+      ok = overlap && (ghost || queue_head(c, x, y) < 0);
     }
-    c.add_err(MG_ERR_PLACEMENT);  // RecursionError base.py:706
-  };
-  if (p.goal_mode == MG_GOAL_FIXED) put_static(W - 2, H - 2, MG_T_GOAL, MG_C_GREEN, 0);  // put_obj base.py:655-662 (replaces)
-  else if (p.goal_mode == MG_GOAL_RANDOM) place(-1, MG_T_GOAL, MG_C_GREEN, 0, 100);      // cluttered.py:28-29
-  for (int b = 0; b < p.n_bonus; ++b) place(-1, MG_T_BONUS, MG_C_YELLOW, b, 100);        // goalcycle.py:34-46
-  for (int k = 0; k < p.n_clutter; ++k) place(-1, MG_T_WALL, MG_C_WORST, 0, 100);        // cluttered.py:32-33
-  for (int a = 0; a < p.A; ++a)                                                          // base.py:409-412
-    if (p.spawn_delay[a] == 0) {
-      place(a, 0, 0, 0, 100000);
-      c.R(a, 0) |= (uint32_t)MG_AF_ACTIVE << 24;
+    if (ok) {
+      if (agent >= 0) { put_agent(c, agent, x, y); c.R(agent, 0) |= (uint32_t)MG_AF_ACTIVE << 24; }
+      else if (obj < n_goal) put_static(x, y, MG_T_GOAL, MG_C_GREEN, 0);
+      else if (obj < n_goal + n_bonus) put_static(x, y, MG_T_BONUS, MG_C_YELLOW, obj - n_goal);
+      else put_static(x, y, MG_T_WALL, MG_C_WORST, 0);
+      ++obj; tries = 0;
+    } else if (++tries >= (agent >= 0 ? 100000 : 100)) {
+      c.add_err(MG_ERR_PLACEMENT);  // RecursionError base.py:706
+      if (agent >= 0) c.R(agent, 0) |= (uint32_t)MG_AF_ACTIVE << 24;  // the reference would have raised before activate()
+      ++obj; tries = 0;
     }
+  }
   c.sc = 0;
   c.ep += 1;
-  if (BITS) {  // derive the 48 words: rows, columns (transposes), canonical walls
+  if (BITS) {  // the masks ARE the bit-plane words
     uint32_t* bits = c.bits;
-    for (int x = 0; x < 16; ++x) {
-      const uint32_t wl = wall[x * RS], ot = other[x * RS];
-      bits[x] = wl | ((wl | ot) << 16);
-      bits[32 + x] = wl;
-    }
-    for (int y = 0; y < 16; ++y) {
-      uint32_t opq = 0, ne = 0;
-      for (int x = 0; x < 16; ++x) {
-        const uint32_t wl = (wall[x * RS] >> y) & 1u, ot = (other[x * RS] >> y) & 1u;
-        opq |= wl << x; ne |= (wl | ot) << x;
-      }
-      bits[16 + y] = opq | (ne << 16);
-      bits[32 + y] |= opq << 16;
+    for (int i = 0; i < 16; ++i) {
+      const uint32_t wl = wall[i * RS], ot = other[i * RS], wc = wallc[i * RS], oc = otherc[i * RS];
+      bits[i] = wl | ((wl | ot) << 16);
+      bits[16 + i] = wc | ((wc | oc) << 16);
+      bits[32 + i] = wl | (wc << 16);
     }
   }
 }
@@ -1028,10 +1032,16 @@ __global__ void __launch_bounds__(32 * MG_MAX_AGENTS) obs_kernel(const __grid_co
 constexpr uint32_t FL_SLOW = 1u, FL_RESET = 2u, FL_BITS_DIRTY = 4u, FL_NOTDONE = 8u;  // s_flag bits; bits 8..15 movers, 16..31 error bits
 
 // the general sequential code, kept out of line so the common path keeps its registers
-__device__ __noinline__ void seq_step(EnvCtx<32>& c, unsigned long long g, const int32_t* act, double* rew) {
+__device__ __noinline__ void seq_step(EnvCtx<32>& cref, unsigned long long g, const int32_t* act, double* rew) {
+  EnvCtx<32> c = cref;  // work on registers, not through the reference (local memory)
   env_step<32, true, MG_MAX_AGENTS>(c, g, act, rew);
+  cref.sc = c.sc; cref.ep = c.ep; cref.tl = c.tl; cref.w3 = c.w3; cref.dirty = c.dirty;
 }
-__device__ __noinline__ void seq_reset(EnvCtx<32>& c, unsigned long long g) { env_reset<32, true>(c, g); }
+__device__ __noinline__ void seq_reset(EnvCtx<32>& cref, unsigned long long g) {
+  EnvCtx<32> c = cref;
+  env_reset<32, true>(c, g);
+  cref.sc = c.sc; cref.ep = c.ep; cref.tl = c.tl; cref.w3 = c.w3; cref.dirty = c.dirty;
+}
 
 template <int OBS, int V, bool TS4>
 __global__ void __launch_bounds__(32 * MG_MAX_AGENTS, 4) fused_kernel(const __grid_constant__ KP p) {
@@ -1052,7 +1062,7 @@ __global__ void __launch_bounds__(32 * MG_MAX_AGENTS, 4) fused_kernel(const __gr
   const ObsSmem<V> o = obs_smem<V>(s_out, A);
   // scratch of the sequential path, aliased with the output area (which is re-zeroed if it was used)
   uint32_t* s_trec = reinterpret_cast<uint32_t*>(s_out);  // [A*4][32] transposed records
-  uint32_t* s_scr = s_trec + A * 4 * 32;                  // [32][32] reset row masks
+  uint32_t* s_scr = s_trec + A * 4 * 32;                  // [64][32] reset row / column masks
 
   if (tid == 0) mbar_init(s_bar, 1);
   if (tid < ENVS_PER_CTA) s_flag[tid] = 0u;
@@ -1184,7 +1194,8 @@ __global__ void __launch_bounds__(32 * MG_MAX_AGENTS, 4) fused_kernel(const __gr
   }
   __syncthreads();
 
-  // ---- phase 3 (warp 0, lane == env): env bookkeeping, done (base.py:649), reset of finished envs (base.py:402-416) ----
+  // ---- phase 3 (warp 0, lane == env): env bookkeeping and done (base.py:649) ----
+  bool want_reset = false;
   if (warp == 0 && lane < n_valid) {
     const int e = lane;
     const uint32_t fl = s_flag[e];
@@ -1196,20 +1207,21 @@ __global__ void __launch_bounds__(32 * MG_MAX_AGENTS, 4) fused_kernel(const __gr
     }
     const bool dn = (s_env[e * 4] >= p.max_steps) || !(fl & FL_NOTDONE);
     p.done[env0 + e] = dn ? 1 : 0;
-    if (dn && p.autoreset) {
-      used_scratch = true;
-      uint32_t* r = s_rec + e * A * 4;
-      EnvCtx<32> c{p, s_trec + e, p.grid + (env0 + e) * 3 * S, s_bits + e * BITS_WORDS, s_scr + e, 0, 0, 0, 0u, false};
-      for (int q = 0; q < A; ++q) { c.R(q, 0) = r[q * 4]; c.R(q, 1) = r[q * 4 + 1]; c.R(q, 2) = r[q * 4 + 2]; }
-      c.sc = s_env[e * 4]; c.ep = s_env[e * 4 + 1]; c.tl = s_env[e * 4 + 2]; c.w3 = (uint32_t)s_env[e * 4 + 3];
-      seq_reset(c, (unsigned long long)(p.env_offset + env0 + e));
-      for (int q = 0; q < A; ++q) { r[q * 4] = c.R(q, 0); r[q * 4 + 1] = c.R(q, 1); r[q * 4 + 2] = c.R(q, 2); r[q * 4 + 3] = 0u; }
-      s_env[e * 4] = c.sc; s_env[e * 4 + 1] = c.ep; s_env[e * 4 + 3] = (int)c.w3;
-      s_flag[e] = fl | FL_BITS_DIRTY | FL_RESET;
-    }
+    if (dn && p.autoreset) { want_reset = true; s_flag[e] = fl | FL_BITS_DIRTY | FL_RESET; }
   }
-  if (__syncthreads_or(used_scratch ? 1 : 0)) {  // the sequential path borrowed the output area: clean it again
-    obs_prepare<OBS, V>(p, o, tid, nthreads);
+  const int scratch_state = __syncthreads_or((used_scratch ? 1 : 0) | (want_reset ? 2 : 0));
+  if (scratch_state) {
+    // finished envs: MultiGridEnv.reset (base.py:402-416), one lane per env spread over all warps of the CTA
+    if (mine && a == 0 && (s_flag[le] & FL_RESET)) {
+      EnvCtx<32> c{p, s_trec + le, tp, s_bits + le * BITS_WORDS, s_scr + le, 0, 0, 0, 0u, false};
+      for (int q = 0; q < A; ++q) { c.R(q, 0) = rec[q * 4]; c.R(q, 1) = rec[q * 4 + 1]; c.R(q, 2) = rec[q * 4 + 2]; }
+      c.sc = s_env[le * 4]; c.ep = s_env[le * 4 + 1]; c.tl = s_env[le * 4 + 2]; c.w3 = (uint32_t)s_env[le * 4 + 3];
+      seq_reset(c, (unsigned long long)(p.env_offset + env));
+      for (int q = 0; q < A; ++q) { rec[q * 4] = c.R(q, 0); rec[q * 4 + 1] = c.R(q, 1); rec[q * 4 + 2] = c.R(q, 2); rec[q * 4 + 3] = 0u; }
+      s_env[le * 4] = c.sc; s_env[le * 4 + 1] = c.ep; s_env[le * 4 + 3] = (int)c.w3;
+    }
+    __syncthreads();
+    obs_prepare<OBS, V>(p, o, tid, nthreads);  // the sequential path borrowed the output area: clean it again
     __syncthreads();
   }
 
@@ -1386,7 +1398,7 @@ static size_t fused_smem_bytes(const KP& p, int obs) {
   size_t out = 0;
   if (obs == 1) out = (size_t)ENVS_PER_CTA * p.A * p.V * p.V * 3;
   else out = (size_t)ENVS_PER_CTA * p.A * p.V * p.V + (size_t)((ENVS_PER_CTA * p.A + 15) / 16) * 16 + (size_t)(p.n_tiles * p.orient_slots + 1) * p.ts * p.ts * 3;
-  const size_t scratch = (size_t)(p.A * 4 * 32 + 32 * 32) * 4;
+  const size_t scratch = (size_t)(p.A * 4 * 32 + 64 * 32) * 4;
   const size_t b = (size_t)ENVS_PER_CTA * BITS_WORDS * 4 + (size_t)ENVS_PER_CTA * p.A * 16 + (size_t)ENVS_PER_CTA * 16 + (size_t)ENVS_PER_CTA * 8 +
                    32 * MG_MAX_AGENTS + 16 + std::max(out, scratch);
   return (b + 15) / 16 * 16;
@@ -1439,7 +1451,7 @@ template <int MODE>
 static int launch_env(const KP& p, cudaStream_t s) {
   const long long blocks = (p.B + ENV_THREADS - 1) / ENV_THREADS;
   if (blocks <= 0) return 0;
-  const size_t sm = (size_t)ENV_THREADS * p.A * 16 + (size_t)ENV_THREADS * 32 * 4;
+  const size_t sm = (size_t)ENV_THREADS * p.A * 16 + (size_t)ENV_THREADS * 64 * 4;
   if (p.A <= 4) {
     if (p.cellbits) env_kernel<MODE, true, 4><<<(unsigned)blocks, ENV_THREADS, sm, s>>>(p);
     else env_kernel<MODE, false, 4><<<(unsigned)blocks, ENV_THREADS, sm, s>>>(p);
