@@ -55,7 +55,7 @@ class BatchedMultiGridEnv:
         self.envrec = torch.empty((B, 4), dtype=torch.int32, device=dev)
         self.cellbits = torch.empty((B, 52), dtype=torch.int32, device=dev)  # derived bit-planes (include/marlgrid_b200.h)
         self.rewards = torch.zeros((B, A), dtype=torch.float64, device=dev)
-        self.done = torch.zeros((B,), dtype=torch.uint8, device=dev)
+        self.done = torch.zeros((B,), dtype=torch.bool, device=dev)  # the kernels write 0/1 bytes: no conversion pass per step
         if obs_mode == "encoded":
             self.obs = torch.zeros((B, A, V, V, 3), dtype=torch.uint8, device=dev)
             self.atlas = None
@@ -139,7 +139,7 @@ class BatchedMultiGridEnv:
             _lib.check(rc, "mg_step_fused")
             if self.check_errors_each_step:
                 self.check_errors()
-            return self.obs, self.rewards, self.done.bool(), {}
+            return self.obs, self.rewards, self.done, {}
 
     def step_only(self, actions):
         """step without producing observations (mg_step); returns (rewards, done)."""
@@ -147,7 +147,7 @@ class BatchedMultiGridEnv:
             a = self._actions(actions)
             _lib.check(self._lib.mg_step(ctypes.byref(self.cfg), ctypes.byref(self._state), a.data_ptr(), self.rewards.data_ptr(),
                                          self.done.data_ptr(), int(self.autoreset), self._stream()), "mg_step")
-            return self.rewards, self.done.bool()
+            return self.rewards, self.done
 
     def observe(self):
         with torch.cuda.device(self.device):
@@ -169,7 +169,7 @@ class BatchedMultiGridEnv:
             assert a.shape[1:] == (self.num_envs, self.cfg.n_agents)
             _lib.check(self._lib.mg_rollout_fused(ctypes.byref(self.cfg), ctypes.byref(self._state), a.data_ptr(), T, self.rewards.data_ptr(),
                                                   self.done.data_ptr(), self.obs.data_ptr(), int(self.autoreset), self._stream()), "mg_rollout_fused")
-            return self.obs, self.rewards, self.done.bool()
+            return self.obs, self.rewards, self.done
 
     def random_actions(self, counter, n_actions=7, seed=0, out=None):
         """Uniform synthetic policy on the device; `counter` selects the draw."""
