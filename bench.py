@@ -28,6 +28,13 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 ENV_ID = "MarlGrid-3AgentCluttered15x15-v0"
+# other BASELINE.json configs, runnable for the record with --workload (the driver's line is always cfg3):
+#   name -> (env id, default batch, obs mode, agents, algorithmic bytes per env-step [SURVEY.md 8(d)])
+WORKLOADS = {
+    "cfg3": ("MarlGrid-3AgentCluttered15x15-v0", 65536, "encoded", 3, 1272),
+    "cfg2": ("MarlGrid-3AgentCluttered11x11-v0", 4096, "encoded", 3, 957),
+    "cfg4": ("MarlGrid-4AgentEmpty9x9-v0", 262144, "rgb", 4, 38070),
+}
 ALGO_BYTES_PER_ENV_STEP = 1272  # 743 read + 522 write + 7 amortised reset (whole env.step)
 ALGO_BYTES_OBS_KERNEL = 1164    # SURVEY.md 8(d) obs-kernel-only figure: read 3*W*H + 16*A = 723, write obs 441
 FALLBACK_HBM_GBS = 6650.0       # /opt/skills/guides/B200_PROFILING.md fallback
@@ -153,6 +160,41 @@ def workload_config(args, world):
     }
 
 
+def run_other_workload(args):
+    """Device-side throughput of another BASELINE config (cold, per-step events) -- informational line."""
+    import torch
+
+    from marlgrid_b200 import envs
+
+    env_id, B, mode, A, algo = WORKLOADS[args.workload]
+    if args.batch_per_gpu != 65536:
+        B = args.batch_per_gpu
+    env = envs.make(env_id, num_envs=B, obs_mode=mode, seed=1337)
+    env.reset()
+    acts = [env.random_actions(t) for t in range(32)]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=env.device)
+    for t in range(args.warmup):
+        env.step(acts[t % 32])
+    K = args.steps
+    st = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    en = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    torch.cuda.synchronize()
+    for t in range(K):
+        flush.fill_(t & 0xFF)
+        st[t].record()
+        env.step(acts[t % 32])
+        en[t].record()
+    torch.cuda.synchronize()
+    ms = sorted(a.elapsed_time(b) for a, b in zip(st, en))
+    tot = sum(ms)
+    peak, src = measured_peak()
+    ach = algo * B / (tot / K * 1e-3) / 1e9
+    print(json.dumps({"metric": "env-steps/s", "workload": args.workload, "env_id": env_id, "batch": B, "obs": mode, "value": B * K / (tot * 1e-3),
+                      "agent_steps_per_s": A * B * K / (tot * 1e-3), "ms_per_step": tot / K, "step_ms_median": ms[K // 2], "steps": K,
+                      "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                                   "algorithmic_bytes_per_launch": algo * B, "peak_source": src}}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -162,8 +204,11 @@ def main():
     ap.add_argument("--batch-per-gpu", type=int, default=65536)
     ap.add_argument("--e2e-steps", type=int, default=100)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if args.workload != "cfg3":
+        return run_other_workload(args)
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -186,6 +231,7 @@ def main():
 
         dist = dist_mod
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ["NCCL_DEBUG"] = "WARN"  # NCCL's version banner goes to stdout: rank 0 must print ONE JSON line
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
     B, K, W = args.batch_per_gpu, args.steps, args.warmup

@@ -766,7 +766,8 @@ __device__ __forceinline__ void encode_walls(uint32_t m, uint8_t* __restrict__ o
 // building blocks shared by the observe kernel and the fused step+observe kernel (32 envs per CTA, one thread
 // per agent view)
 //   OBS : 1 = encoded (MultiGrid.encode base.py:196-214), 2 = RGB tiles (base.py:301-331)
-//   TS4 : RGB only: tile rows are whole 32-bit words (ts % 4 == 0) -> 16-byte store path
+//   TSC : RGB only: 8 = tile size 8 known at compile time (every registered env), 1 = run-time tile size that is a
+//         multiple of 4 (tile rows are whole words -> 16-byte stores), 0 = any tile size (byte path)
 //   BITS: world described by the bit-planes (W, H <= 16) / by the byte planes staged in shared memory
 // ---------------------------------------------------------------------------------------------
 template <int V>
@@ -802,10 +803,21 @@ __device__ __forceinline__ void obs_prepare(const KP& p, const ObsSmem<V>& o, in
   } else {
     const int tile_bytes = p.ts * p.ts * 3;
     const int slots = p.n_tiles * p.orient_slots;
-    for (int i = tid; i < slots * tile_bytes; i += nthreads) {
-      const int slot = i / tile_bytes, off = i - slot * tile_bytes;
-      const int tile = slot / p.orient_slots, orient = slot - tile * p.orient_slots;
-      o.atlas[i] = p.atlas[(size_t)(tile * 4 + orient) * tile_bytes + off];
+    if ((tile_bytes & 15) == 0) {  // whole 16-byte chunks: vector copy (the atlas pointer is 16-byte aligned, checked on the host)
+      const int cpt = tile_bytes / 16;
+      const int4* src = reinterpret_cast<const int4*>(p.atlas);
+      int4* dst = reinterpret_cast<int4*>(o.atlas);
+      for (int i = tid; i < slots * cpt; i += nthreads) {
+        const int slot = i / cpt, ch = i - slot * cpt;
+        const int tile = slot / p.orient_slots, orient = slot - tile * p.orient_slots;
+        dst[i] = __ldg(src + (size_t)(tile * 4 + orient) * cpt + ch);
+      }
+    } else {
+      for (int i = tid; i < slots * tile_bytes; i += nthreads) {
+        const int slot = i / tile_bytes, off = i - slot * tile_bytes;
+        const int tile = slot / p.orient_slots, orient = slot - tile * p.orient_slots;
+        o.atlas[i] = p.atlas[(size_t)(tile * 4 + orient) * tile_bytes + off];
+      }
     }
     for (int i = tid; i < tile_bytes; i += nthreads) {  // COLORS['shadow'] objects.py:25, base.py:305
       const int c = i % 3;
@@ -914,7 +926,7 @@ __device__ __forceinline__ void obs_view(const KP& p, const ObsSmem<V>& o, int v
 }
 
 // stream the CTA's observations to HBM.  Must be called by all threads after a __syncthreads().
-template <int OBS, int V, bool TS4>
+template <int OBS, int V, int TSC>
 __device__ __forceinline__ void obs_emit(const KP& p, const ObsSmem<V>& o, long long env0, int n_valid, int tid, int nthreads) {
   constexpr int VV = V * V;
   const int A = p.A;
@@ -940,26 +952,38 @@ __device__ __forceinline__ void obs_emit(const KP& p, const ObsSmem<V>& o, long 
     const int row_bytes = V * ts * 3;
     const long long view_bytes = (long long)row_bytes * V * ts;
     uint8_t* dst = p.obs + env0 * A * view_bytes;
-    if (TS4) {
-      const int wpt = ts * 3 / 4;         // words per tile row
+    if (TSC != 0) {
+      // one thread = one 16-byte store; with TSC == 8 every divisor below is a compile-time constant
+      const int tsz = (TSC == 8) ? 8 : ts;
+      const int wpt = tsz * 3 / 4;        // words per tile row
       const int wpr = V * wpt;            // words per image row
-      const int v16 = (int)(view_bytes / 16);
+      const int v16 = (V * tsz * 3) * (V * tsz) / 16;
       const uint32_t* atlas_w = reinterpret_cast<const uint32_t*>(o.atlas);
       const int total16 = n_views * v16;
+      const int shadow_slot = p.n_tiles * p.orient_slots;
       for (int i = tid; i < total16; i += nthreads) {
         const int view = i / v16, k = i - view * v16;
         const int os = o.orient[view];
         const uint8_t* tl = o.tile + view * VV;
+        const int gw0 = 4 * k;
+        int y = gw0 / wpr;
+        const int xw = gw0 - y * wpr;
+        int va = xw / wpt, r = xw - va * wpt;
+        int vb = y / tsz, pyy = y - vb * tsz;
+        // the four words of a store walk along a tile row and at most once into the next tile (or image row):
+        // the tile is looked up again only then
+        int t = tl[vb * V + va];
+        const uint32_t* trow = atlas_w + (((t >= p.n_tiles) ? shadow_slot : t * p.orient_slots + os) * tsz + pyy) * wpt;
         uint32_t wv[4];
 #pragma unroll
         for (int w = 0; w < 4; ++w) {
-          const int gw = 4 * k + w;
-          const int y = gw / wpr, xw = gw - y * wpr;
-          const int va = xw / wpt, r = xw - va * wpt;
-          const int vb = y / ts, pyy = y - vb * ts;
-          const int t = tl[vb * V + va];
-          const int slot = (t >= p.n_tiles) ? p.n_tiles * p.orient_slots : t * p.orient_slots + os;
-          wv[w] = atlas_w[(slot * ts + pyy) * wpt + r];
+          wv[w] = trow[r];
+          if (++r == wpt && w < 3) {
+            r = 0;
+            if (++va == V) { va = 0; ++y; vb = y / tsz; pyy = y - vb * tsz; }
+            t = tl[vb * V + va];
+            trow = atlas_w + (((t >= p.n_tiles) ? shadow_slot : t * p.orient_slots + os) * tsz + pyy) * wpt;
+          }
         }
         st_stream_v4(reinterpret_cast<int4*>(dst) + i, make_int4((int)wv[0], (int)wv[1], (int)wv[2], (int)wv[3]));
       }
@@ -982,7 +1006,7 @@ __device__ __forceinline__ void obs_emit(const KP& p, const ObsSmem<V>& o, long 
 // ---------------------------------------------------------------------------------------------
 // observe kernel
 // ---------------------------------------------------------------------------------------------
-template <int OBS, int V, bool TS4, bool BITS>
+template <int OBS, int V, int TSC, bool BITS>
 __global__ void __launch_bounds__(32 * MG_MAX_AGENTS) obs_kernel(const __grid_constant__ KP p) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, nthreads = blockDim.x;
@@ -1015,7 +1039,7 @@ __global__ void __launch_bounds__(32 * MG_MAX_AGENTS) obs_kernel(const __grid_co
                            BITS ? s_bits + le * BITS_WORDS : nullptr);
   }
   __syncthreads();
-  obs_emit<OBS, V, TS4>(p, o, env0, n_valid, tid, nthreads);
+  obs_emit<OBS, V, TSC>(p, o, env0, n_valid, tid, nthreads);
   if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the CTA (and its shared memory) must outlive the read
 }
 
@@ -1043,7 +1067,7 @@ __device__ __noinline__ void seq_reset(EnvCtx<32>& cref, unsigned long long g) {
   cref.sc = c.sc; cref.ep = c.ep; cref.tl = c.tl; cref.w3 = c.w3; cref.dirty = c.dirty;
 }
 
-template <int OBS, int V, bool TS4>
+template <int OBS, int V, int TSC>
 __global__ void __launch_bounds__(32 * MG_MAX_AGENTS, 4) fused_kernel(const __grid_constant__ KP p) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, nthreads = blockDim.x, lane = tid & 31, warp = tid >> 5;
@@ -1247,7 +1271,7 @@ __global__ void __launch_bounds__(32 * MG_MAX_AGENTS, 4) fused_kernel(const __gr
     obs_view<OBS, V, true, true>(p, o, tid, a, env, rec, tp, bits, s_head + le * A);
   }
   __syncthreads();
-  obs_emit<OBS, V, TS4>(p, o, env0, n_valid, tid, nthreads);
+  obs_emit<OBS, V, TSC>(p, o, env0, n_valid, tid, nthreads);
   if (tid == 0) {  // state goes back as it came: contiguous chunks, bulk copies
     fence_proxy_async_smem();
     bulk_s2g(p.agents + env0 * A * 16, s_rec, (uint32_t)n_valid * (uint32_t)A * 16u);
@@ -1354,10 +1378,10 @@ static size_t obs_smem_bytes(const KP& p, int obs) {
   return (b + 15) / 16 * 16;
 }
 
-template <int OBS, int V, bool TS4, bool BITS>
+template <int OBS, int V, int TSC, bool BITS>
 static int launch_obs_one(const KP& p, cudaStream_t s) {
   const size_t sm = obs_smem_bytes(p, OBS);
-  auto k = obs_kernel<OBS, V, TS4, BITS>;
+  auto k = obs_kernel<OBS, V, TSC, BITS>;
   static size_t configured[64] = {0};  // per instantiation and device
   int dev = 0;
   cudaGetDevice(&dev);
@@ -1373,15 +1397,15 @@ static int launch_obs_one(const KP& p, cudaStream_t s) {
   return (int)cudaGetLastError();
 }
 
-template <int OBS, bool TS4, bool BITS>
+template <int OBS, int TSC, bool BITS>
 static int launch_obs_v(const KP& p, cudaStream_t s) {
   switch (p.V) {
-    case 3: return launch_obs_one<OBS, 3, TS4, BITS>(p, s);
-    case 4: return launch_obs_one<OBS, 4, TS4, BITS>(p, s);
-    case 5: return launch_obs_one<OBS, 5, TS4, BITS>(p, s);
-    case 6: return launch_obs_one<OBS, 6, TS4, BITS>(p, s);
-    case 7: return launch_obs_one<OBS, 7, TS4, BITS>(p, s);
-    case 8: return launch_obs_one<OBS, 8, TS4, BITS>(p, s);
+    case 3: return launch_obs_one<OBS, 3, TSC, BITS>(p, s);
+    case 4: return launch_obs_one<OBS, 4, TSC, BITS>(p, s);
+    case 5: return launch_obs_one<OBS, 5, TSC, BITS>(p, s);
+    case 6: return launch_obs_one<OBS, 6, TSC, BITS>(p, s);
+    case 7: return launch_obs_one<OBS, 7, TSC, BITS>(p, s);
+    case 8: return launch_obs_one<OBS, 8, TSC, BITS>(p, s);
   }
   return MG_E_CONFIG;
 }
@@ -1389,9 +1413,10 @@ static int launch_obs_v(const KP& p, cudaStream_t s) {
 // obs: 1 encoded / 2 rgb
 static int launch_obs(const KP& p, int obs, cudaStream_t s) {
   const bool bits = p.cellbits != nullptr;
-  if (obs == 1) return bits ? launch_obs_v<1, false, true>(p, s) : launch_obs_v<1, false, false>(p, s);
-  if (p.ts % 4 == 0) return bits ? launch_obs_v<2, true, true>(p, s) : launch_obs_v<2, true, false>(p, s);
-  return bits ? launch_obs_v<2, false, true>(p, s) : launch_obs_v<2, false, false>(p, s);
+  if (obs == 1) return bits ? launch_obs_v<1, 0, true>(p, s) : launch_obs_v<1, 0, false>(p, s);
+  if (p.ts == 8) return bits ? launch_obs_v<2, 8, true>(p, s) : launch_obs_v<2, 8, false>(p, s);
+  if (p.ts % 4 == 0) return bits ? launch_obs_v<2, 1, true>(p, s) : launch_obs_v<2, 1, false>(p, s);
+  return bits ? launch_obs_v<2, 0, true>(p, s) : launch_obs_v<2, 0, false>(p, s);
 }
 
 static size_t fused_smem_bytes(const KP& p, int obs) {
@@ -1404,10 +1429,10 @@ static size_t fused_smem_bytes(const KP& p, int obs) {
   return (b + 15) / 16 * 16;
 }
 
-template <int OBS, int V, bool TS4>
+template <int OBS, int V, int TSC>
 static int launch_fused_one(const KP& p, cudaStream_t s) {
   const size_t sm = fused_smem_bytes(p, OBS);
-  auto k = fused_kernel<OBS, V, TS4>;
+  auto k = fused_kernel<OBS, V, TSC>;
   static size_t configured[64] = {0};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -1423,15 +1448,15 @@ static int launch_fused_one(const KP& p, cudaStream_t s) {
   return (int)cudaGetLastError();
 }
 
-template <int OBS, bool TS4>
+template <int OBS, int TSC>
 static int launch_fused_v(const KP& p, cudaStream_t s) {
   switch (p.V) {
-    case 3: return launch_fused_one<OBS, 3, TS4>(p, s);
-    case 4: return launch_fused_one<OBS, 4, TS4>(p, s);
-    case 5: return launch_fused_one<OBS, 5, TS4>(p, s);
-    case 6: return launch_fused_one<OBS, 6, TS4>(p, s);
-    case 7: return launch_fused_one<OBS, 7, TS4>(p, s);
-    case 8: return launch_fused_one<OBS, 8, TS4>(p, s);
+    case 3: return launch_fused_one<OBS, 3, TSC>(p, s);
+    case 4: return launch_fused_one<OBS, 4, TSC>(p, s);
+    case 5: return launch_fused_one<OBS, 5, TSC>(p, s);
+    case 6: return launch_fused_one<OBS, 6, TSC>(p, s);
+    case 7: return launch_fused_one<OBS, 7, TSC>(p, s);
+    case 8: return launch_fused_one<OBS, 8, TSC>(p, s);
   }
   return MG_E_CONFIG;
 }
@@ -1468,8 +1493,9 @@ static cudaEvent_t g_mid_event = nullptr;  // profiling hook: recorded between t
 // env.step: one fused launch when eligible; else the step kernel (incl. auto-reset), then the observation
 static int launch_step_obs(const KP& p, int obs, cudaStream_t s) {
   if (obs != 0 && !g_force_two_kernels && fused_eligible(p)) {
-    if (obs == 1) return launch_fused_v<1, false>(p, s);
-    return (p.ts % 4 == 0) ? launch_fused_v<2, true>(p, s) : launch_fused_v<2, false>(p, s);
+    if (obs == 1) return launch_fused_v<1, 0>(p, s);
+    if (p.ts == 8) return launch_fused_v<2, 8>(p, s);
+    return (p.ts % 4 == 0) ? launch_fused_v<2, 1>(p, s) : launch_fused_v<2, 0>(p, s);
   }
   int e = launch_env<0>(p, s);
   if (e) return e;
@@ -1553,7 +1579,7 @@ static int atlas_mode(const MgConfig* cfg) { return (cfg->view_tile_size <= 10) 
 int mg_obs_rgb(const MgConfig* cfg, const MgState* st, const uint8_t* atlas, uint8_t* obs, mg_stream_t stream) {
   int e = check_state(cfg, st);
   if (e) return e;
-  if (!obs || !atlas || !aligned16(obs) || cfg->view_tile_size < 1) return MG_E_ARG;
+  if (!obs || !atlas || !aligned16(obs) || !aligned16(atlas) || cfg->view_tile_size < 1) return MG_E_ARG;
   KP p = make_kp(cfg, st);
   p.obs = obs; p.atlas = atlas; p.orient_slots = atlas_mode(cfg);
   return launch_obs(p, 2, (cudaStream_t)stream);
@@ -1573,7 +1599,7 @@ int mg_step_fused_rgb(const MgConfig* cfg, const MgState* st, const int32_t* act
                       const uint8_t* atlas, uint8_t* obs, int autoreset, mg_stream_t stream) {
   int e = check_state(cfg, st);
   if (e) return e;
-  if (!actions || !rewards || !done || !obs || !atlas || !aligned16(obs) || cfg->view_tile_size < 1) return MG_E_ARG;
+  if (!actions || !rewards || !done || !obs || !atlas || !aligned16(obs) || !aligned16(atlas) || cfg->view_tile_size < 1) return MG_E_ARG;
   KP p = make_kp(cfg, st);
   p.actions = actions; p.rewards = rewards; p.done = done; p.obs = obs; p.atlas = atlas; p.autoreset = autoreset;
   p.orient_slots = atlas_mode(cfg);
