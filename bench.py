@@ -50,54 +50,79 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock / throttle reasons sampled DURING the timed region: an NVML polling thread (5 ms period; the
+    timed region of this bench lasts ~0.1 s, too short for `nvidia-smi -lms` to even start), nvidia-smi as fallback."""
 
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index=0):
         self.index = index
-        self.proc = None
-        self.lines = []
+        self.sm, self.power, self.reason_bits = [], [], 0
+        self.sm_max = None
+        self.stop_flag = threading.Event()
+        self.thread = None
+        self.source = None
+
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if self.index < len(ids) and ids[self.index].isdigit():
+                return int(ids[self.index])
+        return self.index
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._pump, daemon=True)
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.source = "nvml"
+            self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
             self.thread.start()
         except Exception:  # noqa: BLE001
-            self.proc = None
+            self.source = None
 
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+    def _poll_nvml(self):
+        nv = self.nv
+        while not self.stop_flag.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.reason_bits |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.005)
+
+    def _one_shot_smi(self):
+        try:
+            out = subprocess.run(["nvidia-smi", f"--id={self._physical_index()}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                 capture_output=True, text=True, timeout=20).stdout.strip().splitlines()
+            parts = [p.strip() for p in out[0].split(",")]
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            return {"sm_mhz": float(parts[0]), "sm_max_mhz": float(parts[1]), "samples": 1, "source": "nvidia-smi (single sample after the timed region)",
+                    "reasons": sorted(n for n, v in zip(names, parts[3:7]) if v.lower().startswith("active"))}
+        except Exception:  # noqa: BLE001
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["nvml and nvidia-smi unavailable"]}
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:  # noqa: BLE001
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            parts = [p.strip() for p in ln.split(",")]
-            if len(parts) < 7:
-                continue
-            try:
-                sm.append(float(parts[0]))
-                mx.append(float(parts[1]))
-            except ValueError:
-                continue
-            for n, v in zip(names, parts[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "samples": len(sm), "reasons": sorted(reasons)}
+        if self.source != "nvml":
+            return self._one_shot_smi()
+        self.stop_flag.set()
+        self.thread.join(timeout=2)
+        nv = self.nv
+        names = [("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                 ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap),
+                 ("hw_power_brake", nv.nvmlClocksEventReasonHwPowerBrakeSlowdown)]
+        reasons = sorted(n for n, b in names if self.reason_bits & b)
+        sm = sorted(self.sm)
+        if not sm:
+            return self._one_shot_smi()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_min_mhz": sm[0], "sm_max_mhz": self.sm_max, "samples": len(sm), "source": "nvml, 5 ms period",
+                "power_w_max": max(self.power) if self.power else None, "reasons": reasons}
 
 
 def cpu_port_throughput(n_envs, threads, target_s=12.0, seed=1337):

@@ -222,6 +222,9 @@ void mg_debug_set_mid_event(void* cuda_event);
 /* Test hook: != 0 makes mg_step_fused* use the two-launch path (per-env step kernel, then observe kernel) even
  * where the single fused kernel applies, so both implementations stay covered. */
 void mg_debug_force_two_kernels(int on);
+/* Test hook: != 0 makes mg_step_fused* use the general fused kernel (run-time agent count / view size) even where a
+ * specialised instantiation (compile-time A and V: the registered env shapes) exists. */
+void mg_debug_force_general_fused(int on);
 
 #ifdef __cplusplus
 }

@@ -14,7 +14,7 @@ EXPORTS = (
     "mg_version", "mg_build_info", "mg_sizeof_config", "mg_config_validate", "mg_obs_bytes_per_env", "mg_init", "mg_sync_derived", "mg_reset", "mg_step",
     "mg_obs_encode", "mg_obs_rgb", "mg_step_fused", "mg_step_fused_rgb", "mg_rollout_fused", "mg_random_actions",
     "mg_los_batch", "mg_engine_create", "mg_engine_destroy", "mg_engine_reset", "mg_engine_step", "mg_host_alloc",
-    "mg_host_free", "mg_launch_count", "mg_debug_set_mid_event", "mg_debug_force_two_kernels",
+    "mg_host_free", "mg_launch_count", "mg_debug_set_mid_event", "mg_debug_force_two_kernels", "mg_debug_force_general_fused",
 )
 
 _lib = None
@@ -69,6 +69,8 @@ def load():
     L.mg_debug_set_mid_event.restype = None
     L.mg_debug_force_two_kernels.argtypes = [I]
     L.mg_debug_force_two_kernels.restype = None
+    L.mg_debug_force_general_fused.argtypes = [I]
+    L.mg_debug_force_general_fused.restype = None
     for name in EXPORTS:
         fn = getattr(L, name)
         if fn.restype is ctypes.c_int and name not in ("mg_version",):

@@ -1,0 +1,287 @@
+// mg_abi.cu -- host side of libmarlgrid_b200.so: the C ABI of include/marlgrid_b200.h on top of the kernel launchers.
+#include <atomic>
+
+#include "mg_common.cuh"
+
+using namespace mg;
+
+static std::atomic<long long> g_launches{0};
+namespace mg {
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+}
+
+static int check_cfg(const MgConfig* c) {
+  if (!c) return MG_E_CONFIG;
+  if (c->n_agents < 1 || c->n_agents > MG_MAX_AGENTS) return MG_E_CONFIG;
+  if (c->view_size < 3 || c->view_size > MG_MAX_VIEW) return MG_E_CONFIG;
+  if (c->width < 3 || c->height < 3 || c->width > 255 || c->height > 255) return MG_E_CONFIG;
+  if (c->plane_stride % 16 != 0 || c->plane_stride < c->width * c->height) return MG_E_CONFIG;
+  if (c->view_offset < 0 || c->view_offset >= c->view_size) return MG_E_CONFIG;
+  if (c->max_steps < 1 || c->n_clutter < 0 || c->n_bonus_tiles < 0 || c->n_bonus_tiles > 250) return MG_E_CONFIG;
+  return 0;
+}
+
+static KP make_kp(const MgConfig* c, const MgState* st) {
+  KP p;
+  memset(&p, 0, sizeof p);
+  p.W = c->width; p.H = c->height; p.A = c->n_agents; p.V = c->view_size; p.vo = c->view_offset; p.ts = c->view_tile_size;
+  p.max_steps = c->max_steps; p.n_clutter = c->n_clutter; p.n_bonus = c->n_bonus_tiles; p.goal_mode = c->goal_mode;
+  p.flags = c->flags; p.S = c->plane_stride;
+  p.goal_reward = c->goal_reward; p.bonus_reward = c->bonus_reward; p.bonus_penalty = c->bonus_penalty;
+  for (int i = 0; i < MG_MAX_AGENTS; ++i) { p.agent_color[i] = c->agent_color[i]; p.spawn_delay[i] = c->spawn_delay[i]; }
+  for (int i = 0; i < 15; ++i) p.kind_of_type[i] = c->kind_of_type[i];
+  p.kind_of_type[15] = 0xFF;
+  p.grid = st->grid; p.agents = st->agents; p.envrec = st->envrec; p.B = st->n_envs;
+  p.cellbits = (c->width <= 16 && c->height <= 16) ? st->cellbits : nullptr; p.env_offset = st->env_offset; p.seed = st->seed;
+  p.n_tiles = (c->n_static_kinds + 1) * (1 + 4 * c->n_agents);
+  p.orient_slots = 4;
+  return p;
+}
+
+static int g_force_two_kernels = 0;    // test hook: exercise the per-env step kernel + observe kernel pair
+static int g_force_general_fused = 0;  // test hook: exercise the general fused kernel where the specialised one applies
+
+static cudaEvent_t g_mid_event = nullptr;  // profiling hook: recorded between the two launches of a step
+
+// env.step: one fused launch when eligible; else the step kernel (incl. auto-reset), then the observation
+static int launch_step_obs(const KP& p, int obs, cudaStream_t s) {
+  if (obs != 0 && !g_force_two_kernels && fused_eligible(p)) {
+    if (!g_force_general_fused) {  // specialised kernel for the common shapes (mg_fused2.cu); MG_E_UNSUPPORTED = not one of them
+      const int e2 = launch_fused2(p, obs, s);
+      if (e2 != MG_E_UNSUPPORTED) return e2;
+    }
+    return launch_fused(p, obs, s);
+  }
+  int e = launch_env(0, p, s);
+  if (e) return e;
+  if (g_mid_event) cudaEventRecord(g_mid_event, s);
+  if (obs != 0) return launch_obs(p, obs, s);
+  return 0;
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+static int check_state(const MgConfig* c, const MgState* st) {
+  int e = check_cfg(c);
+  if (e) return e;
+  if (!st || !st->grid || !st->agents || !st->envrec || st->n_envs < 0) return MG_E_ARG;
+  if (!aligned16(st->grid) || !aligned16(st->agents) || !aligned16(st->envrec) || !aligned16(st->cellbits)) return MG_E_ARG;
+  return 0;
+}
+
+extern "C" {
+
+int mg_version(void) { return 1; }
+const char* mg_build_info(void) { return "marlgrid_b200 sm_100a: per-env step kernel + bit-plane observe kernel (cp.async.bulk + mbarrier staging, 32 envs/CTA)"; }
+int mg_sizeof_config(void) { return (int)sizeof(MgConfig); }
+int mg_config_validate(const MgConfig* cfg) { return check_cfg(cfg); }
+int64_t mg_obs_bytes_per_env(const MgConfig* c, int rgb) {
+  if (check_cfg(c)) return MG_E_CONFIG;
+  const int64_t v = c->view_size;
+  return rgb ? (int64_t)c->n_agents * v * c->view_tile_size * v * c->view_tile_size * 3 : (int64_t)c->n_agents * v * v * 3;
+}
+int64_t mg_launch_count(void) { return g_launches.load(); }
+void mg_debug_set_mid_event(void* cuda_event) { g_mid_event = (cudaEvent_t)cuda_event; }
+void mg_debug_force_two_kernels(int on) { g_force_two_kernels = on; }
+void mg_debug_force_general_fused(int on) { g_force_general_fused = on; }
+
+int mg_init(const MgConfig* cfg, const MgState* st, mg_stream_t stream) {
+  int e = check_state(cfg, st);
+  if (e) return e;
+  if (st->n_envs == 0) return 0;
+  return launch_init(st->grid, st->agents, st->envrec, st->cellbits, st->n_envs, cfg->n_agents, cfg->plane_stride, (cudaStream_t)stream);
+}
+
+int mg_sync_derived(const MgConfig* cfg, const MgState* st, mg_stream_t stream) {
+  int e = check_state(cfg, st);
+  if (e) return e;
+  if (st->n_envs == 0) return 0;
+  KP p = make_kp(cfg, st);
+  return launch_env(2, p, (cudaStream_t)stream);
+}
+
+int mg_reset(const MgConfig* cfg, const MgState* st, const uint8_t* reset_mask, mg_stream_t stream) {
+  int e = check_state(cfg, st);
+  if (e) return e;
+  KP p = make_kp(cfg, st);
+  p.reset_mask = reset_mask;
+  return launch_env(1, p, (cudaStream_t)stream);
+}
+
+int mg_step(const MgConfig* cfg, const MgState* st, const int32_t* actions, double* rewards, uint8_t* done, int autoreset,
+            mg_stream_t stream) {
+  int e = check_state(cfg, st);
+  if (e) return e;
+  if (!actions || !rewards || !done) return MG_E_ARG;
+  KP p = make_kp(cfg, st);
+  p.actions = actions; p.rewards = rewards; p.done = done; p.autoreset = autoreset;
+  return launch_step_obs(p, 0, (cudaStream_t)stream);
+}
+
+int mg_obs_encode(const MgConfig* cfg, const MgState* st, uint8_t* obs, mg_stream_t stream) {
+  int e = check_state(cfg, st);
+  if (e) return e;
+  if (!obs || !aligned16(obs)) return MG_E_ARG;
+  KP p = make_kp(cfg, st);
+  p.obs = obs;
+  return launch_obs(p, 1, (cudaStream_t)stream);
+}
+
+static int atlas_mode(const MgConfig* cfg) { return (cfg->view_tile_size <= 10) ? 1 : 4; }  // empty_tile alpha == 0 (base.py:247): rotation-equivariant
+
+int mg_obs_rgb(const MgConfig* cfg, const MgState* st, const uint8_t* atlas, uint8_t* obs, mg_stream_t stream) {
+  int e = check_state(cfg, st);
+  if (e) return e;
+  if (!obs || !atlas || !aligned16(obs) || !aligned16(atlas) || cfg->view_tile_size < 1) return MG_E_ARG;
+  KP p = make_kp(cfg, st);
+  p.obs = obs; p.atlas = atlas; p.orient_slots = atlas_mode(cfg);
+  return launch_obs(p, 2, (cudaStream_t)stream);
+}
+
+int mg_step_fused(const MgConfig* cfg, const MgState* st, const int32_t* actions, double* rewards, uint8_t* done, uint8_t* obs,
+                  int autoreset, mg_stream_t stream) {
+  int e = check_state(cfg, st);
+  if (e) return e;
+  if (!actions || !rewards || !done || !obs || !aligned16(obs)) return MG_E_ARG;
+  KP p = make_kp(cfg, st);
+  p.actions = actions; p.rewards = rewards; p.done = done; p.obs = obs; p.autoreset = autoreset;
+  return launch_step_obs(p, 1, (cudaStream_t)stream);
+}
+
+int mg_step_fused_rgb(const MgConfig* cfg, const MgState* st, const int32_t* actions, double* rewards, uint8_t* done,
+                      const uint8_t* atlas, uint8_t* obs, int autoreset, mg_stream_t stream) {
+  int e = check_state(cfg, st);
+  if (e) return e;
+  if (!actions || !rewards || !done || !obs || !atlas || !aligned16(obs) || !aligned16(atlas) || cfg->view_tile_size < 1) return MG_E_ARG;
+  KP p = make_kp(cfg, st);
+  p.actions = actions; p.rewards = rewards; p.done = done; p.obs = obs; p.atlas = atlas; p.autoreset = autoreset;
+  p.orient_slots = atlas_mode(cfg);
+  return launch_step_obs(p, 2, (cudaStream_t)stream);
+}
+
+int mg_rollout_fused(const MgConfig* cfg, const MgState* st, const int32_t* actions, int64_t n_steps, double* rewards, uint8_t* done,
+                     uint8_t* obs, int autoreset, mg_stream_t stream) {
+  int e = check_state(cfg, st);
+  if (e) return e;
+  if (!actions || !rewards || !done || !obs || !aligned16(obs)) return MG_E_ARG;
+  KP p = make_kp(cfg, st);
+  p.rewards = rewards; p.done = done; p.obs = obs; p.autoreset = autoreset;
+  for (int64_t t = 0; t < n_steps; ++t) {
+    p.actions = actions + t * st->n_envs * cfg->n_agents;
+    e = launch_step_obs(p, 1, (cudaStream_t)stream);
+    if (e) return e;
+  }
+  return 0;
+}
+
+int mg_random_actions(int32_t* actions, int64_t n, int n_actions, uint64_t seed, uint64_t counter, mg_stream_t stream) {
+  if (!actions || n < 0 || n_actions < 1) return MG_E_ARG;
+  if (n == 0) return 0;
+  return launch_random_actions(actions, n, n_actions, seed, counter, (cudaStream_t)stream);
+}
+
+int mg_los_batch(const uint8_t* transparent, uint8_t* mask, int64_t n, int view_size, int ax, int ay, mg_stream_t stream) {
+  if (!transparent || !mask || n < 0 || ax < 0 || ay < 0 || ax >= view_size || ay >= view_size) return MG_E_ARG;
+  if (n == 0) return 0;
+  return launch_los(transparent, mask, n, view_size, ax, ay, (cudaStream_t)stream);
+}
+
+// ---- host-buffer engine -----------------------------------------------------------------------
+struct MgEngine {
+  MgConfig cfg;
+  MgState st;
+  int device, rgb;
+  cudaStream_t stream;
+  int32_t* d_actions;
+  double* d_rewards;
+  uint8_t* d_done;
+  uint8_t* d_obs;
+  uint8_t* d_atlas;
+  int64_t obs_bytes;
+};
+
+#define MG_CUDA(x)                                \
+  do {                                            \
+    cudaError_t _e = (x);                         \
+    if (_e != cudaSuccess) return (int)_e;        \
+  } while (0)
+
+int mg_engine_create(MgEngine** out, const MgConfig* cfg, int64_t n_envs, int64_t env_offset, uint64_t seed, int device, int rgb,
+                     const uint8_t* atlas_host, int64_t atlas_bytes) {
+  if (!out || n_envs < 1) return MG_E_ARG;
+  int e = check_cfg(cfg);
+  if (e) return e;
+  if (rgb && (!atlas_host || atlas_bytes <= 0)) return MG_E_ARG;
+  MG_CUDA(cudaSetDevice(device));
+  MgEngine* en = new MgEngine();
+  memset(en, 0, sizeof *en);
+  en->cfg = *cfg; en->device = device; en->rgb = rgb;
+  en->st.n_envs = n_envs; en->st.env_offset = env_offset; en->st.seed = seed;
+  en->obs_bytes = n_envs * mg_obs_bytes_per_env(cfg, rgb);
+  MG_CUDA(cudaStreamCreateWithFlags(&en->stream, cudaStreamNonBlocking));
+  MG_CUDA(cudaMalloc(&en->st.grid, (size_t)n_envs * 3 * cfg->plane_stride));
+  MG_CUDA(cudaMalloc(&en->st.agents, (size_t)n_envs * cfg->n_agents * MG_AGENT_REC));
+  MG_CUDA(cudaMalloc(&en->st.envrec, (size_t)n_envs * MG_ENV_REC));
+  MG_CUDA(cudaMalloc(&en->st.cellbits, (size_t)n_envs * BITS_WORDS * 4));
+  MG_CUDA(cudaMalloc(&en->d_actions, (size_t)n_envs * cfg->n_agents * sizeof(int32_t)));
+  MG_CUDA(cudaMalloc(&en->d_rewards, (size_t)n_envs * cfg->n_agents * sizeof(double)));
+  MG_CUDA(cudaMalloc(&en->d_done, (size_t)n_envs));
+  MG_CUDA(cudaMalloc(&en->d_obs, (size_t)en->obs_bytes));
+  if (rgb) {
+    MG_CUDA(cudaMalloc(&en->d_atlas, (size_t)atlas_bytes));
+    MG_CUDA(cudaMemcpy(en->d_atlas, atlas_host, (size_t)atlas_bytes, cudaMemcpyHostToDevice));
+  }
+  e = mg_init(&en->cfg, &en->st, en->stream);
+  if (e) return e;
+  MG_CUDA(cudaStreamSynchronize(en->stream));
+  *out = en;
+  return 0;
+}
+
+void mg_engine_destroy(MgEngine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  cudaStreamSynchronize(e->stream);
+  cudaFree(e->st.grid); cudaFree(e->st.agents); cudaFree(e->st.envrec); cudaFree(e->st.cellbits);
+  cudaFree(e->d_actions); cudaFree(e->d_rewards); cudaFree(e->d_done); cudaFree(e->d_obs); cudaFree(e->d_atlas);
+  cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+int mg_engine_reset(MgEngine* e, uint8_t* obs_host) {
+  if (!e) return MG_E_ARG;
+  MG_CUDA(cudaSetDevice(e->device));
+  int r = mg_reset(&e->cfg, &e->st, nullptr, e->stream);
+  if (r) return r;
+  r = e->rgb ? mg_obs_rgb(&e->cfg, &e->st, e->d_atlas, e->d_obs, e->stream) : mg_obs_encode(&e->cfg, &e->st, e->d_obs, e->stream);
+  if (r) return r;
+  if (obs_host) MG_CUDA(cudaMemcpyAsync(obs_host, e->d_obs, (size_t)e->obs_bytes, cudaMemcpyDeviceToHost, e->stream));
+  MG_CUDA(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+int mg_engine_step(MgEngine* e, const int32_t* actions_host, uint8_t* obs_host, double* rewards_host, uint8_t* done_host, int autoreset) {
+  if (!e || !actions_host) return MG_E_ARG;
+  MG_CUDA(cudaSetDevice(e->device));
+  const size_t na = (size_t)e->st.n_envs * e->cfg.n_agents;
+  MG_CUDA(cudaMemcpyAsync(e->d_actions, actions_host, na * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+  int r = e->rgb ? mg_step_fused_rgb(&e->cfg, &e->st, e->d_actions, e->d_rewards, e->d_done, e->d_atlas, e->d_obs, autoreset, e->stream)
+                 : mg_step_fused(&e->cfg, &e->st, e->d_actions, e->d_rewards, e->d_done, e->d_obs, autoreset, e->stream);
+  if (r) return r;
+  if (obs_host) MG_CUDA(cudaMemcpyAsync(obs_host, e->d_obs, (size_t)e->obs_bytes, cudaMemcpyDeviceToHost, e->stream));
+  if (rewards_host) MG_CUDA(cudaMemcpyAsync(rewards_host, e->d_rewards, na * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+  if (done_host) MG_CUDA(cudaMemcpyAsync(done_host, e->d_done, (size_t)e->st.n_envs, cudaMemcpyDeviceToHost, e->stream));
+  MG_CUDA(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+void* mg_host_alloc(int64_t bytes) {
+  void* p = nullptr;
+  if (cudaMallocHost(&p, (size_t)bytes) != cudaSuccess) return nullptr;
+  return p;
+}
+void mg_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+}  // extern "C"

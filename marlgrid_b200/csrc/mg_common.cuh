@@ -1,0 +1,124 @@
+// mg_common.cuh -- kernel parameter block, derived bit-plane layout and launcher declarations shared by the
+// translation units of libmarlgrid_b200.so (sm_100a).  Reference citations are relative to /root/reference.
+#pragma once
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+
+#include "mg_device.cuh"
+
+namespace mg {
+
+constexpr int ENVS_PER_CTA = 32;
+constexpr int BITS_WORDS = 52;       // per env: 16 row words, 16 column words, 16 canonical-wall words, 4 object-list words
+constexpr int OBJ_SLOTS = 4;
+constexpr uint32_t AF_HEAD = 0x80u;  // derived flag bit: agent is the head of its cell's queue
+
+struct KP {
+  int W, H, A, V, vo, ts, max_steps, n_clutter, n_bonus, goal_mode;
+  uint32_t flags;
+  int S;
+  double goal_reward, bonus_reward, bonus_penalty;
+  uint8_t agent_color[MG_MAX_AGENTS];
+  int spawn_delay[MG_MAX_AGENTS];
+  uint8_t kind_of_type[16];
+  uint8_t* grid;
+  uint8_t* agents;
+  int32_t* envrec;
+  uint32_t* cellbits;  // [B][48] or nullptr (grid wider/taller than 16, or caller passed none): byte path
+  long long B, env_offset;
+  unsigned long long seed;
+  const int32_t* actions;
+  double* rewards;
+  uint8_t* done;
+  uint8_t* obs;
+  const uint8_t* atlas;
+  const uint8_t* reset_mask;
+  int autoreset;
+  int n_tiles;       // atlas tiles (without the appended shadow tile)
+  int orient_slots;  // 1: atlas is rotation-equivariant (dir remap), 4: one slot per view orientation
+};
+
+// ---------------------------------------------------------------------------------------------
+// bit-planes.  word x (0..15): row x, bit y = opaque(x,y), bit 16+y = non-empty(x,y)
+//              word 16+y     : column y, bit x = opaque, bit 16+x = non-empty
+//              word 32+i     : bit j = canonical wall at (i, j) [row i], bit 16+j = canonical wall at (j, i) [column i]
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool cell_opaque(int type, int state) {  // objects.py:281-282,330-331
+  return type == MG_T_WALL || (type == MG_T_DOOR && state != MG_DOOR_OPEN);
+}
+__device__ __forceinline__ bool cell_canon(int type, int colour, int state) {
+  return type == MG_T_WALL && colour == MG_C_WORST && state == 0;
+}
+//              word 48+k     : object list: up to 4 of the non-wall objects, x | y<<4 | type<<8 | colour<<12 | state<<16 | 1<<31.
+//                              A non-empty, non-canonical cell that is NOT listed is looked up in the byte planes, so the
+//                              list may be incomplete (more than 4 objects) but never wrong.
+__device__ __forceinline__ uint32_t obj_entry(int x, int y, int type, int colour, int state) {
+  return (uint32_t)x | ((uint32_t)y << 4) | ((uint32_t)type << 8) | ((uint32_t)(colour & 15) << 12) | ((uint32_t)(state & 255) << 16) | 0x80000000u;
+}
+__device__ __forceinline__ uint32_t obj_lookup(const uint32_t* bits, int x, int y) {
+  const uint32_t key = 0x80000000u | (uint32_t)x | ((uint32_t)y << 4);
+  uint32_t e = 0;
+#pragma unroll
+  for (int k = 0; k < OBJ_SLOTS; ++k) {
+    const uint32_t w = bits[48 + k];
+    if ((w & 0x800000FFu) == key) e = w;
+  }
+  return e;
+}
+__device__ __forceinline__ void obj_update(uint32_t* bits, int x, int y, int type, int colour, int state) {
+  const uint32_t key = 0x80000000u | (uint32_t)x | ((uint32_t)y << 4);
+  const bool listable = type != MG_T_EMPTY && !(type == MG_T_WALL && colour == MG_C_WORST && state == 0) && colour < 16;
+  int slot = -1;
+  for (int k = 0; k < OBJ_SLOTS; ++k) {
+    const uint32_t w = bits[48 + k];
+    if ((w & 0x800000FFu) == key) { bits[48 + k] = 0u; if (slot < 0) slot = k; }
+    else if (!(w >> 31) && slot < 0) slot = k;
+  }
+  if (listable && slot >= 0) bits[48 + slot] = obj_entry(x, y, type, colour, state);
+}
+__device__ __forceinline__ void bits_update_cell(uint32_t* bits, int x, int y, int type, int colour, int state) {
+  if (bits == nullptr) return;
+  const uint32_t op = cell_opaque(type, state) ? 1u : 0u, ne = type != MG_T_EMPTY ? 1u : 0u, cn = cell_canon(type, colour, state) ? 1u : 0u;
+  bits[x] = (bits[x] & ~((1u << y) | (1u << (16 + y)))) | (op << y) | (ne << (16 + y));
+  bits[16 + y] = (bits[16 + y] & ~((1u << x) | (1u << (16 + x)))) | (op << x) | (ne << (16 + x));
+  bits[32 + x] = (bits[32 + x] & ~(1u << y)) | (cn << y);
+  bits[32 + y] = (bits[32 + y] & ~(1u << (16 + x))) | (cn << (16 + x));
+  obj_update(bits, x, y, type, colour, state);
+}
+// rebuild all words from the byte planes
+__device__ inline void bits_rebuild(const uint8_t* tp, uint32_t* bits, int W, int H, int S) {
+  if (bits == nullptr) return;
+  for (int i = 0; i < BITS_WORDS; ++i) bits[i] = 0u;
+  for (int x = 0; x < W; ++x)
+    for (int y = 0; y < H; ++y) {
+      const int idx = x * H + y;
+      const int t = tp[idx];
+      if (t != MG_T_EMPTY) bits_update_cell(bits, x, y, t, tp[S + idx], tp[2 * S + idx]);
+    }
+}
+
+// (type | colour<<8 | state<<16) of the static object at (x, y): bit-planes, then the object list, then -- for
+// objects that did not fit the list -- the byte planes
+__device__ __forceinline__ uint32_t cell_triple(const uint32_t* bits, int x, int y, const uint8_t* tp, int H, int S) {
+  if (!((bits[x] >> (16 + y)) & 1u)) return 0u;
+  if ((bits[32 + x] >> y) & 1u) return (uint32_t)MG_T_WALL | ((uint32_t)MG_C_WORST << 8);
+  const uint32_t e = obj_lookup(bits, x, y);
+  if (e) return ((e >> 8) & 0xFu) | (((e >> 12) & 0xFu) << 8) | (((e >> 16) & 0xFFu) << 16);
+  const int idx = x * H + y;
+  return (uint32_t)tp[idx] | ((uint32_t)tp[S + idx] << 8) | ((uint32_t)tp[2 * S + idx] << 16);
+}
+
+// ---- launchers (one translation unit per kernel family, so the library builds in parallel) ----
+void count_launch();
+int launch_env(int mode, const KP& p, cudaStream_t s);          // mg_env_kernels.cu: 0 step(+auto-reset), 1 reset, 2 sync derived
+int launch_init(uint8_t* grid, uint8_t* agents, int32_t* envrec, uint32_t* cellbits, long long B, int A, int S, cudaStream_t s);
+int launch_random_actions(int32_t* actions, long long n, int n_actions, unsigned long long seed, unsigned long long counter, cudaStream_t s);
+int launch_los(const uint8_t* transparent, uint8_t* mask, long long n, int view_size, int ax, int ay, cudaStream_t s);
+int launch_obs(const KP& p, int obs, cudaStream_t s);           // mg_obs_kernels.cu: obs 1 encoded / 2 rgb
+int launch_fused(const KP& p, int obs, cudaStream_t s);         // mg_fused_kernels.cu: general one-launch step+observe
+bool fused_eligible(const KP& p);
+constexpr int MG_E_UNSUPPORTED = -100;                          // internal: the specialised kernel has no instantiation for this shape
+int launch_fused2(const KP& p, int obs, cudaStream_t s);        // mg_fused2.cu: specialised (compile-time A, V) one-launch step+observe
+
+}  // namespace mg

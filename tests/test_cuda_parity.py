@@ -52,12 +52,15 @@ def test_los_kernel_matches_golden_and_oracle(cuda_lib, oracle):
         assert np.array_equal(dm.cpu().numpy(), want), f"V={V} pos=({ax},{ay})"
 
 
-@pytest.fixture(params=["fused", "two_kernels"])
+@pytest.fixture(params=["fused", "general_fused", "two_kernels"])
 def step_impl(request, cuda_lib):
-    """env.step has two implementations (one fused launch / per-env step kernel + observe kernel): test both."""
+    """env.step has three implementations (specialised fused launch for the registered shapes / general fused launch /
+    per-env step kernel + observe kernel): test all of them."""
     cuda_lib.mg_debug_force_two_kernels(1 if request.param == "two_kernels" else 0)
+    cuda_lib.mg_debug_force_general_fused(1 if request.param == "general_fused" else 0)
     yield request.param
     cuda_lib.mg_debug_force_two_kernels(0)
+    cuda_lib.mg_debug_force_general_fused(0)
 
 
 @pytest.mark.parametrize("path", trajectory_files(), ids=lambda p: os.path.basename(p)[5:-4])
