@@ -35,6 +35,7 @@ static KP make_kp(const MgConfig* c, const MgState* st) {
   p.cellbits = (c->width <= 16 && c->height <= 16) ? st->cellbits : nullptr; p.env_offset = st->env_offset; p.seed = st->seed;
   p.n_tiles = (c->n_static_kinds + 1) * (1 + 4 * c->n_agents);
   p.orient_slots = 4;
+  p.wall_enc = (uint32_t)MG_T_WALL | ((uint32_t)MG_C_WORST << 8);
   return p;
 }
 

@@ -10,7 +10,19 @@
 namespace mg {
 
 constexpr int ENVS_PER_CTA = 32;
-constexpr int BITS_WORDS = 52;       // per env: 16 row words, 16 column words, 16 canonical-wall words, 4 object-list words
+// Derived bit-planes `cellbits`, 44 words per env (grids up to 16x16).  Two bits per cell:
+//   OP = opaque (Wall / Door that is not open: see_behind() false, objects.py:281-282,330-331)
+//   OT = "other": non-empty and NOT a canonical wall (canonical = exactly Wall('worst', state 0), the only wall the
+//        reference's generators create).   canonical wall == OP & ~OT,   non-empty == OP | OT.
+// stored as LINES, one word each: bits 0..15 = OP along the line, bits 16..31 = OT along the line,
+//   word LINE_X0 + x : x-line (cells (x, 0..15), bit = y)       words 0 and 17 stay zero (guard lines: a view
+//   word LINE_Y0 + y : y-line (cells (0..15, y), bit = x)       words 18 and 35     row outside the world is empty)
+//   word OBJ_WORD0 + k (k < 4): object list, x | y<<4 | type<<8 | colour<<12 | state<<16 | 1<<31 -- up to 4 of the OT objects
+//        (Goal, BonusTiles, Keys ...).  An OT cell that is NOT listed is looked up in the byte planes, so the list may be
+//        incomplete (more than 4 objects) but never wrong.
+//   words 40..43: reserved (zero)
+constexpr int BITS_WORDS = 44;
+constexpr int LINE_X0 = 1, LINE_Y0 = 19, OBJ_WORD0 = 36;
 constexpr int OBJ_SLOTS = 4;
 constexpr uint32_t AF_HEAD = 0x80u;  // derived flag bit: agent is the head of its cell's queue
 
@@ -37,22 +49,15 @@ struct KP {
   int autoreset;
   int n_tiles;       // atlas tiles (without the appended shadow tile)
   int orient_slots;  // 1: atlas is rotation-equivariant (dir remap), 4: one slot per view orientation
+  uint32_t wall_enc; // MG_T_WALL | MG_C_WORST << 8: the encoded canonical wall, as run-time data (see mg_fused2.cu)
 };
 
-// ---------------------------------------------------------------------------------------------
-// bit-planes.  word x (0..15): row x, bit y = opaque(x,y), bit 16+y = non-empty(x,y)
-//              word 16+y     : column y, bit x = opaque, bit 16+x = non-empty
-//              word 32+i     : bit j = canonical wall at (i, j) [row i], bit 16+j = canonical wall at (j, i) [column i]
-// ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool cell_opaque(int type, int state) {  // objects.py:281-282,330-331
   return type == MG_T_WALL || (type == MG_T_DOOR && state != MG_DOOR_OPEN);
 }
 __device__ __forceinline__ bool cell_canon(int type, int colour, int state) {
   return type == MG_T_WALL && colour == MG_C_WORST && state == 0;
 }
-//              word 48+k     : object list: up to 4 of the non-wall objects, x | y<<4 | type<<8 | colour<<12 | state<<16 | 1<<31.
-//                              A non-empty, non-canonical cell that is NOT listed is looked up in the byte planes, so the
-//                              list may be incomplete (more than 4 objects) but never wrong.
 __device__ __forceinline__ uint32_t obj_entry(int x, int y, int type, int colour, int state) {
   return (uint32_t)x | ((uint32_t)y << 4) | ((uint32_t)type << 8) | ((uint32_t)(colour & 15) << 12) | ((uint32_t)(state & 255) << 16) | 0x80000000u;
 }
@@ -61,29 +66,27 @@ __device__ __forceinline__ uint32_t obj_lookup(const uint32_t* bits, int x, int 
   uint32_t e = 0;
 #pragma unroll
   for (int k = 0; k < OBJ_SLOTS; ++k) {
-    const uint32_t w = bits[48 + k];
+    const uint32_t w = bits[OBJ_WORD0 + k];
     if ((w & 0x800000FFu) == key) e = w;
   }
   return e;
 }
 __device__ __forceinline__ void obj_update(uint32_t* bits, int x, int y, int type, int colour, int state) {
   const uint32_t key = 0x80000000u | (uint32_t)x | ((uint32_t)y << 4);
-  const bool listable = type != MG_T_EMPTY && !(type == MG_T_WALL && colour == MG_C_WORST && state == 0) && colour < 16;
+  const bool listable = type != MG_T_EMPTY && !cell_canon(type, colour, state) && colour < 16 && type < 16;
   int slot = -1;
   for (int k = 0; k < OBJ_SLOTS; ++k) {
-    const uint32_t w = bits[48 + k];
-    if ((w & 0x800000FFu) == key) { bits[48 + k] = 0u; if (slot < 0) slot = k; }
+    const uint32_t w = bits[OBJ_WORD0 + k];
+    if ((w & 0x800000FFu) == key) { bits[OBJ_WORD0 + k] = 0u; if (slot < 0) slot = k; }
     else if (!(w >> 31) && slot < 0) slot = k;
   }
-  if (listable && slot >= 0) bits[48 + slot] = obj_entry(x, y, type, colour, state);
+  if (listable && slot >= 0) bits[OBJ_WORD0 + slot] = obj_entry(x, y, type, colour, state);
 }
 __device__ __forceinline__ void bits_update_cell(uint32_t* bits, int x, int y, int type, int colour, int state) {
   if (bits == nullptr) return;
-  const uint32_t op = cell_opaque(type, state) ? 1u : 0u, ne = type != MG_T_EMPTY ? 1u : 0u, cn = cell_canon(type, colour, state) ? 1u : 0u;
-  bits[x] = (bits[x] & ~((1u << y) | (1u << (16 + y)))) | (op << y) | (ne << (16 + y));
-  bits[16 + y] = (bits[16 + y] & ~((1u << x) | (1u << (16 + x)))) | (op << x) | (ne << (16 + x));
-  bits[32 + x] = (bits[32 + x] & ~(1u << y)) | (cn << y);
-  bits[32 + y] = (bits[32 + y] & ~(1u << (16 + x))) | (cn << (16 + x));
+  const uint32_t op = cell_opaque(type, state) ? 1u : 0u, ot = (type != MG_T_EMPTY && !cell_canon(type, colour, state)) ? 1u : 0u;
+  bits[LINE_X0 + x] = (bits[LINE_X0 + x] & ~(0x10001u << y)) | (op << y) | (ot << (16 + y));
+  bits[LINE_Y0 + y] = (bits[LINE_Y0 + y] & ~(0x10001u << x)) | (op << x) | (ot << (16 + x));
   obj_update(bits, x, y, type, colour, state);
 }
 // rebuild all words from the byte planes
@@ -101,8 +104,9 @@ __device__ inline void bits_rebuild(const uint8_t* tp, uint32_t* bits, int W, in
 // (type | colour<<8 | state<<16) of the static object at (x, y): bit-planes, then the object list, then -- for
 // objects that did not fit the list -- the byte planes
 __device__ __forceinline__ uint32_t cell_triple(const uint32_t* bits, int x, int y, const uint8_t* tp, int H, int S) {
-  if (!((bits[x] >> (16 + y)) & 1u)) return 0u;
-  if ((bits[32 + x] >> y) & 1u) return (uint32_t)MG_T_WALL | ((uint32_t)MG_C_WORST << 8);
+  const uint32_t c = (bits[LINE_X0 + x] >> y) & 0x10001u;
+  if (c == 0u) return 0u;
+  if (c == 1u) return (uint32_t)MG_T_WALL | ((uint32_t)MG_C_WORST << 8);  // opaque and not "other": canonical wall
   const uint32_t e = obj_lookup(bits, x, y);
   if (e) return ((e >> 8) & 0xFu) | (((e >> 12) & 0xFu) << 8) | (((e >> 16) & 0xFFu) << 16);
   const int idx = x * H + y;

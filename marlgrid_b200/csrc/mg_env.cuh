@@ -128,7 +128,7 @@ __device__ void env_reset(EnvCtx<RS>& c, unsigned long long g) {
       wallc[i * RS] = (i == 0 || i == H - 1) ? fullc : (i < H ? endsc : 0u);
       other[i * RS] = 0u; otherc[i * RS] = 0u;
     }
-    for (int k = 0; k < OBJ_SLOTS; ++k) c.bits[48 + k] = 0u;
+    for (int k = 0; k < OBJ_SLOTS; ++k) c.bits[OBJ_WORD0 + k] = 0u;
   }
   for (int i = 0; i < W; ++i) {  // wall_rect base.py:172-176
     c.tp[i * H] = MG_T_WALL; c.tp[S + i * H] = MG_C_WORST;
@@ -146,7 +146,7 @@ __device__ void env_reset(EnvCtx<RS>& c, unsigned long long g) {
       if (type == MG_T_WALL) { wall[x * RS] |= 1u << y; wallc[y * RS] |= 1u << x; }
       else {
         other[x * RS] |= 1u << y; otherc[y * RS] |= 1u << x;
-        if (n_listed < OBJ_SLOTS) c.bits[48 + n_listed++] = obj_entry(x, y, type, colour, state);  // Goal / BonusTiles
+        if (n_listed < OBJ_SLOTS) c.bits[OBJ_WORD0 + n_listed++] = obj_entry(x, y, type, colour, state);  // Goal / BonusTiles
       }
     }
   };
@@ -189,14 +189,14 @@ __device__ void env_reset(EnvCtx<RS>& c, unsigned long long g) {
   }
   c.sc = 0;
   c.ep += 1;
-  if (BITS) {  // the masks ARE the bit-plane words
+  if (BITS) {  // the masks ARE the bit-plane lines (OP = walls, OT = Goal / BonusTiles)
     uint32_t* bits = c.bits;
     for (int i = 0; i < 16; ++i) {
-      const uint32_t wl = wall[i * RS], ot = other[i * RS], wc = wallc[i * RS], oc = otherc[i * RS];
-      bits[i] = wl | ((wl | ot) << 16);
-      bits[16 + i] = wc | ((wc | oc) << 16);
-      bits[32 + i] = wl | (wc << 16);
+      bits[LINE_X0 + i] = wall[i * RS] | (other[i * RS] << 16);
+      bits[LINE_Y0 + i] = wallc[i * RS] | (otherc[i * RS] << 16);
     }
+    bits[0] = 0u; bits[17] = 0u; bits[18] = 0u; bits[35] = 0u;
+    for (int i = OBJ_WORD0 + OBJ_SLOTS; i < BITS_WORDS; ++i) bits[i] = 0u;
   }
 }
 

@@ -53,7 +53,7 @@ class BatchedMultiGridEnv:
         self.grid = torch.empty((B, 3, S), dtype=torch.uint8, device=dev)
         self.agents = torch.empty((B, A, 16), dtype=torch.uint8, device=dev)
         self.envrec = torch.empty((B, 4), dtype=torch.int32, device=dev)
-        self.cellbits = torch.empty((B, 52), dtype=torch.int32, device=dev)  # derived bit-planes (include/marlgrid_b200.h)
+        self.cellbits = torch.empty((B, 44), dtype=torch.int32, device=dev)  # derived bit-planes (include/marlgrid_b200.h)
         self.rewards = torch.zeros((B, A), dtype=torch.float64, device=dev)
         self.done = torch.zeros((B,), dtype=torch.bool, device=dev)  # the kernels write 0/1 bytes: no conversion pass per step
         if obs_mode == "encoded":

@@ -27,7 +27,19 @@ fi
 if [[ "$what" == *ncu* ]]; then
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
       python bench.py --steps 100 --warmup 10 --no-cpu-baseline --e2e-steps 3 > gpurun_out/ncu_bench.log 2>&1
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:fused_kernel -s 40 -c 2 -f -o gpurun_out/prof \
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:fused2?_kernel -s 40 -c 2 -f -o gpurun_out/prof \
       python bench.py --steps 20 --warmup 10 --no-cpu-baseline --e2e-steps 3 > gpurun_out/ncu_full.log 2>&1
   ls -la gpurun_out/
+fi
+if [[ "$what" == *exp* ]]; then
+  # quick A/B of launch-shape knobs of the specialised fused kernel (cold per-step timing, no CPU baseline)
+  for st in 2 1; do for c in 9 8 7 6 5 4; do
+    echo "== MG_F2_STAGES=$st MG_F2_CTAS_PER_SM=$c"
+    MG_F2_STAGES=$st MG_F2_CTAS_PER_SM=$c timeout 300 python bench.py --steps 300 --warmup 50 --no-cpu-baseline --e2e-steps 3 2>&1 | python -c "
+import sys, json
+for l in sys.stdin:
+    if l.startswith('{'):
+        d = json.loads(l); print('value %.3e  avg %.2f us  med %.2f us  min %.2f us  warm %.2f us' % (d['value'], 1e3*d['ms_per_step'], 1e3*d['step_ms']['median'], 1e3*d['step_ms']['min'], 1e3*d['warm']['ms_per_step']))
+"
+  done; done 2>&1 | tee gpurun_out/exp.log
 fi
