@@ -189,6 +189,12 @@ int mg_step_fused_rgb(const MgConfig* cfg, const MgState* st, const int32_t* act
 int mg_rollout_fused(const MgConfig* cfg, const MgState* st, const int32_t* actions, int64_t n_steps,
                      double* rewards, uint8_t* done, uint8_t* obs, int autoreset, mg_stream_t stream);
 
+/* The same driver over n_states independent env families of equal size, visited round robin: step t advances family
+ * t % n_states with actions[t] and writes that family's rewards[r] / done[r] / obs[r].  With enough families the working
+ * set exceeds the L2 cache, which is how bench.py times cold steps back to back (no flush kernel in between). */
+int mg_rollout_fused_rr(const MgConfig* cfg, const MgState* states, int n_states, const int32_t* actions, int64_t n_steps,
+                        double* const* rewards, uint8_t* const* done, uint8_t* const* obs, int autoreset, mg_stream_t stream);
+
 /* Uniform random actions in {0..n_actions-1}, Philox stream keyed (seed, call counter):
  * the synthetic policy of the benchmark. */
 int mg_random_actions(int32_t* actions, int64_t n, int n_actions, uint64_t seed, uint64_t counter,

@@ -175,6 +175,25 @@ int mg_rollout_fused(const MgConfig* cfg, const MgState* st, const int32_t* acti
   return 0;
 }
 
+int mg_rollout_fused_rr(const MgConfig* cfg, const MgState* states, int n_states, const int32_t* actions, int64_t n_steps,
+                         double* const* rewards, uint8_t* const* done, uint8_t* const* obs, int autoreset, mg_stream_t stream) {
+  if (!states || n_states < 1 || !actions || !rewards || !done || !obs) return MG_E_ARG;
+  for (int r = 0; r < n_states; ++r) {
+    int e = check_state(cfg, &states[r]);
+    if (e) return e;
+    if (!rewards[r] || !done[r] || !obs[r] || !aligned16(obs[r]) || states[r].n_envs != states[0].n_envs) return MG_E_ARG;
+  }
+  const int64_t per_step = states[0].n_envs * cfg->n_agents;
+  for (int64_t t = 0; t < n_steps; ++t) {
+    const int r = (int)(t % n_states);
+    KP p = make_kp(cfg, &states[r]);
+    p.actions = actions + t * per_step; p.rewards = rewards[r]; p.done = done[r]; p.obs = obs[r]; p.autoreset = autoreset;
+    int e = launch_step_obs(p, 1, (cudaStream_t)stream);
+    if (e) return e;
+  }
+  return 0;
+}
+
 int mg_random_actions(int32_t* actions, int64_t n, int n_actions, uint64_t seed, uint64_t counter, mg_stream_t stream) {
   if (!actions || n < 0 || n_actions < 1) return MG_E_ARG;
   if (n == 0) return 0;

@@ -105,7 +105,9 @@ __device__ __forceinline__ Draws make_draws(const KP& p, unsigned long long g, u
 // others) and never reads a plane; the bit-plane words are those masks.
 // The placement list (goal?, bonus tiles, clutter walls, agents) is walked by ONE loop over the try index k, so
 // that all lanes of a warp draw their Philox block on the same iteration (two tries per block).
-template <int RS, bool BITS>
+// PLANES = false (needs BITS): the byte planes are NOT written here; the caller rebuilds them from the bit-plane lines and
+// the object list (mg_fused2.cu stages the image in shared memory and stores it with one bulk copy per group of envs).
+template <int RS, bool BITS, bool PLANES = true>
 __device__ void env_reset(EnvCtx<RS>& c, unsigned long long g) {
   const KP& p = c.p;
   const int W = p.W, H = p.H, S = p.S, A = p.A;
@@ -114,8 +116,10 @@ __device__ void env_reset(EnvCtx<RS>& c, unsigned long long g) {
     c.R(a, 1) = 0xFF000000u;
     c.R(a, 2) = 0;
   }
-  int4* z = reinterpret_cast<int4*>(c.tp);
-  for (int i = 0; i < 3 * S / 16; ++i) z[i] = make_int4(0, 0, 0, 0);
+  if (PLANES) {
+    int4* z = reinterpret_cast<int4*>(c.tp);
+    for (int i = 0; i < 3 * S / 16; ++i) z[i] = make_int4(0, 0, 0, 0);
+  }
   c.w3 &= 0xFFFF0000u;
   uint32_t* wall = c.scratch;                // wall[x*RS]: bit y = canonical wall at (x, y)
   uint32_t* other = c.scratch + 16 * RS;     // other[x*RS]: bit y = Goal / BonusTile (both can_overlap)
@@ -130,18 +134,22 @@ __device__ void env_reset(EnvCtx<RS>& c, unsigned long long g) {
     }
     for (int k = 0; k < OBJ_SLOTS; ++k) c.bits[OBJ_WORD0 + k] = 0u;
   }
-  for (int i = 0; i < W; ++i) {  // wall_rect base.py:172-176
-    c.tp[i * H] = MG_T_WALL; c.tp[S + i * H] = MG_C_WORST;
-    c.tp[i * H + H - 1] = MG_T_WALL; c.tp[S + i * H + H - 1] = MG_C_WORST;
-  }
-  for (int j = 0; j < H; ++j) {
-    c.tp[j] = MG_T_WALL; c.tp[S + j] = MG_C_WORST;
-    c.tp[(W - 1) * H + j] = MG_T_WALL; c.tp[S + (W - 1) * H + j] = MG_C_WORST;
+  if (PLANES) {
+    for (int i = 0; i < W; ++i) {  // wall_rect base.py:172-176
+      c.tp[i * H] = MG_T_WALL; c.tp[S + i * H] = MG_C_WORST;
+      c.tp[i * H + H - 1] = MG_T_WALL; c.tp[S + i * H + H - 1] = MG_C_WORST;
+    }
+    for (int j = 0; j < H; ++j) {
+      c.tp[j] = MG_T_WALL; c.tp[S + j] = MG_C_WORST;
+      c.tp[(W - 1) * H + j] = MG_T_WALL; c.tp[S + (W - 1) * H + j] = MG_C_WORST;
+    }
   }
   int n_listed = 0;
   auto put_static = [&](int x, int y, int type, int colour, int state) {
-    const int idx = x * H + y;
-    c.tp[idx] = (uint8_t)type; c.tp[S + idx] = (uint8_t)colour; c.tp[2 * S + idx] = (uint8_t)state;
+    if (PLANES) {
+      const int idx = x * H + y;
+      c.tp[idx] = (uint8_t)type; c.tp[S + idx] = (uint8_t)colour; c.tp[2 * S + idx] = (uint8_t)state;
+    }
     if (BITS) {
       if (type == MG_T_WALL) { wall[x * RS] |= 1u << y; wallc[y * RS] |= 1u << x; }
       else {

@@ -24,7 +24,7 @@ namespace mg {
 
 namespace f2 {
 
-constexpr uint32_t FL_SLOW = 1u, FL_RESET = 2u, FL_BITS_DIRTY = 4u, FL_NOTDONE = 8u;  // s_flag bits; bits 8..15 movers, 16..31 error bits
+constexpr uint32_t FL_SLOW = 1u, FL_RESET = 2u, FL_BITS_DIRTY = 4u, FL_NOTDONE = 8u, FL_IMAGE = 16u;  // s_flag bits; bits 8..15 movers, 16..31 error bits
 
 // the general sequential code, kept out of line so the common path keeps its registers
 __device__ __noinline__ void seq_step(EnvCtx<32>& cref, unsigned long long g, const int32_t* act, double* rew) {
@@ -32,9 +32,10 @@ __device__ __noinline__ void seq_step(EnvCtx<32>& cref, unsigned long long g, co
   env_step<32, true, MG_MAX_AGENTS>(c, g, act, rew);
   cref.sc = c.sc; cref.ep = c.ep; cref.tl = c.tl; cref.w3 = c.w3; cref.dirty = c.dirty;
 }
+template <bool PLANES>
 __device__ __noinline__ void seq_reset(EnvCtx<32>& cref, unsigned long long g) {
   EnvCtx<32> c = cref;
-  env_reset<32, true>(c, g);
+  env_reset<32, true, PLANES>(c, g);
   cref.sc = c.sc; cref.ep = c.ep; cref.tl = c.tl; cref.w3 = c.w3; cref.dirty = c.dirty;
 }
 
@@ -148,6 +149,9 @@ __global__ void __maxnreg__((max_regs<V, A, NST>())) fused2_kernel(const __grid_
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, a = tid >> 5;  // lane = env within the tile, warp = agent
   const int W = p.W, H = p.H, S = p.S;
+  // fresh worlds hold canonical walls plus (goal + bonus tiles) listed objects: if those always fit the object list, reset
+  // leaves the byte planes to the cooperative image below
+  const bool image_planes = (p.goal_mode != MG_GOAL_NONE ? 1 : 0) + p.n_bonus <= OBJ_SLOTS && 3 * S <= SM::OUT_AREA;
 
   double* s_rew = reinterpret_cast<double*>(smem + SM::REW);       // [env][a]
   uint8_t* s_done = smem + SM::DONE;                               // [env]
@@ -358,7 +362,9 @@ __global__ void __maxnreg__((max_regs<V, A, NST>())) fused2_kernel(const __grid_
     }
   } else if (mine && a == 0) rare = true;
   if (__syncthreads_or(rare ? 1 : 0)) {
-    if (a == 0 && mine) {  // lane == env on warp 0: the sequential code of mg_env.cuh, scratch in the (not yet used) output tile
+    // lane == env in every warp: the envs are dealt out over the CTA's warps (env e goes to warp e % A), so that A warps
+    // instead of one chew through the sequential code of mg_env.cuh; scratch lives in the (not yet used) output tile
+    if (a == lane % A && mine) {
       uint32_t fl = s_flag[lane];
       if (fl & (FL_SLOW | FL_RESET)) {
         EnvCtx<32> c{p, s_trec + lane, tp, bits, s_scr + lane, 0, 0, 0, 0u, false};
@@ -377,13 +383,65 @@ __global__ void __maxnreg__((max_regs<V, A, NST>())) fused2_kernel(const __grid_
           if (full) s_done[lane] = dn ? 1 : 0; else p.done[env] = dn ? 1 : 0;
           fl = FL_SLOW | (c.dirty ? FL_BITS_DIRTY : 0u) | ((dn && p.autoreset) ? (FL_BITS_DIRTY | FL_RESET) : 0u);
         }
-        if (fl & FL_RESET) seq_reset(c, g);  // MultiGridEnv.reset (base.py:402-416)
+        if (fl & FL_RESET) {  // MultiGridEnv.reset (base.py:402-416)
+          // an env whose replayed step edited the planes with plain stores keeps plain stores (no cross-proxy ordering games)
+          if (image_planes && !(fl & FL_SLOW)) { seq_reset<false>(c, g); fl |= FL_IMAGE; } else seq_reset<true>(c, g);
+        }
         for (int q = 0; q < A; ++q) { rec[q * 4] = c.R(q, 0); rec[q * 4 + 1] = c.R(q, 1); rec[q * 4 + 2] = c.R(q, 2); rec[q * 4 + 3] = 0u; }
         s_env[lane * 4] = c.sc; s_env[lane * 4 + 1] = c.ep; s_env[lane * 4 + 2] = c.tl; s_env[lane * 4 + 3] = (int)c.w3;
         s_flag[lane] = fl;
       }
     }
     __syncthreads();
+    if (image_planes) {
+      // The byte planes of the regenerated envs, rebuilt from their bit-plane lines (walls) and object lists (Goal,
+      // BonusTiles) in the -- still unused -- output area, group by group, and stored with bulk copies: a fresh world is
+      // 3*S bytes of mostly zeros, which single lanes writing to global memory would turn into hundreds of scattered stores.
+      const int plane_bytes = 3 * S;
+      const int G = min(ENVS_PER_CTA, SM::OUT_AREA / plane_bytes);
+      const uint32_t image_mask = __ballot_sync(0xFFFFFFFFu, mine && (s_flag[lane] & FL_IMAGE));  // lane == env: the same word in every warp
+      for (int g0 = 0; g0 < n_valid; g0 += G) {
+        const int gn = min(G, n_valid - g0);
+        const uint32_t group_mask = (image_mask >> g0) & (gn == 32 ? 0xFFFFFFFFu : ((1u << gn) - 1u));  // envs of the group that were reset
+        if (group_mask == 0u) continue;
+        {
+          int4* z = reinterpret_cast<int4*>(s_out);
+          for (int i = tid; i < gn * plane_bytes / 16; i += 32 * A) z[i] = make_int4(0, 0, 0, 0);
+        }
+        __syncthreads();
+        for (int i = tid; i < gn * 16; i += 32 * A) {  // one (env, x-line) pair per iteration
+          const int e = i >> 4, x = i & 15;
+          if (x >= W || !((group_mask >> e) & 1u)) continue;
+          const uint32_t* eb = s_bits + (g0 + e) * BITS_WORDS;
+          const uint32_t w = eb[LINE_X0 + x];
+          uint8_t* img = s_out + e * plane_bytes + x * H;
+          uint32_t walls = w & 0xFFFFu & ~(w >> 16), others = w >> 16;
+          while (walls) {
+            const int y = __ffs(walls) - 1;
+            walls &= walls - 1u;
+            img[y] = MG_T_WALL; img[S + y] = MG_C_WORST;
+          }
+          while (others) {
+            const int y = __ffs(others) - 1;
+            others &= others - 1u;
+            const uint32_t oe = obj_lookup(eb, x, y);  // always listed: image_planes requires goal + bonus tiles <= OBJ_SLOTS
+            img[y] = (uint8_t)((oe >> 8) & 15u); img[S + y] = (uint8_t)((oe >> 12) & 15u); img[2 * S + y] = (uint8_t)((oe >> 16) & 255u);
+          }
+        }
+        __syncthreads();
+        if (a == 0) {
+          const bool all = group_mask == (gn == 32 ? 0xFFFFFFFFu : ((1u << gn) - 1u));
+          if (all ? lane == 0 : (lane < gn && ((group_mask >> lane) & 1u))) {
+            fence_proxy_async_smem();
+            if (all) bulk_s2g(p.grid + (env0 + g0) * plane_bytes, s_out, (uint32_t)(gn * plane_bytes));
+            else bulk_s2g(p.grid + (env0 + g0 + lane) * plane_bytes, s_out + lane * plane_bytes, (uint32_t)plane_bytes);
+            bulk_commit();
+            bulk_wait_read0();
+          }
+        }
+        __syncthreads();
+      }
+    }
     zero_out();  // the sequential path borrowed the output area: clean it again
     __syncthreads();
   }

@@ -43,3 +43,9 @@ for l in sys.stdin:
 "
   done; done 2>&1 | tee gpurun_out/exp.log
 fi
+if [[ "$what" == *ncureset* ]]; then
+  # the step on which every episode ends (step_count hits max_steps = 100): launch 100 of the single-family warm-up
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:fused2?_kernel -s 99 -c 1 -f -o gpurun_out/prof_reset \
+      python bench.py --steps 6 --warmup 120 --replicas 1 --no-cpu-baseline --e2e-steps 3 > gpurun_out/ncu_reset.log 2>&1
+  ls -la gpurun_out/
+fi
