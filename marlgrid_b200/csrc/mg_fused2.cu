@@ -134,14 +134,8 @@ constexpr int ctas_per_sm() {  // shared-memory / thread limited residency the r
 
 // Persistent CTAs: CTA c handles tiles c, c + gridDim.x, ...; while a tile is being processed the next tile's inputs are
 // already on their way into the other input stage (NST = 2), and the previous tile's outputs drain in the background.
-template <int V, int A, int NST>
-constexpr int max_regs() {  // the most registers per thread that still allow ctas_per_sm() resident CTAs
-  constexpr int r = (65536 / (ctas_per_sm<V, A, NST>() * 32 * A)) / 8 * 8;
-  return r > 128 ? 128 : r;
-}
-
 template <int V, int A, bool VO0, int NST>
-__global__ void __maxnreg__((max_regs<V, A, NST>())) fused2_kernel(const __grid_constant__ KP p, const int n_tiles) {
+__global__ void __launch_bounds__(32 * A, ctas_per_sm<V, A, NST>()) fused2_kernel(const __grid_constant__ KP p, const int n_tiles) {
   using namespace f2;
   using SM = Smem<V, A, NST>;
   constexpr int VV3 = V * V * 3;
@@ -631,6 +625,8 @@ static int launch_one(const KP& p, cudaStream_t s) {
   if (!resident[dev & 63]) {
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL);
     if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);  // the kernel lives on shared memory, not on L1
+    if (e != cudaSuccess) return (int)e;
     int n = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, 32 * A, SM::TOTAL);
     if (e != cudaSuccess) return (int)e;
@@ -640,7 +636,11 @@ static int launch_one(const KP& p, cudaStream_t s) {
   const long long tiles = (p.B + ENVS_PER_CTA - 1) / ENVS_PER_CTA;
   if (tiles <= 0) return 0;
   if (tiles > 0x7FFFFFFF) return MG_E_ARG;
-  const long long grid = std::min<long long>(tiles, (long long)resident[dev & 63] * sm_count(dev));
+  // as many CTAs as stay resident, trimmed so that every CTA gets the same number of tiles (no ragged last round)
+  const long long slots = (long long)resident[dev & 63] * sm_count(dev);
+  const long long rounds = (tiles + slots - 1) / slots;
+  const long long grid = getenv("MG_F2_RAGGED") ? std::min(tiles, slots) : (tiles + rounds - 1) / rounds;
+  if (getenv("MG_F2_VERBOSE")) fprintf(stderr, "fused2<V=%d,A=%d,NST=%d>: %d CTAs/SM x %d SMs, %lld tiles in %lld rounds -> grid %lld, %d B shared\n", V, A, NST, resident[dev & 63], sm_count(dev), tiles, rounds, grid, SM::TOTAL);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(32 * A); cfg.dynamicSmemBytes = SM::TOTAL; cfg.stream = s;
   cudaLaunchAttribute attr[1];

@@ -32,16 +32,17 @@ if [[ "$what" == *ncu* ]]; then
   ls -la gpurun_out/
 fi
 if [[ "$what" == *exp* ]]; then
-  # quick A/B of launch-shape knobs of the specialised fused kernel (cold per-step timing, no CPU baseline)
-  for st in 2 1; do for c in 9 8 7 6 5 4; do
-    echo "== MG_F2_STAGES=$st MG_F2_CTAS_PER_SM=$c"
-    MG_F2_STAGES=$st MG_F2_CTAS_PER_SM=$c timeout 300 python bench.py --steps 300 --warmup 50 --no-cpu-baseline --e2e-steps 3 2>&1 | python -c "
+  # quick A/B of launch-shape knobs of the specialised fused kernel (no CPU baseline)
+  for knobs in ${EXP_KNOBS:-"MG_F2_CTAS_PER_SM=7" "MG_F2_CTAS_PER_SM=6" "MG_F2_RAGGED=1" "MG_F2_PDL=0"}; do
+    echo "== $knobs"
+    env $knobs MG_F2_VERBOSE=1 timeout 300 python bench.py --steps 600 --warmup 60 --no-cpu-baseline --e2e-steps 3 2>gpurun_out/exp.err | python -c "
 import sys, json
 for l in sys.stdin:
     if l.startswith('{'):
-        d = json.loads(l); print('value %.3e  avg %.2f us  med %.2f us  min %.2f us  warm %.2f us' % (d['value'], 1e3*d['ms_per_step'], 1e3*d['step_ms']['median'], 1e3*d['step_ms']['min'], 1e3*d['warm']['ms_per_step']))
+        d = json.loads(l); print('value %.3e  cold-rr %.2f us  flushed med %.2f us  warm %.2f us' % (d['value'], 1e3*d['ms_per_step'], 1e3*d['step_ms_flushed']['median'], 1e3*d['warm']['ms_per_step']))
 "
-  done; done 2>&1 | tee gpurun_out/exp.log
+    sort -u gpurun_out/exp.err | head -3
+  done 2>&1 | tee gpurun_out/exp.log
 fi
 if [[ "$what" == *ncureset* ]]; then
   # the step on which every episode ends (step_count hits max_steps = 100): launch 100 of the single-family warm-up
