@@ -410,7 +410,7 @@ def main():
                     "steps": KE, "api": "mg_engine_step (C ABI, pinned host buffers, synchronous)", "checksum": e2e_checksum},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "kernel": "fused_kernel<OBS=1,V=7> (env.step + auto-reset + egocentric encode: the only launch of a step)",
+                         "kernel": "fused2_kernel<V=7,A=3> (env.step + auto-reset + egocentric encode: the only launch of a step)",
                          "algorithmic_bytes_per_launch": ALGO_BYTES_PER_ENV_STEP * B, "avg_launch_ms": avg_step_s * 1e3,
                          "peak_source": peak_src,
                          "note": "algorithmic bytes = SURVEY.md 8(d) 1272 B/env-step x 65536; K launches back to back over env families larger than L2, one CUDA event pair",
