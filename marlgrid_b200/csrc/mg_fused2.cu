@@ -41,10 +41,14 @@ __device__ __noinline__ void seq_reset(EnvCtx<32>& cref, unsigned long long g) {
 
 // shared memory of one persistent CTA: NST input stages (what the bulk loads fill and the state stores drain), one output
 // tile, the small per-tile exchange arrays.  Offsets in bytes, every block a multiple of 16.
-template <int V, int A, int NST>
+template <int OBS, int V, int A, int NST>
 struct Smem {
   static constexpr int E = ENVS_PER_CTA;
-  static constexpr int OUT_BYTES = E * A * V * V * 3;
+  // OBS 1: the encoded observation tile.  OBS 2: per-view tile-id maps (V rows of 8 bytes) + per warp two image chunks
+  // (one row of V cells = 8 pixel rows of V*24 bytes) that bulk copies drain while the next chunk is being built.
+  static constexpr int MAP_BYTES = E * A * V * 8;
+  static constexpr int CHUNK = V * 8 * 24;
+  static constexpr int OUT_BYTES = OBS == 1 ? E * A * V * V * 3 : MAP_BYTES + A * 2 * CHUNK;
   static constexpr int SCRATCH_BYTES = (A * 4 * 32 + 64 * 32) * 4;  // sequential path: transposed records + reset masks
   static constexpr int OUT_AREA = ((OUT_BYTES > SCRATCH_BYTES ? OUT_BYTES : SCRATCH_BYTES) + 15) / 16 * 16;
   // one input stage
@@ -60,7 +64,7 @@ struct Smem {
   static constexpr int ORDER = FLAG + 2 * E * 4;
   static constexpr int BAR = ORDER + E * 4;      // NST mbarriers
   static constexpr int OUT = BAR + ((NST * 8 + 15) / 16) * 16;
-  static constexpr int TOTAL = OUT + OUT_AREA;
+  static constexpr int TOTAL = OUT + OUT_AREA;   // OBS 2: the tile atlas (run-time size) follows
 };
 
 // Lehmer / Fisher-Yates decode of the permutation number (oracle/philox.py shuffle_perm): nibble q of the result = agent
@@ -125,19 +129,19 @@ __device__ __forceinline__ void sts_u8(uint32_t saddr, uint32_t v) {
 
 }  // namespace f2
 
-template <int V, int A, int NST>
+template <int OBS, int V, int A, int NST>
 constexpr int ctas_per_sm() {  // shared-memory / thread limited residency the register allocation should allow
-  constexpr int by_smem = (227 * 1024) / (f2::Smem<V, A, NST>::TOTAL + 1024), by_threads = 64 / A;
+  constexpr int by_smem = (227 * 1024) / (f2::Smem<OBS, V, A, NST>::TOTAL + (OBS == 2 ? 11 * 1024 : 0) + 1024), by_threads = 64 / A;
   constexpr int n = by_smem < by_threads ? by_smem : by_threads;
   return n > 32 ? 32 : n;
 }
 
 // Persistent CTAs: CTA c handles tiles c, c + gridDim.x, ...; while a tile is being processed the next tile's inputs are
 // already on their way into the other input stage (NST = 2), and the previous tile's outputs drain in the background.
-template <int V, int A, bool VO0, int NST>
-__global__ void __launch_bounds__(32 * A, ctas_per_sm<V, A, NST>()) fused2_kernel(const __grid_constant__ KP p, const int n_tiles) {
+template <int OBS, int V, int A, bool VO0, int NST>
+__global__ void __launch_bounds__(32 * A, ctas_per_sm<OBS, V, A, NST>()) fused2_kernel(const __grid_constant__ KP p, const int n_tiles) {
   using namespace f2;
-  using SM = Smem<V, A, NST>;
+  using SM = Smem<OBS, V, A, NST>;
   constexpr int VV3 = V * V * 3;
   constexpr uint32_t RM = (1u << V) - 1u;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -157,7 +161,8 @@ __global__ void __launch_bounds__(32 * A, ctas_per_sm<V, A, NST>()) fused2_kerne
   uint8_t* const out = s_out + (lane * A + a) * VV3;
   const uint32_t out_s = smem_u32(out);
 
-  auto zero_out = [&]() {  // invisible / empty cells encode as 0
+  auto zero_out = [&]() {  // invisible / empty cells encode as 0 (the RGB path writes every byte of its tile maps)
+    if (OBS != 1) return;
     int4* z = reinterpret_cast<int4*>(s_out);
     constexpr int N16 = SM::OUT_BYTES / 16, ITERS = (N16 + 32 * A - 1) / (32 * A);
 #pragma unroll
@@ -193,6 +198,15 @@ __global__ void __launch_bounds__(32 * A, ctas_per_sm<V, A, NST>()) fused2_kerne
   }
   if (a == 0) { reinterpret_cast<uint32_t*>(smem + SM::FLAG)[lane] = 0u; reinterpret_cast<uint32_t*>(smem + SM::FLAG)[32 + lane] = 0u; }
   __syncthreads();
+  uint8_t* const s_atlas = smem + SM::TOTAL;  // OBS 2: tiles [n_tiles] + the shadow tile, 192 bytes each (tile size 8)
+  if (OBS == 2) {  // the atlas is constant data: copy it while the previous kernel may still be running
+    const int4* src = reinterpret_cast<const int4*>(p.atlas);
+    int4* dst = reinterpret_cast<int4*>(s_atlas);
+    for (int i = tid; i < p.n_tiles * 12; i += 32 * A) dst[i] = __ldg(src + (i / 12) * 48 + (i % 12));  // global: [tile][4 orientations][192]; slot 0 only
+    // COLORS['shadow'] = (35, 25, 30) (objects.py:25, base.py:305): the byte pattern repeats every three words
+    for (int i = tid; i < 48; i += 32 * A)
+      reinterpret_cast<uint32_t*>(s_atlas + p.n_tiles * 192)[i] = (i % 3 == 0) ? 0x231E1923u : (i % 3 == 1) ? 0x19231E19u : 0x1E19231Eu;
+  }
   // programmatic dependent launch: this grid may have been started while the previous kernel of the stream was still
   // draining (its launch latency and this prologue overlap that tail); nothing before this line touches global memory
   asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -200,6 +214,7 @@ __global__ void __launch_bounds__(32 * A, ctas_per_sm<V, A, NST>()) fused2_kerne
   if ((int)blockIdx.x < n_tiles) issue_load((int)blockIdx.x, 0);
 
   int it = 0;
+  int chunk_parity = 0;  // OBS 2: which of the warp's two chunk buffers is filled next
   for (int tile = (int)blockIdx.x; tile < n_tiles; tile += (int)gridDim.x, ++it) {
   const int stage = it % NST;
   unsigned char* const stg = smem + stage * SM::STAGE;
@@ -468,6 +483,12 @@ __global__ void __launch_bounds__(32 * A, ctas_per_sm<V, A, NST>()) fused2_kerne
 #pragma unroll
       for (int q = 0; q < A; ++q) rec[q * 4] = (q0[q] & ~(AF_HEAD << 24)) | (((heads >> q) & 1u) << 31);
     }
+    uint8_t* const tmap = s_out + (lane * A + a) * (V * 8);  // OBS 2: this view's tile ids, V rows of 8 bytes
+    if (OBS == 2 && !(me & ((uint32_t)MG_AF_ACTIVE << 24))) {  // inactive agent: every cell is shadow (base.py:305,420-425)
+      const uint32_t sh4 = (uint32_t)p.n_tiles * 0x01010101u;
+#pragma unroll
+      for (int b = 0; b < V; ++b) *reinterpret_cast<uint2*>(tmap + b * 8) = make_uint2(sh4, sh4);
+    }
     if (me & ((uint32_t)MG_AF_ACTIVE << 24)) {  // inactive agent: empty view, nothing visible (base.py:420-425)
       const int px = (int)(me & 0xFFu), py = (int)((me >> 8) & 0xFFu), dir = (int)((me >> 16) & 3u);
       constexpr int h = V / 2;
@@ -506,22 +527,37 @@ __global__ void __launch_bounds__(32 * A, ctas_per_sm<V, A, NST>()) fused2_kerne
       const uint64_t m64 = pack_rows8<V>(M), op64 = pack_rows8<V>(OP), ot64 = pack_rows8<V>(OT);
       const uint64_t wall64 = m64 & op64 & ~ot64, free64 = m64 & ~(op64 | ot64);
       uint64_t oth64 = m64 & ot64;
+      if (OBS == 1) {
       {  // visible canonical walls (8, 9, 0): constants at compile-time offsets of the staging tile.  The two constants
-         // come in through a kernel parameter and the stores are spelled out, or ptxas re-materialises 8 / 9 around every store
-        const uint32_t wlo = (uint32_t)wall64, whi = (uint32_t)(wall64 >> 32);
-        const uint32_t c8 = p.wall_enc & 0xFFu, c9 = p.wall_enc >> 8;  // (MG_T_WALL, MG_C_WORST) through a kernel parameter
+           // come in through a kernel parameter and the stores are spelled out, or ptxas re-materialises 8 / 9 around every store
+          const uint32_t wlo = (uint32_t)wall64, whi = (uint32_t)(wall64 >> 32);
+          const uint32_t c8 = p.wall_enc & 0xFFu, c9 = p.wall_enc >> 8;  // (MG_T_WALL, MG_C_WORST) through a kernel parameter
 #pragma unroll
-        for (int b = 0; b < V; ++b)
+          for (int b = 0; b < V; ++b)
 #pragma unroll
-          for (int va = 0; va < V; ++va) {
-            if ((b < 4 ? wlo : whi) & (1u << (8 * (b & 3) + va))) {
-              sts_u8(out_s + (va * (V * 3) + b * 3 + 0), c8);
-              sts_u8(out_s + (va * (V * 3) + b * 3 + 1), c9);
+            for (int va = 0; va < V; ++va) {
+              if ((b < 4 ? wlo : whi) & (1u << (8 * (b & 3) + va))) {
+                sts_u8(out_s + (va * (V * 3) + b * 3 + 0), c8);
+                sts_u8(out_s + (va * (V * 3) + b * 3 + 1), c9);
+              }
             }
-          }
+        }
+      }
+      if (OBS == 2) {
+        // tile ids (render_tile base.py:275-299): shadow where invisible, 0 for a visible empty cell, the Wall tile for a
+        // visible canonical wall -- per row, seven mask bits spread to seven bytes and scaled (no carries: one term per byte)
+        const uint32_t shadow = (uint32_t)p.n_tiles, wall_tile = (uint32_t)p.kind_of_type[MG_T_WALL] * (1u + 4u * A);
+#pragma unroll
+        for (int b = 0; b < V; ++b) {
+          const uint32_t vis = (uint32_t)(m64 >> (8 * b)) & 0xFFu, wl = (uint32_t)(wall64 >> (8 * b)) & 0xFFu;
+          const uint32_t v_lo = ((vis & 15u) * 0x00204081u) & 0x01010101u, v_hi = ((vis >> 4) * 0x00204081u) & 0x01010101u;
+          const uint32_t w_lo = ((wl & 15u) * 0x00204081u) & 0x01010101u, w_hi = ((wl >> 4) * 0x00204081u) & 0x01010101u;
+          *reinterpret_cast<uint2*>(tmap + b * 8) = make_uint2((0x01010101u - v_lo) * shadow + w_lo * wall_tile, (0x01010101u - v_hi) * shadow + w_hi * wall_tile);
+        }
       }
       // world cell -> view cell: vb = bu + su*cu, va = bv + sv*cv with (cu, cv) = (x, y) or (y, x)
       const int su = flip ? -1 : 1, bu = flip ? V - 1 + u0 : -u0, sv = rev ? -1 : 1, bv = rev ? V - 1 + v0 : -v0;
+      bool bad_render = false;  // OBS 2: an object whose render() raises in the reference (objects.py:274-277,309-321,370)
       if (oth64 != 0ull) {  // visible Goal / BonusTile / Key ...: the object list answers for (almost) all of them
 #pragma unroll
         for (int k = 0; k < OBJ_SLOTS; ++k) {
@@ -533,8 +569,13 @@ __global__ void __launch_bounds__(32 * A, ctas_per_sm<V, A, NST>()) fused2_kerne
           const uint64_t m = 1ull << (8 * vb + va);
           if (!(oth64 & m)) continue;
           oth64 &= ~m;
-          uint8_t* oo = out + va * (V * 3) + vb * 3;
-          oo[0] = (uint8_t)((e >> 8) & 15u); oo[1] = (uint8_t)((e >> 12) & 15u); oo[2] = (uint8_t)((e >> 16) & 255u);
+          if (OBS == 1) {
+            uint8_t* oo = out + va * (V * 3) + vb * 3;
+            oo[0] = (uint8_t)((e >> 8) & 15u); oo[1] = (uint8_t)((e >> 12) & 15u); oo[2] = (uint8_t)((e >> 16) & 255u);
+          } else {
+            const uint32_t kind = p.kind_of_type[(e >> 8) & 15u];
+            if (kind == 0xFFu) bad_render = true; else tmap[vb * 8 + va] = (uint8_t)(kind * (1u + 4u * A));
+          }
         }
         // objects that did not fit the list: WorldObj.encode (objects.py:90-99) from the byte planes
         while (oth64 != 0ull) {
@@ -544,8 +585,13 @@ __global__ void __launch_bounds__(32 * A, ctas_per_sm<V, A, NST>()) fused2_kerne
           const int uu = flip ? V - 1 - vb : vb, vv = rev ? V - 1 - va : va;
           const int wx = topX + (vertical ? vv : uu), wy = topY + (vertical ? uu : vv);
           const uint8_t* cp = p.grid + env * 3 * S + wx * H + wy;
-          uint8_t* oo = out + va * (V * 3) + vb * 3;
-          oo[0] = cp[0]; oo[1] = cp[S]; oo[2] = cp[2 * S];
+          if (OBS == 1) {
+            uint8_t* oo = out + va * (V * 3) + vb * 3;
+            oo[0] = cp[0]; oo[1] = cp[S]; oo[2] = cp[2 * S];
+          } else {
+            const uint32_t kind = p.kind_of_type[cp[0] & 15u];
+            if (kind == 0xFFu) bad_render = true; else tmap[vb * 8 + va] = (uint8_t)(kind * (1u + 4u * A));
+          }
         }
       }
       // agents that are their cell's object: (13, colour, dir) where no static object stands (base.py:204-214)
@@ -554,12 +600,24 @@ __global__ void __launch_bounds__(32 * A, ctas_per_sm<V, A, NST>()) fused2_kerne
       for (int q = 0; q < A; ++q) {
         const int vb = bu + su * (int)__byte_perm(q0[q], 0u, sel_u), va = bv + sv * (int)__byte_perm(q0[q], 0u, sel_v);
         const bool in_view = (unsigned)vb < (unsigned)V && (unsigned)va < (unsigned)V;
-        const bool draw = in_view && ((heads >> q) & 1u) && ((free64 >> ((8 * vb + va) & 63)) & 1ull);
-        if (draw) {
-          uint8_t* oo = out + va * (V * 3) + vb * 3;
-          oo[0] = MG_T_AGENT; oo[1] = p.agent_color[q]; oo[2] = (uint8_t)((q0[q] >> 16) & 3u);
+        if (OBS == 1) {
+          const bool draw = in_view && ((heads >> q) & 1u) && ((free64 >> ((8 * vb + va) & 63)) & 1ull);
+          if (draw) {
+            uint8_t* oo = out + va * (V * 3) + vb * 3;
+            oo[0] = MG_T_AGENT; oo[1] = p.agent_color[q]; oo[2] = (uint8_t)((q0[q] >> 16) & 3u);
+          }
+        } else {
+          // the cell's tile gets an agent on top: the observer itself if it stands there, else the queue head
+          // (base.py:282-293); tiles of size <= 10 are rotation-equivariant, so the view orientation is a dir remap
+          const bool draw = in_view && ((heads >> q) & 1u) && ((m64 >> ((8 * vb + va) & 63)) & 1ull);
+          if (draw) {
+            const bool own = ((q0[q] ^ me) & 0xFFFFu) == 0u;
+            const uint32_t qq = own ? (uint32_t)a : (uint32_t)q, qd = ((own ? me : q0[q]) >> 16) & 3u;
+            tmap[vb * 8 + va] = (uint8_t)(tmap[vb * 8 + va] + 1u + 4u * qq + ((qd + 3u - (uint32_t)dir) & 3u));
+          }
         }
       }
+      if (OBS == 2 && bad_render) atomicOr(reinterpret_cast<unsigned int*>(s_env) + lane * 4 + 3, (unsigned int)MG_ERR_RENDER << 16);
     }
   }
   __syncthreads();
@@ -568,16 +626,18 @@ __global__ void __launch_bounds__(32 * A, ctas_per_sm<V, A, NST>()) fused2_kerne
   if (full) {
     if (lane == 0) {  // again spread over the warps' first lanes
       fence_proxy_async_smem();
-      if (a == A - 1) bulk_s2g(p.obs + env0 * (A * VV3), s_out, (uint32_t)SM::OUT_BYTES);
+      if (OBS == 1 && a == A - 1) bulk_s2g(p.obs + env0 * (A * VV3), s_out, (uint32_t)SM::OUT_BYTES);
       if (a == 0) { bulk_s2g(p.agents + env0 * A * 16, s_rec, ENVS_PER_CTA * A * 16u); bulk_s2g(p.done + env0, s_done, ENVS_PER_CTA); }
       if (a == 1 % A) bulk_s2g(p.envrec + env0 * 4, s_env, ENVS_PER_CTA * 16u);
       if (a == 2 % A) bulk_s2g(p.rewards + env0 * A, s_rew, ENVS_PER_CTA * A * 8u);
       bulk_commit();
     }
   } else {  // ragged last tile: plain stores
-    const int total = n_valid * A * VV3;
-    uint8_t* dst = p.obs + env0 * (A * VV3);
-    for (int i = tid; i < total; i += 32 * A) dst[i] = s_out[i];
+    if (OBS == 1) {
+      const int total = n_valid * A * VV3;
+      uint8_t* dst = p.obs + env0 * (A * VV3);
+      for (int i = tid; i < total; i += 32 * A) dst[i] = s_out[i];
+    }
     if (tid == 0) {
       fence_proxy_async_smem();
       bulk_s2g(p.agents + env0 * A * 16, s_rec, (uint32_t)n_valid * (A * 16u));
@@ -589,6 +649,53 @@ __global__ void __launch_bounds__(32 * A, ctas_per_sm<V, A, NST>()) fused2_kerne
     fence_proxy_async_smem();
     bulk_s2g(p.cellbits + env * BITS_WORDS, bits, BITS_WORDS * 4u);
     bulk_commit();
+  }
+  if (OBS == 2) {
+    // ---- RGB: MultiGrid.render (base.py:301-331) of the tile's 32*A views from their tile-id maps.  Warp w expands views
+    // [32w, 32w+32), one row of V cells (8 pixel rows x V*24 bytes, contiguous in the image) at a time: every lane copies
+    // 8-byte pieces of tile rows from the atlas into the chunk buffer -- piece u of the chunk belongs to pixel row u / (3V),
+    // cell (u % 3V) / 3 --, then one bulk copy sends the chunk to HBM while the warp fills its other buffer.
+    constexpr int PIECES = V * 8 * 3, ITERS = (PIECES + 31) / 32;
+    uint32_t src_off[ITERS], cell_sel[ITERS];
+#pragma unroll
+    for (int i = 0; i < ITERS; ++i) {
+      const int u = lane + 32 * i, py = u / (3 * V), rem = u % (3 * V);
+      src_off[i] = (uint32_t)(py * 24 + (rem % 3) * 8);
+      cell_sel[i] = (uint32_t)(rem / 3);
+    }
+    const uint32_t atlas_s = smem_u32(s_atlas);
+    uint8_t* const bufs = s_out + SM::MAP_BYTES + a * (2 * SM::CHUNK);
+    const int n_views = n_valid * A;
+    constexpr long long VIEW_BYTES = (long long)V * V * 192;
+    for (int v = 0; v < 32; ++v) {
+      const int vi = a * 32 + v;
+      if (vi >= n_views) break;
+      uint8_t* const dstv = p.obs + (env0 * A + vi) * VIEW_BYTES;
+#pragma unroll 1
+      for (int b = 0; b < V; ++b) {
+        uint8_t* const buf = bufs + (chunk_parity ? SM::CHUNK : 0);
+        chunk_parity ^= 1;
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // the copy that last read this buffer is done
+        __syncwarp();
+        const uint2 ids = *reinterpret_cast<const uint2*>(s_out + vi * (V * 8) + b * 8);  // the row's V tile ids
+#pragma unroll
+        for (int i = 0; i < ITERS; ++i) {
+          const int u = lane + 32 * i;
+          if (ITERS * 32 == PIECES || u < PIECES) {
+            const uint32_t t = __byte_perm(ids.x, ids.y, cell_sel[i]) & 0xFFu;
+            uint2 px;
+            asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(px.x), "=r"(px.y) : "r"(atlas_s + t * 192u + src_off[i]));
+            *reinterpret_cast<uint2*>(buf + 8 * u) = px;
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          bulk_s2g(dstv + b * SM::CHUNK, buf, (uint32_t)SM::CHUNK);
+          bulk_commit();
+        }
+      }
+    }
   }
   }  // tile loop
   bulk_wait_read0();  // the CTA's shared memory must outlive the reads
@@ -615,23 +722,26 @@ static int stages() {  // input stages of the persistent CTAs: 2 = prefetch the 
   return n;
 }
 
-template <int V, int A, bool VO0, int NST>
+template <int OBS, int V, int A, bool VO0, int NST>
 static int launch_one(const KP& p, cudaStream_t s) {
-  using SM = f2::Smem<V, A, NST>;
-  auto k = fused2_kernel<V, A, VO0, NST>;
-  static int resident[64] = {0};  // CTAs per SM of this instantiation, per device
+  using SM = f2::Smem<OBS, V, A, NST>;
+  auto k = fused2_kernel<OBS, V, A, VO0, NST>;
+  const int smem_bytes = SM::TOTAL + (OBS == 2 ? (p.n_tiles + 1) * 192 : 0);  // OBS 2: + the tile atlas and the shadow tile
+  if (smem_bytes > 227 * 1024) return MG_E_UNSUPPORTED;
+  static int resident[64] = {0}, configured_smem[64] = {0};  // CTAs per SM of this instantiation, per device
   int dev = 0;
   cudaGetDevice(&dev);
-  if (!resident[dev & 63]) {
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL);
+  if (!resident[dev & 63] || configured_smem[dev & 63] != smem_bytes) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);  // the kernel lives on shared memory, not on L1
     if (e != cudaSuccess) return (int)e;
     int n = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, 32 * A, SM::TOTAL);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, 32 * A, smem_bytes);
     if (e != cudaSuccess) return (int)e;
     if (const char* o = getenv("MG_F2_CTAS_PER_SM")) n = std::min(n, std::max(1, atoi(o)));  // experiments
     resident[dev & 63] = std::max(n, 1);
+    configured_smem[dev & 63] = smem_bytes;
   }
   const long long tiles = (p.B + ENVS_PER_CTA - 1) / ENVS_PER_CTA;
   if (tiles <= 0) return 0;
@@ -640,9 +750,9 @@ static int launch_one(const KP& p, cudaStream_t s) {
   const long long slots = (long long)resident[dev & 63] * sm_count(dev);
   const long long rounds = (tiles + slots - 1) / slots;
   const long long grid = getenv("MG_F2_RAGGED") ? std::min(tiles, slots) : (tiles + rounds - 1) / rounds;
-  if (getenv("MG_F2_VERBOSE")) fprintf(stderr, "fused2<V=%d,A=%d,NST=%d>: %d CTAs/SM x %d SMs, %lld tiles in %lld rounds -> grid %lld, %d B shared\n", V, A, NST, resident[dev & 63], sm_count(dev), tiles, rounds, grid, SM::TOTAL);
+  if (getenv("MG_F2_VERBOSE")) fprintf(stderr, "fused2<OBS=%d,V=%d,A=%d,NST=%d>: %d CTAs/SM x %d SMs, %lld tiles in %lld rounds -> grid %lld, %d B shared\n", OBS, V, A, NST, resident[dev & 63], sm_count(dev), tiles, rounds, grid, smem_bytes);
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(32 * A); cfg.dynamicSmemBytes = SM::TOTAL; cfg.stream = s;
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(32 * A); cfg.dynamicSmemBytes = (size_t)smem_bytes; cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
@@ -652,25 +762,45 @@ static int launch_one(const KP& p, cudaStream_t s) {
   return (int)e;
 }
 
-template <int V, bool VO0>
+template <int OBS, int V, bool VO0>
 static int launch_a(const KP& p, cudaStream_t s) {
+  // encoded observations: two input stages (the next tile is prefetched); RGB: the image expansion dwarfs everything else,
+  // one stage leaves more shared memory for resident CTAs
+  constexpr int NS = OBS == 1 ? 2 : 1;
+  if (OBS == 1 && stages() == 1) {
+    switch (p.A) {
+      case 1: return launch_one<1, V, 1, VO0, 1>(p, s);
+      case 2: return launch_one<1, V, 2, VO0, 1>(p, s);
+      case 3: return launch_one<1, V, 3, VO0, 1>(p, s);
+      case 4: return launch_one<1, V, 4, VO0, 1>(p, s);
+    }
+    return MG_E_UNSUPPORTED;
+  }
   switch (p.A) {
-    case 1: return stages() == 2 ? launch_one<V, 1, VO0, 2>(p, s) : launch_one<V, 1, VO0, 1>(p, s);
-    case 2: return stages() == 2 ? launch_one<V, 2, VO0, 2>(p, s) : launch_one<V, 2, VO0, 1>(p, s);
-    case 3: return stages() == 2 ? launch_one<V, 3, VO0, 2>(p, s) : launch_one<V, 3, VO0, 1>(p, s);
-    case 4: return stages() == 2 ? launch_one<V, 4, VO0, 2>(p, s) : launch_one<V, 4, VO0, 1>(p, s);
+    case 1: return launch_one<OBS, V, 1, VO0, NS>(p, s);
+    case 2: return launch_one<OBS, V, 2, VO0, NS>(p, s);
+    case 3: return launch_one<OBS, V, 3, VO0, NS>(p, s);
+    case 4: return launch_one<OBS, V, 4, VO0, NS>(p, s);
   }
   return MG_E_UNSUPPORTED;
 }
 
 static bool al16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; }
 
-int launch_fused2(const KP& p, int obs, cudaStream_t s) {
-  if (obs != 1 || !fused_eligible(p)) return MG_E_UNSUPPORTED;
-  if (!al16(p.actions) || !al16(p.rewards) || !al16(p.done) || !al16(p.obs)) return MG_E_UNSUPPORTED;  // bulk copies need 16-byte alignment
+template <int OBS>
+static int launch_v(const KP& p, cudaStream_t s) {
   const bool vo0 = p.vo == 0;
-  if (p.V == 7) return vo0 ? launch_a<7, true>(p, s) : launch_a<7, false>(p, s);
-  if (p.V == 5) return vo0 ? launch_a<5, true>(p, s) : launch_a<5, false>(p, s);
+  if (p.V == 7) return vo0 ? launch_a<OBS, 7, true>(p, s) : launch_a<OBS, 7, false>(p, s);
+  if (p.V == 5) return vo0 ? launch_a<OBS, 5, true>(p, s) : launch_a<OBS, 5, false>(p, s);
+  return MG_E_UNSUPPORTED;
+}
+
+int launch_fused2(const KP& p, int obs, cudaStream_t s) {
+  if (!fused_eligible(p)) return MG_E_UNSUPPORTED;
+  if (!al16(p.actions) || !al16(p.rewards) || !al16(p.done) || !al16(p.obs)) return MG_E_UNSUPPORTED;  // bulk copies need 16-byte alignment
+  if (obs == 1) return launch_v<1>(p, s);
+  // RGB: tile size 8 (every registered env), rotation-equivariant atlas (one slot per tile), tile ids that fit a byte
+  if (obs == 2 && p.ts == 8 && p.orient_slots == 1 && p.n_tiles < 255 && al16(p.atlas)) return launch_v<2>(p, s);
   return MG_E_UNSUPPORTED;
 }
 

@@ -50,3 +50,8 @@ if [[ "$what" == *ncureset* ]]; then
       python bench.py --steps 6 --warmup 120 --replicas 1 --no-cpu-baseline --e2e-steps 3 > gpurun_out/ncu_reset.log 2>&1
   ls -la gpurun_out/
 fi
+if [[ "$what" == *ncurgb* ]]; then
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:fused -s 6 -c 1 -f -o gpurun_out/prof_rgb \
+      python bench.py --workload cfg4 --steps 4 --warmup 4 > gpurun_out/ncu_rgb.log 2>&1
+  ls -la gpurun_out/
+fi
