@@ -48,7 +48,8 @@ struct Smem {
   // (one row of V cells = 8 pixel rows of V*24 bytes) that bulk copies drain while the next chunk is being built.
   static constexpr int MAP_BYTES = E * A * V * 8;
   static constexpr int CHUNK = V * 8 * 24;
-  static constexpr int OUT_BYTES = OBS == 1 ? E * A * V * V * 3 : MAP_BYTES + A * 2 * CHUNK;
+  static constexpr int NBUF = 6;  // OBS 2: chunk buffers per warp (NBUF - 1 bulk copies in flight while one is being filled)
+  static constexpr int OUT_BYTES = OBS == 1 ? E * A * V * V * 3 : MAP_BYTES + A * NBUF * CHUNK;
   static constexpr int SCRATCH_BYTES = (A * 4 * 32 + 64 * 32) * 4;  // sequential path: transposed records + reset masks
   static constexpr int OUT_AREA = ((OUT_BYTES > SCRATCH_BYTES ? OUT_BYTES : SCRATCH_BYTES) + 15) / 16 * 16;
   // one input stage
@@ -214,7 +215,7 @@ __global__ void __launch_bounds__(32 * A, ctas_per_sm<OBS, V, A, NST>()) fused2_
   if ((int)blockIdx.x < n_tiles) issue_load((int)blockIdx.x, 0);
 
   int it = 0;
-  int chunk_parity = 0;  // OBS 2: which of the warp's two chunk buffers is filled next
+  int chunk_parity = 0;  // OBS 2: which of the warp's chunk buffers is filled next
   for (int tile = (int)blockIdx.x; tile < n_tiles; tile += (int)gridDim.x, ++it) {
   const int stage = it % NST;
   unsigned char* const stg = smem + stage * SM::STAGE;
@@ -664,7 +665,7 @@ __global__ void __launch_bounds__(32 * A, ctas_per_sm<OBS, V, A, NST>()) fused2_
       cell_sel[i] = (uint32_t)(rem / 3);
     }
     const uint32_t atlas_s = smem_u32(s_atlas);
-    uint8_t* const bufs = s_out + SM::MAP_BYTES + a * (2 * SM::CHUNK);
+    uint8_t* const bufs = s_out + SM::MAP_BYTES + a * (SM::NBUF * SM::CHUNK);
     const int n_views = n_valid * A;
     constexpr long long VIEW_BYTES = (long long)V * V * 192;
     for (int v = 0; v < 32; ++v) {
@@ -673,9 +674,9 @@ __global__ void __launch_bounds__(32 * A, ctas_per_sm<OBS, V, A, NST>()) fused2_
       uint8_t* const dstv = p.obs + (env0 * A + vi) * VIEW_BYTES;
 #pragma unroll 1
       for (int b = 0; b < V; ++b) {
-        uint8_t* const buf = bufs + (chunk_parity ? SM::CHUNK : 0);
-        chunk_parity ^= 1;
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // the copy that last read this buffer is done
+        uint8_t* const buf = bufs + chunk_parity * SM::CHUNK;
+        chunk_parity = (chunk_parity + 1) % SM::NBUF;
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(SM::NBUF - 1) : "memory");  // the copy that last read this buffer is done
         __syncwarp();
         const uint2 ids = *reinterpret_cast<const uint2*>(s_out + vi * (V * 8) + b * 8);  // the row's V tile ids
 #pragma unroll
