@@ -218,7 +218,11 @@ struct MgEngine {
   uint8_t* d_obs;
   uint8_t* d_atlas;
   int64_t obs_bytes;
+  cudaStream_t copy_stream;    // device -> host copies of a finished slice run here, under the next slice's kernel
+  cudaEvent_t slice_done[8];
 };
+
+constexpr int ENGINE_SLICES = 4;  // mg_engine_step cuts the batch into this many env ranges (multiples of 32 envs)
 
 #define MG_CUDA(x)                                \
   do {                                            \
@@ -239,6 +243,8 @@ int mg_engine_create(MgEngine** out, const MgConfig* cfg, int64_t n_envs, int64_
   en->st.n_envs = n_envs; en->st.env_offset = env_offset; en->st.seed = seed;
   en->obs_bytes = n_envs * mg_obs_bytes_per_env(cfg, rgb);
   MG_CUDA(cudaStreamCreateWithFlags(&en->stream, cudaStreamNonBlocking));
+  MG_CUDA(cudaStreamCreateWithFlags(&en->copy_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 8; ++i) MG_CUDA(cudaEventCreateWithFlags(&en->slice_done[i], cudaEventDisableTiming));
   MG_CUDA(cudaMalloc(&en->st.grid, (size_t)n_envs * 3 * cfg->plane_stride));
   MG_CUDA(cudaMalloc(&en->st.agents, (size_t)n_envs * cfg->n_agents * MG_AGENT_REC));
   MG_CUDA(cudaMalloc(&en->st.envrec, (size_t)n_envs * MG_ENV_REC));
@@ -264,6 +270,9 @@ void mg_engine_destroy(MgEngine* e) {
   cudaStreamSynchronize(e->stream);
   cudaFree(e->st.grid); cudaFree(e->st.agents); cudaFree(e->st.envrec); cudaFree(e->st.cellbits);
   cudaFree(e->d_actions); cudaFree(e->d_rewards); cudaFree(e->d_done); cudaFree(e->d_obs); cudaFree(e->d_atlas);
+  cudaStreamSynchronize(e->copy_stream);
+  for (int i = 0; i < 8; ++i) cudaEventDestroy(e->slice_done[i]);
+  cudaStreamDestroy(e->copy_stream);
   cudaStreamDestroy(e->stream);
   delete e;
 }
@@ -283,14 +292,34 @@ int mg_engine_reset(MgEngine* e, uint8_t* obs_host) {
 int mg_engine_step(MgEngine* e, const int32_t* actions_host, uint8_t* obs_host, double* rewards_host, uint8_t* done_host, int autoreset) {
   if (!e || !actions_host) return MG_E_ARG;
   MG_CUDA(cudaSetDevice(e->device));
-  const size_t na = (size_t)e->st.n_envs * e->cfg.n_agents;
-  MG_CUDA(cudaMemcpyAsync(e->d_actions, actions_host, na * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
-  int r = e->rgb ? mg_step_fused_rgb(&e->cfg, &e->st, e->d_actions, e->d_rewards, e->d_done, e->d_atlas, e->d_obs, autoreset, e->stream)
-                 : mg_step_fused(&e->cfg, &e->st, e->d_actions, e->d_rewards, e->d_done, e->d_obs, autoreset, e->stream);
-  if (r) return r;
-  if (obs_host) MG_CUDA(cudaMemcpyAsync(obs_host, e->d_obs, (size_t)e->obs_bytes, cudaMemcpyDeviceToHost, e->stream));
-  if (rewards_host) MG_CUDA(cudaMemcpyAsync(rewards_host, e->d_rewards, na * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
-  if (done_host) MG_CUDA(cudaMemcpyAsync(done_host, e->d_done, (size_t)e->st.n_envs, cudaMemcpyDeviceToHost, e->stream));
+  // The step is PCIe-bound (the observations leaving the device): the batch is cut into env ranges, and while range k's
+  // results cross the bus on the copy stream, range k+1's actions come in and its kernel runs on the compute stream.
+  const int64_t B = e->st.n_envs;
+  const int A = e->cfg.n_agents;
+  const int64_t per_env_obs = e->obs_bytes / B;
+  const int n_slices = B >= 4096 ? ENGINE_SLICES : 1;
+  const int64_t slice = ((B + n_slices - 1) / n_slices + 31) / 32 * 32;
+  int k = 0;
+  for (int64_t b0 = 0; b0 < B; b0 += slice, ++k) {
+    const int64_t nb = std::min(slice, B - b0);
+    MgState st = e->st;
+    st.grid += b0 * 3 * e->cfg.plane_stride; st.agents += b0 * A * MG_AGENT_REC; st.envrec += b0 * 4; st.cellbits += b0 * BITS_WORDS;
+    st.n_envs = nb; st.env_offset = e->st.env_offset + b0;
+    int32_t* d_act = e->d_actions + b0 * A;
+    double* d_rew = e->d_rewards + b0 * A;
+    uint8_t* d_done = e->d_done + b0;
+    uint8_t* d_obs = e->d_obs + b0 * per_env_obs;
+    MG_CUDA(cudaMemcpyAsync(d_act, actions_host + b0 * A, (size_t)nb * A * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+    int r = e->rgb ? mg_step_fused_rgb(&e->cfg, &st, d_act, d_rew, d_done, e->d_atlas, d_obs, autoreset, e->stream)
+                   : mg_step_fused(&e->cfg, &st, d_act, d_rew, d_done, d_obs, autoreset, e->stream);
+    if (r) return r;
+    MG_CUDA(cudaEventRecord(e->slice_done[k], e->stream));
+    MG_CUDA(cudaStreamWaitEvent(e->copy_stream, e->slice_done[k], 0));
+    if (obs_host) MG_CUDA(cudaMemcpyAsync(obs_host + b0 * per_env_obs, d_obs, (size_t)(nb * per_env_obs), cudaMemcpyDeviceToHost, e->copy_stream));
+    if (rewards_host) MG_CUDA(cudaMemcpyAsync(rewards_host + b0 * A, d_rew, (size_t)nb * A * sizeof(double), cudaMemcpyDeviceToHost, e->copy_stream));
+    if (done_host) MG_CUDA(cudaMemcpyAsync(done_host + b0, d_done, (size_t)nb, cudaMemcpyDeviceToHost, e->copy_stream));
+  }
+  MG_CUDA(cudaStreamSynchronize(e->copy_stream));
   MG_CUDA(cudaStreamSynchronize(e->stream));
   return 0;
 }

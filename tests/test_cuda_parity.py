@@ -270,13 +270,13 @@ def test_error_bits_mirror_reference_exceptions():
     assert int(env.err.sum().item()) == 0
 
 
-def test_engine_host_buffer_api(cuda_lib, oracle):
-    """mg_engine_*: host buffers in, host buffers out (the e2e path of bench.py)."""
+@pytest.mark.parametrize("B", [3000, 5000])
+def test_engine_host_buffer_api(cuda_lib, oracle, B):
+    """mg_engine_*: host buffers in, host buffers out (the e2e path of bench.py); 5000 envs = four overlapped slices."""
     from marlgrid_b200 import _lib
     from marlgrid_b200.config import make_config
 
     cfg = make_config(15, 15, ["red", "blue", "purple"], n_clutter=25)
-    B = 3000
     h = ctypes.c_void_p()
     _lib.check(cuda_lib.mg_engine_create(ctypes.byref(h), ctypes.byref(cfg), B, 0, 1337, 0, 0, None, 0), "mg_engine_create")
     ob = oracle.OracleBatch(cfg, B, seed=1337, threads=8)
@@ -293,6 +293,30 @@ def test_engine_host_buffer_api(cuda_lib, oracle):
         o2, r2, d2 = ob.step(act, autoreset=True, with_obs=True)
         assert np.array_equal(obs, o2) and np.array_equal(rew.view(np.uint64), r2.view(np.uint64)) and np.array_equal(done, d2)
     cuda_lib.mg_engine_destroy(h)
+
+
+def test_round_robin_rollout_equals_separate_families(cuda_lib):
+    """mg_rollout_fused_rr (bench.py's timed loop): R families stepped round robin from C == each family stepped alone."""
+    from marlgrid_b200 import _lib, envs
+    from marlgrid_b200.config import MgState
+
+    R, B, T = 3, 2048, 36
+    fams = [envs.make("MarlGrid-3AgentCluttered15x15-v0", num_envs=B, obs_mode="encoded", seed=11, env_offset=r * B) for r in range(R)]
+    refs = [envs.make("MarlGrid-3AgentCluttered15x15-v0", num_envs=B, obs_mode="encoded", seed=11, env_offset=r * B) for r in range(R)]
+    for e in fams + refs:
+        e.reset()
+    actions = torch.stack([fams[0].random_actions(t) for t in range(T)])
+    states = (MgState * R)(*[f._state for f in fams])
+    PP = ctypes.c_void_p * R
+    _lib.check(cuda_lib.mg_rollout_fused_rr(ctypes.byref(fams[0].cfg), states, R, actions.data_ptr(), T,
+                                            PP(*[f.rewards.data_ptr() for f in fams]), PP(*[f.done.data_ptr() for f in fams]),
+                                            PP(*[f.obs.data_ptr() for f in fams]), 1, None), "mg_rollout_fused_rr")
+    for t in range(T):
+        refs[t % R].step(actions[t])
+    torch.cuda.synchronize()
+    for f, g in zip(fams, refs):
+        assert torch.equal(f.obs, g.obs) and torch.equal(f.rewards, g.rewards) and torch.equal(f.done, g.done)
+        assert torch.equal(f.grid, g.grid) and torch.equal(f.agents, g.agents) and torch.equal(f.envrec, g.envrec)
 
 
 def test_checkpoint_resume_is_exact():
