@@ -73,7 +73,7 @@ static int check_state(const MgConfig* c, const MgState* st) {
 extern "C" {
 
 int mg_version(void) { return 1; }
-const char* mg_build_info(void) { return "marlgrid_b200 sm_100a: per-env step kernel + bit-plane observe kernel (cp.async.bulk + mbarrier staging, 32 envs/CTA)"; }
+const char* mg_build_info(void) { return "marlgrid_b200 sm_100a: persistent fused step+observe kernel (cp.async.bulk + mbarrier staging, 32 envs per tile, PDL), general fused / per-env / observe kernels"; }
 int mg_sizeof_config(void) { return (int)sizeof(MgConfig); }
 int mg_config_validate(const MgConfig* cfg) { return check_cfg(cfg); }
 int64_t mg_obs_bytes_per_env(const MgConfig* c, int rgb) {

@@ -1,21 +1,29 @@
-// mg_fused2.cu -- the hot path: env.step + auto-reset + encoded egocentric observation in ONE launch, specialised at
-// compile time on the agent count A and view size V of the registered env shapes (MarlGrid-*: V = 7 or 5, A <= 4).
+// mg_fused2.cu -- the hot path: env.step + auto-reset + egocentric observation (encoded or RGB) in ONE launch, specialised
+// at compile time on the agent count A and view size V of the registered env shapes (MarlGrid-*: V = 7 or 5, A <= 4).
 //
-//   CTA  = 32 consecutive envs, A warps:  lane = env, warp = agent  (thread = one agent = one view; no divisions, per-env
+//   grid = persistent CTAs (as many as stay resident, trimmed to equal rounds); CTA c handles tiles c, c + gridDim.x, ...
+//   tile = 32 consecutive envs, A warps:  lane = env, warp = agent  (thread = one agent = one view; no divisions, per-env
 //          work is simply "warp 0", and every shared-memory access pattern is a fixed stride across lanes)
 //   I/O  = bulk-async copies only (cp.async.bulk + mbarrier -- the TMA engine, SASS UBLKCP): the tile's bit-plane lines,
-//          agent records, env records and actions come in as four contiguous chunks; observations, records, env records,
-//          rewards and done flags leave the same way.  No thread touches global memory on the common path.
+//          agent records, env records and actions come in as four contiguous chunks (into one of NST input stages: the next
+//          tile is prefetched while this one is processed); observations, records, env records, rewards and done flags
+//          leave the same way.  No thread touches global memory on the common path.
 //   step = MultiGridEnv.step (base.py:501-649): in ghost mode an action that does not edit the planes is independent of
 //          what the env's other agents do in the same step, so the A agents act in parallel; the reference's random
 //          processing order (base.py:514-516, one Philox block per env) only ranks the arrival stamps of the movers.
-//          Envs in which an action WOULD edit the planes (effective pickup / drop / toggle) are replayed by their warp-0
-//          lane with the sequential code of mg_env.cuh; finished envs are regenerated the same way (env_reset).
-//   obs  = gen_obs_grid (base.py:418-451) + occlude_mask (agents.py:298-343) + MultiGrid.encode (base.py:196-214): a view
-//          row is ONE word load (line of the bit-planes: opaque | other<<16) + a window shift; the reference's rotation is a
-//          row-order flip and a bit reversal of the line; line of sight is carry propagation on 7-bit rows; visible canonical
-//          walls are written as constants, the few other objects come from the env's object list, agents from the records.
+//          Envs in which an action WOULD edit the planes (effective pickup / drop / toggle) are replayed with the
+//          sequential code of mg_env.cuh; finished envs are regenerated the same way (env_reset), their byte planes
+//          rebuilt from the bit-plane lines in shared memory and stored by bulk copies.
+//   obs  = gen_obs_grid (base.py:418-451) + occlude_mask (agents.py:298-343), then
+//          OBS 1: MultiGrid.encode (base.py:196-214).  A view row is ONE word load (line of the bit-planes: opaque |
+//                 other<<16) + a window shift; the reference's rotation is a row-order flip and a bit reversal of the line;
+//                 line of sight is carry propagation on 7-bit rows; visible canonical walls are written as constants, the
+//                 few other objects come from the env's object list, agents from the records.
+//          OBS 2: MultiGrid.render (base.py:301-331) at tile size 8.  The view threads write tile ids; the warps then copy
+//                 tile rows from the atlas (shared memory) into chunk buffers that bulk copies stream to HBM.
 // Everything here is integer work on the ALU/LSU pipes; the path has no dense contraction, hence no tensor cores.
+// Launch-shape knobs for experiments (read once): MG_F2_STAGES=1, MG_F2_CTAS_PER_SM=n, MG_F2_PDL=0, MG_F2_RAGGED=1,
+// MG_F2_VERBOSE=1.
 #include <cstdlib>
 
 #include "mg_env.cuh"

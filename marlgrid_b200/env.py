@@ -25,6 +25,26 @@ from .config import (AF_ACTIVE, AF_DONE, AF_PLACED, ERR_BAD_ACTION, ERR_PLACEMEN
 from .spaces import Box, Discrete, Tuple
 
 
+def compose_rich_obs(pov, agents, width, height, observe_rewards=True, observe_position=True, observe_orientation=True):
+    """The reference's observation_style='rich' dict (marlgrid/base.py:461-471), batched: from the observation tensor
+    `pov` [B, A, ...] and the agent records `agents` uint8 [B, A, 16] (x, y, dir, flags, ...).
+
+    * 'reward' is 0: the reference reads `agent.step_reward`, which `step` only ever sets to 0 (base.py:464,519);
+    * 'position' = pos / (width, height) as float64, (0, 0) for an agent that is not in the grid (base.py:466-467);
+    * 'orientation' = the agent's dir (base.py:469-470).
+    """
+    out = {"pov": pov}
+    if observe_rewards:
+        out["reward"] = torch.zeros(agents.shape[:2], dtype=torch.int64, device=agents.device)
+    if observe_position:
+        placed = (agents[..., 3] & AF_PLACED) != 0
+        xy = agents[..., 0:2].to(torch.float64) * placed[..., None]
+        out["position"] = xy / torch.tensor([width, height], dtype=torch.float64, device=agents.device)
+    if observe_orientation:
+        out["orientation"] = agents[..., 2].to(torch.int64)
+    return out
+
+
 class BatchedMultiGridEnv:
     metadata = {}
 
@@ -306,9 +326,14 @@ class UnbatchedView:
     def seed(self, seed=1337):
         return self.env.seed(seed)
 
+    def _per_agent(self, obs):
+        n = self.env.num_agents
+        if isinstance(obs, dict):  # observation_style='rich': one dict per agent, like the reference
+            return [{k: v[self.index, a] for k, v in obs.items()} for a in range(n)]
+        return [obs[self.index, a] for a in range(n)]
+
     def reset(self, **kw):
-        obs = self.env.reset()
-        return [obs[self.index, a] for a in range(self.env.num_agents)]
+        return self._per_agent(self.env.reset())
 
     def step(self, actions):
         if self.env.num_envs != 1:
@@ -317,4 +342,4 @@ class UnbatchedView:
             raise AssertionError("len(actions) == len(self.agents)")  # base.py:508
         obs, rew, done, info = self.env.step(torch.as_tensor(list(int(a) for a in actions), dtype=torch.int32).view(1, -1))
         self.env.check_errors()
-        return [obs[0, a] for a in range(self.env.num_agents)], rew[0], bool(done[0].item()), info
+        return self._per_agent(obs), rew[0], bool(done[0].item()), info

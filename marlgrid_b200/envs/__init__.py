@@ -13,7 +13,7 @@ import sys
 
 from ..agents import GridAgentInterface
 from ..config import GOAL_FIXED, GOAL_NONE, GOAL_RANDOM, make_config
-from ..env import BatchedMultiGridEnv
+from ..env import BatchedMultiGridEnv, compose_rich_obs
 
 this_module = sys.modules[__name__]
 registered_envs = []
@@ -60,7 +60,8 @@ class MultiGridEnv(BatchedMultiGridEnv):
         if not self.agent_interfaces:
             raise ValueError("a batched MarlGrid env needs at least one agent")
         ai = self.agent_interfaces
-        for field in ("view_size", "view_tile_size", "view_offset", "see_through_walls"):
+        for field in ("view_size", "view_tile_size", "view_offset", "see_through_walls", "observation_style", "observe_rewards",
+                      "observe_position", "observe_orientation"):
             if len({getattr(a, field) for a in ai}) != 1:
                 raise ValueError(f"all agents of a batched env must share {field} (observations are one tensor)")
         self.width, self.height = width, height
@@ -77,6 +78,23 @@ class MultiGridEnv(BatchedMultiGridEnv):
 
     def _scenario(self):
         raise NotImplementedError
+
+    # observation_style='rich' (marlgrid/base.py:461-471, agents.py:66-76): the observation becomes a dict of batched tensors
+    def _style(self, obs):
+        a0 = self.agent_interfaces[0]
+        if a0.observation_style != "rich":
+            return obs
+        return compose_rich_obs(obs, self.agents, self.width, self.height, a0.observe_rewards, a0.observe_position, a0.observe_orientation)
+
+    def reset(self, *args, **kwargs):
+        return self._style(super().reset(*args, **kwargs))
+
+    def observe(self):
+        return self._style(super().observe())
+
+    def step(self, actions):
+        obs, rew, done, info = super().step(actions)
+        return self._style(obs), rew, done, info
 
 
 class EmptyMultiGrid(MultiGridEnv):

@@ -349,3 +349,24 @@ def test_unbatched_gym_surface():
         env.step([2, 17])
     with pytest.raises(AssertionError):
         env.step([2])
+
+
+def test_rich_observation_style():
+    """observation_style='rich' (marlgrid/base.py:461-471): dict of batched tensors / list of per-agent dicts."""
+    from marlgrid_b200.agents import GridAgentInterface
+    from marlgrid_b200.envs import EmptyMultiGrid
+
+    ags = [GridAgentInterface(color=c, view_size=7, view_tile_size=8, observation_style="rich", observe_rewards=True,
+                              observe_position=True, observe_orientation=True) for c in ("red", "blue")]
+    env = EmptyMultiGrid(agents=ags, grid_size=9, num_envs=64, obs_mode="rgb", seed=3)
+    obs = env.reset()
+    assert set(obs) == {"pov", "reward", "position", "orientation"} and tuple(obs["pov"].shape) == (64, 2, 56, 56, 3)
+    for t in range(20):
+        obs, rew, done, _ = env.step(env.random_actions(t))
+        pos = env.agent_pos.to(torch.float64) / 9.0
+        assert torch.equal(obs["position"], pos) and torch.equal(obs["orientation"], env.agent_dir.long())
+        assert int(obs["reward"].abs().sum().item()) == 0
+    one = EmptyMultiGrid(agents=[a.clone() for a in ags], grid_size=9, num_envs=1, obs_mode="rgb", seed=3).unbatched()
+    lst = one.reset()
+    assert isinstance(lst, list) and len(lst) == 2 and set(lst[0]) == {"pov", "reward", "position", "orientation"}
+    assert tuple(lst[0]["pov"].shape) == (56, 56, 3) and tuple(lst[1]["position"].shape) == (2,)

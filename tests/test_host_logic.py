@@ -173,6 +173,29 @@ def test_independent_learners_protocol():
     assert agents.action_step(single) == [0, 1]
 
 
+def test_rich_observation_dict_composition():
+    """observation_style='rich' (marlgrid/base.py:461-471): checked in the dev container against the unmodified reference
+    (reward is always 0 there: base.py:464,519; position = pos / (W, H) float64, (0, 0) when not placed; orientation = dir)."""
+    import numpy as np
+    import torch
+
+    from marlgrid_b200.env import compose_rich_obs
+
+    agents = torch.zeros((2, 3, 16), dtype=torch.uint8)
+    agents[0, 0, :4] = torch.tensor([6, 6, 0, 3], dtype=torch.uint8)   # reference: reset obs of 2AgentEmpty9x9, agent at (6, 6)
+    agents[0, 1, :4] = torch.tensor([1, 6, 3, 3], dtype=torch.uint8)
+    agents[1, 2, :4] = torch.tensor([5, 2, 1, 0], dtype=torch.uint8)   # not placed: pos is None -> (0, 0)
+    pov = torch.zeros((2, 3, 56, 56, 3), dtype=torch.uint8)
+    r = compose_rich_obs(pov, agents, 9, 9)
+    assert set(r) == {"pov", "reward", "position", "orientation"} and r["pov"] is pov
+    assert r["position"].dtype == torch.float64 and tuple(r["position"].shape) == (2, 3, 2)
+    assert np.array_equal(r["position"][0, 0].numpy(), np.array([6, 6]) / np.array([9, 9], dtype=float))
+    assert np.array_equal(r["position"][0, 1].numpy(), np.array([1, 6]) / np.array([9, 9], dtype=float))
+    assert np.array_equal(r["position"][1, 2].numpy(), np.zeros(2))
+    assert int(r["orientation"][0, 1]) == 3 and int(r["orientation"][1, 2]) == 1 and int(r["reward"].abs().sum()) == 0
+    assert set(compose_rich_obs(pov, agents, 9, 9, observe_rewards=False, observe_orientation=False)) == {"pov", "position"}
+
+
 def test_shard_ranges_partition_the_batch():
     from marlgrid_b200.sharding import shard_range
 

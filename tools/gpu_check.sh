@@ -55,3 +55,10 @@ if [[ "$what" == *ncurgb* ]]; then
       python bench.py --workload cfg4 --steps 4 --warmup 4 > gpurun_out/ncu_rgb.log 2>&1
   ls -la gpurun_out/
 fi
+if [[ "$what" == *sanitize* ]]; then
+  # memory-safety and shared-memory hazard checks of the kernels on a small problem (smoke: fused2 encoded + RGB reset/obs)
+  timeout 900 compute-sanitizer --tool memcheck --error-exitcode 7 python __graft_entry__.py smoke > gpurun_out/sanitizer_memcheck.log 2>&1; echo "memcheck exit $?" | tee -a gpurun_out/sanitizer_memcheck.log
+  timeout 900 compute-sanitizer --tool racecheck --error-exitcode 7 python __graft_entry__.py smoke > gpurun_out/sanitizer_racecheck.log 2>&1; echo "racecheck exit $?" | tee -a gpurun_out/sanitizer_racecheck.log
+  timeout 900 compute-sanitizer --tool synccheck --error-exitcode 7 python __graft_entry__.py smoke > gpurun_out/sanitizer_synccheck.log 2>&1; echo "synccheck exit $?" | tee -a gpurun_out/sanitizer_synccheck.log
+  tail -5 gpurun_out/sanitizer_memcheck.log gpurun_out/sanitizer_racecheck.log gpurun_out/sanitizer_synccheck.log
+fi
