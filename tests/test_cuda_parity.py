@@ -363,8 +363,8 @@ def test_rich_observation_style():
     assert set(obs) == {"pov", "reward", "position", "orientation"} and tuple(obs["pov"].shape) == (64, 2, 56, 56, 3)
     for t in range(20):
         obs, rew, done, _ = env.step(env.random_actions(t))
-        pos = env.agent_pos.to(torch.float64) / 9.0
-        assert torch.equal(obs["position"], pos) and torch.equal(obs["orientation"], env.agent_dir.long())
+        pos = env.agent_pos.cpu().numpy() / np.array([9, 9], dtype=float)  # numpy true division, like base.py:467
+        assert np.array_equal(obs["position"].cpu().numpy(), pos) and torch.equal(obs["orientation"], env.agent_dir.long())
         assert int(obs["reward"].abs().sum().item()) == 0
     one = EmptyMultiGrid(agents=[a.clone() for a in ags], grid_size=9, num_envs=1, obs_mode="rgb", seed=3).unbatched()
     lst = one.reset()

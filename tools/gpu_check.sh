@@ -56,9 +56,9 @@ if [[ "$what" == *ncurgb* ]]; then
   ls -la gpurun_out/
 fi
 if [[ "$what" == *sanitize* ]]; then
-  # memory-safety and shared-memory hazard checks of the kernels on a small problem (smoke: fused2 encoded + RGB reset/obs)
-  timeout 900 compute-sanitizer --tool memcheck --error-exitcode 7 python __graft_entry__.py smoke > gpurun_out/sanitizer_memcheck.log 2>&1; echo "memcheck exit $?" | tee -a gpurun_out/sanitizer_memcheck.log
-  timeout 900 compute-sanitizer --tool racecheck --error-exitcode 7 python __graft_entry__.py smoke > gpurun_out/sanitizer_racecheck.log 2>&1; echo "racecheck exit $?" | tee -a gpurun_out/sanitizer_racecheck.log
-  timeout 900 compute-sanitizer --tool synccheck --error-exitcode 7 python __graft_entry__.py smoke > gpurun_out/sanitizer_synccheck.log 2>&1; echo "synccheck exit $?" | tee -a gpurun_out/sanitizer_synccheck.log
-  tail -5 gpurun_out/sanitizer_memcheck.log gpurun_out/sanitizer_racecheck.log gpurun_out/sanitizer_synccheck.log
+  # memory-safety and shared-memory hazard checks of the kernels on a small problem (tools/sanitize_workload.py)
+  timeout 900 compute-sanitizer --tool memcheck --error-exitcode 7 python tools/sanitize_workload.py 103 > gpurun_out/sanitizer_memcheck.log 2>&1; echo "memcheck exit $?" | tee -a gpurun_out/sanitizer_memcheck.log
+  timeout 900 compute-sanitizer --tool racecheck --error-exitcode 7 python tools/sanitize_workload.py 103 > gpurun_out/sanitizer_racecheck.log 2>&1; echo "racecheck exit $?" | tee -a gpurun_out/sanitizer_racecheck.log
+  timeout 900 compute-sanitizer --tool synccheck --error-exitcode 7 python tools/sanitize_workload.py 103 > gpurun_out/sanitizer_synccheck.log 2>&1; echo "synccheck exit $?" | tee -a gpurun_out/sanitizer_synccheck.log
+  for f in memcheck racecheck synccheck; do tail -n 3 gpurun_out/sanitizer_$f.log; done
 fi
