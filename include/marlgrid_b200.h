@@ -64,9 +64,9 @@ enum { MG_A_LEFT = 0, MG_A_RIGHT = 1, MG_A_FORWARD = 2, MG_A_PICKUP = 3, MG_A_DR
 #define MG_AF_PLACED 1u  /* pos is not None: the agent is somewhere in the grid */
 #define MG_AF_ACTIVE 2u  /* GridAgentInterface.active (agents.py:155-159) */
 #define MG_AF_DONE 4u    /* GridAgentInterface.done (base.py:584-585) */
-#define MG_AF_HEAD 128u  /* DERIVED (maintained by the kernels): the agent is the head of its cell's queue, i.e. the
-                            cell object or `static_obj.agents[0]` of the reference (base.py:547-572).  Callers that edit
-                            agent records by hand must keep it consistent (or call mg_reset). */
+#define MG_AF_HEAD 128u  /* scratch bit: some kernels leave "head of its cell's queue" here; readers must ignore it (the queue
+                            order is defined by the stamps: the placed agent with the smallest stamp on a cell is the cell's
+                            object or `static_obj.agents[0]` of the reference, base.py:547-572) */
 
 /* MgConfig.flags */
 #define MG_F_GHOST 1u           /* ghost_mode (base.py:345,541-542,683-684) */
@@ -150,7 +150,7 @@ int64_t mg_obs_bytes_per_env(const MgConfig* cfg, int rgb);
  * episode 0).  Replaces MultiGridEnv.__init__ state setup (base.py:353-367, agents.py:90). */
 int mg_init(const MgConfig* cfg, const MgState* st, mg_stream_t stream);
 
-/* Recompute the derived state (MgState.cellbits, MG_AF_HEAD flags) from the planes and agent records. */
+/* Recompute the derived state (MgState.cellbits) from the planes and agent records. */
 int mg_sync_derived(const MgConfig* cfg, const MgState* st, mg_stream_t stream);
 
 /* Start a new episode in every env (reset_mask == NULL) or in envs whose mask byte != 0.

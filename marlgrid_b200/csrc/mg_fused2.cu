@@ -466,7 +466,6 @@ __global__ void __launch_bounds__(32 * A, ctas_per_sm<OBS, V, A, NST>()) fused2_
   }
 
   // ---- observe the post-step world: gen_obs_grid + occlude_mask + encode ----
-  uint32_t heads_w0 = 0;
   if (mine) {
     // All records of the env.  Queue heads (the agent with the smallest stamp on its cell is the cell's object or
     // `static_obj.agents[0]`, base.py:547-572) are recomputed by every view thread, branch-free: A is tiny, and it saves a
@@ -490,7 +489,6 @@ __global__ void __launch_bounds__(32 * A, ctas_per_sm<OBS, V, A, NST>()) fused2_
         if (same) heads &= ~loser;
       }
     const uint32_t me = rec[a * 4];
-    if (a == 0) heads_w0 = heads;  // warp 0 writes the derived head flags back with the records, once nobody reads them any more
     uint8_t* const tmap = s_out + (lane * A + a) * (V * 8);  // OBS 2: this view's tile ids, V rows of 8 bytes
     if (OBS == 2 && !(me & ((uint32_t)MG_AF_ACTIVE << 24))) {  // inactive agent: every cell is shadow (base.py:305,420-425)
       const uint32_t sh4 = (uint32_t)p.n_tiles * 0x01010101u;
@@ -628,14 +626,9 @@ __global__ void __launch_bounds__(32 * A, ctas_per_sm<OBS, V, A, NST>()) fused2_
       if (OBS == 2 && bad_render) atomicOr(reinterpret_cast<unsigned int*>(s_env) + lane * 4 + 3, (unsigned int)MG_ERR_RENDER << 16);
     }
   }
-  fence_proxy_async_smem();  // every thread's shared-memory writes of this tile, made visible to the bulk copies issued below
+  // (the threads that issue the bulk copies below fence the generic -> async proxy hand-over after this barrier, which has
+  // made every thread's shared-memory writes of the tile visible to them)
   __syncthreads();
-  if (a == 0 && mine) {  // derived state for the observe-only kernel: AF_HEAD = the agent is the head of its cell's queue
-#pragma unroll
-    for (int q = 0; q < A; ++q) rec[q * 4] = (rec[q * 4] & ~(AF_HEAD << 24)) | (((heads_w0 >> q) & 1u) << 31);
-    fence_proxy_async_smem();
-  }
-  if (a == 0) __syncwarp();
 
   // ---- everything leaves as contiguous chunks; nobody waits for them here ----
   if (full) {

@@ -270,6 +270,20 @@ __device__ __forceinline__ void obs_view(const KP& p, const ObsSmem<V>& o, int v
   const int A = p.A, S = p.S;
   const uint32_t w0 = rec[a * 4];
   const bool active = ((w0 >> 24) & MG_AF_ACTIVE) != 0;  // base.py:420-425
+  // queue heads: the placed agent with the smallest stamp on a cell is the cell's object or `static_obj.agents[0]`
+  // (base.py:547-572).  Taken from the caller (fused kernel) or worked out here from the records.
+  uint32_t headmask = 0;
+  if (!HEADS && active) {
+    for (int q = 0; q < A; ++q) {
+      const uint32_t v0 = rec[q * 4];
+      bool head = ((v0 >> 24) & MG_AF_PLACED) != 0;
+      for (int r = 0; r < A; ++r) {
+        const uint32_t u0 = rec[r * 4];
+        if (r != q && ((u0 >> 24) & MG_AF_PLACED) && ((u0 ^ v0) & 0xFFFFu) == 0u && rec[r * 4 + 2] < rec[q * 4 + 2]) head = false;
+      }
+      headmask |= (head ? 1u : 0u) << q;
+    }
+  }
   const int px = (int)(w0 & 0xFFu), py = (int)((w0 >> 8) & 0xFFu), dir = (int)((w0 >> 16) & 3u);
   const int orient = (3 - dir) & 3;  // view orientation (0 - rot_k) % 4, base.py:130
   if (OBS == 2) {
@@ -305,7 +319,7 @@ __device__ __forceinline__ void obs_view(const KP& p, const ObsSmem<V>& o, int v
     if (V > 4) encode_cells<V, 4>(g_hi, pv, tp, S, out);
     for (int q = 0; q < A; ++q) {  // agents that are their cell's object: (13, colour, dir)
       const uint32_t v0 = rec[q * 4];
-      if (HEADS ? !heads[q] : !((v0 >> 24) & AF_HEAD)) continue;
+      if (HEADS ? !heads[q] : !((headmask >> q) & 1u)) continue;
       int va, vb;
       if (!world_to_view<V>(g, (int)(v0 & 0xFFu), (int)((v0 >> 8) & 0xFFu), va, vb)) continue;
       if (!pv.visible(va, vb) || pv.nonempty(va, vb)) continue;
@@ -345,7 +359,7 @@ __device__ __forceinline__ void obs_view(const KP& p, const ObsSmem<V>& o, int v
     }
     for (int q = 0; q < A; ++q) {
       const uint32_t v0 = rec[q * 4];
-      if (HEADS ? !heads[q] : !((v0 >> 24) & AF_HEAD)) continue;
+      if (HEADS ? !heads[q] : !((headmask >> q) & 1u)) continue;
       int va, vb;
       if (!world_to_view<V>(g, (int)(v0 & 0xFFu), (int)((v0 >> 8) & 0xFFu), va, vb)) continue;
       if (!pv.visible(va, vb)) continue;
