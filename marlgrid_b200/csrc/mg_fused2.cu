@@ -1,814 +1,25 @@
-// mg_fused2.cu -- the hot path: env.step + auto-reset + egocentric observation (encoded or RGB) in ONE launch, specialised
-// at compile time on the agent count A and view size V of the registered env shapes (MarlGrid-*: V = 7 or 5, A <= 4).
-//
-//   grid = persistent CTAs (as many as stay resident, trimmed to equal rounds); CTA c handles tiles c, c + gridDim.x, ...
-//   tile = 32 consecutive envs, A warps:  lane = env, warp = agent  (thread = one agent = one view; no divisions, per-env
-//          work is simply "warp 0", and every shared-memory access pattern is a fixed stride across lanes)
-//   I/O  = bulk-async copies only (cp.async.bulk + mbarrier -- the TMA engine, SASS UBLKCP): the tile's bit-plane lines,
-//          agent records, env records and actions come in as four contiguous chunks (into one of NST input stages: the next
-//          tile is prefetched while this one is processed); observations, records, env records, rewards and done flags
-//          leave the same way.  No thread touches global memory on the common path.
-//   step = MultiGridEnv.step (base.py:501-649): in ghost mode an action that does not edit the planes is independent of
-//          what the env's other agents do in the same step, so the A agents act in parallel; the reference's random
-//          processing order (base.py:514-516, one Philox block per env) only ranks the arrival stamps of the movers.
-//          Envs in which an action WOULD edit the planes (effective pickup / drop / toggle) are replayed with the
-//          sequential code of mg_env.cuh; finished envs are regenerated the same way (env_reset), their byte planes
-//          rebuilt from the bit-plane lines in shared memory and stored by bulk copies.
-//   obs  = gen_obs_grid (base.py:418-451) + occlude_mask (agents.py:298-343), then
-//          OBS 1: MultiGrid.encode (base.py:196-214).  A view row is ONE word load (line of the bit-planes: opaque |
-//                 other<<16) + a window shift; the reference's rotation is a row-order flip and a bit reversal of the line;
-//                 line of sight is carry propagation on 7-bit rows; visible canonical walls are written as constants, the
-//                 few other objects come from the env's object list, agents from the records.
-//          OBS 2: MultiGrid.render (base.py:301-331) at tile size 8.  The view threads write tile ids; the warps then copy
-//                 tile rows from the atlas (shared memory) into chunk buffers that bulk copies stream to HBM.
-// Everything here is integer work on the ALU/LSU pipes; the path has no dense contraction, hence no tensor cores.
-// Launch-shape knobs for experiments (read once): MG_F2_STAGES=1, MG_F2_CTAS_PER_SM=n, MG_F2_PDL=0, MG_F2_RAGGED=1,
-// MG_F2_VERBOSE=1.
-#include <cstdlib>
-
-#include "mg_env.cuh"
+// mg_fused2.cu -- dispatch of the specialised fused step+observe kernel (mg_fused2.cuh; instantiated per observation mode
+// and view size in mg_fused2_{enc,rgb}{7,5}.cu).
+#include "mg_common.cuh"
 
 namespace mg {
 
-namespace f2 {
-
-constexpr uint32_t FL_SLOW = 1u, FL_RESET = 2u, FL_BITS_DIRTY = 4u, FL_NOTDONE = 8u, FL_IMAGE = 16u;  // s_flag bits; bits 8..15 movers, 16..31 error bits
-
-// the general sequential code, kept out of line so the common path keeps its registers
-__device__ __noinline__ void seq_step(EnvCtx<32>& cref, unsigned long long g, const int32_t* act, double* rew) {
-  EnvCtx<32> c = cref;
-  env_step<32, true, MG_MAX_AGENTS>(c, g, act, rew);
-  cref.sc = c.sc; cref.ep = c.ep; cref.tl = c.tl; cref.w3 = c.w3; cref.dirty = c.dirty;
-}
-template <bool PLANES>
-__device__ __noinline__ void seq_reset(EnvCtx<32>& cref, unsigned long long g) {
-  EnvCtx<32> c = cref;
-  env_reset<32, true, PLANES>(c, g);
-  cref.sc = c.sc; cref.ep = c.ep; cref.tl = c.tl; cref.w3 = c.w3; cref.dirty = c.dirty;
-}
-
-// shared memory of one persistent CTA: NST input stages (what the bulk loads fill and the state stores drain), one output
-// tile, the small per-tile exchange arrays.  Offsets in bytes, every block a multiple of 16.
-template <int OBS, int V, int A, int NST>
-struct Smem {
-  static constexpr int E = ENVS_PER_CTA;
-  // OBS 1: the encoded observation tile.  OBS 2: per-view tile-id maps (V rows of 8 bytes) + per warp two image chunks
-  // (one row of V cells = 8 pixel rows of V*24 bytes) that bulk copies drain while the next chunk is being built.
-  static constexpr int MAP_BYTES = E * A * V * 8;
-  static constexpr int CHUNK = V * 8 * 24;
-  static constexpr int NBUF = 6;  // OBS 2: chunk buffers per warp (NBUF - 1 bulk copies in flight while one is being filled)
-  static constexpr int OUT_BYTES = OBS == 1 ? E * A * V * V * 3 : MAP_BYTES + A * NBUF * CHUNK;
-  static constexpr int SCRATCH_BYTES = (A * 4 * 32 + 64 * 32) * 4;  // sequential path: transposed records + reset masks
-  static constexpr int OUT_AREA = ((OUT_BYTES > SCRATCH_BYTES ? OUT_BYTES : SCRATCH_BYTES) + 15) / 16 * 16;
-  // one input stage
-  static constexpr int ST_BITS = 0;
-  static constexpr int ST_REC = ST_BITS + E * BITS_WORDS * 4;
-  static constexpr int ST_ENV = ST_REC + E * A * 16;
-  static constexpr int ST_ACT = ST_ENV + E * 16;
-  static constexpr int STAGE = ST_ACT + (E * A * 4 + 15) / 16 * 16;
-  // after the stages
-  static constexpr int REW = NST * STAGE;
-  static constexpr int DONE = REW + E * A * 8;
-  static constexpr int FLAG = DONE + E;          // two copies (tile parity)
-  static constexpr int ORDER = FLAG + 2 * E * 4;
-  static constexpr int BAR = ORDER + E * 4;      // NST mbarriers
-  static constexpr int OUT = BAR + ((NST * 8 + 15) / 16) * 16;
-  static constexpr int TOTAL = OUT + OUT_AREA;   // OBS 2: the tile atlas (run-time size) follows
-};
-
-// Lehmer / Fisher-Yates decode of the permutation number (oracle/philox.py shuffle_perm): nibble q of the result = agent
-// processed q-th.  A is a compile-time constant: the divisions are multiplications.
-template <int A>
-__device__ __forceinline__ uint32_t decode_order_ct(uint32_t pidx) {
-  uint32_t order = 0x76543210u;
-#pragma unroll
-  for (int i = A - 1; i >= 1; --i) {
-    const uint32_t n = (uint32_t)(i + 1);
-    const uint32_t qd = pidx / n;
-    const uint32_t j = pidx - qd * n;
-    pidx = qd;
-    const uint32_t ni = (order >> (4 * i)) & 0xFu, nj = (order >> (4 * j)) & 0xFu;
-    order = (order & ~(0xFu << (4 * i)) & ~(0xFu << (4 * j))) | (nj << (4 * i)) | (ni << (4 * j));
-  }
-  return order;
-}
-
-template <int N>
-struct Fact { static constexpr uint32_t v = N * Fact<N - 1>::v; };
-template <>
-struct Fact<0> { static constexpr uint32_t v = 1; };
-
-// occlude_mask (agents.py:298-343) for the agent at (V/2, V-1), i.e. view_offset 0: the upward pass visits every row;
-// the downward pass then only re-sweeps the agent's own row V-1, which the upward pass has already closed under both
-// sweeps (and row V does not exist), so it changes nothing and is skipped.
-template <int V>
-__device__ __forceinline__ void occlude_rows_vo0(const uint32_t (&T)[V], uint32_t (&M)[V]) {
-  constexpr uint32_t RM = (1u << V) - 1u;
-  constexpr int ax = V / 2;
-  constexpr uint32_t ge_ax = RM & ~((1u << ax) - 1u);
-  constexpr uint32_t left_src = ((1u << (ax + 2)) - 1u) & ~1u & RM;
-#pragma unroll
-  for (int j = 0; j < V; ++j) M[j] = (j == V - 1) ? (1u << ax) : 0u;
-#pragma unroll
-  for (int j = V - 1; j >= 1; --j) {
-    uint32_t nxt = 0;
-    sweep_row<V>(M[j], T[j], nxt, ge_ax, left_src);
-    M[j - 1] |= nxt;
-  }
-  {  // row 0 is a sweep target only in the reference's loop bounds (j = ay+1 .. 1): nothing left to do
-  }
-}
-
-// rows (one per register, V bits each) -> one byte per row of a 64-bit word: three byte permutes per four rows.  Bits of
-// a row above bit 7 are dropped; bit 7 itself is kept (callers mask with a clean row set).
-template <int V>
-__device__ __forceinline__ uint64_t pack_rows8(const uint32_t (&r)[V]) {
-  auto pack4 = [](uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
-    return __byte_perm(__byte_perm(r0, r1, 0x0040), __byte_perm(r2, r3, 0x0040), 0x5410);
-  };
-  const uint32_t lo = pack4(r[0], V > 1 ? r[1] : 0u, V > 2 ? r[2] : 0u, V > 3 ? r[3] : 0u);
-  const uint32_t hi = V > 4 ? pack4(r[4 < V ? 4 : 0], V > 5 ? r[5 < V ? 5 : 0] : 0u, V > 6 ? r[6 < V ? 6 : 0] : 0u, V > 7 ? r[7 < V ? 7 : 0] : 0u) : 0u;
-  return ((uint64_t)hi << 32) | lo;
-}
-
-// one-byte shared-memory store at a compile-time offset from a 32-bit shared address
-__device__ __forceinline__ void sts_u8(uint32_t saddr, uint32_t v) {
-  asm volatile("st.shared.u8 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
-}
-
-}  // namespace f2
-
-template <int OBS, int V, int A, int NST>
-constexpr int ctas_per_sm() {  // shared-memory / thread limited residency the register allocation should allow
-  constexpr int by_smem = (227 * 1024) / (f2::Smem<OBS, V, A, NST>::TOTAL + (OBS == 2 ? 11 * 1024 : 0) + 1024), by_threads = 64 / A;
-  constexpr int n = by_smem < by_threads ? by_smem : by_threads;
-  return n > 32 ? 32 : n;
-}
-
-// Persistent CTAs: CTA c handles tiles c, c + gridDim.x, ...; while a tile is being processed the next tile's inputs are
-// already on their way into the other input stage (NST = 2), and the previous tile's outputs drain in the background.
-template <int OBS, int V, int A, bool VO0, int NST>
-__global__ void __launch_bounds__(32 * A, ctas_per_sm<OBS, V, A, NST>()) fused2_kernel(const __grid_constant__ KP p, const int n_tiles) {
-  using namespace f2;
-  using SM = Smem<OBS, V, A, NST>;
-  constexpr int VV3 = V * V * 3;
-  constexpr uint32_t RM = (1u << V) - 1u;
-  extern __shared__ __align__(128) unsigned char smem[];
-  const int tid = threadIdx.x, lane = tid & 31, a = tid >> 5;  // lane = env within the tile, warp = agent
-  const int W = p.W, H = p.H, S = p.S;
-  // fresh worlds hold canonical walls plus (goal + bonus tiles) listed objects: if those always fit the object list, reset
-  // leaves the byte planes to the cooperative image below
-  const bool image_planes = (p.goal_mode != MG_GOAL_NONE ? 1 : 0) + p.n_bonus <= OBJ_SLOTS && 3 * S <= SM::OUT_AREA;
-
-  double* s_rew = reinterpret_cast<double*>(smem + SM::REW);       // [env][a]
-  uint8_t* s_done = smem + SM::DONE;                               // [env]
-  uint32_t* s_order = reinterpret_cast<uint32_t*>(smem + SM::ORDER);
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + SM::BAR);
-  uint8_t* s_out = smem + SM::OUT;
-  uint32_t* s_trec = reinterpret_cast<uint32_t*>(s_out);  // sequential path scratch, aliased with the output tile
-  uint32_t* s_scr = s_trec + A * 4 * 32;
-  uint8_t* const out = s_out + (lane * A + a) * VV3;
-  const uint32_t out_s = smem_u32(out);
-
-  auto zero_out = [&]() {  // invisible / empty cells encode as 0 (the RGB path writes every byte of its tile maps)
-    if (OBS != 1) return;
-    int4* z = reinterpret_cast<int4*>(s_out);
-    constexpr int N16 = SM::OUT_BYTES / 16, ITERS = (N16 + 32 * A - 1) / (32 * A);
-#pragma unroll
-    for (int k = 0; k < ITERS; ++k) {
-      const int i = tid + k * 32 * A;
-      if (i < N16) z[i] = make_int4(0, 0, 0, 0);
-    }
-  };
-  // one tile's inputs as four bulk copies on the stage's mbarrier.  Issuing a bulk copy costs its thread a few hundred
-  // cycles, so the four go out from lane 0 of different warps; thread 0 arms the barrier with the byte count (the
-  // transaction count may run ahead of it, the phase cannot complete before this arrival).
-  auto issue_load = [&](int tile, int stage) {
-    if (lane != 0) return;
-    const long long e0 = (long long)tile * ENVS_PER_CTA;
-    const int nv = (int)min((long long)ENVS_PER_CTA, p.B - e0);
-    unsigned char* st = smem + stage * SM::STAGE;
-    const uint32_t wbytes = (uint32_t)nv * (BITS_WORDS * 4u), rbytes = (uint32_t)nv * (A * 16u), ebytes = (uint32_t)nv * 16u;
-    const uint32_t abytes = nv == ENVS_PER_CTA ? (uint32_t)(ENVS_PER_CTA * A * 4) : 0u;
-    if (a == 0) {
-      mbar_expect_tx(s_bar + stage, wbytes + rbytes + ebytes + abytes);
-      bulk_g2s(st + SM::ST_BITS, p.cellbits + e0 * BITS_WORDS, wbytes, s_bar + stage);
-    }
-    if (a == 1 % A) bulk_g2s(st + SM::ST_REC, p.agents + e0 * A * 16, rbytes, s_bar + stage);
-    if (a == 2 % A) {
-      bulk_g2s(st + SM::ST_ENV, p.envrec + e0 * 4, ebytes, s_bar + stage);
-      if (abytes) bulk_g2s(st + SM::ST_ACT, p.actions + e0 * A, abytes, s_bar + stage);
-    }
-  };
-
-  if (tid == 0) {
-#pragma unroll
-    for (int i = 0; i < NST; ++i) mbar_init(s_bar + i, 1);
-  }
-  if (a == 0) { reinterpret_cast<uint32_t*>(smem + SM::FLAG)[lane] = 0u; reinterpret_cast<uint32_t*>(smem + SM::FLAG)[32 + lane] = 0u; }
-  __syncthreads();
-  uint8_t* const s_atlas = smem + SM::TOTAL;  // OBS 2: tiles [n_tiles] + the shadow tile, 192 bytes each (tile size 8)
-  if (OBS == 2) {  // the atlas is constant data: copy it while the previous kernel may still be running
-    const int4* src = reinterpret_cast<const int4*>(p.atlas);
-    int4* dst = reinterpret_cast<int4*>(s_atlas);
-    for (int i = tid; i < p.n_tiles * 12; i += 32 * A) dst[i] = __ldg(src + (i / 12) * 48 + (i % 12));  // global: [tile][4 orientations][192]; slot 0 only
-    // COLORS['shadow'] = (35, 25, 30) (objects.py:25, base.py:305): the byte pattern repeats every three words
-    for (int i = tid; i < 48; i += 32 * A)
-      reinterpret_cast<uint32_t*>(s_atlas + p.n_tiles * 192)[i] = (i % 3 == 0) ? 0x231E1923u : (i % 3 == 1) ? 0x19231E19u : 0x1E19231Eu;
-  }
-  // programmatic dependent launch: this grid may have been started while the previous kernel of the stream was still
-  // draining (its launch latency and this prologue overlap that tail); nothing before this line touches global memory
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  if ((int)blockIdx.x < n_tiles) issue_load((int)blockIdx.x, 0);
-
-  int it = 0;
-  int chunk_parity = 0;  // OBS 2: which of the warp's chunk buffers is filled next
-  for (int tile = (int)blockIdx.x; tile < n_tiles; tile += (int)gridDim.x, ++it) {
-  const int stage = it % NST;
-  unsigned char* const stg = smem + stage * SM::STAGE;
-  uint32_t* const s_bits = reinterpret_cast<uint32_t*>(stg + SM::ST_BITS);
-  uint32_t* const s_rec = reinterpret_cast<uint32_t*>(stg + SM::ST_REC);   // [env][a][4]
-  int32_t* const s_env = reinterpret_cast<int32_t*>(stg + SM::ST_ENV);     // [env][4]
-  const int32_t* const s_act = reinterpret_cast<const int32_t*>(stg + SM::ST_ACT);  // [env][a]
-  uint32_t* const s_flag = reinterpret_cast<uint32_t*>(smem + SM::FLAG) + (it & 1) * 32;
-  const long long env0 = (long long)tile * ENVS_PER_CTA;
-  const int n_valid = (int)min((long long)ENVS_PER_CTA, p.B - env0);
-  const bool full = n_valid == ENVS_PER_CTA;
-  const bool mine = lane < n_valid;
-  const long long env = env0 + lane;
-  const int next_tile = tile + (int)gridDim.x;
-  if (NST == 1 && it > 0) {  // single stage: the inputs can only be requested once the previous tile has drained
-    if (lane == 0) bulk_wait_read0();
-    __syncthreads();
-    issue_load(tile, 0);
-  }
-
-  int action = MG_A_DONE;
-  if (!full && mine) action = p.actions[env * A + a];
-  mbar_wait(s_bar + stage, (uint32_t)((it / NST) & 1));
-  if (full) action = s_act[lane * A + a];
-
-  // ---- warp 0: the step's agent order, base.py:514-516 -- one Philox block per env ----
-  if (a == 0 && mine) {
-    const unsigned long long g = (unsigned long long)(p.env_offset + env);
-    const U4 r = philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)s_env[lane * 4 + 2], 0u, (uint32_t)p.seed, (uint32_t)(p.seed >> 32));
-    s_order[lane] = decode_order_ct<A>(__umulhi(r.x, Fact<A>::v));
-  }
-
-  // ---- every agent plays its action on a private copy of its record (base.py:517-622) ----
-  uint32_t* const rec = s_rec + lane * (A * 4);
-  uint32_t* const bits = s_bits + lane * BITS_WORDS;
-  uint8_t* const tp = p.grid + env * 3 * S;
-  uint32_t w0 = 0, w1 = 0, errb = 0, base_stamp = 0;
-  bool moved = false, slow = false;
-  double reward = 0.0;
-  if (mine) {
-    const uint2 r01 = *reinterpret_cast<const uint2*>(rec + a * 4);
-    w0 = r01.x; w1 = r01.y;
-    base_stamp = (uint32_t)s_env[lane * 4 + 3] & 0xFFFFu;  // read before warp 0 advances it
-    if ((w0 >> 24) & MG_AF_ACTIVE) {  // base.py:521
-      const int cx = (int)(w0 & 0xFFu), cy = (int)((w0 >> 8) & 0xFFu), dir = (int)((w0 >> 16) & 3u);
-      if (action == MG_A_LEFT) w0 = (w0 & 0xFF00FFFFu) | ((uint32_t)((dir + 3) & 3) << 16);        // base.py:530-531
-      else if (action == MG_A_RIGHT) w0 = (w0 & 0xFF00FFFFu) | ((uint32_t)((dir + 1) & 3) << 16);  // base.py:534-535
-      else if (action >= MG_A_FORWARD && action <= MG_A_TOGGLE) {
-        const int fx = cx + ((dir == 0) ? 1 : (dir == 2) ? -1 : 0), fy = cy + ((dir == 1) ? 1 : (dir == 3) ? -1 : 0);  // agents.py:183
-        const bool inb = (unsigned)fx < (unsigned)W && (unsigned)fy < (unsigned)H;
-        if (!inb) errb |= MG_ERR_STACK;  // grid.get asserts in-bounds (base.py:154-156); never hit inside wall_rect
-        const uint32_t fc = inb ? ((bits[LINE_X0 + (fx & 15)] >> (fy & 15)) & 0x10001u) : 1u;  // 0 empty, 1 canonical wall, else "other"
-        if (fc <= 1u) {  // empty or wall in front: only forward can do anything (pickup / toggle need an object, drop needs hands full)
-          if (action == MG_A_FORWARD) {
-            if (fc == 0u) {
-              const uint32_t cc = (bits[LINE_X0 + (cx & 15)] >> (cy & 15)) & 0x10001u;
-              if (cc != 0u) {  // leaving a cell that holds a static object: it must be overlappable (base.py:558)
-                const uint32_t ccell = cell_triple(bits, cx & 15, cy & 15, tp, H, S);
-                if (!can_overlap_static((int)(ccell & 0xFFu), (int)(ccell >> 16))) errb |= MG_ERR_STACK;
-              }
-              w0 = (w0 & 0xFFFF0000u) | (uint32_t)fx | ((uint32_t)fy << 8);
-              moved = true;
-            }
-          } else if (action == MG_A_DROP) {
-            slow = inb && fc == 0u && (w1 & 0xFFu) != 0u;  // carrying and facing an empty cell (base.py:600-606)
-          }
-        } else {  // an object other than a canonical wall
-          const uint32_t fcell = cell_triple(bits, fx & 15, fy & 15, tp, H, S);
-          const int ftype = (int)(fcell & 0xFFu), fstate = (int)(fcell >> 16);
-          if (action == MG_A_FORWARD) {  // base.py:538-585 (ghost mode: other agents never block)
-            if (can_overlap_static(ftype, fstate)) {
-              const uint32_t cc = (bits[LINE_X0 + (cx & 15)] >> (cy & 15)) & 0x10001u;
-              if (cc != 0u) {
-                const uint32_t ccell = cell_triple(bits, cx & 15, cy & 15, tp, H, S);
-                if (!can_overlap_static((int)(ccell & 0xFFu), (int)(ccell >> 16))) errb |= MG_ERR_STACK;
-              }
-              w0 = (w0 & 0xFFFF0000u) | (uint32_t)fx | ((uint32_t)fy << 8);
-              moved = true;
-              if (ftype == MG_T_GOAL || ftype == MG_T_BONUS) {  // base.py:576-581
-                double rwd;
-                if (ftype == MG_T_GOAL) rwd = p.goal_reward;
-                else {  // BonusTile.get_reward objects.py:180-206 on the private copy of w1
-                  const int n = p.n_bonus, bonus_id = fstate;
-                  int bs = (int)(w1 >> 24);
-                  bool first = false;
-                  const double pen = p.bonus_penalty < 0 ? p.bonus_penalty : -p.bonus_penalty;
-                  if (bs == 0xFF) { bs = ((bonus_id - 1) % n + n) % n; first = true; }
-                  if (bs == bonus_id) rwd = pen;
-                  else if ((bs + 1) % n == bonus_id) { bs = bonus_id; rwd = p.bonus_reward; }
-                  else rwd = pen;
-                  if (p.flags & MG_F_BONUS_RESET) bs = bonus_id;
-                  w1 = (w1 & 0x00FFFFFFu) | ((uint32_t)bs << 24);
-                  if (first && !(p.flags & MG_F_BONUS_INITIAL)) rwd = 0.0;
-                }
-                if (p.flags & MG_F_REWARD_DECAY) {  // base.py:579, every operation rounded on its own
-                  const int sc = s_env[lane * 4] + 1;  // base.py:512
-                  const double qd = __ddiv_rn((double)sc, (double)p.max_steps);
-                  const double u = __dmul_rn(0.9, qd);
-                  const double f = __dsub_rn(1.0, u);
-                  rwd = __dmul_rn(rwd, f);
-                }
-                reward = __dadd_rn(0.0, rwd);  // step_rewards[agent_no] += rwd (base.py:580): 0.0 + (-0.0) is +0.0
-              }
-              if (ftype == MG_T_LAVA || ftype == MG_T_GOAL) w0 = (w0 | ((uint32_t)MG_AF_DONE << 24)) & ~((uint32_t)MG_AF_ACTIVE << 24);  // base.py:584-585,646
-            }
-          } else if (action == MG_A_PICKUP) {  // takes effect only on a pickable object with empty hands (base.py:590-597)
-            slow = ((PICKUP_MASK >> ftype) & 1u) && (w1 & 0xFFu) == 0u;
-          } else if (action == MG_A_TOGGLE) {  // only Door / Box react (base.py:609-613)
-            slow = ftype == MG_T_DOOR || ftype == MG_T_BOX;
-          }
-        }
-      } else if (action != MG_A_DONE) errb |= MG_ERR_BAD_ACTION;  // base.py:619-620
-    }
-    // one shared-memory atomic per agent: slow request / mover bit / "not done yet" bit / error bits
-    const uint32_t add = (slow ? FL_SLOW : 0u) | (moved ? (0x100u << a) : 0u) | (((w0 >> 24) & MG_AF_DONE) ? 0u : FL_NOTDONE) | (errb << 16);
-    if (add) atomicOr(&s_flag[lane], add);
-  }
-  if (lane == 0 || a == 0) bulk_wait_read0();  // the previous tile's stores (issued by these threads) have left shared memory
-  __syncthreads();
-
-  if (NST > 1 && next_tile < n_tiles) issue_load(next_tile, (it + 1) % NST);  // prefetch: lands during this tile's observe phase
-  zero_out();
-  if (a == 0) (reinterpret_cast<uint32_t*>(smem + SM::FLAG) + ((it + 1) & 1) * 32)[lane] = 0u;  // next tile's flag words
-
-  // ---- commit the parallel envs; envs whose planes change (FL_SLOW) are replayed below ----
-  const uint32_t fl1 = mine ? s_flag[lane] : 0u;
-  bool rare = false;
-  if (mine && !(fl1 & FL_SLOW)) {
-    uint32_t stamp = rec[a * 4 + 2];
-    if (moved) {  // arrival stamp: movers are numbered in the reference's processing order (base.py:547-552)
-      const uint32_t order = s_order[lane], movers = (fl1 >> 8) & 0xFFu;
-      uint32_t rank = 0;
-      bool before = true;
-#pragma unroll
-      for (int q = 0; q < A; ++q) {
-        const uint32_t b = (order >> (4 * q)) & 0xFu;
-        before = before && (b != (uint32_t)a);
-        rank += (before ? (movers >> b) & 1u : 0u);
-      }
-      stamp = (base_stamp + rank) & 0xFFFFu;
-    }
-    *reinterpret_cast<uint4*>(rec + a * 4) = make_uint4(w0, w1, stamp, 0u);
-    if (full) s_rew[lane * A + a] = reward; else p.rewards[env * A + a] = reward;
-    if (a == 0) {  // env bookkeeping and done (base.py:512,649)
-      int4 er = *reinterpret_cast<const int4*>(s_env + lane * 4);
-      const uint32_t w3 = (uint32_t)er.w;
-      er.x += 1;  // step_count
-      er.z += 1;  // lifetime steps
-      er.w = (int)((w3 & 0xFFFF0000u) | (((w3 & 0xFFFFu) + (uint32_t)__popc((fl1 >> 8) & 0xFFu)) & 0xFFFFu) | (fl1 & 0xFFFF0000u));
-      *reinterpret_cast<int4*>(s_env + lane * 4) = er;
-      const bool dn = (er.x >= p.max_steps) || !(fl1 & FL_NOTDONE);
-      if (full) s_done[lane] = dn ? 1 : 0; else p.done[env] = dn ? 1 : 0;
-      if (dn && p.autoreset) { rare = true; s_flag[lane] = fl1 | FL_BITS_DIRTY | FL_RESET; }
-    }
-  } else if (mine && a == 0) rare = true;
-  if (__syncthreads_or(rare ? 1 : 0)) {
-    // lane == env in every warp: the envs are dealt out over the CTA's warps (env e goes to warp e % A), so that A warps
-    // instead of one chew through the sequential code of mg_env.cuh; scratch lives in the (not yet used) output tile
-    if (a == lane % A && mine) {
-      uint32_t fl = s_flag[lane];
-      if (fl & (FL_SLOW | FL_RESET)) {
-        EnvCtx<32> c{p, s_trec + lane, tp, bits, s_scr + lane, 0, 0, 0, 0u, false};
-        for (int q = 0; q < A; ++q) { c.R(q, 0) = rec[q * 4]; c.R(q, 1) = rec[q * 4 + 1]; c.R(q, 2) = rec[q * 4 + 2]; }
-        c.sc = s_env[lane * 4]; c.ep = s_env[lane * 4 + 1]; c.tl = s_env[lane * 4 + 2]; c.w3 = (uint32_t)s_env[lane * 4 + 3];
-        const unsigned long long g = (unsigned long long)(p.env_offset + env);
-        if (fl & FL_SLOW) {  // MultiGridEnv.step replayed in the reference's order (base.py:501-649)
-          double rw[MG_MAX_AGENTS];
-          seq_step(c, g, p.actions + env * A, rw);
-          bool nd = false;
-          for (int q = 0; q < A; ++q) {
-            nd = nd || !((c.R(q, 0) >> 24) & MG_AF_DONE);
-            if (full) s_rew[lane * A + q] = rw[q]; else p.rewards[env * A + q] = rw[q];
-          }
-          const bool dn = (c.sc >= p.max_steps) || !nd;
-          if (full) s_done[lane] = dn ? 1 : 0; else p.done[env] = dn ? 1 : 0;
-          fl = FL_SLOW | (c.dirty ? FL_BITS_DIRTY : 0u) | ((dn && p.autoreset) ? (FL_BITS_DIRTY | FL_RESET) : 0u);
-        }
-        if (fl & FL_RESET) {  // MultiGridEnv.reset (base.py:402-416)
-          // an env whose replayed step edited the planes with plain stores keeps plain stores (no cross-proxy ordering games)
-          if (image_planes && !(fl & FL_SLOW)) { seq_reset<false>(c, g); fl |= FL_IMAGE; } else seq_reset<true>(c, g);
-        }
-        for (int q = 0; q < A; ++q) { rec[q * 4] = c.R(q, 0); rec[q * 4 + 1] = c.R(q, 1); rec[q * 4 + 2] = c.R(q, 2); rec[q * 4 + 3] = 0u; }
-        s_env[lane * 4] = c.sc; s_env[lane * 4 + 1] = c.ep; s_env[lane * 4 + 2] = c.tl; s_env[lane * 4 + 3] = (int)c.w3;
-        s_flag[lane] = fl;
-      }
-    }
-    __syncthreads();
-    if (image_planes) {
-      // The byte planes of the regenerated envs, rebuilt from their bit-plane lines (walls) and object lists (Goal,
-      // BonusTiles) in the -- still unused -- output area, group by group, and stored with bulk copies: a fresh world is
-      // 3*S bytes of mostly zeros, which single lanes writing to global memory would turn into hundreds of scattered stores.
-      const int plane_bytes = 3 * S;
-      const int G = min(ENVS_PER_CTA, SM::OUT_AREA / plane_bytes);
-      const uint32_t image_mask = __ballot_sync(0xFFFFFFFFu, mine && (s_flag[lane] & FL_IMAGE));  // lane == env: the same word in every warp
-      for (int g0 = 0; g0 < n_valid; g0 += G) {
-        const int gn = min(G, n_valid - g0);
-        const uint32_t group_mask = (image_mask >> g0) & (gn == 32 ? 0xFFFFFFFFu : ((1u << gn) - 1u));  // envs of the group that were reset
-        if (group_mask == 0u) continue;
-        {
-          int4* z = reinterpret_cast<int4*>(s_out);
-          for (int i = tid; i < gn * plane_bytes / 16; i += 32 * A) z[i] = make_int4(0, 0, 0, 0);
-        }
-        __syncthreads();
-        for (int i = tid; i < gn * 16; i += 32 * A) {  // one (env, x-line) pair per iteration
-          const int e = i >> 4, x = i & 15;
-          if (x >= W || !((group_mask >> e) & 1u)) continue;
-          const uint32_t* eb = s_bits + (g0 + e) * BITS_WORDS;
-          const uint32_t w = eb[LINE_X0 + x];
-          uint8_t* img = s_out + e * plane_bytes + x * H;
-          uint32_t walls = w & 0xFFFFu & ~(w >> 16), others = w >> 16;
-          while (walls) {
-            const int y = __ffs(walls) - 1;
-            walls &= walls - 1u;
-            img[y] = MG_T_WALL; img[S + y] = MG_C_WORST;
-          }
-          while (others) {
-            const int y = __ffs(others) - 1;
-            others &= others - 1u;
-            const uint32_t oe = obj_lookup(eb, x, y);  // always listed: image_planes requires goal + bonus tiles <= OBJ_SLOTS
-            img[y] = (uint8_t)((oe >> 8) & 15u); img[S + y] = (uint8_t)((oe >> 12) & 15u); img[2 * S + y] = (uint8_t)((oe >> 16) & 255u);
-          }
-        }
-        fence_proxy_async_smem();
-        __syncthreads();
-        if (a == 0) {
-          const bool all = group_mask == (gn == 32 ? 0xFFFFFFFFu : ((1u << gn) - 1u));
-          if (all ? lane == 0 : (lane < gn && ((group_mask >> lane) & 1u))) {
-            fence_proxy_async_smem();
-            if (all) bulk_s2g(p.grid + (env0 + g0) * plane_bytes, s_out, (uint32_t)(gn * plane_bytes));
-            else bulk_s2g(p.grid + (env0 + g0 + lane) * plane_bytes, s_out + lane * plane_bytes, (uint32_t)plane_bytes);
-            bulk_commit();
-            bulk_wait_read0();
-          }
-        }
-        __syncthreads();
-      }
-    }
-    zero_out();  // the sequential path borrowed the output area: clean it again
-    __syncthreads();
-  }
-
-  // ---- observe the post-step world: gen_obs_grid + occlude_mask + encode ----
-  if (mine) {
-    // All records of the env.  Queue heads (the agent with the smallest stamp on its cell is the cell's object or
-    // `static_obj.agents[0]`, base.py:547-572) are recomputed by every view thread, branch-free: A is tiny, and it saves a
-    // barrier.  Composite key = cell << 16 | stamp (an unplaced agent gets a cell nobody can stand on).
-    uint32_t q0[A], ck[A];
-    uint32_t heads = (1u << A) - 1u;
-#pragma unroll
-    for (int q = 0; q < A; ++q) {
-      const uint4 r = *reinterpret_cast<const uint4*>(rec + q * 4);
-      q0[q] = r.x;
-      const bool placed = (r.x & ((uint32_t)MG_AF_PLACED << 24)) != 0u;
-      ck[q] = placed ? __byte_perm(r.z, r.x, 0x5410) : (0xFF000000u | ((uint32_t)q << 16));
-      if (!placed) heads &= ~(1u << q);
-    }
-#pragma unroll
-    for (int q = 0; q < A; ++q)
-#pragma unroll
-      for (int r = q + 1; r < A; ++r) {
-        const bool same = (ck[q] ^ ck[r]) < 0x10000u;  // same cell: the one that arrived later is not the head
-        const uint32_t loser = (ck[q] < ck[r]) ? (1u << r) : (1u << q);
-        if (same) heads &= ~loser;
-      }
-    const uint32_t me = rec[a * 4];
-    uint8_t* const tmap = s_out + (lane * A + a) * (V * 8);  // OBS 2: this view's tile ids, V rows of 8 bytes
-    if (OBS == 2 && !(me & ((uint32_t)MG_AF_ACTIVE << 24))) {  // inactive agent: every cell is shadow (base.py:305,420-425)
-      const uint32_t sh4 = (uint32_t)p.n_tiles * 0x01010101u;
-#pragma unroll
-      for (int b = 0; b < V; ++b) *reinterpret_cast<uint2*>(tmap + b * 8) = make_uint2(sh4, sh4);
-    }
-    if (me & ((uint32_t)MG_AF_ACTIVE << 24)) {  // inactive agent: empty view, nothing visible (base.py:420-425)
-      const int px = (int)(me & 0xFFu), py = (int)((me >> 8) & 0xFFu), dir = (int)((me >> 16) & 3u);
-      constexpr int h = V / 2;
-      const int vo = VO0 ? 0 : p.vo;
-      // agents.py:237-266 get_view_exts; u = axis the agent faces along (view rows), v = axis across (bits of a row)
-      const int topX = (dir == 0) ? px - vo : (dir == 2) ? px - V + 1 + vo : px - h;
-      const int topY = (dir == 1) ? py - vo : (dir == 3) ? py - V + 1 + vo : py - h;
-      const bool vertical = (dir & 1) != 0, flip = dir < 2, rev = ((dir + 1) & 2) != 0;
-      const int u0 = vertical ? topY : topX, v0 = vertical ? topX : topY;
-      // window of a line: the 16 line bits are parked in the top half of a word (zeros below), shifted down to bit 0.
-      //   as stored:    OP = bits 0..15, OT = bits 16..31, view column a <-> line bit v0 + a
-      //   rotated view: the line is bit-reversed and its halves swapped back, view column a <-> line bit v0 + V-1 - a
-      const int shw = rev ? (32 - V - v0) : (v0 + 16);
-      // line of view row b = u0 + b (or u0 + V-1 - b): slot index + 1, clamped as unsigned to the zero guard lines 0 and 17
-      const uint32_t lines_s = smem_u32(bits + (vertical ? LINE_Y0 - 1 : LINE_X0 - 1));
-      const int ustep = flip ? -1 : 1, ubase = (flip ? u0 + V - 1 : u0) + 1;
-      uint32_t T[V], OT[V], OP[V], M[V];
-#pragma unroll
-      for (int b = 0; b < V; ++b) {
-        uint32_t w;
-        asm("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(lines_s + 4u * min((uint32_t)(ubase + b * ustep), 17u)));
-        if (rev) w = __byte_perm(__brev(w), 0u, 0x1032);  // reversed line, OP back in the low half
-        OP[b] = (w << 16) >> shw;                          // bits above the window (neighbouring cells) are masked by
-        OT[b] = (w & 0xFFFF0000u) >> shw;                  // the visibility rows below
-        T[b] = ~OP[b] & RM;
-      }
-      if (p.flags & MG_F_SEE_THROUGH) {  // agents.py:294-295
-#pragma unroll
-        for (int b = 0; b < V; ++b) M[b] = RM;
-      } else if (VO0) {
-        occlude_rows_vo0<V>(T, M);
-      } else {
-        occlude_rows<V>(T, V / 2, V - 1 - vo, M);  // agents.py:233-234,293
-      }
-      // rows packed one byte each (view cell (a, b) = bit 8*b + a): visible canonical walls / other objects / free cells
-      const uint64_t m64 = pack_rows8<V>(M), op64 = pack_rows8<V>(OP), ot64 = pack_rows8<V>(OT);
-      const uint64_t wall64 = m64 & op64 & ~ot64, free64 = m64 & ~(op64 | ot64);
-      uint64_t oth64 = m64 & ot64;
-      if (OBS == 1) {
-      {  // visible canonical walls (8, 9, 0): constants at compile-time offsets of the staging tile.  The two constants
-           // come in through a kernel parameter and the stores are spelled out, or ptxas re-materialises 8 / 9 around every store
-          const uint32_t wlo = (uint32_t)wall64, whi = (uint32_t)(wall64 >> 32);
-          const uint32_t c8 = p.wall_enc & 0xFFu, c9 = p.wall_enc >> 8;  // (MG_T_WALL, MG_C_WORST) through a kernel parameter
-#pragma unroll
-          for (int b = 0; b < V; ++b)
-#pragma unroll
-            for (int va = 0; va < V; ++va) {
-              if ((b < 4 ? wlo : whi) & (1u << (8 * (b & 3) + va))) {
-                sts_u8(out_s + (va * (V * 3) + b * 3 + 0), c8);
-                sts_u8(out_s + (va * (V * 3) + b * 3 + 1), c9);
-              }
-            }
-        }
-      }
-      if (OBS == 2) {
-        // tile ids (render_tile base.py:275-299): shadow where invisible, 0 for a visible empty cell, the Wall tile for a
-        // visible canonical wall -- per row, seven mask bits spread to seven bytes and scaled (no carries: one term per byte)
-        const uint32_t shadow = (uint32_t)p.n_tiles, wall_tile = (uint32_t)p.kind_of_type[MG_T_WALL] * (1u + 4u * A);
-#pragma unroll
-        for (int b = 0; b < V; ++b) {
-          const uint32_t vis = (uint32_t)(m64 >> (8 * b)) & 0xFFu, wl = (uint32_t)(wall64 >> (8 * b)) & 0xFFu;
-          const uint32_t v_lo = ((vis & 15u) * 0x00204081u) & 0x01010101u, v_hi = ((vis >> 4) * 0x00204081u) & 0x01010101u;
-          const uint32_t w_lo = ((wl & 15u) * 0x00204081u) & 0x01010101u, w_hi = ((wl >> 4) * 0x00204081u) & 0x01010101u;
-          *reinterpret_cast<uint2*>(tmap + b * 8) = make_uint2((0x01010101u - v_lo) * shadow + w_lo * wall_tile, (0x01010101u - v_hi) * shadow + w_hi * wall_tile);
-        }
-      }
-      // world cell -> view cell: vb = bu + su*cu, va = bv + sv*cv with (cu, cv) = (x, y) or (y, x)
-      const int su = flip ? -1 : 1, bu = flip ? V - 1 + u0 : -u0, sv = rev ? -1 : 1, bv = rev ? V - 1 + v0 : -v0;
-      bool bad_render = false;  // OBS 2: an object whose render() raises in the reference (objects.py:274-277,309-321,370)
-      if (oth64 != 0ull) {  // visible Goal / BonusTile / Key ...: the object list answers for (almost) all of them
-#pragma unroll
-        for (int k = 0; k < OBJ_SLOTS; ++k) {
-          const uint32_t e = bits[OBJ_WORD0 + k];
-          if (!(e >> 31)) continue;
-          const int ex = (int)(e & 15u), ey = (int)((e >> 4) & 15u);
-          const int vb = bu + su * (vertical ? ey : ex), va = bv + sv * (vertical ? ex : ey);
-          if ((unsigned)vb >= (unsigned)V || (unsigned)va >= (unsigned)V) continue;
-          const uint64_t m = 1ull << (8 * vb + va);
-          if (!(oth64 & m)) continue;
-          oth64 &= ~m;
-          if (OBS == 1) {
-            uint8_t* oo = out + va * (V * 3) + vb * 3;
-            oo[0] = (uint8_t)((e >> 8) & 15u); oo[1] = (uint8_t)((e >> 12) & 15u); oo[2] = (uint8_t)((e >> 16) & 255u);
-          } else {
-            const uint32_t kind = p.kind_of_type[(e >> 8) & 15u];
-            if (kind == 0xFFu) bad_render = true; else tmap[vb * 8 + va] = (uint8_t)(kind * (1u + 4u * A));
-          }
-        }
-        // objects that did not fit the list: WorldObj.encode (objects.py:90-99) from the byte planes
-        while (oth64 != 0ull) {
-          const int bit = __ffsll((long long)oth64) - 1;
-          oth64 &= oth64 - 1ull;
-          const int va = bit & 7, vb = bit >> 3;
-          const int uu = flip ? V - 1 - vb : vb, vv = rev ? V - 1 - va : va;
-          const int wx = topX + (vertical ? vv : uu), wy = topY + (vertical ? uu : vv);
-          const uint8_t* cp = p.grid + env * 3 * S + wx * H + wy;
-          if (OBS == 1) {
-            uint8_t* oo = out + va * (V * 3) + vb * 3;
-            oo[0] = cp[0]; oo[1] = cp[S]; oo[2] = cp[2 * S];
-          } else {
-            const uint32_t kind = p.kind_of_type[cp[0] & 15u];
-            if (kind == 0xFFu) bad_render = true; else tmap[vb * 8 + va] = (uint8_t)(kind * (1u + 4u * A));
-          }
-        }
-      }
-      // agents that are their cell's object: (13, colour, dir) where no static object stands (base.py:204-214)
-      const uint32_t sel_u = vertical ? 0x4441u : 0x4440u, sel_v = vertical ? 0x4440u : 0x4441u;
-#pragma unroll
-      for (int q = 0; q < A; ++q) {
-        const int vb = bu + su * (int)__byte_perm(q0[q], 0u, sel_u), va = bv + sv * (int)__byte_perm(q0[q], 0u, sel_v);
-        const bool in_view = (unsigned)vb < (unsigned)V && (unsigned)va < (unsigned)V;
-        if (OBS == 1) {
-          const bool draw = in_view && ((heads >> q) & 1u) && ((free64 >> ((8 * vb + va) & 63)) & 1ull);
-          if (draw) {
-            uint8_t* oo = out + va * (V * 3) + vb * 3;
-            oo[0] = MG_T_AGENT; oo[1] = p.agent_color[q]; oo[2] = (uint8_t)((q0[q] >> 16) & 3u);
-          }
-        } else {
-          // the cell's tile gets an agent on top: the observer itself if it stands there, else the queue head
-          // (base.py:282-293); tiles of size <= 10 are rotation-equivariant, so the view orientation is a dir remap
-          const bool draw = in_view && ((heads >> q) & 1u) && ((m64 >> ((8 * vb + va) & 63)) & 1ull);
-          if (draw) {
-            const bool own = ((q0[q] ^ me) & 0xFFFFu) == 0u;
-            const uint32_t qq = own ? (uint32_t)a : (uint32_t)q, qd = ((own ? me : q0[q]) >> 16) & 3u;
-            tmap[vb * 8 + va] = (uint8_t)(tmap[vb * 8 + va] + 1u + 4u * qq + ((qd + 3u - (uint32_t)dir) & 3u));
-          }
-        }
-      }
-      if (OBS == 2 && bad_render) atomicOr(reinterpret_cast<unsigned int*>(s_env) + lane * 4 + 3, (unsigned int)MG_ERR_RENDER << 16);
-    }
-  }
-  // (the threads that issue the bulk copies below fence the generic -> async proxy hand-over after this barrier, which has
-  // made every thread's shared-memory writes of the tile visible to them)
-  __syncthreads();
-
-  // ---- everything leaves as contiguous chunks; nobody waits for them here ----
-  if (full) {
-    if (lane == 0) {  // again spread over the warps' first lanes
-      fence_proxy_async_smem();
-      if (OBS == 1 && a == A - 1) bulk_s2g(p.obs + env0 * (A * VV3), s_out, (uint32_t)SM::OUT_BYTES);
-      if (a == 0) { bulk_s2g(p.agents + env0 * A * 16, s_rec, ENVS_PER_CTA * A * 16u); bulk_s2g(p.done + env0, s_done, ENVS_PER_CTA); }
-      if (a == 1 % A) bulk_s2g(p.envrec + env0 * 4, s_env, ENVS_PER_CTA * 16u);
-      if (a == 2 % A) bulk_s2g(p.rewards + env0 * A, s_rew, ENVS_PER_CTA * A * 8u);
-      bulk_commit();
-    }
-  } else {  // ragged last tile: plain stores
-    if (OBS == 1) {
-      const int total = n_valid * A * VV3;
-      uint8_t* dst = p.obs + env0 * (A * VV3);
-      for (int i = tid; i < total; i += 32 * A) dst[i] = s_out[i];
-    }
-    if (tid == 0) {
-      fence_proxy_async_smem();
-      bulk_s2g(p.agents + env0 * A * 16, s_rec, (uint32_t)n_valid * (A * 16u));
-      bulk_s2g(p.envrec + env0 * 4, s_env, (uint32_t)n_valid * 16u);
-      bulk_commit();
-    }
-  }
-  if (a == 0 && mine && (s_flag[lane] & FL_BITS_DIRTY)) {
-    fence_proxy_async_smem();
-    bulk_s2g(p.cellbits + env * BITS_WORDS, bits, BITS_WORDS * 4u);
-    bulk_commit();
-  }
-  if (OBS == 2) {
-    // ---- RGB: MultiGrid.render (base.py:301-331) of the tile's 32*A views from their tile-id maps.  Warp w expands views
-    // [32w, 32w+32), one row of V cells (8 pixel rows x V*24 bytes, contiguous in the image) at a time: every lane copies
-    // 8-byte pieces of tile rows from the atlas into the chunk buffer -- piece u of the chunk belongs to pixel row u / (3V),
-    // cell (u % 3V) / 3 --, then one bulk copy sends the chunk to HBM while the warp fills its other buffer.
-    constexpr int PIECES = V * 8 * 3, ITERS = (PIECES + 31) / 32;
-    uint32_t src_off[ITERS], cell_sel[ITERS];
-#pragma unroll
-    for (int i = 0; i < ITERS; ++i) {
-      const int u = lane + 32 * i, py = u / (3 * V), rem = u % (3 * V);
-      src_off[i] = (uint32_t)(py * 24 + (rem % 3) * 8);
-      cell_sel[i] = (uint32_t)(rem / 3);
-    }
-    const uint32_t atlas_s = smem_u32(s_atlas);
-    uint8_t* const bufs = s_out + SM::MAP_BYTES + a * (SM::NBUF * SM::CHUNK);
-    const int n_views = n_valid * A;
-    constexpr long long VIEW_BYTES = (long long)V * V * 192;
-    for (int v = 0; v < 32; ++v) {
-      const int vi = a * 32 + v;
-      if (vi >= n_views) break;
-      uint8_t* const dstv = p.obs + (env0 * A + vi) * VIEW_BYTES;
-#pragma unroll 1
-      for (int b = 0; b < V; ++b) {
-        uint8_t* const buf = bufs + chunk_parity * SM::CHUNK;
-        chunk_parity = (chunk_parity + 1) % SM::NBUF;
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(SM::NBUF - 1) : "memory");  // the copy that last read this buffer is done
-        __syncwarp();
-        const uint2 ids = *reinterpret_cast<const uint2*>(s_out + vi * (V * 8) + b * 8);  // the row's V tile ids
-#pragma unroll
-        for (int i = 0; i < ITERS; ++i) {
-          const int u = lane + 32 * i;
-          if (ITERS * 32 == PIECES || u < PIECES) {
-            const uint32_t t = __byte_perm(ids.x, ids.y, cell_sel[i]) & 0xFFu;
-            uint2 px;
-            asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(px.x), "=r"(px.y) : "r"(atlas_s + t * 192u + src_off[i]));
-            *reinterpret_cast<uint2*>(buf + 8 * u) = px;
-          }
-        }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          bulk_s2g(dstv + b * SM::CHUNK, buf, (uint32_t)SM::CHUNK);
-          bulk_commit();
-        }
-      }
-    }
-  }
-  }  // tile loop
-  bulk_wait_read0();  // the CTA's shared memory must outlive the reads
-}
-
-// ---------------------------------------------------------------------------------------------
-// launcher
-// ---------------------------------------------------------------------------------------------
-static int sm_count(int dev) {
-  static int cached[64] = {0};
-  if (!cached[dev & 63]) cudaDeviceGetAttribute(&cached[dev & 63], cudaDevAttrMultiProcessorCount, dev);
-  return cached[dev & 63];
-}
-
-static bool pdl_enabled() {  // MG_F2_PDL=0 turns programmatic dependent launch off (experiments)
-  static int v = -1;
-  if (v < 0) { const char* o = getenv("MG_F2_PDL"); v = (o && atoi(o) == 0) ? 0 : 1; }
-  return v != 0;
-}
-
-static int stages() {  // input stages of the persistent CTAs: 2 = prefetch the next tile (default), 1 = no prefetch
-  static int n = 0;
-  if (!n) { const char* o = getenv("MG_F2_STAGES"); n = (o && atoi(o) == 1) ? 1 : 2; }
-  return n;
-}
-
-template <int OBS, int V, int A, bool VO0, int NST>
-static int launch_one(const KP& p, cudaStream_t s) {
-  using SM = f2::Smem<OBS, V, A, NST>;
-  auto k = fused2_kernel<OBS, V, A, VO0, NST>;
-  const int smem_bytes = SM::TOTAL + (OBS == 2 ? (p.n_tiles + 1) * 192 : 0);  // OBS 2: + the tile atlas and the shadow tile
-  if (smem_bytes > 227 * 1024) return MG_E_UNSUPPORTED;
-  static int resident[64] = {0}, configured_smem[64] = {0};  // CTAs per SM of this instantiation, per device
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (!resident[dev & 63] || configured_smem[dev & 63] != smem_bytes) {
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-    if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);  // the kernel lives on shared memory, not on L1
-    if (e != cudaSuccess) return (int)e;
-    int n = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, 32 * A, smem_bytes);
-    if (e != cudaSuccess) return (int)e;
-    if (const char* o = getenv("MG_F2_CTAS_PER_SM")) n = std::min(n, std::max(1, atoi(o)));  // experiments
-    resident[dev & 63] = std::max(n, 1);
-    configured_smem[dev & 63] = smem_bytes;
-  }
-  const long long tiles = (p.B + ENVS_PER_CTA - 1) / ENVS_PER_CTA;
-  if (tiles <= 0) return 0;
-  if (tiles > 0x7FFFFFFF) return MG_E_ARG;
-  // as many CTAs as stay resident, trimmed so that every CTA gets the same number of tiles (no ragged last round)
-  const long long slots = (long long)resident[dev & 63] * sm_count(dev);
-  const long long rounds = (tiles + slots - 1) / slots;
-  const long long grid = getenv("MG_F2_RAGGED") ? std::min(tiles, slots) : (tiles + rounds - 1) / rounds;
-  if (getenv("MG_F2_VERBOSE")) fprintf(stderr, "fused2<OBS=%d,V=%d,A=%d,NST=%d>: %d CTAs/SM x %d SMs, %lld tiles in %lld rounds -> grid %lld, %d B shared\n", OBS, V, A, NST, resident[dev & 63], sm_count(dev), tiles, rounds, grid, smem_bytes);
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(32 * A); cfg.dynamicSmemBytes = (size_t)smem_bytes; cfg.stream = s;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
-  cfg.attrs = attr; cfg.numAttrs = 1;
-  const cudaError_t e = cudaLaunchKernelEx(&cfg, k, p, (int)tiles);
-  count_launch();
-  return (int)e;
-}
-
-template <int OBS, int V, bool VO0>
-static int launch_a(const KP& p, cudaStream_t s) {
-  // encoded observations: two input stages (the next tile is prefetched); RGB: the image expansion dwarfs everything else,
-  // one stage leaves more shared memory for resident CTAs
-  constexpr int NS = OBS == 1 ? 2 : 1;
-  if (OBS == 1 && stages() == 1) {
-    switch (p.A) {
-      case 1: return launch_one<1, V, 1, VO0, 1>(p, s);
-      case 2: return launch_one<1, V, 2, VO0, 1>(p, s);
-      case 3: return launch_one<1, V, 3, VO0, 1>(p, s);
-      case 4: return launch_one<1, V, 4, VO0, 1>(p, s);
-    }
-    return MG_E_UNSUPPORTED;
-  }
-  switch (p.A) {
-    case 1: return launch_one<OBS, V, 1, VO0, NS>(p, s);
-    case 2: return launch_one<OBS, V, 2, VO0, NS>(p, s);
-    case 3: return launch_one<OBS, V, 3, VO0, NS>(p, s);
-    case 4: return launch_one<OBS, V, 4, VO0, NS>(p, s);
-  }
-  return MG_E_UNSUPPORTED;
-}
+template <int OBS, int V>
+int launch_fused2_ov(const KP& p, cudaStream_t s);
+extern template int launch_fused2_ov<1, 7>(const KP&, cudaStream_t);
+extern template int launch_fused2_ov<1, 5>(const KP&, cudaStream_t);
+extern template int launch_fused2_ov<2, 7>(const KP&, cudaStream_t);
+extern template int launch_fused2_ov<2, 5>(const KP&, cudaStream_t);
 
 static bool al16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; }
 
-template <int OBS>
-static int launch_v(const KP& p, cudaStream_t s) {
-  const bool vo0 = p.vo == 0;
-  if (p.V == 7) return vo0 ? launch_a<OBS, 7, true>(p, s) : launch_a<OBS, 7, false>(p, s);
-  if (p.V == 5) return vo0 ? launch_a<OBS, 5, true>(p, s) : launch_a<OBS, 5, false>(p, s);
-  return MG_E_UNSUPPORTED;
-}
-
 int launch_fused2(const KP& p, int obs, cudaStream_t s) {
-  if (!fused_eligible(p)) return MG_E_UNSUPPORTED;
+  if (!fused_eligible(p) || p.A > 6 || (p.V != 7 && p.V != 5)) return MG_E_UNSUPPORTED;
   if (!al16(p.actions) || !al16(p.rewards) || !al16(p.done) || !al16(p.obs)) return MG_E_UNSUPPORTED;  // bulk copies need 16-byte alignment
-  if (obs == 1) return launch_v<1>(p, s);
+  if (obs == 1) return p.V == 7 ? launch_fused2_ov<1, 7>(p, s) : launch_fused2_ov<1, 5>(p, s);
   // RGB: tile size 8 (every registered env), rotation-equivariant atlas (one slot per tile), tile ids that fit a byte
-  if (obs == 2 && p.ts == 8 && p.orient_slots == 1 && p.n_tiles < 255 && al16(p.atlas)) return launch_v<2>(p, s);
+  if (obs == 2 && p.ts == 8 && p.orient_slots == 1 && p.n_tiles < 255 && al16(p.atlas))
+    return p.V == 7 ? launch_fused2_ov<2, 7>(p, s) : launch_fused2_ov<2, 5>(p, s);
   return MG_E_UNSUPPORTED;
 }
 
