@@ -143,7 +143,7 @@ def cpu_port_throughput(n_envs, threads, target_s=12.0, seed=1337):
     t0 = time.perf_counter()
     ob.rollout(act, n_steps=20)  # warm-up + probe
     probe = (time.perf_counter() - t0) / 20
-    n_steps = int(min(5000, max(100, target_s / max(probe, 1e-6))))
+    n_steps = int(min(50000, max(100, target_s / max(probe, 1e-6))))
     t0 = time.perf_counter()
     ob.rollout(act, n_steps=n_steps)
     dt = time.perf_counter() - t0

@@ -196,6 +196,21 @@ def test_rich_observation_dict_composition():
     assert set(compose_rich_obs(pov, agents, 9, 9, observe_rewards=False, observe_orientation=False)) == {"pov", "position"}
 
 
+def test_marlgrid_import_alias():
+    """compat/marlgrid: code written against the reference (`import marlgrid.envs`, README.md:29-36) resolves to this package."""
+    import subprocess
+    import sys
+
+    code = ("import marlgrid, marlgrid.envs, marlgrid.agents, marlgrid.base, marlgrid.objects;"
+            "from marlgrid.agents import GridAgentInterface;"
+            "assert marlgrid.envs.registered_envs[1] == 'MarlGrid-3AgentCluttered11x11-v0';"
+            "assert marlgrid.IndependentLearners is marlgrid.agents.IndependentLearners;"
+            "assert marlgrid.envs.ClutteredMultiGrid.__mro__[1] is marlgrid.base.MultiGridEnv; print('alias ok')")
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(ROOT, "compat"), ROOT]))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd="/")
+    assert out.returncode == 0 and "alias ok" in out.stdout, out.stderr
+
+
 def test_shard_ranges_partition_the_batch():
     from marlgrid_b200.sharding import shard_range
 
