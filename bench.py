@@ -344,6 +344,18 @@ def main():
     e1.record()
     barrier()
     warm_total_ms = e0.elapsed_time(e1)
+
+    # ---- the same K warm steps through the Python surface, env.step(actions) called in a Python loop -------------------
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for t in range(K):
+        env.step(actions[t % POOL])
+    e1.record()
+    host_issue_s = time.perf_counter() - t0  # time the host needed to enqueue K steps
+    barrier()
+    py_total_ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
     del fams[1:]
 
@@ -410,6 +422,8 @@ def main():
             "step_ms_flushed": {"min": srt[0], "median": srt[len(srt) // 2], "p99": srt[min(len(srt) - 1, int(0.99 * len(srt)))], "max": srt[-1], "steps": len(srt),
                                 "note": "secondary: single steps, 256 MiB L2 flush before each, per-step CUDA events (~2 us resolution)"},
             "warm": {"value": warm_value, "ms_per_step": warm_total_ms / K, "note": "K steps back to back, state L2-resident, launched from mg_rollout_fused"},
+            "python_api": {"value": world * B * K / (py_total_ms * 1e-3), "ms_per_step": py_total_ms / K, "host_issue_ms_per_step": 1e3 * host_issue_s / K,
+                           "note": "env.step(actions) in a Python loop on one family (rank 0's figures; host-bound when host_issue_ms_per_step ~ ms_per_step)"},
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": act_bytes, "d2h_bytes_per_step": obs_bytes + rew_bytes + B,
                     "steps": KE, "api": "mg_engine_step (C ABI, pinned host buffers, synchronous; batch cut into 4 env ranges whose D2H copies overlap the next range's kernel)", "checksum": e2e_checksum},
             "gpu_launches": int(launches),

@@ -85,6 +85,7 @@ class BatchedMultiGridEnv:
             assert at.shape[0] == n_tiles(cfg)
             self.atlas = torch.from_numpy(at).to(dev)
         self._state = MgState()
+        self._fast = None
         self.seed(seed)
         self._sync_state_struct()
         with torch.cuda.device(dev):
@@ -139,27 +140,47 @@ class BatchedMultiGridEnv:
             return self._observe()
 
     def _actions(self, actions):
-        a = torch.as_tensor(actions, device=self.device)
-        if a.dtype != torch.int32:
-            a = a.to(torch.int32)
-        a = a.reshape(self.num_envs, self.cfg.n_agents).contiguous()
+        a = actions
+        if not (torch.is_tensor(a) and a.dtype == torch.int32 and a.device == self.device and a.is_contiguous()
+                and a.numel() == self.num_envs * self.cfg.n_agents):
+            a = torch.as_tensor(actions, device=self.device)
+            if a.dtype != torch.int32:
+                a = a.to(torch.int32)
+            a = a.reshape(self.num_envs, self.cfg.n_agents).contiguous()
         return a
+
+    def _prepare_fast_step(self):
+        """Everything of a step call that does not change from step to step, resolved once: a Python loop around
+        env.step() is host-bound long before the 16 us kernel is (ctypes argument conversion, context managers)."""
+        L = self._lib
+        cfg, st = ctypes.byref(self.cfg), ctypes.byref(self._state)
+        rew, done, obs = ctypes.c_void_p(self.rewards.data_ptr()), ctypes.c_void_p(self.done.data_ptr()), ctypes.c_void_p(self.obs.data_ptr())
+        if self.obs_mode == "encoded":
+            fn = L.mg_step_fused
+            tail = (rew, done, obs)
+        else:
+            fn = L.mg_step_fused_rgb
+            tail = (rew, done, ctypes.c_void_p(self.atlas.data_ptr()), obs)
+        self._fast = (fn, cfg, st, tail, self.device.index)
 
     def step(self, actions):
         """One env.step for the whole batch (marlgrid/base.py:501-653) in a single kernel launch."""
-        with torch.cuda.device(self.device):
-            a = self._actions(actions)
-            cfg, st = ctypes.byref(self.cfg), ctypes.byref(self._state)
-            if self.obs_mode == "encoded":
-                rc = self._lib.mg_step_fused(cfg, st, a.data_ptr(), self.rewards.data_ptr(), self.done.data_ptr(), self.obs.data_ptr(),
-                                             int(self.autoreset), self._stream())
-            else:
-                rc = self._lib.mg_step_fused_rgb(cfg, st, a.data_ptr(), self.rewards.data_ptr(), self.done.data_ptr(),
-                                                 self.atlas.data_ptr(), self.obs.data_ptr(), int(self.autoreset), self._stream())
+        a = self._actions(actions)
+        fast = self._fast
+        if fast is None:
+            self._prepare_fast_step()
+            fast = self._fast
+        fn, cfg, st, tail, dev_index = fast
+        if torch.cuda.current_device() != dev_index:
+            with torch.cuda.device(self.device):
+                rc = fn(cfg, st, a.data_ptr(), *tail, self.autoreset, torch.cuda.current_stream(self.device).cuda_stream)
+        else:
+            rc = fn(cfg, st, a.data_ptr(), *tail, self.autoreset, torch.cuda.current_stream().cuda_stream)
+        if rc:
             _lib.check(rc, "mg_step_fused")
-            if self.check_errors_each_step:
-                self.check_errors()
-            return self.obs, self.rewards, self.done, {}
+        if self.check_errors_each_step:
+            self.check_errors()
+        return self.obs, self.rewards, self.done, {}
 
     def step_only(self, actions):
         """step without producing observations (mg_step); returns (rewards, done)."""
