@@ -53,7 +53,7 @@ __device__ __noinline__ void seq_reset(EnvCtx<32>& cref, unsigned long long g) {
 template <int OBS, int V, int A, int NST>
 struct Smem {
   static constexpr int E = ENVS_PER_CTA;
-  // OBS 1: the encoded observation tile.  OBS 2: per-view tile-id maps (V rows of 8 bytes) + per warp two image chunks
+  // OBS 1: the encoded observation tile.  OBS 2: per-view tile-id maps (V rows of 8 bytes) + per warp NBUF image chunks
   // (one row of V cells = 8 pixel rows of V*24 bytes) that bulk copies drain while the next chunk is being built.
   static constexpr int MAP_BYTES = E * A * V * 8;
   static constexpr int CHUNK = V * 8 * 24;
@@ -116,8 +116,7 @@ __device__ __forceinline__ void occlude_rows_vo0(const uint32_t (&T)[V], uint32_
     sweep_row<V>(M[j], T[j], nxt, ge_ax, left_src);
     M[j - 1] |= nxt;
   }
-  {  // row 0 is a sweep target only in the reference's loop bounds (j = ay+1 .. 1): nothing left to do
-  }
+  // (row 0 is only ever a sweep target: the reference's loop runs j = ay+1 .. 1)
 }
 
 // rows (one per register, V bits each) -> one byte per row of a 64-bit word: three byte permutes per four rows.  Bits of
@@ -240,7 +239,7 @@ __global__ void __launch_bounds__(32 * A, ctas_per_sm<OBS, V, A, NST>()) fused2_
   const long long env = env0 + lane;
   const int next_tile = tile + (int)gridDim.x;
   if (NST == 1 && it > 0) {  // single stage: the inputs can only be requested once the previous tile has drained
-    if (lane == 0) bulk_wait_read0();
+    if (lane == 0 || a == 0) bulk_wait_read0();  // every thread that issued bulk stores reading the stage (or the chunk buffers)
     __syncthreads();
     issue_load(tile, 0);
   }
