@@ -28,6 +28,13 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
+    if not os.path.exists(LIB_PATH) and int(os.environ.get("WORLD_SIZE", "1")) == 1:
+        try:  # a fresh checkout: compile the CUDA library in tree (nvcc cross-compiles sm_100a without a GPU)
+            from . import build as _build
+
+            _build.build()
+        except Exception:  # noqa: BLE001 -- reported below
+            pass
     if not os.path.exists(LIB_PATH):
         raise MarlgridLibraryError(
             f"{LIB_PATH} not found: the CUDA extension is not built. Run `python -c 'import __graft_entry__ as g; g.build()'` "
