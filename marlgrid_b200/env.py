@@ -194,6 +194,14 @@ class BatchedMultiGridEnv:
         with torch.cuda.device(self.device):
             return self._observe()
 
+    def render(self, index=0, mode="rgb_array", **kwargs):
+        """Whole-grid view of env `index` (marlgrid/base.py:714-795): uint8 image [H*32, W*32 + agent-view columns, 3].
+        Same keyword arguments as the reference (highlight, tile_size, show_agent_views, ...); there is no window: every
+        mode returns the array."""
+        from . import render as _render
+
+        return _render.render(self, index=index, **kwargs)
+
     def sync_derived(self):
         """Recompute the derived device state (occupancy bitboards, queue-head flags) after the planes or
         the agent records were edited from Python (e.g. `env.planes[...] = ...`)."""
@@ -355,6 +363,9 @@ class UnbatchedView:
 
     def reset(self, **kw):
         return self._per_agent(self.env.reset())
+
+    def render(self, mode="rgb_array", **kwargs):
+        return self.env.render(index=self.index, mode=mode, **kwargs)
 
     def step(self, actions):
         if self.env.num_envs != 1:

@@ -159,8 +159,61 @@ def gen_atlas():
         print(f"  atlas_ts{ts}.npz")
 
 
+class RenderRecorder(val.LockStep):
+    """Short runs that freeze the reference's whole-grid view env.render(mode='rgb_array') (base.py:714-795) after every event."""
+
+    def __init__(self, *a, **kw):
+        super().__init__(*a, **kw)
+        self.ev = []
+        rh.prewarm_tile_cache(32)  # TILE_PIXELS: the same cache-poisoning hazard as for the agent views (SURVEY.md A.5)
+
+    def _snap(self, kind, actions):
+        A = len(self.env.agents)
+        self.ev.append(dict(kind=kind, actions=np.zeros(A, np.int32) if actions is None else np.asarray(actions, np.int32),
+                            img=np.asarray(self.env.render(mode="rgb_array")).astype(np.uint8)))
+
+    def reset(self):
+        rh.ref_reset(self.env)
+        self.ob.reset()
+        self._snap(0, None)
+        self.compare("reset")
+
+    def step(self, actions, t):
+        d = super().step(actions, t)
+        self._snap(1, actions)
+        return d
+
+
+def gen_render():
+    """render_<scenario>.npz: event stream (0 = reset, 1 = step(actions)) + the reference's rendered frame after every event."""
+    rng = np.random.RandomState(77)
+    picks = {"3AgentCluttered11x11": 12, "4AgentEmpty9x9": 10, "Empty-offset1": 8, "Empty-seethrough": 6, "Goalcycle-demo-solo": 8, "Empty5x5x4-crowded": 45}
+    for k, sc in enumerate(s for s in val.SCENARIOS if s["name"] in picks):
+        sc = dict(sc)
+        name = sc.pop("name")
+        seed, env_index = 4242 + 5 * k, 77 * k + 1
+        rec = RenderRecorder(name, seed=seed, env_index=env_index, rgb=True, **sc)
+        rec.reset()
+        for t in range(picks[name]):
+            act = rng.randint(0, 7, size=len(rec.env.agents))
+            act[rng.rand(len(act)) < 0.5] = 2
+            if rec.step(act, t) is True:
+                rec.reset()
+        fname = "render_" + "".join(ch if ch.isalnum() else "_" for ch in name).strip("_") + ".npz"
+        np.savez_compressed(os.path.join(OUT, fname), meta=np.frombuffer(json.dumps(cfg_kwargs(rec.cfg, seed, env_index)).encode(), dtype=np.uint8),
+                            kind=np.array([e["kind"] for e in rec.ev], np.uint8), actions=np.stack([e["actions"] for e in rec.ev]),
+                            img=np.stack([e["img"] for e in rec.ev]))
+        print(f"  {fname:48s} {len(rec.ev)} frames {rec.ev[0]['img'].shape}")
+
+
 if __name__ == "__main__":
+    import sys
+
     os.makedirs(OUT, exist_ok=True)
-    gen_los()
-    gen_atlas()
-    gen_trajectories()
+    if "render" in sys.argv[1:]:
+        gen_render()
+    else:
+        gen_los()
+        gen_atlas()
+        gen_trajectories()
+        gen_render()

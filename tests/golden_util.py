@@ -12,6 +12,10 @@ def trajectory_files():
     return sorted(glob.glob(os.path.join(GOLDEN, "traj_*.npz")))
 
 
+def render_files():
+    return sorted(glob.glob(os.path.join(GOLDEN, "render_*.npz")))
+
+
 def load_traj(path):
     from marlgrid_b200.config import make_config
 

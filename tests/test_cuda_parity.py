@@ -8,7 +8,7 @@ import os
 import numpy as np
 import pytest
 
-from golden_util import load_los, load_traj, rank_from, trajectory_files
+from golden_util import render_files, load_los, load_traj, rank_from, trajectory_files
 
 pytestmark = pytest.mark.gpu
 
@@ -370,3 +370,41 @@ def test_rich_observation_style():
     lst = one.reset()
     assert isinstance(lst, list) and len(lst) == 2 and set(lst[0]) == {"pov", "reward", "position", "orientation"}
     assert tuple(lst[0]["pov"].shape) == (56, 56, 3) and tuple(lst[1]["position"].shape) == (2,)
+
+
+@pytest.mark.parametrize("path", render_files(), ids=lambda p: os.path.basename(p)[7:-4])
+def test_render_matches_reference_frames(path):
+    """env.render(): the reference's whole-grid view env.render(mode='rgb_array') (base.py:714-795), frame by frame."""
+    cfg, meta, z = load_traj(path)
+    env = _env(cfg, 1, seed=meta["seed"], env_offset=meta["env_index"], obs_mode="encoded", autoreset=False)
+    for i, kind in enumerate(z["kind"]):
+        if kind == 0:
+            env.reset()
+        else:
+            env.step(torch.from_numpy(z["actions"][i][None].astype(np.int32)).cuda())
+        img = env.render(0)
+        assert img.dtype == np.uint8 and img.shape == z["img"][i].shape and np.array_equal(img, z["img"][i]), f"frame {i}"
+    plain = env.render(0, highlight=False, show_agent_views=False)
+    assert plain.shape == (cfg.height * 32, cfg.width * 32, 3)
+
+
+def test_grid_recorder(tmp_path):
+    """GridRecorder (marlgrid/utils/video.py:55-154): frames of one env of a batch, exported at the next reset."""
+    from PIL import Image
+
+    from marlgrid_b200 import envs
+    from marlgrid_b200.utils.video import GridRecorder
+
+    env = GridRecorder(envs.make("MarlGrid-3AgentCluttered11x11-v0", num_envs=8, obs_mode="encoded", autoreset=False),
+                       save_root=str(tmp_path), max_steps=20, index=3)
+    env.recording = True
+    env.reset()
+    first = env.env.render(index=3)
+    for t in range(6):
+        env.step(env.random_actions(t))
+    assert env.ptr == 6 and np.array_equal(env.frames[0], first)
+    env.reset()
+    frames_dir = os.path.join(str(tmp_path), "frames_8")
+    assert sorted(os.listdir(frames_dir)) == sorted(f"frame_{k}.png" for k in range(7))
+    assert np.array_equal(np.asarray(Image.open(os.path.join(frames_dir, "frame_0.png"))), first)
+    assert any(f.startswith("video_8.") for f in os.listdir(str(tmp_path)))

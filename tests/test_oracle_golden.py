@@ -131,3 +131,48 @@ def test_oracle_threads_and_offsets_agree(oracle):
         assert np.array_equal(o1[32:48], o3) and np.array_equal(r1[32:48], r3) and np.array_equal(d1[32:48], d3)
     assert np.array_equal(full.grid, mt.grid) and np.array_equal(full.agents, mt.agents) and np.array_equal(full.envrec, mt.envrec)
     assert full.envrec[:, 1].min() >= 2  # episodes really rolled over
+
+
+def test_render_composition_against_reference_frames(oracle):
+    """The host-side composition of marlgrid_b200/render.py (tile lookup, highlight, agent-view columns) against the frames
+    the reference rendered; its two GPU inputs -- line-of-sight masks and the agents' RGB views -- come from the oracle here."""
+    import glob
+    import json
+
+    import torch
+
+    from marlgrid_b200 import render as R
+    from marlgrid_b200.atlas import build_atlas
+    from marlgrid_b200.config import make_config
+
+    class HostEnv:  # what render() reads from an env
+        def __init__(self, cfg, ob):
+            self.cfg, self.ob, self.obs_mode, self.atlas = cfg, ob, "encoded", None
+
+        planes = property(lambda self: torch.from_numpy(self.ob.planes().copy()))
+        agents = property(lambda self: torch.from_numpy(self.ob.agents.copy()))
+
+    def views(env, index=0):
+        c = env.cfg
+        return env.ob.obs_rgb(build_atlas([int(x) for x in c.agent_color[: c.n_agents]], c.view_tile_size, c.n_static_kinds))[index]
+
+    saved = R.visibility_masks, R.agent_views_rgb
+    R.visibility_masks, R.agent_views_rgb = (lambda env, index=0: env.ob.vis()[index] != 0), views
+    try:
+        files = sorted(glob.glob(os.path.join(GOLDEN, "render_*.npz")))
+        assert len(files) >= 6
+        for path in files:
+            z = np.load(path)
+            meta = json.loads(bytes(z["meta"]).decode())
+            cfg = make_config(**meta["config"])
+            ob = oracle.OracleBatch(cfg, 1, seed=meta["seed"], env_offset=meta["env_index"])
+            env = HostEnv(cfg, ob)
+            for i, kind in enumerate(z["kind"]):
+                if kind == 0:
+                    ob.reset()
+                else:
+                    ob.step(z["actions"][i][None].astype(np.int32), autoreset=False)
+                if i % 3 == 0 or i == len(z["kind"]) - 1:
+                    assert np.array_equal(R.render(env, 0), z["img"][i]), f"{os.path.basename(path)} frame {i}"
+    finally:
+        R.visibility_masks, R.agent_views_rgb = saved
