@@ -112,6 +112,9 @@ typedef struct MgConfig {
   int32_t spawn_delay[MG_MAX_AGENTS];  /* agents.py:34 */
   uint8_t n_static_kinds;    /* RGB: number of distinct static tile kinds in the atlas (excl. empty) */
   uint8_t kind_of_type[15];  /* RGB: type index -> atlas kind (0 = none/empty, 0xFF = undefined render) */
+  uint32_t hide_types;       /* GridAgentInterface.hide_item_types (agents.py:30, base.py:441-449) as a bit set over the type
+                                indices (bit MG_T_AGENT = 'Agent'): objects of these types are masked out of every agent's
+                                observation (after the line of sight has been computed with them in place) */
 } MgConfig;
 
 /* Device pointers of the SoA world state (caller-owned, e.g. torch tensors). */

@@ -44,8 +44,6 @@ class GridAgentInterface:
             raise ValueError(f"{type(self).__name__} kwarg 'observation_style' must be one of 'image', 'rich'.")  # agents.py:78
         if color not in COLOR_TO_IDX:
             raise ValueError(f"unknown colour {color!r}")
-        if len(hide_item_types) > 0:
-            raise NotImplementedError("hide_item_types (marlgrid/base.py:441-449) is not on the batched hot path yet")
         self.view_size = view_size
         self.view_tile_size = view_tile_size
         self.view_offset = view_offset

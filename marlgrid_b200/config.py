@@ -41,6 +41,7 @@ class MgConfig(ctypes.Structure):
         ("spawn_delay", ctypes.c_int32 * MG_MAX_AGENTS),
         ("n_static_kinds", ctypes.c_uint8),
         ("kind_of_type", ctypes.c_uint8 * 15),
+        ("hide_types", ctypes.c_uint32),
     ]
 
     def describe(self):
@@ -85,6 +86,7 @@ def make_config(
     bonus_initial_reward=True,
     bonus_reset_on_mistake=False,
     spawn_delay=None,
+    hide_types=0,
 ):
     n_agents = len(agent_colors)
     if not (1 <= n_agents <= MG_MAX_AGENTS):
@@ -124,6 +126,7 @@ def make_config(
     cfg.kind_of_type[T_GOAL] = 2
     cfg.kind_of_type[T_BONUS] = 3
     cfg.n_static_kinds = 3
+    cfg.hide_types = int(hide_types)
     return cfg
 
 

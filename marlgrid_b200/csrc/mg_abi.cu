@@ -26,7 +26,7 @@ static KP make_kp(const MgConfig* c, const MgState* st) {
   memset(&p, 0, sizeof p);
   p.W = c->width; p.H = c->height; p.A = c->n_agents; p.V = c->view_size; p.vo = c->view_offset; p.ts = c->view_tile_size;
   p.max_steps = c->max_steps; p.n_clutter = c->n_clutter; p.n_bonus = c->n_bonus_tiles; p.goal_mode = c->goal_mode;
-  p.flags = c->flags; p.S = c->plane_stride;
+  p.flags = c->flags; p.S = c->plane_stride; p.hide = c->hide_types;
   p.goal_reward = c->goal_reward; p.bonus_reward = c->bonus_reward; p.bonus_penalty = c->bonus_penalty;
   for (int i = 0; i < MG_MAX_AGENTS; ++i) { p.agent_color[i] = c->agent_color[i]; p.spawn_delay[i] = c->spawn_delay[i]; }
   for (int i = 0; i < 15; ++i) p.kind_of_type[i] = c->kind_of_type[i];

@@ -49,6 +49,7 @@ struct KP {
   int autoreset;
   int n_tiles;       // atlas tiles (without the appended shadow tile)
   int orient_slots;  // 1: atlas is rotation-equivariant (dir remap), 4: one slot per view orientation
+  uint32_t hide;     // MgConfig.hide_types
   uint32_t wall_enc; // MG_T_WALL | MG_C_WORST << 8: the encoded canonical wall, as run-time data (see mg_fused2.cu)
 };
 

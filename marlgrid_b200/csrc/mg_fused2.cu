@@ -14,7 +14,7 @@ extern template int launch_fused2_ov<2, 5>(const KP&, cudaStream_t);
 static bool al16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; }
 
 int launch_fused2(const KP& p, int obs, cudaStream_t s) {
-  if (!fused_eligible(p) || p.A > 6 || (p.V != 7 && p.V != 5)) return MG_E_UNSUPPORTED;
+  if (!fused_eligible(p) || p.A > 6 || (p.V != 7 && p.V != 5) || p.hide != 0u) return MG_E_UNSUPPORTED;  // hide_item_types: general kernels
   if (!al16(p.actions) || !al16(p.rewards) || !al16(p.done) || !al16(p.obs)) return MG_E_UNSUPPORTED;  // bulk copies need 16-byte alignment
   if (obs == 1) return p.V == 7 ? launch_fused2_ov<1, 7>(p, s) : launch_fused2_ov<1, 5>(p, s);
   // RGB: tile size 8 (every registered env), rotation-equivariant atlas (one slot per tile), tile ids that fit a byte

@@ -261,6 +261,74 @@ __device__ __forceinline__ void obs_prepare(const KP& p, const ObsSmem<V>& o, in
   }
 }
 
+// hide_item_types (agents.py:30, base.py:441-449): after the line of sight has been computed on the real grid, every cell
+// of the view whose object `item` (the static object, else the head of the agent queue) is not the observer itself and has
+// a hidden type shows `item.agents[0]` instead -- for a static object the queue head, for a head agent the second in the
+// queue -- or nothing.  The replacement is a bare agent: no blending with the object underneath, no "own tile on top"
+// (render_tile base.py:282-293 looks at the replaced object's own, empty, `agents`).  Rarely used, so written as a plain
+// loop over the view cells that follows the reference cell by cell; the fast paths never come here.
+template <int OBS, int V>
+__device__ __noinline__ void obs_view_hidden(const KP& p, const ObsSmem<V>& o, int view, int a, long long env, const uint32_t* __restrict__ rec,
+                                             const uint8_t* __restrict__ tp, const ViewGeom& g, const PackedView& pv, int orient) {
+  constexpr int VV = V * V;
+  const int A = p.A, S = p.S, W = p.W, H = p.H, per_kind = 1 + 4 * A;
+  const uint32_t w0 = rec[a * 4];
+  bool bad = false;
+  for (int vb = 0; vb < V; ++vb)
+    for (int va = 0; va < V; ++va) {
+      const bool vis = pv.visible(va, vb);
+      const int u = g.flip ? V - 1 - vb : vb, v = g.rev ? V - 1 - va : va;
+      const int wx = g.topX + (g.vertical ? v : u), wy = g.topY + (g.vertical ? u : v);
+      int type = 0, colour = 0, state = 0, head = -1, second = -1;
+      if (vis && (unsigned)wx < (unsigned)W && (unsigned)wy < (unsigned)H) {
+        const int idx = wx * H + wy;
+        type = tp[idx]; colour = tp[S + idx]; state = tp[2 * S + idx];
+        uint32_t hs = 0, ss = 0;
+        for (int q = 0; q < A; ++q) {  // the cell's queue: placed agents in stamp order
+          const uint32_t v0 = rec[q * 4];
+          if (!((v0 >> 24) & MG_AF_PLACED) || (int)(v0 & 0xFFu) != wx || (int)((v0 >> 8) & 0xFFu) != wy) continue;
+          const uint32_t st = rec[q * 4 + 2];
+          if (head < 0 || st < hs) { second = head; ss = hs; head = q; hs = st; }
+          else if (second < 0 || st < ss) { second = q; ss = st; }
+        }
+      }
+      const bool on_cell = ((w0 & 0xFFu) == (uint32_t)wx) && (((w0 >> 8) & 0xFFu) == (uint32_t)wy);
+      // what the cell shows after hiding: the static object, an agent as the cell's object, or nothing
+      bool show_static = false, replaced = false;
+      int ag = -1;
+      if (type != MG_T_EMPTY) {
+        if ((p.hide >> type) & 1u) { replaced = true; ag = head; }             // grid.set(i, j, item.agents[0]) / None, base.py:446-449
+        else show_static = true;
+      } else if (head >= 0) {
+        if (((p.hide >> MG_T_AGENT) & 1u) && head != a) { replaced = true; ag = second; }  // `item is not agent`: the observer never hides itself
+        else ag = head;
+      }
+      if (OBS == 1) {
+        if (!vis) continue;  // the staging tile is zero-filled
+        uint8_t* oo = o.out + view * (VV * 3) + va * (V * 3) + vb * 3;
+        if (show_static) { oo[0] = (uint8_t)type; oo[1] = (uint8_t)colour; oo[2] = (uint8_t)state; }
+        else if (ag >= 0) { oo[0] = MG_T_AGENT; oo[1] = p.agent_color[ag]; oo[2] = (uint8_t)((rec[ag * 4] >> 16) & 3u); }
+      } else {
+        uint8_t t = (uint8_t)p.n_tiles;  // shadow
+        if (vis) {
+          t = 0;
+          int q = -1;
+          if (show_static) {
+            const int kind = p.kind_of_type[type];
+            if (kind == 0xFF) bad = true; else t = (uint8_t)(kind * per_kind);
+            if (head >= 0) q = on_cell ? a : head;             // the observer's own tile if it stands there, else agents[0] (base.py:289-293)
+          } else if (ag >= 0) q = (!replaced && on_cell) ? a : ag;  // base.py:282-285; a replacement has no agents of its own
+          if (q >= 0) {
+            const int qd = (int)((rec[q * 4] >> 16) & 3u);
+            t = (uint8_t)(t + 1 + 4 * q + ((p.orient_slots == 4) ? qd : ((qd + orient) & 3)));
+          }
+        }
+        o.tile[view * VV + vb * V + va] = t;
+      }
+    }
+  if (OBS == 2 && bad) atomicOr(reinterpret_cast<unsigned int*>(p.envrec) + env * 4 + 3, (unsigned int)MG_ERR_RENDER << 16);
+}
+
 // one agent view: gen_obs_grid + encode / tile ids.  rec = the env's agent records [q*4 + w] in shared memory,
 // tp = the env's byte planes (global memory on the bit-plane path, shared memory on the byte path)
 template <int OBS, int V, bool BITS, bool HEADS = false>
@@ -296,6 +364,10 @@ __device__ __forceinline__ void obs_view(const KP& p, const ObsSmem<V>& o, int v
   if (!active) return;
   const ViewGeom g = view_geom(px, py, dir, V, p.vo, p.W, p.H);
   const PackedView pv = view_masks<V, BITS>(p, tp, bits, g);
+  if (p.hide != 0u) {  // hide_item_types: the cell-by-cell variant (reads the byte planes)
+    obs_view_hidden<OBS, V>(p, o, view, a, env, rec, tp, g, pv, orient);
+    return;
+  }
   if (OBS == 1) {
     uint8_t* out = o.out + view * (VV * 3);
     if (BITS) {

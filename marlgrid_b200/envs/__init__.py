@@ -13,6 +13,7 @@ import sys
 
 from ..agents import GridAgentInterface
 from ..config import GOAL_FIXED, GOAL_NONE, GOAL_RANDOM, make_config
+from ..objects import hide_mask
 from ..env import BatchedMultiGridEnv, compose_rich_obs
 
 this_module = sys.modules[__name__]
@@ -60,6 +61,8 @@ class MultiGridEnv(BatchedMultiGridEnv):
         if not self.agent_interfaces:
             raise ValueError("a batched MarlGrid env needs at least one agent")
         ai = self.agent_interfaces
+        if len({tuple(sorted(a.hide_item_types)) for a in ai}) != 1:
+            raise ValueError("all agents of a batched env must share hide_item_types (one mask per env family)")
         for field in ("view_size", "view_tile_size", "view_offset", "see_through_walls", "observation_style", "observe_rewards",
                       "observe_position", "observe_orientation"):
             if len({getattr(a, field) for a in ai}) != 1:
@@ -71,6 +74,7 @@ class MultiGridEnv(BatchedMultiGridEnv):
             view_size=ai[0].view_size, view_offset=ai[0].view_offset, view_tile_size=ai[0].view_tile_size,
             max_steps=max_steps, ghost_mode=ghost_mode, respawn=respawn, reward_decay=reward_decay,
             see_through_walls=ai[0].see_through_walls, spawn_delay=[a.spawn_delay for a in ai],
+            hide_types=hide_mask(ai[0].hide_item_types),
             **self._scenario(),
         )
         super().__init__(cfg, num_envs=num_envs, device=device, seed=seed, env_offset=env_offset, obs_mode=obs_mode,

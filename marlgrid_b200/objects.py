@@ -57,3 +57,17 @@ def see_behind(type_idx, state=0):
     if type_idx == T_DOOR:
         return state == DOOR_OPEN
     return True
+
+
+def hide_mask(type_names):
+    """GridAgentInterface.hide_item_types (a list of WorldObj.type strings, agents.py:30; 'Agent' for agents,
+    objects.py:137-138) -> the MgConfig.hide_types bit set over type indices."""
+    mask = 0
+    for name in type_names:
+        if name == "Agent":
+            mask |= 1 << T_AGENT
+        elif name in TYPE_TO_IDX:
+            mask |= 1 << TYPE_TO_IDX[name]
+        else:
+            raise ValueError(f"unknown object type {name!r} in hide_item_types")
+    return mask

@@ -104,14 +104,22 @@ def cfg_kwargs(cfg, seed, env_index):
             see_through_walls=bool(cfg.flags & F_SEE_THROUGH), goal_reward=cfg.goal_reward, bonus_reward=cfg.bonus_reward,
             bonus_penalty=cfg.bonus_penalty, bonus_initial_reward=bool(cfg.flags & F_BONUS_INITIAL),
             bonus_reset_on_mistake=bool(cfg.flags & F_BONUS_RESET), spawn_delay=[int(s) for s in cfg.spawn_delay[: cfg.n_agents]],
+            hide_types=int(cfg.hide_types),
         ),
     )
 
 
-def gen_trajectories():
+def gen_trajectories(only=None):
+    """only: substring filter on the scenario name (the RNG / seed schedule of the other scenarios is unchanged: scenarios
+    added later get their own stream below)."""
     rng = np.random.RandomState(2024)
     k = 0
     for sc in val.SCENARIOS + val.INTERACTIVE[:3]:
+        if "hide" in sc["name"]:  # added after the first fixtures were frozen: own stream, so the older files stay reproducible
+            continue
+        if only is not None and only not in sc["name"]:
+            k += 1
+            continue
         sc = dict(sc)
         name = sc.pop("name")
         interactive = sc.pop("interactive", False)
@@ -124,6 +132,20 @@ def gen_trajectories():
             rec.inject = val.inject_interactive
             rec.with_box = with_box
         rec.run(episodes=3, steps=rec.cfg.max_steps + 3, rng=rng, p_forward=0.35 if interactive else 0.5)
+        fname = "traj_" + "".join(ch if ch.isalnum() else "_" for ch in name).strip("_") + ".npz"
+        n = rec.save(fname, cfg_kwargs(rec.cfg, seed, env_index))
+        print(f"  {fname:48s} {n} events; {rec.events}")
+
+
+def gen_hide_trajectories():
+    """hide_item_types scenarios (base.py:441-449), recorded with their own RNG stream."""
+    rng = np.random.RandomState(4048)
+    for k, sc in enumerate(s for s in val.SCENARIOS if "hide" in s["name"]):
+        sc = dict(sc)
+        name = sc.pop("name")
+        seed, env_index = 7001 + 13 * k, 500 * k + 9
+        rec = Recorder(name, seed=seed, env_index=env_index, rgb=True, **sc)
+        rec.run(episodes=3, steps=rec.cfg.max_steps + 3, rng=rng, p_forward=0.5)
         fname = "traj_" + "".join(ch if ch.isalnum() else "_" for ch in name).strip("_") + ".npz"
         n = rec.save(fname, cfg_kwargs(rec.cfg, seed, env_index))
         print(f"  {fname:48s} {n} events; {rec.events}")
@@ -212,8 +234,11 @@ if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     if "render" in sys.argv[1:]:
         gen_render()
+    elif "hide" in sys.argv[1:]:
+        gen_hide_trajectories()
     else:
         gen_los()
         gen_atlas()
         gen_trajectories()
+        gen_hide_trajectories()
         gen_render()

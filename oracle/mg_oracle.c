@@ -141,6 +141,17 @@ static int queue_head(const Env* v, int x, int y) {
   return best;
 }
 
+/* the agent right behind `head` in the queue of (x,y): the reference's head.agents[0] / static_obj.agents[1]; -1 if none */
+static int queue_second(const Env* v, int x, int y, int head) {
+  int best = -1; int32_t bs = 0;
+  for (int a = 0; a < v->c->n_agents; ++a)
+    if (a != head && (AFL(v, a) & MG_AF_PLACED) && AX(v, a) == x && AY(v, a) == y) {
+      int32_t s = get_stamp(v, a);
+      if (best < 0 || s < bs) { best = a; bs = s; }
+    }
+  return best;
+}
+
 /* base.py:664-688 try_place_obj.  agent >= 0: placing that agent; else placing a static triple. */
 static int try_place(Env* v, int x, int y, int agent, int type, int colour, int state) {
   const MgConfig* c = v->c;
@@ -349,7 +360,8 @@ static void occlude_mask(const uint8_t* grid /* [V][V] transparent, [i][j] */, i
   }
 }
 
-typedef struct { uint8_t type, colour, state; int8_t head; /* queue head agent or -1 */ uint8_t has_obs; } ViewCell;
+typedef struct { uint8_t type, colour, state; int8_t head; /* queue head agent or -1 */ uint8_t has_obs;
+                 int8_t second; /* agent behind the head or -1 */ uint8_t replaced; /* hide_item_types put agents[0] here */ } ViewCell;
 
 /* base.py:418-451 gen_obs_grid: slice (base.py:123-147) + rotate_grid (base.py:67-80) + opacity (103-106)
  * + process_vis (agents.py:290-295).  Fills cells[V*V] ([a][b]) and vis[V*V]; returns 0 if inactive. */
@@ -364,12 +376,13 @@ static int gen_obs_grid(const Env* v, int a, ViewCell* cells, uint8_t* vis) {
   else { topX = px - h; topY = py - V + 1 + o; }               /* agents.py:257-259 */
   ViewCell sub[MG_MAX_VIEW * MG_MAX_VIEW];
   for (int sx = 0; sx < V; ++sx) for (int sy = 0; sy < V; ++sy) { /* slice: zero padded */
-    ViewCell cell = {0, 0, 0, -1, 0};
+    ViewCell cell = {0, 0, 0, -1, 0, -1, 0};
     int wx = topX + sx, wy = topY + sy;
     if (wx >= 0 && wy >= 0 && wx < W && wy < H) {
       int idx = wx * H + wy;
       cell.type = v->type[idx]; cell.colour = v->colour[idx]; cell.state = v->state[idx];
       cell.head = (int8_t)queue_head(v, wx, wy);
+      cell.second = (int8_t)(cell.head >= 0 ? queue_second(v, wx, wy, cell.head) : -1);
       cell.has_obs = (uint8_t)(AX(v, a) == wx && AY(v, a) == wy); /* the observer itself stands on this cell */
     }
     sub[sx * V + sy] = cell;
@@ -388,6 +401,19 @@ static int gen_obs_grid(const Env* v, int a, ViewCell* cells, uint8_t* vis) {
   }
   if (c->flags & MG_F_SEE_THROUGH) memset(vis, 1, (size_t)V * V); /* agents.py:294-295 */
   else occlude_mask(transp, V, V / 2, V - 1 - o, vis);           /* agents.py:233-234,293 */
+  if (c->hide_types) { /* base.py:441-449: objects of hidden types are replaced by item.agents[0] (or nothing) */
+    for (int i = 0; i < V * V; ++i) {
+      ViewCell* cc = &cells[i];
+      if (cc->type != MG_T_EMPTY) { /* item = the static object; item.agents = the whole queue */
+        if ((c->hide_types >> cc->type) & 1u) {
+          cc->type = MG_T_EMPTY; cc->colour = 0; cc->state = 0; cc->replaced = 1; /* head (if any) becomes the cell object */
+          cc->second = -1;
+        }
+      } else if (cc->head >= 0 && cc->head != a && ((c->hide_types >> MG_T_AGENT) & 1u)) { /* item = the head agent, not the observer */
+        cc->head = cc->second; cc->second = -1; cc->replaced = 1;
+      }
+    }
+  }
   return 1;
 }
 
@@ -438,7 +464,8 @@ static void obs_rgb_env(Env* v, const uint8_t* atlas, uint8_t* obs) {
         if (kind == 0xFF) { add_err(v, MG_ERR_RENDER); kind = 0; }
       }
       int q = -1;
-      if (cc->head >= 0) q = cc->has_obs ? a : cc->head; /* base.py:282-293: top_agent if it is on this cell, else queue head */
+      if (cc->head >= 0) q = (cc->has_obs && !cc->replaced) ? a : cc->head; /* base.py:282-293: top_agent if it is on this cell, else queue
+                                                                               head; a hide_item_types replacement has no agents of its own */
       int t = tile_index(c, kind, q, q >= 0 ? (ADIR(v, q) & 3) : 0);
       const uint8_t* tile = atlas + ((size_t)t * 4 + orient) * tile_bytes;
       for (int y = 0; y < ts; ++y) memcpy(img + (size_t)(vb * ts + y) * row + (size_t)va * ts * 3, tile + (size_t)y * ts * 3, (size_t)ts * 3);

@@ -13,7 +13,7 @@ import numpy as np
 
 from marlgrid_b200 import atlas as product_atlas
 from marlgrid_b200.config import GOAL_FIXED, GOAL_NONE, GOAL_RANDOM, make_config
-from marlgrid_b200.objects import COLOR_TO_IDX
+from marlgrid_b200.objects import COLOR_TO_IDX, hide_mask
 
 from . import mg_oracle as mo
 from . import philox as px
@@ -32,6 +32,7 @@ def config_from_ref_env(env):
         max_steps=env.max_steps, ghost_mode=bool(env.ghost_mode), respawn=bool(env.respawn),
         reward_decay=bool(env.reward_decay), see_through_walls=bool(ag[0].see_through_walls),
         spawn_delay=[a.spawn_delay for a in ag],
+        hide_types=hide_mask(getattr(ag[0], "hide_item_types", [])),
     )
     if "ClutteredGoalCycleEnv" in names:
         kw.update(goal_mode=GOAL_NONE, n_clutter=env.n_clutter, n_bonus_tiles=env.n_bonus_tiles,
@@ -213,6 +214,8 @@ SCENARIOS = [
     dict(name="Empty-seethrough", env_class="EmptyMultiGrid", agents=agents_cfg(2, see_through_walls=True), grid_size=8),
     dict(name="Empty-respawn", env_class="EmptyMultiGrid", agents=agents_cfg(3), grid_size=5, respawn=True, max_steps=60),
     dict(name="Empty-spawndelay", env_class="EmptyMultiGrid", agents=[dict(color="red", view_size=7, view_tile_size=8), dict(color="blue", view_size=7, view_tile_size=8, spawn_delay=3), dict(color="purple", view_size=7, view_tile_size=8, spawn_delay=7)], grid_size=6, max_steps=40),
+    dict(name="Cluttered-hide-walls", env_class="ClutteredMultiGrid", agents=agents_cfg(3, hide_item_types=["Wall"]), grid_size=8, n_clutter=6, max_steps=40),
+    dict(name="Empty-hide-goal-agents", env_class="EmptyMultiGrid", agents=agents_cfg(4, hide_item_types=["Goal", "Agent"]), grid_size=5, max_steps=50),
     dict(name="Goalcycle-demo-solo", env_id="Goalcycle-demo-solo-v0"),
     dict(name="Goalcycle-3agents", env_class="ClutteredGoalCycleEnv", agents=agents_cfg(3, view_offset=1), grid_size=9, clutter_density=0.1, n_bonus_tiles=3, penalty=-1.5, respawn=True, max_steps=80),
     dict(name="Goalcycle-noinit-reset", env_class="ClutteredGoalCycleEnv", agents=agents_cfg(2), grid_size=7, n_clutter=2, n_bonus_tiles=4, penalty=0.25, reward=2, initial_reward=False, reset_on_mistake=True, max_steps=80),
