@@ -22,8 +22,7 @@
 //          OBS 2: MultiGrid.render (base.py:301-331) at tile size 8.  The view threads write tile ids; the warps then copy
 //                 tile rows from the atlas (shared memory) into chunk buffers that bulk copies stream to HBM.
 // Everything here is integer work on the ALU/LSU pipes; the path has no dense contraction, hence no tensor cores.
-// Launch-shape knobs for experiments (read once): MG_F2_STAGES=1, MG_F2_CTAS_PER_SM=n, MG_F2_PDL=0, MG_F2_RAGGED=1,
-// MG_F2_VERBOSE=1.
+// Launch-shape knobs for experiments: MG_F2_CTAS_PER_SM=n, MG_F2_PDL=0, MG_F2_RAGGED=1, MG_F2_VERBOSE=1.
 #pragma once
 #include <cstdlib>
 
@@ -724,12 +723,6 @@ static inline bool pdl_enabled() {  // MG_F2_PDL=0 turns programmatic dependent 
   return v != 0;
 }
 
-static inline int stages() {  // input stages of the persistent CTAs: 2 = prefetch the next tile (default), 1 = no prefetch
-  static int n = 0;
-  if (!n) { const char* o = getenv("MG_F2_STAGES"); n = (o && atoi(o) == 1) ? 1 : 2; }
-  return n;
-}
-
 template <int OBS, int V, int A, bool VO0, int NST>
 static int launch_one(const KP& p, cudaStream_t s) {
   using SM = f2::Smem<OBS, V, A, NST>;
@@ -775,15 +768,6 @@ static int launch_a(const KP& p, cudaStream_t s) {
   // encoded observations: two input stages (the next tile is prefetched); RGB: the image expansion dwarfs everything else,
   // one stage leaves more shared memory for resident CTAs
   constexpr int NS = OBS == 1 ? 2 : 1;
-  if (OBS == 1 && stages() == 1) {
-    switch (p.A) {
-      case 1: return launch_one<1, V, 1, VO0, 1>(p, s);
-      case 2: return launch_one<1, V, 2, VO0, 1>(p, s);
-      case 3: return launch_one<1, V, 3, VO0, 1>(p, s);
-      case 4: return launch_one<1, V, 4, VO0, 1>(p, s);
-    }
-    return MG_E_UNSUPPORTED;  // (the single-stage knob exists for the common shapes only)
-  }
   switch (p.A) {
     case 1: return launch_one<OBS, V, 1, VO0, NS>(p, s);
     case 2: return launch_one<OBS, V, 2, VO0, NS>(p, s);
