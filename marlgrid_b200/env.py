@@ -49,7 +49,7 @@ class BatchedMultiGridEnv:
     metadata = {}
 
     def __init__(self, cfg, num_envs=1, device="cuda", seed=1337, env_offset=0, obs_mode="encoded", autoreset=True,
-                 check_errors=False):
+                 check_errors=False, obs_buffers=2):
         if not isinstance(cfg, MgConfig):
             raise TypeError("cfg must be a marlgrid_b200.config.MgConfig")
         if obs_mode not in ("encoded", "rgb"):
@@ -76,11 +76,18 @@ class BatchedMultiGridEnv:
         self.cellbits = torch.empty((B, 44), dtype=torch.int32, device=dev)  # derived bit-planes (include/marlgrid_b200.h)
         self.rewards = torch.zeros((B, A), dtype=torch.float64, device=dev)
         self.done = torch.zeros((B,), dtype=torch.bool, device=dev)  # the kernels write 0/1 bytes: no conversion pass per step
+        # The observation tensor returned by step() is a view of a device buffer.  With obs_buffers = 2 (default) steps
+        # alternate between two buffers, so the previous step's observation stays valid while the next one exists -- the
+        # reference's `save_step(obs, act, next_obs, ...)` pattern works without copies; obs_buffers = 1 halves the memory.
+        if obs_buffers not in (1, 2):
+            raise ValueError("obs_buffers must be 1 or 2")
+        obs_shape = (B, A, V, V, 3) if obs_mode == "encoded" else (B, A, V * ts, V * ts, 3)
+        self._obs_bufs = [torch.zeros(obs_shape, dtype=torch.uint8, device=dev) for _ in range(obs_buffers)]
+        self._obs_idx = 0
+        self.obs = self._obs_bufs[0]
         if obs_mode == "encoded":
-            self.obs = torch.zeros((B, A, V, V, 3), dtype=torch.uint8, device=dev)
             self.atlas = None
         else:
-            self.obs = torch.zeros((B, A, V * ts, V * ts, 3), dtype=torch.uint8, device=dev)
             at = _atlas.build_atlas([int(c) for c in cfg.agent_color[:A]], ts, cfg.n_static_kinds)
             assert at.shape[0] == n_tiles(cfg)
             self.atlas = torch.from_numpy(at).to(dev)
@@ -154,14 +161,13 @@ class BatchedMultiGridEnv:
         env.step() is host-bound long before the 16 us kernel is (ctypes argument conversion, context managers)."""
         L = self._lib
         cfg, st = ctypes.byref(self.cfg), ctypes.byref(self._state)
-        rew, done, obs = ctypes.c_void_p(self.rewards.data_ptr()), ctypes.c_void_p(self.done.data_ptr()), ctypes.c_void_p(self.obs.data_ptr())
-        if self.obs_mode == "encoded":
-            fn = L.mg_step_fused
-            tail = (rew, done, obs)
-        else:
-            fn = L.mg_step_fused_rgb
-            tail = (rew, done, ctypes.c_void_p(self.atlas.data_ptr()), obs)
-        self._fast = (fn, cfg, st, tail, self.device.index)
+        rew, done = ctypes.c_void_p(self.rewards.data_ptr()), ctypes.c_void_p(self.done.data_ptr())
+        tails = []
+        for buf in self._obs_bufs:  # one argument tail per observation buffer
+            obs = ctypes.c_void_p(buf.data_ptr())
+            tails.append((rew, done, obs) if self.obs_mode == "encoded" else (rew, done, ctypes.c_void_p(self.atlas.data_ptr()), obs))
+        fn = L.mg_step_fused if self.obs_mode == "encoded" else L.mg_step_fused_rgb
+        self._fast = (fn, cfg, st, tails, self.device.index)
 
     def step(self, actions):
         """One env.step for the whole batch (marlgrid/base.py:501-653) in a single kernel launch."""
@@ -170,7 +176,10 @@ class BatchedMultiGridEnv:
         if fast is None:
             self._prepare_fast_step()
             fast = self._fast
-        fn, cfg, st, tail, dev_index = fast
+        fn, cfg, st, tails, dev_index = fast
+        self._obs_idx = (self._obs_idx + 1) % len(tails)
+        tail = tails[self._obs_idx]
+        self.obs = self._obs_bufs[self._obs_idx]
         if torch.cuda.current_device() != dev_index:
             with torch.cuda.device(self.device):
                 rc = fn(cfg, st, a.data_ptr(), *tail, self.autoreset, torch.cuda.current_stream(self.device).cuda_stream)

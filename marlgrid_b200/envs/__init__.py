@@ -42,6 +42,7 @@ class MultiGridEnv(BatchedMultiGridEnv):
         env_offset=0,
         autoreset=True,
         check_errors=False,
+        obs_buffers=2,
     ):
         if grid_size is not None:
             assert width is None and height is None  # base.py:349-351
@@ -78,7 +79,7 @@ class MultiGridEnv(BatchedMultiGridEnv):
             **self._scenario(),
         )
         super().__init__(cfg, num_envs=num_envs, device=device, seed=seed, env_offset=env_offset, obs_mode=obs_mode,
-                         autoreset=autoreset, check_errors=check_errors)
+                         autoreset=autoreset, check_errors=check_errors, obs_buffers=obs_buffers)
 
     def _scenario(self):
         raise NotImplementedError

@@ -454,3 +454,21 @@ def test_grid_recorder(tmp_path):
     assert sorted(os.listdir(frames_dir)) == sorted(f"frame_{k}.png" for k in range(7))
     assert np.array_equal(np.asarray(Image.open(os.path.join(frames_dir, "frame_0.png"))), first)
     assert any(f.startswith("video_8.") for f in os.listdir(str(tmp_path)))
+
+
+def test_previous_observation_survives_the_next_step():
+    """obs_buffers=2 (default): `save_step(obs, act, next_obs, ...)` of the reference's loop (README.md:43-57) sees two different
+    observations without copying; obs_buffers=1 returns the same storage every step."""
+    from marlgrid_b200 import envs
+
+    env = envs.make("MarlGrid-3AgentCluttered11x11-v0", num_envs=64, obs_mode="encoded", seed=2)
+    obs = env.reset()
+    for t in range(12):
+        keep = obs.clone()
+        next_obs, rew, done, _ = env.step(env.random_actions(t))
+        assert next_obs.data_ptr() != obs.data_ptr() and torch.equal(obs, keep)
+        obs = next_obs
+    one = envs.make("MarlGrid-3AgentCluttered11x11-v0", num_envs=64, obs_mode="encoded", seed=2, obs_buffers=1)
+    o0 = one.reset()
+    o1, _, _, _ = one.step(one.random_actions(0))
+    assert o1.data_ptr() == o0.data_ptr()
