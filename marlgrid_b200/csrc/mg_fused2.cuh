@@ -625,9 +625,8 @@ __global__ void __launch_bounds__(32 * A, ctas_per_sm<OBS, V, A, NST>()) fused2_
       if (OBS == 2 && bad_render) atomicOr(reinterpret_cast<unsigned int*>(s_env) + lane * 4 + 3, (unsigned int)MG_ERR_RENDER << 16);
     }
   }
-  // (the threads that issue the bulk copies below fence the generic -> async proxy hand-over after this barrier, which has
-  // made every thread's shared-memory writes of the tile visible to them)
-  __syncthreads();
+  fence_proxy_async_smem();  // writer side of the generic -> async proxy hand-over: every thread's shared-memory writes of this
+  __syncthreads();           // tile (observations, records, rewards ...) are ordered before the bulk copies issued below
 
   // ---- everything leaves as contiguous chunks; nobody waits for them here ----
   if (full) {
