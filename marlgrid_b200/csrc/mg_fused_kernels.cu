@@ -231,6 +231,7 @@ __global__ void __launch_bounds__(32 * MG_MAX_AGENTS, 4) fused_kernel(const __gr
     rec[a * 4] = s_head[tid] ? (rec[a * 4] | (AF_HEAD << 24)) : (rec[a * 4] & ~(AF_HEAD << 24));
     obs_view<OBS, V, true, true>(p, o, tid, a, env, rec, tp, bits, s_head + le * A);
   }
+  fence_proxy_async_smem();  // writer side of the generic -> async proxy hand-over for the bulk copies issued after the barrier
   __syncthreads();
   obs_emit<OBS, V, TSC>(p, o, env0, n_valid, tid, nthreads);
   if (tid == 0) {  // state goes back as it came: contiguous chunks, bulk copies

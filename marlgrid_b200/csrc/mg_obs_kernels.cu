@@ -39,6 +39,7 @@ __global__ void __launch_bounds__(32 * MG_MAX_AGENTS) obs_kernel(const __grid_co
     obs_view<OBS, V, BITS>(p, o, tid, a, env0 + le, s_rec + le * A * 4, BITS ? p.grid + (env0 + le) * 3 * S : s_grid + le * 3 * S,
                            BITS ? s_bits + le * BITS_WORDS : nullptr);
   }
+  fence_proxy_async_smem();  // writer side of the generic -> async proxy hand-over for the bulk copies issued after the barrier
   __syncthreads();
   obs_emit<OBS, V, TSC>(p, o, env0, n_valid, tid, nthreads);
   if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the CTA (and its shared memory) must outlive the read
