@@ -345,6 +345,21 @@ def main():
     barrier()
     warm_total_ms = e0.elapsed_time(e1)
 
+    # ---- on-device rollout loop: 100 steps per launch (mg_rollout_persistent), every step's outputs written to its own slice ----
+    TP = 100
+    pout = (torch.empty((TP, B, A, 7, 7, 3), dtype=torch.uint8, device=dev), torch.empty((TP, B, A), dtype=torch.float64, device=dev),
+            torch.empty((TP, B), dtype=torch.bool, device=dev))
+    env.rollout_all(actions[:TP], out=pout)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        env.rollout_all(actions[:TP], out=pout)
+    e1.record()
+    barrier()
+    persistent_ms = e0.elapsed_time(e1) / (5 * TP)
+    del pout
+
     # ---- the same K warm steps through the Python surface, env.step(actions) called in a Python loop -------------------
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -387,10 +402,10 @@ def main():
     L.mg_engine_destroy(h)
 
     # ---- max over ranks --------------------------------------------------------------------------
-    times = torch.tensor([cold_total_ms, warm_total_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    times = torch.tensor([cold_total_ms, warm_total_ms, e2e_s * 1e3, persistent_ms], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    cold_total_ms, warm_total_ms, e2e_ms = (float(x) for x in times.tolist())
+    cold_total_ms, warm_total_ms, e2e_ms, persistent_ms = (float(x) for x in times.tolist())
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -422,6 +437,10 @@ def main():
             "step_ms_flushed": {"min": srt[0], "median": srt[len(srt) // 2], "p99": srt[min(len(srt) - 1, int(0.99 * len(srt)))], "max": srt[-1], "steps": len(srt),
                                 "note": "secondary: single steps, 256 MiB L2 flush before each, per-step CUDA events (~2 us resolution)"},
             "warm": {"value": warm_value, "ms_per_step": warm_total_ms / K, "note": "K steps back to back, state L2-resident, launched from mg_rollout_fused"},
+            "rollout_persistent": {"value": world * B / (persistent_ms * 1e-3), "ms_per_step": persistent_ms, "steps_per_launch": TP,
+                                   "note": "on-device rollout loop (mg_rollout_persistent): 100 steps per launch on a fixed action tape, the tiles' state stays in "
+                                           "shared memory between steps, every step's obs / rewards / done go to their own HBM slice (informational: an "
+                                           "open-loop rollout; `value` is one launch per step)"},
             "python_api": {"value": world * B * K / (py_total_ms * 1e-3), "ms_per_step": py_total_ms / K, "host_issue_ms_per_step": 1e3 * host_issue_s / K,
                            "note": "env.step(actions) in a Python loop on one family (rank 0's figures; host-bound when host_issue_ms_per_step ~ ms_per_step)"},
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": act_bytes, "d2h_bytes_per_step": obs_bytes + rew_bytes + B,

@@ -192,6 +192,13 @@ int mg_step_fused_rgb(const MgConfig* cfg, const MgState* st, const int32_t* act
 int mg_rollout_fused(const MgConfig* cfg, const MgState* st, const int32_t* actions, int64_t n_steps,
                      double* rewards, uint8_t* done, uint8_t* obs, int autoreset, mg_stream_t stream);
 
+/* On-device rollout loop: n_steps env.steps on a fixed action tape with EVERY step's outputs kept -- actions int32
+ * [n_steps][B][A], rewards float64 [n_steps][B][A], done uint8 [n_steps][B], obs uint8 [n_steps][B][A][V][V][3].  For the
+ * registered shapes and batches whose tiles all fit the resident CTAs (65 536 envs of 3 agents on a B200) this is ONE launch:
+ * every CTA keeps its tiles' state in shared memory between the steps; otherwise it launches step by step. */
+int mg_rollout_persistent(const MgConfig* cfg, const MgState* st, const int32_t* actions, int64_t n_steps,
+                          double* rewards, uint8_t* done, uint8_t* obs, int autoreset, mg_stream_t stream);
+
 /* The same driver over n_states independent env families of equal size, visited round robin: step t advances family
  * t % n_states with actions[t] and writes that family's rewards[r] / done[r] / obs[r].  With enough families the working
  * set exceeds the L2 cache, which is how bench.py times cold steps back to back (no flush kernel in between). */

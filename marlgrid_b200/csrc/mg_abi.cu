@@ -175,6 +175,27 @@ int mg_rollout_fused(const MgConfig* cfg, const MgState* st, const int32_t* acti
   return 0;
 }
 
+int mg_rollout_persistent(const MgConfig* cfg, const MgState* st, const int32_t* actions, int64_t n_steps, double* rewards, uint8_t* done,
+                          uint8_t* obs, int autoreset, mg_stream_t stream) {
+  int e = check_state(cfg, st);
+  if (e) return e;
+  if (!actions || !rewards || !done || !obs || !aligned16(obs) || n_steps < 0 || n_steps > 0x7FFFFFFF) return MG_E_ARG;
+  if (n_steps == 0 || st->n_envs == 0) return 0;
+  KP p = make_kp(cfg, st);
+  p.actions = actions; p.rewards = rewards; p.done = done; p.obs = obs; p.autoreset = autoreset;
+  if (!g_force_two_kernels && !g_force_general_fused) {
+    e = launch_fused2_rollout(p, (int)n_steps, (cudaStream_t)stream);  // ONE launch, the tiles' state stays in shared memory
+    if (e != MG_E_UNSUPPORTED) return e;
+  }
+  const int64_t na = st->n_envs * cfg->n_agents, no = mg_obs_bytes_per_env(cfg, 0) * st->n_envs;
+  for (int64_t t = 0; t < n_steps; ++t) {  // shapes / batch sizes outside the persistent kernel's reach: step by step
+    p.actions = actions + t * na; p.rewards = rewards + t * na; p.done = done + t * st->n_envs; p.obs = obs + t * no;
+    e = launch_step_obs(p, 1, (cudaStream_t)stream);
+    if (e) return e;
+  }
+  return 0;
+}
+
 int mg_rollout_fused_rr(const MgConfig* cfg, const MgState* states, int n_states, const int32_t* actions, int64_t n_steps,
                          double* const* rewards, uint8_t* const* done, uint8_t* const* obs, int autoreset, mg_stream_t stream) {
   if (!states || n_states < 1 || !actions || !rewards || !done || !obs) return MG_E_ARG;

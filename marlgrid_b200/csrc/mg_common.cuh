@@ -125,5 +125,6 @@ int launch_fused(const KP& p, int obs, cudaStream_t s);         // mg_fused_kern
 bool fused_eligible(const KP& p);
 constexpr int MG_E_UNSUPPORTED = -100;                          // internal: the specialised kernel has no instantiation for this shape
 int launch_fused2(const KP& p, int obs, cudaStream_t s);        // mg_fused2.cu: specialised (compile-time A, V) one-launch step+observe
+int launch_fused2_rollout(const KP& p, int n_steps, cudaStream_t s);  // the same kernel playing n_steps steps per launch (per-step output slices)
 
 }  // namespace mg

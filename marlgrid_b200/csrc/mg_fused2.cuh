@@ -146,8 +146,11 @@ constexpr int ctas_per_sm() {  // shared-memory / thread limited residency the r
 
 // Persistent CTAs: CTA c handles tiles c, c + gridDim.x, ...; while a tile is being processed the next tile's inputs are
 // already on their way into the other input stage (NST = 2), and the previous tile's outputs drain in the background.
-template <int OBS, int V, int A, bool VO0, int NST>
-__global__ void __launch_bounds__(32 * A, ctas_per_sm<OBS, V, A, NST>()) fused2_kernel(const __grid_constant__ KP p, const int n_tiles) {
+// KS (K steps per launch, mg_rollout_persistent): the CTA keeps the state of its (at most NST) tiles in its input stages and
+// plays n_steps steps on them -- actions[step], observations[step], rewards[step], done[step] are per-step slices --, so that
+// an open-loop rollout costs one launch, no state reloads and no grid-wide dependency between steps.
+template <int OBS, int V, int A, bool VO0, int NST, bool KS = false>
+__global__ void __launch_bounds__(32 * A, ctas_per_sm<OBS, V, A, NST>()) fused2_kernel(const __grid_constant__ KP p, const int n_tiles, const int n_steps) {
   using namespace f2;
   using SM = Smem<OBS, V, A, NST>;
   constexpr int VV3 = V * V * 3;
@@ -188,7 +191,7 @@ __global__ void __launch_bounds__(32 * A, ctas_per_sm<OBS, V, A, NST>()) fused2_
     const int nv = (int)min((long long)ENVS_PER_CTA, p.B - e0);
     unsigned char* st = smem + stage * SM::STAGE;
     const uint32_t wbytes = (uint32_t)nv * (BITS_WORDS * 4u), rbytes = (uint32_t)nv * (A * 16u), ebytes = (uint32_t)nv * 16u;
-    const uint32_t abytes = nv == ENVS_PER_CTA ? (uint32_t)(ENVS_PER_CTA * A * 4) : 0u;
+    const uint32_t abytes = (!KS && nv == ENVS_PER_CTA) ? (uint32_t)(ENVS_PER_CTA * A * 4) : 0u;  // KS: actions change every step, read directly
     if (a == 0) {
       mbar_expect_tx(s_bar + stage, wbytes + rbytes + ebytes + abytes);
       bulk_g2s(st + SM::ST_BITS, p.cellbits + e0 * BITS_WORDS, wbytes, s_bar + stage);
@@ -220,11 +223,24 @@ __global__ void __launch_bounds__(32 * A, ctas_per_sm<OBS, V, A, NST>()) fused2_
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if ((int)blockIdx.x < n_tiles) issue_load((int)blockIdx.x, 0);
+  const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // KS: <= NST, all resident
+  if (KS) {
+    for (int j = 1; j < my_tiles; ++j) issue_load((int)blockIdx.x + j * (int)gridDim.x, j);
+  }
+  uint32_t dirty_acc0 = 0, dirty_acc1 = 0;  // KS, warp 0: this env's bit-plane lines changed at some step (stored after the last one)
 
-  int it = 0;
   int chunk_parity = 0;  // OBS 2: which of the warp's chunk buffers is filled next
-  for (int tile = (int)blockIdx.x; tile < n_tiles; tile += (int)gridDim.x, ++it) {
-  const int stage = it % NST;
+  const int n_iter = KS ? my_tiles * n_steps : my_tiles;
+  for (int it = 0; it < n_iter; ++it) {
+  const int step = KS ? it / my_tiles : 0;
+  const int tile = (int)blockIdx.x + (KS ? it % my_tiles : it) * (int)gridDim.x;
+  const int stage = KS ? it % my_tiles : it % NST;
+  const bool last_step = !KS || step == n_steps - 1;
+  // this step's slices of the caller's arrays
+  const int32_t* const act_g = p.actions + (KS ? (long long)step * p.B * A : 0);
+  double* const rew_g = p.rewards + (KS ? (long long)step * p.B * A : 0);
+  uint8_t* const done_g = p.done + (KS ? (long long)step * p.B : 0);
+  uint8_t* const obs_g = p.obs + (KS ? (long long)step * p.B * (A * V * V * 3) : 0);
   unsigned char* const stg = smem + stage * SM::STAGE;
   uint32_t* const s_bits = reinterpret_cast<uint32_t*>(stg + SM::ST_BITS);
   uint32_t* const s_rec = reinterpret_cast<uint32_t*>(stg + SM::ST_REC);   // [env][a][4]
@@ -244,9 +260,9 @@ __global__ void __launch_bounds__(32 * A, ctas_per_sm<OBS, V, A, NST>()) fused2_
   }
 
   int action = MG_A_DONE;
-  if (!full && mine) action = p.actions[env * A + a];
-  mbar_wait(s_bar + stage, (uint32_t)((it / NST) & 1));
-  if (full) action = s_act[lane * A + a];
+  if ((KS || !full) && mine) action = act_g[env * A + a];
+  if (!KS || step == 0) mbar_wait(s_bar + stage, KS ? 0u : (uint32_t)((it / NST) & 1));
+  if (!KS && full) action = s_act[lane * A + a];
 
   // ---- warp 0: the step's agent order, base.py:514-516 -- one Philox block per env ----
   if (a == 0 && mine) {
@@ -343,7 +359,7 @@ __global__ void __launch_bounds__(32 * A, ctas_per_sm<OBS, V, A, NST>()) fused2_
   if (lane == 0 || a == 0) bulk_wait_read0();  // the previous tile's stores (issued by these threads) have left shared memory
   __syncthreads();
 
-  if (NST > 1 && next_tile < n_tiles) issue_load(next_tile, (it + 1) % NST);  // prefetch: lands during this tile's observe phase
+  if (!KS && NST > 1 && next_tile < n_tiles) issue_load(next_tile, (it + 1) % NST);  // prefetch: lands during this tile's observe phase
   zero_out();
   if (a == 0) (reinterpret_cast<uint32_t*>(smem + SM::FLAG) + ((it + 1) & 1) * 32)[lane] = 0u;  // next tile's flag words
 
@@ -365,7 +381,7 @@ __global__ void __launch_bounds__(32 * A, ctas_per_sm<OBS, V, A, NST>()) fused2_
       stamp = (base_stamp + rank) & 0xFFFFu;
     }
     *reinterpret_cast<uint4*>(rec + a * 4) = make_uint4(w0, w1, stamp, 0u);
-    if (full) s_rew[lane * A + a] = reward; else p.rewards[env * A + a] = reward;
+    if (full) s_rew[lane * A + a] = reward; else rew_g[env * A + a] = reward;
     if (a == 0) {  // env bookkeeping and done (base.py:512,649)
       int4 er = *reinterpret_cast<const int4*>(s_env + lane * 4);
       const uint32_t w3 = (uint32_t)er.w;
@@ -374,7 +390,7 @@ __global__ void __launch_bounds__(32 * A, ctas_per_sm<OBS, V, A, NST>()) fused2_
       er.w = (int)((w3 & 0xFFFF0000u) | (((w3 & 0xFFFFu) + (uint32_t)__popc((fl1 >> 8) & 0xFFu)) & 0xFFFFu) | (fl1 & 0xFFFF0000u));
       *reinterpret_cast<int4*>(s_env + lane * 4) = er;
       const bool dn = (er.x >= p.max_steps) || !(fl1 & FL_NOTDONE);
-      if (full) s_done[lane] = dn ? 1 : 0; else p.done[env] = dn ? 1 : 0;
+      if (full) s_done[lane] = dn ? 1 : 0; else done_g[env] = dn ? 1 : 0;
       if (dn && p.autoreset) { rare = true; s_flag[lane] = fl1 | FL_BITS_DIRTY | FL_RESET; }
     }
   } else if (mine && a == 0) rare = true;
@@ -390,14 +406,14 @@ __global__ void __launch_bounds__(32 * A, ctas_per_sm<OBS, V, A, NST>()) fused2_
         const unsigned long long g = (unsigned long long)(p.env_offset + env);
         if (fl & FL_SLOW) {  // MultiGridEnv.step replayed in the reference's order (base.py:501-649)
           double rw[MG_MAX_AGENTS];
-          seq_step(c, g, p.actions + env * A, rw);
+          seq_step(c, g, act_g + env * A, rw);
           bool nd = false;
           for (int q = 0; q < A; ++q) {
             nd = nd || !((c.R(q, 0) >> 24) & MG_AF_DONE);
-            if (full) s_rew[lane * A + q] = rw[q]; else p.rewards[env * A + q] = rw[q];
+            if (full) s_rew[lane * A + q] = rw[q]; else rew_g[env * A + q] = rw[q];
           }
           const bool dn = (c.sc >= p.max_steps) || !nd;
-          if (full) s_done[lane] = dn ? 1 : 0; else p.done[env] = dn ? 1 : 0;
+          if (full) s_done[lane] = dn ? 1 : 0; else done_g[env] = dn ? 1 : 0;
           fl = FL_SLOW | (c.dirty ? FL_BITS_DIRTY : 0u) | ((dn && p.autoreset) ? (FL_BITS_DIRTY | FL_RESET) : 0u);
         }
         if (fl & FL_RESET) {  // MultiGridEnv.reset (base.py:402-416)
@@ -632,26 +648,27 @@ __global__ void __launch_bounds__(32 * A, ctas_per_sm<OBS, V, A, NST>()) fused2_
   if (full) {
     if (lane == 0) {  // again spread over the warps' first lanes
       fence_proxy_async_smem();
-      if (OBS == 1 && a == A - 1) bulk_s2g(p.obs + env0 * (A * VV3), s_out, (uint32_t)SM::OUT_BYTES);
-      if (a == 0) { bulk_s2g(p.agents + env0 * A * 16, s_rec, ENVS_PER_CTA * A * 16u); bulk_s2g(p.done + env0, s_done, ENVS_PER_CTA); }
-      if (a == 1 % A) bulk_s2g(p.envrec + env0 * 4, s_env, ENVS_PER_CTA * 16u);
-      if (a == 2 % A) bulk_s2g(p.rewards + env0 * A, s_rew, ENVS_PER_CTA * A * 8u);
+      if (OBS == 1 && a == A - 1) bulk_s2g(obs_g + env0 * (A * VV3), s_out, (uint32_t)SM::OUT_BYTES);
+      if (a == 0) { if (last_step) bulk_s2g(p.agents + env0 * A * 16, s_rec, ENVS_PER_CTA * A * 16u); bulk_s2g(done_g + env0, s_done, ENVS_PER_CTA); }
+      if (a == 1 % A && last_step) bulk_s2g(p.envrec + env0 * 4, s_env, ENVS_PER_CTA * 16u);
+      if (a == 2 % A) bulk_s2g(rew_g + env0 * A, s_rew, ENVS_PER_CTA * A * 8u);
       bulk_commit();
     }
   } else {  // ragged last tile: plain stores
     if (OBS == 1) {
       const int total = n_valid * A * VV3;
-      uint8_t* dst = p.obs + env0 * (A * VV3);
+      uint8_t* dst = obs_g + env0 * (A * VV3);
       for (int i = tid; i < total; i += 32 * A) dst[i] = s_out[i];
     }
-    if (tid == 0) {
+    if (tid == 0 && last_step) {
       fence_proxy_async_smem();
       bulk_s2g(p.agents + env0 * A * 16, s_rec, (uint32_t)n_valid * (A * 16u));
       bulk_s2g(p.envrec + env0 * 4, s_env, (uint32_t)n_valid * 16u);
       bulk_commit();
     }
   }
-  if (a == 0 && mine && (s_flag[lane] & FL_BITS_DIRTY)) {
+  if (KS && a == 0 && mine) { if (stage) dirty_acc1 |= s_flag[lane] & FL_BITS_DIRTY; else dirty_acc0 |= s_flag[lane] & FL_BITS_DIRTY; }
+  if (a == 0 && mine && last_step && ((KS ? (stage ? dirty_acc1 : dirty_acc0) : s_flag[lane]) & FL_BITS_DIRTY)) {
     fence_proxy_async_smem();
     bulk_s2g(p.cellbits + env * BITS_WORDS, bits, BITS_WORDS * 4u);
     bulk_commit();
@@ -722,10 +739,10 @@ static inline bool pdl_enabled() {  // MG_F2_PDL=0 turns programmatic dependent 
   return v != 0;
 }
 
-template <int OBS, int V, int A, bool VO0, int NST>
-static int launch_one(const KP& p, cudaStream_t s) {
+template <int OBS, int V, int A, bool VO0, int NST, bool KS = false>
+static int launch_one(const KP& p, cudaStream_t s, int n_steps = 1) {
   using SM = f2::Smem<OBS, V, A, NST>;
-  auto k = fused2_kernel<OBS, V, A, VO0, NST>;
+  auto k = fused2_kernel<OBS, V, A, VO0, NST, KS>;
   const int smem_bytes = SM::TOTAL + (OBS == 2 ? (p.n_tiles + 1) * 192 : 0);  // OBS 2: + the tile atlas and the shadow tile
   if (smem_bytes > 227 * 1024) return MG_E_UNSUPPORTED;
   static int resident[64] = {0}, configured_smem[64] = {0};  // CTAs per SM of this instantiation, per device
@@ -749,15 +766,16 @@ static int launch_one(const KP& p, cudaStream_t s) {
   // as many CTAs as stay resident, trimmed so that every CTA gets the same number of tiles (no ragged last round)
   const long long slots = (long long)resident[dev & 63] * sm_count(dev);
   const long long rounds = (tiles + slots - 1) / slots;
+  if (KS && rounds > NST) return MG_E_UNSUPPORTED;  // K steps per launch: every tile's state has to stay in a stage of its CTA
   const long long grid = getenv("MG_F2_RAGGED") ? std::min(tiles, slots) : (tiles + rounds - 1) / rounds;
-  if (getenv("MG_F2_VERBOSE")) fprintf(stderr, "fused2<OBS=%d,V=%d,A=%d,NST=%d>: %d CTAs/SM x %d SMs, %lld tiles in %lld rounds -> grid %lld, %d B shared\n", OBS, V, A, NST, resident[dev & 63], sm_count(dev), tiles, rounds, grid, smem_bytes);
+  if (getenv("MG_F2_VERBOSE")) fprintf(stderr, "fused2<OBS=%d,V=%d,A=%d,NST=%d,KS=%d>: %d CTAs/SM x %d SMs, %lld tiles in %lld rounds -> grid %lld, %d B shared, %d step(s)\n", OBS, V, A, NST, (int)KS, resident[dev & 63], sm_count(dev), tiles, rounds, grid, smem_bytes, n_steps);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(32 * A); cfg.dynamicSmemBytes = (size_t)smem_bytes; cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  const cudaError_t e = cudaLaunchKernelEx(&cfg, k, p, (int)tiles);
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, k, p, (int)tiles, n_steps);
   count_launch();
   return (int)e;
 }
@@ -782,6 +800,19 @@ static int launch_a(const KP& p, cudaStream_t s) {
 template <int OBS, int V>
 int launch_fused2_ov(const KP& p, cudaStream_t s) {
   return p.vo == 0 ? launch_a<OBS, V, true>(p, s) : launch_a<OBS, V, false>(p, s);
+}
+
+// K steps per launch (encoded observations, view_offset 0, A <= 4: the registered MarlGrid-* shapes)
+template <int V>
+int launch_fused2_ks(const KP& p, int n_steps, cudaStream_t s) {
+  if (p.vo != 0) return MG_E_UNSUPPORTED;
+  switch (p.A) {
+    case 1: return launch_one<1, V, 1, true, 2, true>(p, s, n_steps);
+    case 2: return launch_one<1, V, 2, true, 2, true>(p, s, n_steps);
+    case 3: return launch_one<1, V, 3, true, 2, true>(p, s, n_steps);
+    case 4: return launch_one<1, V, 4, true, 2, true>(p, s, n_steps);
+  }
+  return MG_E_UNSUPPORTED;
 }
 
 }  // namespace mg

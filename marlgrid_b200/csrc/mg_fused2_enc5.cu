@@ -3,4 +3,5 @@
 
 namespace mg {
 template int launch_fused2_ov<1, 5>(const KP&, cudaStream_t);
+template int launch_fused2_ks<5>(const KP&, int, cudaStream_t);
 }

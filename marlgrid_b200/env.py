@@ -229,6 +229,26 @@ class BatchedMultiGridEnv:
                                                   self.done.data_ptr(), self.obs.data_ptr(), int(self.autoreset), self._stream()), "mg_rollout_fused")
             return self.obs, self.rewards, self.done
 
+    def rollout_all(self, actions, out=None):
+        """On-device rollout loop (mg_rollout_persistent): actions int32 [T, B, A] -> (obs [T, B, A, V, V, 3], rewards
+        [T, B, A], done [T, B]) of EVERY step; one kernel launch when the batch fits the resident CTAs (the tiles' state
+        then stays in shared memory between the steps).  `out` = (obs, rewards, done) tensors to fill."""
+        with torch.cuda.device(self.device):
+            if self.obs_mode != "encoded":
+                raise NotImplementedError("rollout_all() drives the encoded-obs path")
+            a = torch.as_tensor(actions, device=self.device).to(torch.int32).contiguous()
+            T, B, A, V = a.shape[0], self.num_envs, self.cfg.n_agents, self.cfg.view_size
+            assert a.shape[1:] == (B, A)
+            if out is None:
+                out = (torch.empty((T, B, A, V, V, 3), dtype=torch.uint8, device=self.device),
+                       torch.empty((T, B, A), dtype=torch.float64, device=self.device), torch.empty((T, B), dtype=torch.bool, device=self.device))
+            obs, rew, done = out
+            _lib.check(self._lib.mg_rollout_persistent(ctypes.byref(self.cfg), ctypes.byref(self._state), a.data_ptr(), T, rew.data_ptr(),
+                                                       done.data_ptr(), obs.data_ptr(), int(self.autoreset), self._stream()), "mg_rollout_persistent")
+            if T:
+                self.obs.copy_(obs[-1]); self.rewards.copy_(rew[-1]); self.done.copy_(done[-1])
+            return obs, rew, done
+
     def random_actions(self, counter, n_actions=7, seed=0, out=None):
         """Uniform synthetic policy on the device; `counter` selects the draw."""
         with torch.cuda.device(self.device):

@@ -472,3 +472,23 @@ def test_previous_observation_survives_the_next_step():
     o0 = one.reset()
     o1, _, _, _ = one.step(one.random_actions(0))
     assert o1.data_ptr() == o0.data_ptr()
+
+
+@pytest.mark.parametrize("env_id,B", [("MarlGrid-3AgentCluttered15x15-v0", 4096), ("MarlGrid-2AgentEmpty9x9-v0", 1008), ("MarlGrid-4AgentEmpty9x9-v0", 65536 + 32)])
+def test_persistent_rollout_equals_step_by_step(env_id, B):
+    """mg_rollout_persistent: T steps in one launch (state resident in shared memory) == T calls of env.step, every step's
+    outputs compared; the last case does not fit the resident CTAs and takes the step-by-step fallback; resets included."""
+    from marlgrid_b200 import envs
+
+    T = 108
+    a = envs.make(env_id, num_envs=B, obs_mode="encoded", seed=21)
+    b = envs.make(env_id, num_envs=B, obs_mode="encoded", seed=21)
+    a.reset()
+    b.reset()
+    actions = torch.stack([a.random_actions(t) for t in range(T)])
+    obs, rew, done = a.rollout_all(actions)
+    for t in range(T):
+        o, r, d, _ = b.step(actions[t])
+        assert torch.equal(obs[t], o) and torch.equal(rew[t], r) and torch.equal(done[t], d), f"step {t}"
+    assert torch.equal(a.grid, b.grid) and torch.equal(a.envrec, b.envrec) and torch.equal(a.cellbits, b.cellbits)
+    assert torch.equal(a.agents[:, :, :12], b.agents[:, :, :12]) and int(a.episode.min().item()) >= 2

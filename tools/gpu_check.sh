@@ -62,3 +62,24 @@ if [[ "$what" == *sanitize* ]]; then
   timeout 900 compute-sanitizer --tool synccheck --error-exitcode 7 python tools/sanitize_workload.py 103 > gpurun_out/sanitizer_synccheck.log 2>&1; echo "synccheck exit $?" | tee -a gpurun_out/sanitizer_synccheck.log
   for f in memcheck racecheck synccheck; do tail -n 3 gpurun_out/sanitizer_$f.log; done
 fi
+if [[ "$what" == *rollout* ]]; then
+  # K steps per launch (mg_rollout_persistent) next to K launches (mg_rollout_fused), same family, state L2-resident
+  MG_F2_VERBOSE=1 timeout 300 python - > gpurun_out/rollout.log 2>&1 <<'PY'
+import torch, time
+from marlgrid_b200 import envs
+B, T = 65536, 100
+env = envs.make("MarlGrid-3AgentCluttered15x15-v0", num_envs=B, obs_mode="encoded", seed=1337)
+env.reset()
+act = torch.stack([env.random_actions(t) for t in range(T)])
+out = (torch.empty((T, B, 3, 7, 7, 3), dtype=torch.uint8, device="cuda"), torch.empty((T, B, 3), dtype=torch.float64, device="cuda"), torch.empty((T, B), dtype=torch.bool, device="cuda"))
+for name, fn in (("persistent (1 launch / 100 steps)", lambda: env.rollout_all(act, out=out)), ("fused (100 launches)", lambda: env.rollout(act))):
+    fn(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5): fn()
+    e1.record(); torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 1e3 / (5 * T)
+    print(f"{name}: {us:.2f} us per step, {B / us * 1e6:.3e} env-steps/s")
+PY
+  grep -v "^fused2<" gpurun_out/rollout.log; grep "^fused2<" gpurun_out/rollout.log | sort -u | head -3
+fi
