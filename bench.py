@@ -163,7 +163,7 @@ def run_reference(args, rank, world):
         return
     threads = host_threads()
     n_envs = 65536 if threads >= 32 else 8192  # a bench "step" of this arm = one env.step over this sample of the batch
-    v, dt, n_steps = cpu_port_throughput(n_envs, threads, target_s=20.0)
+    v, dt, n_steps = cpu_port_throughput(n_envs, threads, target_s=30.0)
     sample = (f"{n_envs} envs x {n_steps} steps ({dt:.1f} s) of the same workload, C port of the reference step+reset+encode "
               f"(oracle/mg_oracle.c), {threads} threads")
     line = {
@@ -426,7 +426,7 @@ def main():
         if not args.no_cpu_baseline and world == 1:
             thr = host_threads()
             n_envs = 65536 if thr >= 32 else 8192
-            v, dt, n_steps = cpu_port_throughput(n_envs, thr, target_s=12.0)
+            v, dt, n_steps = cpu_port_throughput(n_envs, thr, target_s=22.0)
             cpu = {"value": v, "unit": "env-steps/s", "cores": thr, "kind": "port",
                    "sample": f"{n_envs} envs x {n_steps} steps of the same workload ({dt:.1f} s), C port of the reference step+reset+encode (oracle/mg_oracle.c)"}
         line = {
