@@ -211,6 +211,58 @@ def test_marlgrid_import_alias():
     assert out.returncode == 0 and "alias ok" in out.stdout, out.stderr
 
 
+def test_hide_item_types_mask():
+    """GridAgentInterface.hide_item_types (agents.py:30): WorldObj.type strings -> MgConfig.hide_types bits; 'Agent' is the
+    type string of agents (objects.py:137-138)."""
+    import pytest
+
+    from marlgrid_b200.agents import GridAgentInterface
+    from marlgrid_b200.config import make_config
+    from marlgrid_b200.objects import hide_mask
+
+    assert hide_mask([]) == 0 and hide_mask(["Wall"]) == 1 << 8 and hide_mask(["Goal", "Agent"]) == (1 << 4) | (1 << 13)
+    with pytest.raises(ValueError):
+        hide_mask(["Unicorn"])
+    assert GridAgentInterface(hide_item_types=["Wall"]).clone().hide_item_types == ["Wall"]
+    assert make_config(9, 9, ["red"], hide_types=hide_mask(["Door"])).hide_types == 1 << 11
+
+
+def test_grid_recorder_on_a_host_env(tmp_path):
+    """GridRecorder (utils/video.py:55-154) around any env with reset / step / render: frame bookkeeping and export."""
+    import numpy as np
+
+    from marlgrid_b200.utils.video import GridRecorder
+
+    class Env:  # a stand-in with the gym surface the recorder uses
+        max_steps = 5
+
+        def __init__(self):
+            self.t = 0
+
+        def reset(self):
+            self.t = 0
+            return "obs"
+
+        def step(self, action):
+            self.t += 1
+            return "obs", 0.0, self.t >= 5, {}
+
+        def render(self, mode="rgb_array"):
+            return np.full((4, 6, 3), self.t, np.uint8)
+
+    rec = GridRecorder(Env(), save_root=str(tmp_path), max_steps=None, auto_save_interval=2)
+    assert rec.max_steps == 6 and not rec.recording
+    for episode in range(3):
+        rec.reset()
+        for _ in range(5):
+            rec.step(0)
+    # auto_save_interval: episodes whose reset count is >= 2 past the last save are filmed and exported at the next reset
+    saved = sorted(os.listdir(str(tmp_path)))
+    assert any(n.startswith("frames_") for n in saved) and any(n.startswith("video_") for n in saved), saved
+    frames_dir = os.path.join(str(tmp_path), [n for n in saved if n.startswith("frames_")][0])
+    assert len(os.listdir(frames_dir)) == 6  # five pre-step frames + the final frame appended at reset
+
+
 def test_shard_ranges_partition_the_batch():
     from marlgrid_b200.sharding import shard_range
 
