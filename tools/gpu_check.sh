@@ -83,3 +83,7 @@ for name, fn in (("persistent (1 launch / 100 steps)", lambda: env.rollout_all(a
 PY
   grep -v "^fused2<" gpurun_out/rollout.log; grep "^fused2<" gpurun_out/rollout.log | sort -u | head -3
 fi
+if [[ "$what" == *soak* ]]; then
+  timeout 1200 python tools/soak.py > gpurun_out/soak.log 2>&1; echo "soak exit $?" | tee -a gpurun_out/soak.log
+  cat gpurun_out/soak.log | tail -8
+fi

@@ -1,0 +1,53 @@
+"""Long lock-step runs of the CUDA path against the oracle (tools/gpu_check.sh soak): thousands of steps with auto-reset,
+forward-biased random actions (goal hits, stacking, irregular episode ends), every output compared every step."""
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from marlgrid_b200 import envs  # noqa: E402
+from marlgrid_b200.atlas import build_atlas  # noqa: E402
+from oracle import mg_oracle  # noqa: E402
+
+mg_oracle.build()
+
+
+def soak(env_id, B, T, mode, seed, p_forward):
+    env = envs.make(env_id, num_envs=B, obs_mode=mode, seed=seed, env_offset=123456789)
+    ob = mg_oracle.OracleBatch(env.cfg, B, seed=seed, env_offset=123456789, threads=16)
+    A = env.num_agents
+    atlas = build_atlas([int(c) for c in env.cfg.agent_color[:A]], env.cfg.view_tile_size) if mode == "rgb" else None
+    env.reset()
+    ob.reset()
+    rng = np.random.RandomState(seed)
+    t0 = time.time()
+    hits = 0
+    for t in range(T):
+        act = rng.randint(0, 7, size=(B, A)).astype(np.int32)
+        act[rng.rand(B, A) < p_forward] = 2
+        obs, rew, done, _ = env.step(torch.from_numpy(act).cuda())
+        if mode == "rgb":
+            r2, d2 = ob.step(act, autoreset=True)
+            if t % 10 == 0:
+                assert np.array_equal(obs.cpu().numpy(), ob.obs_rgb(atlas)), f"{env_id} step {t}: rgb obs"
+        else:
+            o2, r2, d2 = ob.step(act, autoreset=True, with_obs=True)
+            assert np.array_equal(obs.cpu().numpy(), o2), f"{env_id} step {t}: obs"
+        assert np.array_equal(rew.cpu().numpy().view(np.uint64), r2.view(np.uint64)), f"{env_id} step {t}: reward bits"
+        assert np.array_equal(done.cpu().numpy(), d2.astype(bool)), f"{env_id} step {t}: done"
+        hits += int((r2 > 0).sum())
+        if t % 100 == 0:
+            assert np.array_equal(env.grid.cpu().numpy(), ob.grid) and np.array_equal(env.envrec.cpu().numpy(), ob.envrec), f"{env_id} step {t}: state"
+    assert int(env.err.max().item()) == 0
+    print(f"{env_id:36s} {mode:8s} B={B:6d} T={T:5d}: ok  ({B * T} env-steps, {hits} goal rewards, episodes {int(env.episode.min())}..{int(env.episode.max())}, {time.time() - t0:.0f} s)")
+
+
+if __name__ == "__main__":
+    soak("MarlGrid-3AgentCluttered15x15-v0", 4096, 3000, "encoded", 11, 0.5)
+    soak("MarlGrid-3AgentCluttered11x11-v0", 2048, 3000, "encoded", 12, 0.6)
+    soak("MarlGrid-4AgentEmpty9x9-v0", 512, 1500, "rgb", 13, 0.6)
+    soak("MarlGrid-2AgentEmpty9x9-v0", 1024, 3000, "encoded", 14, 0.7)
+    soak("Goalcycle-demo-solo-v0", 1024, 2000, "encoded", 15, 0.6)
