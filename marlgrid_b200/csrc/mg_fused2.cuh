@@ -135,6 +135,259 @@ __device__ __forceinline__ void sts_u8(uint32_t saddr, uint32_t v) {
   asm volatile("st.shared.u8 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
 }
 
+// Warp-cooperative reset: it cuts the cost of a tile in which one or two envs finish from ~45 us to ~6 us -- the normal state of
+// a long-running batch, whose episodes have drifted apart (tools/desync_probe.py).
+// MultiGridEnv.reset (base.py:402-416) + _gen_grid (empty.py:9-16, cluttered.py:25-36, goalcycle.py:30-51) for ONE env by a
+// whole warp: lanes = consecutive placement tries of place_obj's rejection sampling (base.py:690-708).
+//   static objects (random goal, bonus tiles, clutter walls, in this order): scanning the tries in order, a try is accepted
+//     iff its cell is free of walls / objects AND no earlier accepted try hit the same cell (the object placed there is what
+//     the sequential code would find) -- within a batch of 32 tries that is "first valid lane of its cell" (match_any); the
+//     j-th accepted try gets the j-th object.
+//   agents (ghost mode: they may share cells): the tries after the last static object's, each non-wall try places the next agent.
+// Returns false WITHOUT having committed anything when the run is not an ordinary one (a whole batch of 32 tries without a
+// placement -- the only way max_tries, base.py:700-706, could come into play --, or more than MAXB batches): the caller then
+// runs the sequential code.  On success bits / rec / envr (shared memory) hold the new episode.
+template <int A>
+__device__ __forceinline__ bool warp_reset(const KP& p, unsigned long long g, uint32_t* __restrict__ bits, uint32_t* __restrict__ rec,
+                                        int32_t* __restrict__ envr, uint32_t* __restrict__ wk /* 36 words of this warp */, int lane) {
+  constexpr int MAXB = 8;
+  const int W = p.W, H = p.H;
+  uint32_t* wall_x = wk;        // [16] bit y = canonical wall at (x, y)
+  uint32_t* other_x = wk + 16;  // [16] bit y = Goal / BonusTile at (x, y)
+  uint32_t* list = wk + 32;     // [4] object list entries
+  if (lane < 16) {
+    const uint32_t fullr = (1u << H) - 1u, endsr = 1u | (1u << (H - 1));
+    wall_x[lane] = (lane == 0 || lane == W - 1) ? fullr : (lane < W ? endsr : 0u);  // wall_rect base.py:172-176
+    other_x[lane] = (p.goal_mode == MG_GOAL_FIXED && lane == W - 2) ? (1u << (H - 2)) : 0u;  // put_obj(Goal) base.py:655-662
+  }
+  if (lane < OBJ_SLOTS) list[lane] = (lane == 0 && p.goal_mode == MG_GOAL_FIXED) ? obj_entry(W - 2, H - 2, MG_T_GOAL, MG_C_GREEN, 0) : 0u;
+  __syncwarp();
+  const int n_goal = (p.goal_mode == MG_GOAL_RANDOM) ? 1 : 0, n_other = n_goal + p.n_bonus, n_static = n_other + p.n_clutter;
+  const int list_base = (p.goal_mode == MG_GOAL_FIXED) ? 1 : 0;
+  const uint32_t ep = (uint32_t)envr[1], lt = (1u << lane) - 1u;
+  int placed_static = 0, agents_done = 0;
+  uint32_t a_xy = 0;  // lane q < A: where agent q goes (x | y << 8)
+  for (int batch = 0; batch < MAXB; ++batch) {
+    const uint32_t k = (uint32_t)(batch * 32 + lane);
+    const U4 r = philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), ep, TAG_RESET | (k >> 1), (uint32_t)p.seed, (uint32_t)(p.seed >> 32));
+    const int x = (int)__umulhi((k & 1u) ? r.z : r.x, (uint32_t)W), y = (int)__umulhi((k & 1u) ? r.w : r.y, (uint32_t)H);
+    int start_lane = 0;
+    if (placed_static < n_static) {
+      const bool valid = !(((wall_x[x] | other_x[x]) >> y) & 1u);
+      const uint32_t vm = __ballot_sync(0xFFFFFFFFu, valid);
+      bool acc = false;
+      if (valid) acc = (__ffs(__match_any_sync(vm, x * 16 + y)) - 1) == lane;  // first valid try of this cell in the batch
+      const uint32_t am = __ballot_sync(0xFFFFFFFFu, acc);
+      if (am == 0u) return false;
+      const int j = placed_static + __popc(am & lt);  // index of the object this try would place
+      const bool take = acc && j < n_static;
+      const uint32_t tm = __ballot_sync(0xFFFFFFFFu, take);
+      if (take) {
+        if (j < n_other) {
+          atomicOr(&other_x[x], 1u << y);
+          const uint32_t e = (j < n_goal) ? obj_entry(x, y, MG_T_GOAL, MG_C_GREEN, 0) : obj_entry(x, y, MG_T_BONUS, MG_C_YELLOW, j - n_goal);
+          if (list_base + j < OBJ_SLOTS) list[list_base + j] = e;
+        } else atomicOr(&wall_x[x], 1u << y);
+      }
+      placed_static += __popc(tm);
+      __syncwarp();
+      if (placed_static < n_static) continue;
+      start_lane = 32 - __clz(tm);  // the agents' tries begin behind the last static object's
+    }
+    const bool valid_a = lane >= start_lane && !((wall_x[x] >> y) & 1u);
+    const uint32_t vma = __ballot_sync(0xFFFFFFFFu, valid_a);
+    if (vma == 0u) { if (start_lane == 0) return false; else continue; }
+    const int q = agents_done + __popc(vma & lt);
+    const uint32_t xy = (uint32_t)x | ((uint32_t)y << 8);
+#pragma unroll
+    for (int t = 0; t < A; ++t) {  // hand try "q == t" to lane t
+      const uint32_t src = __ballot_sync(0xFFFFFFFFu, valid_a && q == t);
+      if (src) { const uint32_t v = __shfl_sync(0xFFFFFFFFu, xy, __ffs(src) - 1); if (lane == t) a_xy = v; }
+    }
+    agents_done += __popc(vma);
+    if (agents_done >= A) {
+      // ---- commit: records, env record, bit-plane lines (x-lines as sampled, y-lines by transposition), object list ----
+      if (lane < A) {  // agents.py:161-170 (dir survives), placement order = stamp order (base.py:409-412,686)
+        const uint32_t old = rec[lane * 4];
+        *reinterpret_cast<uint4*>(rec + lane * 4) = make_uint4((old & 0x00FF0000u) | a_xy | ((uint32_t)(MG_AF_PLACED | MG_AF_ACTIVE) << 24), 0xFF000000u, (uint32_t)lane, 0u);
+      }
+      if (lane == 0) {
+        envr[0] = 0; envr[1] = (int)(ep + 1u);
+        envr[3] = (int)(((uint32_t)envr[3] & 0xFFFF0000u) | (uint32_t)A);
+      }
+      uint32_t wy = 0, oy = 0;  // lane y < 16: its y-line
+      for (int xx = 0; xx < 16; ++xx) {
+        wy |= ((wall_x[xx] >> (lane & 15)) & 1u) << xx;
+        oy |= ((other_x[xx] >> (lane & 15)) & 1u) << xx;
+      }
+      if (lane < 16) {
+        bits[LINE_X0 + lane] = wall_x[lane] | (other_x[lane] << 16);
+        bits[LINE_Y0 + lane] = wy | (oy << 16);
+      }
+      if (lane < 4) bits[OBJ_WORD0 + lane] = list[lane];
+      if (lane >= 4 && lane < 8) bits[OBJ_WORD0 + lane] = 0u;             // words 40..43
+      if (lane >= 8 && lane < 12) bits[(lane == 8) ? 0 : (lane == 9) ? 17 : (lane == 10) ? 18 : 35] = 0u;  // guard lines
+      __syncwarp();
+      return true;
+    }
+  }
+  return false;
+}
+
+// the finished envs of a tile that the warps regenerate cooperatively (env e -> warp e % A): worth it while few envs of the
+// tile end together (a long-running batch whose episodes have drifted apart: one or two per tile and step); a tile in which
+// most envs end at once (episodes still in lock step) is cheaper with one lane per env on the sequential code
+template <int A>
+__device__ __noinline__ void warp_resets(const KP& p, uint32_t* s_flag, uint32_t* s_bits, uint32_t* s_rec, int32_t* s_env, uint32_t* wk,
+                                         long long env0, int n_valid, int a, int lane) {
+  const uint32_t todo = __ballot_sync(0xFFFFFFFFu, lane < n_valid && (s_flag[lane] & (FL_SLOW | FL_RESET)) == FL_RESET);
+  if (__popc(todo) > 4 * A) return;
+  for (int e = a; e < n_valid; e += A) {
+    if (!((todo >> e) & 1u)) continue;
+    const uint32_t fl = s_flag[e];
+    if (warp_reset<A>(p, (unsigned long long)(p.env_offset + env0 + e), s_bits + e * BITS_WORDS, s_rec + e * (A * 4), s_env + e * 4, wk, lane)) {
+      if (lane == 0) s_flag[e] = (fl & ~FL_RESET) | FL_IMAGE;
+    }
+    __syncwarp();
+  }
+}
+
+
+
+template <int OBS, int A, class SM>
+__device__ __forceinline__ void zero_out_tile(uint8_t* s_out, int tid) {  // invisible / empty cells encode as 0 (the RGB path writes every byte of its tile maps)
+  if (OBS != 1) return;
+  int4* z = reinterpret_cast<int4*>(s_out);
+  constexpr int N16 = SM::OUT_BYTES / 16, ITERS = (N16 + 32 * A - 1) / (32 * A);
+#pragma unroll
+  for (int k = 0; k < ITERS; ++k) {
+    const int i = tid + k * 32 * A;
+    if (i < N16) z[i] = make_int4(0, 0, 0, 0);
+  }
+}
+
+// The rare part of a tile's step (some env of the tile finished its episode, or an action edits the byte planes): the whole
+// CTA comes here between the commit of the parallel envs and the observe phase.  Out of line and self-contained on purpose.
+template <int OBS, int V, int A, int NST, bool KS>
+__device__ __noinline__ void rare_path(const KP& p, const int tile, const int stage, const int it, const int step) {
+  using SM = Smem<OBS, V, A, NST>;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x, lane = tid & 31, a = tid >> 5;
+  const int W = p.W, H = p.H, S = p.S;
+  const bool image_planes = (p.goal_mode != MG_GOAL_NONE ? 1 : 0) + p.n_bonus <= OBJ_SLOTS && 3 * S <= SM::OUT_AREA;
+  double* s_rew = reinterpret_cast<double*>(smem + SM::REW);
+  uint8_t* s_done = smem + SM::DONE;
+  uint8_t* s_out = smem + SM::OUT;
+  uint32_t* s_trec = reinterpret_cast<uint32_t*>(s_out);  // sequential path scratch, aliased with the output tile
+  uint32_t* s_scr = s_trec + A * 4 * 32;
+  const int32_t* const act_g = p.actions + (KS ? (long long)step * p.B * A : 0);
+  double* const rew_g = p.rewards + (KS ? (long long)step * p.B * A : 0);
+  uint8_t* const done_g = p.done + (KS ? (long long)step * p.B : 0);
+  unsigned char* const stg = smem + stage * SM::STAGE;
+  uint32_t* const s_bits = reinterpret_cast<uint32_t*>(stg + SM::ST_BITS);
+  uint32_t* const s_rec = reinterpret_cast<uint32_t*>(stg + SM::ST_REC);
+  int32_t* const s_env = reinterpret_cast<int32_t*>(stg + SM::ST_ENV);
+  uint32_t* const s_flag = reinterpret_cast<uint32_t*>(smem + SM::FLAG) + (it & 1) * 32;
+  const long long env0 = (long long)tile * ENVS_PER_CTA;
+  const int n_valid = (int)min((long long)ENVS_PER_CTA, p.B - env0);
+  const bool full = n_valid == ENVS_PER_CTA;
+  const bool mine = lane < n_valid;
+  const long long env = env0 + lane;
+  uint32_t* const rec = s_rec + lane * (A * 4);
+  uint32_t* const bits = s_bits + lane * BITS_WORDS;
+  uint8_t* const tp = p.grid + env * 3 * S;
+  {
+    // lane == env in every warp: the envs are dealt out over the CTA's warps (env e goes to warp e % A), so that A warps
+    // instead of one chew through the sequential code of mg_env.cuh; scratch lives in the (not yet used) output tile
+    if (image_planes) {  // finished envs of a tile with few of them: one env at a time per warp, lanes = placement tries
+      warp_resets<A>(p, s_flag, s_bits, s_rec, s_env, s_scr + a * 64, env0, n_valid, a, lane);
+      __syncthreads();
+    }
+    if (a == lane % A && mine) {
+      uint32_t fl = s_flag[lane];
+      if (fl & (FL_SLOW | FL_RESET)) {
+        EnvCtx<32> c{p, s_trec + lane, tp, bits, s_scr + lane, 0, 0, 0, 0u, false};
+        for (int q = 0; q < A; ++q) { c.R(q, 0) = rec[q * 4]; c.R(q, 1) = rec[q * 4 + 1]; c.R(q, 2) = rec[q * 4 + 2]; }
+        c.sc = s_env[lane * 4]; c.ep = s_env[lane * 4 + 1]; c.tl = s_env[lane * 4 + 2]; c.w3 = (uint32_t)s_env[lane * 4 + 3];
+        const unsigned long long g = (unsigned long long)(p.env_offset + env);
+        if (fl & FL_SLOW) {  // MultiGridEnv.step replayed in the reference's order (base.py:501-649)
+          double rw[MG_MAX_AGENTS];
+          seq_step(c, g, act_g + env * A, rw);
+          bool nd = false;
+          for (int q = 0; q < A; ++q) {
+            nd = nd || !((c.R(q, 0) >> 24) & MG_AF_DONE);
+            if (full) s_rew[lane * A + q] = rw[q]; else rew_g[env * A + q] = rw[q];
+          }
+          const bool dn = (c.sc >= p.max_steps) || !nd;
+          if (full) s_done[lane] = dn ? 1 : 0; else done_g[env] = dn ? 1 : 0;
+          fl = FL_SLOW | (c.dirty ? FL_BITS_DIRTY : 0u) | ((dn && p.autoreset) ? (FL_BITS_DIRTY | FL_RESET) : 0u);
+        }
+        if (fl & FL_RESET) {  // MultiGridEnv.reset (base.py:402-416), sequential code
+          // an env whose replayed step edited the planes with plain stores keeps plain stores (no cross-proxy ordering games)
+          if (image_planes && !(fl & FL_SLOW)) { seq_reset<false>(c, g); fl |= FL_IMAGE; } else seq_reset<true>(c, g);
+          fl &= ~FL_RESET;
+        }
+        for (int q = 0; q < A; ++q) { rec[q * 4] = c.R(q, 0); rec[q * 4 + 1] = c.R(q, 1); rec[q * 4 + 2] = c.R(q, 2); rec[q * 4 + 3] = 0u; }
+        s_env[lane * 4] = c.sc; s_env[lane * 4 + 1] = c.ep; s_env[lane * 4 + 2] = c.tl; s_env[lane * 4 + 3] = (int)c.w3;
+        s_flag[lane] = fl;
+      }
+    }
+    __syncthreads();
+    if (image_planes) {
+      // The byte planes of the regenerated envs, rebuilt from their bit-plane lines (walls) and object lists (Goal,
+      // BonusTiles) in the -- still unused -- output area, group by group, and stored with bulk copies: a fresh world is
+      // 3*S bytes of mostly zeros, which single lanes writing to global memory would turn into hundreds of scattered stores.
+      const int plane_bytes = 3 * S;
+      const int G = min(ENVS_PER_CTA, SM::OUT_AREA / plane_bytes);
+      const uint32_t image_mask = __ballot_sync(0xFFFFFFFFu, mine && (s_flag[lane] & FL_IMAGE));  // lane == env: the same word in every warp
+      for (int g0 = 0; g0 < n_valid; g0 += G) {
+        const int gn = min(G, n_valid - g0);
+        const uint32_t group_mask = (image_mask >> g0) & (gn == 32 ? 0xFFFFFFFFu : ((1u << gn) - 1u));  // envs of the group that were reset
+        if (group_mask == 0u) continue;
+        {
+          int4* z = reinterpret_cast<int4*>(s_out);
+          for (int i = tid; i < gn * plane_bytes / 16; i += 32 * A) z[i] = make_int4(0, 0, 0, 0);
+        }
+        __syncthreads();
+        for (int i = tid; i < gn * 16; i += 32 * A) {  // one (env, x-line) pair per iteration
+          const int e = i >> 4, x = i & 15;
+          if (x >= W || !((group_mask >> e) & 1u)) continue;
+          const uint32_t* eb = s_bits + (g0 + e) * BITS_WORDS;
+          const uint32_t w = eb[LINE_X0 + x];
+          uint8_t* img = s_out + e * plane_bytes + x * H;
+          uint32_t walls = w & 0xFFFFu & ~(w >> 16), others = w >> 16;
+          while (walls) {
+            const int y = __ffs(walls) - 1;
+            walls &= walls - 1u;
+            img[y] = MG_T_WALL; img[S + y] = MG_C_WORST;
+          }
+          while (others) {
+            const int y = __ffs(others) - 1;
+            others &= others - 1u;
+            const uint32_t oe = obj_lookup(eb, x, y);  // always listed: image_planes requires goal + bonus tiles <= OBJ_SLOTS
+            img[y] = (uint8_t)((oe >> 8) & 15u); img[S + y] = (uint8_t)((oe >> 12) & 15u); img[2 * S + y] = (uint8_t)((oe >> 16) & 255u);
+          }
+        }
+        fence_proxy_async_smem();
+        __syncthreads();
+        if (a == 0) {
+          const bool all = group_mask == (gn == 32 ? 0xFFFFFFFFu : ((1u << gn) - 1u));
+          if (all ? lane == 0 : (lane < gn && ((group_mask >> lane) & 1u))) {
+            fence_proxy_async_smem();
+            if (all) bulk_s2g(p.grid + (env0 + g0) * plane_bytes, s_out, (uint32_t)(gn * plane_bytes));
+            else bulk_s2g(p.grid + (env0 + g0 + lane) * plane_bytes, s_out + lane * plane_bytes, (uint32_t)plane_bytes);
+            bulk_commit();
+            bulk_wait_read0();
+          }
+        }
+        __syncthreads();
+      }
+    }
+    zero_out_tile<OBS, A, SM>(s_out, tid);  // the sequential path borrowed the output area: clean it again
+    __syncthreads();
+  }
+}
+
 }  // namespace f2
 
 template <int OBS, int V, int A, int NST>
@@ -172,16 +425,7 @@ __global__ void __launch_bounds__(32 * A, ctas_per_sm<OBS, V, A, NST>()) fused2_
   uint8_t* const out = s_out + (lane * A + a) * VV3;
   const uint32_t out_s = smem_u32(out);
 
-  auto zero_out = [&]() {  // invisible / empty cells encode as 0 (the RGB path writes every byte of its tile maps)
-    if (OBS != 1) return;
-    int4* z = reinterpret_cast<int4*>(s_out);
-    constexpr int N16 = SM::OUT_BYTES / 16, ITERS = (N16 + 32 * A - 1) / (32 * A);
-#pragma unroll
-    for (int k = 0; k < ITERS; ++k) {
-      const int i = tid + k * 32 * A;
-      if (i < N16) z[i] = make_int4(0, 0, 0, 0);
-    }
-  };
+  auto zero_out = [&]() { f2::zero_out_tile<OBS, A, SM>(s_out, tid); };
   // one tile's inputs as four bulk copies on the stage's mbarrier.  Issuing a bulk copy costs its thread a few hundred
   // cycles, so the four go out from lane 0 of different warps; thread 0 arms the barrier with the byte count (the
   // transaction count may run ahead of it, the phase cannot complete before this arrival).
@@ -394,90 +638,16 @@ __global__ void __launch_bounds__(32 * A, ctas_per_sm<OBS, V, A, NST>()) fused2_
       if (dn && p.autoreset) { rare = true; s_flag[lane] = fl1 | FL_BITS_DIRTY | FL_RESET; }
     }
   } else if (mine && a == 0) rare = true;
+  // tiles with a finished env or an env whose planes change: everything rare lives in ONE out-of-line function that
+  // recomputes its pointers, so that it costs the common path a call site and nothing else
   if (__syncthreads_or(rare ? 1 : 0)) {
-    // lane == env in every warp: the envs are dealt out over the CTA's warps (env e goes to warp e % A), so that A warps
-    // instead of one chew through the sequential code of mg_env.cuh; scratch lives in the (not yet used) output tile
-    if (a == lane % A && mine) {
-      uint32_t fl = s_flag[lane];
-      if (fl & (FL_SLOW | FL_RESET)) {
-        EnvCtx<32> c{p, s_trec + lane, tp, bits, s_scr + lane, 0, 0, 0, 0u, false};
-        for (int q = 0; q < A; ++q) { c.R(q, 0) = rec[q * 4]; c.R(q, 1) = rec[q * 4 + 1]; c.R(q, 2) = rec[q * 4 + 2]; }
-        c.sc = s_env[lane * 4]; c.ep = s_env[lane * 4 + 1]; c.tl = s_env[lane * 4 + 2]; c.w3 = (uint32_t)s_env[lane * 4 + 3];
-        const unsigned long long g = (unsigned long long)(p.env_offset + env);
-        if (fl & FL_SLOW) {  // MultiGridEnv.step replayed in the reference's order (base.py:501-649)
-          double rw[MG_MAX_AGENTS];
-          seq_step(c, g, act_g + env * A, rw);
-          bool nd = false;
-          for (int q = 0; q < A; ++q) {
-            nd = nd || !((c.R(q, 0) >> 24) & MG_AF_DONE);
-            if (full) s_rew[lane * A + q] = rw[q]; else rew_g[env * A + q] = rw[q];
-          }
-          const bool dn = (c.sc >= p.max_steps) || !nd;
-          if (full) s_done[lane] = dn ? 1 : 0; else done_g[env] = dn ? 1 : 0;
-          fl = FL_SLOW | (c.dirty ? FL_BITS_DIRTY : 0u) | ((dn && p.autoreset) ? (FL_BITS_DIRTY | FL_RESET) : 0u);
-        }
-        if (fl & FL_RESET) {  // MultiGridEnv.reset (base.py:402-416)
-          // an env whose replayed step edited the planes with plain stores keeps plain stores (no cross-proxy ordering games)
-          if (image_planes && !(fl & FL_SLOW)) { seq_reset<false>(c, g); fl |= FL_IMAGE; } else seq_reset<true>(c, g);
-        }
-        for (int q = 0; q < A; ++q) { rec[q * 4] = c.R(q, 0); rec[q * 4 + 1] = c.R(q, 1); rec[q * 4 + 2] = c.R(q, 2); rec[q * 4 + 3] = 0u; }
-        s_env[lane * 4] = c.sc; s_env[lane * 4 + 1] = c.ep; s_env[lane * 4 + 2] = c.tl; s_env[lane * 4 + 3] = (int)c.w3;
-        s_flag[lane] = fl;
-      }
-    }
-    __syncthreads();
-    if (image_planes) {
-      // The byte planes of the regenerated envs, rebuilt from their bit-plane lines (walls) and object lists (Goal,
-      // BonusTiles) in the -- still unused -- output area, group by group, and stored with bulk copies: a fresh world is
-      // 3*S bytes of mostly zeros, which single lanes writing to global memory would turn into hundreds of scattered stores.
-      const int plane_bytes = 3 * S;
-      const int G = min(ENVS_PER_CTA, SM::OUT_AREA / plane_bytes);
-      const uint32_t image_mask = __ballot_sync(0xFFFFFFFFu, mine && (s_flag[lane] & FL_IMAGE));  // lane == env: the same word in every warp
-      for (int g0 = 0; g0 < n_valid; g0 += G) {
-        const int gn = min(G, n_valid - g0);
-        const uint32_t group_mask = (image_mask >> g0) & (gn == 32 ? 0xFFFFFFFFu : ((1u << gn) - 1u));  // envs of the group that were reset
-        if (group_mask == 0u) continue;
-        {
-          int4* z = reinterpret_cast<int4*>(s_out);
-          for (int i = tid; i < gn * plane_bytes / 16; i += 32 * A) z[i] = make_int4(0, 0, 0, 0);
-        }
-        __syncthreads();
-        for (int i = tid; i < gn * 16; i += 32 * A) {  // one (env, x-line) pair per iteration
-          const int e = i >> 4, x = i & 15;
-          if (x >= W || !((group_mask >> e) & 1u)) continue;
-          const uint32_t* eb = s_bits + (g0 + e) * BITS_WORDS;
-          const uint32_t w = eb[LINE_X0 + x];
-          uint8_t* img = s_out + e * plane_bytes + x * H;
-          uint32_t walls = w & 0xFFFFu & ~(w >> 16), others = w >> 16;
-          while (walls) {
-            const int y = __ffs(walls) - 1;
-            walls &= walls - 1u;
-            img[y] = MG_T_WALL; img[S + y] = MG_C_WORST;
-          }
-          while (others) {
-            const int y = __ffs(others) - 1;
-            others &= others - 1u;
-            const uint32_t oe = obj_lookup(eb, x, y);  // always listed: image_planes requires goal + bonus tiles <= OBJ_SLOTS
-            img[y] = (uint8_t)((oe >> 8) & 15u); img[S + y] = (uint8_t)((oe >> 12) & 15u); img[2 * S + y] = (uint8_t)((oe >> 16) & 255u);
-          }
-        }
-        fence_proxy_async_smem();
-        __syncthreads();
-        if (a == 0) {
-          const bool all = group_mask == (gn == 32 ? 0xFFFFFFFFu : ((1u << gn) - 1u));
-          if (all ? lane == 0 : (lane < gn && ((group_mask >> lane) & 1u))) {
-            fence_proxy_async_smem();
-            if (all) bulk_s2g(p.grid + (env0 + g0) * plane_bytes, s_out, (uint32_t)(gn * plane_bytes));
-            else bulk_s2g(p.grid + (env0 + g0 + lane) * plane_bytes, s_out + lane * plane_bytes, (uint32_t)plane_bytes);
-            bulk_commit();
-            bulk_wait_read0();
-          }
-        }
-        __syncthreads();
-      }
-    }
-    zero_out();  // the sequential path borrowed the output area: clean it again
-    __syncthreads();
+    // Called through a pointer the compiler cannot see through: a direct call lets ptxas allocate registers across caller and
+    // callee, and the values it then spills are stored where they are defined -- on the common path.  An opaque call follows
+    // the ABI instead: the callee saves the registers it clobbers in its own prologue, and the common path has no local-memory
+    // traffic at all (0 bytes of spills, against 24 / 44 before).
+    void (*fn)(const KP&, int, int, int, int) = &f2::rare_path<OBS, V, A, NST, KS>;
+    asm volatile("" : "+l"(fn));
+    fn(p, tile, stage, it, step);
   }
 
   // ---- observe the post-step world: gen_obs_grid + occlude_mask + encode ----

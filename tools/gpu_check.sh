@@ -87,3 +87,6 @@ if [[ "$what" == *soak* ]]; then
   timeout 1200 python tools/soak.py > gpurun_out/soak.log 2>&1; echo "soak exit $?" | tee -a gpurun_out/soak.log
   cat gpurun_out/soak.log | tail -8
 fi
+if [[ "$what" == *desync* ]]; then
+  timeout 600 python tools/desync_probe.py > gpurun_out/desync.log 2>&1; cat gpurun_out/desync.log | tail -10
+fi
