@@ -135,6 +135,127 @@ __device__ __forceinline__ void sts_u8(uint32_t saddr, uint32_t v) {
   asm volatile("st.shared.u8 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
 }
 
+constexpr int WARP_RESET_MAX = 4;  // finished envs per warp up to which the warps regenerate them one by one
+
+// Warp-cooperative reset, for tiles in which only a few envs finish -- the normal state of a long-running batch, whose episodes
+// have drifted apart (tools/desync_probe.py): no table, no CTA-wide barriers, one env at a time per warp.
+// MultiGridEnv.reset (base.py:402-416) + _gen_grid (empty.py:9-16, cluttered.py:25-36, goalcycle.py:30-51) for ONE env by a
+// whole warp: lanes = consecutive placement tries of place_obj's rejection sampling (base.py:690-708).
+//   static objects (random goal, bonus tiles, clutter walls, in this order): scanning the tries in order, a try is accepted
+//     iff its cell is free of walls / objects AND no earlier accepted try hit the same cell (the object placed there is what
+//     the sequential code would find) -- within a batch of 32 tries that is "first valid lane of its cell" (match_any); the
+//     j-th accepted try gets the j-th object.
+//   agents (ghost mode: they may share cells): the tries after the last static object's, each non-wall try places the next agent.
+// Returns false WITHOUT having committed anything when the run is not an ordinary one (a whole batch of 32 tries without a
+// placement -- the only way max_tries, base.py:700-706, could come into play --, or more than MAXB batches): the caller then
+// runs the sequential code.  On success bits / rec / envr (shared memory) hold the new episode.
+template <int A>
+__device__ __forceinline__ bool warp_reset(const KP& p, unsigned long long g, uint32_t* __restrict__ bits, uint32_t* __restrict__ rec,
+                                        int32_t* __restrict__ envr, uint32_t* __restrict__ wk /* 36 words of this warp */, int lane) {
+  constexpr int MAXB = 8;
+  const int W = p.W, H = p.H;
+  uint32_t* wall_x = wk;        // [16] bit y = canonical wall at (x, y)
+  uint32_t* other_x = wk + 16;  // [16] bit y = Goal / BonusTile at (x, y)
+  uint32_t* list = wk + 32;     // [4] object list entries
+  if (lane < 16) {
+    const uint32_t fullr = (1u << H) - 1u, endsr = 1u | (1u << (H - 1));
+    wall_x[lane] = (lane == 0 || lane == W - 1) ? fullr : (lane < W ? endsr : 0u);  // wall_rect base.py:172-176
+    other_x[lane] = (p.goal_mode == MG_GOAL_FIXED && lane == W - 2) ? (1u << (H - 2)) : 0u;  // put_obj(Goal) base.py:655-662
+  }
+  if (lane < OBJ_SLOTS) list[lane] = (lane == 0 && p.goal_mode == MG_GOAL_FIXED) ? obj_entry(W - 2, H - 2, MG_T_GOAL, MG_C_GREEN, 0) : 0u;
+  __syncwarp();
+  const int n_goal = (p.goal_mode == MG_GOAL_RANDOM) ? 1 : 0, n_other = n_goal + p.n_bonus, n_static = n_other + p.n_clutter;
+  const int list_base = (p.goal_mode == MG_GOAL_FIXED) ? 1 : 0;
+  const uint32_t ep = (uint32_t)envr[1], lt = (1u << lane) - 1u;
+  int placed_static = 0, agents_done = 0;
+  uint32_t a_xy = 0;  // lane q < A: where agent q goes (x | y << 8)
+  for (int batch = 0; batch < MAXB; ++batch) {
+    const uint32_t k = (uint32_t)(batch * 32 + lane);
+    const U4 r = philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), ep, TAG_RESET | (k >> 1), (uint32_t)p.seed, (uint32_t)(p.seed >> 32));
+    const int x = (int)__umulhi((k & 1u) ? r.z : r.x, (uint32_t)W), y = (int)__umulhi((k & 1u) ? r.w : r.y, (uint32_t)H);
+    int start_lane = 0;
+    if (placed_static < n_static) {
+      const bool valid = !(((wall_x[x] | other_x[x]) >> y) & 1u);
+      const uint32_t vm = __ballot_sync(0xFFFFFFFFu, valid);
+      bool acc = false;
+      if (valid) acc = (__ffs(__match_any_sync(vm, x * 16 + y)) - 1) == lane;  // first valid try of this cell in the batch
+      const uint32_t am = __ballot_sync(0xFFFFFFFFu, acc);
+      if (am == 0u) return false;
+      const int j = placed_static + __popc(am & lt);  // index of the object this try would place
+      const bool take = acc && j < n_static;
+      const uint32_t tm = __ballot_sync(0xFFFFFFFFu, take);
+      if (take) {
+        if (j < n_other) {
+          atomicOr(&other_x[x], 1u << y);
+          const uint32_t e = (j < n_goal) ? obj_entry(x, y, MG_T_GOAL, MG_C_GREEN, 0) : obj_entry(x, y, MG_T_BONUS, MG_C_YELLOW, j - n_goal);
+          if (list_base + j < OBJ_SLOTS) list[list_base + j] = e;
+        } else atomicOr(&wall_x[x], 1u << y);
+      }
+      placed_static += __popc(tm);
+      __syncwarp();
+      if (placed_static < n_static) continue;
+      start_lane = 32 - __clz(tm);  // the agents' tries begin behind the last static object's
+    }
+    const bool valid_a = lane >= start_lane && !((wall_x[x] >> y) & 1u);
+    const uint32_t vma = __ballot_sync(0xFFFFFFFFu, valid_a);
+    if (vma == 0u) { if (start_lane == 0) return false; else continue; }
+    const int q = agents_done + __popc(vma & lt);
+    const uint32_t xy = (uint32_t)x | ((uint32_t)y << 8);
+#pragma unroll
+    for (int t = 0; t < A; ++t) {  // hand try "q == t" to lane t
+      const uint32_t src = __ballot_sync(0xFFFFFFFFu, valid_a && q == t);
+      if (src) { const uint32_t v = __shfl_sync(0xFFFFFFFFu, xy, __ffs(src) - 1); if (lane == t) a_xy = v; }
+    }
+    agents_done += __popc(vma);
+    if (agents_done >= A) {
+      // ---- commit: records, env record, bit-plane lines (x-lines as sampled, y-lines by transposition), object list ----
+      if (lane < A) {  // agents.py:161-170 (dir survives), placement order = stamp order (base.py:409-412,686)
+        const uint32_t old = rec[lane * 4];
+        *reinterpret_cast<uint4*>(rec + lane * 4) = make_uint4((old & 0x00FF0000u) | a_xy | ((uint32_t)(MG_AF_PLACED | MG_AF_ACTIVE) << 24), 0xFF000000u, (uint32_t)lane, 0u);
+      }
+      if (lane == 0) {
+        envr[0] = 0; envr[1] = (int)(ep + 1u);
+        envr[3] = (int)(((uint32_t)envr[3] & 0xFFFF0000u) | (uint32_t)A);
+      }
+      uint32_t wy = 0, oy = 0;  // lane y < 16: its y-line
+      for (int xx = 0; xx < 16; ++xx) {
+        wy |= ((wall_x[xx] >> (lane & 15)) & 1u) << xx;
+        oy |= ((other_x[xx] >> (lane & 15)) & 1u) << xx;
+      }
+      if (lane < 16) {
+        bits[LINE_X0 + lane] = wall_x[lane] | (other_x[lane] << 16);
+        bits[LINE_Y0 + lane] = wy | (oy << 16);
+      }
+      if (lane < 4) bits[OBJ_WORD0 + lane] = list[lane];
+      if (lane >= 4 && lane < 8) bits[OBJ_WORD0 + lane] = 0u;             // words 40..43
+      if (lane >= 8 && lane < 12) bits[(lane == 8) ? 0 : (lane == 9) ? 17 : (lane == 10) ? 18 : 35] = 0u;  // guard lines
+      __syncwarp();
+      return true;
+    }
+  }
+  return false;
+}
+
+// the finished envs of a tile that the warps regenerate cooperatively (env e -> warp e % A): worth it while few envs of the
+// tile end together (a long-running batch whose episodes have drifted apart: one or two per tile and step); a tile in which
+// most envs end at once (episodes still in lock step) is cheaper with one lane per env on the sequential code
+template <int A>
+__device__ __noinline__ void warp_resets(const KP& p, uint32_t* s_flag, uint32_t* s_bits, uint32_t* s_rec, int32_t* s_env, uint32_t* wk,
+                                         long long env0, int n_valid, int a, int lane) {
+  const uint32_t todo = __ballot_sync(0xFFFFFFFFu, lane < n_valid && (s_flag[lane] & (FL_SLOW | FL_RESET)) == FL_RESET);
+  if (__popc(todo) > WARP_RESET_MAX * A) return;  // many: tile_resets() below
+  for (int e = a; e < n_valid; e += A) {
+    if (!((todo >> e) & 1u)) continue;
+    const uint32_t fl = s_flag[e];
+    if (warp_reset<A>(p, (unsigned long long)(p.env_offset + env0 + e), s_bits + e * BITS_WORDS, s_rec + e * (A * 4), s_env + e * 4, wk, lane)) {
+      if (lane == 0) s_flag[e] = (fl & ~FL_RESET) | FL_IMAGE;
+    }
+    __syncwarp();
+  }
+}
+
+
+
 // Reset of the finished envs of a tile: MultiGridEnv.reset (base.py:402-416) + _gen_grid (empty.py:9-16, cluttered.py:25-36,
 // goalcycle.py:30-51), split so that the expensive part is parallel and the sequential part is cheap.  Per chunk of NT tries:
 //   1. all threads of the CTA draw the Philox blocks of (finished env, block) pairs and leave the tries as cell bytes
@@ -290,7 +411,11 @@ __device__ __noinline__ void rare_path(const KP& p, const int tile, const int st
   {
     // lane == env in every warp: the envs are dealt out over the CTA's warps (env e goes to warp e % A), so that A warps
     // instead of one chew through the sequential code of mg_env.cuh; scratch lives in the (not yet used) output tile
-    if (image_planes) tile_resets<A>(p, s_flag, s_bits, s_rec, s_env, s_scr, env0, n_valid, tid);  // leftovers: sequential code below
+    if (image_planes) {  // few finished envs: warp by warp; many (episodes in lock step): table-driven; leftovers: sequential code below
+      warp_resets<A>(p, s_flag, s_bits, s_rec, s_env, s_scr + a * 64, env0, n_valid, a, lane);
+      __syncthreads();
+      tile_resets<A>(p, s_flag, s_bits, s_rec, s_env, s_scr, env0, n_valid, tid);
+    }
     if (a == lane % A && mine) {
       uint32_t fl = s_flag[lane];
       if (fl & (FL_SLOW | FL_RESET)) {

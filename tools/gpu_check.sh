@@ -90,3 +90,13 @@ fi
 if [[ "$what" == *desync* ]]; then
   timeout 600 python tools/desync_probe.py > gpurun_out/desync.log 2>&1; cat gpurun_out/desync.log | tail -10
 fi
+if [[ "$what" == *final* ]]; then
+  # last call of a round on a tight budget: parity first, then one full ncu capture of the hot kernel, the bench line, the desync probe
+  timeout 120 python -m pytest tests -m gpu -x -q > gpurun_out/tests.log 2>&1; echo "tests exit $?" | tee -a gpurun_out/tests.log
+  tail -2 gpurun_out/tests.log
+  timeout 60 ncu --set full --clock-control none --import-source on -k regex:fused2_kernel -s 40 -c 2 -f -o gpurun_out/prof \
+      python bench.py --steps 20 --warmup 10 --no-cpu-baseline --e2e-steps 3 > gpurun_out/ncu_full.log 2>&1; echo "ncu exit $?"
+  timeout 90 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench exit $?"
+  cat gpurun_out/bench.json
+  timeout 40 python tools/desync_probe.py > gpurun_out/desync.log 2>&1; tail -8 gpurun_out/desync.log
+fi
