@@ -364,6 +364,7 @@ __device__ __forceinline__ void tile_resets(const KP& p, uint32_t* s_flag, uint3
     pending = *s_pending;
     if (pending == 0u) break;
   }
+  __syncthreads();  // the table and s_pending alias the sequential code's scratch: nobody may still be reading them
 }
 
 template <int OBS, int A, class SM>
