@@ -149,6 +149,30 @@ def test_batched_lockstep_vs_oracle(oracle, name, step_impl):
     assert int(env.err.max().item()) == 0
 
 
+@pytest.mark.gpu
+@pytest.mark.skipif(os.environ.get("MG_EXTRA_GPU_TESTS") != "1", reason="round-2 candidate: run by hand once (MG_EXTRA_GPU_TESTS=1) before it joins the suite")
+def test_reset_fall_through_routes_vs_oracle(oracle):
+    """A world so cluttered that runs of 32 failed placement tries are common: the warp / table resets of the fused kernel hand
+    such envs to the sequential code (nothing committed before), which must leave exactly the reference's world (base.py:690-708)."""
+    from marlgrid_b200 import envs
+
+    B, T = 512, 70
+    kw = dict(num_envs=B, obs_mode="encoded", seed=99, clutter_density=None, n_clutter=66, max_steps=6)
+    env = envs.make("MarlGrid-3AgentCluttered11x11-v0", **kw)
+    ob = oracle.OracleBatch(env.cfg, B, seed=99, env_offset=0, threads=8)
+    obs = env.reset()
+    ob.reset()
+    assert np.array_equal(obs.cpu().numpy(), ob.obs_encode())
+    rng = np.random.RandomState(5)
+    for t in range(T):
+        act = rng.randint(0, 7, size=(B, env.num_agents)).astype(np.int32)
+        obs, rew, done, _ = env.step(torch.from_numpy(act).cuda())
+        o2, r2, d2 = ob.step(act, autoreset=True, with_obs=True)
+        assert np.array_equal(obs.cpu().numpy(), o2), f"step {t}: obs"
+        assert np.array_equal(done.cpu().numpy(), d2.astype(bool)), f"step {t}: done"
+        _state_equal(env, ob, f"step {t}")
+
+
 def test_batched_object_interactions_vs_oracle(oracle, step_impl):
     """Keys, balls and doors scattered over full tiles of a batch: the envs whose planes change mid-step (effective
     pickup / drop / toggle, base.py:590-613) take the sequential replay inside the fused kernels, next to envs that do not."""
