@@ -16,6 +16,9 @@ import torch
 from . import _lib
 from . import atlas as _atlas
 from .config import AF_ACTIVE, AF_PLACED, F_SEE_THROUGH, MgState
+from .objects import COLOR_TO_IDX
+
+_PRESTIGE = COLOR_TO_IDX["prestige"]
 
 _ATLAS_CACHE = {}
 
@@ -98,6 +101,8 @@ def render(env, index=0, highlight=True, tile_size=32, show_agent_views=True, ma
     """-> uint8 [H*tile_size, W*tile_size (+ agent view columns), 3]; same keyword arguments as the reference's render."""
     cfg = env.cfg
     A, V, vo, W, H, ts = cfg.n_agents, cfg.view_size, cfg.view_offset, cfg.width, cfg.height, int(tile_size)
+    if any(int(c) == _PRESTIGE for c in cfg.agent_color[:A]):
+        raise NotImplementedError("color='prestige' (agents.py:92-119: tile recoloured by the agent's running reward) is not built yet")
     planes = env.planes[index].cpu().numpy()
     ag = env.agents[index].cpu().numpy()
     placed = (ag[:, 3] & AF_PLACED) != 0

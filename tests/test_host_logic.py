@@ -111,7 +111,7 @@ def test_scenario_kwargs_resolve_like_reference():
     cfg, _ = cfg_of(EmptyMultiGrid, agents=ag[:2], width=9, height=7, max_steps=50, ghost_mode=False, respawn=True, reward_decay=False)
     assert (cfg.width, cfg.height, cfg.max_steps, cfg.flags & 7, cfg.goal_mode) == (9, 7, 50, 2, GOAL_FIXED)
     cfg, _ = cfg_of(ClutteredGoalCycleEnv, agents=[dict(color="prestige", view_size=7, view_offset=1, view_tile_size=11)], grid_size=13,
-                    clutter_density=0.15, n_bonus_tiles=3, penalty=-1.5, max_steps=250, respawn=True)
+                    clutter_density=0.15, n_bonus_tiles=3, penalty=-1.5, max_steps=250, respawn=True, obs_mode="encoded")
     assert (cfg.goal_mode, cfg.n_bonus_tiles, cfg.bonus_penalty, cfg.view_offset, cfg.view_tile_size) == (GOAL_NONE, 3, -1.5, 1, 11)
     assert not (cfg.flags & 4)  # goal-cycle envs default reward_decay=False (goalcycle.py:9,14)
     with pytest.raises(ValueError):
@@ -225,6 +225,16 @@ def test_hide_item_types_mask():
         hide_mask(["Unicorn"])
     assert GridAgentInterface(hide_item_types=["Wall"]).clone().hide_item_types == ["Wall"]
     assert make_config(9, 9, ["red"], hide_types=hide_mask(["Door"])).hide_types == 1 << 11
+
+
+def test_prestige_colour_is_refused_for_pixel_outputs():
+    """agents.py:92-119 recolours a 'prestige' agent's tile from its running reward; the static tile atlas cannot: refuse loudly
+    instead of returning pixels that differ from the reference's (encoded observations only carry the colour index: exact)."""
+    from marlgrid_b200 import envs
+    from marlgrid_b200.agents import GridAgentInterface
+
+    with pytest.raises(NotImplementedError, match="prestige"):
+        envs.ClutteredMultiGrid(agents=[GridAgentInterface(color="prestige")], grid_size=9, n_clutter=3, obs_mode="rgb", device="cpu")
 
 
 def test_grid_recorder_on_a_host_env(tmp_path):
