@@ -3,19 +3,20 @@
 
   python bench.py --gpus 1 --steps K --warmup W                 # this repo's CUDA path
   torchrun --nproc-per-node N ... bench.py --gpus N ...         # N ranks, one per GPU, env-index sharded
-  python bench.py --impl reference ...                          # CPU arm: the oracle port on the host cores
+  python bench.py --impl reference ...                          # CPU arm: the unmodified Python reference on the host cores
 
 A "step" is one env.step() of the whole batch: MarlGrid-3AgentCluttered15x15-v0, 65 536 envs per GPU,
-encoded observations, uniform random actions, auto-reset (BASELINE.json configs[2]; 8 GPUs = the
-sharded family of configs[4]).  One JSON line is printed by rank 0.
+encoded observations, uniform random actions, auto-reset (BASELINE.json configs[2]).  One JSON line is
+printed by rank 0.
 
-Timing: W warm-up steps, then K steps back to back between ONE pair of CUDA events on the launching
-stream.  The steps visit `--replicas` (6) independent env families of 65 536 envs round robin, so a
-family's state has been evicted from the 126 MB L2 by the time it is stepped again ("inputs larger
-than L2"; no flush kernel between launches): `value` = B*K / device time, max over ranks.
-`step_ms_flushed` is the distribution of single steps timed with a 256 MiB flush before each;
-`warm` repeats K steps on one family (state L2-resident: what a rollout loop at this batch sees).  `e2e` drives the C-ABI host
-buffer engine (mg_engine_step): pinned host actions in, obs/rewards/done out, copies inside the timer.
+Timing (`value`): W warm-up steps (+ an untimed clock ramp), then REPEATS x exactly K steps back to back, every
+repeat between its own pair of CUDA events on the launching stream, the whole series between barrier +
+synchronize; `value` = B*K / median repeat (max over ranks per repeat), REPEATS chosen so that the timed region
+lasts >= 60 ms whatever K is.  The steps visit `--replicas` (6) independent env families of 65 536 envs round
+robin, so a family's state has been evicted from the 126 MB L2 by the time it is stepped again ("inputs larger
+than L2"; no flush kernel between launches); `sustained` is the mean over all repeats (all-reset steps included).
+`e2e` drives the C-ABI host-buffer engine (mg_engine_step): pinned host actions in, obs/rewards/done out, copies
+inside the timer; its last step is checked against the oracle outside the timer.
 """
 import argparse
 import json
@@ -30,16 +31,16 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 ENV_ID = "MarlGrid-3AgentCluttered15x15-v0"
-# other BASELINE.json configs, runnable for the record with --workload (the driver's line is always cfg3):
-#   name -> (env id, default batch, obs mode, agents, algorithmic bytes per env-step [SURVEY.md 8(d)])
+# BASELINE.json configs: name -> (env id, batch, obs mode, agents, algorithmic bytes per env-step [SURVEY.md 8(d)])
 WORKLOADS = {
     "cfg3": ("MarlGrid-3AgentCluttered15x15-v0", 65536, "encoded", 3, 1272),
     "cfg2": ("MarlGrid-3AgentCluttered11x11-v0", 4096, "encoded", 3, 957),
     "cfg4": ("MarlGrid-4AgentEmpty9x9-v0", 262144, "rgb", 4, 38070),
+    "cfg5_share": ("MarlGrid-3AgentCluttered15x15-v0", 131072, "encoded", 3, 1272),
 }
 ALGO_BYTES_PER_ENV_STEP = 1272  # 743 read + 522 write + 7 amortised reset (whole env.step)
-ALGO_BYTES_OBS_KERNEL = 1164    # SURVEY.md 8(d) obs-kernel-only figure: read 3*W*H + 16*A = 723, write obs 441
 FALLBACK_HBM_GBS = 6650.0       # /opt/skills/guides/B200_PROFILING.md fallback
+MIN_TIMED_MS = 60.0             # total timed region of the headline figure, whatever --steps is
 
 
 def measured_peak():
@@ -127,8 +128,26 @@ class ClockSampler:
                 "power_w_max": max(self.power) if self.power else None, "reasons": reasons}
 
 
-def cpu_port_throughput(n_envs, threads, target_s=12.0, seed=1337):
-    """The oracle (CPU port of the reference algorithm, oracle/mg_oracle.c) on a bounded sample of the same
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:  # noqa: BLE001
+        return os.cpu_count() or 1
+
+
+def cpu_model():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except Exception:  # noqa: BLE001
+        pass
+    return "unknown"
+
+
+def cpu_port_throughput(n_envs, threads, target_s=10.0, seed=1337):
+    """The oracle (C port of the reference algorithm, oracle/mg_oracle.c) on a bounded sample of the same
     workload: n_envs envs, as many steps as fit ~target_s seconds (probed first), all `threads` host threads."""
     import numpy as np
 
@@ -150,77 +169,96 @@ def cpu_port_throughput(n_envs, threads, target_s=12.0, seed=1337):
     return n_envs * n_steps / dt, dt, n_steps
 
 
-def host_threads():
+def cpu_port_baseline(target_s):
+    thr = host_threads()
+    n_envs = 65536 if thr >= 32 else 8192
+    v, dt, n_steps = cpu_port_throughput(n_envs, thr, target_s=target_s)
+    return {"value": v, "unit": "env-steps/s", "cores": thr, "kind": "port", "cpu": cpu_model(),
+            "sample": f"{n_envs} envs x {n_steps} steps of the same workload ({dt:.1f} s), multithreaded C port of the reference step+reset+encode (oracle/mg_oracle.c)"}
+
+
+def python_reference_baseline(env_id, variant, seconds):
+    """The UNMODIFIED Python reference (oracle/_ref, staged by oracle/stage_reference.py) on all host cores, in a child
+    process (the parent may hold a CUDA context): oracle/reference_bench.py, protocol of BASELINE.md section 3."""
+    procs = host_threads()
     try:
-        return len(os.sched_getaffinity(0))
-    except Exception:  # noqa: BLE001
-        return os.cpu_count() or 1
+        out = subprocess.run([sys.executable, "-m", "oracle.reference_bench", "--env-id", env_id, "--variant", variant, "--procs", str(procs),
+                              "--seconds", str(seconds)], cwd=ROOT, capture_output=True, text=True, timeout=60 + 6 * seconds)
+        for line in reversed(out.stdout.strip().splitlines()):
+            if line.startswith("{"):
+                d = json.loads(line)
+                if "value" in d:
+                    d["cpu"] = cpu_model()
+                    d["sample"] = (f"{procs} processes x {seconds:.0f} s of {env_id} ({variant} observations; {d['steps_timed']} env.step calls), "
+                                   f"unmodified reference from {d['source']}")
+                return d
+        return {"unavailable": "oracle.reference_bench printed no result: " + (out.stderr.strip().splitlines() or ["?"])[-1][:200]}
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": f"{type(e).__name__}: {e}"}
+
+
+def workload_config(args, world):
+    return {
+        "workload": f"{ENV_ID} batch={args.batch_per_gpu}/GPU x {world} GPU(s), encoded obs [B,3,7,7,3] u8, uniform random actions, auto-reset "
+                    f"(BASELINE.json configs[2]{'; the sharded family of configs[4], whose own 131072/GPU share is other_configs.cfg5_share' if world > 1 else ''})",
+        "env_id": ENV_ID, "batch_per_gpu": args.batch_per_gpu, "global_batch": args.batch_per_gpu * world, "n_agents": 3,
+        "parallelism": f"env-index sharding x{world}, no collective on the data path",
+        "l2": f"inputs larger than L2: {getattr(args, 'replicas', 6)} independent env families of batch_per_gpu envs stepped round robin (each step touches ~51 MB, "
+              "a family is revisited after > 126 MB of other traffic); repeats of K steps back to back, one CUDA event pair per repeat, median repeat",
+    }
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference algorithm's CPU implementation (oracle port), all host threads."""
+    """--impl reference: the reference's own CPU implementation of the path -- the unmodified Python package staged in
+    oracle/_ref -- on all host cores (encoded-observation variant of BASELINE.md section 3 for this workload); the
+    multithreaded C port is timed next to it (`cpu_port`, the harder baseline).  A bench "step" of this arm = one env.step
+    on each of the `cores` envs (one per process)."""
     if rank != 0:
         return
-    threads = host_threads()
-    n_envs = 65536 if threads >= 32 else 8192  # a bench "step" of this arm = one env.step over this sample of the batch
-    v, dt, n_steps = cpu_port_throughput(n_envs, threads, target_s=30.0)
-    sample = (f"{n_envs} envs x {n_steps} steps ({dt:.1f} s) of the same workload, C port of the reference step+reset+encode "
-              f"(oracle/mg_oracle.c), {threads} threads")
+    py = python_reference_baseline(ENV_ID, "encoded", seconds=20.0)
+    port = cpu_port_baseline(target_s=12.0)
+    if "value" in py:
+        v, cores, kind, sample = py["value"], py["cores"], "reference", py["sample"]
+    else:  # oracle/_ref was not staged on this box: fall back to the port, and say so
+        v, cores, kind, sample = port["value"], port["cores"], "port", port["sample"] + f" [python reference unavailable: {py.get('unavailable')}]"
     line = {
         "impl": "reference", "metric": "env-steps/s", "value": v, "unit": "env-steps/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * n_envs / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": args.warmup, "ms_per_step": 1e3 * cores / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic", "config": workload_config(args, world),
-        "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": cores, "kind": kind, "sample": sample, "cpu": cpu_model(),
+                         "per_core_mean": py.get("per_core_mean"), "model": py.get("model")},
+        "cpu_port": port,
         "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "agent_steps_per_s": 3 * v,
     }
     print(json.dumps(line), flush=True)
 
 
-def workload_config(args, world):
-    return {
-        "workload": f"{ENV_ID} batch={args.batch_per_gpu}/GPU x {world} GPU(s), encoded obs [B,3,7,7,3] u8, uniform random actions, auto-reset "
-                    f"(BASELINE.json configs[2]{'; sharded family of configs[4]' if world > 1 else ''})",
-        "env_id": ENV_ID, "batch_per_gpu": args.batch_per_gpu, "global_batch": args.batch_per_gpu * world, "n_agents": 3,
-        "parallelism": f"env-index sharding x{world}, no collective on the data path",
-        "l2": f"inputs larger than L2: {getattr(args, 'replicas', 6)} independent env families of batch_per_gpu envs stepped round robin (each step touches ~51 MB, "
-              "a family is revisited after > 126 MB of other traffic); K steps back to back, one CUDA event pair",
-    }
+def pin_to_gpu_numa_node(local_rank):
+    """Run this rank's host thread -- and therefore first-touch its pinned buffers -- on the CPUs NVML reports as local to its
+    GPU (e2e at N > 1: all ranks copying through one NUMA node was a suspect for the flat 1 -> 8 GPU curve of round 1)."""
+    try:
+        import pynvml
 
-
-def run_other_workload(args):
-    """Device-side throughput of another BASELINE config (cold, per-step events) -- informational line."""
-    import torch
-
-    from marlgrid_b200 import envs
-
-    env_id, B, mode, A, algo = WORKLOADS[args.workload]
-    if args.batch_per_gpu != 65536:
-        B = args.batch_per_gpu
-    env = envs.make(env_id, num_envs=B, obs_mode=mode, seed=1337)
-    env.reset()
-    acts = [env.random_actions(t) for t in range(32)]
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=env.device)
-    for t in range(args.warmup):
-        env.step(acts[t % 32])
-    K = args.steps
-    st = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
-    en = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
-    torch.cuda.synchronize()
-    for t in range(K):
-        flush.fill_(t & 0xFF)
-        st[t].record()
-        env.step(acts[t % 32])
-        en[t].record()
-    torch.cuda.synchronize()
-    ms = sorted(a.elapsed_time(b) for a, b in zip(st, en))
-    tot = sum(ms)
-    peak, src = measured_peak()
-    ach = algo * B / (tot / K * 1e-3) / 1e9
-    print(json.dumps({"metric": "env-steps/s", "workload": args.workload, "env_id": env_id, "batch": B, "obs": mode, "value": B * K / (tot * 1e-3),
-                      "agent_steps_per_s": A * B * K / (tot * 1e-3), "ms_per_step": tot / K, "step_ms_median": ms[K // 2], "steps": K,
-                      "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                                   "algorithmic_bytes_per_launch": algo * B, "peak_source": src}}), flush=True)
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = local_rank
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if local_rank < len(ids) and ids[local_rank].isdigit():
+                idx = int(ids[local_rank])
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        n_words = (os.cpu_count() + 63) // 64
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if allowed:
+            before = len(os.sched_getaffinity(0))
+            os.sched_setaffinity(0, allowed)
+            return {"cpus_local_to_gpu": len(allowed), "cpus_before": before}
+    except Exception as e:  # noqa: BLE001
+        return {"error": f"{type(e).__name__}: {e}"}
+    return {"cpus_local_to_gpu": 0}
 
 
 def main():
@@ -233,11 +271,10 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=100)
     ap.add_argument("--replicas", type=int, default=6, help="independent env families visited round robin in the timed loop (working set > L2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--quick", action="store_true", help="headline figure only (profiling runs): no other_configs / desync / CPU arms")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
-    if args.workload != "cfg3":
-        return run_other_workload(args)
+    args.steps = max(args.steps, 1)
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -261,11 +298,25 @@ def main():
 
         dist = dist_mod
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = "WARN"  # NCCL's version banner goes to stdout: rank 0 must print ONE JSON line
+        # communicator lines (rank / nranks) stay visible for the driver, but on stderr: stdout carries the JSON line
+        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
     B, K, W = args.batch_per_gpu, args.steps, args.warmup
     L = _lib.load()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(values):
+        t = torch.tensor(values, dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(x) for x in t.tolist()]
 
     # R independent env families of B envs each, stepped round robin: between two visits of a family the other R-1 steps
     # touch (R-1) x ~51 MB (bit-plane lines, records, actions in; observations, records, rewards out), more than the 126 MB
@@ -282,99 +333,207 @@ def main():
         env.random_actions(t, seed=rank, out=actions[t])
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     torch.cuda.synchronize()
-    states = (MgState * R)(*[f._state for f in fams])
     PP = ctypes.c_void_p * R
-    rew_p, done_p, obs_p = PP(*[f.rewards.data_ptr() for f in fams]), PP(*[f.done.data_ptr() for f in fams]), PP(*[f.obs.data_ptr() for f in fams])
+    rotations = []  # the round robin continues across calls: rotation r starts at family r
+    for r0 in range(R):
+        order = [fams[(r0 + i) % R] for i in range(R)]
+        rotations.append(((MgState * R)(*[f._state for f in order]), PP(*[f.rewards.data_ptr() for f in order]),
+                          PP(*[f.done.data_ptr() for f in order]), PP(*[f.obs.data_ptr() for f in order])))
     stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    cfg_ref = ctypes.byref(env.cfg)
+    step_no = [0]  # global step counter of the round robin
 
-    def rollout_rr(n_steps):
-        done_steps = 0
-        while done_steps < n_steps:  # chunks of POOL steps (a multiple of R: the round robin continues seamlessly)
-            n = min(POOL - POOL % R, n_steps - done_steps)
-            _lib.check(L.mg_rollout_fused_rr(ctypes.byref(env.cfg), states, R, actions.data_ptr(), n, rew_p, done_p, obs_p, 1, stream), "mg_rollout_fused_rr")
-            done_steps += n
+    def run_steps(n):
+        while n > 0:
+            m = min(n, POOL)
+            st, rp, dp, op = rotations[step_no[0] % R]
+            _lib.check(L.mg_rollout_fused_rr(cfg_ref, st, R, actions.data_ptr(), m, rp, dp, op, 1, stream), "mg_rollout_fused_rr")
+            step_no[0] += m
+            n -= m
 
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---- warm-up -------------------------------------------------------------------------------
-    rollout_rr(max(W, R) // R * R)
+    # ---- warm-up: W steps, then an untimed clock ramp (a fresh box idles at ~800 MHz) -----------------------------
+    run_steps(W)
+    ramp_steps = 0
+    if not args.quick:
+        t0 = time.perf_counter()
+        while time.perf_counter() - t0 < 0.25:
+            run_steps(120)
+            ramp_steps += 120
+            torch.cuda.synchronize()
     barrier()
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    # ---- timed: K cold steps back to back, one event pair -----------------------------------------
-    K = max(K // R, 1) * R
+    # ---- timed: REPEATS x exactly K cold steps, back to back, one event pair per repeat ------------------------------
+    est_us = 16.0 * max(1.0, B / 65536.0)
+    REPEATS = int(min(3000, max(5, -(-MIN_TIMED_MS * 1e3 // (K * est_us)))))
+    if args.quick:
+        REPEATS = 2
     launches0 = L.mg_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(REPEATS + 1)]
     barrier()
     wall0 = time.perf_counter()
-    e0.record()
-    rollout_rr(K)  # ONE launch per step: fused step + auto-reset + observe kernel
-    e1.record()
+    evs[0].record()
+    for i in range(REPEATS):
+        run_steps(K)  # ONE launch per step: fused step + auto-reset + observe kernel
+        evs[i + 1].record()
     barrier()
     wall_cold = time.perf_counter() - wall0
     launches = L.mg_launch_count() - launches0
-    cold_total_ms = float(e0.elapsed_time(e1))
-
-    # ---- secondary: per-step events with a 256 MiB L2 flush before each step (distribution of single cold steps) ----
-    KF = min(K, 300)
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(KF)]
-    stops = [torch.cuda.Event(enable_timing=True) for _ in range(KF)]
-    for t in range(KF):
-        flush.fill_(t & 0xFF)
-        starts[t].record()
-        env.step(actions[t % POOL])
-        stops[t].record()
-    barrier()
-    cold_ms = [s.elapsed_time(e) for s, e in zip(starts, stops)]
-
-    # ---- timed: K warm steps back to back on ONE family (state L2-resident: what a rollout loop at this batch sees) ----
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    done_steps = 0
-    while done_steps < K:
-        n = min(POOL, K - done_steps)
-        env.rollout(actions[:n])
-        done_steps += n
-    e1.record()
-    barrier()
-    warm_total_ms = e0.elapsed_time(e1)
-
-    # ---- on-device rollout loop: 100 steps per launch (mg_rollout_persistent), every step's outputs written to its own slice ----
-    TP = 100
-    pout = (torch.empty((TP, B, A, 7, 7, 3), dtype=torch.uint8, device=dev), torch.empty((TP, B, A), dtype=torch.float64, device=dev),
-            torch.empty((TP, B), dtype=torch.bool, device=dev))
-    env.rollout_all(actions[:TP], out=pout)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(5):
-        env.rollout_all(actions[:TP], out=pout)
-    e1.record()
-    barrier()
-    persistent_ms = e0.elapsed_time(e1) / (5 * TP)
-    del pout
-
-    # ---- the same K warm steps through the Python surface, env.step(actions) called in a Python loop -------------------
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0 = time.perf_counter()
-    e0.record()
-    for t in range(K):
-        env.step(actions[t % POOL])
-    e1.record()
-    host_issue_s = time.perf_counter() - t0  # time the host needed to enqueue K steps
-    barrier()
-    py_total_ms = e0.elapsed_time(e1)
+    rep_ms = max_over_ranks([evs[i].elapsed_time(evs[i + 1]) for i in range(REPEATS)])
     clocks = sampler.stop() if rank == 0 else None
+    srt_rep = sorted(rep_ms)
+    median_ms, total_ms = srt_rep[len(srt_rep) // 2], sum(rep_ms)
+
+    extras = {}
+    if not args.quick:
+        # ---- secondary: per-step events with a 256 MiB L2 flush before each step (distribution of single cold steps) ----
+        KF = 100
+        starts = [torch.cuda.Event(enable_timing=True) for _ in range(KF)]
+        stops = [torch.cuda.Event(enable_timing=True) for _ in range(KF)]
+        for t in range(KF):
+            flush.fill_(t & 0xFF)
+            starts[t].record()
+            env.step(actions[t % POOL])
+            stops[t].record()
+        barrier()
+        srt = sorted(s.elapsed_time(e) for s, e in zip(starts, stops))
+        extras["step_ms_flushed"] = {"min": srt[0], "median": srt[len(srt) // 2], "p99": srt[min(len(srt) - 1, int(0.99 * len(srt)))], "max": srt[-1], "steps": len(srt),
+                                     "note": "secondary: single steps, 256 MiB L2 flush before each, per-step CUDA events (~2 us resolution)"}
+
+        # ---- the all-reset step: every episode of the family ends on the same step (uniform random actions keep them in lock step) ----
+        reset_us = []
+        for _ in range(3):
+            env.reset()
+            env.rollout(actions[:99])
+            flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            env.step(actions[99])
+            e1.record()
+            torch.cuda.synchronize()
+            assert float(env.done.float().mean().item()) > 0.99  # (an env whose agents all reached the goal earlier is on another schedule)
+            reset_us.append(1e3 * e0.elapsed_time(e1))
+        extras["all_reset_us"] = sorted(max_over_ranks(reset_us))[1]
+
+        # ---- K warm steps back to back on ONE family (state L2-resident: what a rollout loop at this batch sees) ----
+        KW = max(K, 500)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        done_steps = 0
+        while done_steps < KW:
+            n = min(POOL, KW - done_steps)
+            env.rollout(actions[:n])
+            done_steps += n
+        e1.record()
+        barrier()
+        warm_ms = max_over_ranks([e0.elapsed_time(e1) / KW])[0]
+        extras["warm"] = {"value": world * B / (warm_ms * 1e-3), "ms_per_step": warm_ms, "steps": KW,
+                          "note": "steps back to back on one family, state L2-resident, launched from mg_rollout_fused"}
+
+        # ---- desynchronised episodes (tools/desync_probe.py in short): a forward-biased policy ends episodes at irregular times ----
+        dact = actions.clone()
+        dact[torch.rand(dact.shape, device=dev) < 0.5] = 2
+        env.reset()
+        blocks = []
+        for _ in range(6):  # 6 x 512 steps
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _k in range(4):
+                env.rollout(dact)
+            e1.record()
+            torch.cuda.synchronize()
+            blocks.append(1e3 * e0.elapsed_time(e1) / (4 * POOL))
+        dlast = max_over_ranks([blocks[-1]])[0]
+        extras["desync"] = {"us_per_step_blocks_of_512": blocks, "us_per_step": dlast, "vs_lockstep_warm": dlast / (1e3 * warm_ms),
+                            "note": "one family (L2-resident), half of the actions forced to `forward`: after ~3000 steps most steps find a few finished envs in many tiles; "
+                                    "ratio against `warm` (same regime, episodes in lock step)"}
+        del dact
+
+        # ---- on-device rollout loop: 100 steps per launch (mg_rollout_persistent), every step's outputs written to its own slice ----
+        TP = 100
+        pout = (torch.empty((TP, B, A, 7, 7, 3), dtype=torch.uint8, device=dev), torch.empty((TP, B, A), dtype=torch.float64, device=dev),
+                torch.empty((TP, B), dtype=torch.bool, device=dev))
+        env.rollout_all(actions[:TP], out=pout)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            env.rollout_all(actions[:TP], out=pout)
+        e1.record()
+        barrier()
+        persistent_ms = max_over_ranks([e0.elapsed_time(e1) / (5 * TP)])[0]
+        del pout
+        extras["rollout_persistent"] = {"value": world * B / (persistent_ms * 1e-3), "ms_per_step": persistent_ms, "steps_per_launch": TP,
+                                        "note": "on-device rollout loop (mg_rollout_persistent): 100 steps per launch on a fixed action tape, tile state resident in "
+                                                "shared memory between steps, every step's obs / rewards / done written to HBM (informational: open-loop)"}
+
+        # ---- the same warm steps through the Python surface, env.step(actions) called in a Python loop -------------------
+        KP_ = max(K, 500)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for t in range(KP_):
+            env.step(actions[t % POOL])
+        e1.record()
+        host_issue_s = time.perf_counter() - t0  # time the host needed to enqueue the steps
+        barrier()
+        py_ms = e0.elapsed_time(e1) / KP_
+        extras["python_api"] = {"value": world * B / (py_ms * 1e-3), "ms_per_step": py_ms, "host_issue_ms_per_step": 1e3 * host_issue_s / KP_,
+                                "note": "env.step(actions) in a Python loop on one family (rank 0's figures; host-bound when host_issue_ms_per_step ~ ms_per_step)"}
     del fams[1:]
+    del rotations
+    torch.cuda.empty_cache()
+
+    # ---- other BASELINE configs, measured in the same run (device-timed, max over ranks) --------------------------------
+    other = {}
+    if not args.quick:
+        peak, _ = measured_peak()
+
+        def timed_rollout(make_env, n_fams, steps, name):
+            env_id, Bo, mode, Ao, algo = WORKLOADS[name]
+            fs = [make_env(r) for r in range(n_fams)]
+            for f in fs:
+                f.reset()
+            acts = [fs[0].random_actions(t, seed=rank) for t in range(16)]
+            for t in range(max(3, n_fams)):
+                fs[t % n_fams].step(acts[t % 16])
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            e0.record()
+            for t in range(steps):
+                fs[t % n_fams].step(acts[t % 16])
+            e1.record()
+            host_s = time.perf_counter() - t0
+            barrier()
+            ms = max_over_ranks([e0.elapsed_time(e1) / steps])[0]
+            ach = algo * Bo / (ms * 1e-3) / 1e9
+            del fs
+            torch.cuda.empty_cache()
+            return {"env_id": env_id, "batch_per_gpu": Bo, "obs": mode, "value": world * Bo / (ms * 1e-3), "agent_steps_per_s": world * Ao * Bo / (ms * 1e-3),
+                    "ms_per_step": ms, "steps": steps, "host_issue_ms_per_step": 1e3 * host_s / steps,
+                    "roofline": {"achieved": ach, "peak": peak, "frac": ach / peak, "algorithmic_bytes_per_launch": algo * Bo}}
+
+        def mk(name, **kw):
+            env_id, Bo, mode, _, _ = WORKLOADS[name]
+            return lambda r: envs.make(env_id, num_envs=Bo, obs_mode=mode, seed=1337, env_offset=(rank * 8 + r) * Bo, device=dev, **kw)
+
+        # cfg2: 4 096 envs -- 128 tiles, launch / latency bound; the state of one family is L2-resident whatever one does
+        other["cfg2"] = timed_rollout(mk("cfg2"), 1, 400, "cfg2")
+        other["cfg2"]["note"] = "BASELINE configs[1]; env.step() in a Python loop (one launch per step), state L2-resident (1 MB)"
+        # cfg5's per-GPU share: 131 072 envs; 3 families round robin (a step touches ~100 MB)
+        other["cfg5_share"] = timed_rollout(mk("cfg5_share"), 3, 120, "cfg5_share")
+        other["cfg5_share"]["note"] = "BASELINE configs[4] per-GPU share (131 072 envs/GPU; x N GPUs = the sharded batch), 3 families round robin"
+        # cfg4: RGB, 262 144 envs, 9.9 GB of observations per step (>> L2)
+        other["cfg4"] = timed_rollout(mk("cfg4", obs_buffers=1), 1, 12, "cfg4")
+        other["cfg4"]["note"] = "BASELINE configs[3]; RGB observations [B,4,56,56,3] u8, every step writes 9.9 GB"
 
     # ---- e2e: host buffers through the C ABI engine ----------------------------------------------
+    numa = pin_to_gpu_numa_node(local_rank) if world > 1 else None
     h = ctypes.c_void_p()
     _lib.check(L.mg_engine_create(ctypes.byref(h), ctypes.byref(env.cfg), B, rank * B, 1337, local_rank, 0, None, 0), "mg_engine_create")
     obs_bytes, rew_bytes, act_bytes = B * A * 147, B * A * 8, B * A * 4
@@ -388,74 +547,102 @@ def main():
         np.ctypeslib.as_array(ctypes.cast(pa, ctypes.POINTER(ctypes.c_int32)), shape=(B * A,))[:] = host_actions[i]
         p_acts.append(pa)
     _lib.check(L.mg_engine_reset(h, p_obs), "mg_engine_reset")
-    for t in range(5):
+    KE = args.e2e_steps
+    WE = 5
+    for t in range(WE):
         _lib.check(L.mg_engine_step(h, p_acts[t % 8], p_obs, p_rew, p_done, 1), "mg_engine_step")
     barrier()
     t0 = time.perf_counter()
-    KE = args.e2e_steps
     for t in range(KE):
-        _lib.check(L.mg_engine_step(h, p_acts[t % 8], p_obs, p_rew, p_done, 1), "mg_engine_step")
+        _lib.check(L.mg_engine_step(h, p_acts[(WE + t) % 8], p_obs, p_rew, p_done, 1), "mg_engine_step")
     barrier()
     e2e_s = time.perf_counter() - t0
-    obs_last = np.ctypeslib.as_array(ctypes.cast(p_obs, ctypes.POINTER(ctypes.c_uint8)), shape=(obs_bytes,))
-    e2e_checksum = int(obs_last[:: 4099].astype(np.int64).sum())
-    L.mg_engine_destroy(h)
+    # the copy ceiling of this box: the same transfers (same buffers, same slicing, same streams) without the kernel
+    barrier()
+    t0 = time.perf_counter()
+    for t in range(KE):
+        _lib.check(L.mg_engine_copy_only(h, p_acts[t % 8], p_obs, p_rew, p_done), "mg_engine_copy_only")
+    barrier()
+    copy_s = time.perf_counter() - t0
+    e2e_ms, copy_ms = max_over_ranks([e2e_s * 1e3, copy_s * 1e3])
+    # outside the timer: the last step's results against the oracle replaying the same actions (rank 0)
+    e2e_parity = None
+    if rank == 0 and not args.no_cpu_baseline:
+        from oracle import mg_oracle
 
-    # ---- max over ranks --------------------------------------------------------------------------
-    times = torch.tensor([cold_total_ms, warm_total_ms, e2e_s * 1e3, persistent_ms], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    cold_total_ms, warm_total_ms, e2e_ms, persistent_ms = (float(x) for x in times.tolist())
+        # the copy-only loop overwrote the host buffers with the device's (unchanged) last results: still the last step's outputs
+        obs_last = np.ctypeslib.as_array(ctypes.cast(p_obs, ctypes.POINTER(ctypes.c_uint8)), shape=(B, A, 7, 7, 3))
+        rew_last = np.ctypeslib.as_array(ctypes.cast(p_rew, ctypes.POINTER(ctypes.c_double)), shape=(B, A))
+        done_last = np.ctypeslib.as_array(ctypes.cast(p_done, ctypes.POINTER(ctypes.c_uint8)), shape=(B,))
+        ob = mg_oracle.OracleBatch(env.cfg, B, seed=1337, env_offset=0, threads=host_threads())
+        ob.reset()
+        o2 = r2 = d2 = None
+        for t in range(WE + KE):
+            last = t == WE + KE - 1
+            res = ob.step(host_actions[t % 8].reshape(B, A), autoreset=True, with_obs=last)
+            if last:
+                o2, r2, d2 = res
+        ok = bool(np.array_equal(obs_last, o2) and np.array_equal(rew_last.view(np.uint64), r2.view(np.uint64)) and np.array_equal(done_last, d2))
+        e2e_parity = {"ok": ok, "checked": f"obs / reward bits / done of step {WE + KE} of all {B} envs == oracle replay of the same host actions",
+                      "obs_checksum": int(obs_last.reshape(-1)[::4099].astype(np.int64).sum())}
+    L.mg_engine_destroy(h)
 
     if rank == 0:
         peak, peak_src = measured_peak()
-        value = world * B * K / (cold_total_ms * 1e-3)
-        warm_value = world * B * K / (warm_total_ms * 1e-3)
+        value = world * B * K / (median_ms * 1e-3)
+        sustained = world * B * K * REPEATS / (total_ms * 1e-3)
         e2e_value = world * B * KE / (e2e_ms * 1e-3)
-        srt = sorted(cold_ms)
-        avg_step_s = (cold_total_ms / K) * 1e-3           # one launch per step, back to back: the kernel's average launch duration (launch gaps included)
-        med_step_s = srt[len(srt) // 2] * 1e-3            # flushed single step on which no episode ends (99 of 100); event resolution ~2 us
+        d2h = obs_bytes + rew_bytes + B
+        avg_step_s = (median_ms / K) * 1e-3  # one launch per step, back to back: the kernel's average launch duration (launch gaps included)
         achieved = ALGO_BYTES_PER_ENV_STEP * B / avg_step_s / 1e9
-        traffic = None
+        traffic, traffic_src = None, None
         try:
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-                traffic = json.load(f).get("fused_kernel_dram_bytes_per_launch")
+                tj = json.load(f)
+                traffic, traffic_src = tj.get("fused_kernel_dram_bytes_per_launch"), tj.get("source")
         except Exception:  # noqa: BLE001
             pass
-        cpu = None
-        if not args.no_cpu_baseline and world == 1:
-            thr = host_threads()
-            n_envs = 65536 if thr >= 32 else 8192
-            v, dt, n_steps = cpu_port_throughput(n_envs, thr, target_s=22.0)
-            cpu = {"value": v, "unit": "env-steps/s", "cores": thr, "kind": "port",
-                   "sample": f"{n_envs} envs x {n_steps} steps of the same workload ({dt:.1f} s), C port of the reference step+reset+encode (oracle/mg_oracle.c)"}
+        cpu = cpu_py = None
+        if not args.no_cpu_baseline and not args.quick:
+            cpu_py = python_reference_baseline(ENV_ID, "encoded", seconds=8.0)
+            cpu_port = cpu_port_baseline(target_s=8.0)
+            if "value" in cpu_py:
+                cpu = {"value": cpu_py["value"], "unit": "env-steps/s", "cores": cpu_py["cores"], "kind": "reference", "sample": cpu_py["sample"],
+                       "cpu": cpu_py["cpu"], "per_core_mean": cpu_py["per_core_mean"], "model": cpu_py["model"]}
+            else:
+                cpu = dict(cpu_port, note=f"python reference unavailable: {cpu_py.get('unavailable')}")
+            extras["cpu_port"] = cpu_port
+            extras["cpu_baseline_python"] = cpu_py
+            extras["cpu_baseline_python_rgb"] = python_reference_baseline(ENV_ID, "rgb", seconds=5.0)
         line = {
             "metric": "env-steps/s", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": cold_total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+            "ms_per_step": median_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
             "data": "synthetic", "config": workload_config(args, world),
             "agent_steps_per_s": value * A,
-            "step_ms_flushed": {"min": srt[0], "median": srt[len(srt) // 2], "p99": srt[min(len(srt) - 1, int(0.99 * len(srt)))], "max": srt[-1], "steps": len(srt),
-                                "note": "secondary: single steps, 256 MiB L2 flush before each, per-step CUDA events (~2 us resolution)"},
-            "warm": {"value": warm_value, "ms_per_step": warm_total_ms / K, "note": "K steps back to back, state L2-resident, launched from mg_rollout_fused"},
-            "rollout_persistent": {"value": world * B / (persistent_ms * 1e-3), "ms_per_step": persistent_ms, "steps_per_launch": TP,
-                                   "note": "on-device rollout loop (mg_rollout_persistent): 100 steps per launch on a fixed action tape, the tiles' state stays in "
-                                           "shared memory between steps, every step's obs / rewards / done go to their own HBM slice (informational: an "
-                                           "open-loop rollout; `value` is one launch per step)"},
-            "python_api": {"value": world * B * K / (py_total_ms * 1e-3), "ms_per_step": py_total_ms / K, "host_issue_ms_per_step": 1e3 * host_issue_s / K,
-                           "note": "env.step(actions) in a Python loop on one family (rank 0's figures; host-bound when host_issue_ms_per_step ~ ms_per_step)"},
-            "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": act_bytes, "d2h_bytes_per_step": obs_bytes + rew_bytes + B,
-                    "steps": KE, "api": "mg_engine_step (C ABI, pinned host buffers, synchronous; batch cut into 4 env ranges whose D2H copies overlap the next range's kernel)", "checksum": e2e_checksum},
+            "timing": {"repeats": REPEATS, "steps_per_repeat": K, "timed_region_ms": total_ms, "repeat_ms": {"min": srt_rep[0], "median": median_ms, "max": srt_rep[-1]},
+                       "ramp_steps": ramp_steps,
+                       "note": "value = B*K / median repeat; each repeat = exactly K launches between its own CUDA event pair, repeats enqueued back to back"},
+            "sustained": {"value": sustained, "ms_per_step": total_ms / (K * REPEATS),
+                          "note": "mean over all repeats: includes the all-reset steps (every 100th step of a family regenerates all its envs)"},
+            "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": act_bytes, "d2h_bytes_per_step": d2h,
+                    "steps": KE, "api": "mg_engine_step (C ABI, pinned host buffers, synchronous; batch cut into 4 env ranges whose D2H copies overlap the next range's kernel)",
+                    "copy_ceiling": {"value": world * B * KE / (copy_ms * 1e-3), "gbs": world * (d2h + act_bytes) * KE / (copy_ms * 1e-3) / 1e9,
+                                     "note": "the same H2D / D2H transfers (same pinned buffers, slices and streams) without the kernel, all ranks concurrently"},
+                    "frac_of_copy_ceiling": copy_ms / e2e_ms, "parity": e2e_parity, "numa": numa},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "kernel": "fused2_kernel<V=7,A=3> (env.step + auto-reset + egocentric encode: the only launch of a step)",
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                         "kernel": "fused2_kernel<OBS=1,V=7,A=3> (env.step + auto-reset + egocentric encode: the only launch of a step)",
                          "algorithmic_bytes_per_launch": ALGO_BYTES_PER_ENV_STEP * B, "avg_launch_ms": avg_step_s * 1e3,
                          "peak_source": peak_src,
-                         "note": "algorithmic bytes = SURVEY.md 8(d) 1272 B/env-step x 65536; K launches back to back over env families larger than L2, one CUDA event pair",
-                         "flushed_median_launch": {"ms": med_step_s * 1e3, "frac": ALGO_BYTES_PER_ENV_STEP * B / med_step_s / 1e9 / peak}},
+                         "note": "algorithmic bytes = SURVEY.md 8(d) 1272 B/env-step x envs per launch; launch duration = median K-step repeat / K (back to back over env "
+                                 "families larger than L2, launch gaps included)",
+                         "sustained_frac": ALGO_BYTES_PER_ENV_STEP * B / (total_ms / (K * REPEATS) * 1e-3) / 1e9 / peak},
+            "other_configs": other,
             "cpu_baseline": cpu,
             "clocks": clocks,
             "wall_s": {"cold_loop": wall_cold},
         }
+        line.update(extras)
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()

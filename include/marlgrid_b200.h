@@ -229,6 +229,9 @@ int mg_engine_reset(MgEngine* e, uint8_t* obs_host);
 /* env.step(actions): H2D actions, fused step kernel, D2H obs/rewards/done; returns after the copies. */
 int mg_engine_step(MgEngine* e, const int32_t* actions_host, uint8_t* obs_host, double* rewards_host,
                    uint8_t* done_host, int autoreset);
+/* The host<->device transfers of mg_engine_step WITHOUT the kernel (same buffers, slices and streams): measures the copy
+ * ceiling of the box that the end-to-end figure is bound by (bench.py e2e.copy_ceiling). */
+int mg_engine_copy_only(MgEngine* e, const int32_t* actions_host, uint8_t* obs_host, double* rewards_host, uint8_t* done_host);
 /* Pinned host allocation helpers so callers without a CUDA runtime can get page-locked buffers. */
 void* mg_host_alloc(int64_t bytes);
 void mg_host_free(void* p);

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(HERE, "libmarlgrid_b200.so")
 EXPORTS = (
     "mg_version", "mg_build_info", "mg_sizeof_config", "mg_config_validate", "mg_obs_bytes_per_env", "mg_init", "mg_sync_derived", "mg_reset", "mg_step",
     "mg_obs_encode", "mg_obs_rgb", "mg_step_fused", "mg_step_fused_rgb", "mg_rollout_fused", "mg_rollout_persistent", "mg_rollout_fused_rr", "mg_random_actions",
-    "mg_los_batch", "mg_engine_create", "mg_engine_destroy", "mg_engine_reset", "mg_engine_step", "mg_host_alloc",
+    "mg_los_batch", "mg_engine_create", "mg_engine_destroy", "mg_engine_reset", "mg_engine_step", "mg_engine_copy_only", "mg_host_alloc",
     "mg_host_free", "mg_launch_count", "mg_debug_set_mid_event", "mg_debug_force_two_kernels", "mg_debug_force_general_fused",
 )
 
@@ -28,13 +28,17 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH) and int(os.environ.get("WORLD_SIZE", "1")) == 1:
-        try:  # a fresh checkout: compile the CUDA library in tree (nvcc cross-compiles sm_100a without a GPU)
+    if int(os.environ.get("WORLD_SIZE", "1")) == 1 and os.environ.get("MG_NO_AUTOBUILD") != "1":
+        # a fresh checkout, or csrc edited since the library was linked: (re)compile in tree (nvcc cross-compiles sm_100a
+        # without a GPU).  Under torchrun the ranks would race, so there the library must have been built beforehand.
+        try:
             from . import build as _build
 
-            _build.build()
-        except Exception:  # noqa: BLE001 -- reported below
-            pass
+            if not os.path.exists(LIB_PATH) or _build.needs_build():
+                _build.build()
+        except Exception as e:  # noqa: BLE001 -- a missing library is reported below; a stale one must not pass silently
+            if os.path.exists(LIB_PATH):
+                raise MarlgridLibraryError(f"{LIB_PATH} is older than marlgrid_b200/csrc and rebuilding it failed: {e}") from e
     if not os.path.exists(LIB_PATH):
         raise MarlgridLibraryError(
             f"{LIB_PATH} not found: the CUDA extension is not built. Run `python -c 'import __graft_entry__ as g; g.build()'` "
@@ -69,6 +73,7 @@ def load():
     L.mg_engine_destroy.restype = None
     L.mg_engine_reset.argtypes = [P, P]
     L.mg_engine_step.argtypes = [P, P, P, P, P, I]
+    L.mg_engine_copy_only.argtypes = [P, P, P, P, P]
     L.mg_host_alloc.argtypes = [I64]
     L.mg_host_alloc.restype = P
     L.mg_host_free.argtypes = [P]
@@ -96,4 +101,7 @@ def check(code, what):
         return
     if code > 0:
         raise RuntimeError(f"{what}: CUDA error {code}")
-    raise ValueError(f"{what}: {'invalid configuration' if code == -1 else 'invalid argument'} (code {code})")
+    if code == -1:
+        raise ValueError(f"{what}: invalid configuration (MG_E_CONFIG): field out of range, (2*max_steps+1)*n_agents >= 65536 (16-bit arrival "
+                         "stamps), or a grid / tile atlas too large for the 227 KB of shared memory one CTA stages 32 envs in")
+    raise ValueError(f"{what}: invalid argument (code {code})")

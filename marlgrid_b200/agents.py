@@ -14,12 +14,12 @@ import contextlib
 import numpy as np
 import torch
 
-from .objects import ACTIONS, COLOR_TO_IDX
+from .objects import Actions, COLOR_TO_IDX
 from .spaces import Box, Dict, Discrete
 
 
 class GridAgentInterface:
-    actions = ACTIONS  # marlgrid/agents.py:10-17
+    actions = Actions  # marlgrid/agents.py:10-17 (an IntEnum: agent.actions.forward == 2)
 
     def __init__(
         self,

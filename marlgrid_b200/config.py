@@ -97,6 +97,8 @@ def make_config(
         raise ValueError("Grid needs width, height >= 3")  # marlgrid/base.py:98-99
     if width > 255 or height > 255:
         raise ValueError("width/height must fit a byte")
+    if (2 * int(max_steps) + 1) * n_agents >= 65536:
+        raise ValueError("(2*max_steps+1)*n_agents must stay below 65536: queue-arrival stamps are 16 bits wide (include/marlgrid_b200.h)")
     cfg = MgConfig()
     cfg.width, cfg.height, cfg.n_agents = int(width), int(height), n_agents
     cfg.view_size, cfg.view_offset, cfg.view_tile_size = int(view_size), int(view_offset), int(view_tile_size)

@@ -18,6 +18,14 @@ static int check_cfg(const MgConfig* c) {
   if (c->plane_stride % 16 != 0 || c->plane_stride < c->width * c->height) return MG_E_CONFIG;
   if (c->view_offset < 0 || c->view_offset >= c->view_size) return MG_E_CONFIG;
   if (c->max_steps < 1 || c->n_clutter < 0 || c->n_bonus_tiles < 0 || c->n_bonus_tiles > 250) return MG_E_CONFIG;
+  // arrival stamps are 16 bits wide and compared raw: an episode issues at most A placement stamps + A per step (twice
+  // that with respawn, base.py:629-644), which must not wrap
+  if ((long long)(2 * c->max_steps + 1) * c->n_agents >= 65536) return MG_E_CONFIG;
+  // grids wider / taller than 16 cells take the byte-plane kernels, which stage 32 envs' planes in shared memory
+  if (c->width > 16 || c->height > 16) {
+    const long long sm = 32ll * 3 * c->plane_stride + 32ll * c->n_agents * 16 + 16 + 32ll * c->n_agents * c->view_size * c->view_size * 3;
+    if (sm > 227 * 1024) return MG_E_CONFIG;
+  }
   return 0;
 }
 
@@ -104,6 +112,7 @@ int mg_sync_derived(const MgConfig* cfg, const MgState* st, mg_stream_t stream) 
 int mg_reset(const MgConfig* cfg, const MgState* st, const uint8_t* reset_mask, mg_stream_t stream) {
   int e = check_state(cfg, st);
   if (e) return e;
+  if (st->n_envs == 0) return 0;
   KP p = make_kp(cfg, st);
   p.reset_mask = reset_mask;
   return launch_env(1, p, (cudaStream_t)stream);
@@ -114,6 +123,7 @@ int mg_step(const MgConfig* cfg, const MgState* st, const int32_t* actions, doub
   int e = check_state(cfg, st);
   if (e) return e;
   if (!actions || !rewards || !done) return MG_E_ARG;
+  if (st->n_envs == 0) return 0;
   KP p = make_kp(cfg, st);
   p.actions = actions; p.rewards = rewards; p.done = done; p.autoreset = autoreset;
   return launch_step_obs(p, 0, (cudaStream_t)stream);
@@ -280,6 +290,11 @@ int mg_engine_create(MgEngine** out, const MgConfig* cfg, int64_t n_envs, int64_
   }
   e = mg_init(&en->cfg, &en->st, en->stream);
   if (e) return e;
+  // MultiGridEnv.__init__ ends with self.reset() (base.py:368): the engine can be stepped right away; the episode counter
+  // (Philox counter of the placement draws) is rewound so that mg_engine_reset() as first call regenerates the same world
+  e = mg_reset(&en->cfg, &en->st, nullptr, en->stream);
+  if (e) return e;
+  MG_CUDA(cudaMemset2DAsync(en->st.envrec + 1, MG_ENV_REC, 0, sizeof(int32_t), (size_t)n_envs, en->stream));
   MG_CUDA(cudaStreamSynchronize(en->stream));
   *out = en;
   return 0;
@@ -339,6 +354,30 @@ int mg_engine_step(MgEngine* e, const int32_t* actions_host, uint8_t* obs_host, 
     if (obs_host) MG_CUDA(cudaMemcpyAsync(obs_host + b0 * per_env_obs, d_obs, (size_t)(nb * per_env_obs), cudaMemcpyDeviceToHost, e->copy_stream));
     if (rewards_host) MG_CUDA(cudaMemcpyAsync(rewards_host + b0 * A, d_rew, (size_t)nb * A * sizeof(double), cudaMemcpyDeviceToHost, e->copy_stream));
     if (done_host) MG_CUDA(cudaMemcpyAsync(done_host + b0, d_done, (size_t)nb, cudaMemcpyDeviceToHost, e->copy_stream));
+  }
+  MG_CUDA(cudaStreamSynchronize(e->copy_stream));
+  MG_CUDA(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+// The transfers of mg_engine_step without the kernel: the copy ceiling of the box for this batch (bench.py e2e.copy_ceiling).
+int mg_engine_copy_only(MgEngine* e, const int32_t* actions_host, uint8_t* obs_host, double* rewards_host, uint8_t* done_host) {
+  if (!e || !actions_host) return MG_E_ARG;
+  MG_CUDA(cudaSetDevice(e->device));
+  const int64_t B = e->st.n_envs;
+  const int A = e->cfg.n_agents;
+  const int64_t per_env_obs = e->obs_bytes / B;
+  const int n_slices = B >= 4096 ? ENGINE_SLICES : 1;
+  const int64_t slice = ((B + n_slices - 1) / n_slices + 31) / 32 * 32;
+  int k = 0;
+  for (int64_t b0 = 0; b0 < B; b0 += slice, ++k) {
+    const int64_t nb = std::min(slice, B - b0);
+    MG_CUDA(cudaMemcpyAsync(e->d_actions + b0 * A, actions_host + b0 * A, (size_t)nb * A * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+    MG_CUDA(cudaEventRecord(e->slice_done[k], e->stream));
+    MG_CUDA(cudaStreamWaitEvent(e->copy_stream, e->slice_done[k], 0));
+    if (obs_host) MG_CUDA(cudaMemcpyAsync(obs_host + b0 * per_env_obs, e->d_obs + b0 * per_env_obs, (size_t)(nb * per_env_obs), cudaMemcpyDeviceToHost, e->copy_stream));
+    if (rewards_host) MG_CUDA(cudaMemcpyAsync(rewards_host + b0 * A, e->d_rewards + b0 * A, (size_t)nb * A * sizeof(double), cudaMemcpyDeviceToHost, e->copy_stream));
+    if (done_host) MG_CUDA(cudaMemcpyAsync(done_host + b0, e->d_done + b0, (size_t)nb, cudaMemcpyDeviceToHost, e->copy_stream));
   }
   MG_CUDA(cudaStreamSynchronize(e->copy_stream));
   MG_CUDA(cudaStreamSynchronize(e->stream));

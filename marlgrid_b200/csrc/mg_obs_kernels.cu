@@ -62,6 +62,7 @@ static int launch_obs_one(const KP& p, cudaStream_t s) {
   static size_t configured[64] = {0};  // per instantiation and device
   int dev = 0;
   cudaGetDevice(&dev);
+  if (sm > 227 * 1024) return MG_E_CONFIG;  // tile size / agent count / grid size beyond what one CTA can stage
   if (sm > 48 * 1024 && sm > configured[dev & 63]) {
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     if (e != cudaSuccess) return (int)e;

@@ -71,7 +71,7 @@ class BatchedMultiGridEnv:
         B, A, V, ts, S = self.num_envs, cfg.n_agents, cfg.view_size, cfg.view_tile_size, cfg.plane_stride
         dev = self.device
         self.grid = torch.empty((B, 3, S), dtype=torch.uint8, device=dev)
-        self.agents = torch.empty((B, A, 16), dtype=torch.uint8, device=dev)
+        self.agent_rec = torch.empty((B, A, 16), dtype=torch.uint8, device=dev)  # per-agent records (the reference keeps this state on env.agents[i])
         self.envrec = torch.empty((B, 4), dtype=torch.int32, device=dev)
         self.cellbits = torch.empty((B, 44), dtype=torch.int32, device=dev)  # derived bit-planes (include/marlgrid_b200.h)
         self.rewards = torch.zeros((B, A), dtype=torch.float64, device=dev)
@@ -97,6 +97,11 @@ class BatchedMultiGridEnv:
         self._sync_state_struct()
         with torch.cuda.device(dev):
             _lib.check(self._lib.mg_init(ctypes.byref(cfg), ctypes.byref(self._state), self._stream()), "mg_init")
+            # MultiGridEnv.__init__ ends with self.reset() (base.py:368): a freshly constructed env can be stepped at once.
+            # The episode counter (the Philox counter of the placement draws) is rewound afterwards, so an explicit
+            # reset() as first call regenerates the same first world instead of consuming a second set of draws.
+            _lib.check(self._lib.mg_reset(ctypes.byref(cfg), ctypes.byref(self._state), None, self._stream()), "mg_reset")
+            self.envrec[:, 1] = 0
 
     # ---- plumbing ------------------------------------------------------------------------------
     def _stream(self):
@@ -104,7 +109,7 @@ class BatchedMultiGridEnv:
 
     def _sync_state_struct(self):
         st = self._state
-        st.grid, st.agents, st.envrec = self.grid.data_ptr(), self.agents.data_ptr(), self.envrec.data_ptr()
+        st.grid, st.agents, st.envrec = self.grid.data_ptr(), self.agent_rec.data_ptr(), self.envrec.data_ptr()
         st.cellbits = self.cellbits.data_ptr()
         st.n_envs, st.env_offset, st.seed = self.num_envs, self.env_offset, self._seed
 
@@ -120,13 +125,43 @@ class BatchedMultiGridEnv:
         return self.cfg.n_agents
 
     @property
+    def agents(self):
+        """The per-agent interface objects, like the reference's `env.agents` (base.py:353,392-400).  Their dynamic state
+        (pos / dir / carrying / active / done, agents.py:155-170) lives in the batched record tensor `env.agent_rec`."""
+        ai = getattr(self, "agent_interfaces", None)
+        if ai is None:  # constructed from a bare MgConfig: interfaces with the config's geometry
+            from .agents import GridAgentInterface
+            from .objects import IDX_TO_COLOR
+
+            c = self.cfg
+            ai = [GridAgentInterface(view_size=c.view_size, view_tile_size=c.view_tile_size, view_offset=c.view_offset,
+                                     see_through_walls=bool(c.flags & 8), spawn_delay=int(c.spawn_delay[i]),
+                                     color=IDX_TO_COLOR[int(c.agent_color[i])]) for i in range(c.n_agents)]
+            self.agent_interfaces = ai
+        return ai
+
+    @property
     def action_space(self):
-        return Tuple([Discrete(7) for _ in range(self.cfg.n_agents)])
+        """base.py:376-380: Tuple of the agents' action spaces (Discrete(7), or Discrete(3) with restrict_actions)."""
+        return Tuple([a.action_space for a in self.agents])
 
     @property
     def observation_space(self):
+        """base.py:382-386: Tuple of the agents' observation spaces (a Dict per agent for observation_style='rich').  With
+        obs_mode='encoded' the image part is MultiGrid.encode's (V, V, 3) array instead of the RGB view."""
+        if self.obs_mode == "rgb":
+            return Tuple([a.observation_space for a in self.agents])
         shape = tuple(self.obs.shape[2:])
-        return Tuple([Box(0, 255, shape, np.uint8) for _ in range(self.cfg.n_agents)])
+        out = []
+        for a in self.agents:
+            enc = Box(0, 255, shape, np.uint8)
+            if a.observation_style == "rich":
+                from .spaces import Dict
+
+                out.append(Dict({**a.observation_space.spaces, "pov": enc}))
+            else:
+                out.append(enc)
+        return Tuple(out)
 
     def _observe(self):
         cfg, st = ctypes.byref(self.cfg), ctypes.byref(self._state)
@@ -300,36 +335,36 @@ class BatchedMultiGridEnv:
 
     @property
     def agent_pos(self):
-        return self.agents[:, :, 0:2]
+        return self.agent_rec[:, :, 0:2]
 
     @property
     def agent_dir(self):
-        return self.agents[:, :, 2]
+        return self.agent_rec[:, :, 2]
 
     @property
     def agent_flags(self):
         """MG_AF_* bits (bit 7 of the stored byte is device-derived queue-head state and is masked off)."""
-        return self.agents[:, :, 3] & 0x7F
+        return self.agent_rec[:, :, 3] & 0x7F
 
     @property
     def agent_placed(self):
-        return (self.agents[:, :, 3] & AF_PLACED) != 0
+        return (self.agent_rec[:, :, 3] & AF_PLACED) != 0
 
     @property
     def agent_active(self):
-        return (self.agents[:, :, 3] & AF_ACTIVE) != 0
+        return (self.agent_rec[:, :, 3] & AF_ACTIVE) != 0
 
     @property
     def agent_done(self):
-        return (self.agents[:, :, 3] & AF_DONE) != 0
+        return (self.agent_rec[:, :, 3] & AF_DONE) != 0
 
     @property
     def agent_carrying(self):
-        return self.agents[:, :, 4:7]
+        return self.agent_rec[:, :, 4:7]
 
     @property
     def agent_stamp(self):
-        return self.agents[:, :, 8:12].contiguous().view(torch.int32)[..., 0]
+        return self.agent_rec[:, :, 8:12].contiguous().view(torch.int32)[..., 0]
 
     @property
     def step_count(self):
@@ -341,12 +376,12 @@ class BatchedMultiGridEnv:
 
     # ---- checkpoint / resume (the RNG is counter-based: resume is exact) -----------------------
     def state_dict(self):
-        return {"grid": self.grid.clone(), "agents": self.agents.clone(), "envrec": self.envrec.clone(), "seed": self._seed,
+        return {"grid": self.grid.clone(), "agents": self.agent_rec.clone(), "envrec": self.envrec.clone(), "seed": self._seed,
                 "env_offset": self.env_offset}
 
     def load_state_dict(self, sd):
         self.grid.copy_(sd["grid"])
-        self.agents.copy_(sd["agents"])
+        self.agent_rec.copy_(sd["agents"])
         self.envrec.copy_(sd["envrec"])
         self._seed = int(sd["seed"])
         self.env_offset = int(sd["env_offset"])

@@ -93,7 +93,7 @@ class MultiGridEnv(BatchedMultiGridEnv):
         a0 = self.agent_interfaces[0]
         if a0.observation_style != "rich":
             return obs
-        return compose_rich_obs(obs, self.agents, self.width, self.height, a0.observe_rewards, a0.observe_position, a0.observe_orientation)
+        return compose_rich_obs(obs, self.agent_rec, self.width, self.height, a0.observe_rewards, a0.observe_position, a0.observe_orientation)
 
     def reset(self, *args, **kwargs):
         return self._style(super().reset(*args, **kwargs))

@@ -9,6 +9,8 @@ The per-type behaviour predicates (can_overlap / can_pickup / see_behind, object
 147-148,174,216,230,258,281,292,314,327-331,378) live in the CUDA kernels as constant tables
 (marlgrid_b200/csrc/mg_tables.cuh); the Python copies below are for host-side inspection.
 """
+import enum
+
 import numpy as np
 
 OBJECT_TYPE_NAMES = (
@@ -40,7 +42,20 @@ IDX_TO_COLOR = {i: k for k, i in COLOR_TO_IDX.items()}
 
 DOOR_OPEN, DOOR_CLOSED, DOOR_LOCKED = 1, 2, 3
 
-ACTIONS = {"left": 0, "right": 1, "forward": 2, "pickup": 3, "drop": 4, "toggle": 5, "done": 6}
+
+
+class Actions(enum.IntEnum):
+    """GridAgentInterface.actions (marlgrid/agents.py:10-17): `agent.actions.forward`, `len(agent.actions)`."""
+    left = 0      # Rotate left
+    right = 1     # Rotate right
+    forward = 2   # Move forward
+    pickup = 3    # Pick up an object
+    drop = 4      # Drop an object
+    toggle = 5    # Toggle/activate an object
+    done = 6      # Done completing task
+
+
+ACTIONS = {a.name: int(a) for a in Actions}
 
 
 def can_overlap(type_idx, state=0):

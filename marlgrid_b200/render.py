@@ -46,7 +46,7 @@ def _sub_state(env, index):
     """MgState of the single env `index` (pointers offset into the batch tensors)."""
     st = MgState()
     st.grid = env.grid[index].data_ptr()
-    st.agents = env.agents[index].data_ptr()
+    st.agents = env.agent_rec[index].data_ptr()
     st.envrec = env.envrec[index].data_ptr()
     st.cellbits = env.cellbits[index].data_ptr()
     st.n_envs, st.env_offset, st.seed = 1, env.env_offset + index, env._seed
@@ -74,7 +74,7 @@ def visibility_masks(env, index=0):
     cfg = env.cfg
     A, V, vo, W, H = cfg.n_agents, cfg.view_size, cfg.view_offset, cfg.width, cfg.height
     planes = env.planes[index].cpu().numpy()           # [3, W, H]
-    ag = env.agents[index].cpu().numpy()               # [A, 16]
+    ag = env.agent_rec[index].cpu().numpy()               # [A, 16]
     opaque = (planes[0] == 8) | ((planes[0] == 11) & (planes[2] != 1))  # Wall / Door that is not open (objects.py:281-282,330-331)
     transp = np.ones((A, V, V), dtype=np.uint8)
     active = (ag[:, 3] & AF_ACTIVE) != 0
@@ -104,7 +104,7 @@ def render(env, index=0, highlight=True, tile_size=32, show_agent_views=True, ma
     if any(int(c) == _PRESTIGE for c in cfg.agent_color[:A]):
         raise NotImplementedError("color='prestige' (agents.py:92-119: tile recoloured by the agent's running reward) is not built yet")
     planes = env.planes[index].cpu().numpy()
-    ag = env.agents[index].cpu().numpy()
+    ag = env.agent_rec[index].cpu().numpy()
     placed = (ag[:, 3] & AF_PLACED) != 0
     stamp = ag[:, 8:12].copy().view(np.int32)[:, 0]
     per_kind = 1 + 4 * A

@@ -17,11 +17,32 @@ except Exception:  # noqa: BLE001
             def __init__(self, shape=None, dtype=None):
                 self.shape = None if shape is None else tuple(shape)
                 self.dtype = None if dtype is None else np.dtype(dtype)
+                self._rng = np.random.RandomState()
+
+            def seed(self, seed=None):
+                self._rng = np.random.RandomState(seed)
+                return [seed]
+
+            def sample(self):
+                raise NotImplementedError
 
         class Box(Space):
             def __init__(self, low, high, shape=None, dtype=np.float32):
                 super().__init__(shape if shape is not None else np.shape(low), dtype)
                 self.low, self.high = low, high
+
+            def sample(self):
+                if np.issubdtype(self.dtype, np.integer):
+                    return self._rng.randint(int(np.min(self.low)), int(np.max(self.high)) + 1, size=self.shape).astype(self.dtype)
+                lo = np.broadcast_to(np.asarray(self.low, dtype=np.float64), self.shape)
+                hi = np.broadcast_to(np.asarray(self.high, dtype=np.float64), self.shape)
+                u = self._rng.uniform(size=self.shape)
+                bounded = np.isfinite(lo) & np.isfinite(hi)
+                return np.where(bounded, lo + u * (hi - lo), self._rng.normal(size=self.shape)).astype(self.dtype)
+
+            def contains(self, x):
+                x = np.asarray(x)
+                return x.shape == self.shape and bool(np.all(x >= self.low) and np.all(x <= self.high))
 
             def __repr__(self):
                 return f"Box({self.low}, {self.high}, {self.shape}, {self.dtype})"
@@ -30,6 +51,12 @@ except Exception:  # noqa: BLE001
             def __init__(self, n):
                 super().__init__((), np.int64)
                 self.n = int(n)
+
+            def sample(self):
+                return int(self._rng.randint(self.n))
+
+            def contains(self, x):
+                return 0 <= int(x) < self.n
 
             def __repr__(self):
                 return f"Discrete({self.n})"
@@ -48,6 +75,15 @@ except Exception:  # noqa: BLE001
             def __iter__(self):
                 return iter(self.spaces)
 
+            def sample(self):
+                return tuple(sp.sample() for sp in self.spaces)
+
+            def contains(self, x):
+                return len(x) == len(self.spaces) and all(sp.contains(v) for sp, v in zip(self.spaces, x))
+
+            def __repr__(self):
+                return "Tuple(" + ", ".join(repr(sp) for sp in self.spaces) + ")"
+
         class Dict(Space):
             def __init__(self, spaces=None, **kw):
                 super().__init__(None, None)
@@ -55,3 +91,12 @@ except Exception:  # noqa: BLE001
 
             def __getitem__(self, k):
                 return self.spaces[k]
+
+            def sample(self):
+                return {k: sp.sample() for k, sp in self.spaces.items()}
+
+            def contains(self, x):
+                return set(x) == set(self.spaces) and all(sp.contains(x[k]) for k, sp in self.spaces.items())
+
+            def __repr__(self):
+                return "Dict(" + ", ".join(f"{k}: {sp!r}" for k, sp in self.spaces.items()) + ")"

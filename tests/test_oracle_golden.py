@@ -150,7 +150,7 @@ def test_render_composition_against_reference_frames(oracle):
             self.cfg, self.ob, self.obs_mode, self.atlas = cfg, ob, "encoded", None
 
         planes = property(lambda self: torch.from_numpy(self.ob.planes().copy()))
-        agents = property(lambda self: torch.from_numpy(self.ob.agents.copy()))
+        agent_rec = property(lambda self: torch.from_numpy(self.ob.agents.copy()))
 
     def views(env, index=0):
         c = env.cfg
