@@ -271,10 +271,13 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=100)
     ap.add_argument("--replicas", type=int, default=6, help="independent env families visited round robin in the timed loop (working set > L2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--quick", action="store_true", help="headline figure only (profiling runs): no other_configs / desync / CPU arms")
+    ap.add_argument("--quick", action="store_true", help="headline figure + e2e only: no other_configs / desync / CPU arms")
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS), help="another BASELINE config alone (informational line; the driver's line is cfg3)")
+    ap.add_argument("--profile", action="store_true", help="for runs under ncu: --quick with 2 repeats and no clock ramp")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     args.steps = max(args.steps, 1)
+    args.quick = args.quick or args.profile
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -318,6 +321,48 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return [float(x) for x in t.tolist()]
 
+    # ---- another BASELINE config: `steps` env.step() calls back to back over n_fams families, one CUDA event pair -------
+    peak_gbs, _ = measured_peak()
+
+    def timed_rollout(make_env, n_fams, steps, name):
+        env_id, Bo, mode, Ao, algo = WORKLOADS[name]
+        fs = [make_env(r) for r in range(n_fams)]
+        for f in fs:
+            f.reset()
+        acts = [fs[0].random_actions(t, seed=rank) for t in range(16)]
+        for t in range(max(3, n_fams)):
+            fs[t % n_fams].step(acts[t % 16])
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for t in range(steps):
+            fs[t % n_fams].step(acts[t % 16])
+        e1.record()
+        host_s = time.perf_counter() - t0
+        barrier()
+        ms = max_over_ranks([e0.elapsed_time(e1) / steps])[0]
+        ach = algo * Bo / (ms * 1e-3) / 1e9
+        del fs
+        torch.cuda.empty_cache()
+        return {"env_id": env_id, "batch_per_gpu": Bo, "obs": mode, "value": world * Bo / (ms * 1e-3), "agent_steps_per_s": world * Ao * Bo / (ms * 1e-3),
+                "ms_per_step": ms, "steps": steps, "host_issue_ms_per_step": 1e3 * host_s / steps,
+                "roofline": {"achieved": ach, "peak": peak_gbs, "frac": ach / peak_gbs, "algorithmic_bytes_per_launch": algo * Bo}}
+
+    def mk(name, **kw):
+        env_id, Bo, mode, _, _ = WORKLOADS[name]
+        return lambda r: envs.make(env_id, num_envs=Bo, obs_mode=mode, seed=1337, env_offset=(rank * 8 + r) * Bo, device=dev, **kw)
+
+
+    if args.workload != "cfg3":
+        nf, st = {"cfg2": (1, 400), "cfg5_share": (3, 120), "cfg4": (1, 12)}[args.workload]
+        res = timed_rollout(mk(args.workload, **({"obs_buffers": 1} if args.workload == "cfg4" else {})), nf, max(args.steps, 3) if args.profile else st, args.workload)
+        if rank == 0:
+            print(json.dumps(dict(res, metric="env-steps/s", workload=args.workload, n_gpus=world)), flush=True)
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
     # R independent env families of B envs each, stepped round robin: between two visits of a family the other R-1 steps
     # touch (R-1) x ~51 MB (bit-plane lines, records, actions in; observations, records, rewards out), more than the 126 MB
     # L2 holds, so every timed step finds its inputs in HBM -- "inputs larger than L2", no flush kernel between launches.
@@ -354,7 +399,7 @@ def main():
     # ---- warm-up: W steps, then an untimed clock ramp (a fresh box idles at ~800 MHz) -----------------------------
     run_steps(W)
     ramp_steps = 0
-    if not args.quick:
+    if not args.profile:
         t0 = time.perf_counter()
         while time.perf_counter() - t0 < 0.25:
             run_steps(120)
@@ -368,7 +413,7 @@ def main():
     # ---- timed: REPEATS x exactly K cold steps, back to back, one event pair per repeat ------------------------------
     est_us = 16.0 * max(1.0, B / 65536.0)
     REPEATS = int(min(3000, max(5, -(-MIN_TIMED_MS * 1e3 // (K * est_us)))))
-    if args.quick:
+    if args.profile:
         REPEATS = 2
     launches0 = L.mg_launch_count()
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(REPEATS + 1)]
@@ -491,37 +536,6 @@ def main():
     # ---- other BASELINE configs, measured in the same run (device-timed, max over ranks) --------------------------------
     other = {}
     if not args.quick:
-        peak, _ = measured_peak()
-
-        def timed_rollout(make_env, n_fams, steps, name):
-            env_id, Bo, mode, Ao, algo = WORKLOADS[name]
-            fs = [make_env(r) for r in range(n_fams)]
-            for f in fs:
-                f.reset()
-            acts = [fs[0].random_actions(t, seed=rank) for t in range(16)]
-            for t in range(max(3, n_fams)):
-                fs[t % n_fams].step(acts[t % 16])
-            barrier()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            t0 = time.perf_counter()
-            e0.record()
-            for t in range(steps):
-                fs[t % n_fams].step(acts[t % 16])
-            e1.record()
-            host_s = time.perf_counter() - t0
-            barrier()
-            ms = max_over_ranks([e0.elapsed_time(e1) / steps])[0]
-            ach = algo * Bo / (ms * 1e-3) / 1e9
-            del fs
-            torch.cuda.empty_cache()
-            return {"env_id": env_id, "batch_per_gpu": Bo, "obs": mode, "value": world * Bo / (ms * 1e-3), "agent_steps_per_s": world * Ao * Bo / (ms * 1e-3),
-                    "ms_per_step": ms, "steps": steps, "host_issue_ms_per_step": 1e3 * host_s / steps,
-                    "roofline": {"achieved": ach, "peak": peak, "frac": ach / peak, "algorithmic_bytes_per_launch": algo * Bo}}
-
-        def mk(name, **kw):
-            env_id, Bo, mode, _, _ = WORKLOADS[name]
-            return lambda r: envs.make(env_id, num_envs=Bo, obs_mode=mode, seed=1337, env_offset=(rank * 8 + r) * Bo, device=dev, **kw)
-
         # cfg2: 4 096 envs -- 128 tiles, launch / latency bound; the state of one family is L2-resident whatever one does
         other["cfg2"] = timed_rollout(mk("cfg2"), 1, 400, "cfg2")
         other["cfg2"]["note"] = "BASELINE configs[1]; env.step() in a Python loop (one launch per step), state L2-resident (1 MB)"
@@ -567,7 +581,7 @@ def main():
     e2e_ms, copy_ms = max_over_ranks([e2e_s * 1e3, copy_s * 1e3])
     # outside the timer: the last step's results against the oracle replaying the same actions (rank 0)
     e2e_parity = None
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and not args.no_cpu_baseline and not args.quick:
         from oracle import mg_oracle
 
         # the copy-only loop overwrote the host buffers with the device's (unchanged) last results: still the last step's outputs

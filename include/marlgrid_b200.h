@@ -122,15 +122,20 @@ typedef struct MgState {
   uint8_t* grid;    /* [B][3][S] */
   uint8_t* agents;  /* [B][A][16] */
   int32_t* envrec;  /* [B][4] */
-  uint32_t* cellbits; /* [B][44] DERIVED bit-planes, or NULL (then, and for grids wider/taller than 16, the observe
-                         kernel stages and gathers the byte planes instead).  Two bits per cell: OP = opaque (Wall / Door
-                         not open), OT = "other" = non-empty and not a canonical wall Wall('worst', 0); canonical wall ==
-                         OP & ~OT, non-empty == OP | OT.  Per env, one word per line (bits 0..15 OP, bits 16..31 OT):
+  uint32_t* cellbits; /* [ceil(B/32)][44][32] DERIVED bit-planes, or NULL (then, and for grids wider/taller than 16, the
+                         observe kernel stages and gathers the byte planes instead).  Two bits per cell: OP = opaque (Wall /
+                         Door not open), OT = "other" = non-empty and not a canonical wall Wall('worst', 0); canonical wall ==
+                         OP & ~OT, non-empty == OP | OT.  Per env 44 words, one word per line (bits 0..15 OP, bits 16..31 OT):
                            word 1+x   (x = 0..15): cells (x, 0..15), bit = y        words 0, 17, 18, 35 are zero guard lines
                            word 19+y  (y = 0..15): cells (0..15, y), bit = x
                            word 36+k  (k = 0..3) : object list, x | y<<4 | type<<8 | colour<<12 | state<<16 | 1<<31: the first OT
                                                    objects (Goal, BonusTiles, Keys ...); unlisted ones are read from the byte planes
                            word 40..43: reserved (zero)
+                         TILE-TRANSPOSED in memory: the 32 consecutive envs of a tile interleave their words -- word w of env e
+                         lives at cellbits[((e / 32) * 44 + w) * 32 + e % 32] -- so that a tile is one contiguous 5 632-byte
+                         chunk whose shared-memory image is bank-conflict-free for lane = env, and a thread-per-env kernel
+                         accesses it coalesced.  Allocate whole tiles (ceil(B/32) * 5 632 bytes); sub-ranges of a batch handed
+                         to the library must start at a multiple of 32 envs (or pass NULL).
                          Maintained by mg_reset / mg_step*; after editing planes or agent records by hand call
                          mg_sync_derived. */
   int64_t n_envs;   /* B (envs on THIS device) */

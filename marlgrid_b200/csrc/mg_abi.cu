@@ -279,7 +279,7 @@ int mg_engine_create(MgEngine** out, const MgConfig* cfg, int64_t n_envs, int64_
   MG_CUDA(cudaMalloc(&en->st.grid, (size_t)n_envs * 3 * cfg->plane_stride));
   MG_CUDA(cudaMalloc(&en->st.agents, (size_t)n_envs * cfg->n_agents * MG_AGENT_REC));
   MG_CUDA(cudaMalloc(&en->st.envrec, (size_t)n_envs * MG_ENV_REC));
-  MG_CUDA(cudaMalloc(&en->st.cellbits, (size_t)n_envs * BITS_WORDS * 4));
+  MG_CUDA(cudaMalloc(&en->st.cellbits, (size_t)((n_envs + 31) / 32) * (BITS_WORDS * BS * 4)));  // whole tiles of 32 envs
   MG_CUDA(cudaMalloc(&en->d_actions, (size_t)n_envs * cfg->n_agents * sizeof(int32_t)));
   MG_CUDA(cudaMalloc(&en->d_rewards, (size_t)n_envs * cfg->n_agents * sizeof(double)));
   MG_CUDA(cudaMalloc(&en->d_done, (size_t)n_envs));

@@ -21,9 +21,19 @@ constexpr int ENVS_PER_CTA = 32;
 //        (Goal, BonusTiles, Keys ...).  An OT cell that is NOT listed is looked up in the byte planes, so the list may be
 //        incomplete (more than 4 objects) but never wrong.
 //   words 40..43: reserved (zero)
+// MEMORY LAYOUT -- tile-transposed, in global AND shared memory: the 32 consecutive envs of a tile interleave their words,
+//   word w of env e  at  cellbits[((e >> 5) * BITS_WORDS + w) * 32 + (e & 31)]
+// so a tile is one contiguous 5 632-byte chunk (one bulk copy), the lanes of a warp (lane = env) hit 32 different banks
+// whatever word each of them indexes (the [env][44] layout of round 1 put lanes l and l+8 on the same bank: 4-way conflicts
+// on every view-row load), and a thread-per-env kernel reads / writes global memory coalesced.  Code holds a pointer to an
+// env's word 0 (`env_bits`) and addresses word w as bits[w * BS].  The tensor is allocated for whole tiles.
 constexpr int BITS_WORDS = 44;
+constexpr int BS = 32;  // word stride between consecutive words of one env
 constexpr int LINE_X0 = 1, LINE_Y0 = 19, OBJ_WORD0 = 36;
 constexpr int OBJ_SLOTS = 4;
+__host__ __device__ __forceinline__ long long bits_offset(long long env) { return (env >> 5) * (long long)(BITS_WORDS * BS) + (env & 31); }
+template <class T>
+__host__ __device__ __forceinline__ T* env_bits(T* cellbits, long long env) { return cellbits + bits_offset(env); }
 constexpr uint32_t AF_HEAD = 0x80u;  // derived flag bit: agent is the head of its cell's queue
 
 struct KP {
@@ -37,7 +47,7 @@ struct KP {
   uint8_t* grid;
   uint8_t* agents;
   int32_t* envrec;
-  uint32_t* cellbits;  // [B][48] or nullptr (grid wider/taller than 16, or caller passed none): byte path
+  uint32_t* cellbits;  // [ceil(B/32)][BITS_WORDS][32] (tile-transposed, see below) or nullptr (grid wider/taller than 16, or caller passed none): byte path
   long long B, env_offset;
   unsigned long long seed;
   const int32_t* actions;
@@ -67,7 +77,7 @@ __device__ __forceinline__ uint32_t obj_lookup(const uint32_t* bits, int x, int 
   uint32_t e = 0;
 #pragma unroll
   for (int k = 0; k < OBJ_SLOTS; ++k) {
-    const uint32_t w = bits[OBJ_WORD0 + k];
+    const uint32_t w = bits[(OBJ_WORD0 + k) * BS];
     if ((w & 0x800000FFu) == key) e = w;
   }
   return e;
@@ -77,23 +87,23 @@ __device__ __forceinline__ void obj_update(uint32_t* bits, int x, int y, int typ
   const bool listable = type != MG_T_EMPTY && !cell_canon(type, colour, state) && colour < 16 && type < 16;
   int slot = -1;
   for (int k = 0; k < OBJ_SLOTS; ++k) {
-    const uint32_t w = bits[OBJ_WORD0 + k];
-    if ((w & 0x800000FFu) == key) { bits[OBJ_WORD0 + k] = 0u; if (slot < 0) slot = k; }
+    const uint32_t w = bits[(OBJ_WORD0 + k) * BS];
+    if ((w & 0x800000FFu) == key) { bits[(OBJ_WORD0 + k) * BS] = 0u; if (slot < 0) slot = k; }
     else if (!(w >> 31) && slot < 0) slot = k;
   }
-  if (listable && slot >= 0) bits[OBJ_WORD0 + slot] = obj_entry(x, y, type, colour, state);
+  if (listable && slot >= 0) bits[(OBJ_WORD0 + slot) * BS] = obj_entry(x, y, type, colour, state);
 }
 __device__ __forceinline__ void bits_update_cell(uint32_t* bits, int x, int y, int type, int colour, int state) {
   if (bits == nullptr) return;
   const uint32_t op = cell_opaque(type, state) ? 1u : 0u, ot = (type != MG_T_EMPTY && !cell_canon(type, colour, state)) ? 1u : 0u;
-  bits[LINE_X0 + x] = (bits[LINE_X0 + x] & ~(0x10001u << y)) | (op << y) | (ot << (16 + y));
-  bits[LINE_Y0 + y] = (bits[LINE_Y0 + y] & ~(0x10001u << x)) | (op << x) | (ot << (16 + x));
+  bits[(LINE_X0 + x) * BS] = (bits[(LINE_X0 + x) * BS] & ~(0x10001u << y)) | (op << y) | (ot << (16 + y));
+  bits[(LINE_Y0 + y) * BS] = (bits[(LINE_Y0 + y) * BS] & ~(0x10001u << x)) | (op << x) | (ot << (16 + x));
   obj_update(bits, x, y, type, colour, state);
 }
 // rebuild all words from the byte planes
 __device__ inline void bits_rebuild(const uint8_t* tp, uint32_t* bits, int W, int H, int S) {
   if (bits == nullptr) return;
-  for (int i = 0; i < BITS_WORDS; ++i) bits[i] = 0u;
+  for (int i = 0; i < BITS_WORDS; ++i) bits[i * BS] = 0u;
   for (int x = 0; x < W; ++x)
     for (int y = 0; y < H; ++y) {
       const int idx = x * H + y;
@@ -105,7 +115,7 @@ __device__ inline void bits_rebuild(const uint8_t* tp, uint32_t* bits, int W, in
 // (type | colour<<8 | state<<16) of the static object at (x, y): bit-planes, then the object list, then -- for
 // objects that did not fit the list -- the byte planes
 __device__ __forceinline__ uint32_t cell_triple(const uint32_t* bits, int x, int y, const uint8_t* tp, int H, int S) {
-  const uint32_t c = (bits[LINE_X0 + x] >> y) & 0x10001u;
+  const uint32_t c = (bits[(LINE_X0 + x) * BS] >> y) & 0x10001u;
   if (c == 0u) return 0u;
   if (c == 1u) return (uint32_t)MG_T_WALL | ((uint32_t)MG_C_WORST << 8);  // opaque and not "other": canonical wall
   const uint32_t e = obj_lookup(bits, x, y);

@@ -10,7 +10,7 @@ namespace mg {
 // of agent a at rec[(a*4+w)*RS] (RS = threads per CTA) -> bank == thread, conflict-free for any per-thread a.
 //   w0 = x | y<<8 | dir<<16 | flags<<24     w1 = carry_type | carry_colour<<8 | carry_state<<16 | bonus<<24
 //   w2 = stamp                               w3 = scratch (front-cell prefetch)
-// `tp` = the env's type plane in global memory (colour at +S, state at +2S); `bits` = its 48 bit-plane words.
+// `tp` = the env's type plane in global memory (colour at +S, state at +2S); `bits` = its bit-plane words (word w at bits[w * BS], mg_common.cuh).
 // ---------------------------------------------------------------------------------------------
 template <int RS>
 struct EnvCtx {
@@ -132,7 +132,7 @@ __device__ void env_reset(EnvCtx<RS>& c, unsigned long long g) {
       wallc[i * RS] = (i == 0 || i == H - 1) ? fullc : (i < H ? endsc : 0u);
       other[i * RS] = 0u; otherc[i * RS] = 0u;
     }
-    for (int k = 0; k < OBJ_SLOTS; ++k) c.bits[OBJ_WORD0 + k] = 0u;
+    for (int k = 0; k < OBJ_SLOTS; ++k) c.bits[(OBJ_WORD0 + k) * BS] = 0u;
   }
   if (PLANES) {
     for (int i = 0; i < W; ++i) {  // wall_rect base.py:172-176
@@ -154,7 +154,7 @@ __device__ void env_reset(EnvCtx<RS>& c, unsigned long long g) {
       if (type == MG_T_WALL) { wall[x * RS] |= 1u << y; wallc[y * RS] |= 1u << x; }
       else {
         other[x * RS] |= 1u << y; otherc[y * RS] |= 1u << x;
-        if (n_listed < OBJ_SLOTS) c.bits[OBJ_WORD0 + n_listed++] = obj_entry(x, y, type, colour, state);  // Goal / BonusTiles
+        if (n_listed < OBJ_SLOTS) c.bits[(OBJ_WORD0 + n_listed++) * BS] = obj_entry(x, y, type, colour, state);  // Goal / BonusTiles
       }
     }
   };
@@ -200,11 +200,11 @@ __device__ void env_reset(EnvCtx<RS>& c, unsigned long long g) {
   if (BITS) {  // the masks ARE the bit-plane lines (OP = walls, OT = Goal / BonusTiles)
     uint32_t* bits = c.bits;
     for (int i = 0; i < 16; ++i) {
-      bits[LINE_X0 + i] = wall[i * RS] | (other[i * RS] << 16);
-      bits[LINE_Y0 + i] = wallc[i * RS] | (otherc[i * RS] << 16);
+      bits[(LINE_X0 + i) * BS] = wall[i * RS] | (other[i * RS] << 16);
+      bits[(LINE_Y0 + i) * BS] = wallc[i * RS] | (otherc[i * RS] << 16);
     }
-    bits[0] = 0u; bits[17] = 0u; bits[18] = 0u; bits[35] = 0u;
-    for (int i = OBJ_WORD0 + OBJ_SLOTS; i < BITS_WORDS; ++i) bits[i] = 0u;
+    bits[0] = 0u; bits[17 * BS] = 0u; bits[18 * BS] = 0u; bits[35 * BS] = 0u;
+    for (int i = OBJ_WORD0 + OBJ_SLOTS; i < BITS_WORDS; ++i) bits[i * BS] = 0u;
   }
 }
 

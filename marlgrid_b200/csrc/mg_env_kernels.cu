@@ -19,7 +19,7 @@ __global__ void __launch_bounds__(ENV_THREADS) env_kernel(const __grid_constant_
   if (env >= p.B) return;
   if (MODE == 1 && p.reset_mask != nullptr && p.reset_mask[env] == 0) return;
   const int A = p.A;
-  EnvCtx<ENV_THREADS> c{p, s_rec + threadIdx.x, p.grid + env * 3 * p.S, BITS ? p.cellbits + env * BITS_WORDS : nullptr,
+  EnvCtx<ENV_THREADS> c{p, s_rec + threadIdx.x, p.grid + env * 3 * p.S, BITS ? env_bits(p.cellbits, env) : nullptr,
                         s_scr + threadIdx.x, 0, 0, 0, 0u, false};
   int4* arec = reinterpret_cast<int4*>(p.agents) + env * A;
   const int4 er = reinterpret_cast<const int4*>(p.envrec)[env];
@@ -51,7 +51,7 @@ __global__ void init_kernel(uint8_t* grid, uint8_t* agents, int32_t* envrec, uin
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long n_grid = B * 3 * S / 16, n_ag = B * A, n_er = B;
   if (i < n_grid) reinterpret_cast<int4*>(grid)[i] = make_int4(0, 0, 0, 0);
-  if (cellbits != nullptr && i < B * (BITS_WORDS / 4)) reinterpret_cast<int4*>(cellbits)[i] = make_int4(0, 0, 0, 0);
+  if (cellbits != nullptr && i < (B + 31) / 32 * (BITS_WORDS * BS / 4)) reinterpret_cast<int4*>(cellbits)[i] = make_int4(0, 0, 0, 0);  // whole tiles
   if (i < n_ag) reinterpret_cast<int4*>(agents)[i] = make_int4(0, (int)0xFF000000u, 0, 0);
   if (i < n_er) reinterpret_cast<int4*>(envrec)[i] = make_int4(0, 0, 0, 0);
 }
@@ -116,7 +116,7 @@ int launch_env(int mode, const KP& p, cudaStream_t s) {
 }
 
 int launch_init(uint8_t* grid, uint8_t* agents, int32_t* envrec, uint32_t* cellbits, long long B, int A, int S, cudaStream_t s) {
-  const long long n = std::max<long long>(std::max<long long>(B * 3 * S / 16, B * A), B * (BITS_WORDS / 4));
+  const long long n = std::max<long long>(std::max<long long>(B * 3 * S / 16, B * A), (B + 31) / 32 * (BITS_WORDS * BS / 4));
   init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(grid, agents, envrec, cellbits, B, A, S);
   count_launch();
   return (int)cudaGetLastError();

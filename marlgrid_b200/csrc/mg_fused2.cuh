@@ -130,6 +130,18 @@ __device__ __forceinline__ uint64_t pack_rows8(const uint32_t (&r)[V]) {
   return ((uint64_t)hi << 32) | lo;
 }
 
+// Transpose of two 16x16 bit matrices at once: lane r < 16 holds row r of matrix 0 in bits 0..15 and row r of matrix 1 in
+// bits 16..31; returns, in lane c < 16, column c of both the same way.  Four butterfly stages (block swaps of 8, 4, 2, 1).
+__device__ __forceinline__ uint32_t transpose16x16_pair(uint32_t v, int lane) {
+#pragma unroll
+  for (int j = 8; j >= 1; j >>= 1) {
+    const uint32_t mask = j == 8 ? 0x00FF00FFu : j == 4 ? 0x0F0F0F0Fu : j == 2 ? 0x33333333u : 0x55555555u;
+    const uint32_t other = __shfl_xor_sync(0xFFFFFFFFu, v, j);
+    v = (lane & j) ? (((other >> j) & mask) | (v & ~mask)) : ((v & mask) | ((other & mask) << j));
+  }
+  return v;
+}
+
 // one-byte shared-memory store at a compile-time offset from a 32-bit shared address
 __device__ __forceinline__ void sts_u8(uint32_t saddr, uint32_t v) {
   asm volatile("st.shared.u8 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
@@ -209,6 +221,7 @@ __device__ __forceinline__ bool warp_reset(const KP& p, unsigned long long g, ui
     agents_done += __popc(vma);
     if (agents_done >= A) {
       // ---- commit: records, env record, bit-plane lines (x-lines as sampled, y-lines by transposition), object list ----
+      __syncwarp();  // every lane has read envr[1] (the episode number keys the draws) before lane 0 advances it
       if (lane < A) {  // agents.py:161-170 (dir survives), placement order = stamp order (base.py:409-412,686)
         const uint32_t old = rec[lane * 4];
         *reinterpret_cast<uint4*>(rec + lane * 4) = make_uint4((old & 0x00FF0000u) | a_xy | ((uint32_t)(MG_AF_PLACED | MG_AF_ACTIVE) << 24), 0xFF000000u, (uint32_t)lane, 0u);
@@ -217,18 +230,17 @@ __device__ __forceinline__ bool warp_reset(const KP& p, unsigned long long g, ui
         envr[0] = 0; envr[1] = (int)(ep + 1u);
         envr[3] = (int)(((uint32_t)envr[3] & 0xFFFF0000u) | (uint32_t)A);
       }
-      uint32_t wy = 0, oy = 0;  // lane y < 16: its y-line
-      for (int xx = 0; xx < 16; ++xx) {
-        wy |= ((wall_x[xx] >> (lane & 15)) & 1u) << xx;
-        oy |= ((other_x[xx] >> (lane & 15)) & 1u) << xx;
-      }
+      // lane x < 16 holds its x-line (walls in the low half, Goal / BonusTiles in the high half); the y-lines are the
+      // transposed 16x16 bit matrices: four butterfly stages on both halves at once
+      const uint32_t xl = lane < 16 ? (wall_x[lane] | (other_x[lane] << 16)) : 0u;
+      const uint32_t yl = transpose16x16_pair(xl, lane);
       if (lane < 16) {
-        bits[LINE_X0 + lane] = wall_x[lane] | (other_x[lane] << 16);
-        bits[LINE_Y0 + lane] = wy | (oy << 16);
+        bits[(LINE_X0 + lane) * BS] = xl;
+        bits[(LINE_Y0 + lane) * BS] = yl;
       }
-      if (lane < 4) bits[OBJ_WORD0 + lane] = list[lane];
-      if (lane >= 4 && lane < 8) bits[OBJ_WORD0 + lane] = 0u;             // words 40..43
-      if (lane >= 8 && lane < 12) bits[(lane == 8) ? 0 : (lane == 9) ? 17 : (lane == 10) ? 18 : 35] = 0u;  // guard lines
+      if (lane < 4) bits[(OBJ_WORD0 + lane) * BS] = list[lane];
+      if (lane >= 4 && lane < 8) bits[(OBJ_WORD0 + lane) * BS] = 0u;             // words 40..43
+      if (lane >= 8 && lane < 12) bits[((lane == 8) ? 0 : (lane == 9) ? 17 : (lane == 10) ? 18 : 35) * BS] = 0u;  // guard lines
       __syncwarp();
       return true;
     }
@@ -236,25 +248,90 @@ __device__ __forceinline__ bool warp_reset(const KP& p, unsigned long long g, ui
   return false;
 }
 
-// the finished envs of a tile that the warps regenerate cooperatively (env e -> warp e % A): worth it while few envs of the
-// tile end together (a long-running batch whose episodes have drifted apart: one or two per tile and step); a tile in which
-// most envs end at once (episodes still in lock step) is cheaper with one lane per env on the sequential code
-template <int A>
-__device__ __noinline__ void warp_resets(const KP& p, uint32_t* s_flag, uint32_t* s_bits, uint32_t* s_rec, int32_t* s_env, uint32_t* wk,
-                                         long long env0, int n_valid, int a, int lane) {
-  const uint32_t todo = __ballot_sync(0xFFFFFFFFu, lane < n_valid && (s_flag[lane] & (FL_SLOW | FL_RESET)) == FL_RESET);
-  if (__popc(todo) > WARP_RESET_MAX * A) return;  // many: tile_resets() below
-  for (int e = a; e < n_valid; e += A) {
-    if (!((todo >> e) & 1u)) continue;
-    const uint32_t fl = s_flag[e];
-    if (warp_reset<A>(p, (unsigned long long)(p.env_offset + env0 + e), s_bits + e * BITS_WORDS, s_rec + e * (A * 4), s_env + e * 4, wk, lane)) {
-      if (lane == 0) s_flag[e] = (fl & ~FL_RESET) | FL_IMAGE;
+// The byte planes of freshly regenerated envs, written straight to global memory: ONE ENV PER HALF-WARP, lane hl = lane & 15
+// builds cells [16 hl, 16 hl + 16) of all three planes from the env's bit-plane lines in shared memory (a fresh world holds
+// canonical walls = OP & ~OT -> type 8 / colour 9, and the Goal / BonusTiles of the object list) and stores three 16-byte
+// vectors -- coalesced plain stores, nothing to wait for, no staging image.  W, H <= 16: a plane has at most 16 chunks.
+struct PlaneLane { int c0, x0, sh0; bool on; };
+__device__ __forceinline__ PlaneLane plane_lane(const KP& p, int lane) {  // the per-lane constants (one integer division)
+  PlaneLane q;
+  q.c0 = (lane & 15) << 4;
+  q.on = q.c0 < p.S;
+  q.x0 = q.c0 / p.H;
+  q.sh0 = q.x0 * p.H - q.c0;  // <= 0: where x-line x0 starts relative to the chunk
+  return q;
+}
+__device__ __forceinline__ void patch_byte(uint4& v, int rel, uint32_t b) {
+  const uint32_t sh = 8u * (rel & 3), keep = ~(0xFFu << sh), put = b << sh;
+  const int j = rel >> 2;
+  if (j == 0) v.x = (v.x & keep) | put; else if (j == 1) v.y = (v.y & keep) | put; else if (j == 2) v.z = (v.z & keep) | put; else v.w = (v.w & keep) | put;
+}
+__device__ __forceinline__ void store_planes(const KP& p, uint8_t* __restrict__ tp, const uint32_t* __restrict__ bits, const PlaneLane& q) {
+  if (!q.on) return;
+  const int W = p.W, H = p.H, S = p.S;
+  uint32_t m = 0;  // bit k: cell c0 + k holds a canonical wall
+  for (int x = q.x0, sh = q.sh0; sh < 16 && x < W; ++x, sh += H) {
+    const uint32_t l = bits[(LINE_X0 + x) * BS], wl = l & 0xFFFFu & ~(l >> 16);
+    m |= (sh >= 0) ? (wl << sh) : (wl >> (-sh));
+  }
+  uint32_t w[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) w[j] = (((m >> (4 * j)) & 15u) * 0x00204081u) & 0x01010101u;
+  uint4 vt = make_uint4(w[0] * MG_T_WALL, w[1] * MG_T_WALL, w[2] * MG_T_WALL, w[3] * MG_T_WALL);
+  uint4 vc = make_uint4(w[0] * MG_C_WORST, w[1] * MG_C_WORST, w[2] * MG_C_WORST, w[3] * MG_C_WORST);
+  uint4 vs = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+  for (int k = 0; k < OBJ_SLOTS; ++k) {  // Goal / BonusTiles (always listed: the caller checked image_planes)
+    const uint32_t e = bits[(OBJ_WORD0 + k) * BS];
+    const int rel = (int)(e & 15u) * H + (int)((e >> 4) & 15u) - q.c0;
+    if ((e >> 31) && (unsigned)rel < 16u) {
+      patch_byte(vt, rel, (e >> 8) & 15u); patch_byte(vc, rel, (e >> 12) & 15u); patch_byte(vs, rel, (e >> 16) & 255u);
     }
-    __syncwarp();
+  }
+  *reinterpret_cast<uint4*>(tp + q.c0) = vt;
+  *reinterpret_cast<uint4*>(tp + S + q.c0) = vc;
+  *reinterpret_cast<uint4*>(tp + 2 * S + q.c0) = vs;
+}
+// the envs of `mask` (bit = env of the tile), two per pass: the lower half-warp takes one, the upper half-warp the next
+__device__ __forceinline__ void store_planes_of(const KP& p, uint32_t mask, long long env0, const uint32_t* __restrict__ s_bits, int lane) {
+  if (mask == 0u) return;
+  const PlaneLane q = plane_lane(p, lane);
+  while (mask != 0u) {
+    const int e1 = __ffs(mask) - 1;
+    mask &= mask - 1u;
+    const int e2 = __ffs(mask) - 1;  // -1: none
+    mask &= mask - 1u;               // (0 & -1 stays 0)
+    const int e = (lane < 16) ? e1 : e2;
+    if (e >= 0) store_planes(p, p.grid + (env0 + e) * 3 * p.S, s_bits + e, q);
   }
 }
 
-
+// Fast route of the rare path: only a few envs of the tile finished their episode (a long-running batch whose episodes have
+// drifted apart: one or two per tile and step) and no env needs the sequential step replay.  Env e goes to warp e % A, which
+// regenerates it (warp_reset: lanes = placement tries), stores its byte planes itself and hands its scratch words -- borrowed
+// from the already zeroed output tile -- back clean: no table, no plane image in shared memory, no bulk copy to wait for, and
+// a single CTA-wide barrier (the caller's).  Returns true if some env was left for the general route (nothing of it committed).
+template <int A>
+__device__ __forceinline__ bool fast_resets(const KP& p, uint32_t todo, uint32_t* s_flag, uint32_t* s_bits, uint32_t* s_rec, int32_t* s_env,
+                                            uint32_t* wk, long long env0, int n_valid, int a, int lane) {
+  bool failed = false, used = false;
+  uint32_t ok = 0;
+  for (int e = a; e < n_valid; e += A) {
+    if (!((todo >> e) & 1u)) continue;
+    used = true;
+    if (warp_reset<A>(p, (unsigned long long)(p.env_offset + env0 + e), s_bits + e, s_rec + e * (A * 4), s_env + e * 4, wk, lane)) {
+      ok |= 1u << e;
+      if (lane == 0) s_flag[e] &= ~FL_RESET;  // FL_BITS_DIRTY stays: the env's bit-plane words go back to global memory
+    } else failed = true;
+    __syncwarp();
+  }
+  store_planes_of(p, ok, env0, s_bits, lane);
+  if (used) {  // the scratch lives in the output tile: zero again
+    wk[lane] = 0u;
+    if (lane < 4) wk[32 + lane] = 0u;
+  }
+  return failed;
+}
 
 // Reset of the finished envs of a tile: MultiGridEnv.reset (base.py:402-416) + _gen_grid (empty.py:9-16, cluttered.py:25-36,
 // goalcycle.py:30-51), split so that the expensive part is parallel and the sequential part is cheap.  Per chunk of NT tries:
@@ -275,13 +352,14 @@ __device__ __forceinline__ void tile_resets(const KP& p, uint32_t* s_flag, uint3
   const int W = p.W, H = p.H;
   uint8_t* const table = reinterpret_cast<uint8_t*>(scratch);  // [NT][32 envs]
   uint32_t* const s_pending = scratch + NT * 32 / 4;
+  uint8_t* const s_list = reinterpret_cast<uint8_t*>(s_pending + 4);  // [32] the pending envs, compacted
   // lane == env in every warp: the same word everywhere
   const uint32_t todo = __ballot_sync(0xFFFFFFFFu, lane < n_valid && (s_flag[lane] & (FL_SLOW | FL_RESET)) == FL_RESET);
   if (todo == 0u) return;
   const bool fixed = p.goal_mode == MG_GOAL_FIXED;
   // fresh bit-plane chunks: wall_rect (base.py:172-176), the fixed goal (put_obj base.py:655-662), an empty object list
-  for (int i = tid; i < ENVS_PER_CTA * BITS_WORDS; i += 32 * A) {
-    const int e = i / BITS_WORDS, w = i - e * BITS_WORDS;
+  for (int i = tid; i < ENVS_PER_CTA * BITS_WORDS; i += 32 * A) {  // i = w * 32 + e (tile-transposed words)
+    const int e = i & 31, w = i >> 5;
     if (!((todo >> e) & 1u)) continue;
     uint32_t v = 0u;
     if (w >= LINE_X0 && w < LINE_X0 + 16) {
@@ -304,8 +382,10 @@ __device__ __forceinline__ void tile_resets(const KP& p, uint32_t* s_flag, uint3
   uint32_t pending = todo;
   for (int chunk = 0; chunk < MAXCH; ++chunk) {
     const int n_items = __popc(pending) * (NT / 2);
+    if (a == 0 && ((pending >> lane) & 1u)) s_list[__popc(pending & ((1u << lane) - 1u))] = (uint8_t)lane;  // k-th pending env
+    __syncthreads();
     for (int i = tid; i < n_items; i += 32 * A) {
-      const int e = (int)__fns(pending, 0u, i / (NT / 2) + 1), j = i % (NT / 2);
+      const int e = (int)s_list[i / (NT / 2)], j = i % (NT / 2);
       const unsigned long long g = (unsigned long long)(p.env_offset + env0 + e);
       const U4 r = philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)s_env[e * 4 + 1], TAG_RESET | (uint32_t)(chunk * (NT / 2) + j),
                                  (uint32_t)p.seed, (uint32_t)(p.seed >> 32));
@@ -316,21 +396,21 @@ __device__ __forceinline__ void tile_resets(const KP& p, uint32_t* s_flag, uint3
     if (a == 0) {
       bool open = (pending >> lane) & 1u;
       if (open) {
-        uint32_t* const bits = s_bits + lane * BITS_WORDS;
+        uint32_t* const bits = s_bits + lane;
         for (int t = 0; t < NT; ++t) {
           const uint32_t cell = table[t * 32 + lane];
           const int x = (int)(cell & 15u), y = (int)(cell >> 4);
-          const uint32_t line = bits[LINE_X0 + x];
+          const uint32_t line = bits[(LINE_X0 + x) * BS];
           const uint32_t cb = (line >> y) & 0x10001u;  // bit 0 wall, bit 16 Goal / BonusTile
           const bool agent = obj >= n_static;
           if (agent ? !(cb & 1u) : cb == 0u) {
             if (!agent) {
               const uint32_t bit = (obj < n_other) ? 0x10000u : 1u;
-              bits[LINE_X0 + x] = line | (bit << y);
-              bits[LINE_Y0 + y] |= bit << x;
+              bits[(LINE_X0 + x) * BS] = line | (bit << y);
+              bits[(LINE_Y0 + y) * BS] |= bit << x;
               if (obj < n_other) {
                 const uint32_t e = (obj < n_goal) ? obj_entry(x, y, MG_T_GOAL, MG_C_GREEN, 0) : obj_entry(x, y, MG_T_BONUS, MG_C_YELLOW, obj - n_goal);
-                if (n_listed < OBJ_SLOTS) bits[OBJ_WORD0 + n_listed++] = e;
+                if (n_listed < OBJ_SLOTS) bits[(OBJ_WORD0 + n_listed++) * BS] = e;
               }
             } else {
               const int q = obj - n_static;
@@ -387,7 +467,7 @@ __device__ __noinline__ void rare_path(const KP& p, const int tile, const int st
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, a = tid >> 5;
   const int W = p.W, H = p.H, S = p.S;
-  const bool image_planes = (p.goal_mode != MG_GOAL_NONE ? 1 : 0) + p.n_bonus <= OBJ_SLOTS && 3 * S <= SM::OUT_AREA;
+  const bool image_planes = (p.goal_mode != MG_GOAL_NONE ? 1 : 0) + p.n_bonus <= OBJ_SLOTS;
   double* s_rew = reinterpret_cast<double*>(smem + SM::REW);
   uint8_t* s_done = smem + SM::DONE;
   uint8_t* s_out = smem + SM::OUT;
@@ -407,14 +487,19 @@ __device__ __noinline__ void rare_path(const KP& p, const int tile, const int st
   const bool mine = lane < n_valid;
   const long long env = env0 + lane;
   uint32_t* const rec = s_rec + lane * (A * 4);
-  uint32_t* const bits = s_bits + lane * BITS_WORDS;
+  uint32_t* const bits = s_bits + lane;
   uint8_t* const tp = p.grid + env * 3 * S;
   {
     // lane == env in every warp: the envs are dealt out over the CTA's warps (env e goes to warp e % A), so that A warps
     // instead of one chew through the sequential code of mg_env.cuh; scratch lives in the (not yet used) output tile
-    if (image_planes) {  // few finished envs: warp by warp; many (episodes in lock step): table-driven; leftovers: sequential code below
-      warp_resets<A>(p, s_flag, s_bits, s_rec, s_env, s_scr + a * 64, env0, n_valid, a, lane);
-      __syncthreads();
+    if (image_planes) {  // few finished envs: warp by warp (fast route); many (episodes in lock step): table-driven; leftovers: sequential code below
+      // lane == env in every warp: the same words everywhere
+      const uint32_t todo = __ballot_sync(0xFFFFFFFFu, mine && (s_flag[lane] & (FL_SLOW | FL_RESET)) == FL_RESET);
+      const uint32_t slow = __ballot_sync(0xFFFFFFFFu, mine && (s_flag[lane] & FL_SLOW));
+      if (slow == 0u && __popc(todo) <= WARP_RESET_MAX * A) {
+        const bool failed = fast_resets<A>(p, todo, s_flag, s_bits, s_rec, s_env, s_scr + a * 36, env0, n_valid, a, lane);
+        if (!__syncthreads_or(failed ? 1 : 0)) return;  // the usual case: done, the barrier publishes the new episodes to the view threads
+      }
       tile_resets<A>(p, s_flag, s_bits, s_rec, s_env, s_scr, env0, n_valid, tid);
     }
     if (a == lane % A && mine) {
@@ -448,54 +533,12 @@ __device__ __noinline__ void rare_path(const KP& p, const int tile, const int st
     }
     __syncthreads();
     if (image_planes) {
-      // The byte planes of the regenerated envs, rebuilt from their bit-plane lines (walls) and object lists (Goal,
-      // BonusTiles) in the -- still unused -- output area, group by group, and stored with bulk copies: a fresh world is
-      // 3*S bytes of mostly zeros, which single lanes writing to global memory would turn into hundreds of scattered stores.
-      const int plane_bytes = 3 * S;
-      const int G = min(ENVS_PER_CTA, SM::OUT_AREA / plane_bytes);
-      const uint32_t image_mask = __ballot_sync(0xFFFFFFFFu, mine && (s_flag[lane] & FL_IMAGE));  // lane == env: the same word in every warp
-      for (int g0 = 0; g0 < n_valid; g0 += G) {
-        const int gn = min(G, n_valid - g0);
-        const uint32_t group_mask = (image_mask >> g0) & (gn == 32 ? 0xFFFFFFFFu : ((1u << gn) - 1u));  // envs of the group that were reset
-        if (group_mask == 0u) continue;
-        {
-          int4* z = reinterpret_cast<int4*>(s_out);
-          for (int i = tid; i < gn * plane_bytes / 16; i += 32 * A) z[i] = make_int4(0, 0, 0, 0);
-        }
-        __syncthreads();
-        for (int i = tid; i < gn * 16; i += 32 * A) {  // one (env, x-line) pair per iteration
-          const int e = i >> 4, x = i & 15;
-          if (x >= W || !((group_mask >> e) & 1u)) continue;
-          const uint32_t* eb = s_bits + (g0 + e) * BITS_WORDS;
-          const uint32_t w = eb[LINE_X0 + x];
-          uint8_t* img = s_out + e * plane_bytes + x * H;
-          uint32_t walls = w & 0xFFFFu & ~(w >> 16), others = w >> 16;
-          while (walls) {
-            const int y = __ffs(walls) - 1;
-            walls &= walls - 1u;
-            img[y] = MG_T_WALL; img[S + y] = MG_C_WORST;
-          }
-          while (others) {
-            const int y = __ffs(others) - 1;
-            others &= others - 1u;
-            const uint32_t oe = obj_lookup(eb, x, y);  // always listed: image_planes requires goal + bonus tiles <= OBJ_SLOTS
-            img[y] = (uint8_t)((oe >> 8) & 15u); img[S + y] = (uint8_t)((oe >> 12) & 15u); img[2 * S + y] = (uint8_t)((oe >> 16) & 255u);
-          }
-        }
-        fence_proxy_async_smem();
-        __syncthreads();
-        if (a == 0) {
-          const bool all = group_mask == (gn == 32 ? 0xFFFFFFFFu : ((1u << gn) - 1u));
-          if (all ? lane == 0 : (lane < gn && ((group_mask >> lane) & 1u))) {
-            fence_proxy_async_smem();
-            if (all) bulk_s2g(p.grid + (env0 + g0) * plane_bytes, s_out, (uint32_t)(gn * plane_bytes));
-            else bulk_s2g(p.grid + (env0 + g0 + lane) * plane_bytes, s_out + lane * plane_bytes, (uint32_t)plane_bytes);
-            bulk_commit();
-            bulk_wait_read0();
-          }
-        }
-        __syncthreads();
-      }
+      // The byte planes of the regenerated envs (FL_IMAGE) from their bit-plane lines and object lists: env e by warp e % A,
+      // coalesced 16-byte stores straight to global memory (round 1 staged plane images in the output area and sent them with
+      // bulk copies it then had to wait for: four CTA-wide barriers per group of 19 envs, 2/3 of the all-reset step).
+      // lane == env in every warp: the same word everywhere; warp a takes the envs e with e % A == a
+      const uint32_t image_mask = __ballot_sync(0xFFFFFFFFu, mine && (s_flag[lane] & FL_IMAGE) && lane % A == a);
+      store_planes_of(p, image_mask, env0, s_bits, lane);
     }
     zero_out_tile<OBS, A, SM>(s_out, tid);  // the sequential path borrowed the output area: clean it again
     __syncthreads();
@@ -546,7 +589,7 @@ __global__ void __launch_bounds__(32 * A, ctas_per_sm<OBS, V, A, NST>()) fused2_
     const long long e0 = (long long)tile * ENVS_PER_CTA;
     const int nv = (int)min((long long)ENVS_PER_CTA, p.B - e0);
     unsigned char* st = smem + stage * SM::STAGE;
-    const uint32_t wbytes = (uint32_t)nv * (BITS_WORDS * 4u), rbytes = (uint32_t)nv * (A * 16u), ebytes = (uint32_t)nv * 16u;
+    const uint32_t wbytes = (uint32_t)(ENVS_PER_CTA * BITS_WORDS * 4) /* always the whole tile-transposed chunk */, rbytes = (uint32_t)nv * (A * 16u), ebytes = (uint32_t)nv * 16u;
     const uint32_t abytes = (!KS && nv == ENVS_PER_CTA) ? (uint32_t)(ENVS_PER_CTA * A * 4) : 0u;  // KS: actions change every step, read directly
     if (a == 0) {
       mbar_expect_tx(s_bar + stage, wbytes + rbytes + ebytes + abytes);
@@ -629,7 +672,7 @@ __global__ void __launch_bounds__(32 * A, ctas_per_sm<OBS, V, A, NST>()) fused2_
 
   // ---- every agent plays its action on a private copy of its record (base.py:517-622) ----
   uint32_t* const rec = s_rec + lane * (A * 4);
-  uint32_t* const bits = s_bits + lane * BITS_WORDS;
+  uint32_t* const bits = s_bits + lane;  // word w of this env at bits[w * BS]: bank == lane for every w
   uint8_t* const tp = p.grid + env * 3 * S;
   uint32_t w0 = 0, w1 = 0, errb = 0, base_stamp = 0;
   bool moved = false, slow = false;
@@ -646,11 +689,11 @@ __global__ void __launch_bounds__(32 * A, ctas_per_sm<OBS, V, A, NST>()) fused2_
         const int fx = cx + ((dir == 0) ? 1 : (dir == 2) ? -1 : 0), fy = cy + ((dir == 1) ? 1 : (dir == 3) ? -1 : 0);  // agents.py:183
         const bool inb = (unsigned)fx < (unsigned)W && (unsigned)fy < (unsigned)H;
         if (!inb) errb |= MG_ERR_STACK;  // grid.get asserts in-bounds (base.py:154-156); never hit inside wall_rect
-        const uint32_t fc = inb ? ((bits[LINE_X0 + (fx & 15)] >> (fy & 15)) & 0x10001u) : 1u;  // 0 empty, 1 canonical wall, else "other"
+        const uint32_t fc = inb ? ((bits[(LINE_X0 + (fx & 15)) * BS] >> (fy & 15)) & 0x10001u) : 1u;  // 0 empty, 1 canonical wall, else "other"
         if (fc <= 1u) {  // empty or wall in front: only forward can do anything (pickup / toggle need an object, drop needs hands full)
           if (action == MG_A_FORWARD) {
             if (fc == 0u) {
-              const uint32_t cc = (bits[LINE_X0 + (cx & 15)] >> (cy & 15)) & 0x10001u;
+              const uint32_t cc = (bits[(LINE_X0 + (cx & 15)) * BS] >> (cy & 15)) & 0x10001u;
               if (cc != 0u) {  // leaving a cell that holds a static object: it must be overlappable (base.py:558)
                 const uint32_t ccell = cell_triple(bits, cx & 15, cy & 15, tp, H, S);
                 if (!can_overlap_static((int)(ccell & 0xFFu), (int)(ccell >> 16))) errb |= MG_ERR_STACK;
@@ -666,7 +709,7 @@ __global__ void __launch_bounds__(32 * A, ctas_per_sm<OBS, V, A, NST>()) fused2_
           const int ftype = (int)(fcell & 0xFFu), fstate = (int)(fcell >> 16);
           if (action == MG_A_FORWARD) {  // base.py:538-585 (ghost mode: other agents never block)
             if (can_overlap_static(ftype, fstate)) {
-              const uint32_t cc = (bits[LINE_X0 + (cx & 15)] >> (cy & 15)) & 0x10001u;
+              const uint32_t cc = (bits[(LINE_X0 + (cx & 15)) * BS] >> (cy & 15)) & 0x10001u;
               if (cc != 0u) {
                 const uint32_t ccell = cell_triple(bits, cx & 15, cy & 15, tp, H, S);
                 if (!can_overlap_static((int)(ccell & 0xFFu), (int)(ccell >> 16))) errb |= MG_ERR_STACK;
@@ -806,13 +849,13 @@ __global__ void __launch_bounds__(32 * A, ctas_per_sm<OBS, V, A, NST>()) fused2_
       //   rotated view: the line is bit-reversed and its halves swapped back, view column a <-> line bit v0 + V-1 - a
       const int shw = rev ? (32 - V - v0) : (v0 + 16);
       // line of view row b = u0 + b (or u0 + V-1 - b): slot index + 1, clamped as unsigned to the zero guard lines 0 and 17
-      const uint32_t lines_s = smem_u32(bits + (vertical ? LINE_Y0 - 1 : LINE_X0 - 1));
+      const uint32_t lines_s = smem_u32(bits + (vertical ? LINE_Y0 - 1 : LINE_X0 - 1) * BS);
       const int ustep = flip ? -1 : 1, ubase = (flip ? u0 + V - 1 : u0) + 1;
       uint32_t T[V], OT[V], OP[V], M[V];
 #pragma unroll
       for (int b = 0; b < V; ++b) {
         uint32_t w;
-        asm("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(lines_s + 4u * min((uint32_t)(ubase + b * ustep), 17u)));
+        asm("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(lines_s + (4u * BS) * min((uint32_t)(ubase + b * ustep), 17u)));
         if (rev) w = __byte_perm(__brev(w), 0u, 0x1032);  // reversed line, OP back in the low half
         OP[b] = (w << 16) >> shw;                          // bits above the window (neighbouring cells) are masked by
         OT[b] = (w & 0xFFFF0000u) >> shw;                  // the visibility rows below
@@ -864,7 +907,7 @@ __global__ void __launch_bounds__(32 * A, ctas_per_sm<OBS, V, A, NST>()) fused2_
       if (oth64 != 0ull) {  // visible Goal / BonusTile / Key ...: the object list answers for (almost) all of them
 #pragma unroll
         for (int k = 0; k < OBJ_SLOTS; ++k) {
-          const uint32_t e = bits[OBJ_WORD0 + k];
+          const uint32_t e = bits[(OBJ_WORD0 + k) * BS];
           if (!(e >> 31)) continue;
           const int ex = (int)(e & 15u), ey = (int)((e >> 4) & 15u);
           const int vb = bu + su * (vertical ? ey : ex), va = bv + sv * (vertical ? ex : ey);
@@ -950,10 +993,26 @@ __global__ void __launch_bounds__(32 * A, ctas_per_sm<OBS, V, A, NST>()) fused2_
     }
   }
   if (KS && a == 0 && mine) { if (stage) dirty_acc1 |= s_flag[lane] & FL_BITS_DIRTY; else dirty_acc0 |= s_flag[lane] & FL_BITS_DIRTY; }
-  if (a == 0 && mine && last_step && ((KS ? (stage ? dirty_acc1 : dirty_acc0) : s_flag[lane]) & FL_BITS_DIRTY)) {
-    fence_proxy_async_smem();
-    bulk_s2g(p.cellbits + env * BITS_WORDS, bits, BITS_WORDS * 4u);
-    bulk_commit();
+  if (a == 0) {
+    // envs whose bit-plane lines changed (reset, plane edit): many -> the tile's chunk goes back whole; few -> their words
+    // alone (an env's words are 128 bytes apart in the tile-transposed layout: lanes = words, plain stores)
+    const uint32_t dm = __ballot_sync(0xFFFFFFFFu, mine && last_step && ((KS ? (stage ? dirty_acc1 : dirty_acc0) : s_flag[lane]) & FL_BITS_DIRTY));
+    if (dm != 0u) {
+      uint32_t* const gb = p.cellbits + env0 * BITS_WORDS;
+      if (__popc(dm) > 6) {
+        if (lane == 0) {
+          fence_proxy_async_smem();
+          bulk_s2g(gb, s_bits, (uint32_t)(ENVS_PER_CTA * BITS_WORDS * 4));
+          bulk_commit();
+        }
+      } else {
+        for (uint32_t m = dm; m != 0u; m &= m - 1u) {
+          const int e = __ffs(m) - 1;
+          gb[lane * BS + e] = s_bits[lane * BS + e];
+          if (lane + 32 < BITS_WORDS) gb[(lane + 32) * BS + e] = s_bits[(lane + 32) * BS + e];
+        }
+      }
+    }
   }
   if (OBS == 2) {
     // ---- RGB: MultiGrid.render (base.py:301-331) of the tile's 32*A views from their tile-id maps.  Warp w expands views
@@ -1049,7 +1108,8 @@ static int launch_one(const KP& p, cudaStream_t s, int n_steps = 1) {
   const long long slots = (long long)resident[dev & 63] * sm_count(dev);
   const long long rounds = (tiles + slots - 1) / slots;
   if (KS && rounds > NST) return MG_E_UNSUPPORTED;  // K steps per launch: every tile's state has to stay in a stage of its CTA
-  const long long grid = getenv("MG_F2_RAGGED") ? std::min(tiles, slots) : (tiles + rounds - 1) / rounds;
+  long long grid = getenv("MG_F2_RAGGED") ? std::min(tiles, slots) : (tiles + rounds - 1) / rounds;
+  if (!KS && getenv("MG_F2_ONE_TILE")) grid = tiles;  // experiment: one tile per CTA, the hardware scheduler refills the SMs
   if (getenv("MG_F2_VERBOSE")) fprintf(stderr, "fused2<OBS=%d,V=%d,A=%d,NST=%d,KS=%d>: %d CTAs/SM x %d SMs, %lld tiles in %lld rounds -> grid %lld, %d B shared, %d step(s)\n", OBS, V, A, NST, (int)KS, resident[dev & 63], sm_count(dev), tiles, rounds, grid, smem_bytes, n_steps);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(32 * A); cfg.dynamicSmemBytes = (size_t)smem_bytes; cfg.stream = s;
@@ -1067,6 +1127,10 @@ static int launch_a(const KP& p, cudaStream_t s) {
   // encoded observations: two input stages (the next tile is prefetched); RGB: the image expansion dwarfs everything else,
   // one stage leaves more shared memory for resident CTAs
   constexpr int NS = OBS == 1 ? 2 : 1;
+  if (OBS == 1 && VO0 && p.A == 3) {  // experiment: single input stage (more resident CTAs) for the headline shape
+    static const int nst1 = getenv("MG_F2_NST") ? atoi(getenv("MG_F2_NST")) : 0;
+    if (nst1 == 1) return launch_one<OBS, V, 3, VO0, 1>(p, s);
+  }
   switch (p.A) {
     case 1: return launch_one<OBS, V, 1, VO0, NS>(p, s);
     case 2: return launch_one<OBS, V, 2, VO0, NS>(p, s);

@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(32 * MG_MAX_AGENTS, 4) fused_kernel(const __gr
   if (tid < ENVS_PER_CTA) s_flag[tid] = 0u;
   __syncthreads();
   if (tid == 0) {
-    const uint32_t wbytes = (uint32_t)n_valid * (BITS_WORDS * 4u), rbytes = (uint32_t)n_valid * (uint32_t)A * 16u, ebytes = (uint32_t)n_valid * 16u;
+    const uint32_t wbytes = (uint32_t)(ENVS_PER_CTA * BITS_WORDS * 4) /* the whole transposed tile */, rbytes = (uint32_t)n_valid * (uint32_t)A * 16u, ebytes = (uint32_t)n_valid * 16u;
     mbar_expect_tx(s_bar, wbytes + rbytes + ebytes);
     bulk_g2s(s_bits, p.cellbits + env0 * BITS_WORDS, wbytes, s_bar);
     bulk_g2s(s_rec, p.agents + env0 * A * 16, rbytes, s_bar);
@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(32 * MG_MAX_AGENTS, 4) fused_kernel(const __gr
 
   // ---- phase 1: every agent plays its action on a private copy of its record ----
   uint32_t* rec = s_rec + le * A * 4;
-  const uint32_t* bits = s_bits + le * BITS_WORDS;
+  const uint32_t* bits = s_bits + le;
   uint8_t* tp = p.grid + env * 3 * S;
   uint32_t w0 = 0, w1 = 0, errb = 0, base_stamp = 0;
   bool moved = false, slow = false;
@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(32 * MG_MAX_AGENTS, 4) fused_kernel(const __gr
     }
   } else if (slow_env && a == 0) {
     used_scratch = true;
-    EnvCtx<32> c{p, s_trec + le, tp, s_bits + le * BITS_WORDS, s_scr + le, 0, 0, 0, 0u, false};
+    EnvCtx<32> c{p, s_trec + le, tp, s_bits + le, s_scr + le, 0, 0, 0, 0u, false};
     for (int q = 0; q < A; ++q) { c.R(q, 0) = rec[q * 4]; c.R(q, 1) = rec[q * 4 + 1]; c.R(q, 2) = rec[q * 4 + 2]; }
     c.sc = s_env[le * 4]; c.ep = s_env[le * 4 + 1]; c.tl = s_env[le * 4 + 2]; c.w3 = (uint32_t)s_env[le * 4 + 3];
     seq_step(c, (unsigned long long)(p.env_offset + env), p.actions + env * A, p.rewards + env * A);
@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(32 * MG_MAX_AGENTS, 4) fused_kernel(const __gr
   if (scratch_state) {
     // finished envs: MultiGridEnv.reset (base.py:402-416), one lane per env spread over all warps of the CTA
     if (mine && a == 0 && (s_flag[le] & FL_RESET)) {
-      EnvCtx<32> c{p, s_trec + le, tp, s_bits + le * BITS_WORDS, s_scr + le, 0, 0, 0, 0u, false};
+      EnvCtx<32> c{p, s_trec + le, tp, s_bits + le, s_scr + le, 0, 0, 0, 0u, false};
       for (int q = 0; q < A; ++q) { c.R(q, 0) = rec[q * 4]; c.R(q, 1) = rec[q * 4 + 1]; c.R(q, 2) = rec[q * 4 + 2]; }
       c.sc = s_env[le * 4]; c.ep = s_env[le * 4 + 1]; c.tl = s_env[le * 4 + 2]; c.w3 = (uint32_t)s_env[le * 4 + 3];
       seq_reset(c, (unsigned long long)(p.env_offset + env));
@@ -240,10 +240,13 @@ __global__ void __launch_bounds__(32 * MG_MAX_AGENTS, 4) fused_kernel(const __gr
     bulk_s2g(p.envrec + env0 * 4, s_env, (uint32_t)n_valid * 16u);
     bulk_commit();
   }
-  if (warp == 0 && lane < n_valid && (s_flag[lane] & FL_BITS_DIRTY)) {
-    fence_proxy_async_smem();
-    bulk_s2g(p.cellbits + (env0 + lane) * BITS_WORDS, s_bits + lane * BITS_WORDS, BITS_WORDS * 4u);
-    bulk_commit();
+  if (warp == 0) {  // bit-plane lines changed (reset, plane edit): the tile's (transposed) chunk goes back whole
+    const uint32_t dirty = __ballot_sync(0xFFFFFFFFu, lane < n_valid && (s_flag[lane] & FL_BITS_DIRTY));
+    if (dirty != 0u && lane == 0) {
+      fence_proxy_async_smem();
+      bulk_s2g(p.cellbits + env0 * BITS_WORDS, s_bits, (uint32_t)(ENVS_PER_CTA * BITS_WORDS * 4));
+      bulk_commit();
+    }
   }
   asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }

@@ -63,13 +63,13 @@ template <int V>
 __device__ __forceinline__ void rows_from_bits(const uint32_t* __restrict__ bits /* this env's words */, const ViewGeom& g,
                                                uint32_t (&T)[V], uint32_t (&NE)[V], uint32_t (&CW)[V]) {
   constexpr uint32_t RM = (1u << V) - 1u;
-  const uint32_t* bp = bits + (g.vertical ? LINE_Y0 : LINE_X0);
+  const uint32_t* bp = bits + (g.vertical ? LINE_Y0 : LINE_X0) * BS;
   const int sh = g.v0 + 8;                  // >= 1: the 16 board bits are parked at bits 8..23 before shifting right
 #pragma unroll
   for (int b = 0; b < V; ++b) {
     const int idx = g.u0 + (g.flip ? V - 1 - b : b);
     const bool in = (unsigned)idx < (unsigned)g.Lu;  // rows outside the world: empty, transparent
-    const uint32_t w = in ? bp[idx] : 0u;
+    const uint32_t w = in ? bp[idx * BS] : 0u;
     uint32_t opq = (((w & 0xFFFFu) << 8) >> sh) & RM;
     uint32_t ot = (((w >> 16) << 8) >> sh) & RM;
     if (g.rev) { opq = rev_bits<V>(opq); ot = rev_bits<V>(ot); }
@@ -378,7 +378,7 @@ __device__ __forceinline__ void obs_view(const KP& p, const ObsSmem<V>& o, int v
     if (BITS) {
 #pragma unroll
       for (int k = 0; k < OBJ_SLOTS; ++k) {  // the object list answers for (almost) all of them without touching the planes
-        const uint32_t e = bits[OBJ_WORD0 + k];
+        const uint32_t e = bits[(OBJ_WORD0 + k) * BS];
         int va, vb;
         if (!(e >> 31) || !world_to_view<V>(g, (int)(e & 15u), (int)((e >> 4) & 15u), va, vb)) continue;
         const uint32_t bit = 1u << (8 * (vb & 3) + va);

@@ -24,10 +24,10 @@ __global__ void __launch_bounds__(32 * MG_MAX_AGENTS) obs_kernel(const __grid_co
   if (tid == 0) mbar_init(s_bar, 1);
   __syncthreads();
   if (tid == 0) {
-    const uint32_t wbytes = BITS ? (uint32_t)n_valid * (BITS_WORDS * 4u) : (uint32_t)n_valid * 3u * (uint32_t)S;
+    const uint32_t wbytes = BITS ? (uint32_t)(ENVS_PER_CTA * BITS_WORDS * 4) : (uint32_t)n_valid * 3u * (uint32_t)S;  // bit-planes: always the whole (transposed) tile
     const uint32_t rbytes = (uint32_t)n_valid * (uint32_t)A * 16u;
     mbar_expect_tx(s_bar, wbytes + rbytes);
-    if (BITS) bulk_g2s(s_bits, p.cellbits + env0 * BITS_WORDS, wbytes, s_bar);
+    if (BITS) bulk_g2s(s_bits, p.cellbits + env0 * BITS_WORDS, wbytes, s_bar);  // env0 is a multiple of 32: the tile's chunk
     else bulk_g2s(s_grid, p.grid + env0 * 3 * S, wbytes, s_bar);
     bulk_g2s(s_rec, p.agents + env0 * A * 16, rbytes, s_bar);
   }
@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(32 * MG_MAX_AGENTS) obs_kernel(const __grid_co
   if (tid < n_valid * A) {
     const int le = tid / A, a = tid - le * A;
     obs_view<OBS, V, BITS>(p, o, tid, a, env0 + le, s_rec + le * A * 4, BITS ? p.grid + (env0 + le) * 3 * S : s_grid + le * 3 * S,
-                           BITS ? s_bits + le * BITS_WORDS : nullptr);
+                           BITS ? s_bits + le : nullptr);
   }
   fence_proxy_async_smem();  // writer side of the generic -> async proxy hand-over for the bulk copies issued after the barrier
   __syncthreads();

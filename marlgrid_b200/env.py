@@ -73,7 +73,8 @@ class BatchedMultiGridEnv:
         self.grid = torch.empty((B, 3, S), dtype=torch.uint8, device=dev)
         self.agent_rec = torch.empty((B, A, 16), dtype=torch.uint8, device=dev)  # per-agent records (the reference keeps this state on env.agents[i])
         self.envrec = torch.empty((B, 4), dtype=torch.int32, device=dev)
-        self.cellbits = torch.empty((B, 44), dtype=torch.int32, device=dev)  # derived bit-planes (include/marlgrid_b200.h)
+        # derived bit-planes (include/marlgrid_b200.h), tile-transposed: word w of env e at [e // 32, w, e % 32]
+        self.cellbits = torch.zeros(((B + 31) // 32, 44, 32), dtype=torch.int32, device=dev)
         self.rewards = torch.zeros((B, A), dtype=torch.float64, device=dev)
         self.done = torch.zeros((B,), dtype=torch.bool, device=dev)  # the kernels write 0/1 bytes: no conversion pass per step
         # The observation tensor returned by step() is a view of a device buffer.  With obs_buffers = 2 (default) steps

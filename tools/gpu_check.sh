@@ -26,20 +26,48 @@ if [[ "$what" == *cfg4* ]]; then
 fi
 if [[ "$what" == *ncu* ]]; then
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
-      python bench.py --steps 100 --warmup 10 --no-cpu-baseline --e2e-steps 3 > gpurun_out/ncu_bench.log 2>&1
+      python bench.py --steps 100 --warmup 10 --profile --e2e-steps 3 > gpurun_out/ncu_bench.log 2>&1
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:fused2?_kernel -s 40 -c 2 -f -o gpurun_out/prof \
-      python bench.py --steps 20 --warmup 10 --no-cpu-baseline --e2e-steps 3 > gpurun_out/ncu_full.log 2>&1
+      python bench.py --steps 20 --warmup 10 --profile --e2e-steps 3 > gpurun_out/ncu_full.log 2>&1
   ls -la gpurun_out/
+fi
+if [[ "$what" == *r2first* ]]; then
+  # round 2, first call: the new big-shape parity tests, the bench line + reference arm, launch-shape experiments
+  timeout 1200 python -m pytest tests -m gpu -x -q --durations=8 > gpurun_out/tests.log 2>&1; echo "tests exit $?" | tee -a gpurun_out/tests.log
+  tail -14 gpurun_out/tests.log
+  timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke exit $?" | tee -a gpurun_out/smoke.log
+  timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench exit $?"
+  cat gpurun_out/bench.json; tail -5 gpurun_out/bench.err
+  timeout 300 python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "ref exit $?"
+  cat gpurun_out/bench_ref.json
+fi
+if [[ "$what" == *r2b* ]]; then
+  # parity, the bench line, then one full ncu capture of the hot kernel and of the all-reset launch
+  timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/tests.log 2>&1; echo "tests exit $?" | tee -a gpurun_out/tests.log
+  tail -5 gpurun_out/tests.log
+  timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench exit $?"
+  python - <<'PY'
+import json
+d = json.loads([l for l in open("gpurun_out/bench.json") if l.startswith("{")][-1])
+print("value %.3e  %.2f us/step  frac %.3f  sustained %.2f us  warm %.2f us  persistent %.2f us  all_reset %.1f us  desync %.2f us (x%.2f)  e2e %.3e" % (
+    d["value"], 1e3 * d["ms_per_step"], d["roofline"]["frac"], 1e3 * d["sustained"]["ms_per_step"], 1e3 * d["warm"]["ms_per_step"],
+    1e3 * d["rollout_persistent"]["ms_per_step"], d["all_reset_us"], d["desync"]["us_per_step"], d["desync"]["vs_lockstep_warm"], d["e2e"]["value"]))
+print({k: (round(1e3 * v["ms_per_step"], 2), round(v["roofline"]["frac"], 3)) for k, v in d["other_configs"].items()})
+PY
+  timeout 300 ncu --set full --clock-control none --import-source on -k regex:fused2_kernel -s 40 -c 2 -f -o gpurun_out/prof \
+      python bench.py --steps 20 --warmup 10 --profile --e2e-steps 3 > gpurun_out/ncu_full.log 2>&1; echo "ncu exit $?"
+  timeout 300 ncu --set full --clock-control none --import-source on -k regex:fused2_kernel -s 99 -c 1 -f -o gpurun_out/prof_reset \
+      python bench.py --steps 6 --warmup 120 --replicas 1 --profile --e2e-steps 3 > gpurun_out/ncu_reset.log 2>&1; echo "ncureset exit $?"
 fi
 if [[ "$what" == *exp* ]]; then
   # quick A/B of launch-shape knobs of the specialised fused kernel (no CPU baseline)
-  for knobs in ${EXP_KNOBS:-"MG_F2_CTAS_PER_SM=7" "MG_F2_CTAS_PER_SM=6" "MG_F2_RAGGED=1" "MG_F2_PDL=0"}; do
+  for knobs in ${EXP_KNOBS:-"MG_F2_CTAS_PER_SM=7" "MG_F2_NST=1,MG_F2_ONE_TILE=1" "MG_F2_NST=1,MG_F2_RAGGED=1" "MG_F2_NST=1" "MG_F2_ONE_TILE=1" "MG_F2_PDL=0"}; do
     echo "== $knobs"
-    env $knobs MG_F2_VERBOSE=1 timeout 300 python bench.py --steps 600 --warmup 60 --no-cpu-baseline --e2e-steps 3 2>gpurun_out/exp.err | python -c "
+    env ${knobs//,/ } MG_F2_VERBOSE=1 timeout 300 python bench.py --steps 200 --warmup 60 --quick --e2e-steps 3 2>gpurun_out/exp.err | python -c "
 import sys, json
 for l in sys.stdin:
     if l.startswith('{'):
-        d = json.loads(l); print('value %.3e  cold-rr %.2f us  flushed med %.2f us  warm %.2f us' % (d['value'], 1e3*d['ms_per_step'], 1e3*d['step_ms_flushed']['median'], 1e3*d['warm']['ms_per_step']))
+        d = json.loads(l); t = d['timing']['repeat_ms']; print('value %.3e  median %.2f us  min %.2f  max %.2f us/step  sustained %.2f' % (d['value'], 1e3*d['ms_per_step'], 1e3*t['min']/d['steps'], 1e3*t['max']/d['steps'], 1e3*d['sustained']['ms_per_step']))
 "
     sort -u gpurun_out/exp.err | head -3
   done 2>&1 | tee gpurun_out/exp.log
@@ -47,12 +75,12 @@ fi
 if [[ "$what" == *ncureset* ]]; then
   # the step on which every episode ends (step_count hits max_steps = 100): launch 100 of the single-family warm-up
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:fused2?_kernel -s 99 -c 1 -f -o gpurun_out/prof_reset \
-      python bench.py --steps 6 --warmup 120 --replicas 1 --no-cpu-baseline --e2e-steps 3 > gpurun_out/ncu_reset.log 2>&1
+      python bench.py --steps 6 --warmup 120 --replicas 1 --profile --e2e-steps 3 > gpurun_out/ncu_reset.log 2>&1
   ls -la gpurun_out/
 fi
 if [[ "$what" == *ncurgb* ]]; then
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:fused -s 6 -c 1 -f -o gpurun_out/prof_rgb \
-      python bench.py --workload cfg4 --steps 4 --warmup 4 > gpurun_out/ncu_rgb.log 2>&1
+      python bench.py --workload cfg4 --steps 4 --warmup 4 --profile > gpurun_out/ncu_rgb.log 2>&1
   ls -la gpurun_out/
 fi
 if [[ "$what" == *sanitize* ]]; then
@@ -95,7 +123,7 @@ if [[ "$what" == *final* ]]; then
   timeout 120 python -m pytest tests -m gpu -x -q > gpurun_out/tests.log 2>&1; echo "tests exit $?" | tee -a gpurun_out/tests.log
   tail -2 gpurun_out/tests.log
   timeout 60 ncu --set full --clock-control none --import-source on -k regex:fused2_kernel -s 40 -c 2 -f -o gpurun_out/prof \
-      python bench.py --steps 20 --warmup 10 --no-cpu-baseline --e2e-steps 3 > gpurun_out/ncu_full.log 2>&1; echo "ncu exit $?"
+      python bench.py --steps 20 --warmup 10 --profile --e2e-steps 3 > gpurun_out/ncu_full.log 2>&1; echo "ncu exit $?"
   timeout 90 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench exit $?"
   cat gpurun_out/bench.json
   timeout 40 python tools/desync_probe.py > gpurun_out/desync.log 2>&1; tail -8 gpurun_out/desync.log

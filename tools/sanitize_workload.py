@@ -1,5 +1,7 @@
 """Small workload for compute-sanitizer (tools/gpu_check.sh sanitize): every path of the specialised fused kernel --
-encoded and RGB observation, full and ragged tiles, more tiles than CTAs' first round, the all-reset step."""
+encoded and RGB observation, full and ragged tiles, more tiles than CTAs' first round, the all-reset step (table-driven
+reset), desynchronised episodes (warp-cooperative reset of a few envs per tile), a world so cluttered that placement runs
+fail and fall through to the sequential reset, objects whose pickup / toggle replays an env sequentially, K steps per launch."""
 import os
 import sys
 
@@ -18,4 +20,36 @@ for t in range(steps):
     rgb.step(rgb.random_actions(t))
 torch.cuda.synchronize()
 assert int(enc.episode.min().item()) >= (2 if steps >= 100 else 1) and int(enc.err.max().item()) == 0 and int(rgb.err.max().item()) == 0
-print("sanitize workload ok:", steps, "steps; checksums", int(enc.obs.sum().item()), int(rgb.obs.long().sum().item()))
+
+# desynchronised episodes: a short horizon and a forward-biased policy end a few envs per tile and step (warp_reset route)
+des = envs.make("MarlGrid-3AgentCluttered15x15-v0", num_envs=160, obs_mode="encoded", seed=8, max_steps=23)
+des.reset()
+for t in range(60):
+    a = des.random_actions(t)
+    a[torch.rand(a.shape, device=a.device) < 0.5] = 2
+    des.step(a)
+# dense clutter: runs of 32 failed placement tries -> the warp / table resets hand the env to the sequential reset
+dense = envs.make("MarlGrid-3AgentCluttered11x11-v0", num_envs=96, obs_mode="encoded", seed=99, clutter_density=None, n_clutter=66, max_steps=5)
+dense.reset()
+for t in range(16):
+    dense.step(dense.random_actions(t))
+# objects: effective pickup / drop / toggle replay the env with the sequential step inside the fused kernel
+obj = envs.make("MarlGrid-3AgentEmpty9x9-v0", num_envs=64, obs_mode="encoded", seed=3, max_steps=30)
+obj.reset()
+planes = obj.planes
+planes[:, 0, 3, 3], planes[:, 1, 3, 3] = 9, 3   # Key blue
+planes[:, 0, 5, 4], planes[:, 1, 5, 4] = 10, 2  # Ball green
+planes[:, 0, 4, 6], planes[:, 1, 4, 6], planes[:, 2, 4, 6] = 11, 3, 2  # Door blue, closed
+obj.sync_derived()
+for t in range(40):
+    obj.step(obj.random_actions(t))
+# K steps per launch (state resident in shared memory)
+ks = envs.make("MarlGrid-3AgentCluttered15x15-v0", num_envs=96, obs_mode="encoded", seed=4, max_steps=11)
+ks.reset()
+ks.rollout_all(torch.stack([ks.random_actions(t) for t in range(25)]))
+torch.cuda.synchronize()
+for e in (des, dense, ks):
+    assert int((e.err & ~2).max().item()) == 0  # (MG_ERR_PLACEMENT may legitimately appear in the dense world)
+# (the object world may raise what the reference raises -- a door closed on an agent, base.py:558: error bits, not a kernel fault)
+print("sanitize workload ok:", steps, "steps; checksums", int(enc.obs.sum().item()), int(rgb.obs.long().sum().item()), int(des.obs.sum().item()),
+      int(dense.obs.sum().item()), int(obj.obs.sum().item()), "obj err bits", int(obj.err.max().item()), "carried", int((obj.agent_carrying[:, :, 0] != 0).sum().item()))
