@@ -342,11 +342,24 @@ def main():
         host_s = time.perf_counter() - t0
         barrier()
         ms = max_over_ranks([e0.elapsed_time(e1) / steps])[0]
+        py = None
+        if n_fams == 1 and mode == "encoded":  # launch-bound sizes: the same steps enqueued from C (mg_rollout_fused), without the Python call per step
+            py = {"ms_per_step": ms, "host_issue_ms_per_step": 1e3 * host_s / steps, "note": "env.step() called in a Python loop"}
+            tape = torch.stack(acts)
+            fs[0].rollout(tape)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps // 16):
+                fs[0].rollout(tape)
+            e1.record()
+            barrier()
+            ms = max_over_ranks([e0.elapsed_time(e1) / (steps // 16 * 16)])[0]
         ach = algo * Bo / (ms * 1e-3) / 1e9
         del fs
         torch.cuda.empty_cache()
         return {"env_id": env_id, "batch_per_gpu": Bo, "obs": mode, "value": world * Bo / (ms * 1e-3), "agent_steps_per_s": world * Ao * Bo / (ms * 1e-3),
-                "ms_per_step": ms, "steps": steps, "host_issue_ms_per_step": 1e3 * host_s / steps,
+                "ms_per_step": ms, "steps": steps, "host_issue_ms_per_step": 1e3 * host_s / steps, "python_loop": py,
                 "roofline": {"achieved": ach, "peak": peak_gbs, "frac": ach / peak_gbs, "algorithmic_bytes_per_launch": algo * Bo}}
 
     def mk(name, **kw):
@@ -478,27 +491,36 @@ def main():
         extras["warm"] = {"value": world * B / (warm_ms * 1e-3), "ms_per_step": warm_ms, "steps": KW,
                           "note": "steps back to back on one family, state L2-resident, launched from mg_rollout_fused"}
 
-        # ---- desynchronised episodes (tools/desync_probe.py in short): a forward-biased policy ends episodes at irregular times ----
-        dact = actions.clone()
-        dact[torch.rand(dact.shape, device=dev) < 0.5] = 2
+        # ---- desynchronised episodes: the steady state of a long-running batch.  The step counters of a fresh family are
+        # spread uniformly over an episode, so every step ~1 % of the envs (in ~27 % of the tiles) time out and are regenerated
+        # inside the kernel, instead of all of them on every 100th step.
         env.reset()
-        blocks = []
-        for _ in range(6):  # 6 x 512 steps
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _k in range(4):
-                env.rollout(dact)
-            e1.record()
-            torch.cuda.synchronize()
-            blocks.append(1e3 * e0.elapsed_time(e1) / (4 * POOL))
-        dlast = max_over_ranks([blocks[-1]])[0]
-        extras["desync"] = {"us_per_step_blocks_of_512": blocks, "us_per_step": dlast, "vs_lockstep_warm": dlast / (1e3 * warm_ms),
-                            "note": "one family (L2-resident), half of the actions forced to `forward`: after ~3000 steps most steps find a few finished envs in many tiles; "
-                                    "ratio against `warm` (same regime, episodes in lock step)"}
-        del dact
+        env.envrec[:, 0] = torch.randint(0, 100, (B,), device=dev, dtype=torch.int32)
+        env.rollout(actions[:100])  # warm-up; also spreads the episode numbers
+        KD = 400
+        pg_stats = (ctypes.c_uint64 * 2)()
+        L.mg_pregen_stats(pg_stats, 1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        done_steps = 0
+        while done_steps < KD:
+            n = min(POOL, KD - done_steps)
+            env.rollout(actions[:n])
+            done_steps += n
+        e1.record()
+        torch.cuda.synchronize()
+        d_us = max_over_ranks([1e3 * e0.elapsed_time(e1) / KD])[0]
+        sc = env.step_count
+        L.mg_pregen_stats(pg_stats, 0)
+        extras["desync"] = {"us_per_step": d_us, "vs_lockstep_warm": d_us / (1e3 * warm_ms), "steps": KD,
+                            "pregen_hit_rate": float(pg_stats[0]) / max(1.0, float(pg_stats[0] + pg_stats[1])),
+                            "envs_finishing_per_step": float((sc == 0).sum().item()),
+                            "note": "one family (L2-resident) whose step counters are spread uniformly over the episode length: ~655 envs finish and are "
+                                    "regenerated in every step; ratio against `warm` (same regime, all episodes in lock step, no reset in the window average)"}
 
         # ---- on-device rollout loop: 100 steps per launch (mg_rollout_persistent), every step's outputs written to its own slice ----
         TP = 100
+        env.reset()  # episodes back in lock step (the desynchronised family above is a different regime)
         pout = (torch.empty((TP, B, A, 7, 7, 3), dtype=torch.uint8, device=dev), torch.empty((TP, B, A), dtype=torch.float64, device=dev),
                 torch.empty((TP, B), dtype=torch.bool, device=dev))
         env.rollout_all(actions[:TP], out=pout)
@@ -538,7 +560,7 @@ def main():
     if not args.quick:
         # cfg2: 4 096 envs -- 128 tiles, launch / latency bound; the state of one family is L2-resident whatever one does
         other["cfg2"] = timed_rollout(mk("cfg2"), 1, 400, "cfg2")
-        other["cfg2"]["note"] = "BASELINE configs[1]; env.step() in a Python loop (one launch per step), state L2-resident (1 MB)"
+        other["cfg2"]["note"] = "BASELINE configs[1]: 128 tiles on 148 SMs -- one launch per step enqueued from C (mg_rollout_fused), launch / latency bound; state L2-resident (1 MB)"
         # cfg5's per-GPU share: 131 072 envs; 3 families round robin (a step touches ~100 MB)
         other["cfg5_share"] = timed_rollout(mk("cfg5_share"), 3, 120, "cfg5_share")
         other["cfg5_share"]["note"] = "BASELINE configs[4] per-GPU share (131 072 envs/GPU; x N GPUs = the sharded batch), 3 families round robin"

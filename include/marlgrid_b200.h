@@ -141,6 +141,13 @@ typedef struct MgState {
   int64_t n_envs;   /* B (envs on THIS device) */
   int64_t env_offset; /* global index of local env 0 (RNG is keyed by the global index) */
   uint64_t seed;
+  uint32_t* pregen; /* [B][64] or NULL: PRE-GENERATED NEXT WORLDS.  A fresh world (walls, goal, bonus tiles, spawn cells) is a pure
+                       function of (seed, global env index, episode number), so the library produces every env's next one ahead
+                       of time -- a background kernel on a low-priority side stream, launched after each mg_step_fused* /
+                       mg_rollout_* call, running concurrently with the following steps (no ordering edge; a tag per slot + a
+                       seqlock decide whether a step kernel copies the slot or generates the world itself: both give the same
+                       world, results never depend on timing).  It takes reset()'s Philox + rejection sampling off the step's
+                       critical path.  Zeroed by mg_init.  Before freeing or re-purposing the buffer call mg_pregen_drain(). */
 } MgState;
 
 typedef void* mg_stream_t; /* cudaStream_t */
@@ -157,6 +164,18 @@ int64_t mg_obs_bytes_per_env(const MgConfig* cfg, int rgb);
 /* Zero-initialise state as a freshly constructed env family (all agents unplaced, dir 0,
  * episode 0).  Replaces MultiGridEnv.__init__ state setup (base.py:353-367, agents.py:90). */
 int mg_init(const MgConfig* cfg, const MgState* st, mg_stream_t stream);
+
+/* Pre-generated worlds (MgState.pregen): words per env; one explicit generator pass on `stream` (MG_PREGEN_STREAM = the
+ * library's own side stream); wait for the side stream (before freeing the buffers a pass may still touch); switch the
+ * automatic launch after every fused step off / on (default on). */
+#define MG_PREGEN_STREAM ((mg_stream_t)(intptr_t)-1)
+int mg_pregen_words_per_env(void);
+int mg_pregen_run(const MgConfig* cfg, const MgState* st, mg_stream_t stream);
+int mg_pregen_drain(void);
+void mg_pregen_set_auto(int on);
+/* counters of the current device since load / the last reset: [0] envs a step kernel regenerated by copying a pre-generated
+ * world, [1] envs it had to generate itself (synchronises with the device) */
+int mg_pregen_stats(uint64_t* hits_misses, int reset);
 
 /* Recompute the derived state (MgState.cellbits) from the planes and agent records. */
 int mg_sync_derived(const MgConfig* cfg, const MgState* st, mg_stream_t stream);

@@ -14,7 +14,7 @@ EXPORTS = (
     "mg_version", "mg_build_info", "mg_sizeof_config", "mg_config_validate", "mg_obs_bytes_per_env", "mg_init", "mg_sync_derived", "mg_reset", "mg_step",
     "mg_obs_encode", "mg_obs_rgb", "mg_step_fused", "mg_step_fused_rgb", "mg_rollout_fused", "mg_rollout_persistent", "mg_rollout_fused_rr", "mg_random_actions",
     "mg_los_batch", "mg_engine_create", "mg_engine_destroy", "mg_engine_reset", "mg_engine_step", "mg_engine_copy_only", "mg_host_alloc",
-    "mg_host_free", "mg_launch_count", "mg_debug_set_mid_event", "mg_debug_force_two_kernels", "mg_debug_force_general_fused",
+    "mg_host_free", "mg_launch_count", "mg_pregen_words_per_env", "mg_pregen_run", "mg_pregen_drain", "mg_pregen_set_auto", "mg_pregen_stats", "mg_debug_set_mid_event", "mg_debug_force_two_kernels", "mg_debug_force_general_fused",
 )
 
 _lib = None
@@ -79,6 +79,10 @@ def load():
     L.mg_host_free.argtypes = [P]
     L.mg_host_free.restype = None
     L.mg_launch_count.restype = I64
+    L.mg_pregen_run.argtypes = [CFG, ST, P]
+    L.mg_pregen_set_auto.argtypes = [I]
+    L.mg_pregen_set_auto.restype = None
+    L.mg_pregen_stats.argtypes = [P, I]
     L.mg_debug_set_mid_event.argtypes = [P]
     L.mg_debug_set_mid_event.restype = None
     L.mg_debug_force_two_kernels.argtypes = [I]

@@ -21,10 +21,11 @@ UNITS = {
     "mg_obs_kernels.cu": ["mg_obs.cuh"],
     "mg_fused_kernels.cu": ["mg_env.cuh", "mg_obs.cuh"],
     "mg_fused2.cu": [],
-    "mg_fused2_enc7.cu": ["mg_env.cuh", "mg_fused2.cuh"],
-    "mg_fused2_enc5.cu": ["mg_env.cuh", "mg_fused2.cuh"],
-    "mg_fused2_rgb7.cu": ["mg_env.cuh", "mg_fused2.cuh"],
-    "mg_fused2_rgb5.cu": ["mg_env.cuh", "mg_fused2.cuh"],
+    "mg_pregen.cu": ["mg_world.cuh"],
+    "mg_fused2_enc7.cu": ["mg_env.cuh", "mg_world.cuh", "mg_fused2.cuh"],
+    "mg_fused2_enc5.cu": ["mg_env.cuh", "mg_world.cuh", "mg_fused2.cuh"],
+    "mg_fused2_rgb7.cu": ["mg_env.cuh", "mg_world.cuh", "mg_fused2.cuh"],
+    "mg_fused2_rgb5.cu": ["mg_env.cuh", "mg_world.cuh", "mg_fused2.cuh"],
 }
 COMMON = ["mg_device.cuh", "mg_common.cuh"]
 

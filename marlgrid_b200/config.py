@@ -57,6 +57,7 @@ class MgState(ctypes.Structure):
         ("n_envs", ctypes.c_int64),
         ("env_offset", ctypes.c_int64),
         ("seed", ctypes.c_uint64),
+        ("pregen", ctypes.c_void_p),
     ]
 
 

@@ -1,5 +1,7 @@
 // mg_abi.cu -- host side of libmarlgrid_b200.so: the C ABI of include/marlgrid_b200.h on top of the kernel launchers.
 #include <atomic>
+#include <mutex>
+#include <unordered_map>
 
 #include "mg_common.cuh"
 
@@ -9,6 +11,12 @@ static std::atomic<long long> g_launches{0};
 namespace mg {
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 }
+
+#define MG_CUDA(x)                                \
+  do {                                            \
+    cudaError_t _e = (x);                         \
+    if (_e != cudaSuccess) return (int)_e;        \
+  } while (0)
 
 static int check_cfg(const MgConfig* c) {
   if (!c) return MG_E_CONFIG;
@@ -29,6 +37,17 @@ static int check_cfg(const MgConfig* c) {
   return 0;
 }
 
+static unsigned long long* device_stats() {  // [2] counters per device, allocated on first use
+  static unsigned long long* ptr[64] = {nullptr};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (ptr[dev & 63] == nullptr) {
+    if (cudaMalloc(&ptr[dev & 63], 2 * sizeof(unsigned long long)) != cudaSuccess) return nullptr;
+    cudaMemset(ptr[dev & 63], 0, 2 * sizeof(unsigned long long));
+  }
+  return ptr[dev & 63];
+}
+
 static KP make_kp(const MgConfig* c, const MgState* st) {
   KP p;
   memset(&p, 0, sizeof p);
@@ -44,12 +63,40 @@ static KP make_kp(const MgConfig* c, const MgState* st) {
   p.n_tiles = (c->n_static_kinds + 1) * (1 + 4 * c->n_agents);
   p.orient_slots = 4;
   p.wall_enc = (uint32_t)MG_T_WALL | ((uint32_t)MG_C_WORST << 8);
+  p.pregen = p.cellbits ? st->pregen : nullptr;
+  p.stats = p.pregen ? device_stats() : nullptr;
   return p;
 }
 
 static int g_force_two_kernels = 0;    // test hook: exercise the per-env step kernel + observe kernel pair
 static int g_force_general_fused = 0;  // test hook: exercise the general fused kernel where the specialised one applies
 
+// The generator is launched after every PREGEN_EVERY-th fused step of a family (a pass refills every stale slot it finds; an
+// env needs its next world one episode later, so a lag of a few steps costs nothing): per-family step counters, keyed by the
+// address of the family's slots.
+constexpr int PREGEN_EVERY = 8;
+static bool pregen_due(const void* key) {
+  static std::mutex mu;
+  static std::unordered_map<const void*, unsigned> counters;
+  std::lock_guard<std::mutex> lock(mu);
+  if (counters.size() > 4096) counters.clear();
+  static const int every = getenv("MG_PREGEN_EVERY") ? std::max(1, atoi(getenv("MG_PREGEN_EVERY"))) : PREGEN_EVERY;  // experiments
+  return (counters[key]++ % (unsigned)every) == 0;
+}
+// a ring of events for the "generator pass after this step" edges (a wait captures the record it was called after: an event
+// can be recorded again as soon as the wait has been enqueued)
+static cudaEvent_t pregen_event() {
+  static std::mutex mu;
+  static cudaEvent_t ring[64][32] = {{nullptr}};
+  static unsigned next[64] = {0};
+  std::lock_guard<std::mutex> lock(mu);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaEvent_t& e = ring[dev & 63][next[dev & 63]++ & 31];
+  if (e == nullptr && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) e = nullptr;
+  return e;
+}
+static int g_pregen_auto = 1;           // 0: mg_step* do not launch the background world generator (tests; callers that drive mg_pregen_run themselves)
 static cudaEvent_t g_mid_event = nullptr;  // profiling hook: recorded between the two launches of a step
 
 // env.step: one fused launch when eligible; else the step kernel (incl. auto-reset), then the observation
@@ -57,6 +104,20 @@ static int launch_step_obs(const KP& p, int obs, cudaStream_t s) {
   if (obs != 0 && !g_force_two_kernels && fused_eligible(p)) {
     if (!g_force_general_fused) {  // specialised kernel for the common shapes (mg_fused2.cu); MG_E_UNSUPPORTED = not one of them
       const int e2 = launch_fused2(p, obs, s);
+      if (e2 == 0 && p.pregen != nullptr && p.autoreset && g_pregen_auto && pregen_due(p.pregen)) {
+        // the background world generator (mg_pregen.cu): one pass on the low-priority side stream, concurrent with the NEXT
+        // steps.  It starts once this step has finished (an event edge): the host may be a thousand launches ahead of the
+        // device, and a pass that ran when it was enqueued would look at the family long before the steps it is meant to
+        // follow.  Nothing ever waits for the pass.
+        cudaStream_t ps = pregen_stream();
+        cudaEvent_t ev = pregen_event();
+        if (ps != nullptr && ev != nullptr) {
+          MG_CUDA(cudaEventRecord(ev, s));
+          MG_CUDA(cudaStreamWaitEvent(ps, ev, 0));
+          const int e3 = launch_pregen(p, ps);
+          if (e3) return e3;
+        }
+      }
       if (e2 != MG_E_UNSUPPORTED) return e2;
     }
     return launch_fused(p, obs, s);
@@ -74,7 +135,7 @@ static int check_state(const MgConfig* c, const MgState* st) {
   int e = check_cfg(c);
   if (e) return e;
   if (!st || !st->grid || !st->agents || !st->envrec || st->n_envs < 0) return MG_E_ARG;
-  if (!aligned16(st->grid) || !aligned16(st->agents) || !aligned16(st->envrec) || !aligned16(st->cellbits)) return MG_E_ARG;
+  if (!aligned16(st->grid) || !aligned16(st->agents) || !aligned16(st->envrec) || !aligned16(st->cellbits) || !aligned16(st->pregen)) return MG_E_ARG;
   return 0;
 }
 
@@ -94,10 +155,39 @@ void mg_debug_set_mid_event(void* cuda_event) { g_mid_event = (cudaEvent_t)cuda_
 void mg_debug_force_two_kernels(int on) { g_force_two_kernels = on; }
 void mg_debug_force_general_fused(int on) { g_force_general_fused = on; }
 
+int mg_pregen_words_per_env(void) { return 64; }
+void mg_pregen_set_auto(int on) { g_pregen_auto = on; }
+
+int mg_pregen_run(const MgConfig* cfg, const MgState* st, mg_stream_t stream) {
+  int e = check_state(cfg, st);
+  if (e) return e;
+  if (st->n_envs == 0 || st->pregen == nullptr) return 0;
+  KP p = make_kp(cfg, st);
+  return launch_pregen(p, stream == MG_PREGEN_STREAM ? pregen_stream() : (cudaStream_t)stream);
+}
+
+int mg_pregen_stats(uint64_t* hits_misses, int reset) {
+  unsigned long long* d = device_stats();
+  if (d == nullptr || hits_misses == nullptr) return MG_E_ARG;
+  MG_CUDA(cudaMemcpy(hits_misses, d, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));  // (synchronises with the device)
+  if (reset) MG_CUDA(cudaMemset(d, 0, 2 * sizeof(unsigned long long)));
+  return 0;
+}
+
+int mg_pregen_drain(void) {
+  cudaStream_t ps = pregen_stream();
+  if (ps == nullptr) return 0;
+  return (int)cudaStreamSynchronize(ps);
+}
+
 int mg_init(const MgConfig* cfg, const MgState* st, mg_stream_t stream) {
   int e = check_state(cfg, st);
   if (e) return e;
   if (st->n_envs == 0) return 0;
+  if (st->pregen != nullptr) {  // no world is ready; a generator pass still in flight on a reused buffer must be over first
+    mg_pregen_drain();
+    MG_CUDA(cudaMemsetAsync(st->pregen, 0, (size_t)st->n_envs * 64 * sizeof(uint32_t), (cudaStream_t)stream));
+  }
   return launch_init(st->grid, st->agents, st->envrec, st->cellbits, st->n_envs, cfg->n_agents, cfg->plane_stride, (cudaStream_t)stream);
 }
 
@@ -255,11 +345,6 @@ struct MgEngine {
 
 constexpr int ENGINE_SLICES = 4;  // mg_engine_step cuts the batch into this many env ranges (multiples of 32 envs)
 
-#define MG_CUDA(x)                                \
-  do {                                            \
-    cudaError_t _e = (x);                         \
-    if (_e != cudaSuccess) return (int)_e;        \
-  } while (0)
 
 int mg_engine_create(MgEngine** out, const MgConfig* cfg, int64_t n_envs, int64_t env_offset, uint64_t seed, int device, int rgb,
                      const uint8_t* atlas_host, int64_t atlas_bytes) {
@@ -280,6 +365,7 @@ int mg_engine_create(MgEngine** out, const MgConfig* cfg, int64_t n_envs, int64_
   MG_CUDA(cudaMalloc(&en->st.agents, (size_t)n_envs * cfg->n_agents * MG_AGENT_REC));
   MG_CUDA(cudaMalloc(&en->st.envrec, (size_t)n_envs * MG_ENV_REC));
   MG_CUDA(cudaMalloc(&en->st.cellbits, (size_t)((n_envs + 31) / 32) * (BITS_WORDS * BS * 4)));  // whole tiles of 32 envs
+  MG_CUDA(cudaMalloc(&en->st.pregen, (size_t)n_envs * 64 * sizeof(uint32_t)));
   MG_CUDA(cudaMalloc(&en->d_actions, (size_t)n_envs * cfg->n_agents * sizeof(int32_t)));
   MG_CUDA(cudaMalloc(&en->d_rewards, (size_t)n_envs * cfg->n_agents * sizeof(double)));
   MG_CUDA(cudaMalloc(&en->d_done, (size_t)n_envs));
@@ -304,7 +390,8 @@ void mg_engine_destroy(MgEngine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
-  cudaFree(e->st.grid); cudaFree(e->st.agents); cudaFree(e->st.envrec); cudaFree(e->st.cellbits);
+  mg_pregen_drain();  // a generator pass may still be reading / writing this engine's buffers
+  cudaFree(e->st.grid); cudaFree(e->st.agents); cudaFree(e->st.envrec); cudaFree(e->st.cellbits); cudaFree(e->st.pregen);
   cudaFree(e->d_actions); cudaFree(e->d_rewards); cudaFree(e->d_done); cudaFree(e->d_obs); cudaFree(e->d_atlas);
   cudaStreamSynchronize(e->copy_stream);
   for (int i = 0; i < 8; ++i) cudaEventDestroy(e->slice_done[i]);
@@ -339,7 +426,7 @@ int mg_engine_step(MgEngine* e, const int32_t* actions_host, uint8_t* obs_host, 
   for (int64_t b0 = 0; b0 < B; b0 += slice, ++k) {
     const int64_t nb = std::min(slice, B - b0);
     MgState st = e->st;
-    st.grid += b0 * 3 * e->cfg.plane_stride; st.agents += b0 * A * MG_AGENT_REC; st.envrec += b0 * 4; st.cellbits += b0 * BITS_WORDS;
+    st.grid += b0 * 3 * e->cfg.plane_stride; st.agents += b0 * A * MG_AGENT_REC; st.envrec += b0 * 4; st.cellbits += b0 * BITS_WORDS; st.pregen += b0 * 64;
     st.n_envs = nb; st.env_offset = e->st.env_offset + b0;
     int32_t* d_act = e->d_actions + b0 * A;
     double* d_rew = e->d_rewards + b0 * A;

@@ -61,6 +61,8 @@ struct KP {
   int orient_slots;  // 1: atlas is rotation-equivariant (dir remap), 4: one slot per view orientation
   uint32_t hide;     // MgConfig.hide_types
   uint32_t wall_enc; // MG_T_WALL | MG_C_WORST << 8: the encoded canonical wall, as run-time data (see mg_fused2.cu)
+  uint32_t* pregen;  // MgState.pregen: pre-generated next worlds [B][64] (mg_world.cuh) or nullptr
+  unsigned long long* stats;  // per-device counters: [0] envs regenerated from a pre-generated world, [1] envs generated inside the step kernel
 };
 
 __device__ __forceinline__ bool cell_opaque(int type, int state) {  // objects.py:281-282,330-331
@@ -135,6 +137,8 @@ int launch_fused(const KP& p, int obs, cudaStream_t s);         // mg_fused_kern
 bool fused_eligible(const KP& p);
 constexpr int MG_E_UNSUPPORTED = -100;                          // internal: the specialised kernel has no instantiation for this shape
 int launch_fused2(const KP& p, int obs, cudaStream_t s);        // mg_fused2.cu: specialised (compile-time A, V) one-launch step+observe
-int launch_fused2_rollout(const KP& p, int n_steps, cudaStream_t s);  // the same kernel playing n_steps steps per launch (per-step output slices)
+int launch_fused2_rollout(const KP& p, int n_steps, cudaStream_t s);
+int launch_pregen(const KP& p, cudaStream_t s);                 // mg_pregen.cu: one pass of the background world generator over the family
+cudaStream_t pregen_stream();                                   // its low-priority side stream on the current device  // the same kernel playing n_steps steps per launch (per-step output slices)
 
 }  // namespace mg

@@ -27,6 +27,7 @@
 #include <cstdlib>
 
 #include "mg_env.cuh"
+#include "mg_world.cuh"
 
 namespace mg {
 
@@ -130,18 +131,6 @@ __device__ __forceinline__ uint64_t pack_rows8(const uint32_t (&r)[V]) {
   return ((uint64_t)hi << 32) | lo;
 }
 
-// Transpose of two 16x16 bit matrices at once: lane r < 16 holds row r of matrix 0 in bits 0..15 and row r of matrix 1 in
-// bits 16..31; returns, in lane c < 16, column c of both the same way.  Four butterfly stages (block swaps of 8, 4, 2, 1).
-__device__ __forceinline__ uint32_t transpose16x16_pair(uint32_t v, int lane) {
-#pragma unroll
-  for (int j = 8; j >= 1; j >>= 1) {
-    const uint32_t mask = j == 8 ? 0x00FF00FFu : j == 4 ? 0x0F0F0F0Fu : j == 2 ? 0x33333333u : 0x55555555u;
-    const uint32_t other = __shfl_xor_sync(0xFFFFFFFFu, v, j);
-    v = (lane & j) ? (((other >> j) & mask) | (v & ~mask)) : ((v & mask) | ((other & mask) << j));
-  }
-  return v;
-}
-
 // one-byte shared-memory store at a compile-time offset from a 32-bit shared address
 __device__ __forceinline__ void sts_u8(uint32_t saddr, uint32_t v) {
   asm volatile("st.shared.u8 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
@@ -150,102 +139,75 @@ __device__ __forceinline__ void sts_u8(uint32_t saddr, uint32_t v) {
 constexpr int WARP_RESET_MAX = 4;  // finished envs per warp up to which the warps regenerate them one by one
 
 // Warp-cooperative reset, for tiles in which only a few envs finish -- the normal state of a long-running batch, whose episodes
-// have drifted apart (tools/desync_probe.py): no table, no CTA-wide barriers, one env at a time per warp.
-// MultiGridEnv.reset (base.py:402-416) + _gen_grid (empty.py:9-16, cluttered.py:25-36, goalcycle.py:30-51) for ONE env by a
-// whole warp: lanes = consecutive placement tries of place_obj's rejection sampling (base.py:690-708).
-//   static objects (random goal, bonus tiles, clutter walls, in this order): scanning the tries in order, a try is accepted
-//     iff its cell is free of walls / objects AND no earlier accepted try hit the same cell (the object placed there is what
-//     the sequential code would find) -- within a batch of 32 tries that is "first valid lane of its cell" (match_any); the
-//     j-th accepted try gets the j-th object.
-//   agents (ghost mode: they may share cells): the tries after the last static object's, each non-wall try places the next agent.
-// Returns false WITHOUT having committed anything when the run is not an ordinary one (a whole batch of 32 tries without a
-// placement -- the only way max_tries, base.py:700-706, could come into play --, or more than MAXB batches): the caller then
-// runs the sequential code.  On success bits / rec / envr (shared memory) hold the new episode.
+// have drifted apart (tools/desync_probe.py): no table, no CTA-wide barriers, one env at a time per warp.  The placement itself
+// is world::warp_sample (mg_world.cuh: lanes = consecutive placement tries).  Returns false WITHOUT having committed anything when
+// the run is not an ordinary one: the caller then runs the sequential code.  On success bits / rec / envr (shared memory) hold
+// the new episode.
+template <int A>
+__device__ __forceinline__ void commit_episode(uint32_t* __restrict__ rec, int32_t* __restrict__ envr, uint32_t a_xy, int lane) {
+  if (lane < A) {  // agents.py:161-170 (dir survives), placement order = stamp order (base.py:409-412,686)
+    const uint32_t old = rec[lane * 4];
+    *reinterpret_cast<uint4*>(rec + lane * 4) = make_uint4((old & 0x00FF0000u) | a_xy | ((uint32_t)(MG_AF_PLACED | MG_AF_ACTIVE) << 24), 0xFF000000u, (uint32_t)lane, 0u);
+  }
+  if (lane == 0) {
+    envr[0] = 0; envr[1] += 1;
+    envr[3] = (int)(((uint32_t)envr[3] & 0xFFFF0000u) | (uint32_t)A);
+  }
+}
 template <int A>
 __device__ __forceinline__ bool warp_reset(const KP& p, unsigned long long g, uint32_t* __restrict__ bits, uint32_t* __restrict__ rec,
                                         int32_t* __restrict__ envr, uint32_t* __restrict__ wk /* 36 words of this warp */, int lane) {
-  constexpr int MAXB = 8;
-  const int W = p.W, H = p.H;
-  uint32_t* wall_x = wk;        // [16] bit y = canonical wall at (x, y)
-  uint32_t* other_x = wk + 16;  // [16] bit y = Goal / BonusTile at (x, y)
-  uint32_t* list = wk + 32;     // [4] object list entries
-  if (lane < 16) {
-    const uint32_t fullr = (1u << H) - 1u, endsr = 1u | (1u << (H - 1));
-    wall_x[lane] = (lane == 0 || lane == W - 1) ? fullr : (lane < W ? endsr : 0u);  // wall_rect base.py:172-176
-    other_x[lane] = (p.goal_mode == MG_GOAL_FIXED && lane == W - 2) ? (1u << (H - 2)) : 0u;  // put_obj(Goal) base.py:655-662
-  }
-  if (lane < OBJ_SLOTS) list[lane] = (lane == 0 && p.goal_mode == MG_GOAL_FIXED) ? obj_entry(W - 2, H - 2, MG_T_GOAL, MG_C_GREEN, 0) : 0u;
+  uint32_t a_xy;
+  if (!world::warp_sample<A>(p, g, (uint32_t)envr[1], wk, lane, a_xy)) return false;  // (ends with __syncwarp: every lane has read envr[1])
+  commit_episode<A>(rec, envr, a_xy, lane);
+  world::commit_lines<BS>(bits, wk, lane);
   __syncwarp();
-  const int n_goal = (p.goal_mode == MG_GOAL_RANDOM) ? 1 : 0, n_other = n_goal + p.n_bonus, n_static = n_other + p.n_clutter;
-  const int list_base = (p.goal_mode == MG_GOAL_FIXED) ? 1 : 0;
-  const uint32_t ep = (uint32_t)envr[1], lt = (1u << lane) - 1u;
-  int placed_static = 0, agents_done = 0;
-  uint32_t a_xy = 0;  // lane q < A: where agent q goes (x | y << 8)
-  for (int batch = 0; batch < MAXB; ++batch) {
-    const uint32_t k = (uint32_t)(batch * 32 + lane);
-    const U4 r = philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), ep, TAG_RESET | (k >> 1), (uint32_t)p.seed, (uint32_t)(p.seed >> 32));
-    const int x = (int)__umulhi((k & 1u) ? r.z : r.x, (uint32_t)W), y = (int)__umulhi((k & 1u) ? r.w : r.y, (uint32_t)H);
-    int start_lane = 0;
-    if (placed_static < n_static) {
-      const bool valid = !(((wall_x[x] | other_x[x]) >> y) & 1u);
-      const uint32_t vm = __ballot_sync(0xFFFFFFFFu, valid);
-      bool acc = false;
-      if (valid) acc = (__ffs(__match_any_sync(vm, x * 16 + y)) - 1) == lane;  // first valid try of this cell in the batch
-      const uint32_t am = __ballot_sync(0xFFFFFFFFu, acc);
-      if (am == 0u) return false;
-      const int j = placed_static + __popc(am & lt);  // index of the object this try would place
-      const bool take = acc && j < n_static;
-      const uint32_t tm = __ballot_sync(0xFFFFFFFFu, take);
-      if (take) {
-        if (j < n_other) {
-          atomicOr(&other_x[x], 1u << y);
-          const uint32_t e = (j < n_goal) ? obj_entry(x, y, MG_T_GOAL, MG_C_GREEN, 0) : obj_entry(x, y, MG_T_BONUS, MG_C_YELLOW, j - n_goal);
-          if (list_base + j < OBJ_SLOTS) list[list_base + j] = e;
-        } else atomicOr(&wall_x[x], 1u << y);
-      }
-      placed_static += __popc(tm);
-      __syncwarp();
-      if (placed_static < n_static) continue;
-      start_lane = 32 - __clz(tm);  // the agents' tries begin behind the last static object's
-    }
-    const bool valid_a = lane >= start_lane && !((wall_x[x] >> y) & 1u);
-    const uint32_t vma = __ballot_sync(0xFFFFFFFFu, valid_a);
-    if (vma == 0u) { if (start_lane == 0) return false; else continue; }
-    const int q = agents_done + __popc(vma & lt);
-    const uint32_t xy = (uint32_t)x | ((uint32_t)y << 8);
+  return true;
+}
+
+// Pre-generated worlds (mg_pregen.cu, mg_world.cuh): the finished envs of `mine` (bit = env of the tile; this warp's share)
+// whose slot holds the world of exactly their next episode are regenerated by copying it -- 46 words per env, the loads of up
+// to four envs in flight together.  Two dependent round trips to L2: the tags (acquire: the generator puts a tag up, with
+// release, after the slot is complete, and never touches a slot whose tag is valid for the env's current episode), then the
+// words.  Returns the envs done; the others take the generating routes.
+template <int A>
+__device__ __forceinline__ uint32_t consume_pregen(const KP& p, uint32_t mine, long long env0, uint32_t* __restrict__ s_bits,
+                                                   uint32_t* __restrict__ s_rec, int32_t* __restrict__ s_env, int lane) {
+  using namespace world;
+  if (p.pregen == nullptr || mine == 0u) return 0u;
+  const uint32_t* const pg = p.pregen + env0 * PG_WORDS;
+  bool ok = false;
+  if ((mine >> lane) & 1u) ok = ld_acquire_gpu(pg + lane * PG_WORDS + PG_TAG) == (uint32_t)s_env[lane * 4 + 1] + 1u;  // lane == env
+  uint32_t m = __ballot_sync(0xFFFFFFFFu, ok), done = 0u;
+  while (m != 0u) {
+    int e[4];
+    uint32_t v0[4], v1[4];
 #pragma unroll
-    for (int t = 0; t < A; ++t) {  // hand try "q == t" to lane t
-      const uint32_t src = __ballot_sync(0xFFFFFFFFu, valid_a && q == t);
-      if (src) { const uint32_t v = __shfl_sync(0xFFFFFFFFu, xy, __ffs(src) - 1); if (lane == t) a_xy = v; }
+    for (int j = 0; j < 4; ++j) { e[j] = __ffs(m) - 1; m &= m - 1u; }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      v0[j] = 0u; v1[j] = 0u;
+      if (e[j] >= 0) {
+        v0[j] = __ldcg(pg + e[j] * PG_WORDS + lane);                                                    // words 0..31
+        v1[j] = __ldcg(pg + e[j] * PG_WORDS + (lane < PG_XY0 - 32 + A ? 32 + lane : PG_SEED_LO + (lane & 1)));  // words 32..43, the agents' cells; else the seed
+      }
     }
-    agents_done += __popc(vma);
-    if (agents_done >= A) {
-      // ---- commit: records, env record, bit-plane lines (x-lines as sampled, y-lines by transposition), object list ----
-      __syncwarp();  // every lane has read envr[1] (the episode number keys the draws) before lane 0 advances it
-      if (lane < A) {  // agents.py:161-170 (dir survives), placement order = stamp order (base.py:409-412,686)
-        const uint32_t old = rec[lane * 4];
-        *reinterpret_cast<uint4*>(rec + lane * 4) = make_uint4((old & 0x00FF0000u) | a_xy | ((uint32_t)(MG_AF_PLACED | MG_AF_ACTIVE) << 24), 0xFF000000u, (uint32_t)lane, 0u);
-      }
-      if (lane == 0) {
-        envr[0] = 0; envr[1] = (int)(ep + 1u);
-        envr[3] = (int)(((uint32_t)envr[3] & 0xFFFF0000u) | (uint32_t)A);
-      }
-      // lane x < 16 holds its x-line (walls in the low half, Goal / BonusTiles in the high half); the y-lines are the
-      // transposed 16x16 bit matrices: four butterfly stages on both halves at once
-      const uint32_t xl = lane < 16 ? (wall_x[lane] | (other_x[lane] << 16)) : 0u;
-      const uint32_t yl = transpose16x16_pair(xl, lane);
-      if (lane < 16) {
-        bits[(LINE_X0 + lane) * BS] = xl;
-        bits[(LINE_Y0 + lane) * BS] = yl;
-      }
-      if (lane < 4) bits[(OBJ_WORD0 + lane) * BS] = list[lane];
-      if (lane >= 4 && lane < 8) bits[(OBJ_WORD0 + lane) * BS] = 0u;             // words 40..43
-      if (lane >= 8 && lane < 12) bits[((lane == 8) ? 0 : (lane == 9) ? 17 : (lane == 10) ? 18 : 35) * BS] = 0u;  // guard lines
-      __syncwarp();
-      return true;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (e[j] < 0) continue;
+      // the world was drawn with this family's seed (lanes 30 / 31 hold the slot's seed words)
+      const uint32_t slo = __shfl_sync(0xFFFFFFFFu, v1[j], 30), shi = __shfl_sync(0xFFFFFFFFu, v1[j], 31);
+      if (slo != (uint32_t)p.seed || shi != (uint32_t)(p.seed >> 32)) continue;
+      done |= 1u << e[j];
+      uint32_t* const bits = s_bits + e[j];
+      bits[lane * BS] = v0[j];
+      if (lane < BITS_WORDS - 32) bits[(32 + lane) * BS] = v1[j];
+      const uint32_t a_xy = __shfl_sync(0xFFFFFFFFu, v1[j], (PG_XY0 - 32 + lane) & 31);  // lane q < A: agent q's cell
+      commit_episode<A>(s_rec + e[j] * (A * 4), s_env + e[j] * 4, a_xy, lane);
     }
   }
-  return false;
+  __syncwarp();
+  return done;
 }
 
 // The byte planes of freshly regenerated envs, written straight to global memory: ONE ENV PER HALF-WARP, lane hl = lane & 15
@@ -312,12 +274,12 @@ __device__ __forceinline__ void store_planes_of(const KP& p, uint32_t mask, long
 // from the already zeroed output tile -- back clean: no table, no plane image in shared memory, no bulk copy to wait for, and
 // a single CTA-wide barrier (the caller's).  Returns true if some env was left for the general route (nothing of it committed).
 template <int A>
-__device__ __forceinline__ bool fast_resets(const KP& p, uint32_t todo, uint32_t* s_flag, uint32_t* s_bits, uint32_t* s_rec, int32_t* s_env,
-                                            uint32_t* wk, long long env0, int n_valid, int a, int lane) {
+__device__ __forceinline__ bool fast_resets(const KP& p, uint32_t todo /* this warp's envs still to generate */, uint32_t ok /* its envs copied from pre-generated worlds */,
+                                            uint32_t* s_flag, uint32_t* s_bits, uint32_t* s_rec, int32_t* s_env, uint32_t* wk, long long env0, int lane) {
   bool failed = false, used = false;
-  uint32_t ok = 0;
-  for (int e = a; e < n_valid; e += A) {
-    if (!((todo >> e) & 1u)) continue;
+  while (todo != 0u) {
+    const int e = __ffs(todo) - 1;
+    todo &= todo - 1u;
     used = true;
     if (warp_reset<A>(p, (unsigned long long)(p.env_offset + env0 + e), s_bits + e, s_rec + e * (A * 4), s_env + e * 4, wk, lane)) {
       ok |= 1u << e;
@@ -350,12 +312,29 @@ __device__ __forceinline__ void tile_resets(const KP& p, uint32_t* s_flag, uint3
   constexpr int NT = 32, MAXCH = 4;
   const int lane = tid & 31, a = tid >> 5;
   const int W = p.W, H = p.H;
-  uint8_t* const table = reinterpret_cast<uint8_t*>(scratch);  // [NT][32 envs]
-  uint32_t* const s_pending = scratch + NT * 32 / 4;
-  uint8_t* const s_list = reinterpret_cast<uint8_t*>(s_pending + 4);  // [32] the pending envs, compacted
+  uint8_t* const table0 = reinterpret_cast<uint8_t*>(scratch);             // two tables [NT][32 envs]: while warp 0 replays one chunk,
+  uint8_t* const table1 = reinterpret_cast<uint8_t*>(scratch + NT * 32 / 4);  // the other warps draw the next one
+  uint32_t* const s_pending = scratch + 2 * (NT * 32 / 4);
+  uint32_t* const s_ep = s_pending + 4;                                    // [32] the episode numbers that key the draws (before any commit)
+  uint8_t* const s_list = reinterpret_cast<uint8_t*>(s_ep + 32) + a * 32;  // per warp: [32] the pending envs, compacted
   // lane == env in every warp: the same word everywhere
   const uint32_t todo = __ballot_sync(0xFFFFFFFFu, lane < n_valid && (s_flag[lane] & (FL_SLOW | FL_RESET)) == FL_RESET);
   if (todo == 0u) return;
+  if (a == 0) s_ep[lane] = (uint32_t)s_env[lane * 4 + 1];
+  // the Philox blocks of (pending env, block) pairs of one chunk, by the threads [t0, t0 + nthr) of the CTA
+  auto fill = [&](int chunk, uint32_t pend, uint8_t* table, int ti, int nthr) {
+    if ((pend >> lane) & 1u) s_list[__popc(pend & ((1u << lane) - 1u))] = (uint8_t)lane;  // k-th pending env (this warp's copy)
+    __syncwarp();
+    const int n_items = __popc(pend) * (NT / 2);
+    for (int i = ti; i < n_items; i += nthr) {
+      const int e = (int)s_list[i / (NT / 2)], j = i % (NT / 2);
+      const unsigned long long g = (unsigned long long)(p.env_offset + env0 + e);
+      const U4 r = philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), s_ep[e], TAG_RESET | (uint32_t)(chunk * (NT / 2) + j), (uint32_t)p.seed, (uint32_t)(p.seed >> 32));
+      table[(2 * j) * 32 + e] = (uint8_t)(__umulhi(r.x, (uint32_t)W) | (__umulhi(r.y, (uint32_t)H) << 4));
+      table[(2 * j + 1) * 32 + e] = (uint8_t)(__umulhi(r.z, (uint32_t)W) | (__umulhi(r.w, (uint32_t)H) << 4));
+    }
+    __syncwarp();
+  };
   const bool fixed = p.goal_mode == MG_GOAL_FIXED;
   // fresh bit-plane chunks: wall_rect (base.py:172-176), the fixed goal (put_obj base.py:655-662), an empty object list
   for (int i = tid; i < ENVS_PER_CTA * BITS_WORDS; i += 32 * A) {  // i = w * 32 + e (tile-transposed words)
@@ -380,19 +359,14 @@ __device__ __forceinline__ void tile_resets(const KP& p, uint32_t* s_flag, uint3
 #pragma unroll
   for (int q = 0; q < A; ++q) axy[q] = 0u;
   uint32_t pending = todo;
+  __syncthreads();  // s_ep is there
+  fill(0, todo, table0, tid, 32 * A);
+  __syncthreads();  // also: the fresh lines above are complete
   for (int chunk = 0; chunk < MAXCH; ++chunk) {
-    const int n_items = __popc(pending) * (NT / 2);
-    if (a == 0 && ((pending >> lane) & 1u)) s_list[__popc(pending & ((1u << lane) - 1u))] = (uint8_t)lane;  // k-th pending env
-    __syncthreads();
-    for (int i = tid; i < n_items; i += 32 * A) {
-      const int e = (int)s_list[i / (NT / 2)], j = i % (NT / 2);
-      const unsigned long long g = (unsigned long long)(p.env_offset + env0 + e);
-      const U4 r = philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)s_env[e * 4 + 1], TAG_RESET | (uint32_t)(chunk * (NT / 2) + j),
-                                 (uint32_t)p.seed, (uint32_t)(p.seed >> 32));
-      table[(2 * j) * 32 + e] = (uint8_t)(__umulhi(r.x, (uint32_t)W) | (__umulhi(r.y, (uint32_t)H) << 4));
-      table[(2 * j + 1) * 32 + e] = (uint8_t)(__umulhi(r.z, (uint32_t)W) | (__umulhi(r.w, (uint32_t)H) << 4));
-    }
-    __syncthreads();  // also: the fresh lines above are complete
+    const uint8_t* const table = (chunk & 1) ? table1 : table0;
+    uint8_t* const next_table = (chunk & 1) ? table0 : table1;
+    // the other warps draw the next chunk for every env still pending now (a superset of what will be needed)
+    if (A > 1 && a != 0 && chunk + 1 < MAXCH) fill(chunk + 1, pending, next_table, tid - 32, 32 * (A - 1));
     if (a == 0) {
       bool open = (pending >> lane) & 1u;
       if (open) {
@@ -439,6 +413,7 @@ __device__ __forceinline__ void tile_resets(const KP& p, uint32_t* s_flag, uint3
       }
       const uint32_t still = __ballot_sync(0xFFFFFFFFu, open);
       if (lane == 0) *s_pending = still;
+      if (A == 1 && still != 0u && chunk + 1 < MAXCH) fill(chunk + 1, still, next_table, tid, 32);  // single-warp CTAs: no one to overlap with
     }
     __syncthreads();
     pending = *s_pending;
@@ -492,15 +467,28 @@ __device__ __noinline__ void rare_path(const KP& p, const int tile, const int st
   {
     // lane == env in every warp: the envs are dealt out over the CTA's warps (env e goes to warp e % A), so that A warps
     // instead of one chew through the sequential code of mg_env.cuh; scratch lives in the (not yet used) output tile
-    if (image_planes) {  // few finished envs: warp by warp (fast route); many (episodes in lock step): table-driven; leftovers: sequential code below
-      // lane == env in every warp: the same words everywhere
+    if (image_planes) {
+      // lane == env in every warp: the same words everywhere; env e belongs to warp e % A
       const uint32_t todo = __ballot_sync(0xFFFFFFFFu, mine && (s_flag[lane] & (FL_SLOW | FL_RESET)) == FL_RESET);
       const uint32_t slow = __ballot_sync(0xFFFFFFFFu, mine && (s_flag[lane] & FL_SLOW));
-      if (slow == 0u && __popc(todo) <= WARP_RESET_MAX * A) {
-        const bool failed = fast_resets<A>(p, todo, s_flag, s_bits, s_rec, s_env, s_scr + a * 36, env0, n_valid, a, lane);
-        if (!__syncthreads_or(failed ? 1 : 0)) return;  // the usual case: done, the barrier publishes the new episodes to the view threads
+      const uint32_t mine_a = todo & __ballot_sync(0xFFFFFFFFu, lane % A == a);
+      // 1. worlds the background generator has ready: a copy
+      const uint32_t got = consume_pregen<A>(p, mine_a, env0, s_bits, s_rec, s_env, lane);
+      if (lane == 0 && p.stats != nullptr && mine_a != 0u) {
+        if (got) atomicAdd(p.stats, (unsigned long long)__popc(got));
+        if (mine_a & ~got) atomicAdd(p.stats + 1, (unsigned long long)__popc(mine_a & ~got));
       }
-      tile_resets<A>(p, s_flag, s_bits, s_rec, s_env, s_scr, env0, n_valid, tid);
+      if (slow == 0u && __popc(todo) <= WARP_RESET_MAX * A) {
+        // 2. few finished envs (episodes drifted apart): the rest warp by warp, planes stored by the warps, ONE barrier
+        if (lane == 0) for (uint32_t m = got; m != 0u; m &= m - 1u) s_flag[__ffs(m) - 1] &= ~FL_RESET;
+        const bool failed = fast_resets<A>(p, mine_a & ~got, got, s_flag, s_bits, s_rec, s_env, s_scr + a * 36, env0, lane);
+        if (!__syncthreads_or(failed ? 1 : 0)) return;  // the usual case: done, the barrier publishes the new episodes to the view threads
+      } else {
+        // 3. many (episodes in lock step): what was not pre-generated is drawn into a table by all threads and replayed
+        if (lane == 0) for (uint32_t m = got; m != 0u; m &= m - 1u) { const int e = __ffs(m) - 1; s_flag[e] = (s_flag[e] & ~FL_RESET) | FL_IMAGE; }
+        __syncthreads();
+      }
+      tile_resets<A>(p, s_flag, s_bits, s_rec, s_env, s_scr, env0, n_valid, tid);  // leftovers of 2. / the rest of 3.; then the sequential code below
     }
     if (a == lane % A && mine) {
       uint32_t fl = s_flag[lane];
@@ -665,6 +653,12 @@ __global__ void __launch_bounds__(32 * A, ctas_per_sm<OBS, V, A, NST>()) fused2_
 
   // ---- warp 0: the step's agent order, base.py:514-516 -- one Philox block per env ----
   if (a == 0 && mine) {
+    // an env about to time out (base.py:649) will want its pre-generated world a microsecond from now: start it on its way to L2
+    if (p.pregen != nullptr && s_env[lane * 4] + 1 >= p.max_steps) {
+      const uint32_t* const slot = p.pregen + env * world::PG_WORDS;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(slot));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(slot + 32));
+    }
     const unsigned long long g = (unsigned long long)(p.env_offset + env);
     const U4 r = philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)s_env[lane * 4 + 2], 0u, (uint32_t)p.seed, (uint32_t)(p.seed >> 32));
     s_order[lane] = decode_order_ct<A>(__umulhi(r.x, Fact<A>::v));

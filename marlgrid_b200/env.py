@@ -24,6 +24,10 @@ from .config import (AF_ACTIVE, AF_DONE, AF_PLACED, ERR_BAD_ACTION, ERR_PLACEMEN
                      MgConfig, MgState, n_tiles)
 from .spaces import Box, Discrete, Tuple
 
+# raw accessors (no torch.cuda.Stream / device objects on the per-step path)
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None) or (lambda i: torch.cuda.current_stream(i).cuda_stream)
+_cuda_get_device = getattr(torch._C, "_cuda_getDevice", None) or torch.cuda.current_device
+
 
 def compose_rich_obs(pov, agents, width, height, observe_rewards=True, observe_position=True, observe_orientation=True):
     """The reference's observation_style='rich' dict (marlgrid/base.py:461-471), batched: from the observation tensor
@@ -49,7 +53,7 @@ class BatchedMultiGridEnv:
     metadata = {}
 
     def __init__(self, cfg, num_envs=1, device="cuda", seed=1337, env_offset=0, obs_mode="encoded", autoreset=True,
-                 check_errors=False, obs_buffers=2):
+                 check_errors=False, obs_buffers=2, pregen=True):
         if not isinstance(cfg, MgConfig):
             raise TypeError("cfg must be a marlgrid_b200.config.MgConfig")
         if obs_mode not in ("encoded", "rgb"):
@@ -75,6 +79,8 @@ class BatchedMultiGridEnv:
         self.envrec = torch.empty((B, 4), dtype=torch.int32, device=dev)
         # derived bit-planes (include/marlgrid_b200.h), tile-transposed: word w of env e at [e // 32, w, e % 32]
         self.cellbits = torch.zeros(((B + 31) // 32, 44, 32), dtype=torch.int32, device=dev)
+        # pre-generated next worlds, filled by the library's background generator (include/marlgrid_b200.h MgState.pregen)
+        self.pregen = torch.zeros((B, 64), dtype=torch.int32, device=dev) if pregen else None
         self.rewards = torch.zeros((B, A), dtype=torch.float64, device=dev)
         self.done = torch.zeros((B,), dtype=torch.bool, device=dev)  # the kernels write 0/1 bytes: no conversion pass per step
         # The observation tensor returned by step() is a view of a device buffer.  With obs_buffers = 2 (default) steps
@@ -94,6 +100,7 @@ class BatchedMultiGridEnv:
             self.atlas = torch.from_numpy(at).to(dev)
         self._state = MgState()
         self._fast = None
+        self._n_act = B * A
         self.seed(seed)
         self._sync_state_struct()
         with torch.cuda.device(dev):
@@ -104,6 +111,14 @@ class BatchedMultiGridEnv:
             _lib.check(self._lib.mg_reset(ctypes.byref(cfg), ctypes.byref(self._state), None, self._stream()), "mg_reset")
             self.envrec[:, 1] = 0
 
+    def __del__(self):
+        # a pass of the background world generator may still be reading / writing this env's tensors on the side stream
+        try:
+            if getattr(self, "pregen", None) is not None:
+                self._lib.mg_pregen_drain()
+        except Exception:  # noqa: BLE001 -- interpreter shutdown
+            pass
+
     # ---- plumbing ------------------------------------------------------------------------------
     def _stream(self):
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
@@ -112,11 +127,14 @@ class BatchedMultiGridEnv:
         st = self._state
         st.grid, st.agents, st.envrec = self.grid.data_ptr(), self.agent_rec.data_ptr(), self.envrec.data_ptr()
         st.cellbits = self.cellbits.data_ptr()
+        st.pregen = self.pregen.data_ptr() if self.pregen is not None else None
         st.n_envs, st.env_offset, st.seed = self.num_envs, self.env_offset, self._seed
 
     def seed(self, seed=1337):
         """marlgrid/base.py:371-374.  The Philox key; the global env index is the counter."""
         self._seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        if getattr(self, "pregen", None) is not None:
+            self._lib.mg_pregen_drain()  # no generator pass keyed with the old seed may still be writing world slots
         self._state.seed = self._seed
         return [seed]
 
@@ -206,21 +224,26 @@ class BatchedMultiGridEnv:
         self._fast = (fn, cfg, st, tails, self.device.index)
 
     def step(self, actions):
-        """One env.step for the whole batch (marlgrid/base.py:501-653) in a single kernel launch."""
-        a = self._actions(actions)
+        """One env.step for the whole batch (marlgrid/base.py:501-653) in a single kernel launch.
+
+        The host side of this call is trimmed to the bone (a Python loop around env.step() is host-bound long before the
+        kernel is): argument tuple resolved once, raw stream handle instead of a torch.cuda.Stream object."""
+        a = actions
+        if not (type(a) is torch.Tensor and a.dtype is torch.int32 and a.is_cuda and a.is_contiguous() and a.numel() == self._n_act
+                and a.device == self.device):
+            a = self._actions(actions)
         fast = self._fast
         if fast is None:
             self._prepare_fast_step()
             fast = self._fast
         fn, cfg, st, tails, dev_index = fast
-        self._obs_idx = (self._obs_idx + 1) % len(tails)
-        tail = tails[self._obs_idx]
-        self.obs = self._obs_bufs[self._obs_idx]
-        if torch.cuda.current_device() != dev_index:
+        idx = self._obs_idx = (self._obs_idx + 1) % len(tails)
+        self.obs = self._obs_bufs[idx]
+        if _cuda_get_device() != dev_index:
             with torch.cuda.device(self.device):
-                rc = fn(cfg, st, a.data_ptr(), *tail, self.autoreset, torch.cuda.current_stream(self.device).cuda_stream)
+                rc = fn(cfg, st, a.data_ptr(), *tails[idx], self.autoreset, _raw_stream(dev_index))
         else:
-            rc = fn(cfg, st, a.data_ptr(), *tail, self.autoreset, torch.cuda.current_stream().cuda_stream)
+            rc = fn(cfg, st, a.data_ptr(), *tails[idx], self.autoreset, _raw_stream(dev_index))
         if rc:
             _lib.check(rc, "mg_step_fused")
         if self.check_errors_each_step:

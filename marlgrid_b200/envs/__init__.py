@@ -43,6 +43,7 @@ class MultiGridEnv(BatchedMultiGridEnv):
         autoreset=True,
         check_errors=False,
         obs_buffers=2,
+        pregen=True,
     ):
         if grid_size is not None:
             assert width is None and height is None  # base.py:349-351
@@ -83,7 +84,7 @@ class MultiGridEnv(BatchedMultiGridEnv):
             **self._scenario(),
         )
         super().__init__(cfg, num_envs=num_envs, device=device, seed=seed, env_offset=env_offset, obs_mode=obs_mode,
-                         autoreset=autoreset, check_errors=check_errors, obs_buffers=obs_buffers)
+                         autoreset=autoreset, check_errors=check_errors, obs_buffers=obs_buffers, pregen=pregen)
 
     def _scenario(self):
         raise NotImplementedError

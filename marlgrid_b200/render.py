@@ -48,6 +48,7 @@ def _sub_state(env, index):
     st.grid = env.grid[index].data_ptr()
     st.agents = env.agent_rec[index].data_ptr()
     st.envrec = env.envrec[index].data_ptr()
+    st.pregen = None
     st.cellbits = None  # the bit-planes are tile-transposed (32 envs interleaved): a single env takes the byte-plane kernels
     st.n_envs, st.env_offset, st.seed = 1, env.env_offset + index, env._seed
     return st

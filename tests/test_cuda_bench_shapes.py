@@ -163,3 +163,45 @@ def test_engine_e2e_full_batch_vs_oracle(cuda_lib, oracle):
         o2, r2, d2 = ob.step(act, autoreset=True, with_obs=True)
         assert np.array_equal(obs, o2) and np.array_equal(rew.view(np.uint64), r2.view(np.uint64)) and np.array_equal(done, d2), f"step {t}"
     cuda_lib.mg_engine_destroy(h)
+
+
+def test_pregenerated_worlds_equal_in_kernel_generation(cuda_lib):
+    """The background world generator (MgState.pregen): a batch whose finished envs copy pre-generated worlds and a batch
+    that generates every world inside the step kernel produce identical outputs and state, step by step, in the desynchronised
+    regime (a few resets per tile and step) and across all-reset steps; most resets of the first batch are copies."""
+    import ctypes as C
+
+    from marlgrid_b200 import envs
+
+    B, T = 8192, 260
+    a = envs.make("MarlGrid-3AgentCluttered15x15-v0", num_envs=B, obs_mode="encoded", seed=5, max_steps=40)
+    b = envs.make("MarlGrid-3AgentCluttered15x15-v0", num_envs=B, obs_mode="encoded", seed=5, max_steps=40, pregen=False)
+    a.reset()
+    b.reset()
+    spread = torch.randint(0, 40, (B // 2,), device="cuda", dtype=torch.int32)
+    a.envrec[: B // 2, 0] = spread  # half of the batch desynchronised, the other half in lock step
+    b.envrec[: B // 2, 0] = spread
+    stats = (C.c_uint64 * 2)()
+    cuda_lib.mg_pregen_stats(stats, 1)
+    for t in range(T):
+        act = a.random_actions(t)
+        o1, r1, d1, _ = a.step(act)
+        o2, r2, d2, _ = b.step(act)
+        assert torch.equal(o1, o2) and torch.equal(r1, r2) and torch.equal(d1, d2), f"step {t}"
+        if t % 20 == 0 or t == T - 1:
+            assert torch.equal(a.grid, b.grid) and torch.equal(a.agent_rec[:, :, :12], b.agent_rec[:, :, :12]) and torch.equal(a.envrec, b.envrec)
+            assert torch.equal(a.cellbits, b.cellbits)
+    cuda_lib.mg_pregen_stats(stats, 0)
+    hits, misses = int(stats[0]), int(stats[1])
+    assert hits + misses >= B * (T // 40 - 1)
+    assert hits > 0.5 * (hits + misses), (hits, misses)
+    a.seed(6)  # a new seed invalidates every slot: the same world as a batch that never had any
+    b.seed(6)
+    a._sync_state_struct(); b._sync_state_struct()
+    a._fast = b._fast = None
+    for t in range(45):
+        act = a.random_actions(t)
+        o1, r1, d1, _ = a.step(act)
+        o2, r2, d2, _ = b.step(act)
+        assert torch.equal(o1, o2) and torch.equal(r1, r2) and torch.equal(d1, d2), f"after reseeding, step {t}"
+    assert torch.equal(a.grid, b.grid) and torch.equal(a.envrec, b.envrec)
