@@ -115,7 +115,20 @@ typedef struct MgConfig {
   uint32_t hide_types;       /* GridAgentInterface.hide_item_types (agents.py:30, base.py:441-449) as a bit set over the type
                                 indices (bit MG_T_AGENT = 'Agent'): objects of these types are masked out of every agent's
                                 observation (after the line of sight has been computed with them in place) */
+  int32_t spawn_top[2];      /* agent_spawn_kwargs (base.py:346,409-412,505,642): place_obj(agent, top=..., size=..., max_tries=...) */
+  int32_t spawn_size[2];     /*   (base.py:690-696); size {0, 0} = None = the whole grid.  Agents are then sampled in the box  */
+  int32_t spawn_max_tries;   /*   [max(top,0), min(top+size, grid)); 0 = the default 1e5 (`reject_fn`, a Python callable, is not supported) */
+  int32_t scenario;          /* MG_SCENARIO_*: which _gen_grid builds the world */
+  uint32_t prestige_mask;    /* bit a: agent a is coloured 'prestige' (agents.py:99): its tile is recoloured from its running reward */
+  uint32_t prestige_neg_mask;/* bit a: allow_negative_prestige (agents.py:103-106,146-153) */
+  double prestige_beta[MG_MAX_AGENTS];   /* agents.py:49,144 */
+  double prestige_scale[MG_MAX_AGENTS];  /* agents.py:50,104-106 */
 } MgConfig;
+
+/* scenario generators */
+enum { MG_SCENARIO_STANDARD = 0 /* empty.py / cluttered.py / goalcycle.py, selected by goal_mode, n_clutter, n_bonus_tiles */,
+       MG_SCENARIO_DOORKEY = 1  /* doorkey.py:15-41 with `_rand_int` = np_random.randint (the reference's class cannot be built: the
+                                   method is missing there) */ };
 
 /* Device pointers of the SoA world state (caller-owned, e.g. torch tensors). */
 typedef struct MgState {

@@ -42,6 +42,14 @@ class MgConfig(ctypes.Structure):
         ("n_static_kinds", ctypes.c_uint8),
         ("kind_of_type", ctypes.c_uint8 * 15),
         ("hide_types", ctypes.c_uint32),
+        ("spawn_top", ctypes.c_int32 * 2),
+        ("spawn_size", ctypes.c_int32 * 2),
+        ("spawn_max_tries", ctypes.c_int32),
+        ("scenario", ctypes.c_int32),
+        ("prestige_mask", ctypes.c_uint32),
+        ("prestige_neg_mask", ctypes.c_uint32),
+        ("prestige_beta", ctypes.c_double * MG_MAX_AGENTS),
+        ("prestige_scale", ctypes.c_double * MG_MAX_AGENTS),
     ]
 
     def describe(self):
@@ -88,6 +96,13 @@ def make_config(
     bonus_reset_on_mistake=False,
     spawn_delay=None,
     hide_types=0,
+    spawn_top=(0, 0),
+    spawn_size=None,
+    spawn_max_tries=None,
+    scenario=0,
+    prestige_beta=None,
+    prestige_scale=None,
+    allow_negative_prestige=None,
 ):
     n_agents = len(agent_colors)
     if not (1 <= n_agents <= MG_MAX_AGENTS):
@@ -130,6 +145,25 @@ def make_config(
     cfg.kind_of_type[T_BONUS] = 3
     cfg.n_static_kinds = 3
     cfg.hide_types = int(hide_types)
+    # agent_spawn_kwargs (base.py:409-412 -> place_obj(top, size, max_tries), :690-696)
+    top = (max(int(spawn_top[0]), 0), max(int(spawn_top[1]), 0))
+    size = (int(width), int(height)) if spawn_size is None else (int(spawn_size[0]), int(spawn_size[1]))
+    bottom = (min(top[0] + size[0], int(width)), min(top[1] + size[1], int(height)))
+    if bottom[0] <= top[0] or bottom[1] <= top[1]:
+        raise ValueError("agent_spawn_kwargs: empty spawn region (np_random.randint(top, bottom) with low >= high)")
+    cfg.spawn_top[0], cfg.spawn_top[1] = top
+    cfg.spawn_size[0], cfg.spawn_size[1] = (0, 0) if spawn_size is None else size
+    cfg.spawn_max_tries = 0 if spawn_max_tries is None else int(max(1, min(int(spawn_max_tries), 100000)))
+    cfg.scenario = int(scenario)
+    pmask = nmask = 0
+    for i, c in enumerate(agent_colors):
+        if (c if not isinstance(c, int) else None) == "prestige" or c == COLOR_TO_IDX["prestige"]:
+            pmask |= 1 << i
+        cfg.prestige_beta[i] = 0.95 if prestige_beta is None else float(prestige_beta[i])
+        cfg.prestige_scale[i] = 2.0 if prestige_scale is None else float(prestige_scale[i])
+        if allow_negative_prestige is not None and allow_negative_prestige[i]:
+            nmask |= 1 << i
+    cfg.prestige_mask, cfg.prestige_neg_mask = pmask, nmask
     return cfg
 
 

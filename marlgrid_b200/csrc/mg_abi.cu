@@ -29,6 +29,13 @@ static int check_cfg(const MgConfig* c) {
   // arrival stamps are 16 bits wide and compared raw: an episode issues at most A placement stamps + A per step (twice
   // that with respawn, base.py:629-644), which must not wrap
   if ((long long)(2 * c->max_steps + 1) * c->n_agents >= 65536) return MG_E_CONFIG;
+  {  // agent_spawn_kwargs: the sampled box must not be empty (numpy raises on randint(low >= high))
+    const int tx = std::max(c->spawn_top[0], 0), ty = std::max(c->spawn_top[1], 0);
+    const bool whole = c->spawn_size[0] == 0 && c->spawn_size[1] == 0;
+    if (std::min(tx + (whole ? c->width : c->spawn_size[0]), c->width) <= tx || std::min(ty + (whole ? c->height : c->spawn_size[1]), c->height) <= ty) return MG_E_CONFIG;
+    if (c->spawn_max_tries < 0 || c->scenario < 0 || c->scenario > MG_SCENARIO_DOORKEY) return MG_E_CONFIG;
+    if (c->scenario == MG_SCENARIO_DOORKEY && (c->width < 5 || c->height < 5)) return MG_E_CONFIG;
+  }
   // grids wider / taller than 16 cells take the byte-plane kernels, which stage 32 envs' planes in shared memory
   if (c->width > 16 || c->height > 16) {
     const long long sm = 32ll * 3 * c->plane_stride + 32ll * c->n_agents * 16 + 16 + 32ll * c->n_agents * c->view_size * c->view_size * 3;
@@ -63,6 +70,12 @@ static KP make_kp(const MgConfig* c, const MgState* st) {
   p.n_tiles = (c->n_static_kinds + 1) * (1 + 4 * c->n_agents);
   p.orient_slots = 4;
   p.wall_enc = (uint32_t)MG_T_WALL | ((uint32_t)MG_C_WORST << 8);
+  p.ax0 = std::max(c->spawn_top[0], 0); p.ay0 = std::max(c->spawn_top[1], 0);
+  const bool whole = c->spawn_size[0] == 0 && c->spawn_size[1] == 0;  // size=None
+  p.aw = std::min(p.ax0 + (whole ? c->width : c->spawn_size[0]), c->width) - p.ax0;
+  p.ah = std::min(p.ay0 + (whole ? c->height : c->spawn_size[1]), c->height) - p.ay0;
+  p.amax = c->spawn_max_tries > 0 ? std::min(c->spawn_max_tries, 100000) : 100000;
+  p.scenario = c->scenario;
   p.pregen = p.cellbits ? st->pregen : nullptr;
   p.stats = p.pregen ? device_stats() : nullptr;
   return p;

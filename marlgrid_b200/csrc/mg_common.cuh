@@ -62,6 +62,8 @@ struct KP {
   uint32_t hide;     // MgConfig.hide_types
   uint32_t wall_enc; // MG_T_WALL | MG_C_WORST << 8: the encoded canonical wall, as run-time data (see mg_fused2.cu)
   uint32_t* pregen;  // MgState.pregen: pre-generated next worlds [B][64] (mg_world.cuh) or nullptr
+  int ax0, ay0, aw, ah, amax;  // agent spawn box [ax0, ax0 + aw) x [ay0, ay0 + ah) and max_tries (agent_spawn_kwargs, base.py:690-696)
+  int scenario;                // MG_SCENARIO_*
   unsigned long long* stats;  // per-device counters: [0] envs regenerated from a pre-generated world, [1] envs generated inside the step kernel
 };
 

@@ -49,6 +49,17 @@ struct Draws {
     }
     ++k;
   }
+  // np_random.randint(top, bottom) on a box (place_obj(top, size), base.py:690-699): the same try, mapped to [x0, x0 + w) x [y0, y0 + h)
+  __device__ __forceinline__ void next_box(int x0, int y0, int w, int h, int& x, int& y) {
+    next(w, h, x, y);
+    x += x0; y += y0;
+  }
+  // a scalar np_random.randint(lo, hi) (doorkey.py:26,34 `_rand_int`): one try slot, first word
+  __device__ __forceinline__ int next_int(int lo, int hi) {
+    int x, y;
+    next(hi - lo, 1, x, y);
+    return lo + x;
+  }
 };
 
 // ---------------------------------------------------------------------------------------------

@@ -83,9 +83,9 @@ __device__ __forceinline__ bool try_place_agent(EnvCtx<RS>& c, int x, int y, int
 // base.py:690-708 place_obj(top=(0,0), size=None) for an agent in the live world
 template <int RS>
 __device__ __forceinline__ void place_agent(EnvCtx<RS>& c, Draws& d, int agent) {
-  for (int t = 0; t < 100000; ++t) {
+  for (int t = 0; t < c.p.amax; ++t) {  // place_obj(agent, **agent_spawn_kwargs), base.py:505,642
     int x, y;
-    d.next(c.p.W, c.p.H, x, y);
+    d.next_box(c.p.ax0, c.p.ay0, c.p.aw, c.p.ah, x, y);
     if (try_place_agent(c, x, y, agent)) return;
   }
   c.add_err(MG_ERR_PLACEMENT);  // RecursionError base.py:706
@@ -99,6 +99,60 @@ __device__ __forceinline__ Draws make_draws(const KP& p, unsigned long long g, u
   return d;
 }
 
+// base.py:402-416 reset + DoorKeyEnv._gen_grid (doorkey.py:15-41, with `_rand_int(lo, hi)` = np_random.randint(lo, hi): the
+// reference's class calls a method it does not have): border walls, goal at (W-2, H-2), a vertical wall at a random column
+// with a locked yellow door at a random row, a yellow key somewhere left of the wall, agents anywhere (the generator resets
+// agent_spawn_kwargs to {}, doorkey.py:40).  Sequential, on the byte planes; the bit-plane lines are rebuilt from them.
+template <int RS>
+__device__ void env_reset_doorkey(EnvCtx<RS>& c, unsigned long long g) {
+  const KP& p = c.p;
+  const int W = p.W, H = p.H, S = p.S, A = p.A;
+  for (int a = 0; a < A; ++a) {  // agents.py:161-170 (dir survives)
+    c.R(a, 0) = c.R(a, 0) & 0x00FF0000u;
+    c.R(a, 1) = 0xFF000000u;
+    c.R(a, 2) = 0;
+  }
+  int4* z = reinterpret_cast<int4*>(c.tp);
+  for (int i = 0; i < 3 * S / 16; ++i) z[i] = make_int4(0, 0, 0, 0);
+  c.w3 &= 0xFFFF0000u;
+  auto put = [&](int x, int y, int type, int colour, int state) {
+    const int idx = x * H + y;
+    c.tp[idx] = (uint8_t)type; c.tp[S + idx] = (uint8_t)colour; c.tp[2 * S + idx] = (uint8_t)state;
+  };
+  for (int i = 0; i < W; ++i) { put(i, 0, MG_T_WALL, MG_C_WORST, 0); put(i, H - 1, MG_T_WALL, MG_C_WORST, 0); }  // wall_rect base.py:172-176
+  for (int j = 0; j < H; ++j) { put(0, j, MG_T_WALL, MG_C_WORST, 0); put(W - 1, j, MG_T_WALL, MG_C_WORST, 0); }
+  put(W - 2, H - 2, MG_T_GOAL, MG_C_GREEN, 0);                         // doorkey.py:23
+  Draws d = make_draws(p, g, (uint32_t)c.ep, TAG_RESET);
+  const int split = d.next_int(2, W - 2);                              // doorkey.py:26
+  for (int j = 0; j < H; ++j) put(split, j, MG_T_WALL, MG_C_WORST, 0); // vert_wall(splitIdx, 0) base.py:166-170
+  const int door = d.next_int(1, W - 2);                               // doorkey.py:34 (sic: width)
+  if (door < H) put(split, door, MG_T_DOOR, MG_C_YELLOW, MG_DOOR_LOCKED); else c.add_err(MG_ERR_STACK);  // grid.set asserts j < height
+  {  // place_obj(Key('yellow'), top=(0, 0), size=(splitIdx, height)), doorkey.py:37: an empty cell (no agent is placed yet)
+    int t = 0;
+    for (; t < 100000; ++t) {
+      int x, y;
+      d.next_box(0, 0, split, H, x, y);
+      if (c.tp[x * H + y] == MG_T_EMPTY) { put(x, y, MG_T_KEY, MG_C_YELLOW, 0); break; }
+    }
+    if (t == 100000) c.add_err(MG_ERR_PLACEMENT);
+  }
+  bits_rebuild(c.tp, c.bits, W, H, S);
+  for (int a = 0; a < A; ++a)  // base.py:409-412 with agent_spawn_kwargs = {}
+    if (p.spawn_delay[a] == 0) {
+      bool placed = false;
+      for (int t = 0; t < 100000 && !placed; ++t) {
+        int x, y;
+        d.next(W, H, x, y);
+        placed = try_place_agent(c, x, y, a);
+      }
+      if (!placed) c.add_err(MG_ERR_PLACEMENT);
+      c.R(a, 0) |= (uint32_t)MG_AF_ACTIVE << 24;
+    }
+  c.sc = 0;
+  c.ep += 1;
+  c.dirty = true;
+}
+
 // base.py:402-416 reset + _gen_grid (empty.py:9-16, cluttered.py:25-36, goalcycle.py:30-51), written straight to
 // the global planes.  A fresh world only ever holds canonical walls, a Goal and BonusTiles, so with BITS the
 // rejection sampling (base.py:690-708) runs on row/column mask sets kept in shared memory (walls / overlappable
@@ -110,6 +164,7 @@ __device__ __forceinline__ Draws make_draws(const KP& p, unsigned long long g, u
 template <int RS, bool BITS, bool PLANES = true>
 __device__ void env_reset(EnvCtx<RS>& c, unsigned long long g) {
   const KP& p = c.p;
+  if (p.scenario == MG_SCENARIO_DOORKEY) { env_reset_doorkey(c, g); return; }
   const int W = p.W, H = p.H, S = p.S, A = p.A;
   for (int a = 0; a < A; ++a) {  // agents.py:161-170 (dir survives)
     c.R(a, 0) = c.R(a, 0) & 0x00FF0000u;
@@ -173,7 +228,8 @@ __device__ void env_reset(EnvCtx<RS>& c, unsigned long long g) {
     const int agent = obj - first_agent;
     if (agent >= 0 && ((delayed >> agent) & 1u)) { ++obj; continue; }
     int x, y;
-    d.next(W, H, x, y);
+    if (agent >= 0) d.next_box(p.ax0, p.ay0, p.aw, p.ah, x, y);  // place_obj(agent, **agent_spawn_kwargs), base.py:409-412
+    else d.next(W, H, x, y);
     int st;  // 0 empty, WALL, or GOAL standing for "overlappable other"
     if (BITS) st = ((wall[x * RS] >> y) & 1u) ? (int)MG_T_WALL : (((other[x * RS] >> y) & 1u) ? (int)MG_T_GOAL : (int)MG_T_EMPTY);
     else st = c.tp[x * H + y];
@@ -189,7 +245,7 @@ __device__ void env_reset(EnvCtx<RS>& c, unsigned long long g) {
       else if (obj < n_goal + n_bonus) put_static(x, y, MG_T_BONUS, MG_C_YELLOW, obj - n_goal);
       else put_static(x, y, MG_T_WALL, MG_C_WORST, 0);
       ++obj; tries = 0;
-    } else if (++tries >= (agent >= 0 ? 100000 : 100)) {
+    } else if (++tries >= (agent >= 0 ? p.amax : 100)) {
       c.add_err(MG_ERR_PLACEMENT);  // RecursionError base.py:706
       if (agent >= 0) c.R(agent, 0) |= (uint32_t)MG_AF_ACTIVE << 24;  // the reference would have raised before activate()
       ++obj; tries = 0;

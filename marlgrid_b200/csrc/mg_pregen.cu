@@ -133,6 +133,7 @@ static unsigned int* pregen_counter() {  // one work-list counter per device
 // one pass over the family on `s` (passes of one device must be issued to ONE stream: they share the work-list counter)
 int launch_pregen(const KP& p, cudaStream_t s) {
   if (p.pregen == nullptr || p.cellbits == nullptr || p.B <= 0) return 0;
+  if (p.scenario != 0 || p.ax0 != 0 || p.ay0 != 0 || p.aw != p.W || p.ah != p.H || p.amax != 100000) return 0;  // only the specialised step kernel consumes slots
   if ((p.goal_mode != MG_GOAL_NONE ? 1 : 0) + p.n_bonus > OBJ_SLOTS) return 0;  // worlds whose objects do not fit the list: the step kernel's sequential route
   if (p.B > 0x7FFFFFFFll) return MG_E_ARG;
   unsigned int* const counter = pregen_counter();

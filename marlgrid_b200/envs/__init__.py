@@ -48,8 +48,16 @@ class MultiGridEnv(BatchedMultiGridEnv):
         if grid_size is not None:
             assert width is None and height is None  # base.py:349-351
             width, height = grid_size, grid_size
-        if agent_spawn_kwargs:
-            raise NotImplementedError("agent_spawn_kwargs (restricted spawn regions) are not on the batched hot path")
+        # agent_spawn_kwargs (base.py:346): forwarded to place_obj for every agent placement -- at reset (base.py:409-412), after
+        # a spawn delay (:505) and at respawn (:642).  `top` / `size` / `max_tries` (base.py:690-696) run inside the kernels;
+        # `reject_fn` is a Python callable and cannot.
+        spawn = dict(agent_spawn_kwargs or {})
+        if "reject_fn" in spawn and spawn["reject_fn"] is not None:
+            raise NotImplementedError("agent_spawn_kwargs['reject_fn'] (a Python callable per placement try) cannot run inside the reset kernel")
+        spawn.pop("reject_fn", None)
+        if set(spawn) - {"top", "size", "max_tries"}:
+            raise TypeError(f"place_obj() got an unexpected keyword argument {sorted(set(spawn) - {'top', 'size', 'max_tries'})[0]!r}")  # base.py:690
+        self.agent_spawn_kwargs = spawn
         self.agent_interfaces = []
         for a in agents:  # add_agent base.py:392-400
             if isinstance(a, dict):
@@ -81,7 +89,10 @@ class MultiGridEnv(BatchedMultiGridEnv):
             max_steps=max_steps, ghost_mode=ghost_mode, respawn=respawn, reward_decay=reward_decay,
             see_through_walls=ai[0].see_through_walls, spawn_delay=[a.spawn_delay for a in ai],
             hide_types=hide_mask(ai[0].hide_item_types),
-            **self._scenario(),
+            prestige_beta=[a.prestige_beta for a in ai], prestige_scale=[a.prestige_scale for a in ai],
+            allow_negative_prestige=[a.allow_negative_prestige for a in ai],
+            **{"spawn_top": tuple(spawn.get("top", (0, 0))), "spawn_size": spawn.get("size"), "spawn_max_tries": spawn.get("max_tries"),
+               **self._scenario()},
         )
         super().__init__(cfg, num_envs=num_envs, device=device, seed=seed, env_offset=env_offset, obs_mode=obs_mode,
                          autoreset=autoreset, check_errors=check_errors, obs_buffers=obs_buffers, pregen=pregen)
@@ -132,6 +143,23 @@ class ClutteredMultiGrid(MultiGridEnv):
             n_clutter = int(density * (self.width - 2) * (self.height - 2))  # cluttered.py:15-16
         self.n_clutter = n_clutter
         return dict(goal_mode=GOAL_RANDOM if self.randomize_goal else GOAL_FIXED, n_clutter=n_clutter)
+
+
+class DoorKeyEnv(MultiGridEnv):
+    """marlgrid/envs/doorkey.py: a vertical wall at a random column with a locked yellow door, the yellow key somewhere on the
+    left, the goal in the bottom-right corner.  The reference's class calls `self._rand_int`, which its base class lacks, and its
+    constructor renders a Key tile, whose render() raises: it cannot be instantiated there.  Here `_rand_int(lo, hi)` is
+    `np_random.randint(lo, hi)` (gym-minigrid's definition) and observations are the encoded ones (Key / Door have no working
+    RGB tile in the reference, objects.py:309,370: obs_mode='rgb' sets MG_ERR_RENDER like any such object)."""
+    mission = "use the key to open the door and then get to the goal"
+
+    def __init__(self, *args, **kwargs):
+        kwargs.setdefault("obs_mode", "encoded")
+        super().__init__(*args, **kwargs)
+        self.agent_spawn_kwargs = {}  # doorkey.py:40
+
+    def _scenario(self):
+        return dict(goal_mode=GOAL_FIXED, scenario=1, spawn_top=(0, 0), spawn_size=None, spawn_max_tries=None)
 
 
 class ClutteredGoalCycleEnv(MultiGridEnv):

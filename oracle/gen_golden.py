@@ -105,6 +105,9 @@ def cfg_kwargs(cfg, seed, env_index):
             bonus_penalty=cfg.bonus_penalty, bonus_initial_reward=bool(cfg.flags & F_BONUS_INITIAL),
             bonus_reset_on_mistake=bool(cfg.flags & F_BONUS_RESET), spawn_delay=[int(s) for s in cfg.spawn_delay[: cfg.n_agents]],
             hide_types=int(cfg.hide_types),
+            spawn_top=[int(cfg.spawn_top[0]), int(cfg.spawn_top[1])],
+            spawn_size=None if (cfg.spawn_size[0] == 0 and cfg.spawn_size[1] == 0) else [int(cfg.spawn_size[0]), int(cfg.spawn_size[1])],
+            spawn_max_tries=int(cfg.spawn_max_tries) or None, scenario=int(cfg.scenario),
         ),
     )
 
@@ -146,6 +149,22 @@ def gen_hide_trajectories():
         seed, env_index = 7001 + 13 * k, 500 * k + 9
         rec = Recorder(name, seed=seed, env_index=env_index, rgb=True, **sc)
         rec.run(episodes=3, steps=rec.cfg.max_steps + 3, rng=rng, p_forward=0.5)
+        fname = "traj_" + "".join(ch if ch.isalnum() else "_" for ch in name).strip("_") + ".npz"
+        n = rec.save(fname, cfg_kwargs(rec.cfg, seed, env_index))
+        print(f"  {fname:48s} {n} events; {rec.events}")
+
+
+def gen_extra_trajectories():
+    """agent_spawn_kwargs and DoorKey scenarios (validate_against_reference.EXTRA), recorded with their own RNG stream."""
+    rng = np.random.RandomState(90210)
+    for k, sc in enumerate(val.EXTRA):
+        sc = dict(sc)
+        name = sc.pop("name")
+        interactive = sc.pop("interactive", False)
+        sc.pop("no_inject", None)
+        seed, env_index = 9001 + 11 * k, 321 * k + 5
+        rec = Recorder(name, seed=seed, env_index=env_index, rgb=not interactive, **sc)
+        rec.run(episodes=4, steps=rec.cfg.max_steps + 3, rng=rng, p_forward=0.4)
         fname = "traj_" + "".join(ch if ch.isalnum() else "_" for ch in name).strip("_") + ".npz"
         n = rec.save(fname, cfg_kwargs(rec.cfg, seed, env_index))
         print(f"  {fname:48s} {n} events; {rec.events}")
@@ -236,9 +255,12 @@ if __name__ == "__main__":
         gen_render()
     elif "hide" in sys.argv[1:]:
         gen_hide_trajectories()
+    elif "extra" in sys.argv[1:]:
+        gen_extra_trajectories()
     else:
         gen_los()
         gen_atlas()
         gen_trajectories()
         gen_hide_trajectories()
+        gen_extra_trajectories()
         gen_render()

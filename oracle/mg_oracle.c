@@ -175,17 +175,53 @@ static int try_place(Env* v, int x, int y, int agent, int type, int colour, int 
   return 1;
 }
 
-/* base.py:690-708 place_obj with top=(0,0), size=None */
-static void place_obj(Env* v, Draws* d, int agent, int type, int colour, int state, int max_tries) {
-  const MgConfig* c = v->c;
+/* base.py:690-708 place_obj(obj, top, size, max_tries): pos = np_random.randint(top, bottom) in the box
+ * top = max(top, 0), bottom = min(top + size, grid); size NULL = the whole grid */
+static void place_obj_box(Env* v, Draws* d, int agent, int type, int colour, int state, int max_tries, int tx, int ty, int bx, int by) {
   if (max_tries > 100000) max_tries = 100000;
   if (max_tries < 1) max_tries = 1;
   for (int t = 0; t < max_tries; ++t) {
     int x, y;
-    draw_pos(d, c->width, c->height, &x, &y);
-    if (try_place(v, x, y, agent, type, colour, state)) return;
+    draw_pos(d, bx - tx, by - ty, &x, &y);
+    if (try_place(v, x + tx, y + ty, agent, type, colour, state)) return;
   }
   add_err(v, MG_ERR_PLACEMENT); /* RecursionError base.py:706 */
+}
+static void place_obj(Env* v, Draws* d, int agent, int type, int colour, int state, int max_tries) {
+  place_obj_box(v, d, agent, type, colour, state, max_tries, 0, 0, v->c->width, v->c->height);
+}
+/* place_obj(agent, **self.agent_spawn_kwargs): base.py:409-412 (reset), :505 (spawn delay), :642 (respawn) */
+static void place_agent(Env* v, Draws* d, int agent) {
+  const MgConfig* c = v->c;
+  int tx = c->spawn_top[0] > 0 ? c->spawn_top[0] : 0, ty = c->spawn_top[1] > 0 ? c->spawn_top[1] : 0;
+  int whole = c->spawn_size[0] == 0 && c->spawn_size[1] == 0;
+  int bx = tx + (whole ? c->width : c->spawn_size[0]), by = ty + (whole ? c->height : c->spawn_size[1]);
+  if (bx > c->width) bx = c->width;
+  if (by > c->height) by = c->height;
+  place_obj_box(v, d, agent, 0, 0, 0, c->spawn_max_tries > 0 ? c->spawn_max_tries : 100000, tx, ty, bx, by);
+}
+/* a scalar np_random.randint(lo, hi): one try slot of the stream, its first word */
+static int draw_int(Draws* d, int lo, int hi) {
+  int x, y;
+  draw_pos(d, hi - lo, 1, &x, &y);
+  return lo + x;
+}
+
+/* DoorKeyEnv._gen_grid, doorkey.py:15-41 (with `_rand_int(lo, hi)` = np_random.randint(lo, hi)) */
+static void gen_doorkey(Env* v, Draws* d) {
+  const MgConfig* c = v->c;
+  int W = c->width, H = c->height;
+  int idx = (W - 2) * H + (H - 2);
+  v->type[idx] = MG_T_GOAL; v->colour[idx] = MG_C_GREEN; v->state[idx] = 0;             /* doorkey.py:23 */
+  int split = draw_int(d, 2, W - 2);                                                      /* doorkey.py:26 */
+  for (int j = 0; j < H; ++j) {                                                           /* vert_wall base.py:166-170 */
+    v->type[split * H + j] = MG_T_WALL; v->colour[split * H + j] = MG_C_WORST; v->state[split * H + j] = 0;
+  }
+  int door = draw_int(d, 1, W - 2);                                                       /* doorkey.py:34 */
+  if (door < H) {
+    v->type[split * H + door] = MG_T_DOOR; v->colour[split * H + door] = MG_C_YELLOW; v->state[split * H + door] = MG_DOOR_LOCKED;
+  } else add_err(v, MG_ERR_STACK);                                                        /* grid.set asserts j < height */
+  place_obj_box(v, d, -1, MG_T_KEY, MG_C_YELLOW, 0, 100000, 0, 0, split < W ? split : W, H); /* doorkey.py:37 */
 }
 
 /* base.py:402-416 reset + empty.py:9-16 / cluttered.py:25-36 / goalcycle.py:30-51 _gen_grid */
@@ -203,6 +239,17 @@ static void env_reset(Env* v, uint64_t seed, uint64_t g) {
       v->type[i * H + j] = MG_T_WALL; v->colour[i * H + j] = MG_C_WORST; v->state[i * H + j] = 0;
     }
   Draws d = {seed, g, (uint32_t)v->er[1], TAG_RESET, 0};
+  if (c->scenario == MG_SCENARIO_DOORKEY) {
+    gen_doorkey(v, &d);
+    for (int a = 0; a < A; ++a) /* base.py:409-412; the generator has reset agent_spawn_kwargs to {} (doorkey.py:40) */
+      if (c->spawn_delay[a] == 0) {
+        place_obj(v, &d, a, 0, 0, 0, 100000);
+        AFL(v, a) |= MG_AF_ACTIVE;
+      }
+    v->er[0] = 0;
+    v->er[1] += 1;
+    return;
+  }
   if (c->goal_mode == MG_GOAL_FIXED) { /* put_obj base.py:655-662 replaces whatever is there */
     int idx = (W - 2) * H + (H - 2);
     v->type[idx] = MG_T_GOAL; v->colour[idx] = MG_C_GREEN; v->state[idx] = 0;
@@ -213,7 +260,7 @@ static void env_reset(Env* v, uint64_t seed, uint64_t g) {
   for (int k = 0; k < c->n_clutter; ++k) place_obj(v, &d, -1, MG_T_WALL, MG_C_WORST, 0, 100);        /* cluttered.py:32-33 */
   for (int a = 0; a < A; ++a) /* base.py:409-412 */
     if (c->spawn_delay[a] == 0) {
-      place_obj(v, &d, a, 0, 0, 0, 100000);
+      place_agent(v, &d, a);
       AFL(v, a) |= MG_AF_ACTIVE;
     }
   v->er[0] = 0; /* step_count base.py:414 */
@@ -244,7 +291,7 @@ static int env_step(Env* v, const int32_t* actions, double* rewards, uint64_t se
   Draws d = {seed, g, t_life, TAG_INSTEP, 0};
   for (int a = 0; a < A; ++a) /* base.py:503-506 */
     if (!(AFL(v, a) & MG_AF_ACTIVE) && !(AFL(v, a) & MG_AF_DONE) && v->er[0] >= c->spawn_delay[a]) {
-      place_obj(v, &d, a, 0, 0, 0, 100000);
+      place_agent(v, &d, a);
       AFL(v, a) |= MG_AF_ACTIVE;
     }
   for (int a = 0; a < A; ++a) rewards[a] = 0.0; /* base.py:510 */
@@ -313,7 +360,7 @@ static int env_step(Env* v, const int32_t* actions, double* rewards, uint64_t se
     if (AFL(v, a) & MG_AF_DONE) {
       if (c->flags & MG_F_RESPAWN) {
         AFL(v, a) = 0; ACT(v, a) = 0; ACC(v, a) = 0; ACS(v, a) = 0; /* agent.reset(new_episode=False) agents.py:161-166 */
-        place_obj(v, &d, a, 0, 0, 0, 100000);
+        place_agent(v, &d, a);
         AFL(v, a) |= MG_AF_ACTIVE;
       } else AFL(v, a) &= (uint8_t)~MG_AF_ACTIVE;
     }

@@ -117,7 +117,11 @@ class PhiloxNpRandom:
     def randint(self, low, high=None, size=None):
         lo = np.asarray(low)
         hi = np.asarray(high)
-        assert lo.shape == (2,) and tuple(lo) == (0, 0), "contract covers full-grid placement only"
-        x, y = placement_try(self.seed, self.g, self.c2, self.tag, self.k, int(hi[0]), int(hi[1]))
+        if lo.shape == ():  # scalar draw (doorkey.py `_rand_int`): one try slot, its first word
+            x, _ = placement_try(self.seed, self.g, self.c2, self.tag, self.k, int(hi) - int(lo), 1)
+            self.k += 1
+            return int(lo) + x
+        assert lo.shape == (2,)  # place_obj(top, size): pos = randint(top, bottom), base.py:690-699
+        x, y = placement_try(self.seed, self.g, self.c2, self.tag, self.k, int(hi[0]) - int(lo[0]), int(hi[1]) - int(lo[1]))
         self.k += 1
-        return np.array([x, y])
+        return np.array([int(lo[0]) + x, int(lo[1]) + y])

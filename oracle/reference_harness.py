@@ -99,6 +99,14 @@ def make_env(env_id=None, env_class=None, seed=1337, env_index=0, agents=None, *
         env = gym.make(env_id)
     else:
         cls = getattr(ref.envs, env_class)
+        if env_class == "DoorKeyEnv" and not hasattr(cls, "_rand_int"):
+            # doorkey.py:26,34 calls self._rand_int, a gym-minigrid MiniGridEnv method that MultiGridEnv does not have: supplied
+            # here (`np_random.randint(low, high)`, gym-minigrid's definition) so that the otherwise unmodified class can be built
+            cls._rand_int = lambda self, low, high: self.np_random.randint(low, high)
+            # ... and its constructor ends with reset() -> gen_obs() -> MultiGrid.render, which raises NameError for the Key tile
+            # (objects.py:309 names an undefined point_in_circle): on this subclass the observation is the encoded variant
+            # (gen_obs_grid + MultiGrid.encode, base.py:418-451,196-214), the only one the reference can produce for this world
+            cls.gen_agent_obs = lambda self, agent: (lambda g, v: g.encode(v))(*self.gen_obs_grid(agent))
         ag = [ref.agents.GridAgentInterface(**kw) for kw in agents]
         env = cls(agents=ag, **env_kwargs)
     for a in env.agents:

@@ -34,7 +34,12 @@ def config_from_ref_env(env):
         spawn_delay=[a.spawn_delay for a in ag],
         hide_types=hide_mask(getattr(ag[0], "hide_item_types", [])),
     )
-    if "ClutteredGoalCycleEnv" in names:
+    sk = dict(getattr(env, "agent_spawn_kwargs", {}) or {})  # place_obj(agent, **agent_spawn_kwargs), base.py:409-412
+    assert set(sk) <= {"top", "size", "max_tries"}, sk
+    kw.update(spawn_top=tuple(sk.get("top", (0, 0))), spawn_size=sk.get("size"), spawn_max_tries=sk.get("max_tries"))
+    if "DoorKeyEnv" in names:
+        kw.update(goal_mode=GOAL_FIXED, scenario=1)
+    elif "ClutteredGoalCycleEnv" in names:
         kw.update(goal_mode=GOAL_NONE, n_clutter=env.n_clutter, n_bonus_tiles=env.n_bonus_tiles,
                   bonus_reward=env.reward, bonus_penalty=env.penalty,
                   bonus_initial_reward=env.initial_reward, bonus_reset_on_mistake=env.reset_on_mistake)
@@ -196,6 +201,19 @@ def agents_cfg(n, colors=("red", "blue", "purple", "orange", "olive", "pink"), *
     return [dict(color=colors[i % len(colors)], view_size=7, view_tile_size=8, **kw) for i in range(n)]
 
 
+# added in round 2 (own RNG stream in gen_golden.py, so the older fixtures stay reproducible): agent_spawn_kwargs (base.py:346,
+# 409-412,505,642 -> place_obj(top, size, max_tries) base.py:690-699) and the DoorKey generator (doorkey.py:15-41; the class is
+# made constructible by supplying the `_rand_int` it calls, see reference_harness.make_env)
+EXTRA = [
+    dict(name="Empty-spawnbox", env_class="EmptyMultiGrid", agents=agents_cfg(3), grid_size=9, agent_spawn_kwargs=dict(top=(1, 1), size=(3, 4))),
+    dict(name="Cluttered-spawnbox-respawn", env_class="ClutteredMultiGrid", agents=agents_cfg(3), grid_size=6, n_clutter=2, respawn=True,
+         max_steps=90, agent_spawn_kwargs=dict(top=(2, -2), size=(9, 5), max_tries=500)),
+    dict(name="Empty-spawnbox-delay", env_class="EmptyMultiGrid", agents=agents_cfg(3, spawn_delay=4), grid_size=8, max_steps=40,
+         agent_spawn_kwargs=dict(top=(2, 2), size=(2, 2))),
+    dict(name="DoorKey8x8x2", env_class="DoorKeyEnv", agents=agents_cfg(2), grid_size=8, max_steps=120, interactive=True, no_inject=True),
+    dict(name="DoorKey6x6x1", env_class="DoorKeyEnv", agents=agents_cfg(1), grid_size=6, max_steps=80, interactive=True, no_inject=True),
+]
+
 SCENARIOS = [
     dict(name="2AgentEmpty9x9", env_id="MarlGrid-2AgentEmpty9x9-v0"),
     dict(name="3AgentEmpty9x9", env_id="MarlGrid-3AgentEmpty9x9-v0"),
@@ -293,14 +311,15 @@ def main(quick=False):
     print(f"LOS: C restatement == numba occlude_mask (zero-padded) on {n} grids")
     rng = np.random.RandomState(7)
     total = 0
-    for sc in SCENARIOS + INTERACTIVE:
+    for sc in SCENARIOS + INTERACTIVE + EXTRA:
         sc = dict(sc)
         name = sc.pop("name")
         interactive = sc.pop("interactive", False)
         with_box = sc.pop("with_box", False)
+        no_inject = sc.pop("no_inject", False)
         n_actions = sc.pop("n_actions", 7)
         ls = LockStep(name, seed=1337 + total, env_index=total, rgb=not interactive, **sc)
-        if interactive:
+        if interactive and not no_inject:
             ls.inject = inject_interactive
             ls.with_box = with_box
         ls.run(episodes=3 if quick else 12, steps=ls.cfg.max_steps + 5, rng=rng, p_forward=0.35 if interactive else 0.5, n_actions=n_actions)

@@ -114,6 +114,22 @@ def test_scenario_kwargs_resolve_like_reference():
                     clutter_density=0.15, n_bonus_tiles=3, penalty=-1.5, max_steps=250, respawn=True, obs_mode="encoded")
     assert (cfg.goal_mode, cfg.n_bonus_tiles, cfg.bonus_penalty, cfg.view_offset, cfg.view_tile_size) == (GOAL_NONE, 3, -1.5, 1, 11)
     assert not (cfg.flags & 4)  # goal-cycle envs default reward_decay=False (goalcycle.py:9,14)
+    assert cfg.prestige_mask == 1 and cfg.prestige_beta[0] == 0.95 and cfg.prestige_scale[0] == 2.0
+    # agent_spawn_kwargs -> place_obj(top, size, max_tries) (base.py:346,409-412,690-696): the box is clipped like the reference's
+    from marlgrid_b200.envs import DoorKeyEnv
+
+    cfg, _ = cfg_of(EmptyMultiGrid, agents=ag, grid_size=9, agent_spawn_kwargs=dict(top=(5, -2), size=(9, 5), max_tries=500))
+    assert (tuple(cfg.spawn_top), tuple(cfg.spawn_size), cfg.spawn_max_tries, cfg.scenario) == ((5, 0), (9, 5), 500, 0)
+    cfg, _ = cfg_of(EmptyMultiGrid, agents=ag, grid_size=9)
+    assert (tuple(cfg.spawn_top), tuple(cfg.spawn_size), cfg.spawn_max_tries) == ((0, 0), (0, 0), 0)  # size None = the whole grid
+    with pytest.raises(ValueError, match="empty spawn region"):
+        EmptyMultiGrid(agents=ag, grid_size=9, agent_spawn_kwargs=dict(top=(9, 0)))
+    with pytest.raises(NotImplementedError, match="reject_fn"):
+        EmptyMultiGrid(agents=ag, grid_size=9, agent_spawn_kwargs=dict(reject_fn=lambda pos: False))
+    with pytest.raises(TypeError):
+        EmptyMultiGrid(agents=ag, grid_size=9, agent_spawn_kwargs=dict(rand_dir=True))
+    cfg, k = cfg_of(DoorKeyEnv, agents=ag[:2], grid_size=8)
+    assert cfg.scenario == 1 and k["obs_mode"] == "encoded" and tuple(cfg.spawn_size) == (0, 0)
     with pytest.raises(ValueError):
         ClutteredMultiGrid(agents=ag, grid_size=9)  # n_clutter xor clutter_density (cluttered.py:10-11)
     with pytest.raises(ValueError):
