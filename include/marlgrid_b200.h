@@ -85,6 +85,8 @@ enum { MG_GOAL_NONE = 0, MG_GOAL_FIXED = 1, MG_GOAL_RANDOM = 2 };
 #define MG_ERR_STACK 4u       /* AssertionError / ValueError("?!?!?!") base.py:558,568-569 */
 #define MG_ERR_TOGGLE 8u      /* TypeError from Box.toggle(self) objects.py:381 */
 #define MG_ERR_RENDER 16u     /* object whose render() raises in the reference (objects.py:274-277,309-321,370) */
+#define MG_ERR_PRESTIGE 32u   /* AttributeError: GridAgentInterface.reward() with allow_negative_prestige does `self.rew += rew` on an
+                                 attribute that is never created (agents.py:146-148) */
 
 /* negative return codes */
 #define MG_E_CONFIG (-1)
@@ -161,6 +163,9 @@ typedef struct MgState {
                        seqlock decide whether a step kernel copies the slot or generates the world itself: both give the same
                        world, results never depend on timing).  It takes reset()'s Philox + rejection sampling off the step's
                        critical path.  Zeroed by mg_init.  Before freeing or re-purposing the buffer call mg_pregen_drain(). */
+  double* prestige; /* [B][A] or NULL: GridAgentInterface.prestige (agents.py:141-153,168), the running discounted reward that colours
+                       a color='prestige' agent's tile (agents.py:92-119).  Required (non-NULL) when MgConfig.prestige_mask != 0;
+                       such families take the per-env step kernel + observe kernel (the fused kernels do not carry the state). */
 } MgState;
 
 typedef void* mg_stream_t; /* cudaStream_t */

@@ -16,7 +16,7 @@ MG_ENV_REC = 16
 F_GHOST, F_RESPAWN, F_REWARD_DECAY, F_SEE_THROUGH, F_BONUS_INITIAL, F_BONUS_RESET = 1, 2, 4, 8, 16, 32
 GOAL_NONE, GOAL_FIXED, GOAL_RANDOM = 0, 1, 2
 
-ERR_BAD_ACTION, ERR_PLACEMENT, ERR_STACK, ERR_TOGGLE, ERR_RENDER = 1, 2, 4, 8, 16
+ERR_BAD_ACTION, ERR_PLACEMENT, ERR_STACK, ERR_TOGGLE, ERR_RENDER, ERR_PRESTIGE = 1, 2, 4, 8, 16, 32
 AF_PLACED, AF_ACTIVE, AF_DONE = 1, 2, 4
 
 
@@ -66,6 +66,7 @@ class MgState(ctypes.Structure):
         ("env_offset", ctypes.c_int64),
         ("seed", ctypes.c_uint64),
         ("pregen", ctypes.c_void_p),
+        ("prestige", ctypes.c_void_p),
     ]
 
 

@@ -76,6 +76,8 @@ static KP make_kp(const MgConfig* c, const MgState* st) {
   p.ah = std::min(p.ay0 + (whole ? c->height : c->spawn_size[1]), c->height) - p.ay0;
   p.amax = c->spawn_max_tries > 0 ? std::min(c->spawn_max_tries, 100000) : 100000;
   p.scenario = c->scenario;
+  p.prestige = st->prestige; p.prestige_mask = c->prestige_mask; p.prestige_neg = c->prestige_neg_mask;
+  for (int i = 0; i < MG_MAX_AGENTS; ++i) { p.pbeta[i] = c->prestige_beta[i]; p.pscale[i] = c->prestige_scale[i]; }
   p.pregen = p.cellbits ? st->pregen : nullptr;
   p.stats = p.pregen ? device_stats() : nullptr;
   return p;
@@ -148,6 +150,7 @@ static int check_state(const MgConfig* c, const MgState* st) {
   int e = check_cfg(c);
   if (e) return e;
   if (!st || !st->grid || !st->agents || !st->envrec || st->n_envs < 0) return MG_E_ARG;
+  if (c->prestige_mask != 0u && st->prestige == nullptr) return MG_E_ARG;  // a 'prestige'-coloured agent needs its running reward
   if (!aligned16(st->grid) || !aligned16(st->agents) || !aligned16(st->envrec) || !aligned16(st->cellbits) || !aligned16(st->pregen)) return MG_E_ARG;
   return 0;
 }
@@ -197,6 +200,7 @@ int mg_init(const MgConfig* cfg, const MgState* st, mg_stream_t stream) {
   int e = check_state(cfg, st);
   if (e) return e;
   if (st->n_envs == 0) return 0;
+  if (st->prestige != nullptr) MG_CUDA(cudaMemsetAsync(st->prestige, 0, (size_t)st->n_envs * cfg->n_agents * sizeof(double), (cudaStream_t)stream));
   if (st->pregen != nullptr) {  // no world is ready; a generator pass still in flight on a reused buffer must be over first
     mg_pregen_drain();
     MG_CUDA(cudaMemsetAsync(st->pregen, 0, (size_t)st->n_envs * 64 * sizeof(uint32_t), (cudaStream_t)stream));

@@ -64,6 +64,9 @@ struct KP {
   uint32_t* pregen;  // MgState.pregen: pre-generated next worlds [B][64] (mg_world.cuh) or nullptr
   int ax0, ay0, aw, ah, amax;  // agent spawn box [ax0, ax0 + aw) x [ay0, ay0 + ah) and max_tries (agent_spawn_kwargs, base.py:690-696)
   int scenario;                // MG_SCENARIO_*
+  double* prestige;            // MgState.prestige [B][A] or nullptr
+  uint32_t prestige_mask, prestige_neg;  // agents coloured 'prestige' / with allow_negative_prestige
+  double pbeta[MG_MAX_AGENTS], pscale[MG_MAX_AGENTS];
   unsigned long long* stats;  // per-device counters: [0] envs regenerated from a pre-generated world, [1] envs generated inside the step kernel
 };
 

@@ -22,6 +22,7 @@ struct EnvCtx {
   int sc, ep, tl;     // step_count, episode, lifetime steps
   uint32_t w3;        // lo16 next stamp, hi16 error bits
   bool dirty;         // planes modified during this step
+  double* prest = nullptr;  // the env's GridAgentInterface.prestige values [A] (agents.py:141-153) or nullptr
   __device__ __forceinline__ uint32_t& R(int a, int w) { return rec[(a * 4 + w) * RS]; }
   __device__ __forceinline__ void add_err(uint32_t bits_) { w3 |= bits_ << 16; }
   __device__ __forceinline__ uint32_t next_stamp() {
@@ -111,6 +112,7 @@ __device__ void env_reset_doorkey(EnvCtx<RS>& c, unsigned long long g) {
     c.R(a, 0) = c.R(a, 0) & 0x00FF0000u;
     c.R(a, 1) = 0xFF000000u;
     c.R(a, 2) = 0;
+    if (c.prest != nullptr) c.prest[a] = 0.0;  // new_episode: agents.py:167-168
   }
   int4* z = reinterpret_cast<int4*>(c.tp);
   for (int i = 0; i < 3 * S / 16; ++i) z[i] = make_int4(0, 0, 0, 0);
@@ -170,6 +172,7 @@ __device__ void env_reset(EnvCtx<RS>& c, unsigned long long g) {
     c.R(a, 0) = c.R(a, 0) & 0x00FF0000u;
     c.R(a, 1) = 0xFF000000u;
     c.R(a, 2) = 0;
+    if (c.prest != nullptr) c.prest[a] = 0.0;  // new_episode: agents.py:167-168
   }
   if (PLANES) {
     int4* z = reinterpret_cast<int4*>(c.tp);
@@ -395,6 +398,10 @@ __device__ bool env_step(EnvCtx<RS>& c, unsigned long long g, const int32_t* __r
                 rwd = __dmul_rn(rwd, f);
               }
               reward = __dadd_rn(0.0, rwd);  // step_rewards[agent_no] += rwd (base.py:580): 0.0 + (-0.0) is +0.0
+              if (c.prest != nullptr) {  // agent.reward(rwd) base.py:581, agents.py:146-153
+                if ((p.prestige_neg >> a) & 1u) c.add_err(MG_ERR_PRESTIGE);  // `self.rew += rew`: no such attribute
+                else c.prest[a] = (rwd >= 0.0) ? __dadd_rn(c.prest[a], rwd) : 0.0;
+              }
             }
             if (ftype == MG_T_LAVA || ftype == MG_T_GOAL) w0 |= (uint32_t)MG_AF_DONE << 24;  // base.py:584-585
             c.R(a, 0) = w0;
@@ -427,6 +434,7 @@ __device__ bool env_step(EnvCtx<RS>& c, unsigned long long g, const int32_t* __r
       } else if (action != MG_A_DONE) {
         c.add_err(MG_ERR_BAD_ACTION);  // base.py:619-620
       }
+      if (c.prest != nullptr && !(action > MG_A_DONE || action < 0)) c.prest[a] = __dmul_rn(c.prest[a], p.pbeta[a]);  // agent.on_step base.py:622, agents.py:141-144
     }
     rew[a] = reward;
   }

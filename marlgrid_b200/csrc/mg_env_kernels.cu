@@ -21,6 +21,7 @@ __global__ void __launch_bounds__(ENV_THREADS) env_kernel(const __grid_constant_
   const int A = p.A;
   EnvCtx<ENV_THREADS> c{p, s_rec + threadIdx.x, p.grid + env * 3 * p.S, BITS ? env_bits(p.cellbits, env) : nullptr,
                         s_scr + threadIdx.x, 0, 0, 0, 0u, false};
+  c.prest = p.prestige != nullptr ? p.prestige + env * p.A : nullptr;
   int4* arec = reinterpret_cast<int4*>(p.agents) + env * A;
   const int4 er = reinterpret_cast<const int4*>(p.envrec)[env];
 #pragma unroll

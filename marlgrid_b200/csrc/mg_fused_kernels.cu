@@ -297,6 +297,7 @@ static int launch_fused_v(const KP& p, cudaStream_t s) {
 // the one-launch path exists for bit-plane worlds in ghost mode without respawn / spawn delay (every registered env)
 bool fused_eligible(const KP& p) {
   if (p.cellbits == nullptr || !(p.flags & MG_F_GHOST) || (p.flags & MG_F_RESPAWN)) return false;
+  if (p.prestige != nullptr) return false;  // the running reward of 'prestige' agents is kept by the per-env step kernel only
   for (int a = 0; a < p.A; ++a)
     if (p.spawn_delay[a] != 0) return false;
   return true;

@@ -211,7 +211,10 @@ struct ObsSmem {
   uint8_t* tile;    // OBS 2: tile-id map [32*A][V*V]
   uint8_t* orient;  // OBS 2: view orientation [32*A]
   uint8_t* atlas;   // OBS 2: atlas copy + one shadow tile
+  uint8_t* amax;    // OBS 2, 'prestige' agents: [1 + 4A] largest triangle alpha of every agent tile slot
+  uint8_t* pcol;    // OBS 2, 'prestige' agents: [32*A][4] = (red, blue, active, -) of every agent of the tile's envs
 };
+constexpr int PRESTIGE_SMEM = 64 + ENVS_PER_CTA * MG_MAX_AGENTS * 4;  // bytes behind the atlas when MgConfig.prestige_mask != 0
 
 template <int V>
 __device__ __forceinline__ ObsSmem<V> obs_smem(uint8_t* s_out, int A) {
@@ -219,6 +222,7 @@ __device__ __forceinline__ ObsSmem<V> obs_smem(uint8_t* s_out, int A) {
   o.out = s_out; o.tile = s_out;
   o.orient = o.tile + ENVS_PER_CTA * A * V * V;
   o.atlas = o.orient + ((ENVS_PER_CTA * A + 15) / 16) * 16;
+  o.amax = nullptr; o.pcol = nullptr;
   return o;
 }
 
@@ -258,7 +262,28 @@ __device__ __forceinline__ void obs_prepare(const KP& p, const ObsSmem<V>& o, in
       const int c = i % 3;
       o.atlas[slots * tile_bytes + i] = (c == 0) ? 35 : (c == 1) ? 25 : 30;
     }
+    if (o.amax != nullptr) {  // 'prestige' agents (agents.py:92-119): the largest alpha of every (white) agent tile, from the global atlas
+      for (int slot = tid; slot < 1 + 4 * A; slot += nthreads) {
+        int m = 0;
+        for (int px = 0; px < p.ts * p.ts; ++px)
+          m = max(m, (int)p.atlas[(size_t)(slot * 4) * tile_bytes + px * 3] - (int)p.atlas[px * 3]);  // minus the empty tile's border (base.py:245-250,296-298)
+        o.amax[slot] = (uint8_t)m;
+      }
+    }
   }
+}
+
+// GridAgentInterface.render_post (agents.py:92-119): the colour a 'prestige' agent's tile is multiplied with,
+// new_color = (prestige_scaled * blue + (1 - prestige_scaled) * red).astype(int) = ((1 - s) * 255, 0, s * 255) truncated,
+// s = tanh(prestige / scale) or the logistic function when negative prestige is allowed.  (tanh / exp are libdevice's: within
+// 1 ulp of numpy's, which can only show where s * 255 lies within ~1e-13 of an integer.)
+__device__ __forceinline__ void prestige_colour(const KP& p, int q, double prestige, uint8_t* __restrict__ out4, bool active) {
+  const double x = prestige / p.pscale[q];
+  const double s = ((p.prestige_neg >> q) & 1u) ? 1.0 / (1.0 + exp(-x)) : tanh(x);
+  out4[0] = (uint8_t)(int)(s * 0.0 + (1.0 - s) * 255.0);
+  out4[1] = (uint8_t)(int)(s * 255.0 + (1.0 - s) * 0.0);
+  out4[2] = active ? 1 : 0;
+  out4[3] = 0;
 }
 
 // hide_item_types (agents.py:30, base.py:441-449): after the line of sight has been computed on the real grid, every cell
@@ -355,6 +380,7 @@ __device__ __forceinline__ void obs_view(const KP& p, const ObsSmem<V>& o, int v
   const int px = (int)(w0 & 0xFFu), py = (int)((w0 >> 8) & 0xFFu), dir = (int)((w0 >> 16) & 3u);
   const int orient = (3 - dir) & 3;  // view orientation (0 - rot_k) % 4, base.py:130
   if (OBS == 2) {
+    if (o.pcol != nullptr && ((p.prestige_mask >> a) & 1u)) prestige_colour(p, a, p.prestige[env * A + a], o.pcol + view * 4, active);  // view == local env * A + a
     o.orient[view] = (uint8_t)((p.orient_slots == 4) ? orient : 0);
     if (!active) {
       const uint8_t shadow = (uint8_t)(p.n_tiles);  // one past the last tile: resolved to the shadow slot when expanding
@@ -518,7 +544,33 @@ __device__ __forceinline__ void obs_emit(const KP& p, const ObsSmem<V>& o, long 
         const int vb = y / ts, pyy = y - vb * ts;
         const int t = o.tile[view * VV + vb * V + va];
         const int slot = (t >= p.n_tiles) ? p.n_tiles * p.orient_slots : t * p.orient_slots + o.orient[view];
-        dst[i] = o.atlas[(slot * ts + pyy) * ts * 3 + r];
+        uint8_t val = o.atlas[(slot * ts + pyy) * ts * 3 + r];
+        if (o.pcol != nullptr && t < p.n_tiles) {
+          // a tile with a 'prestige'-coloured agent on it (agents.py:92-119): the atlas holds that agent in white, i.e. its
+          // triangle's alpha; the pixels are alpha * new_color >> 8, blended over the cell's object like any agent tile
+          // (blend_tiles base.py:260-273 with the recoloured tile) -- an inactive agent keeps the cached white tile
+          const int per_kind = 1 + 4 * A, kind = t / per_kind, as = t - kind * per_kind;
+          if (as > 0) {
+            const int q = (as - 1) >> 2;
+            const uint8_t* pc = o.pcol + ((view / A) * A + q) * 4;
+            if (((p.prestige_mask >> q) & 1u) && pc[2]) {
+              const int os = o.orient[view], tb = ts * ts * 3, pix = (pyy * ts) * 3 + (r / 3) * 3, ch = r % 3;
+              const uint8_t* white = o.atlas + (as * p.orient_slots + os) * tb + pix;
+              const uint8_t* empty = o.atlas + os * tb + pix;  // empty_tile: only a border, for tile sizes > 10 (base.py:245-250)
+              const int alpha = (int)white[0] - (int)empty[0];
+              const int col[3] = {pc[0], 0, pc[1]};
+              const int ag = (alpha * col[ch]) >> 8;
+              if (kind == 0) val = (uint8_t)(ag + empty[ch]);
+              else {
+                const int base = o.atlas[((kind * per_kind) * p.orient_slots + os) * tb + pix + ch];
+                const int sa = ((alpha * col[0]) >> 8) + ((alpha * col[2]) >> 8);
+                const int am = o.amax[as], M = ((am * col[0]) >> 8) + ((am * col[2]) >> 8);
+                val = (uint8_t)(M == 0 ? base : (base * (M - sa) + ag * sa) / M);
+              }
+            }
+          }
+        }
+        dst[i] = val;
       }
     }
   }

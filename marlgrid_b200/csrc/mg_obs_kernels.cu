@@ -19,7 +19,11 @@ __global__ void __launch_bounds__(32 * MG_MAX_AGENTS) obs_kernel(const __grid_co
   uint32_t* s_bits = reinterpret_cast<uint32_t*>(s_grid + (BITS ? 0 : ENVS_PER_CTA * 3 * S));  // bit-plane path only
   uint32_t* s_rec = s_bits + (BITS ? ENVS_PER_CTA * BITS_WORDS : 0);                         // agent records as stored: [env][a][4 words]
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_rec + ENVS_PER_CTA * A * 4);
-  const ObsSmem<V> o = obs_smem<V>(reinterpret_cast<uint8_t*>(s_bar + 2), A);  // 16-byte aligned: every block above is a multiple of 16 bytes
+  ObsSmem<V> o = obs_smem<V>(reinterpret_cast<uint8_t*>(s_bar + 2), A);  // 16-byte aligned: every block above is a multiple of 16 bytes
+  if (OBS == 2 && p.prestige_mask != 0u) {  // behind the atlas and the shadow tile
+    o.amax = o.atlas + ((p.n_tiles * p.orient_slots + 1) * p.ts * p.ts * 3 + 15) / 16 * 16;
+    o.pcol = o.amax + 64;
+  }
 
   if (tid == 0) mbar_init(s_bar, 1);
   __syncthreads();
@@ -51,6 +55,7 @@ static size_t obs_smem_bytes(const KP& p, int obs) {
   if (obs == 2) {
     b += (size_t)ENVS_PER_CTA * p.A * p.V * p.V + (size_t)((ENVS_PER_CTA * p.A + 15) / 16) * 16;
     b += (size_t)(p.n_tiles * p.orient_slots + 1) * p.ts * p.ts * 3;
+    if (p.prestige_mask != 0u) b += 16 + PRESTIGE_SMEM;
   }
   return (b + 15) / 16 * 16;
 }
@@ -92,6 +97,7 @@ static int launch_obs_v(const KP& p, cudaStream_t s) {
 int launch_obs(const KP& p, int obs, cudaStream_t s) {
   const bool bits = p.cellbits != nullptr;
   if (obs == 1) return bits ? launch_obs_v<1, 0, true>(p, s) : launch_obs_v<1, 0, false>(p, s);
+  if (p.prestige_mask != 0u) return bits ? launch_obs_v<2, 0, true>(p, s) : launch_obs_v<2, 0, false>(p, s);  // per-pixel recolouring: the byte path
   if (p.ts == 8) return bits ? launch_obs_v<2, 8, true>(p, s) : launch_obs_v<2, 8, false>(p, s);
   if (p.ts % 4 == 0) return bits ? launch_obs_v<2, 1, true>(p, s) : launch_obs_v<2, 1, false>(p, s);
   return bits ? launch_obs_v<2, 0, true>(p, s) : launch_obs_v<2, 0, false>(p, s);

@@ -20,7 +20,7 @@ import torch
 
 from . import _lib
 from . import atlas as _atlas
-from .config import (AF_ACTIVE, AF_DONE, AF_PLACED, ERR_BAD_ACTION, ERR_PLACEMENT, ERR_RENDER, ERR_STACK, ERR_TOGGLE,
+from .config import (AF_ACTIVE, AF_DONE, AF_PLACED, ERR_BAD_ACTION, ERR_PLACEMENT, ERR_PRESTIGE, ERR_RENDER, ERR_STACK, ERR_TOGGLE,
                      MgConfig, MgState, n_tiles)
 from .spaces import Box, Discrete, Tuple
 
@@ -81,6 +81,9 @@ class BatchedMultiGridEnv:
         self.cellbits = torch.zeros(((B + 31) // 32, 44, 32), dtype=torch.int32, device=dev)
         # pre-generated next worlds, filled by the library's background generator (include/marlgrid_b200.h MgState.pregen)
         self.pregen = torch.zeros((B, 64), dtype=torch.int32, device=dev) if pregen else None
+        # GridAgentInterface.prestige (agents.py:141-153): kept only for families with a 'prestige'-coloured agent, whose tile is
+        # recoloured from it (agents.py:92-119); such families take the per-env step kernel + observe kernel
+        self.prestige = torch.zeros((B, A), dtype=torch.float64, device=dev) if cfg.prestige_mask else None
         self.rewards = torch.zeros((B, A), dtype=torch.float64, device=dev)
         self.done = torch.zeros((B,), dtype=torch.bool, device=dev)  # the kernels write 0/1 bytes: no conversion pass per step
         # The observation tensor returned by step() is a view of a device buffer.  With obs_buffers = 2 (default) steps
@@ -128,6 +131,7 @@ class BatchedMultiGridEnv:
         st.grid, st.agents, st.envrec = self.grid.data_ptr(), self.agent_rec.data_ptr(), self.envrec.data_ptr()
         st.cellbits = self.cellbits.data_ptr()
         st.pregen = self.pregen.data_ptr() if self.pregen is not None else None
+        st.prestige = self.prestige.data_ptr() if self.prestige is not None else None
         st.n_envs, st.env_offset, st.seed = self.num_envs, self.env_offset, self._seed
 
     def seed(self, seed=1337):
@@ -334,6 +338,8 @@ class BatchedMultiGridEnv:
             raise AssertionError("agent left a cell that cannot be overlapped (marlgrid/base.py:558)")
         if bits & ERR_TOGGLE:
             raise TypeError("Box.toggle() takes 1 positional argument but 3 were given (marlgrid/objects.py:381)")
+        if bits & ERR_PRESTIGE:
+            raise AttributeError("'GridAgentInterface' object has no attribute 'rew' (allow_negative_prestige, marlgrid/agents.py:146-148)")
         if bits & ERR_RENDER:
             raise NameError("object has no working render() in the reference (marlgrid/objects.py:274-277,309-321,370)")
 
@@ -400,13 +406,21 @@ class BatchedMultiGridEnv:
 
     # ---- checkpoint / resume (the RNG is counter-based: resume is exact) -----------------------
     def state_dict(self):
-        return {"grid": self.grid.clone(), "agents": self.agent_rec.clone(), "envrec": self.envrec.clone(), "seed": self._seed,
-                "env_offset": self.env_offset}
+        sd = {"grid": self.grid.clone(), "agents": self.agent_rec.clone(), "envrec": self.envrec.clone(), "seed": self._seed,
+              "env_offset": self.env_offset}
+        if self.prestige is not None:
+            sd["prestige"] = self.prestige.clone()
+        return sd
 
     def load_state_dict(self, sd):
         self.grid.copy_(sd["grid"])
         self.agent_rec.copy_(sd["agents"])
         self.envrec.copy_(sd["envrec"])
+        if self.prestige is not None and "prestige" in sd:
+            self.prestige.copy_(sd["prestige"])
+        if self.pregen is not None:
+            self._lib.mg_pregen_drain()  # episode numbers may go backwards: no generator pass may be in flight (mg_pregen.cu)
+            self.pregen.zero_()
         self._seed = int(sd["seed"])
         self.env_offset = int(sd["env_offset"])
         self._sync_state_struct()

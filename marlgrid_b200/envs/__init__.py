@@ -77,10 +77,6 @@ class MultiGridEnv(BatchedMultiGridEnv):
                       "observe_position", "observe_orientation"):
             if len({getattr(a, field) for a in ai}) != 1:
                 raise ValueError(f"all agents of a batched env must share {field} (observations are one tensor)")
-        if obs_mode == "rgb" and any(a.color == "prestige" for a in ai):
-            # agents.py:92-119 render_post recolours a 'prestige' agent's tile from its running reward average; the tile atlas
-            # of the RGB kernel is static per agent, so the pixels would silently differ from the reference's
-            raise NotImplementedError("color='prestige' (agents.py:92-119) is not built for obs_mode='rgb' yet; use obs_mode='encoded'")
         self.width, self.height = width, height
         self.max_steps, self.reward_decay, self.respawn, self.ghost_mode = max_steps, reward_decay, respawn, ghost_mode
         cfg = make_config(

@@ -49,6 +49,7 @@ def _sub_state(env, index):
     st.agents = env.agent_rec[index].data_ptr()
     st.envrec = env.envrec[index].data_ptr()
     st.pregen = None
+    st.prestige = env.prestige[index].data_ptr() if getattr(env, "prestige", None) is not None else None
     st.cellbits = None  # the bit-planes are tile-transposed (32 envs interleaved): a single env takes the byte-plane kernels
     st.n_envs, st.env_offset, st.seed = 1, env.env_offset + index, env._seed
     return st
@@ -97,13 +98,32 @@ def visibility_masks(env, index=0):
     return (m.cpu().numpy() != 0) & active[:, None, None]
 
 
+def prestige_colour(prestige, scale, allow_negative):
+    """agents.py:103-111: new_color = (prestige_scaled * blue + (1 - prestige_scaled) * red).astype(int)."""
+    s = 1 / (1 + np.exp(-prestige / scale)) if allow_negative else np.tanh(prestige / scale)
+    return (s * np.array([0, 0, 255]) + (1.0 - s) * np.array([255, 0, 0])).astype(np.int64)
+
+
+def prestige_tile(at, kind, agent_slot, per_kind, colour):
+    """The tile of a cell whose agent is coloured 'prestige': the atlas holds that agent in white, i.e. its triangle's alpha
+    (+ the empty tile's border, base.py:245-250,296-298); render_post multiplies alpha with the colour (agents.py:113-115),
+    render_tile blends the result over the cell's object (blend_tiles, base.py:260-273)."""
+    empty = at[0].astype(np.int64)
+    alpha = at[agent_slot].astype(np.int64)[..., 0] - empty[..., 0]
+    agent = np.right_shift(alpha[..., None] * colour, 8)
+    if kind == 0:
+        return (agent + empty).astype(np.uint8)
+    base = at[kind * per_kind].astype(np.int64)
+    sa = agent.sum(2, keepdims=True)
+    m = int(sa.max())
+    return (base if m == 0 else (base * (m - sa) + agent * sa) // m).astype(np.uint8)
+
+
 def render(env, index=0, highlight=True, tile_size=32, show_agent_views=True, max_agents_per_col=3, agent_col_width_frac=0.3,
            agent_col_padding_px=2, pad_grey=100):
     """-> uint8 [H*tile_size, W*tile_size (+ agent view columns), 3]; same keyword arguments as the reference's render."""
     cfg = env.cfg
     A, V, vo, W, H, ts = cfg.n_agents, cfg.view_size, cfg.view_offset, cfg.width, cfg.height, int(tile_size)
-    if any(int(c) == _PRESTIGE for c in cfg.agent_color[:A]):
-        raise NotImplementedError("color='prestige' (agents.py:92-119: tile recoloured by the agent's running reward) is not built yet")
     planes = env.planes[index].cpu().numpy()
     ag = env.agent_rec[index].cpu().numpy()
     placed = (ag[:, 3] & AF_PLACED) != 0
@@ -122,6 +142,10 @@ def render(env, index=0, highlight=True, tile_size=32, show_agent_views=True, ma
         tiles[x, y] += 1 + 4 * q + (int(ag[q, 2]) & 3)
     at = _atlas_for([int(c) for c in cfg.agent_color[:A]], ts, cfg.n_static_kinds)[:, 0]   # grid orientation 0
     img = at[tiles.T]                                             # [H, W, ts, ts, 3]: image row = y, column = x (base.py:319-324)
+    for (x, y), q in head.items():  # 'prestige'-coloured agents: GridAgentInterface.render_post (agents.py:92-119) on the white tile
+        if int(cfg.agent_color[q]) == _PRESTIGE and (ag[q, 3] & AF_ACTIVE):
+            img[y, x] = prestige_tile(at, int(kinds[x, y]), 1 + 4 * q + (int(ag[q, 2]) & 3), per_kind,
+                                      prestige_colour(float(env.prestige[index, q].item()), float(cfg.prestige_scale[q]), bool((cfg.prestige_neg_mask >> q) & 1)))
     img = np.ascontiguousarray(img.transpose(0, 2, 1, 3, 4)).reshape(H * ts, W * ts, 3)
     if highlight:  # cells inside some active agent's line of sight (base.py:741-753)
         vis = visibility_masks(env, index)

@@ -108,6 +108,8 @@ def cfg_kwargs(cfg, seed, env_index):
             spawn_top=[int(cfg.spawn_top[0]), int(cfg.spawn_top[1])],
             spawn_size=None if (cfg.spawn_size[0] == 0 and cfg.spawn_size[1] == 0) else [int(cfg.spawn_size[0]), int(cfg.spawn_size[1])],
             spawn_max_tries=int(cfg.spawn_max_tries) or None, scenario=int(cfg.scenario),
+            prestige_beta=[float(b) for b in cfg.prestige_beta[: cfg.n_agents]], prestige_scale=[float(b) for b in cfg.prestige_scale[: cfg.n_agents]],
+            allow_negative_prestige=[bool((cfg.prestige_neg_mask >> i) & 1) for i in range(cfg.n_agents)],
         ),
     )
 
@@ -225,6 +227,28 @@ class RenderRecorder(val.LockStep):
         return d
 
 
+def gen_render_extra():
+    """render_<scenario>.npz for scenarios of validate_against_reference.EXTRA (own RNG stream): 'prestige' agents in the whole-grid view."""
+    rng = np.random.RandomState(1177)
+    picks = {"Empty6x6-prestige": 40}
+    for k, sc in enumerate(s for s in val.EXTRA if s["name"] in picks):
+        sc = dict(sc)
+        name = sc.pop("name")
+        seed, env_index = 515 + 5 * k, 19 * k + 2
+        rec = RenderRecorder(name, seed=seed, env_index=env_index, rgb=True, **sc)
+        rec.reset()
+        for t in range(picks[name]):
+            act = rng.randint(0, 7, size=len(rec.env.agents))
+            act[rng.rand(len(act)) < 0.6] = 2
+            if rec.step(act, t) is True:
+                rec.reset()
+        fname = "render_" + "".join(ch if ch.isalnum() else "_" for ch in name).strip("_") + ".npz"
+        np.savez_compressed(os.path.join(OUT, fname), meta=np.frombuffer(json.dumps(cfg_kwargs(rec.cfg, seed, env_index)).encode(), dtype=np.uint8),
+                            kind=np.array([e["kind"] for e in rec.ev], np.uint8), actions=np.stack([e["actions"] for e in rec.ev]),
+                            img=np.stack([e["img"] for e in rec.ev]))
+        print(f"  {fname:48s} {len(rec.ev)} frames {rec.ev[0]['img'].shape}; {rec.events}")
+
+
 def gen_render():
     """render_<scenario>.npz: event stream (0 = reset, 1 = step(actions)) + the reference's rendered frame after every event."""
     rng = np.random.RandomState(77)
@@ -257,6 +281,7 @@ if __name__ == "__main__":
         gen_hide_trajectories()
     elif "extra" in sys.argv[1:]:
         gen_extra_trajectories()
+        gen_render_extra()
     else:
         gen_los()
         gen_atlas()
@@ -264,3 +289,4 @@ if __name__ == "__main__":
         gen_hide_trajectories()
         gen_extra_trajectories()
         gen_render()
+        gen_render_extra()

@@ -21,6 +21,7 @@
  */
 #include <stdint.h>
 #include <stdlib.h>
+#include <math.h>
 #include <string.h>
 
 #include "../include/marlgrid_b200.h"
@@ -85,7 +86,12 @@ typedef struct {
   uint8_t* type; uint8_t* colour; uint8_t* state; /* planes, cell (x,y) at x*H+y (base.py:91) */
   uint8_t* ag;   /* [A][16] */
   int32_t* er;   /* [4] */
+  double* pr;    /* [A] GridAgentInterface.prestige (agents.py:141-153) or NULL */
 } Env;
+
+/* the batch's prestige values [B][A], set by mgo_set_prestige (NULL: not tracked) */
+static double* g_prestige = 0;
+void mgo_set_prestige(double* p) { g_prestige = p; }
 
 static Env env_at(const MgConfig* c, uint8_t* grid, uint8_t* agents, int32_t* envrec, int64_t e) {
   Env v; v.c = c;
@@ -94,6 +100,7 @@ static Env env_at(const MgConfig* c, uint8_t* grid, uint8_t* agents, int32_t* en
   v.state = v.colour + c->plane_stride;
   v.ag = agents + (size_t)e * c->n_agents * MG_AGENT_REC;
   v.er = envrec + (size_t)e * 4;
+  v.pr = g_prestige ? g_prestige + (size_t)e * c->n_agents : 0;
   return v;
 }
 #define AX(v, a) ((v)->ag[(a) * 16 + 0])
@@ -231,6 +238,7 @@ static void env_reset(Env* v, uint64_t seed, uint64_t g) {
   for (int a = 0; a < A; ++a) { /* agents.py:161-170: dir/state untouched */
     AFL(v, a) = 0; AX(v, a) = 0; AY(v, a) = 0; ACT(v, a) = 0; ACC(v, a) = 0; ACS(v, a) = 0; ABONUS(v, a) = 0xFF;
     set_stamp(v, a, 0);
+    if (v->pr) v->pr[a] = 0.0; /* agent.reset(new_episode=True) agents.py:167-168 */
   }
   memset(v->type, 0, (size_t)c->plane_stride * 3);
   v->er[3] = (int32_t)((uint32_t)v->er[3] & 0xFFFF0000u); /* next stamp = 0, keep error bits */
@@ -333,6 +341,11 @@ static int env_step(Env* v, const int32_t* actions, double* rewards, uint64_t se
             rwd = rwd * f;
           }
           rewards[a] += rwd;
+          if (v->pr) { /* agent.reward(rwd) base.py:581, agents.py:146-153 */
+            if ((c->prestige_neg_mask >> a) & 1u) add_err(v, MG_ERR_PRESTIGE); /* `self.rew += rew`: AttributeError */
+            else if (rwd >= 0) { volatile double s = v->pr[a] + rwd; v->pr[a] = s; }
+            else v->pr[a] = 0.0;
+          }
         }
         if (ftype == MG_T_LAVA || ftype == MG_T_GOAL) AFL(v, a) |= MG_AF_DONE; /* base.py:584-585 */
       }
@@ -354,7 +367,8 @@ static int env_step(Env* v, const int32_t* actions, double* rewards, uint64_t se
         else if (fstate == MG_DOOR_OPEN) v->state[fidx] = MG_DOOR_CLOSED;
       } else if (ftype == MG_T_BOX) add_err(v, MG_ERR_TOGGLE); /* Box.toggle(self) objects.py:381 */
     } else if (act == MG_A_DONE) { /* base.py:616-617 */
-    } else add_err(v, MG_ERR_BAD_ACTION); /* base.py:619-620 */
+    } else { add_err(v, MG_ERR_BAD_ACTION); continue; } /* base.py:619-620: raises before on_step */
+    if (v->pr) { volatile double s = v->pr[a] * c->prestige_beta[a]; v->pr[a] = s; } /* agent.on_step base.py:622, agents.py:141-144 */
   }
   for (int a = 0; a < A; ++a) /* base.py:627-646 */
     if (AFL(v, a) & MG_AF_DONE) {
@@ -516,6 +530,27 @@ static void obs_rgb_env(Env* v, const uint8_t* atlas, uint8_t* obs) {
       int t = tile_index(c, kind, q, q >= 0 ? (ADIR(v, q) & 3) : 0);
       const uint8_t* tile = atlas + ((size_t)t * 4 + orient) * tile_bytes;
       for (int y = 0; y < ts; ++y) memcpy(img + (size_t)(vb * ts + y) * row + (size_t)va * ts * 3, tile + (size_t)y * ts * 3, (size_t)ts * 3);
+      if (q >= 0 && v->pr && ((c->prestige_mask >> q) & 1u) && (AFL(v, q) & MG_AF_ACTIVE)) {
+        /* GridAgentInterface.render_post (agents.py:92-119) on the cached WHITE agent tile, then render_tile's blend over the
+         * cell's object (base.py:260-273,289-293) and border rule (:296-298): the atlas tile of (no object, agent q) minus the
+         * empty tile's border is the triangle's alpha; an inactive agent keeps the cached tile (agents.py:93-94) */
+        double x = v->pr[q] / c->prestige_scale[q];
+        double sc = ((c->prestige_neg_mask >> q) & 1u) ? 1.0 / (1.0 + exp(-x)) : tanh(x);
+        int col[3] = {(int)(sc * 0.0 + (1.0 - sc) * 255.0), 0, (int)(sc * 255.0 + (1.0 - sc) * 0.0)};
+        const uint8_t* white = atlas + ((size_t)tile_index(c, 0, q, ADIR(v, q) & 3) * 4 + orient) * tile_bytes;
+        const uint8_t* empty = atlas + (size_t)orient * tile_bytes;
+        const uint8_t* base = atlas + ((size_t)tile_index(c, kind, -1, 0) * 4 + orient) * tile_bytes;
+        int amax = 0;
+        for (int p = 0; p < ts * ts; ++p) { int al = white[p * 3] - empty[p * 3]; if (al > amax) amax = al; }
+        int M = ((amax * col[0]) >> 8) + ((amax * col[2]) >> 8);
+        for (int y = 0; y < ts; ++y) for (int xx = 0; xx < ts; ++xx) {
+          int p = y * ts + xx, al = white[p * 3] - empty[p * 3];
+          int ag[3] = {(al * col[0]) >> 8, 0, (al * col[2]) >> 8}, sa = ag[0] + ag[2];
+          uint8_t* o = img + (size_t)(vb * ts + y) * row + (size_t)(va * ts + xx) * 3;
+          for (int ch = 0; ch < 3; ++ch)
+            o[ch] = (uint8_t)(kind == 0 ? ag[ch] + empty[p * 3 + ch] : (M == 0 ? base[p * 3 + ch] : (base[p * 3 + ch] * (M - sa) + ag[ch] * sa) / M));
+        }
+      }
     }
   }
 }

@@ -55,12 +55,14 @@ class OracleBatch:
         self.grid = np.zeros((self.B, 3, cfg.plane_stride), np.uint8)
         self.agents = np.zeros((self.B, self.A, 16), np.uint8)
         self.envrec = np.zeros((self.B, 4), np.int32)
+        self.prestige = np.zeros((self.B, self.A), np.float64)  # GridAgentInterface.prestige (agents.py:141-153)
         self.threads = threads
         L = lib()
         L.mgo_init(ctypes.byref(cfg), _p(self.grid), _p(self.agents), _p(self.envrec), ctypes.c_int64(self.B))
 
     def _thr(self):
         lib().mgo_set_threads(int(self.threads))
+        lib().mgo_set_prestige(_p(self.prestige))  # (a library-wide pointer: set before every call of this batch)
 
     def reset(self, mask=None):
         self._thr()

@@ -37,6 +37,8 @@ def config_from_ref_env(env):
     sk = dict(getattr(env, "agent_spawn_kwargs", {}) or {})  # place_obj(agent, **agent_spawn_kwargs), base.py:409-412
     assert set(sk) <= {"top", "size", "max_tries"}, sk
     kw.update(spawn_top=tuple(sk.get("top", (0, 0))), spawn_size=sk.get("size"), spawn_max_tries=sk.get("max_tries"))
+    kw.update(prestige_beta=[a.prestige_beta for a in ag], prestige_scale=[a.prestige_scale for a in ag],
+              allow_negative_prestige=[bool(a.allow_negative_prestige) for a in ag])
     if "DoorKeyEnv" in names:
         kw.update(goal_mode=GOAL_FIXED, scenario=1)
     elif "ClutteredGoalCycleEnv" in names:
@@ -123,6 +125,8 @@ class LockStep:
         assert np.array_equal(ob.agent_rank()[0], st["agent_rank"]), f"{self.name} {tag}: queue order {ob.agent_rank()[0]} vs {st['agent_rank']}"
         assert np.array_equal(ob.agent_carry[0].astype(np.int32), st["agent_carry"]), f"{self.name} {tag}: carry"
         assert int(ob.step_count[0]) == int(st["step_count"]), f"{self.name} {tag}: step_count"
+        pr = np.array([float(a.prestige) for a in env.agents], np.float64)
+        assert np.array_equal(ob.prestige[0].view(np.uint64), pr.view(np.uint64)), f"{self.name} {tag}: prestige {ob.prestige[0]} vs {pr}"
         enc_ref = rh.encoded_obs(env)
         enc = ob.obs_encode()[0]
         assert np.array_equal(enc, enc_ref), f"{self.name} {tag}: encoded obs differ at {np.argwhere(enc != enc_ref)[:5]}"
@@ -154,10 +158,10 @@ class LockStep:
         err_before = int(self.ob.err[0])
         try:
             o, r, d, _ = rh.ref_step(self.env, actions)
-        except (TypeError, ValueError, AssertionError, RecursionError) as exc:
+        except (TypeError, ValueError, AssertionError, RecursionError, AttributeError) as exc:
             # the reference raised mid-step: the device contract is an error bit (include/marlgrid_b200.h MG_ERR_*)
             self.ob.step(np.asarray(actions, np.int32)[None], autoreset=False)
-            want = {TypeError: 8, ValueError: 1, AssertionError: 4, RecursionError: 2}[type(exc)]
+            want = {TypeError: 8, ValueError: 1, AssertionError: 4, RecursionError: 2, AttributeError: 32}[type(exc)]
             got = int(self.ob.err[0])
             assert got & want, f"{self.name} step {t}: reference raised {type(exc).__name__} but oracle err={got}"
             self.events["raised"] += 1
@@ -210,6 +214,13 @@ EXTRA = [
          max_steps=90, agent_spawn_kwargs=dict(top=(2, -2), size=(9, 5), max_tries=500)),
     dict(name="Empty-spawnbox-delay", env_class="EmptyMultiGrid", agents=agents_cfg(3, spawn_delay=4), grid_size=8, max_steps=40,
          agent_spawn_kwargs=dict(top=(2, 2), size=(2, 2))),
+    dict(name="Empty6x6-prestige", env_class="EmptyMultiGrid", grid_size=6, max_steps=60, respawn=True,
+         agents=[dict(color="prestige", view_size=7, view_tile_size=8), dict(color="red", view_size=7, view_tile_size=8),
+                 dict(color="prestige", view_size=7, view_tile_size=8, prestige_beta=0.9, prestige_scale=0.7)]),
+    dict(name="Goalcycle-prestige-ts11", env_class="ClutteredGoalCycleEnv", grid_size=9, n_clutter=4, n_bonus_tiles=3, penalty=-0.5, max_steps=80,
+         agents=[dict(color="prestige", view_size=5, view_tile_size=11, view_offset=1), dict(color="prestige", view_size=5, view_tile_size=11, view_offset=1, prestige_scale=1.0)]),
+    dict(name="Empty5x5-prestige-negative (AttributeError)", env_class="EmptyMultiGrid", grid_size=5, max_steps=40,
+         agents=[dict(color="prestige", view_size=5, view_tile_size=8, allow_negative_prestige=True)]),
     dict(name="DoorKey8x8x2", env_class="DoorKeyEnv", agents=agents_cfg(2), grid_size=8, max_steps=120, interactive=True, no_inject=True),
     dict(name="DoorKey6x6x1", env_class="DoorKeyEnv", agents=agents_cfg(1), grid_size=6, max_steps=80, interactive=True, no_inject=True),
 ]

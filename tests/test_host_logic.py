@@ -243,14 +243,21 @@ def test_hide_item_types_mask():
     assert make_config(9, 9, ["red"], hide_types=hide_mask(["Door"])).hide_types == 1 << 11
 
 
-def test_prestige_colour_is_refused_for_pixel_outputs():
-    """agents.py:92-119 recolours a 'prestige' agent's tile from its running reward; the static tile atlas cannot: refuse loudly
-    instead of returning pixels that differ from the reference's (encoded observations only carry the colour index: exact)."""
-    from marlgrid_b200 import envs
-    from marlgrid_b200.agents import GridAgentInterface
+def test_prestige_tile_arithmetic():
+    """agents.py:92-119 + blend_tiles base.py:260-273 on the white atlas tile: the host-side composition used by env.render()
+    (the device kernels' version is checked against the reference's frames in the GPU suite)."""
+    from marlgrid_b200.atlas import build_atlas
+    from marlgrid_b200.render import prestige_colour, prestige_tile
 
-    with pytest.raises(NotImplementedError, match="prestige"):
-        envs.ClutteredMultiGrid(agents=[GridAgentInterface(color="prestige")], grid_size=9, n_clutter=3, obs_mode="rgb", device="cpu")
+    assert list(prestige_colour(0.0, 2.0, False)) == [255, 0, 0] and list(prestige_colour(50.0, 2.0, False)) == [0, 0, 255]
+    assert list(prestige_colour(0.0, 2.0, True)) == [127, 0, 127]
+    at = build_atlas([12], 8)[:, 0]  # one agent, coloured 'prestige' = white (objects.py:24)
+    col = prestige_colour(1.0, 2.0, False)
+    t = prestige_tile(at, 0, 1, 5, col)  # on an empty cell, facing right
+    alpha = at[1][..., 0].astype(np.int64)
+    assert np.array_equal(t[..., 0], (alpha * col[0]) >> 8) and not t[..., 1].any() and np.array_equal(t[..., 2], (alpha * col[2]) >> 8)
+    g = prestige_tile(at, 2, 1, 5, col)  # over the Goal: green where the triangle is absent
+    assert tuple(g[0, 0]) == (0, 255, 0) and g[..., 1].min() < 255
 
 
 def test_grid_recorder_on_a_host_env(tmp_path):

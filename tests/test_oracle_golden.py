@@ -151,6 +151,7 @@ def test_render_composition_against_reference_frames(oracle):
 
         planes = property(lambda self: torch.from_numpy(self.ob.planes().copy()))
         agent_rec = property(lambda self: torch.from_numpy(self.ob.agents.copy()))
+        prestige = property(lambda self: torch.from_numpy(self.ob.prestige.copy()))
 
     def views(env, index=0):
         c = env.cfg
