@@ -227,6 +227,35 @@ class RenderRecorder(val.LockStep):
         return d
 
 
+def gen_rich():
+    """rich_<scenario>.npz: the observation dicts of observation_style='rich' agents (base.py:461-471: pov, reward, position,
+    orientation) after a reset and every step, recorded from the reference."""
+    rng = np.random.RandomState(31337)
+    agents = [dict(color=c, view_size=7, view_tile_size=8, observation_style="rich", observe_rewards=True, observe_position=True,
+                   observe_orientation=True) for c in ("red", "blue", "purple")]
+    seed, env_index = 2718, 44
+    env = rh.make_env(env_class="EmptyMultiGrid", agents=agents, grid_size=7, max_steps=30, seed=seed, env_index=env_index)
+    ev = []
+
+    def snap(kind, actions, obs):
+        ev.append(dict(kind=kind, actions=np.zeros(3, np.int32) if actions is None else np.asarray(actions, np.int32),
+                       pov=np.stack([np.asarray(o["pov"]).astype(np.uint8) for o in obs]), reward=np.array([o["reward"] for o in obs], np.float64),
+                       position=np.stack([np.asarray(o["position"], np.float64) for o in obs]), orientation=np.array([o["orientation"] for o in obs], np.int64)))
+
+    snap(0, None, rh.ref_reset(env))
+    for t in range(70):
+        act = rng.randint(0, 7, size=3)
+        act[rng.rand(3) < 0.5] = 2
+        obs, rew, done, _ = rh.ref_step(env, act)
+        snap(1, act, obs)
+        if done:
+            snap(0, None, rh.ref_reset(env))
+    cfg = val.config_from_ref_env(env)
+    np.savez_compressed(os.path.join(OUT, "rich_Empty7x7x3.npz"), meta=np.frombuffer(json.dumps(cfg_kwargs(cfg, seed, env_index)).encode(), dtype=np.uint8),
+                        **{k: np.stack([e[k] for e in ev]) for k in ("kind", "actions", "pov", "reward", "position", "orientation")})
+    print(f"  rich_Empty7x7x3.npz                              {len(ev)} events")
+
+
 def gen_render_extra():
     """render_<scenario>.npz for scenarios of validate_against_reference.EXTRA (own RNG stream): 'prestige' agents in the whole-grid view."""
     rng = np.random.RandomState(1177)
@@ -282,6 +311,7 @@ if __name__ == "__main__":
     elif "extra" in sys.argv[1:]:
         gen_extra_trajectories()
         gen_render_extra()
+        gen_rich()
     else:
         gen_los()
         gen_atlas()
@@ -290,3 +320,4 @@ if __name__ == "__main__":
         gen_extra_trajectories()
         gen_render()
         gen_render_extra()
+        gen_rich()

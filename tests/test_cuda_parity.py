@@ -419,24 +419,36 @@ def test_unbatched_gym_surface():
         env.step([2])
 
 
-def test_rich_observation_style():
-    """observation_style='rich' (marlgrid/base.py:461-471): dict of batched tensors / list of per-agent dicts."""
+def test_rich_observation_style_matches_reference():
+    """observation_style='rich' (marlgrid/base.py:461-471): the dict of batched tensors against the dicts the reference returned
+    (tests/golden/rich_*.npz, recorded by oracle/gen_golden.py gen_rich), event by event."""
+    import json
+
     from marlgrid_b200.agents import GridAgentInterface
     from marlgrid_b200.envs import EmptyMultiGrid
 
-    ags = [GridAgentInterface(color=c, view_size=7, view_tile_size=8, observation_style="rich", observe_rewards=True,
-                              observe_position=True, observe_orientation=True) for c in ("red", "blue")]
-    env = EmptyMultiGrid(agents=ags, grid_size=9, num_envs=64, obs_mode="rgb", seed=3)
-    obs = env.reset()
-    assert set(obs) == {"pov", "reward", "position", "orientation"} and tuple(obs["pov"].shape) == (64, 2, 56, 56, 3)
-    for t in range(20):
-        obs, rew, done, _ = env.step(env.random_actions(t))
-        pos = env.agent_pos.cpu().numpy() / np.array([9, 9], dtype=float)  # numpy true division, like base.py:467
-        assert np.array_equal(obs["position"].cpu().numpy(), pos) and torch.equal(obs["orientation"], env.agent_dir.long())
-        assert int(obs["reward"].abs().sum().item()) == 0
-    one = EmptyMultiGrid(agents=[a.clone() for a in ags], grid_size=9, num_envs=1, obs_mode="rgb", seed=3).unbatched()
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "rich_Empty7x7x3.npz"))
+    meta = json.loads(bytes(z["meta"]).decode())
+    c = meta["config"]
+    from marlgrid_b200.objects import IDX_TO_COLOR
+
+    ags = [GridAgentInterface(color=IDX_TO_COLOR[ci], view_size=c["view_size"], view_tile_size=c["view_tile_size"], observation_style="rich",
+                              observe_rewards=True, observe_position=True, observe_orientation=True) for ci in c["agent_colors"]]
+    env = EmptyMultiGrid(agents=ags, grid_size=c["width"], max_steps=c["max_steps"], num_envs=1, obs_mode="rgb", seed=meta["seed"],
+                         env_offset=meta["env_index"], autoreset=False)
+    for i, kind in enumerate(z["kind"]):
+        if kind == 0:
+            obs = env.reset()
+        else:
+            obs, rew, done, _ = env.step(torch.from_numpy(z["actions"][i][None].astype(np.int32)).cuda())
+        assert set(obs) == {"pov", "reward", "position", "orientation"}
+        assert np.array_equal(obs["pov"][0].cpu().numpy(), z["pov"][i]), f"event {i}: pov"
+        assert np.array_equal(obs["position"][0].cpu().numpy().view(np.uint64), z["position"][i].view(np.uint64)), f"event {i}: position bits"
+        assert np.array_equal(obs["orientation"][0].cpu().numpy(), z["orientation"][i]), f"event {i}: orientation"
+        assert np.array_equal(obs["reward"][0].cpu().numpy().astype(np.float64), z["reward"][i]), f"event {i}: reward"
+    one = EmptyMultiGrid(agents=[a.clone() for a in ags], grid_size=7, num_envs=1, obs_mode="rgb", seed=3).unbatched()
     lst = one.reset()
-    assert isinstance(lst, list) and len(lst) == 2 and set(lst[0]) == {"pov", "reward", "position", "orientation"}
+    assert isinstance(lst, list) and len(lst) == 3 and set(lst[0]) == {"pov", "reward", "position", "orientation"}
     assert tuple(lst[0]["pov"].shape) == (56, 56, 3) and tuple(lst[1]["position"].shape) == (2,)
 
 
