@@ -286,6 +286,14 @@ def main():
         run_reference(args, rank, world)
         return
 
+    if world > 1:
+        # communicator lines (rank / nranks) stay visible for the driver, but on stderr: stdout carries the JSON line.  Set before
+        # torch is imported: NCCL reads its debug settings once.
+        if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):  # (this image presets NCCL_DEBUG=VERSION)
+            os.environ["NCCL_DEBUG"] = "INFO"
+            os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
     import ctypes
 
     import numpy as np
@@ -301,10 +309,6 @@ def main():
 
         dist = dist_mod
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # communicator lines (rank / nranks) stay visible for the driver, but on stderr: stdout carries the JSON line
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
-        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
     B, K, W = args.batch_per_gpu, args.steps, args.warmup
