@@ -412,11 +412,11 @@ __device__ __forceinline__ void tile_resets(const KP& p, uint32_t* s_flag, uint3
         } else if (fails >= NT) open = false;  // left to the sequential code
       }
       const uint32_t still = __ballot_sync(0xFFFFFFFFu, open);
-      if (lane == 0) *s_pending = still;
+      if (lane == 0) s_pending[chunk & 1] = still;  // two slots: a warp may read this chunk's word while warp 0 is already replaying the next chunk
       if (A == 1 && still != 0u && chunk + 1 < MAXCH) fill(chunk + 1, still, next_table, tid, 32);  // single-warp CTAs: no one to overlap with
     }
     __syncthreads();
-    pending = *s_pending;
+    pending = s_pending[chunk & 1];
     if (pending == 0u) break;
   }
   __syncthreads();  // the table and s_pending alias the sequential code's scratch: nobody may still be reading them
