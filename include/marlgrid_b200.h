@@ -241,6 +241,34 @@ int mg_rollout_fused(const MgConfig* cfg, const MgState* st, const int32_t* acti
 int mg_rollout_persistent(const MgConfig* cfg, const MgState* st, const int32_t* actions, int64_t n_steps,
                           double* rewards, uint8_t* done, uint8_t* obs, int autoreset, mg_stream_t stream);
 
+/* ON-DEVICE POLICY HAND-OFF (the caller loop of README.md:43-57 `act = agents.action_step(obs);
+ * obs, rew, done, _ = env.step(act)` without leaving the GPU): a closed-loop rollout of n_steps steps in which step t + 1 plays the
+ * actions a built-in policy chose from the observations of step t.  The policy is one int8 linear layer per agent over the
+ * encoded observation (exact integer arithmetic): action = argmax_k (bias[a][k] + sum_i weights[a][k][i] * obs[i]), lowest k on
+ * ties, k < n_actions; with probability epsilon / 2^32 a uniform action instead (Philox block keyed by `seed`, counter =
+ * (global env index, lifetime step, agent)).  For the registered shapes and batches whose tiles fit the resident CTAs this is
+ * ONE launch (the persistent rollout kernel evaluates the policy on the observation tile while it is still in shared memory);
+ * otherwise one step launch + one policy launch per step.
+ *   weights : device, int8, packed for the kernels as [A][NW][8][4]: byte b of word i of action k's row = w[a][k][4 i + b],
+ *             NW = ceil(V*V*3 / 4), zero beyond the observation and for k >= n_actions (marlgrid_b200.policy packs it)
+ *   bias    : device, int32 [A][8]
+ *   actions : int32 [n_steps][B][A]: row 0 = the first step's actions, given by the caller; rows 1.. are WRITTEN (the actions
+ *             played at every step, for the learner); rewards / done / obs: per-step slices as for mg_rollout_persistent
+ * Batches that are not a multiple of 16 envs (per-step slices off the 16-byte grid) take the launch-per-step route. */
+typedef struct MgLinearPolicy {
+  const int8_t* weights;
+  const int32_t* bias;
+  int32_t n_actions;
+  uint32_t epsilon;
+  uint64_t seed;
+} MgLinearPolicy;
+int mg_rollout_policy(const MgConfig* cfg, const MgState* st, const MgLinearPolicy* policy, int64_t n_steps, int32_t* actions,
+                      double* rewards, uint8_t* done, uint8_t* obs, int autoreset, mg_stream_t stream);
+
+/* The policy alone, for a host loop: actions int32 [B][A] <- what the policy chooses from obs uint8 [B][A][V][V][3] (the encoded
+ * observations of the step just played; exploration draws are keyed by the envs' lifetime step counters in `st`). */
+int mg_policy_act(const MgConfig* cfg, const MgState* st, const MgLinearPolicy* policy, const uint8_t* obs, int32_t* actions, mg_stream_t stream);
+
 /* The same driver over n_states independent env families of equal size, visited round robin: step t advances family
  * t % n_states with actions[t] and writes that family's rewards[r] / done[r] / obs[r].  With enough families the working
  * set exceeds the L2 cache, which is how bench.py times cold steps back to back (no flush kernel in between). */

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(HERE, "libmarlgrid_b200.so")
 
 EXPORTS = (
     "mg_version", "mg_build_info", "mg_sizeof_config", "mg_config_validate", "mg_obs_bytes_per_env", "mg_init", "mg_sync_derived", "mg_reset", "mg_step",
-    "mg_obs_encode", "mg_obs_rgb", "mg_step_fused", "mg_step_fused_rgb", "mg_rollout_fused", "mg_rollout_persistent", "mg_rollout_fused_rr", "mg_random_actions",
+    "mg_obs_encode", "mg_obs_rgb", "mg_step_fused", "mg_step_fused_rgb", "mg_rollout_fused", "mg_rollout_persistent", "mg_rollout_policy", "mg_policy_act", "mg_rollout_fused_rr", "mg_random_actions",
     "mg_los_batch", "mg_engine_create", "mg_engine_destroy", "mg_engine_reset", "mg_engine_step", "mg_engine_copy_only", "mg_host_alloc",
     "mg_host_free", "mg_launch_count", "mg_pregen_words_per_env", "mg_pregen_run", "mg_pregen_drain", "mg_pregen_set_auto", "mg_pregen_stats", "mg_debug_set_mid_event", "mg_debug_force_two_kernels", "mg_debug_force_general_fused",
 )
@@ -65,6 +65,8 @@ def load():
     L.mg_step_fused_rgb.argtypes = [CFG, ST, P, P, P, P, P, I, P]
     L.mg_rollout_fused.argtypes = [CFG, ST, P, I64, P, P, P, I, P]
     L.mg_rollout_persistent.argtypes = [CFG, ST, P, I64, P, P, P, I, P]
+    L.mg_rollout_policy.argtypes = [CFG, ST, P, I64, P, P, P, P, I, P]
+    L.mg_policy_act.argtypes = [CFG, ST, P, P, P, P]
     L.mg_rollout_fused_rr.argtypes = [CFG, ST, I, P, I64, P, P, P, I, P]
     L.mg_random_actions.argtypes = [P, I64, I, U64, U64, P]
     L.mg_los_batch.argtypes = [P, P, I64, I, I, I, P]

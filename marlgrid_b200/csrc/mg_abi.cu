@@ -155,6 +155,28 @@ static int check_state(const MgConfig* c, const MgState* st) {
   return 0;
 }
 
+// The K-steps-per-launch entries outside the persistent kernel's reach: one step launch (+ one policy launch) per step on the
+// per-step slices.  The kernels store observations as 16-byte vectors; a slice that starts off that grid (batches that are
+// not a multiple of 16 envs) is produced in a stream-ordered scratch buffer and copied into place.
+static int rollout_step_by_step(const MgConfig* cfg, const MgState* st, const KP& p, int64_t n_steps, bool closed_loop, cudaStream_t s) {
+  const int64_t na = st->n_envs * cfg->n_agents, no = mg_obs_bytes_per_env(cfg, 0) * st->n_envs;
+  uint8_t* scratch = nullptr;
+  if (no % 16 != 0) MG_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&scratch), (size_t)no, s));
+  int e = 0;
+  for (int64_t t = 0; t < n_steps && !e; ++t) {
+    KP q = p;
+    uint8_t* const slice = p.obs + t * no;
+    const bool direct = (reinterpret_cast<uintptr_t>(slice) & 15u) == 0;
+    q.actions = p.actions + t * na; q.rewards = p.rewards + t * na; q.done = p.done + t * st->n_envs; q.obs = direct ? slice : scratch;
+    q.pol_w = nullptr;
+    e = launch_step_obs(q, 1, s);
+    if (!e && !direct) e = (int)cudaMemcpyAsync(slice, scratch, (size_t)no, cudaMemcpyDeviceToDevice, s);
+    if (!e && closed_loop && t + 1 < n_steps) e = launch_policy(p, slice, const_cast<int32_t*>(p.actions) + (t + 1) * na, s);
+  }
+  if (scratch) cudaFreeAsync(scratch, s);
+  return e;
+}
+
 extern "C" {
 
 int mg_version(void) { return 1; }
@@ -304,13 +326,37 @@ int mg_rollout_persistent(const MgConfig* cfg, const MgState* st, const int32_t*
     e = launch_fused2_rollout(p, (int)n_steps, (cudaStream_t)stream);  // ONE launch, the tiles' state stays in shared memory
     if (e != MG_E_UNSUPPORTED) return e;
   }
-  const int64_t na = st->n_envs * cfg->n_agents, no = mg_obs_bytes_per_env(cfg, 0) * st->n_envs;
-  for (int64_t t = 0; t < n_steps; ++t) {  // shapes / batch sizes outside the persistent kernel's reach: step by step
-    p.actions = actions + t * na; p.rewards = rewards + t * na; p.done = done + t * st->n_envs; p.obs = obs + t * no;
-    e = launch_step_obs(p, 1, (cudaStream_t)stream);
-    if (e) return e;
+  return rollout_step_by_step(cfg, st, p, n_steps, false, (cudaStream_t)stream);  // shapes / batch sizes outside the persistent kernel's reach
+}
+
+// Closed-loop rollout on the device: step t + 1 plays the actions the policy chose from step t's observations (see the header).
+int mg_rollout_policy(const MgConfig* cfg, const MgState* st, const MgLinearPolicy* pol, int64_t n_steps, int32_t* actions, double* rewards,
+                      uint8_t* done, uint8_t* obs, int autoreset, mg_stream_t stream) {
+  int e = check_state(cfg, st);
+  if (e) return e;
+  if (!pol || !pol->weights || !pol->bias || pol->n_actions < 1 || pol->n_actions > 7) return MG_E_ARG;
+  if (!actions || !rewards || !done || !obs || !aligned16(obs) || !aligned16(pol->weights) || !aligned16(pol->bias) || n_steps < 0 || n_steps > 0x7FFFFFFF) return MG_E_ARG;
+  if (n_steps == 0 || st->n_envs == 0) return 0;
+  KP p = make_kp(cfg, st);
+  p.actions = actions; p.rewards = rewards; p.done = done; p.obs = obs; p.autoreset = autoreset;
+  p.pol_w = reinterpret_cast<const int32_t*>(pol->weights); p.pol_b = pol->bias; p.pol_n = pol->n_actions; p.pol_eps = pol->epsilon; p.pol_seed = pol->seed;
+  if (!g_force_two_kernels && !g_force_general_fused) {
+    e = launch_fused2_rollout(p, (int)n_steps, (cudaStream_t)stream);  // ONE launch: state and policy hand-off stay on the SMs
+    if (e != MG_E_UNSUPPORTED) return e;
   }
-  return 0;
+  return rollout_step_by_step(cfg, st, p, n_steps, true, (cudaStream_t)stream);  // a step launch + a policy launch per step
+}
+
+// The policy alone: actions the policy chooses from `obs` (the observations of the step just played) -- what the host loop
+// `act = agents.action_step(obs)` (README.md:43-57) calls between two steps.
+int mg_policy_act(const MgConfig* cfg, const MgState* st, const MgLinearPolicy* pol, const uint8_t* obs, int32_t* actions, mg_stream_t stream) {
+  int e = check_state(cfg, st);
+  if (e) return e;
+  if (!pol || !pol->weights || !pol->bias || pol->n_actions < 1 || pol->n_actions > 7 || !aligned16(pol->weights) || !aligned16(pol->bias) || !obs || !actions) return MG_E_ARG;
+  if (st->n_envs == 0) return 0;
+  KP p = make_kp(cfg, st);
+  p.pol_w = reinterpret_cast<const int32_t*>(pol->weights); p.pol_b = pol->bias; p.pol_n = pol->n_actions; p.pol_eps = pol->epsilon; p.pol_seed = pol->seed;
+  return launch_policy(p, obs, actions, (cudaStream_t)stream);
 }
 
 int mg_rollout_fused_rr(const MgConfig* cfg, const MgState* states, int n_states, const int32_t* actions, int64_t n_steps,

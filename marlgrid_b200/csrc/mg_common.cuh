@@ -64,6 +64,12 @@ struct KP {
   uint32_t* pregen;  // MgState.pregen: pre-generated next worlds [B][64] (mg_world.cuh) or nullptr
   int ax0, ay0, aw, ah, amax;  // agent spawn box [ax0, ax0 + aw) x [ay0, ay0 + ah) and max_tries (agent_spawn_kwargs, base.py:690-696)
   int scenario;                // MG_SCENARIO_*
+  // on-device policy of the persistent rollout (mg_rollout_policy): int8 linear layer over the encoded observation
+  const int32_t* pol_w;        // [A][NW][8] words: word i (4 observation bytes) of action k's weight row, NW = ceil(V*V*3 / 4)
+  const int32_t* pol_b;        // [A][8]
+  int pol_n;                   // number of actions the policy chooses from (1..7)
+  uint32_t pol_eps;            // exploration probability * 2^32
+  unsigned long long pol_seed;
   double* prestige;            // MgState.prestige [B][A] or nullptr
   uint32_t prestige_mask, prestige_neg;  // agents coloured 'prestige' / with allow_negative_prestige
   double pbeta[MG_MAX_AGENTS], pscale[MG_MAX_AGENTS];
@@ -143,6 +149,7 @@ bool fused_eligible(const KP& p);
 constexpr int MG_E_UNSUPPORTED = -100;                          // internal: the specialised kernel has no instantiation for this shape
 int launch_fused2(const KP& p, int obs, cudaStream_t s);        // mg_fused2.cu: specialised (compile-time A, V) one-launch step+observe
 int launch_fused2_rollout(const KP& p, int n_steps, cudaStream_t s);
+int launch_policy(const KP& p, const uint8_t* obs, int32_t* actions_next, cudaStream_t s);  // mg_env_kernels.cu: the linear policy as a kernel of its own
 int launch_pregen(const KP& p, cudaStream_t s);                 // mg_pregen.cu: one pass of the background world generator over the family
 cudaStream_t pregen_stream();                                   // its low-priority side stream on the current device  // the same kernel playing n_steps steps per launch (per-step output slices)
 

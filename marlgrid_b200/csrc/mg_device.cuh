@@ -29,6 +29,7 @@ __device__ __forceinline__ U4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c
   return U4{c0, c1, c2, c3};
 }
 
+constexpr uint32_t TAG_POLICY = 0x20000000u;  // exploration draws of the on-device policy (mg_rollout_policy)
 constexpr uint32_t TAG_RESET = 0x80000000u;
 constexpr uint32_t TAG_INSTEP = 0x40000000u;
 

@@ -1,6 +1,7 @@
 // mg_env_kernels.cu -- per-env kernels (one THREAD per env, world state in place in global memory) and the small
 // utility kernels (init, synthetic actions, line-of-sight known-answer).
 #include "mg_env.cuh"
+#include "mg_world.cuh"
 
 namespace mg {
 
@@ -103,6 +104,43 @@ static int launch_env_mode(const KP& p, cudaStream_t s) {
   } else {
     if (p.cellbits) env_kernel<MODE, true, MG_MAX_AGENTS><<<(unsigned)blocks, ENV_THREADS, sm, s>>>(p);
     else env_kernel<MODE, false, MG_MAX_AGENTS><<<(unsigned)blocks, ENV_THREADS, sm, s>>>(p);
+  }
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+// The policy of mg_rollout_policy as a kernel of its own (batches whose tiles do not all fit the resident CTAs of the
+// persistent rollout kernel are stepped launch by launch): thread = (env, agent); observations of the step just played ->
+// actions of the next step.
+template <int NW>
+__global__ void policy_kernel(const __grid_constant__ KP p, const uint8_t* __restrict__ obs, int32_t* __restrict__ actions_next) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.B * p.A) return;
+  const long long env = i / p.A;
+  const int a = (int)(i - env * p.A);
+  const uint8_t* o = obs + i * (p.V * p.V * 3);
+  const int n_bytes = p.V * p.V * 3;
+  actions_next[i] = world::linear_policy_action<NW>(p, a, (unsigned long long)(p.env_offset + env), (uint32_t)p.envrec[env * 4 + 2], [&](int w) {
+    uint32_t v = 0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+      if (4 * w + b < n_bytes) v |= (uint32_t)o[4 * w + b] << (8 * b);
+    return v;
+  });
+}
+
+int launch_policy(const KP& p, const uint8_t* obs, int32_t* actions_next, cudaStream_t s) {
+  const long long n = p.B * p.A;
+  if (n <= 0) return 0;
+  const unsigned blocks = (unsigned)((n + 127) / 128);
+  switch (p.V) {
+    case 3: policy_kernel<7><<<blocks, 128, 0, s>>>(p, obs, actions_next); break;
+    case 4: policy_kernel<12><<<blocks, 128, 0, s>>>(p, obs, actions_next); break;
+    case 5: policy_kernel<19><<<blocks, 128, 0, s>>>(p, obs, actions_next); break;
+    case 6: policy_kernel<27><<<blocks, 128, 0, s>>>(p, obs, actions_next); break;
+    case 7: policy_kernel<37><<<blocks, 128, 0, s>>>(p, obs, actions_next); break;
+    case 8: policy_kernel<48><<<blocks, 128, 0, s>>>(p, obs, actions_next); break;
+    default: return MG_E_CONFIG;
   }
   count_launch();
   return (int)cudaGetLastError();

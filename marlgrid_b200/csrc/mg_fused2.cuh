@@ -647,7 +647,7 @@ __global__ void __launch_bounds__(32 * A, ctas_per_sm<OBS, V, A, NST>()) fused2_
   }
 
   int action = MG_A_DONE;
-  if ((KS || !full) && mine) action = act_g[env * A + a];
+  if ((KS || !full) && mine) action = KS ? __ldcg(act_g + env * A + a) : act_g[env * A + a];  // (KS: the policy hand-off below may have written it a step ago)
   if (!KS || step == 0) mbar_wait(s_bar + stage, KS ? 0u : (uint32_t)((it / NST) & 1));
   if (!KS && full) action = s_act[lane * A + a];
 
@@ -962,6 +962,20 @@ __global__ void __launch_bounds__(32 * A, ctas_per_sm<OBS, V, A, NST>()) fused2_
   }
   fence_proxy_async_smem();  // writer side of the generic -> async proxy hand-over: every thread's shared-memory writes of this
   __syncthreads();           // tile (observations, records, rewards ...) are ordered before the bulk copies issued below
+
+  // ---- policy hand-off (mg_rollout_policy): the action of the NEXT step from the observation this thread has just written ----
+  if (KS && OBS == 1 && p.pol_w != nullptr && mine && step + 1 < n_steps) {
+    constexpr int NW = (VV3 + 3) / 4;
+    const uint32_t base_s = out_s & ~3u, sh = (out_s & 3u) * 8u;  // a view starts at any byte: aligned words + funnel shift
+    const uint32_t last_s = smem_u32(s_out) + (uint32_t)SM::OUT_BYTES - 4u;  // the last word of the tile
+    const int nxt = world::linear_policy_action<NW>(p, a, (unsigned long long)(p.env_offset + env), (uint32_t)s_env[lane * 4 + 2], [&](int i) {
+      uint32_t lo, hi;
+      asm("ld.shared.u32 %0, [%1];" : "=r"(lo) : "r"(base_s + 4u * (uint32_t)i));
+      asm("ld.shared.u32 %0, [%1];" : "=r"(hi) : "r"(min(base_s + 4u * (uint32_t)i + 4u, last_s)));  // (clamped: beyond the view only zero-weight bytes matter)
+      return __funnelshift_r(lo, hi, sh);
+    });
+    const_cast<int32_t*>(p.actions)[(long long)(step + 1) * p.B * A + env * A + a] = nxt;
+  }
 
   // ---- everything leaves as contiguous chunks; nobody waits for them here ----
   if (full) {

@@ -26,6 +26,36 @@ __device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// The on-device policy of mg_rollout_policy: action = argmax_k (bias[k] + sum_i w[k][i] * obs[i]) over the agent's encoded
+// observation (uint8) with int8 weights -- exact integer arithmetic (dp4a), lowest k wins ties -- or, with probability
+// eps / 2^32, a uniform action from the Philox block (g, lifetime step, TAG_POLICY | agent) keyed by the policy's seed.
+// `word(i)` returns observation bytes 4i .. 4i+3 (bytes beyond the observation must read as anything: their weights are 0).
+template <int NW, class WordFn>
+__device__ __forceinline__ int linear_policy_action(const KP& p, int a, unsigned long long g, uint32_t t_life, WordFn word) {
+  int acc[8];
+  const int4* const bias = reinterpret_cast<const int4*>(p.pol_b + a * 8);
+  const int4 b0 = __ldg(bias), b1 = __ldg(bias + 1);
+  acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w; acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
+  const int4* const w = reinterpret_cast<const int4*>(p.pol_w + (size_t)a * NW * 8);
+#pragma unroll 4
+  for (int i = 0; i < NW; ++i) {
+    const uint32_t o = word(i);
+    const int4 w0 = __ldg(w + 2 * i), w1 = __ldg(w + 2 * i + 1);  // the same address in every lane of the warp (warp = agent)
+    const int ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) asm("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(acc[k]) : "r"(o), "r"(ww[k]));
+  }
+  int best = 0;
+#pragma unroll
+  for (int k = 1; k < 8; ++k)
+    if (k < p.pol_n && acc[k] > acc[best]) best = k;
+  if (p.pol_eps != 0u) {
+    const U4 r = philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), t_life, TAG_POLICY | (uint32_t)a, (uint32_t)p.pol_seed, (uint32_t)(p.pol_seed >> 32));
+    if (r.x < p.pol_eps) best = (int)__umulhi(r.y, (uint32_t)p.pol_n);
+  }
+  return best;
+}
+
 // Transpose of two 16x16 bit matrices at once: lane r < 16 holds row r of matrix 0 in bits 0..15 and row r of matrix 1 in
 // bits 16..31; returns, in lane c < 16, column c of both the same way.  Four butterfly stages (block swaps of 8, 4, 2, 1).
 __device__ __forceinline__ uint32_t transpose16x16_pair(uint32_t v, int lane) {

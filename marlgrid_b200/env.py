@@ -312,6 +312,45 @@ class BatchedMultiGridEnv:
                 self.obs.copy_(obs[-1]); self.rewards.copy_(rew[-1]); self.done.copy_(done[-1])
             return obs, rew, done
 
+    def rollout_policy(self, policy, first_actions, n_steps, out=None):
+        """Closed-loop rollout on the device (mg_rollout_policy; the loop of the reference's README.md:43-57 without the host):
+        step 0 plays `first_actions` int32 [B, A], step t + 1 the actions `policy` (marlgrid_b200.policy.LinearPolicy) chooses
+        from step t's observations.  Returns (obs [T, B, A, V, V, 3], rewards [T, B, A], done [T, B], actions [T, B, A]) of
+        every step; one kernel launch when the batch fits the resident CTAs of the rollout kernel.  `out` = the four tensors."""
+        with torch.cuda.device(self.device):
+            if self.obs_mode != "encoded":
+                raise NotImplementedError("rollout_policy() drives the encoded-obs path")
+            T, B, A, V = int(n_steps), self.num_envs, self.cfg.n_agents, self.cfg.view_size
+            if policy.n_agents != A or policy.view_size != V:
+                raise ValueError(f"policy is for {policy.n_agents} agents with view {policy.view_size}, env has {A} / {V}")
+            if out is None:
+                out = (torch.empty((T, B, A, V, V, 3), dtype=torch.uint8, device=self.device), torch.empty((T, B, A), dtype=torch.float64, device=self.device),
+                       torch.empty((T, B), dtype=torch.bool, device=self.device), torch.empty((T, B, A), dtype=torch.int32, device=self.device))
+            obs, rew, done, act = out
+            assert act.shape == (T, B, A) and act.dtype == torch.int32 and act.is_contiguous()
+            if T:
+                act[0].copy_(torch.as_tensor(first_actions, device=self.device).to(torch.int32).reshape(B, A))
+            pol, keep = policy.device_struct(self.device)
+            _lib.check(self._lib.mg_rollout_policy(ctypes.byref(self.cfg), ctypes.byref(self._state), ctypes.byref(pol), T, act.data_ptr(), rew.data_ptr(),
+                                                   done.data_ptr(), obs.data_ptr(), int(self.autoreset), self._stream()), "mg_rollout_policy")
+            if T:
+                self.obs.copy_(obs[-1]); self.rewards.copy_(rew[-1]); self.done.copy_(done[-1])
+            return obs, rew, done, act
+
+    def policy_act(self, policy, obs=None, out=None):
+        """Actions int32 [B, A] the LinearPolicy chooses from `obs` (default: the observations of the last step / reset) --
+        `agents.action_step(obs)` of the reference's loop as one kernel launch (mg_policy_act)."""
+        with torch.cuda.device(self.device):
+            if self.obs_mode != "encoded":
+                raise NotImplementedError("LinearPolicy reads encoded observations")
+            obs = self.obs if obs is None else obs
+            assert obs.dtype == torch.uint8 and obs.is_contiguous() and obs.numel() == self.obs.numel()
+            if out is None:
+                out = torch.empty((self.num_envs, self.cfg.n_agents), dtype=torch.int32, device=self.device)
+            pol, keep = policy.device_struct(self.device)
+            _lib.check(self._lib.mg_policy_act(ctypes.byref(self.cfg), ctypes.byref(self._state), ctypes.byref(pol), obs.data_ptr(), out.data_ptr(), self._stream()), "mg_policy_act")
+            return out
+
     def random_actions(self, counter, n_actions=7, seed=0, out=None):
         """Uniform synthetic policy on the device; `counter` selects the draw."""
         with torch.cuda.device(self.device):

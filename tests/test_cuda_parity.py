@@ -508,7 +508,8 @@ def test_previous_observation_survives_the_next_step():
     assert o1.data_ptr() == o0.data_ptr()
 
 
-@pytest.mark.parametrize("env_id,B", [("MarlGrid-3AgentCluttered15x15-v0", 4096), ("MarlGrid-2AgentEmpty9x9-v0", 1008), ("MarlGrid-4AgentEmpty9x9-v0", 65536 + 32)])
+@pytest.mark.parametrize("env_id,B", [("MarlGrid-3AgentCluttered15x15-v0", 4096), ("MarlGrid-2AgentEmpty9x9-v0", 1008), ("MarlGrid-4AgentEmpty9x9-v0", 65536 + 32),
+                                       ("MarlGrid-3AgentCluttered11x11-v0", 1001)])  # (1001: per-step slices off the 16-byte grid -> launch per step through a scratch buffer)
 def test_persistent_rollout_equals_step_by_step(env_id, B):
     """mg_rollout_persistent: T steps in one launch (state resident in shared memory) == T calls of env.step, every step's
     outputs compared; the last case does not fit the resident CTAs and takes the step-by-step fallback; resets included."""
@@ -526,3 +527,67 @@ def test_persistent_rollout_equals_step_by_step(env_id, B):
         assert torch.equal(obs[t], o) and torch.equal(rew[t], r) and torch.equal(done[t], d), f"step {t}"
     assert torch.equal(a.grid, b.grid) and torch.equal(a.envrec, b.envrec) and torch.equal(a.cellbits, b.cellbits)
     assert torch.equal(a.agent_rec[:, :, :12], b.agent_rec[:, :, :12]) and int(a.episode.min().item()) >= 2
+
+
+@pytest.mark.parametrize("env_id,B,eps,impl", [
+    ("MarlGrid-3AgentCluttered15x15-v0", 4096, 0.0, "fused"),
+    ("MarlGrid-3AgentCluttered15x15-v0", 1000, 0.25, "fused"),       # ragged last tile, exploration draws
+    ("MarlGrid-3AgentCluttered11x11-v0", 777, 0.1, "fused"),
+    ("MarlGrid-2AgentEmpty9x9-v0", 333, 0.5, "fused"),
+    ("MarlGrid-3AgentCluttered15x15-v0", 300, 0.25, "general_fused"),  # step launch + policy launch per step
+    ("MarlGrid-3AgentCluttered15x15-v0", 300, 0.25, "two_kernels"),
+    ("MarlGrid-4AgentEmpty9x9-v0", 65536 + 32, 0.05, "fused"),        # more tiles than resident CTAs: the per-step fallback
+])
+def test_policy_rollout_closed_loop_vs_oracle(cuda_lib, oracle, env_id, B, eps, impl):
+    """mg_rollout_policy: step t + 1 plays what the on-device policy chose from step t's observations -- compared step by step
+    (observations, reward bits, done, the actions played, final state) with the oracle closing the same loop on the CPU."""
+    from marlgrid_b200 import envs
+    from marlgrid_b200.policy import LinearPolicy
+    from oracle import policy_oracle
+
+    cuda_lib.mg_debug_force_two_kernels(1 if impl == "two_kernels" else 0)
+    cuda_lib.mg_debug_force_general_fused(1 if impl == "general_fused" else 0)
+    try:
+        T = 40 if B > 5000 else 115
+        env = envs.make(env_id, num_envs=B, obs_mode="encoded", seed=77, env_offset=5)
+        env.reset()
+        A, V = env.cfg.n_agents, env.cfg.view_size
+        pol = LinearPolicy.random(A, V, n_actions=7, epsilon=eps, seed=0xABCDEF0123, rng_seed=B)
+        ob = oracle.OracleBatch(env.cfg, B, seed=77, env_offset=5, threads=8)
+        ob.reset()
+        first = np.random.RandomState(B).randint(0, 7, size=(B, A)).astype(np.int32)
+        obs, rew, done, act = env.rollout_policy(pol, first, T)
+        torch.cuda.synchronize()
+        o2, r2, d2, a2 = policy_oracle.closed_loop(ob, pol, first, T)
+        act, obs, rew, done = act.cpu().numpy(), obs.cpu().numpy(), rew.cpu().numpy(), done.cpu().numpy()
+        for t in range(T):
+            assert np.array_equal(act[t], a2[t]), f"step {t}: actions differ at {np.argwhere(act[t] != a2[t])[:4]}"
+            assert np.array_equal(obs[t], o2[t]), f"step {t}: obs"
+            assert np.array_equal(rew[t].view(np.uint64), r2[t].view(np.uint64)), f"step {t}: rewards"
+            assert np.array_equal(done[t], d2[t].astype(bool)), f"step {t}: done"
+        _state_equal(env, ob, "after the closed loop")
+        assert len(np.unique(act[1:])) >= 3  # (the policy is not degenerate)
+        if T > 100:
+            assert int(env.episode.min().item()) >= 2  # crossed the auto-reset
+    finally:
+        cuda_lib.mg_debug_force_two_kernels(0)
+        cuda_lib.mg_debug_force_general_fused(0)
+
+
+def test_policy_act_host_loop_vs_oracle(cuda_lib, oracle):
+    """mg_policy_act between two env.step calls (the reference's README loop with the policy as a kernel) == the CPU statement."""
+    from marlgrid_b200 import envs
+    from marlgrid_b200.policy import LinearPolicy
+    from oracle import policy_oracle
+
+    B = 515
+    env = envs.make("MarlGrid-3AgentCluttered11x11-v0", num_envs=B, obs_mode="encoded", seed=3)
+    obs = env.reset()
+    pol = LinearPolicy.random(3, 7, n_actions=3, epsilon=0.3, seed=11, rng_seed=1)  # restrict_actions-style: 3 actions
+    g = np.arange(B)
+    for t in range(30):
+        act = env.policy_act(pol, obs)
+        want = policy_oracle.linear_policy_actions(obs.cpu().numpy(), pol.weights, pol.bias, 3, pol.epsilon_u32, pol.seed, g, env.envrec[:, 2].cpu().numpy())
+        assert np.array_equal(act.cpu().numpy(), want), f"step {t}"
+        assert int(act.max()) <= 2
+        obs, _, _, _ = env.step(act)

@@ -305,3 +305,44 @@ def test_shard_ranges_partition_the_batch():
         for (o1, c1), (o2, _) in zip(spans, spans[1:]):
             assert o1 + c1 == o2
     assert shard_range(1048576, 3, 8) == (3 * 131072, 131072)
+
+
+def test_policy_packing_and_cpu_statement():
+    """marlgrid_b200.policy packs int8 weights as [A][NW][8][4] for the kernels; the oracle's vectorised Philox equals the
+    scalar statement of the RNG contract; the CPU policy statement takes the lowest maximal action and explores as specified."""
+    from marlgrid_b200.policy import LinearPolicy, epsilon_to_u32, n_obs_words, pack_bias, pack_weights
+    from oracle import philox, policy_oracle
+
+    A, V, K = 3, 7, 5
+    n = V * V * 3
+    rng = np.random.RandomState(4)
+    w = rng.randint(-128, 128, size=(A, K, n)).astype(np.int8)
+    pw = pack_weights(w, V)
+    assert pw.shape == (A, n_obs_words(V), 8, 4) and pw.dtype == np.int8
+    for a, k, i in [(0, 0, 0), (1, 3, 77), (2, 4, n - 1)]:
+        assert pw[a, i // 4, k, i % 4] == w[a, k, i]
+    assert not pw[:, :, K:, :].any() and pw[:, -1, :, (n % 4):].any() == 0 if n % 4 else True
+    assert pack_bias([[1, 2, 3, 4, 5]] * A, A, K).tolist() == [[1, 2, 3, 4, 5, 0, 0, 0]] * A
+    assert epsilon_to_u32(0.0) == 0 and epsilon_to_u32(1.0) == 0xFFFFFFFF and epsilon_to_u32(0.5) == 1 << 31
+    with pytest.raises(ValueError):
+        pack_weights(np.full((A, K, n), 300), V)
+    with pytest.raises(ValueError):
+        LinearPolicy(np.zeros((A, 8, n), np.int8))
+    # vectorised Philox == scalar statement
+    c = rng.randint(0, 2**32, size=(4, 50), dtype=np.uint64)
+    got = policy_oracle.philox4x32_10_np(c[0], c[1], c[2], c[3], 0x12345678, 0x9ABCDEF0)
+    for j in range(50):
+        assert tuple(int(x[j]) for x in got) == philox.philox4x32_10(tuple(int(c[q][j]) for q in range(4)), (0x12345678, 0x9ABCDEF0))
+    # the policy statement: ties -> lowest k; epsilon = 1 -> always the uniform draw
+    obs = rng.randint(0, 12, size=(6, A, V, V, 3)).astype(np.uint8)
+    zero = np.zeros((A, K, n), np.int8)
+    act = policy_oracle.linear_policy_actions(obs, zero, np.array([[0, 5, 5, 1, 5]] * A, np.int32), K, 0, 0, np.arange(6), np.zeros(6, np.int64))
+    assert (act == 1).all()
+    g, t = np.arange(6) + 100, np.arange(6) + 9
+    act = policy_oracle.linear_policy_actions(obs, zero, np.zeros((A, K), np.int32), K, 0xFFFFFFFF, 99, g, t)
+    for b in range(6):
+        for a in range(A):
+            r = philox.philox4x32_10((int(g[b]), 0, int(t[b]), 0x20000000 | a), (99, 0))
+            assert act[b, a] == (philox.mulhi32(r[1], K) if r[0] < 0xFFFFFFFF else 0)
+    want = (obs.reshape(6, A, -1).astype(np.int64)[:, :, None, :] * w.astype(np.int64)[None]).sum(-1)
+    assert np.array_equal(policy_oracle.linear_policy_actions(obs, w, np.zeros((A, K), np.int32), K, 0, 0, g, t), want.argmax(-1))

@@ -156,3 +156,9 @@ if [[ " $what " == *" final "* ]]; then
   cat gpurun_out/bench.json
   timeout 40 python tools/desync_probe.py > gpurun_out/desync.log 2>&1; tail -8 gpurun_out/desync.log
 fi
+if [[ " $what " == *" policy "* ]]; then
+  # closed-loop rollout with the on-device policy: parity against the CPU statement, then its cost next to the open-loop kernel
+  timeout 600 python -m pytest tests -m gpu -x -q -k "policy or persistent_rollout" > gpurun_out/tests_policy.log 2>&1; echo "policy tests exit $?" | tee -a gpurun_out/tests_policy.log
+  tail -15 gpurun_out/tests_policy.log
+  timeout 300 python tools/policy_probe.py 2>&1 | tee gpurun_out/policy_probe.log
+fi
