@@ -535,6 +535,54 @@ __device__ __noinline__ void rare_path(const KP& p, const int tile, const int st
 
 }  // namespace f2
 
+// ---------------------------------------------------------------------------------------------
+// on-device policy of the K-steps-per-launch kernel (mg_rollout_policy)
+// ---------------------------------------------------------------------------------------------
+namespace f2 {
+constexpr int POL_MAX_A = 4, POL_MAX_NW = 37;  // the K-steps-per-launch instantiations: A <= 4, V <= 7
+// The packed weights [A][NW][8 actions] words and biases [A][8] of the launch in flight, copied here by launch_fused2_ks
+// (stream-ordered): every lane of a warp multiplies by the same weight, so the weight is a constant-bank operand of the
+// dp4a itself -- no load instruction, no register, no latency to hide.
+static __constant__ int4 c_pol_w[POL_MAX_A * POL_MAX_NW * 2];
+static __constant__ int4 c_pol_b[POL_MAX_A * 2];
+
+// action of agent Q (a constant once the caller's loop is unrolled) from the encoded view at shared address base_s (word aligned; the view starts sh / 8 bytes in)
+template <int NW>
+__device__ __forceinline__ int policy_from_tile(const KP& p, const int Q, unsigned long long g, uint32_t t_life, uint32_t base_s, uint32_t sh, uint32_t last_s) {
+  static_assert(NW <= POL_MAX_NW, "policy constants");
+  int acc[8];
+  {
+    const int4 b0 = c_pol_b[Q * 2], b1 = c_pol_b[Q * 2 + 1];
+    acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w; acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
+  }
+  uint32_t lo;
+  // (volatile + "memory": these loads read what the observe phase has just stored through ordinary pointers -- without the
+  // clobber the compiler may schedule an asm load, a pure function of its address in its eyes, above those stores)
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(lo) : "r"(base_s) : "memory");
+#pragma unroll
+  for (int i = 0; i < NW; ++i) {
+    uint32_t hi;
+    const uint32_t ha = base_s + 4u * (uint32_t)i + 4u;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(hi) : "r"(i == NW - 1 ? min(ha, last_s) : ha) : "memory");  // (clamped: beyond the view only zero-weight bytes matter)
+    const uint32_t o = __funnelshift_r(lo, hi, sh);
+    lo = hi;
+    const int4 w0 = c_pol_w[(Q * NW + i) * 2], w1 = c_pol_w[(Q * NW + i) * 2 + 1];
+    const int ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) asm("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(acc[k]) : "r"(o), "r"(ww[k]));
+  }
+  int best = 0;
+#pragma unroll
+  for (int k = 1; k < 8; ++k)
+    if (k < p.pol_n && acc[k] > acc[best]) best = k;
+  if (p.pol_eps != 0u) {
+    const U4 r = philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), t_life, TAG_POLICY | (uint32_t)Q, (uint32_t)p.pol_seed, (uint32_t)(p.pol_seed >> 32));
+    if (r.x < p.pol_eps) best = (int)__umulhi(r.y, (uint32_t)p.pol_n);
+  }
+  return best;
+}
+}  // namespace f2
+
 template <int OBS, int V, int A, int NST>
 constexpr int ctas_per_sm() {  // shared-memory / thread limited residency the register allocation should allow
   constexpr int by_smem = (227 * 1024) / (f2::Smem<OBS, V, A, NST>::TOTAL + (OBS == 2 ? 11 * 1024 : 0) + 1024), by_threads = 64 / A;
@@ -964,16 +1012,14 @@ __global__ void __launch_bounds__(32 * A, ctas_per_sm<OBS, V, A, NST>()) fused2_
   __syncthreads();           // tile (observations, records, rewards ...) are ordered before the bulk copies issued below
 
   // ---- policy hand-off (mg_rollout_policy): the action of the NEXT step from the observation this thread has just written ----
-  if (KS && OBS == 1 && p.pol_w != nullptr && mine && step + 1 < n_steps) {
+  if constexpr (KS && OBS == 1) if (p.pol_w != nullptr && mine && step + 1 < n_steps) {
     constexpr int NW = (VV3 + 3) / 4;
     const uint32_t base_s = out_s & ~3u, sh = (out_s & 3u) * 8u;  // a view starts at any byte: aligned words + funnel shift
     const uint32_t last_s = smem_u32(s_out) + (uint32_t)SM::OUT_BYTES - 4u;  // the last word of the tile
-    const int nxt = world::linear_policy_action<NW>(p, a, (unsigned long long)(p.env_offset + env), (uint32_t)s_env[lane * 4 + 2], [&](int i) {
-      uint32_t lo, hi;
-      asm("ld.shared.u32 %0, [%1];" : "=r"(lo) : "r"(base_s + 4u * (uint32_t)i));
-      asm("ld.shared.u32 %0, [%1];" : "=r"(hi) : "r"(min(base_s + 4u * (uint32_t)i + 4u, last_s)));  // (clamped: beyond the view only zero-weight bytes matter)
-      return __funnelshift_r(lo, hi, sh);
-    });
+    int nxt = 0;
+#pragma unroll
+    for (int q = 0; q < A; ++q)  // warp = agent: with the agent a compile-time constant the weights are constant-bank operands
+      if (a == q) nxt = f2::policy_from_tile<NW>(p, q, (unsigned long long)(p.env_offset + env), (uint32_t)s_env[lane * 4 + 2], base_s, sh, last_s);
     const_cast<int32_t*>(p.actions)[(long long)(step + 1) * p.B * A + env * A + a] = nxt;
   }
 
@@ -1159,7 +1205,13 @@ int launch_fused2_ov(const KP& p, cudaStream_t s) {
 // K steps per launch (encoded observations, view_offset 0, A <= 4: the registered MarlGrid-* shapes)
 template <int V>
 int launch_fused2_ks(const KP& p, int n_steps, cudaStream_t s) {
-  if (p.vo != 0) return MG_E_UNSUPPORTED;
+  if (p.vo != 0 || p.A > f2::POL_MAX_A) return MG_E_UNSUPPORTED;
+  if (p.pol_w != nullptr) {  // the policy's weights and biases into constant memory, ordered on the stream before the launch
+    constexpr int NW = (V * V * 3 + 3) / 4;
+    cudaError_t e = cudaMemcpyToSymbolAsync(f2::c_pol_w, p.pol_w, (size_t)p.A * NW * 32, 0, cudaMemcpyDeviceToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyToSymbolAsync(f2::c_pol_b, p.pol_b, (size_t)p.A * 32, 0, cudaMemcpyDeviceToDevice, s);
+    if (e != cudaSuccess) return (int)e;
+  }
   switch (p.A) {
     case 1: return launch_one<1, V, 1, true, 2, true>(p, s, n_steps);
     case 2: return launch_one<1, V, 2, true, 2, true>(p, s, n_steps);

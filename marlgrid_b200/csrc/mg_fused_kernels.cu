@@ -225,12 +225,13 @@ __global__ void __launch_bounds__(32 * MG_MAX_AGENTS, 4) fused_kernel(const __gr
   }
   __syncthreads();
 
+  // own record: publish the head flag (a barrier of its own: the neighbours' observe phase reads this word -- they take the
+  // head flags from s_head and ignore the bit, but racecheck rightly calls an unordered write/read pair a hazard)
+  if (mine) rec[a * 4] = s_head[tid] ? (rec[a * 4] | (AF_HEAD << 24)) : (rec[a * 4] & ~(AF_HEAD << 24));
+  __syncthreads();
+
   // ---- phase 5: observe the post-step world ----
-  if (mine) {
-    // own record: publish the head flag (other threads take head flags from s_head and ignore this bit)
-    rec[a * 4] = s_head[tid] ? (rec[a * 4] | (AF_HEAD << 24)) : (rec[a * 4] & ~(AF_HEAD << 24));
-    obs_view<OBS, V, true, true>(p, o, tid, a, env, rec, tp, bits, s_head + le * A);
-  }
+  if (mine) obs_view<OBS, V, true, true>(p, o, tid, a, env, rec, tp, bits, s_head + le * A);
   fence_proxy_async_smem();  // writer side of the generic -> async proxy hand-over for the bulk copies issued after the barrier
   __syncthreads();
   obs_emit<OBS, V, TSC>(p, o, env0, n_valid, tid, nthreads);

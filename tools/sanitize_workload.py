@@ -1,7 +1,8 @@
 """Small workload for compute-sanitizer (tools/gpu_check.sh sanitize): every path of the specialised fused kernel --
 encoded and RGB observation, full and ragged tiles, more tiles than CTAs' first round, the all-reset step (table-driven
 reset), desynchronised episodes (warp-cooperative reset of a few envs per tile), a world so cluttered that placement runs
-fail and fall through to the sequential reset, objects whose pickup / toggle replays an env sequentially, K steps per launch."""
+fail and fall through to the sequential reset, objects whose pickup / toggle replays an env sequentially, K steps per launch, the
+on-device policy hand-off."""
 import os
 import sys
 
@@ -47,6 +48,14 @@ for t in range(40):
 ks = envs.make("MarlGrid-3AgentCluttered15x15-v0", num_envs=96, obs_mode="encoded", seed=4, max_steps=11)
 ks.reset()
 ks.rollout_all(torch.stack([ks.random_actions(t) for t in range(25)]))
+# closed loop: the policy evaluated on the observation tile inside the kernel (ragged last tile), and the launch-per-step route
+from marlgrid_b200.policy import LinearPolicy  # noqa: E402
+
+pol = LinearPolicy.random(3, 7, n_actions=7, epsilon=0.2, seed=9)
+ks.rollout_policy(pol, ks.random_actions(99), 25)
+odd = envs.make("MarlGrid-3AgentCluttered11x11-v0", num_envs=41, obs_mode="encoded", seed=4, max_steps=11)
+odd.reset()
+odd.rollout_policy(pol, odd.random_actions(99), 14)
 torch.cuda.synchronize()
 for e in (des, dense, ks):
     assert int((e.err & ~2).max().item()) == 0  # (MG_ERR_PLACEMENT may legitimately appear in the dense world)
