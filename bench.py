@@ -541,6 +541,52 @@ def main():
                                         "note": "on-device rollout loop (mg_rollout_persistent): 100 steps per launch on a fixed action tape, tile state resident in "
                                                 "shared memory between steps, every step's obs / rewards / done written to HBM (informational: open-loop)"}
 
+        # ---- closed loop on the device: the policy (int8 linear layer + epsilon-greedy) evaluated inside the rollout kernel ----
+        from marlgrid_b200.policy import LinearPolicy
+
+        pol = LinearPolicy.random(A, 7, n_actions=7, epsilon=0.1, seed=5)
+        qout = (torch.empty((TP, B, A, 7, 7, 3), dtype=torch.uint8, device=dev), torch.empty((TP, B, A), dtype=torch.float64, device=dev),
+                torch.empty((TP, B), dtype=torch.bool, device=dev), torch.empty((TP, B, A), dtype=torch.int32, device=dev))
+        env.rollout_policy(pol, actions[0], TP, out=qout)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            env.rollout_policy(pol, actions[0], TP, out=qout)
+        e1.record()
+        barrier()
+        policy_ms = max_over_ranks([e0.elapsed_time(e1) / (5 * TP)])[0]
+        del qout
+        extras["rollout_policy"] = {"value": world * B / (policy_ms * 1e-3), "ms_per_step": policy_ms, "steps_per_launch": TP,
+                                    "note": "closed-loop rollout (mg_rollout_policy): step t+1 plays the actions an int8 linear policy (7 actions, epsilon 0.1) chose from "
+                                            "step t's observations, evaluated on the observation tile inside the rollout kernel; every step's obs / rewards / done / actions written"}
+
+        # ---- env kwargs off the specialised shape (general fused kernel / step kernel + observe kernel): parity-tested, here timed ----
+        feats = {}
+        from marlgrid_b200.agents import GridAgentInterface
+
+        for name, akw, ekw in (("hide_item_types=['wall']", {"hide_item_types": ["wall"]}, {}), ("ghost_mode=False", {}, {"ghost_mode": False}),
+                               ("respawn=True", {}, {"respawn": True}), ("see_through_walls=True", {"see_through_walls": True}, {})):
+            try:
+                fe = envs.ClutteredMultiGrid(agents=[GridAgentInterface(color=c, view_size=7, view_tile_size=8, **akw) for c in ("red", "blue", "purple")],
+                                             grid_size=15, clutter_density=0.15, num_envs=B, obs_mode="encoded", seed=1337, env_offset=rank * B, device=dev, **ekw)
+                fe.reset()
+                fe.rollout(actions[:20])
+                l0 = L.mg_launch_count()
+                barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                fe.rollout(actions[:100])
+                fe.rollout(actions[:100])
+                e1.record()
+                barrier()
+                f_ms = max_over_ranks([e0.elapsed_time(e1) / 200])[0]
+                feats[name] = {"value": world * B / (f_ms * 1e-3), "ms_per_step": f_ms, "launches_per_step": (L.mg_launch_count() - l0) / 200.0}
+                del fe
+            except Exception as ex:  # noqa: BLE001 -- informational section: report, do not fail the bench line
+                feats[name] = {"error": repr(ex)}
+        extras["feature_paths"] = dict(feats, note="cfg3 with one env kwarg changed, 200 warm steps enqueued from C on one family (compare `warm`)")
+
         # ---- the same warm steps through the Python surface, env.step(actions) called in a Python loop -------------------
         KP_ = max(K, 500)
         barrier()

@@ -346,3 +346,35 @@ def test_policy_packing_and_cpu_statement():
             assert act[b, a] == (philox.mulhi32(r[1], K) if r[0] < 0xFFFFFFFF else 0)
     want = (obs.reshape(6, A, -1).astype(np.int64)[:, :, None, :] * w.astype(np.int64)[None]).sum(-1)
     assert np.array_equal(policy_oracle.linear_policy_actions(obs, w, np.zeros((A, K), np.int32), K, 0, 0, g, t), want.argmax(-1))
+
+
+def test_linear_q_learner_protocol_and_quantisation():
+    """marlgrid_b200.learners: the learner protocol of README.md:21-25 on batched tensors, TD(0) updates that fit a synthetic
+    batch, and the int8 hand-off to the rollout kernel (the quantised policy picks the float model's greedy action)."""
+    import torch
+
+    from marlgrid_b200 import IndependentLearners
+    from marlgrid_b200.learners import LinearQLearner, quantized_policy
+    from oracle import policy_oracle
+
+    rng = np.random.RandomState(0)
+    learners = IndependentLearners(*[LinearQLearner(view_size=7, epsilon=0.0, seed=k, color=c) for k, c in enumerate(("red", "blue"))])
+    obs = torch.from_numpy(rng.randint(0, 14, size=(64, 2, 7, 7, 3)).astype(np.uint8))
+    act = learners.action_step(obs)
+    assert act.shape == (64, 2) and act.dtype == torch.int32 and int(act.max()) < 7
+    nxt = torch.from_numpy(rng.randint(0, 14, size=(64, 2, 7, 7, 3)).astype(np.uint8))
+    rew = torch.from_numpy((rng.rand(64, 2) < 0.2).astype(np.float64))
+    with learners.episode():
+        learners.save_step(obs, act, nxt, rew, torch.zeros(64, dtype=torch.bool))
+        assert len(learners[0].buffer) == 1
+    assert learners[0].buffer == []  # end_episode consumed it in an update
+    l0 = learners[0]
+    first = l0.update(obs[:, 0], act[:, 0], nxt[:, 0], rew[:, 0], torch.zeros(64, dtype=torch.bool))
+    for _ in range(200):
+        last = l0.update(obs[:, 0], act[:, 0], nxt[:, 0], rew[:, 0], torch.ones(64, dtype=torch.bool))  # done: the target is the reward
+    assert last < 0.1 * first
+    pol = quantized_policy(list(learners), epsilon=0.0)
+    assert pol.weights.dtype == np.int8 and np.abs(pol.weights).max(axis=(1, 2)).tolist() == [127, 127]
+    greedy = torch.stack([l.q_values(obs[:, k]).argmax(-1) for k, l in enumerate(learners)], dim=1).numpy()
+    got = policy_oracle.linear_policy_actions(obs.numpy(), pol.weights, pol.bias, 7, 0, 0, np.arange(64), np.zeros(64, np.int64))
+    assert (got == greedy).mean() > 0.9  # (int8 rounding may flip near-ties)

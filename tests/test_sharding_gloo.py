@@ -80,3 +80,61 @@ def test_two_rank_shards_equal_unsharded_batch(oracle):
     assert np.array_equal(np.concatenate([g[2] for g in gathered]), full.grid)
     assert np.array_equal(np.concatenate([g[3] for g in gathered]), full.envrec)
     assert abs(mean_return - ret.mean()) < 1e-12
+
+
+def _synthetic_transitions(n, seed):
+    rng = np.random.RandomState(seed)
+    obs = rng.randint(0, 14, size=(n, 7, 7, 3)).astype(np.uint8)
+    nxt = rng.randint(0, 14, size=(n, 7, 7, 3)).astype(np.uint8)
+    act = rng.randint(0, 7, size=(n,)).astype(np.int32)
+    rew = (rng.rand(n) < 0.1).astype(np.float64)
+    done = rng.rand(n) < 0.05
+    return obs, act, nxt, rew, done
+
+
+def _learner_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+
+    from marlgrid_b200.learners import LinearQLearner
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    learner = LinearQLearner(view_size=7, seed=3)
+    o, a, n, r, d = (torch.from_numpy(x) for x in _synthetic_transitions(512, 9))
+    half = slice(rank * 256, (rank + 1) * 256)  # each rank learns from its own envs' transitions
+    for _ in range(5):
+        learner.update(o[half], a[half], n[half], r[half], d[half])
+    w = [None] * world
+    dist.all_gather_object(w, (learner.W.detach().numpy().copy(), learner.b.detach().numpy().copy()))
+    if rank == 0:
+        out.put(w)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_learner_gradient_allreduce():
+    """LinearQLearner.update under torch.distributed (gloo here, NCCL on the GPU box): both ranks end with the same weights,
+    equal to one process learning from the whole batch -- the system's only collective, off the env data path."""
+    import torch
+    import torch.multiprocessing as mp
+
+    from marlgrid_b200.learners import LinearQLearner
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_learner_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    w = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert np.array_equal(w[0][0], w[1][0]) and np.array_equal(w[0][1], w[1][1])
+    single = LinearQLearner(view_size=7, seed=3)
+    o, a, n, r, d = (torch.from_numpy(x) for x in _synthetic_transitions(512, 9))
+    for _ in range(5):
+        single.update(o, a, n, r, d)
+    assert np.allclose(w[0][0], single.W.detach().numpy(), atol=2e-5) and np.allclose(w[0][1], single.b.detach().numpy(), atol=2e-5)

@@ -158,7 +158,8 @@ if [[ " $what " == *" final "* ]]; then
 fi
 if [[ " $what " == *" policy "* ]]; then
   # closed-loop rollout with the on-device policy: parity against the CPU statement, then its cost next to the open-loop kernel
-  timeout 600 python -m pytest tests -m gpu -x -q -k "policy or persistent_rollout" > gpurun_out/tests_policy.log 2>&1; echo "policy tests exit $?" | tee -a gpurun_out/tests_policy.log
+  timeout 600 python -m pytest tests -m gpu -x -q -k "policy or persistent_rollout or trainer" > gpurun_out/tests_policy.log 2>&1; echo "policy tests exit $?" | tee -a gpurun_out/tests_policy.log
   tail -15 gpurun_out/tests_policy.log
   timeout 300 python tools/policy_probe.py 2>&1 | tee gpurun_out/policy_probe.log
+  timeout 300 python tools/train_linear_q.py 150 16384 2>&1 | tee gpurun_out/train_linear_q.log
 fi
