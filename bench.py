@@ -565,7 +565,7 @@ def main():
         feats = {}
         from marlgrid_b200.agents import GridAgentInterface
 
-        for name, akw, ekw in (("hide_item_types=['wall']", {"hide_item_types": ["wall"]}, {}), ("ghost_mode=False", {}, {"ghost_mode": False}),
+        for name, akw, ekw in (("hide_item_types=['Goal']", {"hide_item_types": ["Goal"]}, {}), ("ghost_mode=False", {}, {"ghost_mode": False}),
                                ("respawn=True", {}, {"respawn": True}), ("see_through_walls=True", {"see_through_walls": True}, {})):
             try:
                 fe = envs.ClutteredMultiGrid(agents=[GridAgentInterface(color=c, view_size=7, view_tile_size=8, **akw) for c in ("red", "blue", "purple")],

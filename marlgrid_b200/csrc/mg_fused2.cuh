@@ -24,6 +24,7 @@
 // Everything here is integer work on the ALU/LSU pipes; the path has no dense contraction, hence no tensor cores.
 // Launch-shape knobs for experiments: MG_F2_CTAS_PER_SM=n, MG_F2_PDL=0, MG_F2_RAGGED=1, MG_F2_VERBOSE=1.
 #pragma once
+#include <climits>
 #include <cstdlib>
 
 #include "mg_env.cuh"
@@ -538,48 +539,100 @@ __device__ __noinline__ void rare_path(const KP& p, const int tile, const int st
 // ---------------------------------------------------------------------------------------------
 // on-device policy of the K-steps-per-launch kernel (mg_rollout_policy)
 // ---------------------------------------------------------------------------------------------
+// The policy is a small integer GEMM per warp and step: [32 envs of the tile] x [V*V*3 observation bytes] times
+// [V*V*3] x [8 actions] (warp = agent).  It runs on the tensor cores as mma.sync m16n8k32 (u8 x s8 -> s32, exact): two row
+// tiles of 16 envs, ceil(V*V*3 / 32) k-steps; the A fragments come straight from the observation tile in shared memory (a view
+// starts at any byte: two aligned words + a funnel shift per fragment register), the B fragments (weights) from a
+// per-launch table laid out fragment by fragment.  10 MMAs replace the 296 dp4a per THREAD of a thread-per-view dot product.
 namespace f2 {
-constexpr int POL_MAX_A = 4, POL_MAX_NW = 37;  // the K-steps-per-launch instantiations: A <= 4, V <= 7
-// The packed weights [A][NW][8 actions] words and biases [A][8] of the launch in flight, copied here by launch_fused2_ks
-// (stream-ordered): every lane of a warp multiplies by the same weight, so the weight is a constant-bank operand of the
-// dp4a itself -- no load instruction, no register, no latency to hide.
-static __constant__ int4 c_pol_w[POL_MAX_A * POL_MAX_NW * 2];
-static __constant__ int4 c_pol_b[POL_MAX_A * 2];
+constexpr int POL_MAX_A = 4, POL_MAX_KSTEPS = 5;  // the K-steps-per-launch instantiations: A <= 4, V <= 7
+// B fragments of the launch in flight: [A][k-step][register 0/1][lane] -- register j of k-step ks in lane (g = lane / 4, t = lane % 4)
+// holds weight bytes k = 32 ks + 16 j + 4 t .. + 3 of action g.  Written by pack_policy_fragments, stream-ordered before the launch.
+static __device__ uint32_t d_pol_frag[POL_MAX_A * POL_MAX_KSTEPS * 2 * 32];
 
-// action of agent Q (a constant once the caller's loop is unrolled) from the encoded view at shared address base_s (word aligned; the view starts sh / 8 bytes in)
-template <int NW>
-__device__ __forceinline__ int policy_from_tile(const KP& p, const int Q, unsigned long long g, uint32_t t_life, uint32_t base_s, uint32_t sh, uint32_t last_s) {
-  static_assert(NW <= POL_MAX_NW, "policy constants");
-  int acc[8];
+// pol_w: the C ABI's layout [A][NW][8 actions] words (word i of action n = weight bytes 4 i .. 4 i + 3)
+static __global__ void pack_policy_fragments(const int32_t* __restrict__ pol_w, int A, int NW, int ksteps) {
+  for (int idx = threadIdx.x; idx < A * ksteps * 64; idx += blockDim.x) {
+    const int lane = idx & 31, j = (idx >> 5) & 1, ks = (idx >> 6) % ksteps, a = (idx >> 6) / ksteps;
+    const int i = ks * 8 + j * 4 + (lane & 3), n = lane >> 2;
+    d_pol_frag[idx] = i < NW ? (uint32_t)pol_w[(a * NW + i) * 8 + n] : 0u;
+  }
+}
+
+__device__ __forceinline__ void mma_u8s8(int (&c)[4], const uint32_t (&af)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3]) : "r"(af[0]), "r"(af[1]), "r"(af[2]), "r"(af[3]), "r"(b0), "r"(b1));
+}
+
+// Actions of the tile's 32 envs for agent a (the whole warp takes part: mma.sync), written to `act_next` [env][A].
+// s_out_u32: shared address of the observation tile [env][A][VV3]; last_s: its last aligned word (loads are clamped there: only
+// zero-weight bytes lie beyond a view).
+template <int VV3, int A>
+__device__ __forceinline__ void policy_tile_mma(const KP& p, int a, int lane, uint32_t s_out_u32, uint32_t last_s, const int32_t* s_env,
+                                                long long env0, int n_valid, int32_t* act_next) {
+  constexpr int KSTEPS = (VV3 + 31) / 32;
+  static_assert(KSTEPS <= POL_MAX_KSTEPS && A <= POL_MAX_A, "policy fragments");
+  const int g = lane >> 2, t4 = lane & 3;
+  int c[2][4];
   {
-    const int4 b0 = c_pol_b[Q * 2], b1 = c_pol_b[Q * 2 + 1];
-    acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w; acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
-  }
-  uint32_t lo;
-  // (volatile + "memory": these loads read what the observe phase has just stored through ordinary pointers -- without the
-  // clobber the compiler may schedule an asm load, a pure function of its address in its eyes, above those stores)
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(lo) : "r"(base_s) : "memory");
+    const int2 b = __ldg(reinterpret_cast<const int2*>(p.pol_b + a * 8) + t4);  // accumulators start at the bias of columns 2 t, 2 t + 1
 #pragma unroll
-  for (int i = 0; i < NW; ++i) {
-    uint32_t hi;
-    const uint32_t ha = base_s + 4u * (uint32_t)i + 4u;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(hi) : "r"(i == NW - 1 ? min(ha, last_s) : ha) : "memory");  // (clamped: beyond the view only zero-weight bytes matter)
-    const uint32_t o = __funnelshift_r(lo, hi, sh);
-    lo = hi;
-    const int4 w0 = c_pol_w[(Q * NW + i) * 2], w1 = c_pol_w[(Q * NW + i) * 2 + 1];
-    const int ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-#pragma unroll
-    for (int k = 0; k < 8; ++k) asm("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(acc[k]) : "r"(o), "r"(ww[k]));
+    for (int mt = 0; mt < 2; ++mt) { c[mt][0] = b.x; c[mt][1] = b.y; c[mt][2] = b.x; c[mt][3] = b.y; }
   }
-  int best = 0;
+  uint32_t base[2][2], sh[2][2];
 #pragma unroll
-  for (int k = 1; k < 8; ++k)
-    if (k < p.pol_n && acc[k] > acc[best]) best = k;
-  if (p.pol_eps != 0u) {
-    const U4 r = philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), t_life, TAG_POLICY | (uint32_t)Q, (uint32_t)p.pol_seed, (uint32_t)(p.pol_seed >> 32));
-    if (r.x < p.pol_eps) best = (int)__umulhi(r.y, (uint32_t)p.pol_n);
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {  // fragment rows g and g + 8 of row tile mt = envs 16 mt + 8 h + g
+      const uint32_t b = s_out_u32 + (uint32_t)(((mt * 16 + h * 8 + g) * A + a) * VV3 + t4 * 4);
+      base[mt][h] = b & ~3u; sh[mt][h] = (b & 3u) * 8u;
+    }
+  const uint32_t* const frag = d_pol_frag + a * (KSTEPS * 64) + lane;
+#pragma unroll
+  for (int ks = 0; ks < KSTEPS; ++ks) {
+    const uint32_t b0 = frag[ks * 64], b1 = frag[ks * 64 + 32];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      uint32_t af[4];
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {  // a0: (row g, k 0..15)  a1: (row g + 8, k 0..15)  a2: (row g, k 16..31)  a3: (row g + 8, k 16..31)
+          uint32_t lo_a = base[mt][h] + (uint32_t)(ks * 32 + j * 16), hi_a = lo_a + 4u, lo, hi;
+          if (ks == KSTEPS - 1) { lo_a = min(lo_a, last_s); hi_a = min(hi_a, last_s); }
+          // (volatile + "memory": these loads read what the observe phase has just stored through ordinary pointers)
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(lo) : "r"(lo_a) : "memory");
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(hi) : "r"(hi_a) : "memory");
+          af[j * 2 + h] = __funnelshift_r(lo, hi, sh[mt][h]);
+        }
+      mma_u8s8(c[mt], af, b0, b1);
+    }
   }
-  return best;
+  // argmax over the 8 columns of every row, lowest column on ties, columns >= pol_n excluded: key = 8 logit + (7 - column)
+  long long best[2][2];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const long long k0 = (long long)c[mt][2 * h] * 8 + (7 - 2 * t4), k1 = (long long)c[mt][2 * h + 1] * 8 + (6 - 2 * t4);
+      long long k = (2 * t4 < p.pol_n) ? k0 : LLONG_MIN;
+      if (2 * t4 + 1 < p.pol_n && k1 > k) k = k1;
+      k = max(k, __shfl_xor_sync(0xFFFFFFFFu, k, 1));
+      k = max(k, __shfl_xor_sync(0xFFFFFFFFu, k, 2));
+      best[mt][h] = k;
+    }
+  // the quad's four lanes share out its four rows
+  const long long mine_k = (t4 & 2) ? ((t4 & 1) ? best[1][1] : best[1][0]) : ((t4 & 1) ? best[0][1] : best[0][0]);
+  const int row = (t4 >> 1) * 16 + (t4 & 1) * 8 + g;
+  if (row < n_valid) {
+    int act = 7 - (int)(mine_k & 7);
+    if (p.pol_eps != 0u) {
+      const unsigned long long gidx = (unsigned long long)(p.env_offset + env0 + row);
+      const U4 r = philox4x32_10((uint32_t)gidx, (uint32_t)(gidx >> 32), (uint32_t)s_env[row * 4 + 2], TAG_POLICY | (uint32_t)a, (uint32_t)p.pol_seed, (uint32_t)(p.pol_seed >> 32));
+      if (r.x < p.pol_eps) act = (int)__umulhi(r.y, (uint32_t)p.pol_n);
+    }
+    act_next[(env0 + row) * A + a] = act;
+  }
 }
 }  // namespace f2
 
@@ -1011,16 +1064,11 @@ __global__ void __launch_bounds__(32 * A, ctas_per_sm<OBS, V, A, NST>()) fused2_
   fence_proxy_async_smem();  // writer side of the generic -> async proxy hand-over: every thread's shared-memory writes of this
   __syncthreads();           // tile (observations, records, rewards ...) are ordered before the bulk copies issued below
 
-  // ---- policy hand-off (mg_rollout_policy): the action of the NEXT step from the observation this thread has just written ----
-  if constexpr (KS && OBS == 1) if (p.pol_w != nullptr && mine && step + 1 < n_steps) {
-    constexpr int NW = (VV3 + 3) / 4;
-    const uint32_t base_s = out_s & ~3u, sh = (out_s & 3u) * 8u;  // a view starts at any byte: aligned words + funnel shift
-    const uint32_t last_s = smem_u32(s_out) + (uint32_t)SM::OUT_BYTES - 4u;  // the last word of the tile
-    int nxt = 0;
-#pragma unroll
-    for (int q = 0; q < A; ++q)  // warp = agent: with the agent a compile-time constant the weights are constant-bank operands
-      if (a == q) nxt = f2::policy_from_tile<NW>(p, q, (unsigned long long)(p.env_offset + env), (uint32_t)s_env[lane * 4 + 2], base_s, sh, last_s);
-    const_cast<int32_t*>(p.actions)[(long long)(step + 1) * p.B * A + env * A + a] = nxt;
+  // ---- policy hand-off (mg_rollout_policy): the actions of the NEXT step from the observation tile just written ----
+  if constexpr (KS && OBS == 1 && A <= f2::POL_MAX_A) {
+    if (p.pol_w != nullptr && step + 1 < n_steps)  // (uniform: every lane takes part in the MMAs, ragged tiles included)
+      f2::policy_tile_mma<VV3, A>(p, a, lane, smem_u32(s_out), smem_u32(s_out) + (uint32_t)SM::OUT_BYTES - 4u, s_env, env0, n_valid,
+                                  const_cast<int32_t*>(p.actions) + (long long)(step + 1) * p.B * A);
   }
 
   // ---- everything leaves as contiguous chunks; nobody waits for them here ----
@@ -1206,11 +1254,12 @@ int launch_fused2_ov(const KP& p, cudaStream_t s) {
 template <int V>
 int launch_fused2_ks(const KP& p, int n_steps, cudaStream_t s) {
   if (p.vo != 0 || p.A > f2::POL_MAX_A) return MG_E_UNSUPPORTED;
-  if (p.pol_w != nullptr) {  // the policy's weights and biases into constant memory, ordered on the stream before the launch
-    constexpr int NW = (V * V * 3 + 3) / 4;
-    cudaError_t e = cudaMemcpyToSymbolAsync(f2::c_pol_w, p.pol_w, (size_t)p.A * NW * 32, 0, cudaMemcpyDeviceToDevice, s);
-    if (e == cudaSuccess) e = cudaMemcpyToSymbolAsync(f2::c_pol_b, p.pol_b, (size_t)p.A * 32, 0, cudaMemcpyDeviceToDevice, s);
+  if (p.pol_w != nullptr) {  // the policy's weights as MMA B fragments, ordered on the stream before the launch
+    constexpr int NW = (V * V * 3 + 3) / 4, KSTEPS = (V * V * 3 + 31) / 32;
+    f2::pack_policy_fragments<<<1, 256, 0, s>>>(p.pol_w, p.A, NW, KSTEPS);
+    const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
+    count_launch();
   }
   switch (p.A) {
     case 1: return launch_one<1, V, 1, true, 2, true>(p, s, n_steps);

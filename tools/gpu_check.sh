@@ -163,3 +163,9 @@ if [[ " $what " == *" policy "* ]]; then
   timeout 300 python tools/policy_probe.py 2>&1 | tee gpurun_out/policy_probe.log
   timeout 300 python tools/train_linear_q.py 150 16384 2>&1 | tee gpurun_out/train_linear_q.log
 fi
+if [[ " $what " == *" ncupolicy "* ]]; then
+  # one full capture of the K-steps-per-launch kernel with the policy hand-off (launch 7 of the probe = the first timed closed-loop rollout)
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:fused2_kernel -s 7 -c 1 -f -o gpurun_out/prof_policy \
+      python tools/policy_probe.py > gpurun_out/ncu_policy.log 2>&1; echo "ncupolicy exit $?"
+  ls -la gpurun_out/*.ncu-rep
+fi
