@@ -561,30 +561,35 @@ def main():
                                     "note": "closed-loop rollout (mg_rollout_policy): step t+1 plays the actions an int8 linear policy (7 actions, epsilon 0.1) chose from "
                                             "step t's observations, evaluated on the observation tile inside the rollout kernel; every step's obs / rewards / done / actions written"}
 
-        # ---- env kwargs off the specialised shape (general fused kernel / step kernel + observe kernel): parity-tested, here timed ----
-        feats = {}
         from marlgrid_b200.agents import GridAgentInterface
 
-        for name, akw, ekw in (("hide_item_types=['Goal']", {"hide_item_types": ["Goal"]}, {}), ("ghost_mode=False", {}, {"ghost_mode": False}),
-                               ("respawn=True", {}, {"respawn": True}), ("see_through_walls=True", {"see_through_walls": True}, {})):
-            try:
+        # ---- env kwargs off the specialised shape (general fused kernel / step kernel + observe kernel): parity-tested, here timed ----
+        feats, local_ms, local_launches = {}, [], []
+        feat_cases = (("hide_item_types=['Goal']", {"hide_item_types": ["Goal"]}, {}), ("ghost_mode=False", {}, {"ghost_mode": False}),
+                      ("respawn=True", {}, {"respawn": True}), ("see_through_walls=True", {"see_through_walls": True}, {}))
+        for name, akw, ekw in feat_cases:
+            try:  # (no collective inside the try: a rank that failed alone must not leave the others waiting)
                 fe = envs.ClutteredMultiGrid(agents=[GridAgentInterface(color=c, view_size=7, view_tile_size=8, **akw) for c in ("red", "blue", "purple")],
                                              grid_size=15, clutter_density=0.15, num_envs=B, obs_mode="encoded", seed=1337, env_offset=rank * B, device=dev, **ekw)
                 fe.reset()
                 fe.rollout(actions[:20])
+                torch.cuda.synchronize()
                 l0 = L.mg_launch_count()
-                barrier()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
                 fe.rollout(actions[:100])
                 fe.rollout(actions[:100])
                 e1.record()
-                barrier()
-                f_ms = max_over_ranks([e0.elapsed_time(e1) / 200])[0]
-                feats[name] = {"value": world * B / (f_ms * 1e-3), "ms_per_step": f_ms, "launches_per_step": (L.mg_launch_count() - l0) / 200.0}
+                torch.cuda.synchronize()
+                local_ms.append(e0.elapsed_time(e1) / 200)
+                local_launches.append((L.mg_launch_count() - l0) / 200.0)
                 del fe
             except Exception as ex:  # noqa: BLE001 -- informational section: report, do not fail the bench line
-                feats[name] = {"error": repr(ex)}
+                local_ms.append(float("nan"))
+                local_launches.append(repr(ex))
+        barrier()
+        for (name, _, _), f_ms, nl in zip(feat_cases, max_over_ranks(local_ms), local_launches):
+            feats[name] = {"value": world * B / (f_ms * 1e-3), "ms_per_step": f_ms, "launches_per_step": nl} if f_ms == f_ms else {"error": str(nl)}
         extras["feature_paths"] = dict(feats, note="cfg3 with one env kwarg changed, 200 warm steps enqueued from C on one family (compare `warm`)")
 
         # ---- the same warm steps through the Python surface, env.step(actions) called in a Python loop -------------------

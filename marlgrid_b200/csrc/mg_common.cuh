@@ -70,6 +70,7 @@ struct KP {
   int pol_n;                   // number of actions the policy chooses from (1..7)
   uint32_t pol_eps;            // exploration probability * 2^32
   unsigned long long pol_seed;
+  int f2_prefetch;             // specialised fused kernel: L2 prefetch of a CTA's first tile ahead of the grid dependency (launch_one sets it)
   double* prestige;            // MgState.prestige [B][A] or nullptr
   uint32_t prestige_mask, prestige_neg;  // agents coloured 'prestige' / with allow_negative_prestige
   double pbeta[MG_MAX_AGENTS], pscale[MG_MAX_AGENTS];

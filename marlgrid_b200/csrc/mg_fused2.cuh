@@ -708,6 +708,23 @@ __global__ void __launch_bounds__(32 * A, ctas_per_sm<OBS, V, A, NST>()) fused2_
   }
   // programmatic dependent launch: this grid may have been started while the previous kernel of the stream was still
   // draining (its launch latency and this prologue overlap that tail); nothing before this line touches global memory
+  // While this CTA waits for the previous kernel of the stream, its first tile's inputs can already travel from HBM to L2: a
+  // prefetch reads nothing into the CTA, so it cannot observe stale data -- whatever the previous kernel still writes lands in
+  // L2, the point of coherence, and the real loads below are issued after the dependency is resolved.  (A family that is
+  // stepped back to back finds its state in L2 anyway; this is for batches / round-robin families larger than L2.)
+  auto prefetch_tile = [&](int tile) {
+    if (lane != 0) return;
+    const long long e0 = (long long)tile * ENVS_PER_CTA;
+    const int nv = (int)min((long long)ENVS_PER_CTA, p.B - e0);
+    auto prefetch_l2 = [](const void* src, uint32_t bytes) { asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory"); };
+    if (a == 0) prefetch_l2(p.cellbits + e0 * BITS_WORDS, (uint32_t)(ENVS_PER_CTA * BITS_WORDS * 4));
+    if (a == 1 % A) prefetch_l2(p.agents + e0 * A * 16, (uint32_t)nv * (A * 16u));
+    if (a == 2 % A) {
+      prefetch_l2(p.envrec + e0 * 4, (uint32_t)nv * 16u);
+      if (nv == ENVS_PER_CTA) prefetch_l2(p.actions + e0 * A, (uint32_t)(ENVS_PER_CTA * A * 4));
+    }
+  };
+  if (!KS && OBS == 1 && p.f2_prefetch && (int)blockIdx.x < n_tiles) prefetch_tile((int)blockIdx.x);  // (OBS 2 is bound by its 38 KB of pixels per env: measured slightly worse with it)
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if ((int)blockIdx.x < n_tiles) issue_load((int)blockIdx.x, 0);
@@ -750,6 +767,8 @@ __global__ void __launch_bounds__(32 * A, ctas_per_sm<OBS, V, A, NST>()) fused2_
   int action = MG_A_DONE;
   if ((KS || !full) && mine) action = KS ? __ldcg(act_g + env * A + a) : act_g[env * A + a];  // (KS: the policy hand-off below may have written it a step ago)
   if (!KS || step == 0) mbar_wait(s_bar + stage, KS ? 0u : (uint32_t)((it / NST) & 1));
+  // single input stage: the next tile's inputs cannot be loaded before this tile has drained -- but they can come as far as L2
+  if (!KS && OBS == 1 && NST == 1 && p.f2_prefetch && next_tile < n_tiles) prefetch_tile(next_tile);
   if (!KS && full) action = s_act[lane * A + a];
 
   // ---- warp 0: the step's agent order, base.py:514-516 -- one Philox block per env ----
@@ -1219,7 +1238,10 @@ static int launch_one(const KP& p, cudaStream_t s, int n_steps = 1) {
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  const cudaError_t e = cudaLaunchKernelEx(&cfg, k, p, (int)tiles, n_steps);
+  KP q = p;
+  static const int prefetch = getenv("MG_F2_PREFETCH") ? atoi(getenv("MG_F2_PREFETCH")) : 1;  // MG_F2_PREFETCH=0: experiments
+  q.f2_prefetch = prefetch;
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, k, q, (int)tiles, n_steps);
   count_launch();
   return (int)e;
 }

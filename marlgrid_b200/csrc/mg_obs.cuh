@@ -292,23 +292,39 @@ __device__ __forceinline__ void prestige_colour(const KP& p, int q, double prest
 // queue -- or nothing.  The replacement is a bare agent: no blending with the object underneath, no "own tile on top"
 // (render_tile base.py:282-293 looks at the replaced object's own, empty, `agents`).  Rarely used, so written as a plain
 // loop over the view cells that follows the reference cell by cell; the fast paths never come here.
-template <int OBS, int V>
+template <int OBS, int V, bool BITS>
 __device__ __noinline__ void obs_view_hidden(const KP& p, const ObsSmem<V>& o, int view, int a, long long env, const uint32_t* __restrict__ rec,
                                              const uint8_t* __restrict__ tp, const ViewGeom& g, const PackedView& pv, int orient) {
   constexpr int VV = V * V;
   const int A = p.A, S = p.S, W = p.W, H = p.H, per_kind = 1 + 4 * A;
   const uint32_t w0 = rec[a * 4];
   bool bad = false;
+  unsigned long long agent_cells = 0ull;  // view cells some placed agent stands on (bit 8 vb + va): only those need the queue scan
+  for (int q = 0; q < A; ++q) {
+    const uint32_t v0 = rec[q * 4];
+    int va, vb;
+    if (((v0 >> 24) & MG_AF_PLACED) && world_to_view<V>(g, (int)(v0 & 0xFFu), (int)((v0 >> 8) & 0xFFu), va, vb)) agent_cells |= 1ull << (8 * vb + va);
+  }
   for (int vb = 0; vb < V; ++vb)
     for (int va = 0; va < V; ++va) {
       const bool vis = pv.visible(va, vb);
+      const bool has_agent = ((agent_cells >> (8 * vb + va)) & 1ull) != 0ull;
+      if (BITS && (!vis || (!pv.nonempty(va, vb) && !has_agent))) {  // nothing to decide: invisible, or an empty cell without agents
+        if (OBS == 2) o.tile[view * VV + vb * V + va] = vis ? (uint8_t)0 : (uint8_t)p.n_tiles;
+        continue;
+      }
       const int u = g.flip ? V - 1 - vb : vb, v = g.rev ? V - 1 - va : va;
       const int wx = g.topX + (g.vertical ? v : u), wy = g.topY + (g.vertical ? u : v);
       int type = 0, colour = 0, state = 0, head = -1, second = -1;
       if (vis && (unsigned)wx < (unsigned)W && (unsigned)wy < (unsigned)H) {
         const int idx = wx * H + wy;
-        type = tp[idx]; colour = tp[S + idx]; state = tp[2 * S + idx];
+        // bit-plane worlds: the masks answer for empty cells and canonical walls; only the few other objects are read from
+        // the byte planes (global memory on this path)
+        if (BITS && !pv.nonempty(va, vb)) type = MG_T_EMPTY;
+        else if (BITS && ((((vb < 4 ? pv.cw_lo : pv.cw_hi) >> (8 * (vb & 3) + va)) & 1u) != 0)) { type = MG_T_WALL; colour = MG_C_WORST; state = 0; }
+        else { type = tp[idx]; colour = tp[S + idx]; state = tp[2 * S + idx]; }
         uint32_t hs = 0, ss = 0;
+        if (has_agent)
         for (int q = 0; q < A; ++q) {  // the cell's queue: placed agents in stamp order
           const uint32_t v0 = rec[q * 4];
           if (!((v0 >> 24) & MG_AF_PLACED) || (int)(v0 & 0xFFu) != wx || (int)((v0 >> 8) & 0xFFu) != wy) continue;
@@ -391,7 +407,7 @@ __device__ __forceinline__ void obs_view(const KP& p, const ObsSmem<V>& o, int v
   const ViewGeom g = view_geom(px, py, dir, V, p.vo, p.W, p.H);
   const PackedView pv = view_masks<V, BITS>(p, tp, bits, g);
   if (p.hide != 0u) {  // hide_item_types: the cell-by-cell variant (reads the byte planes)
-    obs_view_hidden<OBS, V>(p, o, view, a, env, rec, tp, g, pv, orient);
+    obs_view_hidden<OBS, V, BITS>(p, o, view, a, env, rec, tp, g, pv, orient);
     return;
   }
   if (OBS == 1) {

@@ -169,3 +169,7 @@ if [[ " $what " == *" ncupolicy "* ]]; then
       python tools/policy_probe.py > gpurun_out/ncu_policy.log 2>&1; echo "ncupolicy exit $?"
   ls -la gpurun_out/*.ncu-rep
 fi
+if [[ " $what " == *" features "* ]]; then
+  timeout 300 python -m pytest tests -m gpu -x -q -k "hide or golden or traj" > gpurun_out/tests_features.log 2>&1; echo "feature tests exit $?"; tail -2 gpurun_out/tests_features.log
+  timeout 300 python tools/feature_probe.py 2>&1 | tee gpurun_out/feature_probe.log
+fi
