@@ -294,7 +294,11 @@ __device__ __forceinline__ void prestige_colour(const KP& p, int q, double prest
 // loop over the view cells that follows the reference cell by cell; the fast paths never come here.
 template <int OBS, int V, bool BITS>
 __device__ __noinline__ void obs_view_hidden(const KP& p, const ObsSmem<V>& o, int view, int a, long long env, const uint32_t* __restrict__ rec,
-                                             const uint8_t* __restrict__ tp, const ViewGeom& g, const PackedView& pv, int orient) {
+                                             const uint8_t* __restrict__ tp, const ViewGeom& g_in, const PackedView& pv_in, int orient) {
+  // private copies: the byte stores below may alias anything the references point to, and every mask would be reloaded from
+  // the caller's stack frame after each of them
+  const ViewGeom g = g_in;
+  const PackedView pv = pv_in;
   constexpr int VV = V * V;
   const int A = p.A, S = p.S, W = p.W, H = p.H, per_kind = 1 + 4 * A;
   const uint32_t w0 = rec[a * 4];
