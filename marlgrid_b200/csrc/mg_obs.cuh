@@ -374,6 +374,71 @@ __device__ __noinline__ void obs_view_hidden(const KP& p, const ObsSmem<V>& o, i
   if (OBS == 2 && bad) atomicOr(reinterpret_cast<unsigned int*>(p.envrec) + env * 4 + 3, (unsigned int)MG_ERR_RENDER << 16);
 }
 
+// hide_item_types for encoded observations of bit-plane worlds, on the masks (same rules as obs_view_hidden above, base.py:441-449):
+// a hidden static object leaves its cell to the head of the agents standing on it (whatever that agent's type says: the cell is
+// replaced once); a head agent other than the observer is replaced by the second of its queue when agents are hidden.
+template <int V, bool HEADS>
+__device__ __forceinline__ void obs_view_hidden_masks(const KP& p, const ObsSmem<V>& o, int view, int a, const uint32_t* __restrict__ rec,
+                                                      const uint8_t* __restrict__ tp, const uint32_t* __restrict__ bits, const ViewGeom& g,
+                                                      const PackedView& pv, const uint8_t* __restrict__ heads, uint32_t headmask) {
+  const int A = p.A, S = p.S;
+  uint8_t* out = o.out + view * (V * V * 3);
+  const bool hide_agents = ((p.hide >> MG_T_AGENT) & 1u) != 0u;
+  uint32_t ne_lo = pv.ne_lo, ne_hi = pv.ne_hi;  // cells that still show a static object after hiding
+  if ((p.hide >> MG_T_WALL) & 1u) { ne_lo &= ~pv.cw_lo; ne_hi &= ~pv.cw_hi; }
+  else {
+    encode_walls<V, 0>(pv.vis_lo & pv.cw_lo, out);
+    if (V > 4) encode_walls<V, 4>(pv.vis_hi & pv.cw_hi, out);
+  }
+  uint32_t g_lo = pv.vis_lo & pv.ne_lo & ~pv.cw_lo, g_hi = pv.vis_hi & pv.ne_hi & ~pv.cw_hi;  // visible objects that are not canonical walls
+#pragma unroll
+  for (int k = 0; k < OBJ_SLOTS; ++k) {
+    const uint32_t e = bits[(OBJ_WORD0 + k) * BS];
+    int va, vb;
+    if (!(e >> 31) || !world_to_view<V>(g, (int)(e & 15u), (int)((e >> 4) & 15u), va, vb)) continue;
+    const uint32_t bit = 1u << (8 * (vb & 3) + va);
+    if (vb < 4) { if (!(g_lo & bit)) continue; g_lo &= ~bit; } else { if (!(g_hi & bit)) continue; g_hi &= ~bit; }
+    if ((p.hide >> ((e >> 8) & 15u)) & 1u) { if (vb < 4) ne_lo &= ~bit; else ne_hi &= ~bit; continue; }
+    uint8_t* oo = out + va * (V * 3) + vb * 3;
+    oo[0] = (uint8_t)((e >> 8) & 15u); oo[1] = (uint8_t)((e >> 12) & 15u); oo[2] = (uint8_t)((e >> 16) & 255u);
+  }
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {  // objects that did not fit the list: from the byte planes
+    uint32_t m = half ? g_hi : g_lo;
+    while (m) {
+      const int bitn = __ffs(m) - 1;
+      m &= m - 1;
+      const int va = bitn & 7, vb = (bitn >> 3) + 4 * half;
+      const uint8_t* cp = tp + pv.row0 + vb * pv.ustep + va * pv.vstep;
+      const uint32_t type = cp[0];
+      if ((p.hide >> type) & 1u) { if (half) ne_hi &= ~(1u << bitn); else ne_lo &= ~(1u << bitn); continue; }
+      uint8_t* oo = out + va * (V * 3) + vb * 3;
+      oo[0] = (uint8_t)type; oo[1] = cp[S]; oo[2] = cp[2 * S];
+    }
+  }
+  for (int q = 0; q < A; ++q) {  // queue heads: the cell's object where no static object shows
+    const uint32_t v0 = rec[q * 4];
+    if (HEADS ? !heads[q] : !((headmask >> q) & 1u)) continue;
+    int va, vb;
+    if (!world_to_view<V>(g, (int)(v0 & 0xFFu), (int)((v0 >> 8) & 0xFFu), va, vb)) continue;
+    const uint32_t bit = 1u << (8 * (vb & 3) + va);
+    if (!pv.visible(va, vb) || ((vb < 4 ? ne_lo : ne_hi) & bit)) continue;
+    int show = q;
+    if (hide_agents && q != a && !pv.nonempty(va, vb)) {  // an agent as the cell's object, hidden: the second of its queue, or nothing
+      show = -1;
+      uint32_t best = 0xFFFFFFFFu;
+      for (int r = 0; r < A; ++r) {
+        const uint32_t u0 = rec[r * 4];
+        if (r == q || !((u0 >> 24) & MG_AF_PLACED) || ((u0 ^ v0) & 0xFFFFu) != 0u) continue;
+        if (rec[r * 4 + 2] < best) { best = rec[r * 4 + 2]; show = r; }
+      }
+      if (show < 0) continue;
+    }
+    uint8_t* oo = out + va * (V * 3) + vb * 3;
+    oo[0] = MG_T_AGENT; oo[1] = p.agent_color[show]; oo[2] = (uint8_t)((rec[show * 4] >> 16) & 3u);
+  }
+}
+
 // one agent view: gen_obs_grid + encode / tile ids.  rec = the env's agent records [q*4 + w] in shared memory,
 // tp = the env's byte planes (global memory on the bit-plane path, shared memory on the byte path)
 template <int OBS, int V, bool BITS, bool HEADS = false>
@@ -410,8 +475,12 @@ __device__ __forceinline__ void obs_view(const KP& p, const ObsSmem<V>& o, int v
   if (!active) return;
   const ViewGeom g = view_geom(px, py, dir, V, p.vo, p.W, p.H);
   const PackedView pv = view_masks<V, BITS>(p, tp, bits, g);
-  if (p.hide != 0u) {  // hide_item_types: the cell-by-cell variant (reads the byte planes)
-    obs_view_hidden<OBS, V, BITS>(p, o, view, a, env, rec, tp, g, pv, orient);
+  if (p.hide != 0u) {
+    if (OBS == 1 && BITS) {  // hide_item_types on the mask path: the same rules as obs_view_hidden, whole rows at a time
+      obs_view_hidden_masks<V, HEADS>(p, o, view, a, rec, tp, bits, g, pv, heads, headmask);
+      return;
+    }
+    obs_view_hidden<OBS, V, BITS>(p, o, view, a, env, rec, tp, g, pv, orient);  // the cell-by-cell variant
     return;
   }
   if (OBS == 1) {

@@ -617,3 +617,33 @@ def test_linear_q_trainer_closes_the_loop_on_the_device():
     assert all(np.isfinite(r) for r in rates)
     best = max(np.mean(rates[i: i + 10]) for i in range(10, 51))  # (TD(0) on a linear model is not monotone: best later window)
     assert best > 1.5 * np.mean(rates[:5]), f"reward rate did not improve: {np.mean(rates[:5]):.5f} -> best window {best:.5f}"
+
+
+@pytest.mark.parametrize("hidden", [["Wall"], ["Goal"], ["Agent"], ["Goal", "Agent"], ["Wall", "Agent", "Key", "Door"]])
+def test_hide_item_types_lockstep_vs_oracle(oracle, hidden, step_impl):
+    """hide_item_types (agents.py:30, base.py:441-449) in a crowded world -- stacked agents on goals and on each other, keys and
+    doors in view -- in lock step with the oracle: the mask variant of the encoded observe (general fused kernel, bit-plane
+    worlds) and the cell-by-cell variant (observe kernel) must both follow the reference's replace-once rule."""
+    from marlgrid_b200.config import make_config
+    from marlgrid_b200.objects import hide_mask
+
+    B, T = 600, 130
+    cfg = make_config(9, 9, ["red", "blue", "purple", "orange"], n_clutter=6, max_steps=40, hide_types=hide_mask(hidden))
+    env = _env(cfg, B, seed=31, env_offset=77)
+    ob = oracle.OracleBatch(cfg, B, seed=31, env_offset=77, threads=8)
+    env.reset()
+    ob.reset()
+    for w in (env.planes, ob.planes()):  # a key and a closed door in every world (objects beyond the generators')
+        w[:, 0, 3, 4], w[:, 1, 3, 4], w[:, 2, 3, 4] = 9, 3, 0
+        w[:, 0, 5, 2], w[:, 1, 5, 2], w[:, 2, 5, 2] = 11, 2, 1
+    env.sync_derived()
+    assert np.array_equal(env.observe().cpu().numpy(), ob.obs_encode())
+    rng = np.random.RandomState(5)
+    for t in range(T):
+        act = rng.randint(0, 3, size=(B, 4)).astype(np.int32)  # left / right / forward: the planes stay as edited
+        act[rng.rand(B, 4) < 0.5] = 2
+        obs, rew, done, _ = env.step(torch.from_numpy(act).cuda())
+        o2, r2, d2 = ob.step(act, autoreset=True, with_obs=True)  # (the edited objects live until the first reset, step 40)
+        assert np.array_equal(obs.cpu().numpy(), o2), f"step {t}: obs differ at {np.argwhere(obs.cpu().numpy() != o2)[:3]}"
+        assert np.array_equal(rew.cpu().numpy().view(np.uint64), r2.view(np.uint64)) and np.array_equal(done.cpu().numpy(), d2.astype(bool)), f"step {t}"
+    assert len(np.unique(o2[..., 0])) >= 3
