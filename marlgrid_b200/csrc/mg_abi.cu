@@ -115,23 +115,26 @@ static int g_pregen_auto = 1;           // 0: mg_step* do not launch the backgro
 static cudaEvent_t g_mid_event = nullptr;  // profiling hook: recorded between the two launches of a step
 
 // env.step: one fused launch when eligible; else the step kernel (incl. auto-reset), then the observation
+// The background world generator (mg_pregen.cu): one pass on the low-priority side stream, concurrent with the NEXT steps.  It
+// starts once the work enqueued on `s` so far has finished (an event edge): the host may be a thousand launches ahead of the
+// device, and a pass that ran when it was enqueued would look at the family long before the steps it is meant to follow.
+// Nothing ever waits for the pass.
+static int pregen_pass_after(const KP& p, cudaStream_t s) {
+  cudaStream_t ps = pregen_stream();
+  cudaEvent_t ev = pregen_event();
+  if (ps == nullptr || ev == nullptr) return 0;
+  MG_CUDA(cudaEventRecord(ev, s));
+  MG_CUDA(cudaStreamWaitEvent(ps, ev, 0));
+  return launch_pregen(p, ps);
+}
+
 static int launch_step_obs(const KP& p, int obs, cudaStream_t s) {
   if (obs != 0 && !g_force_two_kernels && fused_eligible(p)) {
     if (!g_force_general_fused) {  // specialised kernel for the common shapes (mg_fused2.cu); MG_E_UNSUPPORTED = not one of them
       const int e2 = launch_fused2(p, obs, s);
       if (e2 == 0 && p.pregen != nullptr && p.autoreset && g_pregen_auto && pregen_due(p.pregen)) {
-        // the background world generator (mg_pregen.cu): one pass on the low-priority side stream, concurrent with the NEXT
-        // steps.  It starts once this step has finished (an event edge): the host may be a thousand launches ahead of the
-        // device, and a pass that ran when it was enqueued would look at the family long before the steps it is meant to
-        // follow.  Nothing ever waits for the pass.
-        cudaStream_t ps = pregen_stream();
-        cudaEvent_t ev = pregen_event();
-        if (ps != nullptr && ev != nullptr) {
-          MG_CUDA(cudaEventRecord(ev, s));
-          MG_CUDA(cudaStreamWaitEvent(ps, ev, 0));
-          const int e3 = launch_pregen(p, ps);
-          if (e3) return e3;
-        }
+        const int e3 = pregen_pass_after(p, s);
+        if (e3) return e3;
       }
       if (e2 != MG_E_UNSUPPORTED) return e2;
     }
@@ -175,6 +178,15 @@ static int rollout_step_by_step(const MgConfig* cfg, const MgState* st, const KP
   }
   if (scratch) cudaFreeAsync(scratch, s);
   return e;
+}
+
+// A K-steps-per-launch rollout consumes pre-generated worlds like K single steps do (each env's slot holds its NEXT world: one
+// reset per env and launch is served, further ones are generated in the kernel), so a generator pass follows every launch of
+// eight steps or more; shorter launches count towards the per-family period like single steps.
+static int rollout_pregen_pass(const KP& p, int64_t n_steps, cudaStream_t s) {
+  if (p.pregen == nullptr || !p.autoreset || !g_pregen_auto) return 0;
+  if (n_steps < PREGEN_EVERY && !pregen_due(p.pregen)) return 0;
+  return pregen_pass_after(p, s);
 }
 
 extern "C" {
@@ -324,6 +336,7 @@ int mg_rollout_persistent(const MgConfig* cfg, const MgState* st, const int32_t*
   p.actions = actions; p.rewards = rewards; p.done = done; p.obs = obs; p.autoreset = autoreset;
   if (!g_force_two_kernels && !g_force_general_fused) {
     e = launch_fused2_rollout(p, (int)n_steps, (cudaStream_t)stream);  // ONE launch, the tiles' state stays in shared memory
+    if (e == 0) return rollout_pregen_pass(p, n_steps, (cudaStream_t)stream);
     if (e != MG_E_UNSUPPORTED) return e;
   }
   return rollout_step_by_step(cfg, st, p, n_steps, false, (cudaStream_t)stream);  // shapes / batch sizes outside the persistent kernel's reach
@@ -342,6 +355,7 @@ int mg_rollout_policy(const MgConfig* cfg, const MgState* st, const MgLinearPoli
   p.pol_w = reinterpret_cast<const int32_t*>(pol->weights); p.pol_b = pol->bias; p.pol_n = pol->n_actions; p.pol_eps = pol->epsilon; p.pol_seed = pol->seed;
   if (!g_force_two_kernels && !g_force_general_fused) {
     e = launch_fused2_rollout(p, (int)n_steps, (cudaStream_t)stream);  // ONE launch: state and policy hand-off stay on the SMs
+    if (e == 0) return rollout_pregen_pass(p, n_steps, (cudaStream_t)stream);
     if (e != MG_E_UNSUPPORTED) return e;
   }
   return rollout_step_by_step(cfg, st, p, n_steps, true, (cudaStream_t)stream);  // a step launch + a policy launch per step

@@ -92,8 +92,12 @@ class LinearPolicy:
         b = rng.randint(-1000, 1000, size=(n_agents, n_actions)).astype(np.int32)
         return cls(w, b, epsilon=epsilon, seed=seed, view_size=view_size)
 
+    def invalidate(self):
+        """Call after changing `weights` / `bias` in place: the packed device copies are rebuilt on the next use."""
+        self._dev = {}
+
     def device_struct(self, device):
-        """(MgLinearPolicy, keep-alive tensors) with the packed weights on `device`."""
+        """(MgLinearPolicy, keep-alive tensors) with the packed weights on `device` (uploaded on first use per device)."""
         import torch
 
         key = str(device)
