@@ -24,6 +24,8 @@ UNITS = {
     "mg_pregen.cu": ["mg_world.cuh"],
     "mg_fused2_enc7.cu": ["mg_env.cuh", "mg_world.cuh", "mg_fused2.cuh"],
     "mg_fused2_enc5.cu": ["mg_env.cuh", "mg_world.cuh", "mg_fused2.cuh"],
+    "mg_fused2_enc7h.cu": ["mg_env.cuh", "mg_world.cuh", "mg_fused2.cuh"],
+    "mg_fused2_enc5h.cu": ["mg_env.cuh", "mg_world.cuh", "mg_fused2.cuh"],
     "mg_fused2_rgb7.cu": ["mg_env.cuh", "mg_world.cuh", "mg_fused2.cuh"],
     "mg_fused2_rgb5.cu": ["mg_env.cuh", "mg_world.cuh", "mg_fused2.cuh"],
 }

@@ -648,7 +648,7 @@ constexpr int ctas_per_sm() {  // shared-memory / thread limited residency the r
 // KS (K steps per launch, mg_rollout_persistent): the CTA keeps the state of its (at most NST) tiles in its input stages and
 // plays n_steps steps on them -- actions[step], observations[step], rewards[step], done[step] are per-step slices --, so that
 // an open-loop rollout costs one launch, no state reloads and no grid-wide dependency between steps.
-template <int OBS, int V, int A, bool VO0, int NST, bool KS = false>
+template <int OBS, int V, int A, bool VO0, int NST, bool KS = false, bool HIDE = false>
 __global__ void __launch_bounds__(32 * A, ctas_per_sm<OBS, V, A, NST>()) fused2_kernel(const __grid_constant__ KP p, const int n_tiles, const int n_steps) {
   using namespace f2;
   using SM = Smem<OBS, V, A, NST>;
@@ -985,8 +985,12 @@ __global__ void __launch_bounds__(32 * A, ctas_per_sm<OBS, V, A, NST>()) fused2_
       }
       // rows packed one byte each (view cell (a, b) = bit 8*b + a): visible canonical walls / other objects / free cells
       const uint64_t m64 = pack_rows8<V>(M), op64 = pack_rows8<V>(OP), ot64 = pack_rows8<V>(OT);
-      const uint64_t wall64 = m64 & op64 & ~ot64, free64 = m64 & ~(op64 | ot64);
-      uint64_t oth64 = m64 & ot64;
+      // HIDE (hide_item_types, agents.py:30, base.py:441-449; encoded observations): hidden canonical walls are not drawn, a hidden
+      // object leaves its cell (hid64) to the head of the agents standing on it, and a head agent other than the observer gives
+      // way to the second of its queue when agents are hidden -- every cell is replaced once, after the line of sight was
+      // computed on the real grid (the same rules as obs_view_hidden_masks, mg_obs.cuh)
+      const uint64_t wall64 = (HIDE && ((p.hide >> MG_T_WALL) & 1u)) ? 0ull : (m64 & op64 & ~ot64), free64 = m64 & ~(op64 | ot64);
+      uint64_t oth64 = m64 & ot64, hid64 = 0ull;
       if (OBS == 1) {
       {  // visible canonical walls (8, 9, 0): constants at compile-time offsets of the staging tile.  The two constants
            // come in through a kernel parameter and the stores are spelled out, or ptxas re-materialises 8 / 9 around every store
@@ -1029,6 +1033,7 @@ __global__ void __launch_bounds__(32 * A, ctas_per_sm<OBS, V, A, NST>()) fused2_
           const uint64_t m = 1ull << (8 * vb + va);
           if (!(oth64 & m)) continue;
           oth64 &= ~m;
+          if (HIDE && ((p.hide >> ((e >> 8) & 15u)) & 1u)) { hid64 |= m; continue; }
           if (OBS == 1) {
             uint8_t* oo = out + va * (V * 3) + vb * 3;
             oo[0] = (uint8_t)((e >> 8) & 15u); oo[1] = (uint8_t)((e >> 12) & 15u); oo[2] = (uint8_t)((e >> 16) & 255u);
@@ -1045,6 +1050,7 @@ __global__ void __launch_bounds__(32 * A, ctas_per_sm<OBS, V, A, NST>()) fused2_
           const int uu = flip ? V - 1 - vb : vb, vv = rev ? V - 1 - va : va;
           const int wx = topX + (vertical ? vv : uu), wy = topY + (vertical ? uu : vv);
           const uint8_t* cp = p.grid + env * 3 * S + wx * H + wy;
+          if (HIDE && ((p.hide >> cp[0]) & 1u)) { hid64 |= 1ull << bit; continue; }
           if (OBS == 1) {
             uint8_t* oo = out + va * (V * 3) + vb * 3;
             oo[0] = cp[0]; oo[1] = cp[S]; oo[2] = cp[2 * S];
@@ -1061,10 +1067,21 @@ __global__ void __launch_bounds__(32 * A, ctas_per_sm<OBS, V, A, NST>()) fused2_
         const int vb = bu + su * (int)__byte_perm(q0[q], 0u, sel_u), va = bv + sv * (int)__byte_perm(q0[q], 0u, sel_v);
         const bool in_view = (unsigned)vb < (unsigned)V && (unsigned)va < (unsigned)V;
         if (OBS == 1) {
-          const bool draw = in_view && ((heads >> q) & 1u) && ((free64 >> ((8 * vb + va) & 63)) & 1ull);
+          const bool draw = in_view && ((heads >> q) & 1u) && (((HIDE ? (free64 | hid64) : free64) >> ((8 * vb + va) & 63)) & 1ull);
           if (draw) {
-            uint8_t* oo = out + va * (V * 3) + vb * 3;
-            oo[0] = MG_T_AGENT; oo[1] = p.agent_color[q]; oo[2] = (uint8_t)((q0[q] >> 16) & 3u);
+            uint32_t colour = p.agent_color[q], qdir = (q0[q] >> 16) & 3u;
+            bool show = true;
+            if (HIDE && ((p.hide >> MG_T_AGENT) & 1u) && q != a && !((hid64 >> ((8 * vb + va) & 63)) & 1ull)) {
+              show = false;  // an agent as its cell's object, hidden: the second of the queue on that cell, or nothing
+              uint32_t best = 0xFFFFFFFFu;
+#pragma unroll
+              for (int r = 0; r < A; ++r)
+                if (r != q && (ck[r] ^ ck[q]) < 0x10000u && ck[r] < best) { best = ck[r]; colour = p.agent_color[r]; qdir = (q0[r] >> 16) & 3u; show = true; }
+            }
+            if (show) {
+              uint8_t* oo = out + va * (V * 3) + vb * 3;
+              oo[0] = MG_T_AGENT; oo[1] = (uint8_t)colour; oo[2] = (uint8_t)qdir;
+            }
           }
         } else {
           // the cell's tile gets an agent on top: the observer itself if it stands there, else the queue head
@@ -1201,10 +1218,10 @@ static inline bool pdl_enabled() {  // MG_F2_PDL=0 turns programmatic dependent 
   return v != 0;
 }
 
-template <int OBS, int V, int A, bool VO0, int NST, bool KS = false>
+template <int OBS, int V, int A, bool VO0, int NST, bool KS = false, bool HIDE = false>
 static int launch_one(const KP& p, cudaStream_t s, int n_steps = 1) {
   using SM = f2::Smem<OBS, V, A, NST>;
-  auto k = fused2_kernel<OBS, V, A, VO0, NST, KS>;
+  auto k = fused2_kernel<OBS, V, A, VO0, NST, KS, HIDE>;
   const int smem_bytes = SM::TOTAL + (OBS == 2 ? (p.n_tiles + 1) * 192 : 0);  // OBS 2: + the tile atlas and the shadow tile
   if (smem_bytes > 227 * 1024) return MG_E_UNSUPPORTED;
   static int resident[64] = {0}, configured_smem[64] = {0};  // CTAs per SM of this instantiation, per device
@@ -1264,6 +1281,24 @@ static int launch_a(const KP& p, cudaStream_t s) {
     case 6: return launch_one<OBS, V, 6, VO0, NS>(p, s);
   }
   return MG_E_UNSUPPORTED;
+}
+
+// hide_item_types (encoded observations): the HIDE instantiations, in translation units of their own (mg_fused2_enc{7,5}h.cu)
+template <int V, bool VO0>
+static int launch_a_hide(const KP& p, cudaStream_t s) {
+  switch (p.A) {
+    case 1: return launch_one<1, V, 1, VO0, 2, false, true>(p, s);
+    case 2: return launch_one<1, V, 2, VO0, 2, false, true>(p, s);
+    case 3: return launch_one<1, V, 3, VO0, 2, false, true>(p, s);
+    case 4: return launch_one<1, V, 4, VO0, 2, false, true>(p, s);
+    case 5: return launch_one<1, V, 5, VO0, 2, false, true>(p, s);
+    case 6: return launch_one<1, V, 6, VO0, 2, false, true>(p, s);
+  }
+  return MG_E_UNSUPPORTED;
+}
+template <int V>
+int launch_fused2_hide(const KP& p, cudaStream_t s) {
+  return p.vo == 0 ? launch_a_hide<V, true>(p, s) : launch_a_hide<V, false>(p, s);
 }
 
 // one (OBS, V) family per translation unit (mg_fused2_*.cu), so that the instantiations compile in parallel
