@@ -647,3 +647,30 @@ def test_hide_item_types_lockstep_vs_oracle(oracle, hidden, step_impl):
         assert np.array_equal(obs.cpu().numpy(), o2), f"step {t}: obs differ at {np.argwhere(obs.cpu().numpy() != o2)[:3]}"
         assert np.array_equal(rew.cpu().numpy().view(np.uint64), r2.view(np.uint64)) and np.array_equal(done.cpu().numpy(), d2.astype(bool)), f"step {t}"
     assert len(np.unique(o2[..., 0])) >= 3
+
+
+def test_respawn_lockstep_vs_oracle(oracle, step_impl):
+    """respawn=True (base.py:626-644) with many goal hits: an agent that finishes is placed anew inside the step.  The specialised
+    kernel replays such envs with the sequential code; every output and the whole state against the oracle, every step."""
+    from marlgrid_b200.config import make_config
+
+    B, T = 1500, 230
+    cfg = make_config(9, 9, ["red", "blue", "purple", "orange"], respawn=True, max_steps=100)
+    env = _env(cfg, B, seed=9, env_offset=3)
+    ob = oracle.OracleBatch(cfg, B, seed=9, env_offset=3, threads=8)
+    env.reset()
+    ob.reset()
+    rng = np.random.RandomState(2)
+    hits = 0
+    for t in range(T):
+        act = rng.randint(0, 7, size=(B, 4)).astype(np.int32)
+        act[rng.rand(B, 4) < 0.6] = 2
+        obs, rew, done, _ = env.step(torch.from_numpy(act).cuda())
+        o2, r2, d2 = ob.step(act, autoreset=True, with_obs=True)
+        assert np.array_equal(obs.cpu().numpy(), o2), f"step {t}: obs"
+        assert np.array_equal(rew.cpu().numpy().view(np.uint64), r2.view(np.uint64)), f"step {t}: reward bits"
+        assert np.array_equal(done.cpu().numpy(), d2.astype(bool)), f"step {t}: done"
+        hits += int((r2 > 0).sum())
+        if t % 16 == 0 or t == T - 1:
+            _state_equal(env, ob, f"step {t}")
+    assert hits > 500 and int(env.episode.min().item()) >= 3 and int(env.err.max().item()) == 0
