@@ -254,7 +254,10 @@ int mg_rollout_persistent(const MgConfig* cfg, const MgState* st, const int32_t*
  *   bias    : device, int32 [A][8]
  *   actions : int32 [n_steps][B][A]: row 0 = the first step's actions, given by the caller; rows 1.. are WRITTEN (the actions
  *             played at every step, for the learner); rewards / done / obs: per-step slices as for mg_rollout_persistent
- * Batches that are not a multiple of 16 envs (per-step slices off the 16-byte grid) take the launch-per-step route. */
+ * Batches that are not a multiple of 16 envs (per-step slices off the 16-byte grid) take the launch-per-step route.
+ * The one-launch route evaluates the layer on the tensor cores (mma.sync m16n8k32, u8 x s8 -> s32: exact) from a per-process table
+ * of weight fragments that a small kernel fills, stream-ordered, before the launch: rollouts with DIFFERENT policies must not be
+ * in flight on two streams of one process at the same time (the same policy, or one stream, is fine). */
 typedef struct MgLinearPolicy {
   const int8_t* weights;
   const int32_t* bias;
