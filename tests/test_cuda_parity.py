@@ -674,3 +674,29 @@ def test_respawn_lockstep_vs_oracle(oracle, step_impl):
         if t % 16 == 0 or t == T - 1:
             _state_equal(env, ob, f"step {t}")
     assert hits > 500 and int(env.episode.min().item()) >= 3 and int(env.err.max().item()) == 0
+
+
+def test_reference_readme_loop_with_torch_learners():
+    """The training loop of the reference's README.md:29-57, verbatim, with torch learners (LinearQLearner) as the env's agents:
+    IndependentLearners.action_step / save_step / episode() on device tensors, one TD update per learner at the end of an episode."""
+    from marlgrid_b200 import IndependentLearners, envs
+    from marlgrid_b200.learners import LinearQLearner
+
+    agents = IndependentLearners(*[LinearQLearner(view_size=7, device="cuda", seed=k, color=c, epsilon=0.3) for k, c in enumerate(("red", "blue"))])
+    env = envs.ClutteredMultiGrid(agents, grid_size=15, n_clutter=10, obs_mode="encoded", max_steps=40)
+    w_before = [l.W.detach().clone() for l in agents]
+    for i_episode in range(3):
+        obs_array = env.reset()
+        with agents.episode():
+            episode_over = False
+            steps = 0
+            while not episode_over:
+                action_array = agents.action_step(obs_array)
+                next_obs_array, reward_array, done, _ = env.step(action_array)
+                agents.save_step(obs_array, action_array, next_obs_array.clone(), reward_array.clone(), done.clone())
+                obs_array = next_obs_array.clone()
+                episode_over = done
+                steps += 1
+            assert steps == 40 or bool(done)
+    assert all(l.updates == 3 and l.buffer == [] for l in agents)
+    assert all(not torch.equal(w, l.W.detach()) for w, l in zip(w_before, agents))
