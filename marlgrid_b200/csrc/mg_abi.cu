@@ -129,7 +129,7 @@ static int pregen_pass_after(const KP& p, cudaStream_t s) {
 }
 
 static int launch_step_obs(const KP& p, int obs, cudaStream_t s) {
-  if (obs != 0 && !g_force_two_kernels && fused_eligible(p)) {
+  if (obs != 0 && !g_force_two_kernels && fused2_eligible(p)) {
     if (!g_force_general_fused) {  // specialised kernel for the common shapes (mg_fused2.cu); MG_E_UNSUPPORTED = not one of them
       const int e2 = launch_fused2(p, obs, s);
       if (e2 == 0 && p.pregen != nullptr && p.autoreset && g_pregen_auto && pregen_due(p.pregen)) {
@@ -138,7 +138,7 @@ static int launch_step_obs(const KP& p, int obs, cudaStream_t s) {
       }
       if (e2 != MG_E_UNSUPPORTED) return e2;
     }
-    return launch_fused(p, obs, s);
+    if (fused_eligible(p)) return launch_fused(p, obs, s);
   }
   int e = launch_env(0, p, s);
   if (e) return e;

@@ -147,6 +147,7 @@ int launch_los(const uint8_t* transparent, uint8_t* mask, long long n, int view_
 int launch_obs(const KP& p, int obs, cudaStream_t s);           // mg_obs_kernels.cu: obs 1 encoded / 2 rgb
 int launch_fused(const KP& p, int obs, cudaStream_t s);         // mg_fused_kernels.cu: general one-launch step+observe
 bool fused_eligible(const KP& p);
+bool fused2_eligible(const KP& p);
 constexpr int MG_E_UNSUPPORTED = -100;                          // internal: the specialised kernel has no instantiation for this shape
 int launch_fused2(const KP& p, int obs, cudaStream_t s);        // mg_fused2.cu: specialised (compile-time A, V) one-launch step+observe
 int launch_fused2_rollout(const KP& p, int n_steps, cudaStream_t s);

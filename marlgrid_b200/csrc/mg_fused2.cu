@@ -26,7 +26,7 @@ static bool standard_worlds(const KP& p) { return p.scenario == 0 && p.ax0 == 0 
 static bool al16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; }
 
 int launch_fused2(const KP& p, int obs, cudaStream_t s) {
-  if (!fused_eligible(p) || p.A > 6 || (p.V != 7 && p.V != 5)) return MG_E_UNSUPPORTED;
+  if (!fused2_eligible(p) || p.A > 6 || (p.V != 7 && p.V != 5)) return MG_E_UNSUPPORTED;
   if (p.hide != 0u && obs != 1) return MG_E_UNSUPPORTED;  // hide_item_types with RGB observations: general kernels
   if (!standard_worlds(p)) return MG_E_UNSUPPORTED;  // spawn boxes / other generators: the general kernels' sequential reset
   if (!al16(p.actions) || !al16(p.rewards) || !al16(p.done) || !al16(p.obs)) return MG_E_UNSUPPORTED;  // bulk copies need 16-byte alignment

@@ -855,7 +855,13 @@ __global__ void __launch_bounds__(32 * A, ctas_per_sm<OBS, V, A, NST>()) fused2_
                 }
                 reward = __dadd_rn(0.0, rwd);  // step_rewards[agent_no] += rwd (base.py:580): 0.0 + (-0.0) is +0.0
               }
-              if (ftype == MG_T_LAVA || ftype == MG_T_GOAL) w0 = (w0 | ((uint32_t)MG_AF_DONE << 24)) & ~((uint32_t)MG_AF_ACTIVE << 24);  // base.py:584-585,646
+              if (ftype == MG_T_LAVA || ftype == MG_T_GOAL) {
+                w0 = (w0 | ((uint32_t)MG_AF_DONE << 24)) & ~((uint32_t)MG_AF_ACTIVE << 24);  // base.py:584-585,646
+                // respawn=True (base.py:626-644): the agent leaves its queue and is placed anew inside this step -- order-dependent:
+                // the env is replayed by the sequential code.  (With respawn no agent ever starts a step `done`; worlds without
+                // Goal / Lava -- the goal-cycle scenario of examples/human_player.py:35-55 -- never come here.)
+                if (p.flags & MG_F_RESPAWN) slow = true;
+              }
             }
           } else if (action == MG_A_PICKUP) {  // takes effect only on a pickable object with empty hands (base.py:590-597)
             slow = ((PICKUP_MASK >> ftype) & 1u) && (w1 & 0xFFu) == 0u;

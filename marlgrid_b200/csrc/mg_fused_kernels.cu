@@ -296,13 +296,17 @@ static int launch_fused_v(const KP& p, cudaStream_t s) {
 }
 
 // the one-launch path exists for bit-plane worlds in ghost mode without respawn / spawn delay (every registered env)
-bool fused_eligible(const KP& p) {
-  if (p.cellbits == nullptr || !(p.flags & MG_F_GHOST) || (p.flags & MG_F_RESPAWN)) return false;
+// the specialised kernel (mg_fused2.cuh): bit-plane worlds in ghost mode without spawn delays; respawn is fine (an env in which
+// an agent finishes is replayed sequentially)
+bool fused2_eligible(const KP& p) {
+  if (p.cellbits == nullptr || !(p.flags & MG_F_GHOST)) return false;
   if (p.prestige != nullptr) return false;  // the running reward of 'prestige' agents is kept by the per-env step kernel only
   for (int a = 0; a < p.A; ++a)
     if (p.spawn_delay[a] != 0) return false;
   return true;
 }
+// the general fused kernel: the same without respawn
+bool fused_eligible(const KP& p) { return fused2_eligible(p) && !(p.flags & MG_F_RESPAWN); }
 
 int launch_fused(const KP& p, int obs, cudaStream_t s) {
   if (obs == 1) return launch_fused_v<1, 0>(p, s);

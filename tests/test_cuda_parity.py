@@ -700,3 +700,33 @@ def test_reference_readme_loop_with_torch_learners():
             assert steps == 40 or bool(done)
     assert all(l.updates == 3 and l.buffer == [] for l in agents)
     assert all(not torch.equal(w, l.W.detach()) for w, l in zip(w_before, agents))
+
+
+def test_human_player_config_lockstep_vs_oracle(oracle, step_impl):
+    """The reference's only example config (examples/human_player.py:33-55: ClutteredGoalCycleEnv 13x13, respawn=True, no reward
+    decay, 3 bonus tiles, penalty -1.5, view_offset 1), encoded observations, three agents: with no Goal / Lava in the world a
+    respawn never happens, and the specialised kernel takes the config; in lock step with the oracle."""
+    from marlgrid_b200 import envs
+    from marlgrid_b200.agents import GridAgentInterface
+
+    B, T = 1200, 270
+    agents = [GridAgentInterface(view_size=7, view_offset=1, view_tile_size=11, see_through_walls=False, color=c) for c in ("red", "blue", "green")]
+    env = envs.ClutteredGoalCycleEnv(agents=agents, grid_size=13, max_steps=250, clutter_density=0.15, respawn=True, ghost_mode=True, reward_decay=False,
+                                     n_bonus_tiles=3, initial_reward=True, penalty=-1.5, num_envs=B, obs_mode="encoded", seed=17, env_offset=1000)
+    ob = oracle.OracleBatch(env.cfg, B, seed=17, env_offset=1000, threads=8)
+    env.reset()
+    ob.reset()
+    rng = np.random.RandomState(3)
+    bonus = 0
+    for t in range(T):
+        act = rng.randint(0, 7, size=(B, 3)).astype(np.int32)
+        act[rng.rand(B, 3) < 0.5] = 2
+        obs, rew, done, _ = env.step(torch.from_numpy(act).cuda())
+        o2, r2, d2 = ob.step(act, autoreset=True, with_obs=True)
+        assert np.array_equal(obs.cpu().numpy(), o2), f"step {t}: obs"
+        assert np.array_equal(rew.cpu().numpy().view(np.uint64), r2.view(np.uint64)), f"step {t}: reward bits"
+        assert np.array_equal(done.cpu().numpy(), d2.astype(bool)), f"step {t}: done"
+        bonus += int((r2 != 0).sum())
+        if t % 32 == 0 or t == T - 1:
+            _state_equal(env, ob, f"step {t}")
+    assert bonus > 1000 and int(env.episode.min().item()) >= 2 and int(env.err.max().item()) == 0

@@ -14,8 +14,14 @@ L = None
 for name, akw, ekw in (("(specialised kernel)", {}, {}), ("(general fused kernel, forced)", {}, {}), ("(step + observe kernels, forced)", {}, {}), ("hide_item_types=['Goal']", {"hide_item_types": ["Goal"]}, {}), ("hide_item_types=['Wall']", {"hide_item_types": ["Wall"]}, {}),
                        ("hide_item_types=['Agent']", {"hide_item_types": ["Agent"]}, {}), ("ghost_mode=False", {}, {"ghost_mode": False}),
                        ("respawn=True", {}, {"respawn": True}), ("see_through_walls=True", {"see_through_walls": True}, {}),
-                       ("spawn_delay=5", {"spawn_delay": 5}, {}), ("view_offset=1", {"view_offset": 1}, {})):
-    env = envs.ClutteredMultiGrid(agents=[GridAgentInterface(color=c, view_size=7, view_tile_size=8, **akw) for c in ("red", "blue", "purple")],
+                       ("spawn_delay=5", {"spawn_delay": 5}, {}), ("view_offset=1", {"view_offset": 1}, {}),
+                       ("human_player.py config (goal cycle 13x13, respawn=True, 3 agents)", {}, {})):
+    if name.startswith("human_player"):
+        env = envs.ClutteredGoalCycleEnv(agents=[GridAgentInterface(color=c, view_size=7, view_offset=1, view_tile_size=11) for c in ("red", "blue", "purple")],
+                                         grid_size=13, max_steps=250, clutter_density=0.15, respawn=True, reward_decay=False, n_bonus_tiles=3,
+                                         initial_reward=True, penalty=-1.5, num_envs=B, obs_mode="encoded", seed=1337)
+    else:
+      env = envs.ClutteredMultiGrid(agents=[GridAgentInterface(color=c, view_size=7, view_tile_size=8, **akw) for c in ("red", "blue", "purple")],
                                   grid_size=15, clutter_density=0.15, num_envs=B, obs_mode="encoded", seed=1337, **ekw)
     L = env._lib
     L.mg_debug_force_general_fused(1 if "general fused" in name else 0)
@@ -40,5 +46,5 @@ for name, akw, ekw in (("(specialised kernel)", {}, {}), ("(general fused kernel
     e1.record()
     torch.cuda.synchronize()
     us = 1e3 * e0.elapsed_time(e1) / 200
-    print(f"{name:28s} {us:8.2f} us per step  {B / us * 1e6:.3e} env-steps/s  {(L.mg_launch_count() - l0) / 200:.2f} launches per step   ({us_steady:.2f} us per step between the all-reset steps)", flush=True)
+    print(f"{name:34s} {us:8.2f} us per step  {B / us * 1e6:.3e} env-steps/s  {(L.mg_launch_count() - l0) / 200:.2f} launches per step   ({us_steady:.2f} us per step between the all-reset steps)", flush=True)
     del env
