@@ -378,3 +378,45 @@ def test_linear_q_learner_protocol_and_quantisation():
     greedy = torch.stack([l.q_values(obs[:, k]).argmax(-1) for k, l in enumerate(learners)], dim=1).numpy()
     got = policy_oracle.linear_policy_actions(obs.numpy(), pol.weights, pol.bias, 7, 0, 0, np.arange(64), np.zeros(64, np.int64))
     assert (got == greedy).mean() > 0.9  # (int8 rounding may flip near-ties)
+
+
+def test_linear_q_trainer_iteration_on_a_stand_in_env():
+    """LinearQTrainer.iterate (host logic): quantise -> rollout_policy -> one TD update per agent on the transitions
+    (obs[t], act[t+1], rew[t+1], obs[t+1], done[t+1]); checked on a stand-in env that records what it is asked for."""
+    import types
+
+    import torch
+
+    from marlgrid_b200.learners import LinearQLearner, LinearQTrainer
+
+    B, A, V = 32, 2, 5
+    calls = []
+
+    class StandIn:
+        num_envs, num_agents, device = B, A, "cpu"
+        cfg = types.SimpleNamespace(view_size=V)
+
+        def policy_act(self, pol):
+            calls.append(("act", pol.n_actions, pol.epsilon_u32))
+            return torch.zeros((B, A), dtype=torch.int32)
+
+        def rollout_policy(self, pol, first, n_steps, out=None):
+            calls.append(("rollout", n_steps, pol.weights.shape, pol.seed))
+            g = torch.Generator().manual_seed(len(calls))
+            obs, rew, done, act = out
+            obs.copy_(torch.randint(0, 14, obs.shape, generator=g, dtype=torch.uint8))
+            rew.copy_((torch.rand(rew.shape, generator=g) < 0.1).double())
+            done.copy_(torch.rand(done.shape, generator=g) < 0.05)
+            act.copy_(torch.randint(0, 7, act.shape, generator=g, dtype=torch.int32))
+            act[0] = first
+            return out
+
+    learners = [LinearQLearner(view_size=V, seed=k, color=c) for k, c in enumerate(("red", "blue"))]
+    tr = LinearQTrainer(StandIn(), learners, horizon=8, epsilon=0.25, seed=100)
+    w0 = [l.W.detach().clone() for l in learners]
+    s1 = tr.iterate()
+    s2 = tr.iterate()
+    assert [c[0] for c in calls] == ["act", "rollout", "act", "rollout", "act"]  # the first actions once, then every rollout continues the last
+    assert calls[1][1:] == (8, (A, 7, V * V * 3), 100) and calls[3][3] == 101 and calls[0][2] == 1 << 30
+    assert all(l.updates == 2 for l in learners) and all(not torch.equal(w, l.W.detach()) for w, l in zip(w0, learners))
+    assert set(s1) == {"reward_per_env_step", "loss", "episodes"} and len(s2["loss"]) == A and all(np.isfinite(s2["loss"]))
