@@ -255,6 +255,8 @@ INTERACTIVE = [
     dict(name="Empty8x8x3+keys/doors/balls", env_class="EmptyMultiGrid", agents=agents_cfg(3), grid_size=8, interactive=True, max_steps=150),
     dict(name="Empty7x7x4-noghost+objects", env_class="EmptyMultiGrid", agents=agents_cfg(4), grid_size=7, ghost_mode=False, interactive=True, max_steps=150),
     dict(name="Empty7x7x2+box (TypeError)", env_class="EmptyMultiGrid", agents=agents_cfg(2), grid_size=7, interactive=True, with_box=True, max_steps=150),
+    dict(name="Empty8x8x4+objects, hidden Wall/Agent/Key/Door", env_class="EmptyMultiGrid", agents=agents_cfg(4, hide_item_types=["Wall", "Agent", "Key", "Door"]), grid_size=8, interactive=True, max_steps=120),
+    dict(name="Empty6x6x4 crowded, hidden Agent", env_class="EmptyMultiGrid", agents=agents_cfg(4, hide_item_types=["Agent"]), grid_size=6, max_steps=60),
     dict(name="Empty6x6x2 bad action (ValueError)", env_class="EmptyMultiGrid", agents=agents_cfg(2), grid_size=6, n_actions=8, max_steps=30),
 ]
 
