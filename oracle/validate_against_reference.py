@@ -202,7 +202,7 @@ class LockStep:
 
 
 def agents_cfg(n, colors=("red", "blue", "purple", "orange", "olive", "pink"), **kw):
-    return [dict(color=colors[i % len(colors)], view_size=7, view_tile_size=8, **kw) for i in range(n)]
+    return [dict(color=colors[i % len(colors)], **{"view_size": 7, "view_tile_size": 8, **kw}) for i in range(n)]
 
 
 # added in round 2 (own RNG stream in gen_golden.py, so the older fixtures stay reproducible): agent_spawn_kwargs (base.py:346,
@@ -223,6 +223,8 @@ EXTRA = [
          agents=[dict(color="prestige", view_size=5, view_tile_size=8, allow_negative_prestige=True)]),
     dict(name="DoorKey8x8x2", env_class="DoorKeyEnv", agents=agents_cfg(2), grid_size=8, max_steps=120, interactive=True, no_inject=True),
     dict(name="DoorKey6x6x1", env_class="DoorKeyEnv", agents=agents_cfg(1), grid_size=6, max_steps=80, interactive=True, no_inject=True),
+    dict(name="human_player.py config x3 agents", env_class="ClutteredGoalCycleEnv", agents=agents_cfg(3, view_offset=1, view_tile_size=11), grid_size=13, max_steps=250, clutter_density=0.15,
+         respawn=True, ghost_mode=True, reward_decay=False, n_bonus_tiles=3, initial_reward=True, penalty=-1.5),  # examples/human_player.py:33-55 (encoded / RGB views)
 ]
 
 SCENARIOS = [
