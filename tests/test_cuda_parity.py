@@ -730,3 +730,11 @@ def test_human_player_config_lockstep_vs_oracle(oracle, step_impl):
         if t % 32 == 0 or t == T - 1:
             _state_equal(env, ob, f"step {t}")
     assert bonus > 1000 and int(env.episode.min().item()) >= 2 and int(env.err.max().item()) == 0
+
+
+def test_policy_rollout_other_agent_counts_and_view_sizes(oracle):
+    """tools/policy_shapes_check.py: the one-launch closed-loop route for A = 1 / view size 5, A = 4 / view size 7 and a batch that
+    is a multiple of 16 but not of 32 envs, against the CPU statement (the MMA fragment layout is generic in A and V)."""
+    import runpy
+
+    runpy.run_path(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "policy_shapes_check.py"), run_name="__main__")
